@@ -1,0 +1,42 @@
+"""gated_gcrnns_b200 — B200-native gated GCRNN recurrence behind the reference's module API.
+
+    import gated_gcrnns_b200 as gg
+    gg.install()                       # rebinds Utils.graphML.{LSIGF,GraphFilter,GraphAttentional,GGCRNNCell}
+    # ... the reference's Modules/architectures.py, train_rnn.py, train_rnn_quake.py now run on the CUDA path
+
+See DESIGN.md / INTEGRATION.md.  The C ABI is include/gcrnn_b200.h.
+"""
+from .functional import LSIGF, graph_attention_relu, gated_gcrnn, set_precision, get_precision, cell_param_slots
+from .modules import GraphFilter, GraphAttentional, GGCRNNCell
+from . import dist, graph, graphs
+from ._lib import GcrnnError, LIB_PATH
+
+__all__ = ['LSIGF', 'GraphFilter', 'GraphAttentional', 'GGCRNNCell', 'install', 'uninstall', 'set_precision',
+           'get_precision', 'dist', 'graph', 'graphs', 'GcrnnError']
+
+_PATCHED = ('LSIGF', 'GraphFilter', 'GraphAttentional', 'GGCRNNCell')
+_originals = {}
+
+
+def install(graphML_module=None):
+    """Rebind the four hot-path names on the reference's ``Utils.graphML`` module.
+
+    ``Modules/architectures.py`` looks them up as ``gml.<Name>`` at call time (architectures.py:6, :1521), so
+    nothing in the reference needs editing.  Everything else in ``Utils.graphML`` is left untouched."""
+    if graphML_module is None:
+        import Utils.graphML as graphML_module  # the reference must be importable (sys.path)
+    import sys
+    me = sys.modules[__name__]
+    for n in _PATCHED:
+        _originals.setdefault((id(graphML_module), n), getattr(graphML_module, n))
+        setattr(graphML_module, n, getattr(me, n))
+    return graphML_module
+
+
+def uninstall(graphML_module=None):
+    if graphML_module is None:
+        import Utils.graphML as graphML_module
+    for n in _PATCHED:
+        o = _originals.pop((id(graphML_module), n), None)
+        if o is not None:
+            setattr(graphML_module, n, o)

@@ -1,0 +1,233 @@
+// extern "C" surface of libgcrnn_b200.so (see include/gcrnn_b200.h).  Exceptions stop here.
+#include "common.cuh"
+#include <dlfcn.h>
+#include <cstring>
+
+namespace gcrnn {
+static thread_local char g_err[1024] = "";
+unsigned long long g_launches = 0;
+void set_last_error(const char* fmt, ...) {
+  va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof g_err, fmt, ap); va_end(ap);
+}
+gcrnn_graph* graph_create_csr(int N, int E, const int64_t* const* rowptr, const int32_t* const* colidx,
+                              const float* const* vals, int device);
+gcrnn_graph* graph_create_dense(int N, int E, const float* S, int keep_dense, int device);
+void graph_destroy(gcrnn_graph* g);
+}  // namespace gcrnn
+
+using namespace gcrnn;
+
+#define API_BEGIN try {
+#define API_END                                                                     \
+  } catch (const gcrnn::Error& e) { set_last_error("%s", e.what()); return e.code; } \
+    catch (const std::exception& e) { set_last_error("%s", e.what()); return -1; }   \
+    catch (...) { set_last_error("unknown error"); return -1; }                      \
+  return 0;
+
+extern "C" {
+
+int gcrnn_abi_version(void) { return GCRNN_ABI_VERSION; }
+const char* gcrnn_last_error(void) { return g_err; }
+uint64_t gcrnn_debug_launch_count(void) { return g_launches; }
+
+int gcrnn_graph_create_csr(gcrnn_graph** out, int32_t N, int32_t E, const int64_t* const* rowptr,
+                           const int32_t* const* colidx, const float* const* vals, int32_t device) {
+  API_BEGIN
+  GCRNN_CHECK(out && rowptr && colidx && vals, "null argument");
+  *out = graph_create_csr(N, E, rowptr, colidx, vals, device);
+  API_END
+}
+int gcrnn_graph_create_dense(gcrnn_graph** out, int32_t N, int32_t E, const float* S, int32_t keep_dense, int32_t device) {
+  API_BEGIN
+  GCRNN_CHECK(out && S, "null argument");
+  *out = graph_create_dense(N, E, S, keep_dense, device);
+  API_END
+}
+int gcrnn_graph_destroy(gcrnn_graph* g) {
+  API_BEGIN
+  graph_destroy(g);
+  API_END
+}
+int gcrnn_graph_info(const gcrnn_graph* g, int32_t* N, int32_t* E, int64_t* nnz, int64_t* nnz_att) {
+  API_BEGIN
+  GCRNN_CHECK(g, "null graph");
+  if (N) *N = g->N;
+  if (E) *E = g->E;
+  if (nnz) *nnz = g->nnz_total;
+  if (nnz_att) *nnz_att = g->nnz_att;
+  API_END
+}
+
+// ---- LSIGF -------------------------------------------------------------------------------------------
+size_t gcrnn_lsigf_workspace_bytes(const gcrnn_graph* g, int32_t F, int32_t K, int32_t G, int64_t B) {
+  try {
+    size_t f = lsigf_forward_f32(g, nullptr, nullptr, nullptr, nullptr, F, K, G, B, nullptr, 0, nullptr);
+    size_t b = lsigf_backward_f32(g, nullptr, nullptr, nullptr, (float*)1, (float*)1, (float*)1, F, K, G, B, nullptr, 0, nullptr);
+    return (f > b ? f : b) + 256;
+  } catch (const std::exception& e) { set_last_error("%s", e.what()); return 0; }
+}
+int gcrnn_lsigf_forward(const gcrnn_graph* g, const float* h, const float* bias, const float* x, float* y, int32_t F,
+                        int32_t K, int32_t G, int64_t B, void* ws, size_t wsb, void* stream) {
+  API_BEGIN
+  GCRNN_CHECK(g && h && x && y && ws, "null argument");
+  GCRNN_CHECK(F > 0 && K > 0 && G > 0 && B > 0, "bad sizes F=%d K=%d G=%d B=%lld", F, K, G, (long long)B);
+  CUDA_OK(cudaSetDevice(g->device));
+  lsigf_forward_f32(g, h, bias, x, y, F, K, G, B, ws, wsb, (cudaStream_t)stream);
+  API_END
+}
+int gcrnn_lsigf_backward(const gcrnn_graph* g, const float* h, const float* x, const float* dy, float* dx, float* dh,
+                         float* dbias, int32_t F, int32_t K, int32_t G, int64_t B, void* ws, size_t wsb, void* stream) {
+  API_BEGIN
+  GCRNN_CHECK(g && h && x && dy && ws, "null argument");
+  CUDA_OK(cudaSetDevice(g->device));
+  lsigf_backward_f32(g, h, x, dy, dx, dh, dbias, F, K, G, B, ws, wsb, (cudaStream_t)stream);
+  API_END
+}
+
+// ---- attention ---------------------------------------------------------------------------------------
+size_t gcrnn_gat_workspace_bytes(const gcrnn_graph* g, int32_t F, int32_t G, int64_t B) {
+  try {
+    return gat_backward_f32(g, nullptr, nullptr, nullptr, nullptr, (float*)1, nullptr, nullptr, F, G, B, nullptr, 0, nullptr) + 256;
+  } catch (const std::exception& e) { set_last_error("%s", e.what()); return 0; }
+}
+int gcrnn_gat_forward(const gcrnn_graph* g, const float* mixer, const float* weight, const float* x, float* y, int32_t F,
+                      int32_t G, int64_t B, void* ws, size_t wsb, void* stream) {
+  API_BEGIN
+  GCRNN_CHECK(g && mixer && weight && x && y && ws, "null argument");
+  CUDA_OK(cudaSetDevice(g->device));
+  gat_forward_f32(g, mixer, weight, x, y, F, G, B, ws, wsb, (cudaStream_t)stream);
+  API_END
+}
+int gcrnn_gat_backward(const gcrnn_graph* g, const float* mixer, const float* weight, const float* x, const float* dy,
+                       float* dx, float* dmixer, float* dweight, int32_t F, int32_t G, int64_t B, void* ws, size_t wsb,
+                       void* stream) {
+  API_BEGIN
+  GCRNN_CHECK(g && mixer && weight && x && dy && ws, "null argument");
+  CUDA_OK(cudaSetDevice(g->device));
+  gat_backward_f32(g, mixer, weight, x, dy, dx, dmixer, dweight, F, G, B, ws, wsb, (cudaStream_t)stream);
+  API_END
+}
+
+// ---- cell ----------------------------------------------------------------------------------------------
+int gcrnn_cell_create(gcrnn_cell** out, const gcrnn_cell_desc* d, const gcrnn_graph* g) {
+  API_BEGIN
+  GCRNN_CHECK(out && d && g, "null argument");
+  GCRNN_CHECK(d->G > 0 && d->F > 0 && d->Kin > 0 && d->Kst > 0, "bad cell sizes");
+  GCRNN_CHECK(d->E == g->E, "cell E=%d does not match graph E=%d", d->E, g->E);
+  GCRNN_CHECK(d->spatial_gating >= 0 && d->spatial_gating <= 2, "bad spatial_gating %d", d->spatial_gating);
+  if (d->precision == GCRNN_PREC_BF16_TC) {
+    GCRNN_CHECK(g->S_bf16 != nullptr, "tensor-core precision needs a graph created with keep_dense != 0");
+    GCRNN_CHECK(d->spatial_gating == GCRNN_SPATIAL_NONE, "tensor-core path supports time gating only; use fp32 for node/edge gating");
+  } else {
+    GCRNN_CHECK(d->precision == GCRNN_PREC_FP32, "unknown precision %d", d->precision);
+  }
+  auto* c = new gcrnn_cell();
+  c->d = *d; c->g = g;
+  *out = c;
+  API_END
+}
+int gcrnn_cell_destroy(gcrnn_cell* c) {
+  API_BEGIN
+  delete c;
+  API_END
+}
+int gcrnn_cell_workspace_bytes(const gcrnn_cell* c, int64_t B, int64_t T, int32_t need_input_grads, size_t* saved_bytes,
+                               size_t* fwd_bytes, size_t* bwd_bytes) {
+  API_BEGIN
+  GCRNN_CHECK(c, "null cell");
+  size_t su = 0, f, b;
+  float* flag = need_input_grads ? (float*)1 : nullptr;
+  if (c->d.precision == GCRNN_PREC_BF16_TC) {
+    f = cell_forward_tc(c, nullptr, nullptr, nullptr, nullptr, nullptr, 0, &su, nullptr, 0, B, T, nullptr);
+    b = cell_backward_tc(c, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr, flag, flag, nullptr, 0, B, T, nullptr);
+  } else {
+    f = cell_forward_f32(c, nullptr, nullptr, nullptr, nullptr, nullptr, 0, &su, nullptr, 0, B, T, nullptr);
+    b = cell_backward_f32(c, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr, flag, flag, nullptr, 0, B, T, nullptr);
+  }
+  if (saved_bytes) *saved_bytes = su + 256;
+  if (fwd_bytes) *fwd_bytes = f + 256;
+  if (bwd_bytes) *bwd_bytes = b + 256;
+  API_END
+}
+int gcrnn_cell_forward(gcrnn_cell* c, const gcrnn_cell_params* p, const float* X, const float* h0, float* H, void* saved,
+                       size_t savedb, void* ws, size_t wsb, int64_t B, int64_t T, void* stream) {
+  API_BEGIN
+  GCRNN_CHECK(c && p && X && h0 && H && ws && saved, "null argument");
+  CUDA_OK(cudaSetDevice(c->g->device));
+  if (c->d.precision == GCRNN_PREC_BF16_TC) cell_forward_tc(c, p, X, h0, H, saved, savedb, nullptr, ws, wsb, B, T, (cudaStream_t)stream);
+  else cell_forward_f32(c, p, X, h0, H, saved, savedb, nullptr, ws, wsb, B, T, (cudaStream_t)stream);
+  API_END
+}
+int gcrnn_cell_backward(gcrnn_cell* c, const gcrnn_cell_params* p, const float* X, const float* h0, const float* H,
+                        const float* dH, const void* saved, size_t savedb, const gcrnn_cell_params* grads, float* dX,
+                        float* dh0, void* ws, size_t wsb, int64_t B, int64_t T, void* stream) {
+  API_BEGIN
+  GCRNN_CHECK(c && p && X && h0 && H && dH && saved && grads && ws, "null argument");
+  CUDA_OK(cudaSetDevice(c->g->device));
+  if (c->d.precision == GCRNN_PREC_BF16_TC) cell_backward_tc(c, p, X, h0, H, dH, saved, savedb, grads, dX, dh0, ws, wsb, B, T, (cudaStream_t)stream);
+  else cell_backward_f32(c, p, X, h0, H, dH, saved, savedb, grads, dX, dh0, ws, wsb, B, T, (cudaStream_t)stream);
+  API_END
+}
+
+// ---- NCCL (resolved at run time so that the library shares the process's libnccl with torch) ------------
+typedef struct { char internal[128]; } nccl_uid;
+typedef void* nccl_comm_t;
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(nccl_uid*) = nullptr;
+  int (*CommInitRank)(nccl_comm_t*, int, nccl_uid, int) = nullptr;
+  int (*CommDestroy)(nccl_comm_t) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi& nccl() {
+  static NcclApi api;
+  if (!api.lib) {
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) { api.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (api.lib) break; }
+    if (!api.lib) throw gcrnn::Error(-5, std::string("cannot load libnccl: ") + dlerror());
+    api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(api.lib, "ncclGetUniqueId");
+    api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.lib, "ncclCommInitRank");
+    api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.lib, "ncclCommDestroy");
+    api.AllReduce = (decltype(api.AllReduce))dlsym(api.lib, "ncclAllReduce");
+    api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.lib, "ncclGetErrorString");
+    if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.AllReduce)
+      throw gcrnn::Error(-5, "libnccl is missing symbols");
+  }
+  return api;
+}
+#define NCCL_OK(expr) do { int _r = (expr); if (_r != 0) throw gcrnn::Error(-6, std::string(#expr ": ") + (nccl().GetErrorString ? nccl().GetErrorString(_r) : "nccl error")); } while (0)
+
+struct gcrnn_comm { nccl_comm_t comm; int rank, world, device; };
+
+int gcrnn_comm_unique_id(void* id128) {
+  API_BEGIN
+  GCRNN_CHECK(id128, "null argument");
+  nccl_uid id; NCCL_OK(nccl().GetUniqueId(&id)); memcpy(id128, &id, 128);
+  API_END
+}
+int gcrnn_comm_create(gcrnn_comm** out, const void* id128, int32_t rank, int32_t world, int32_t device) {
+  API_BEGIN
+  GCRNN_CHECK(out && id128, "null argument");
+  CUDA_OK(cudaSetDevice(device));
+  nccl_uid id; memcpy(&id, id128, 128);
+  auto* c = new gcrnn_comm{nullptr, rank, world, device};
+  int r = nccl().CommInitRank(&c->comm, world, id, rank);
+  if (r != 0) { delete c; NCCL_OK(r); }
+  *out = c;
+  API_END
+}
+int gcrnn_comm_destroy(gcrnn_comm* c) {
+  API_BEGIN
+  if (c) { nccl().CommDestroy(c->comm); delete c; }
+  API_END
+}
+int gcrnn_allreduce_sum(gcrnn_comm* c, float* bucket, int64_t count, void* stream) {
+  API_BEGIN
+  GCRNN_CHECK(c && bucket && count >= 0, "bad argument");
+  CUDA_OK(cudaSetDevice(c->device));
+  NCCL_OK(nccl().AllReduce(bucket, bucket, (size_t)count, /*ncclFloat32*/ 7, /*ncclSum*/ 0, c->comm, (cudaStream_t)stream));
+  API_END
+}
+
+}  // extern "C"

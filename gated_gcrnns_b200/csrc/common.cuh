@@ -1,0 +1,113 @@
+// Shared declarations of the gcrnn_b200 library (internal; the public surface is include/gcrnn_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdarg>
+#include <string>
+#include <vector>
+#include <stdexcept>
+#include "../../include/gcrnn_b200.h"
+
+namespace gcrnn {
+
+// ---- error handling: C++ exceptions never cross the ABI; api.cu converts them to codes ----------------
+void set_last_error(const char* fmt, ...);
+extern unsigned long long g_launches;   // kernels launched by this library (gcrnn_debug_launch_count)
+
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define GCRNN_CHECK(cond, ...)                                                   \
+  do { if (!(cond)) { char _b[512]; snprintf(_b, sizeof _b, __VA_ARGS__);        \
+       throw ::gcrnn::Error(-2, std::string(_b) + " [" #cond "]"); } } while (0)
+
+#define CUDA_OK(expr)                                                            \
+  do { cudaError_t _e = (expr); if (_e != cudaSuccess) {                         \
+       throw ::gcrnn::Error(-3, std::string(#expr ": ") + cudaGetErrorString(_e)); } } while (0)
+
+// ---- sparse operator on the device ------------------------------------------------------------------
+// "gather form": out[dst] = sum_{p in ptr[dst]..ptr[dst+1]} val[p] * in[idx[p]]
+struct Gather {
+  int64_t nnz = 0;
+  int* ptr = nullptr;   // [N+1]
+  int* idx = nullptr;   // [nnz]
+  float* val = nullptr; // [nnz]
+};
+
+}  // namespace gcrnn
+
+struct gcrnn_graph {
+  int N = 0, E = 0, device = 0;
+  int64_t nnz_total = 0;
+  std::vector<gcrnn::Gather> fwd;   // per e: CSC of S_e  (z @ S_e : gather sources i for each destination j)
+  std::vector<gcrnn::Gather> bwd;   // per e: CSR of S_e  (g @ S_e^T: gather j for each destination i)
+  // attention pattern of S' = S + I with |S'| > 1e-9 (E == 1 only), edges numbered in CSR (row i) order
+  int64_t nnz_att = 0;
+  int *att_rptr = nullptr, *att_col = nullptr;          // row i -> columns j
+  float* att_val = nullptr;                             // S'_ij
+  int *att_cptr = nullptr, *att_crow = nullptr, *att_ceid = nullptr;  // column j -> (row i, edge id)
+  int max_row_deg = 0;
+  // dense copies for the tensor-core path (E == 1): row-major [Npad, Npad] bf16, zero padded
+  int Npad = 0;
+  __nv_bfloat16* S_bf16 = nullptr;    // S    (K-major B operand of the backward shift  g @ S^T)
+  __nv_bfloat16* St_bf16 = nullptr;   // S^T  (K-major B operand of the forward shift   z @ S)
+  std::vector<void*> owned;           // every device allocation, for destroy
+};
+
+struct gcrnn_cell {
+  gcrnn_cell_desc d;
+  const gcrnn_graph* g = nullptr;
+};
+
+namespace gcrnn {
+
+// Bump allocator over a caller-provided workspace.  With base == nullptr it only counts, which is how the
+// *_workspace_bytes entry points are implemented (same code path as the real run).
+struct Arena {
+  char* base; size_t cap; size_t off = 0;
+  Arena(void* b, size_t c) : base((char*)b), cap(c) {}
+  bool dry() const { return base == nullptr; }
+  template <class T> T* get(size_t count) {
+    size_t bytes = (count * sizeof(T) + 255) & ~size_t(255);
+    size_t o = off; off += bytes;
+    if (!base) return nullptr;
+    if (off > cap) throw Error(-4, "workspace too small: need > " + std::to_string(off) + " bytes, have " + std::to_string(cap));
+    return (T*)(base + o);
+  }
+};
+
+// fp32 path (gcrnn_f32.cu)
+size_t lsigf_forward_f32(const gcrnn_graph* g, const float* h, const float* bias, const float* x, float* y,
+                         int F, int K, int G, int64_t B, void* ws, size_t wsb, cudaStream_t st);
+size_t lsigf_backward_f32(const gcrnn_graph* g, const float* h, const float* x, const float* dy, float* dx,
+                          float* dh, float* dbias, int F, int K, int G, int64_t B, void* ws, size_t wsb,
+                          cudaStream_t st);
+size_t gat_forward_f32(const gcrnn_graph* g, const float* mixer, const float* weight, const float* x, float* y,
+                       int F, int G, int64_t B, void* ws, size_t wsb, cudaStream_t st);
+size_t gat_backward_f32(const gcrnn_graph* g, const float* mixer, const float* weight, const float* x,
+                        const float* dy, float* dx, float* dmixer, float* dweight, int F, int G, int64_t B,
+                        void* ws, size_t wsb, cudaStream_t st);
+// returns scratch bytes used; *saved_used gets the bytes of `saved` used
+size_t cell_forward_f32(const gcrnn_cell* c, const gcrnn_cell_params* p, const float* X, const float* h0, float* H,
+                        void* saved, size_t savedb, size_t* saved_used, void* ws, size_t wsb, int64_t B, int64_t T,
+                        cudaStream_t st);
+size_t cell_backward_f32(const gcrnn_cell* c, const gcrnn_cell_params* p, const float* X, const float* h0,
+                         const float* H, const float* dH, const void* saved, size_t savedb,
+                         const gcrnn_cell_params* gr, float* dX, float* dh0, void* ws, size_t wsb, int64_t B,
+                         int64_t T, cudaStream_t st);
+
+// tensor-core path (gcrnn_tc.cu)
+size_t cell_forward_tc(const gcrnn_cell* c, const gcrnn_cell_params* p, const float* X, const float* h0, float* H,
+                       void* saved, size_t savedb, size_t* saved_used, void* ws, size_t wsb, int64_t B, int64_t T,
+                       cudaStream_t st);
+size_t cell_backward_tc(const gcrnn_cell* c, const gcrnn_cell_params* p, const float* X, const float* h0,
+                        const float* H, const float* dH, const void* saved, size_t savedb,
+                        const gcrnn_cell_params* gr, float* dX, float* dh0, void* ws, size_t wsb, int64_t B,
+                        int64_t T, cudaStream_t st);
+void tc_prepare_graph(gcrnn_graph* g, const float* S_host);
+
+}  // namespace gcrnn

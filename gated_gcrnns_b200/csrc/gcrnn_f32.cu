@@ -1,0 +1,581 @@
+// Host orchestration of the fp32 sparse exact path: LSIGF, graph attention and the gated GCRNN recurrence
+// with its hand-derived reverse-time backward.  Follows Utils/graphML.py:47-140 (LSIGF), :521-627 + :2084-2116
+// (attention), :2336-2428 (GGCRNNCell.forward); see DESIGN.md for the restructuring (gates hoisted out of the
+// recurrence because they depend on (x_t, h0) only; recompute-from-H backward).
+#include "kernels_f32.cuh"
+
+namespace gcrnn {
+using namespace k;
+
+namespace {
+
+struct Ctx {
+  const gcrnn_graph* g;
+  cudaStream_t st;
+  bool dry;
+};
+
+constexpr int TPB = 256;
+
+void zero(const Ctx& c, void* p, size_t bytes) {
+  if (c.dry || bytes == 0) return;
+  CUDA_OK(cudaMemsetAsync(p, 0, bytes, c.st));
+}
+void copy(const Ctx& c, void* dst, const void* src, size_t bytes) {
+  if (c.dry || bytes == 0) return;
+  CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, c.st));
+}
+void check_launch() { ++g_launches; CUDA_OK(cudaGetLastError()); }
+
+void transpose(const Ctx& c, const float* in, const float* add, float* out, int A, int Bd, long long R1, long long R2,
+               long long is1, long long is2, long long os1, long long os2) {
+  if (c.dry) return;
+  dim3 grid((Bd + 31) / 32, (A + 31) / 32, (unsigned)std::min<long long>(R1 * R2, 32768));
+  transpose_k<<<grid, dim3(32, 8), 0, c.st>>>(in, add, out, A, Bd, R1, R2, is1, is2, os1, os2);
+  check_launch();
+}
+
+void spmm(const Ctx& c, const Gather& op, const float* in, const float* add, float* out, int C, long long R) {
+  if (c.dry) return;
+  const int N = c.g->N;
+  const bool v4 = (C % 4 == 0) && ((uintptr_t)in % 16 == 0) && ((uintptr_t)out % 16 == 0) && (!add || (uintptr_t)add % 16 == 0);
+  if (v4) spmm_k<4><<<grid1d(R * N * (C / 4), TPB), TPB, 0, c.st>>>(op.ptr, op.idx, op.val, in, add, out, N, C, R);
+  else    spmm_k<1><<<grid1d(R * N * C, TPB), TPB, 0, c.st>>>(op.ptr, op.idx, op.val, in, add, out, N, C, R);
+  check_launch();
+}
+
+size_t smem_opt_in(const void* fn, size_t bytes) {
+  if (bytes > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  GCRNN_CHECK(bytes <= 200 * 1024, "filter taps do not fit in shared memory (%zu bytes)", bytes);
+  return bytes;
+}
+
+void contract_fwd(const Ctx& c, const Slabs& z, const float* W, const float* bias, float bias_scale, const float* addb,
+                  long long RB, float* y, long long R, int F, int S, int G) {
+  if (c.dry) return;
+  const int N = c.g->N;
+  const size_t sm = (size_t)S * G * F * sizeof(float);
+  if (addb) {
+    smem_opt_in((const void*)contract_fwd_k<1>, sm);
+    contract_fwd_k<1><<<grid1d(R * N * F, TPB), TPB, sm, c.st>>>(z, W, bias, bias_scale, addb, RB, y, R, N, F, S, G);
+  } else {
+    smem_opt_in((const void*)contract_fwd_k<0>, sm);
+    contract_fwd_k<0><<<grid1d(R * N * F, TPB), TPB, sm, c.st>>>(z, W, bias, bias_scale, nullptr, 1, y, R, N, F, S, G);
+  }
+  check_launch();
+}
+
+void contract_bwd_data(const Ctx& c, const SlabsMut& dz, const float* W, const float* dy, long long RN, int F, int S, int G,
+                       int accumulate) {
+  if (c.dry) return;
+  const size_t sm = smem_opt_in((const void*)contract_bwd_data_k, (size_t)S * G * F * sizeof(float));
+  contract_bwd_data_k<<<grid1d(RN * S * G, TPB), TPB, sm, c.st>>>(dz, W, dy, RN, F, S, G, accumulate);
+  check_launch();
+}
+
+void contract_wgrad(const Ctx& c, const Slabs& z, const float* dy, float* dW, long long RN, int F, int S, int G) {
+  if (c.dry || !dW) return;
+  const size_t sm = smem_opt_in((const void*)contract_wgrad_k, (size_t)WG_ITEMS * (F + S * G) * sizeof(float));
+  const int outs = F * S * G;
+  dim3 grid((unsigned)std::min<long long>((RN + WG_ITEMS - 1) / WG_ITEMS, 148 * 4), (outs + TPB * WG_OPT - 1) / (TPB * WG_OPT));
+  contract_wgrad_k<<<grid, TPB, sm, c.st>>>(z, dy, dW, RN, F, S, G);
+  check_launch();
+}
+
+void colsum(const Ctx& c, const float* in, float* out, long long rows, int C, float scale = 1.f) {
+  if (c.dry || !out) return;
+  colsum_k<<<(unsigned)std::min<long long>((rows + 63) / 64, 148 * 8), 64, 0, c.st>>>(in, out, rows, C, scale);
+  check_launch();
+}
+
+void add_inplace(const Ctx& c, float* dst, const float* src, long long n) {
+  if (c.dry) return;
+  add_inplace_k<<<grid1d(n, TPB), TPB, 0, c.st>>>(dst, src, n);
+  check_launch();
+}
+
+// Slab s = e*K + k of a K-tap chain: (e, 0) is the base signal itself, (e, k>=1) lives in `chain`.
+Slabs chain_slabs(const float* base, const float* chain, int E, int K, long long slab_elems, long long base_off = 0) {
+  GCRNN_CHECK(E * K <= MAX_SLABS, "E*K = %d exceeds the supported %d filter slabs", E * K, MAX_SLABS);
+  Slabs s{};
+  for (int e = 0; e < E; ++e)
+    for (int kk = 0; kk < K; ++kk)
+      s.p[e * K + kk] = (kk == 0) ? base + base_off
+                                  : (chain ? chain + (long long)(e * (K - 1) + (kk - 1)) * slab_elems + base_off : nullptr);
+  return s;
+}
+SlabsMut mut_slabs(float* buf, int S, long long slab_elems, long long off = 0) {
+  GCRNN_CHECK(S <= MAX_SLABS, "too many slabs (%d)", S);
+  SlabsMut s{};
+  for (int i = 0; i < S; ++i) s.p[i] = buf ? buf + (long long)i * slab_elems + off : nullptr;
+  return s;
+}
+
+// z_{e,k} = z_{e,k-1} @ S_e, k = 1..K-1, over R samples of C channels (node-major)
+void shift_chain(const Ctx& c, const float* base, float* chain, int E, int K, int C, long long R) {
+  const long long slab = R * c.g->N * C;
+  for (int e = 0; e < E; ++e) {
+    const float* prev = base;
+    for (int kk = 1; kk < K; ++kk) {
+      float* out = chain ? chain + (long long)(e * (K - 1) + (kk - 1)) * slab : nullptr;
+      spmm(c, c.g->fwd[e], prev, nullptr, out, C, R);
+      prev = out;
+    }
+  }
+}
+
+// Given dz_{e,k} (E*K distinct buffers): g_{e,k-1} = dz_{e,k-1} + g_{e,k} @ S_e^T (in place), dst (+)= sum_e g_{e,0}
+void reverse_chain(const Ctx& c, float* dz, int E, int K, int C, long long R, float* dst, bool accumulate) {
+  const long long slab = R * c.g->N * C;
+  for (int e = 0; e < E; ++e)
+    for (int kk = K - 1; kk >= 1; --kk) {
+      float* hi = dz ? dz + (long long)(e * K + kk) * slab : nullptr;
+      float* lo = dz ? dz + (long long)(e * K + kk - 1) * slab : nullptr;
+      spmm(c, c.g->bwd[e], hi, lo, lo, C, R);
+    }
+  for (int e = 0; e < E; ++e) {
+    float* g0 = dz ? dz + (long long)(e * K) * slab : nullptr;
+    if (e == 0 && !accumulate) copy(c, dst, g0, slab * sizeof(float));
+    else add_inplace(c, dst, g0, slab);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// attention on node-major signals
+// ---------------------------------------------------------------------------------------------------
+struct GatBufs {
+  float* wu = nullptr;     // [R][N][F]
+  float2* rc = nullptr;    // [R][N]
+  float* alpha = nullptr;  // [R][nnz_att]
+  void alloc(Arena& a, long long R, int N, int F, long long nnz) {
+    wu = a.get<float>(R * N * F); rc = a.get<float2>(R * N); alpha = a.get<float>(R * nnz);
+  }
+};
+
+void gat_fwd_nm(const Ctx& c, const float* mixer, const float* weight, const float* un, float* yn, const GatBufs& b,
+                int F, int G, long long R) {
+  const gcrnn_graph* g = c.g;
+  const int N = g->N;
+  Slabs z{}; z.p[0] = un;
+  contract_fwd(c, z, weight, nullptr, 0.f, nullptr, 1, b.wu, R, F, 1, G);              // Wu  (graphML.py:586-588)
+  if (c.dry) return;
+  gat_scores_k<<<grid1d(R * N, TPB), TPB, 0, c.st>>>(b.wu, mixer, b.rc, R * N, F);      // :591-594
+  check_launch();
+  gat_softmax_k<<<grid1d(R * N, 128), 128, 0, c.st>>>(g->att_rptr, g->att_col, b.rc, b.alpha, R, N, g->nnz_att);  // :597-622
+  check_launch();
+  gat_aggregate_k<<<grid1d(R * N * F, TPB), TPB, 0, c.st>>>(g->att_cptr, g->att_crow, g->att_ceid, g->att_val, b.alpha,
+                                                            b.wu, yn, R, N, F, g->nnz_att);  // :625 + relu :2101
+  check_launch();
+}
+
+struct GatBwdBufs {
+  float *dyr = nullptr, *ds = nullptr, *dc = nullptr, *dwu = nullptr; float2* drc = nullptr;
+  void alloc(Arena& a, long long R, int N, int F, long long nnz) {
+    dyr = a.get<float>(R * N * F); ds = a.get<float>(R * nnz); dc = a.get<float>(R * N);
+    dwu = a.get<float>(R * N * F); drc = a.get<float2>(R * N);
+  }
+};
+
+// dyn: gradient w.r.t. the relu output yn.  Writes dun (may be null), accumulates dmixer / dweight (may be null).
+void gat_bwd_nm(const Ctx& c, const float* mixer, const float* weight, const float* un, const float* yn, const float* dyn,
+                const GatBufs& b, const GatBwdBufs& w, float* dun, float* dmixer, float* dweight, int F, int G, long long R) {
+  const gcrnn_graph* g = c.g;
+  const int N = g->N;
+  if (!c.dry) {
+    relu_mask_k<<<grid1d(R * N * F, TPB), TPB, 0, c.st>>>(dyn, yn, w.dyr, R * N * F);
+    check_launch();
+    gat_bwd_rows_k<<<grid1d(R * N, 128), 128, 0, c.st>>>(g->att_rptr, g->att_col, g->att_val, b.rc, b.alpha, b.wu, w.dyr,
+                                                         w.ds, w.dc, R, N, F, g->nnz_att);
+    check_launch();
+    gat_bwd_dwu_k<<<grid1d(R * N * F, TPB), TPB, 0, c.st>>>(g->att_rptr, g->att_col, g->att_val, g->att_cptr, g->att_ceid,
+                                                            b.alpha, w.ds, w.dc, w.dyr, mixer, w.dwu, w.drc, R, N, F, g->nnz_att);
+    check_launch();
+    if (dmixer) {
+      gat_bwd_mixer_k<<<(unsigned)std::min<long long>((R * N + 63) / 64, 148 * 8), 64, 0, c.st>>>(w.drc, b.wu, dmixer, R * N, F);
+      check_launch();
+    }
+  }
+  Slabs z{}; z.p[0] = un;
+  contract_wgrad(c, z, w.dwu, dweight, R * N, F, 1, G);
+  if (dun) { SlabsMut dz{}; dz.p[0] = dun; contract_bwd_data(c, dz, weight, w.dwu, R * N, F, 1, G, 0); }
+}
+
+}  // namespace
+
+// ===================================================================================================
+// LSIGF, reference layout  x:[B,G,N] -> y:[B,F,N]
+// ===================================================================================================
+size_t lsigf_forward_f32(const gcrnn_graph* g, const float* h, const float* bias, const float* x, float* y,
+                         int F, int K, int G, int64_t B, void* ws, size_t wsb, cudaStream_t st) {
+  Arena a(ws, wsb);
+  Ctx c{g, st, a.dry()};
+  const int N = g->N, E = g->E;
+  const long long slab = (long long)B * N * G;
+  float* xn = (G == 1) ? const_cast<float*>(x) : a.get<float>(slab);
+  float* chain = a.get<float>((size_t)E * (K - 1) * slab);
+  float* yn = (F == 1) ? y : a.get<float>((size_t)B * N * F);
+  if (G != 1) transpose(c, x, nullptr, xn, G, N, B, 1, (long long)G * N, 0, (long long)N * G, 0);
+  shift_chain(c, xn, chain, E, K, G, B);
+  contract_fwd(c, chain_slabs(xn, chain, E, K, slab), h, bias, 1.f, nullptr, 1, yn, B, F, E * K, G);
+  if (F != 1) transpose(c, yn, nullptr, y, N, F, B, 1, (long long)N * F, 0, (long long)F * N, 0);
+  return a.off;
+}
+
+size_t lsigf_backward_f32(const gcrnn_graph* g, const float* h, const float* x, const float* dy, float* dx, float* dh,
+                          float* dbias, int F, int K, int G, int64_t B, void* ws, size_t wsb, cudaStream_t st) {
+  Arena a(ws, wsb);
+  Ctx c{g, st, a.dry()};
+  const int N = g->N, E = g->E;
+  const long long slab = (long long)B * N * G;
+  float* xn = (G == 1) ? const_cast<float*>(x) : a.get<float>(slab);
+  float* chain = a.get<float>((size_t)E * (K - 1) * slab);
+  float* dyn = (F == 1) ? const_cast<float*>(dy) : a.get<float>((size_t)B * N * F);
+  float* dz = a.get<float>((size_t)E * K * slab);
+  float* dxn = (G == 1) ? dx : a.get<float>(slab);
+  if (G != 1) transpose(c, x, nullptr, xn, G, N, B, 1, (long long)G * N, 0, (long long)N * G, 0);
+  if (F != 1) transpose(c, dy, nullptr, dyn, F, N, B, 1, (long long)F * N, 0, (long long)N * F, 0);
+  if (dh) {
+    shift_chain(c, xn, chain, E, K, G, B);
+    contract_wgrad(c, chain_slabs(xn, chain, E, K, slab), dyn, dh, (long long)B * N, F, E * K, G);
+  }
+  colsum(c, dyn, dbias, (long long)B * N, F);
+  if (dx) {
+    contract_bwd_data(c, mut_slabs(dz, E * K, slab), h, dyn, (long long)B * N, F, E * K, G, 0);
+    reverse_chain(c, dz, E, K, G, B, dxn, false);
+    if (G != 1) transpose(c, dxn, nullptr, dx, N, G, B, 1, (long long)N * G, 0, (long long)G * N, 0);
+  }
+  return a.off;
+}
+
+// ===================================================================================================
+// graph attention, reference layout
+// ===================================================================================================
+size_t gat_forward_f32(const gcrnn_graph* g, const float* mixer, const float* weight, const float* x, float* y,
+                       int F, int G, int64_t B, void* ws, size_t wsb, cudaStream_t st) {
+  GCRNN_CHECK(g->E == 1, "graph attention is defined for E == 1 (graphML.py:2327), got E=%d", g->E);
+  Arena a(ws, wsb);
+  Ctx c{g, st, a.dry()};
+  const int N = g->N;
+  float* xn = a.get<float>((size_t)B * N * G);
+  float* yn = a.get<float>((size_t)B * N * F);
+  GatBufs b; b.alloc(a, B, N, F, g->nnz_att);
+  transpose(c, x, nullptr, xn, G, N, B, 1, (long long)G * N, 0, (long long)N * G, 0);
+  gat_fwd_nm(c, mixer, weight, xn, yn, b, F, G, B);
+  transpose(c, yn, nullptr, y, N, F, B, 1, (long long)N * F, 0, (long long)F * N, 0);
+  return a.off;
+}
+
+size_t gat_backward_f32(const gcrnn_graph* g, const float* mixer, const float* weight, const float* x, const float* dy,
+                        float* dx, float* dmixer, float* dweight, int F, int G, int64_t B, void* ws, size_t wsb,
+                        cudaStream_t st) {
+  GCRNN_CHECK(g->E == 1, "graph attention is defined for E == 1 (graphML.py:2327), got E=%d", g->E);
+  Arena a(ws, wsb);
+  Ctx c{g, st, a.dry()};
+  const int N = g->N;
+  float* xn = a.get<float>((size_t)B * N * G);
+  float* yn = a.get<float>((size_t)B * N * F);
+  float* dyn = a.get<float>((size_t)B * N * F);
+  float* dxn = a.get<float>((size_t)B * N * G);
+  GatBufs b; b.alloc(a, B, N, F, g->nnz_att);
+  GatBwdBufs w; w.alloc(a, B, N, F, g->nnz_att);
+  transpose(c, x, nullptr, xn, G, N, B, 1, (long long)G * N, 0, (long long)N * G, 0);
+  transpose(c, dy, nullptr, dyn, F, N, B, 1, (long long)F * N, 0, (long long)N * F, 0);
+  gat_fwd_nm(c, mixer, weight, xn, yn, b, F, G, B);
+  gat_bwd_nm(c, mixer, weight, xn, yn, dyn, b, w, dx ? dxn : nullptr, dmixer, dweight, F, G, B);
+  if (dx) transpose(c, dxn, nullptr, dx, N, G, B, 1, (long long)N * G, 0, (long long)G * N, 0);
+  return a.off;
+}
+
+// ===================================================================================================
+// the gated GCRNN cell
+// ===================================================================================================
+namespace {
+
+struct CellDims {
+  int N, E, G, F, Kin, Kst;
+  long long B, T, TB, NG, NF;
+  bool tg, node, edge, gates;
+};
+
+CellDims dims_of(const gcrnn_cell* c, int64_t B, int64_t T) {
+  CellDims d;
+  d.N = c->g->N; d.E = c->d.E; d.G = c->d.G; d.F = c->d.F; d.Kin = c->d.Kin; d.Kst = c->d.Kst;
+  d.B = B; d.T = T; d.TB = B * T; d.NG = (long long)d.N * d.G; d.NF = (long long)d.N * d.F;
+  d.tg = c->d.time_gating != 0;
+  d.node = c->d.spatial_gating == GCRNN_SPATIAL_NODE;
+  d.edge = c->d.spatial_gating == GCRNN_SPATIAL_EDGE;
+  d.gates = d.tg || d.node;
+  GCRNN_CHECK(d.E == c->g->E, "cell E=%d but graph E=%d", d.E, c->g->E);
+  GCRNN_CHECK(!d.edge || d.E == 1, "edge gating needs E == 1");
+  GCRNN_CHECK(B > 0 && T > 0, "empty batch or sequence (B=%lld, T=%lld)", (long long)B, (long long)T);
+  return d;
+}
+
+// what forward leaves for backward (all node-major, time-major)
+struct Saved {
+  float *Hn, *Xn, *zx, *h0n, *zh0, *gt, *qn;
+  void layout(Arena& a, const CellDims& d) {
+    Hn = a.get<float>(d.TB * d.NF);
+    Xn = a.get<float>(d.TB * d.NG);
+    zx = a.get<float>((size_t)d.E * (d.Kin - 1) * d.TB * d.NG);
+    h0n = a.get<float>(d.B * d.NF);
+    zh0 = d.gates ? a.get<float>((size_t)d.E * (d.Kst - 1) * d.B * d.NF) : nullptr;
+    gt = d.tg ? a.get<float>(2 * d.TB) : nullptr;
+    qn = d.node ? a.get<float>(2 * d.TB * d.N) : nullptr;
+  }
+};
+
+struct SubCell { const float *A, *Bw, *b; };
+
+// u = tanh( LSIGF(A_s, x_t, b_s) + LSIGF(B_s, h0, b_s) ) for every (t, b): graphML.py:2362 / :2383 with :2417-2423
+void subcell_state(const Ctx& c, const CellDims& d, const Saved& s, const SubCell& sc, float* c0, float* ubuf) {
+  contract_fwd(c, chain_slabs(s.h0n, s.zh0, d.E, d.Kst, d.B * d.NF), sc.Bw, sc.b, 1.f, nullptr, 1, c0, d.B, d.F, d.E * d.Kst, d.F);
+  contract_fwd(c, chain_slabs(s.Xn, s.zx, d.E, d.Kin, d.TB * d.NG), sc.A, sc.b, 1.f, c0, d.B, ubuf, d.TB, d.F, d.E * d.Kin, d.G);
+}
+
+// node-gate head on u: q = sigmoid( sum_e Horner_k( p_{e,k} ) + c ), p_{e,k}[rn] = w[e,k,:] . u[rn,:]   (graphML.py:2385-2389)
+void node_head_fwd(const Ctx& c, const CellDims& d, const float* ubuf, const float* w, const float* cb, float* pbuf,
+                   float* v1, float* v2, float* q) {
+  const long long RN = d.TB * d.N;
+  const int S = d.E * d.Kst;
+  if (!c.dry) {
+    node_proj_fwd_k<<<grid1d(RN, 128), 128, (size_t)S * d.F * sizeof(float), c.st>>>(ubuf, w, pbuf, RN, d.F, S);
+    check_launch();
+  }
+  float* lin = nullptr;
+  for (int e = 0; e < d.E; ++e) {
+    float* cur = pbuf ? pbuf + (long long)(e * d.Kst + d.Kst - 1) * RN : nullptr;
+    for (int kk = d.Kst - 2; kk >= 0; --kk) {
+      float* pk = pbuf ? pbuf + (long long)(e * d.Kst + kk) * RN : nullptr;
+      float* out = (cur == v1) ? v2 : v1;
+      spmm(c, c.g->fwd[e], cur, pk, out, 1, d.TB);
+      cur = out;
+    }
+    if (e == 0) lin = cur;
+    else add_inplace(c, lin, cur, RN);
+    if (e == 0 && d.E > 1 && lin != q) {  // keep the running sum out of the ping-pong buffers
+      copy(c, q, lin, RN * sizeof(float));
+      lin = q;
+    }
+  }
+  if (!c.dry) {
+    sigmoid_bias_k<<<grid1d(RN, TPB), TPB, 0, c.st>>>(lin, cb, q, RN);
+    check_launch();
+  }
+}
+
+}  // namespace
+
+size_t cell_forward_f32(const gcrnn_cell* cell, const gcrnn_cell_params* p, const float* X, const float* h0, float* H,
+                        void* saved, size_t savedb, size_t* saved_used, void* ws, size_t wsb, int64_t B, int64_t T,
+                        cudaStream_t st) {
+  const CellDims d = dims_of(cell, B, T);
+  Arena a(ws, wsb);
+  Ctx c{cell->g, st, a.dry()};
+  Saved s;
+  {
+    Arena sa(saved, savedb);
+    s.layout(sa, d);
+    if (saved_used) *saved_used = sa.off;
+  }
+  GCRNN_CHECK(a.dry() || saved, "forward needs the `saved` buffer (see gcrnn_cell_workspace_bytes)");
+  const gcrnn_graph* g = cell->g;
+  // scratch
+  float* zh = a.get<float>((size_t)d.E * (d.Kst - 1) * d.B * d.NF);
+  float* ua = a.get<float>(d.B * d.NF);
+  float* ur = a.get<float>(d.B * d.NF);
+  GatBufs gb; float *qa = nullptr, *qr = nullptr;
+  if (d.edge) { gb.alloc(a, d.B, d.N, d.F, g->nnz_att); qa = a.get<float>(d.B * d.NF); qr = a.get<float>(d.B * d.NF); }
+  float *ubuf = nullptr, *c0 = nullptr, *wg = nullptr, *pbuf = nullptr, *v1 = nullptr, *v2 = nullptr;
+  if (d.gates) { ubuf = a.get<float>(d.TB * d.NF); c0 = a.get<float>(d.B * d.NF); }
+  if (d.tg) wg = a.get<float>(d.NF);
+  if (d.node) { pbuf = a.get<float>((size_t)d.E * d.Kst * d.TB * d.N); v1 = a.get<float>(d.TB * d.N); v2 = a.get<float>(d.TB * d.N); }
+  if (a.dry()) return a.off;
+
+  // ---- layout change + the non-recurrent part ---------------------------------------------------------
+  transpose(c, X, nullptr, s.Xn, d.G, d.N, d.B, d.T, d.T * d.NG, d.NG, d.NG, d.B * d.NG);          // [B,T,G,N] -> [T,B,N,G]
+  transpose(c, h0, nullptr, s.h0n, d.F, d.N, d.B, 1, d.NF, 0, d.NF, 0);                            // [B,F,N]  -> [B,N,F]
+  shift_chain(c, s.Xn, s.zx, d.E, d.Kin, d.G, d.TB);
+  if (d.gates) shift_chain(c, s.h0n, s.zh0, d.E, d.Kst, d.F, d.B);
+  if (d.tg)
+    for (int gi = 0; gi < 2; ++gi) {                                                             // graphML.py:2357-2374
+      subcell_state(c, d, s, SubCell{p->t_weight_A[gi], p->t_weight_B[gi], p->t_bias[gi]}, c0, ubuf);
+      transpose(c, p->t_mlp_w[gi], nullptr, wg, d.F, d.N, 1, 1, 0, 0, 0, 0);                       // index f*N+n -> n*F+f
+      gate_logit_k<<<(unsigned)std::min<long long>(d.TB, 148 * 8), TPB, 0, st>>>(ubuf, wg, p->t_mlp_b[gi], s.gt + gi * d.TB, d.TB, d.NF);
+      check_launch();
+    }
+  if (d.node)
+    for (int gi = 0; gi < 2; ++gi) {                                                             // graphML.py:2379-2399
+      subcell_state(c, d, s, SubCell{p->n_weight_A[gi], p->n_weight_B[gi], p->n_bias[gi]}, c0, ubuf);
+      node_head_fwd(c, d, ubuf, p->n_head_w[gi], p->n_head_b[gi], pbuf, v1, v2, s.qn + gi * d.TB * d.N);
+    }
+  // ---- the recurrence (graphML.py:2351-2427) ------------------------------------------------------------
+  for (long long t = 0; t < d.T; ++t) {
+    const float* hprev = t == 0 ? s.h0n : s.Hn + (t - 1) * d.B * d.NF;
+    shift_chain(c, hprev, zh, d.E, d.Kst, d.F, d.B);
+    contract_fwd(c, chain_slabs(hprev, zh, d.E, d.Kst, d.B * d.NF), p->weight_B, p->bias, 1.f, nullptr, 1, ur, d.B, d.F, d.E * d.Kst, d.F);
+    contract_fwd(c, chain_slabs(s.Xn, s.zx, d.E, d.Kin, d.TB * d.NG, t * d.B * d.NG), p->weight_A, p->bias, 1.f, nullptr, 1, ua,
+                 d.B, d.F, d.E * d.Kin, d.G);
+    const float *va = ua, *vr = ur;
+    if (d.edge) {
+      gat_fwd_nm(c, p->e_mixer[0], p->e_weight[0], ua, qa, gb, d.F, d.F, d.B);
+      gat_fwd_nm(c, p->e_mixer[1], p->e_weight[1], ur, qr, gb, d.F, d.F, d.B);
+      va = qa; vr = qr;
+    }
+    combine_fwd_k<<<grid1d(d.B * d.NF, TPB), TPB, 0, st>>>(
+        va, vr, d.tg ? s.gt + t * d.B : nullptr, d.tg ? s.gt + d.TB + t * d.B : nullptr,
+        d.node ? s.qn + t * d.B * d.N : nullptr, d.node ? s.qn + d.TB * d.N + t * d.B * d.N : nullptr,
+        s.Hn + t * d.B * d.NF, d.B, d.N, d.F);
+    check_launch();
+  }
+  transpose(c, s.Hn, nullptr, H, d.N, d.F, d.T, d.B, d.B * d.NF, d.NF, d.NF, d.T * d.NF);           // [T,B,N,F] -> [B,T,F,N]
+  return a.off;
+}
+
+size_t cell_backward_f32(const gcrnn_cell* cell, const gcrnn_cell_params* p, const float* X, const float* h0,
+                         const float* H, const float* dH, const void* saved, size_t savedb,
+                         const gcrnn_cell_params* gr, float* dX, float* dh0, void* ws, size_t wsb, int64_t B,
+                         int64_t T, cudaStream_t st) {
+  (void)X; (void)h0; (void)H;
+  const CellDims d = dims_of(cell, B, T);
+  Arena a(ws, wsb);
+  Ctx c{cell->g, st, a.dry()};
+  const gcrnn_graph* g = cell->g;
+  Saved s;
+  { Arena sa(const_cast<void*>(saved), savedb); s.layout(sa, d); }
+  GCRNN_CHECK(a.dry() || saved, "backward needs the buffer written by forward");
+  const int SA = d.E * d.Kin, SB = d.E * d.Kst;
+  const bool need_dx = dX != nullptr;
+  // scratch
+  float* zh = a.get<float>((size_t)d.E * (d.Kst - 1) * d.B * d.NF);
+  float* ua = a.get<float>(d.B * d.NF);
+  float* ur = a.get<float>(d.B * d.NF);
+  float* dht = a.get<float>(d.B * d.NF);
+  float* dhn = a.get<float>(d.B * d.NF);
+  float* da = a.get<float>(d.B * d.NF);
+  float* dr = a.get<float>(d.B * d.NF);
+  float* dzh = a.get<float>((size_t)SB * d.B * d.NF);
+  GatBufs gba, gbr; GatBwdBufs gw; float *qa = nullptr, *qr = nullptr, *da2 = nullptr, *dr2 = nullptr;
+  if (d.edge) {
+    gba.alloc(a, d.B, d.N, d.F, g->nnz_att); gbr.alloc(a, d.B, d.N, d.F, g->nnz_att); gw.alloc(a, d.B, d.N, d.F, g->nnz_att);
+    qa = a.get<float>(d.B * d.NF); qr = a.get<float>(d.B * d.NF); da2 = a.get<float>(d.B * d.NF); dr2 = a.get<float>(d.B * d.NF);
+  }
+  float* dzx = need_dx ? a.get<float>((size_t)SA * d.TB * d.NG) : nullptr;
+  float* dxn = need_dx ? a.get<float>(d.TB * d.NG) : nullptr;
+  float *dgt = nullptr, *dqn = nullptr, *ubuf = nullptr, *c0 = nullptr, *dc0 = nullptr, *wg = nullptr, *dwg = nullptr,
+        *dl = nullptr, *dzh0 = nullptr, *pbuf = nullptr;
+  if (d.tg) { dgt = a.get<float>(2 * d.TB); wg = a.get<float>(d.NF); dwg = a.get<float>(d.NF); dl = a.get<float>(d.TB); }
+  if (d.node) { dqn = a.get<float>(2 * d.TB * d.N); pbuf = a.get<float>((size_t)SB * d.TB * d.N); }
+  if (d.gates) {
+    ubuf = a.get<float>(d.TB * d.NF); c0 = a.get<float>(d.B * d.NF); dc0 = a.get<float>(d.B * d.NF);
+    dzh0 = a.get<float>((size_t)SB * d.B * d.NF);
+  }
+  if (a.dry()) return a.off;
+
+  zero(c, dhn, d.B * d.NF * sizeof(float));
+  if (d.tg) zero(c, dgt, 2 * d.TB * sizeof(float));
+
+  // ---- reverse-time sweep -----------------------------------------------------------------------------
+  for (long long t = d.T - 1; t >= 0; --t) {
+    const float* hprev = t == 0 ? s.h0n : s.Hn + (t - 1) * d.B * d.NF;
+    const Slabs zhs = chain_slabs(hprev, zh, d.E, d.Kst, d.B * d.NF);
+    const Slabs zxs = chain_slabs(s.Xn, s.zx, d.E, d.Kin, d.TB * d.NG, t * d.B * d.NG);
+    // recompute the step's filter outputs from the stored states
+    shift_chain(c, hprev, zh, d.E, d.Kst, d.F, d.B);
+    contract_fwd(c, zhs, p->weight_B, p->bias, 1.f, nullptr, 1, ur, d.B, d.F, SB, d.F);
+    contract_fwd(c, zxs, p->weight_A, p->bias, 1.f, nullptr, 1, ua, d.B, d.F, SA, d.G);
+    const float *va = ua, *vr = ur;
+    if (d.edge) {
+      gat_fwd_nm(c, p->e_mixer[0], p->e_weight[0], ua, qa, gba, d.F, d.F, d.B);
+      gat_fwd_nm(c, p->e_mixer[1], p->e_weight[1], ur, qr, gbr, d.F, d.F, d.B);
+      va = qa; vr = qr;
+    }
+    // dh_t = dH[:, t] (reference layout) + what flowed back from step t+1
+    transpose(c, dH + t * d.NF, dhn, dht, d.F, d.N, d.B, 1, d.T * d.NF, 0, d.NF, 0);
+    {
+      dim3 grid((d.N + 127) / 128, (unsigned)std::min<long long>(d.B, 32768));
+      combine_bwd_k<<<grid, 128, 0, st>>>(dht, s.Hn + t * d.B * d.NF, va, vr,
+                                          d.tg ? s.gt + t * d.B : nullptr, d.tg ? s.gt + d.TB + t * d.B : nullptr,
+                                          d.node ? s.qn + t * d.B * d.N : nullptr, d.node ? s.qn + d.TB * d.N + t * d.B * d.N : nullptr,
+                                          da, dr, d.tg ? dgt + t * d.B : nullptr, d.tg ? dgt + d.TB + t * d.B : nullptr,
+                                          d.node ? dqn + t * d.B * d.N : nullptr, d.node ? dqn + d.TB * d.N + t * d.B * d.N : nullptr,
+                                          d.B, d.N, d.F);
+      check_launch();
+    }
+    const float *dua = da, *dur = dr;
+    if (d.edge) {
+      gat_bwd_nm(c, p->e_mixer[0], p->e_weight[0], ua, qa, da, gba, gw, da2, gr->e_mixer[0], gr->e_weight[0], d.F, d.F, d.B);
+      gat_bwd_nm(c, p->e_mixer[1], p->e_weight[1], ur, qr, dr, gbr, gw, dr2, gr->e_mixer[1], gr->e_weight[1], d.F, d.F, d.B);
+      dua = da2; dur = dr2;
+    }
+    contract_wgrad(c, zxs, dua, gr->weight_A, d.B * d.N, d.F, SA, d.G);
+    contract_wgrad(c, zhs, dur, gr->weight_B, d.B * d.N, d.F, SB, d.F);
+    colsum(c, dua, gr->bias, d.B * d.N, d.F);
+    colsum(c, dur, gr->bias, d.B * d.N, d.F);
+    contract_bwd_data(c, mut_slabs(dzh, SB, d.B * d.NF), p->weight_B, dur, d.B * d.N, d.F, SB, d.F, 0);
+    reverse_chain(c, dzh, d.E, d.Kst, d.F, d.B, dhn, false);
+    if (need_dx) contract_bwd_data(c, mut_slabs(dzx, SA, d.TB * d.NG, t * d.B * d.NG), p->weight_A, dua, d.B * d.N, d.F, SA, d.G, 0);
+  }
+
+  // ---- gates: batched over all (t, b); they depend on (x_t, h0) only ------------------------------------
+  bool first_h0 = true;
+  auto subcell_bwd = [&](const SubCell& sc, float* gA, float* gB, float* gb) {
+    // ubuf holds d(pre-activation) of the sub-cell state for every (t, b)
+    contract_wgrad(c, chain_slabs(s.Xn, s.zx, d.E, d.Kin, d.TB * d.NG), ubuf, gA, d.TB * d.N, d.F, SA, d.G);
+    colsum(c, ubuf, gb, d.TB * d.N, d.F, 2.f);                    // the sub-cell adds its bias twice (graphML.py:2421-2422)
+    reduce_t_k<<<grid1d(d.B * d.NF, TPB), TPB, 0, st>>>(ubuf, dc0, d.T, d.B, d.NF);
+    check_launch();
+    contract_wgrad(c, chain_slabs(s.h0n, s.zh0, d.E, d.Kst, d.B * d.NF), dc0, gB, d.B * d.N, d.F, SB, d.F);
+    if (need_dx) contract_bwd_data(c, mut_slabs(dzx, SA, d.TB * d.NG), sc.A, ubuf, d.TB * d.N, d.F, SA, d.G, 1);
+    if (dh0) { contract_bwd_data(c, mut_slabs(dzh0, SB, d.B * d.NF), sc.Bw, dc0, d.B * d.N, d.F, SB, d.F, first_h0 ? 0 : 1); first_h0 = false; }
+  };
+  if (d.tg)
+    for (int gi = 0; gi < 2; ++gi) {
+      const SubCell sc{p->t_weight_A[gi], p->t_weight_B[gi], p->t_bias[gi]};
+      subcell_state(c, d, s, sc, c0, ubuf);
+      transpose(c, p->t_mlp_w[gi], nullptr, wg, d.F, d.N, 1, 1, 0, 0, 0, 0);
+      gate_dlogit_k<<<1, 1024, 0, st>>>(dgt + gi * d.TB, s.gt + gi * d.TB, dl, gr->t_mlp_b[gi], d.TB);
+      check_launch();
+      zero(c, dwg, d.NF * sizeof(float));
+      {
+        dim3 grid((unsigned)std::min<long long>((d.NF + TPB - 1) / TPB, 148 * 8), (unsigned)std::max<long long>(1, std::min<long long>(d.TB / 64, 64)));
+        gate_du_k<<<grid, TPB, 0, st>>>(ubuf, wg, dl, dwg, d.TB, d.NF);
+        check_launch();
+      }
+      if (gr->t_mlp_w[gi]) transpose(c, dwg, gr->t_mlp_w[gi], gr->t_mlp_w[gi], d.N, d.F, 1, 1, 0, 0, 0, 0);
+      subcell_bwd(sc, gr->t_weight_A[gi], gr->t_weight_B[gi], gr->t_bias[gi]);
+    }
+  if (d.node)
+    for (int gi = 0; gi < 2; ++gi) {
+      const SubCell sc{p->n_weight_A[gi], p->n_weight_B[gi], p->n_bias[gi]};
+      const long long RN = d.TB * d.N;
+      subcell_state(c, d, s, sc, c0, ubuf);
+      // d(lin) = dq q (1-q); dp_{e,0} = dlin, dp_{e,k} = dp_{e,k-1} @ S_e^T
+      dsigmoid_k<<<grid1d(RN, TPB), TPB, 0, st>>>(dqn + gi * RN, s.qn + gi * RN, pbuf, gr->n_head_b[gi], RN);
+      check_launch();
+      for (int e = 0; e < d.E; ++e) {
+        float* p0 = pbuf + (long long)(e * d.Kst) * RN;
+        if (e > 0) copy(c, p0, pbuf, RN * sizeof(float));
+        for (int kk = 1; kk < d.Kst; ++kk) spmm(c, g->bwd[e], p0 + (long long)(kk - 1) * RN, nullptr, p0 + (long long)kk * RN, 1, d.TB);
+      }
+      {
+        float* dw = gr->n_head_w[gi];
+        GCRNN_CHECK(dw, "node-gate head gradient buffer missing");
+        node_proj_bwd_k<<<grid1d(RN, 128, 148 * 4), 128, (size_t)2 * SB * d.F * sizeof(float), st>>>(ubuf, p->n_head_w[gi], pbuf, dw, RN, d.F, SB);
+        check_launch();
+      }
+      subcell_bwd(sc, gr->n_weight_A[gi], gr->n_weight_B[gi], gr->n_bias[gi]);
+    }
+  // ---- input gradients ------------------------------------------------------------------------------------
+  if (dh0) {
+    if (d.gates) reverse_chain(c, dzh0, d.E, d.Kst, d.F, d.B, dhn, true);
+    transpose(c, dhn, nullptr, dh0, d.N, d.F, d.B, 1, d.NF, 0, d.NF, 0);
+  }
+  if (need_dx) {
+    reverse_chain(c, dzx, d.E, d.Kin, d.G, d.TB, dxn, false);
+    transpose(c, dxn, nullptr, dX, d.N, d.G, d.T, d.B, d.B * d.NG, d.NG, d.NG, d.T * d.NG);          // [T,B,N,G] -> [B,T,G,N]
+  }
+  return a.off;
+}
+
+}  // namespace gcrnn

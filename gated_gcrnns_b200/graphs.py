@@ -1,0 +1,61 @@
+"""Synthetic graph generators for the benchmark configurations.
+
+Host-side setup only (numpy); the reference builds its graphs with Utils/graphTools.py (SBM, kStepPredGRNNs.py:110-116)
+or loads Adj.p (epicenterEstimation.py:474).  These are our own generators of the same families.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+
+def dense_random(N=1024, density=0.3, seed=0) -> torch.Tensor:
+    """cfg3: W = triu(rand < density, 1); W += W^T; S = W / lambda_max.  Returns [1,N,N] float32."""
+    rng = np.random.RandomState(seed)
+    W = np.triu(rng.rand(N, N) < density, 1).astype(np.float64)
+    W = W + W.T
+    lam = np.abs(np.linalg.eigvalsh(W)).max()
+    return torch.tensor(W / lam, dtype=torch.float32).reshape(1, N, N)
+
+
+def sbm(N=80, C=5, p_in=0.8, p_out=0.2, seed=0) -> torch.Tensor:
+    """cfg1-like stochastic block model, S = W / lambda_max, [1,N,N] float32."""
+    rng = np.random.RandomState(seed)
+    lab = np.arange(N) % C
+    P = np.where(lab[:, None] == lab[None, :], p_in, p_out)
+    W = np.triu(rng.rand(N, N) < P, 1).astype(np.float64)
+    W = W + W.T
+    lam = np.abs(np.linalg.eigvalsh(W)).max()
+    return torch.tensor(W / lam, dtype=torch.float32).reshape(1, N, N)
+
+
+def knn_csr(N=100_000, k=16, seed=0, sigma2=None, power_iters=50):
+    """cfg5: directed kNN graph on uniform points of the unit square, weights exp(-d^2/sigma^2),
+    normalised by |lambda|max estimated with power iterations.  Returns (rowptr int64, colidx int32, vals float32)."""
+    from scipy.spatial import cKDTree
+    import scipy.sparse as sp
+    rng = np.random.RandomState(seed)
+    pts = rng.rand(N, 2)
+    order = np.lexsort((pts[:, 1], np.floor(pts[:, 0] * 64)))     # coarse spatial ordering -> neighbour locality
+    pts = pts[order]
+    d, idx = cKDTree(pts).query(pts, k=k + 1)
+    d, idx = d[:, 1:], idx[:, 1:]
+    if sigma2 is None:
+        sigma2 = float(np.mean(d[:, -1] ** 2))
+    w = np.exp(-d ** 2 / sigma2)
+    rows = np.repeat(np.arange(N), k)
+    A = sp.csr_matrix((w.ravel(), (rows, idx.ravel())), shape=(N, N))
+    v = np.ones(N) / np.sqrt(N)
+    lam = 1.0
+    for _ in range(power_iters):
+        v2 = A.T @ (A @ v)
+        lam = np.sqrt(np.linalg.norm(v2) / max(np.linalg.norm(v), 1e-30))
+        v = v2 / max(np.linalg.norm(v2), 1e-30)
+    A = (A / lam).tocsr()
+    A.sort_indices()
+    return A.indptr.astype(np.int64), A.indices.astype(np.int32), A.data.astype(np.float32)
+
+
+def csr_to_torch_sparse(rowptr, colidx, vals, N) -> torch.Tensor:
+    return torch.sparse_csr_tensor(torch.as_tensor(rowptr), torch.as_tensor(colidx).to(torch.int64), torch.as_tensor(vals),
+                                   size=(N, N))

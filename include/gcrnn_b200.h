@@ -1,0 +1,129 @@
+/* gcrnn_b200.h — C ABI of the B200-native gated-GCRNN hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types.  The
+ * Python host layer (gated_gcrnns_b200/) binds it with ctypes and mirrors the
+ * reference's module interface (Utils/graphML.py) on top of it.
+ *
+ * Every entry point replaces one piece of /root/reference/Utils/graphML.py:
+ *   gcrnn_graph_*            <- the `S` tensor handed to `addGSO`            (:1166-1173, :2074-2081, :2237-2244)
+ *   gcrnn_lsigf_forward/...  <- `LSIGF(h, S, x, b)` + its autograd backward   (:47-140)
+ *   gcrnn_gat_forward/...    <- `graphAttention` + `GraphAttentional.forward` (:521-627, :2084-2116)
+ *   gcrnn_cell_forward/...   <- `GGCRNNCell.forward` + its autograd backward  (:2336-2428)
+ *   gcrnn_allreduce_*        <- (new) the data-parallel gradient sum; the reference is single-process.
+ *
+ * Conventions
+ *   - all tensor pointers are DEVICE pointers to contiguous fp32 row-major arrays in the
+ *     reference's own layouts (x:[B,G,N], X:[B,T,G,N], H:[B,T,F,N], weights as in the
+ *     reference's Parameters); graph construction takes HOST pointers;
+ *   - work is enqueued on the `cudaStream_t` passed as `void* stream`; nothing synchronises;
+ *   - return value 0 = OK, negative = error; `gcrnn_last_error()` returns a thread-local message;
+ *   - the caller owns every tensor and the workspace; a graph/cell handle owns only its
+ *     pre-processed copies of the shift operator (CSR/CSC, S+I pattern, bf16 tiles, TMA maps);
+ *   - a handle is used from one host thread at a time; one handle per device.
+ */
+#ifndef GCRNN_B200_H
+#define GCRNN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GCRNN_ABI_VERSION 1
+
+typedef struct gcrnn_graph gcrnn_graph;   /* shift operator S (E edge features, N nodes) on one device */
+typedef struct gcrnn_cell  gcrnn_cell;    /* one GGCRNNCell configuration bound to a graph            */
+
+enum { GCRNN_SPATIAL_NONE = 0, GCRNN_SPATIAL_NODE = 1, GCRNN_SPATIAL_EDGE = 2 };
+enum { GCRNN_PREC_FP32 = 0,      /* CUDA-core fp32 everywhere, sparse (CSR) shift — exact path           */
+       GCRNN_PREC_BF16_TC = 1 }; /* dense shift on tcgen05 tensor cores, bf16 operands, fp32 accumulate   */
+
+/* GGCRNNCell(G, F, Kin, Kst, sigma=tanh, time_gating, spatial_gating, E, bias)  graphML.py:2196 */
+typedef struct {
+  int32_t G, F, Kin, Kst, E;
+  int32_t time_gating;       /* 0 / 1 */
+  int32_t spatial_gating;    /* GCRNN_SPATIAL_* */
+  int32_t bias;              /* 0 / 1 */
+  int32_t precision;         /* GCRNN_PREC_* */
+} gcrnn_cell_desc;
+
+/* Parameter (and gradient) pointers, named after the reference's state_dict keys.
+ * Index 0 = input gate, 1 = forget gate.  Unused groups are NULL.  In a gradient block a NULL pointer
+ * means "do not compute"; gradients are ACCUMULATED (+=) into the given buffers. */
+typedef struct {
+  float *weight_A, *weight_B, *bias;                /* [F,E,Kin,G] [F,E,Kst,F] [F]                         */
+  float *t_weight_A[2], *t_weight_B[2], *t_bias[2]; /* GFL_in / GFL_forget sub-cells                       */
+  float *t_mlp_w[2], *t_mlp_b[2];                   /* MLP_in.0 / MLP_forget.0: [F*N] (index f*N+n), [1]   */
+  float *n_weight_A[2], *n_weight_B[2], *n_bias[2]; /* GRNN_node_in / GRNN_node_forget sub-cells           */
+  float *n_head_w[2], *n_head_b[2];                 /* GFL_node_*.0: [1,E,Kst,F], [1]                      */
+  float *e_mixer[2], *e_weight[2];                  /* input_attention / forget_attention: [2F], [F,F]     */
+} gcrnn_cell_params;
+
+int         gcrnn_abi_version(void);
+const char* gcrnn_last_error(void);
+/* number of CUDA kernels this library has launched in this process (bench.py's `gpu_launches`) */
+uint64_t    gcrnn_debug_launch_count(void);
+
+/* ---- graph -------------------------------------------------------------------------------------- */
+/* E operators in CSR, HOST arrays: rowptr[e] has N+1 entries, entry (i, colidx[p]) = S_e[i, j] = vals[p].
+ * Row-vector convention of the reference: shift is z <- z @ S_e (graphML.py:123). */
+int gcrnn_graph_create_csr(gcrnn_graph** out, int32_t N, int32_t E,
+                           const int64_t* const* rowptr, const int32_t* const* colidx,
+                           const float* const* vals, int32_t device);
+/* Dense HOST array S[E,N,N] (what `addGSO` receives); exact zeros are dropped from the CSR form.
+ * keep_dense != 0 additionally keeps bf16 copies of S and S^T for the tensor-core path (E must be 1). */
+int gcrnn_graph_create_dense(gcrnn_graph** out, int32_t N, int32_t E, const float* S,
+                             int32_t keep_dense, int32_t device);
+int gcrnn_graph_destroy(gcrnn_graph* g);
+int gcrnn_graph_info(const gcrnn_graph* g, int32_t* N, int32_t* E, int64_t* nnz, int64_t* nnz_att);
+
+/* ---- LSIGF: y[b,f,n] = sum_{e,k,g} h[f,e,k,g] (x S_e^k)[b,g,n] + bias[f] -------------------------- */
+size_t gcrnn_lsigf_workspace_bytes(const gcrnn_graph* g, int32_t F, int32_t K, int32_t G, int64_t B);
+int gcrnn_lsigf_forward(const gcrnn_graph* g, const float* h, const float* bias /*NULL ok*/,
+                        const float* x, float* y, int32_t F, int32_t K, int32_t G, int64_t B,
+                        void* workspace, size_t workspace_bytes, void* stream);
+/* dx / dh / dbias may be NULL; dh and dbias are accumulated (+=), dx is overwritten. */
+int gcrnn_lsigf_backward(const gcrnn_graph* g, const float* h, const float* x, const float* dy,
+                         float* dx, float* dh, float* dbias, int32_t F, int32_t K, int32_t G, int64_t B,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- graph attention (edge gate): y = relu(GAT_{1 head}(x)); mixer[2F], weight[F,G] ---------------- */
+size_t gcrnn_gat_workspace_bytes(const gcrnn_graph* g, int32_t F, int32_t G, int64_t B);
+int gcrnn_gat_forward(const gcrnn_graph* g, const float* mixer, const float* weight, const float* x,
+                      float* y, int32_t F, int32_t G, int64_t B,
+                      void* workspace, size_t workspace_bytes, void* stream);
+int gcrnn_gat_backward(const gcrnn_graph* g, const float* mixer, const float* weight, const float* x,
+                       const float* dy, float* dx, float* dmixer, float* dweight,
+                       int32_t F, int32_t G, int64_t B,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- the gated GCRNN cell --------------------------------------------------------------------------- */
+int gcrnn_cell_create(gcrnn_cell** out, const gcrnn_cell_desc* desc, const gcrnn_graph* g);
+int gcrnn_cell_destroy(gcrnn_cell* c);
+/* saved_bytes: buffer written by forward and read by backward; fwd/bwd_bytes: scratch. */
+int gcrnn_cell_workspace_bytes(const gcrnn_cell* c, int64_t B, int64_t T, int32_t need_input_grads,
+                               size_t* saved_bytes, size_t* fwd_bytes, size_t* bwd_bytes);
+/* X:[B,T,G,N], h0:[B,F,N] -> H:[B,T,F,N].  `saved` (saved_bytes from gcrnn_cell_workspace_bytes) is required. */
+int gcrnn_cell_forward(gcrnn_cell* c, const gcrnn_cell_params* p, const float* X, const float* h0,
+                       float* H, void* saved, size_t saved_bytes,
+                       void* workspace, size_t workspace_bytes, int64_t B, int64_t T, void* stream);
+/* grads: accumulated (+=).  dX / dh0 may be NULL.  Parameters the reference never uses
+ * (GFL_out.*, MLP_out.*) do not appear here at all: their gradient stays None, as in the reference. */
+int gcrnn_cell_backward(gcrnn_cell* c, const gcrnn_cell_params* p, const float* X, const float* h0,
+                        const float* H, const float* dH, const void* saved, size_t saved_bytes,
+                        const gcrnn_cell_params* grads, float* dX, float* dh0,
+                        void* workspace, size_t workspace_bytes, int64_t B, int64_t T, void* stream);
+
+/* ---- data-parallel gradient sum (one NCCL all-reduce per step on a flat fp32 bucket) ----------------- */
+typedef struct gcrnn_comm gcrnn_comm;
+int gcrnn_comm_unique_id(void* id128 /* 128 bytes out */);
+int gcrnn_comm_create(gcrnn_comm** out, const void* id128, int32_t rank, int32_t world, int32_t device);
+int gcrnn_comm_destroy(gcrnn_comm* c);
+int gcrnn_allreduce_sum(gcrnn_comm* c, float* bucket, int64_t count, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GCRNN_B200_H */
