@@ -1,0 +1,621 @@
+// Tensor-core cell path: everything around the tcgen05 shift GEMM for the dense, time-gated (or ungated) cell.
+//
+// Native reference layout throughout: a signal is [(b, f), n] row-major, so the shift GEMM's output rows are
+// H[b, t, f, :] rows and no transposes are needed.  Per time step (Utils/graphML.py:2351-2427):
+//     z_k = z_{k-1} @ S           (k = 1..Kst-1)   tcgen05 GEMM, bf16 in / bf16 out             [tc_gemm.cuh]
+//     r   = sum_k B_k z_k ;  h_t = tanh(gi (A(S)x_t + b) + gf (r + b))     contract_mma<EPI_FWD>  [here]
+// and in reverse (hand-derived adjoint, no recomputation of the forward chain):
+//     dpre = (dH_t + dh_rec) (1 - h_t^2)                                    dpre_kernel           [here]
+//     v_k = v_{k-1} @ S^T          (k = 1..Kst-1)   tcgen05 GEMM
+//     q = sum_k B_k^T v_k ; dgf = <q, h_{t-1}> ; dh_rec = gf q              contract_mma<EPI_BWD>
+//     dB_k += gf * v_k h_{t-1}^T                                            wgrad_mma
+// The tap contractions are bf16 mma.sync (HMMA) kernels: they are ~8 % of the flops and HBM-bound.
+#pragma once
+#include "tc_gemm.cuh"
+
+namespace gcrnn {
+namespace tc {
+
+// ---- small device helpers ---------------------------------------------------------------------------------
+__device__ __forceinline__ void ldsm_x4(uint32_t* r, uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t* r, uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N_> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_) : "memory"); }
+
+__device__ __forceinline__ float warp_sum_f(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---- fp32 -> bf16 ---------------------------------------------------------------------------------------------
+__global__ void cvt_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n4) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(in)[i];
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 u; u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
+    reinterpret_cast<uint2*>(out)[i] = u;
+  }
+}
+
+// ---- weight preparation: W[f, k, g] fp32 -> bf16 [rows][ld] ------------------------------------------------------
+// mode 0: out[f][k*G + g] = W[f,k,g]          (forward contraction, rows = output features)
+// mode 1: out[g][k*F + f] = W[f,k,g]          (data-gradient contraction, rows = input features)
+__global__ void prep_weight_kernel(const float* __restrict__ W, __nv_bfloat16* __restrict__ out, int F, int K, int G, int ld, int mode) {
+  const int total = F * K * G;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int g = i % G, k = (i / G) % K, f = i / (G * K);
+    const float v = W[i];
+    if (mode == 0) out[f * ld + k * G + g] = __float2bfloat16(v);
+    else out[g * ld + k * F + f] = __float2bfloat16(v);
+  }
+}
+
+// =====================================================================================================
+// contract_mma: Y[b, m, n] = sum_{k, c} W[m, k*C + c] * Z_k[b, c, n]      (per sample; mma.sync bf16)
+// =====================================================================================================
+constexpr int CT_NT = 64;          // n columns per tile
+constexpr int CT_ZLD = CT_NT + 8;  // padded smem row (144 B: conflict-free ldmatrix)
+constexpr int CT_THREADS = 256;
+
+enum { EPI_PLAIN = 0, EPI_FWD = 1, EPI_BWD = 2 };
+
+struct ContractArgs {
+  const __nv_bfloat16* W;    // [M][ldw] bf16
+  const __nv_bfloat16* z0;   // slab 0            [B][C][N]
+  const __nv_bfloat16* zc;   // slabs 1..K-1      [K-1][B][C][N]
+  int K, C, M, N, ldw;
+  long long B;
+  // EPI_PLAIN: out_f32[b,m,n] = acc + bias_scale * bias[m]
+  // EPI_FWD  : h = tanh(gi (a + bias) + gf (acc + bias)), a = sum_{k,g} A[m,k,g] zx_k[(b,t,g), n]
+  // EPI_BWD  : dgf[b] += <acc, hprev[b]> ; out_f32[b,m,n] = gf[b] * acc (+ out_f32 if accumulate)
+  float* out_f32; long long out_bstride;      // sample stride of out_f32 (H uses T*F*N)
+  __nv_bfloat16* out_bf16;                    // [B][M][N] or null
+  const float* bias; float bias_scale;
+  const float* gi; const float* gf; long long gate_stride;     // gate value of sample b at gi[b*gate_stride]
+  const float* A; int Kin, G;                                   // [M][Kin][G] fp32
+  const float* x0; long long x0_bstride;                        // zx_0 = X[b, t]: [G][N] at x0 + b*x0_bstride
+  const float* zx; long long zx_kstride, zx_bstride;            // zx_k (k>=1) at zx + (k-1)*kstride + b*bstride
+  const float* hprev; long long hprev_bstride;                  // EPI_BWD: fp32 h_{t-1}[b] = hprev + b*bstride
+  float* dgf; int accumulate;
+};
+
+template <int EPI>
+__global__ void __launch_bounds__(CT_THREADS, 1) contract_mma_kernel(const ContractArgs a) {
+  extern __shared__ __align__(16) uint8_t ct_smem[];
+  const int KK = a.K * a.C;
+  __nv_bfloat16* Ws = reinterpret_cast<__nv_bfloat16*>(ct_smem);                 // [64][ldw]
+  __nv_bfloat16* Zs = Ws + 64 * a.ldw;                                            // [2][KK][CT_ZLD]
+  float* fs = reinterpret_cast<float*>(Zs + 2 * (size_t)KK * CT_ZLD);             // A [M*Kin*G], bias [M], red[8]
+  float* As = fs; float* bs = fs + 64 * 32; float* red = bs + 64;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wm = warp & 3, wn = warp >> 2;
+  const int tiles_n = a.N / CT_NT;
+  const long long num_tiles = a.B * tiles_n;
+
+  // weights (once per CTA)
+  {
+    const int chunks_per_row = a.ldw / 8;
+    for (int i = tid; i < 64 * chunks_per_row; i += CT_THREADS) {
+      const int r = i / chunks_per_row, c = i % chunks_per_row;
+      if (r < a.M) cp_async16(smem_u32(Ws + r * a.ldw + c * 8), a.W + (size_t)r * a.ldw + c * 8);
+      else *reinterpret_cast<uint4*>(Ws + r * a.ldw + c * 8) = make_uint4(0, 0, 0, 0);
+    }
+    if (EPI == EPI_FWD) {
+      for (int i = tid; i < a.M * a.Kin * a.G; i += CT_THREADS) As[i] = a.A[i];
+    }
+    if (EPI != EPI_BWD) for (int i = tid; i < 64; i += CT_THREADS) bs[i] = (a.bias && i < a.M) ? a.bias[i] : 0.f;
+  }
+  auto load_tile = [&](long long tile, int buf) {
+    const long long b = tile / tiles_n;
+    const int n0 = (int)(tile % tiles_n) * CT_NT;
+    __nv_bfloat16* dst = Zs + (size_t)buf * KK * CT_ZLD;
+    for (int i = tid; i < KK * 8; i += CT_THREADS) {
+      const int row = i >> 3, ch = i & 7;
+      const int k = row / a.C, c = row % a.C;
+      const __nv_bfloat16* src = (k == 0 ? a.z0 : a.zc + (size_t)(k - 1) * a.B * a.C * a.N) + ((size_t)(b * a.C + c) * a.N + n0 + ch * 8);
+      cp_async16(smem_u32(dst + row * CT_ZLD + ch * 8), src);
+    }
+  };
+
+  long long tile = blockIdx.x;
+  if (tile < num_tiles) load_tile(tile, 0);
+  cp_async_commit();
+  int buf = 0;
+  for (; tile < num_tiles; tile += gridDim.x, buf ^= 1) {
+    const long long nxt = tile + gridDim.x;
+    if (nxt < num_tiles) load_tile(nxt, buf ^ 1);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+
+    const long long b = tile / tiles_n;
+    const int n0 = (int)(tile % tiles_n) * CT_NT;
+    const __nv_bfloat16* Zb = Zs + (size_t)buf * KK * CT_ZLD;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
+    const uint32_t a_addr = smem_u32(Ws + (16 * wm + (lane & 7) + 8 * ((lane >> 3) & 1)) * a.ldw + 8 * (lane >> 4));
+    const uint32_t b_addr = smem_u32(Zb + ((lane & 7) + 8 * ((lane >> 3) & 1)) * CT_ZLD + 32 * wn + 8 * (lane >> 4));
+    for (int ks = 0; ks < KK / 16; ++ks) {
+      uint32_t af[4], bf0[4], bf1[4];
+      ldsm_x4(af, a_addr + ks * 32);
+      ldsm_x4_t(bf0, b_addr + ks * 16 * CT_ZLD * 2);
+      ldsm_x4_t(bf1, b_addr + ks * 16 * CT_ZLD * 2 + 32);
+      mma_bf16(acc[0], af, bf0[0], bf0[1]);
+      mma_bf16(acc[1], af, bf0[2], bf0[3]);
+      mma_bf16(acc[2], af, bf1[0], bf1[1]);
+      mma_bf16(acc[3], af, bf1[2], bf1[3]);
+    }
+
+    // ---- epilogue: this thread holds rows m0, m0+8 and columns nb + 8*j + {0,1}, j = 0..3 ----
+    const int m0 = 16 * wm + (lane >> 2);
+    const int nb = n0 + 32 * wn + 2 * (lane & 3);
+    float part = 0.f;
+    float vgi = 1.f, vgf = 1.f;
+    if (EPI == EPI_FWD || EPI == EPI_BWD) {
+      if (a.gi) vgi = a.gi[b * a.gate_stride];
+      if (a.gf) vgf = a.gf[b * a.gate_stride];
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = nb + 8 * j;
+      float ax[2][2] = {{0.f, 0.f}, {0.f, 0.f}};   // [row half][col] input-filter term
+      if (EPI == EPI_FWD) {
+        for (int k = 0; k < a.Kin; ++k)
+          for (int g = 0; g < a.G; ++g) {
+            const float* zp = (k == 0) ? a.x0 + b * a.x0_bstride + (size_t)g * a.N
+                                       : a.zx + (size_t)(k - 1) * a.zx_kstride + b * a.zx_bstride + (size_t)g * a.N;
+            const float2 z = *reinterpret_cast<const float2*>(zp + n);
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              const int m = m0 + 8 * hh;
+              if (m < a.M) { const float w = As[(m * a.Kin + k) * a.G + g]; ax[hh][0] = fmaf(w, z.x, ax[hh][0]); ax[hh][1] = fmaf(w, z.y, ax[hh][1]); }
+            }
+          }
+      }
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int m = m0 + 8 * hh;
+        if (m >= a.M) continue;
+        float v0 = acc[j][2 * hh], v1 = acc[j][2 * hh + 1];
+        if (EPI == EPI_PLAIN) {
+          v0 += a.bias_scale * bs[m]; v1 += a.bias_scale * bs[m];
+          *reinterpret_cast<float2*>(a.out_f32 + b * a.out_bstride + (size_t)m * a.N + n) = make_float2(v0, v1);
+        } else if (EPI == EPI_FWD) {
+          const float bb = bs[m];
+          v0 = tanhf(vgi * (ax[hh][0] + bb) + vgf * (v0 + bb));
+          v1 = tanhf(vgi * (ax[hh][1] + bb) + vgf * (v1 + bb));
+          *reinterpret_cast<float2*>(a.out_f32 + b * a.out_bstride + (size_t)m * a.N + n) = make_float2(v0, v1);
+          *reinterpret_cast<__nv_bfloat162*>(a.out_bf16 + ((size_t)b * a.M + m) * a.N + n) = __floats2bfloat162_rn(v0, v1);
+        } else {
+          const float2 hp = *reinterpret_cast<const float2*>(a.hprev + b * a.hprev_bstride + (size_t)m * a.N + n);
+          part = fmaf(v0, hp.x, fmaf(v1, hp.y, part));
+          float* o = a.out_f32 + b * a.out_bstride + (size_t)m * a.N + n;
+          float2 r = make_float2(vgf * v0, vgf * v1);
+          if (a.accumulate) { const float2 old = *reinterpret_cast<float2*>(o); r.x += old.x; r.y += old.y; }
+          *reinterpret_cast<float2*>(o) = r;
+        }
+      }
+    }
+    if (EPI == EPI_BWD && a.dgf) {
+      part = warp_sum_f(part);
+      if (lane == 0) red[warp] = part;
+      __syncthreads();
+      if (tid == 0) { float s = 0.f; for (int w = 0; w < CT_THREADS / 32; ++w) s += red[w]; atomicAdd(a.dgf + b * a.gate_stride, s); }
+    }
+    __syncthreads();   // everyone is done with Zs[buf] (and red) before it is refilled
+  }
+  cp_async_wait<0>();
+}
+
+inline size_t contract_smem_bytes(int K, int C, int ldw) {
+  return (size_t)64 * ldw * 2 + (size_t)2 * K * C * CT_ZLD * 2 + (64 * 32 + 64 + 8) * sizeof(float);
+}
+
+template <int EPI>
+void launch_contract(const ContractArgs& a, int sms, cudaStream_t st) {
+  GCRNN_CHECK(a.M <= 64 && a.M % 16 == 0 && a.C % 16 == 0 && a.N % CT_NT == 0, "contract_mma: unsupported sizes M=%d C=%d N=%d", a.M, a.C, a.N);
+  GCRNN_CHECK(EPI != EPI_FWD || a.Kin * a.G <= 32, "tensor-core path supports Kin*G <= 32 (got %d)", a.Kin * a.G);
+  const size_t sm = contract_smem_bytes(a.K, a.C, a.ldw);
+  GCRNN_CHECK(sm <= 220 * 1024, "contract_mma: taps do not fit in shared memory (%zu B)", sm);
+  auto kern = contract_mma_kernel<EPI>;
+  CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  const long long tiles = a.B * (a.N / CT_NT);
+  const int grid = (int)std::min<long long>(tiles, sms);
+  kern<<<grid, CT_THREADS, sm, st>>>(a);
+  ++g_launches;
+  CUDA_OK(cudaGetLastError());
+}
+
+// =====================================================================================================
+// wgrad_mma: part[cta][k][f][g] += sum_{b in cta's tiles} scale[b] * sum_n V_k[b,f,n] * h[b,g,n]
+// =====================================================================================================
+constexpr int WG_NT = 64;
+constexpr int WG_LD = WG_NT + 8;
+constexpr int WG_MAXK = 5;
+
+struct WgradArgs {
+  const __nv_bfloat16* v0;   // slab 0         [B][F][N]
+  const __nv_bfloat16* vc;   // slabs 1..K-1   [K-1][B][F][N]
+  const float* h; long long h_bstride;          // fp32 h_{t-1}[b] = h + b*bstride, [F][N]
+  const float* scale; long long scale_stride;   // per-sample scale (gf[b,t]) or null
+  float* part;                                   // [grid][K][F][F] fp32, read-modify-write by its owner CTA
+  int K, F, N; long long B;
+};
+
+__global__ void __launch_bounds__(256, 1) wgrad_mma_kernel(const WgradArgs a) {
+  extern __shared__ __align__(16) uint8_t wg_smem[];
+  __nv_bfloat16* Vs = reinterpret_cast<__nv_bfloat16*>(wg_smem);          // [2][K][64][WG_LD]
+  __nv_bfloat16* Hs = Vs + (size_t)2 * a.K * 64 * WG_LD;                  // [2][64][WG_LD]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wm = warp & 3, wn = warp >> 2;       // m-tile (16 rows of f), half of g (32 columns)
+  const int tiles_n = a.N / WG_NT;
+  const long long num_tiles = a.B * tiles_n;
+
+  float acc[WG_MAXK][4][4];
+#pragma unroll
+  for (int k = 0; k < WG_MAXK; ++k)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { acc[k][j][0] = acc[k][j][1] = acc[k][j][2] = acc[k][j][3] = 0.f; }
+
+  auto load_tile = [&](long long tile, int buf) {
+    const long long b = tile / tiles_n;
+    const int n0 = (int)(tile % tiles_n) * WG_NT;
+    __nv_bfloat16* vd = Vs + (size_t)buf * a.K * 64 * WG_LD;
+    for (int i = tid; i < a.K * 64 * 8; i += 256) {
+      const int ch = i & 7, row = (i >> 3) & 63, k = i >> 9;
+      if (row < a.F) {
+        const __nv_bfloat16* src = (k == 0 ? a.v0 : a.vc + (size_t)(k - 1) * a.B * a.F * a.N) + ((size_t)(b * a.F + row) * a.N + n0 + ch * 8);
+        cp_async16(smem_u32(vd + ((size_t)k * 64 + row) * WG_LD + ch * 8), src);
+      }
+    }
+    // h: fp32 -> (scale) -> bf16
+    const float sc = a.scale ? a.scale[b * a.scale_stride] : 1.f;
+    __nv_bfloat16* hd = Hs + (size_t)buf * 64 * WG_LD;
+    for (int i = tid; i < 64 * 16; i += 256) {
+      const int row = i >> 4, c4 = i & 15;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row < a.F) v = *reinterpret_cast<const float4*>(a.h + b * a.h_bstride + (size_t)row * a.N + n0 + c4 * 4);
+      __nv_bfloat162 p = __floats2bfloat162_rn(v.x * sc, v.y * sc), q = __floats2bfloat162_rn(v.z * sc, v.w * sc);
+      uint2 u; u.x = *reinterpret_cast<uint32_t*>(&p); u.y = *reinterpret_cast<uint32_t*>(&q);
+      *reinterpret_cast<uint2*>(hd + row * WG_LD + c4 * 4) = u;
+    }
+  };
+  // rows >= F of the V tiles are never written: zero them once
+  for (int i = tid; i < 2 * a.K * 64 * WG_LD / 8; i += 256) reinterpret_cast<uint4*>(Vs)[i] = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+
+  long long tile = blockIdx.x;
+  if (tile < num_tiles) load_tile(tile, 0);
+  cp_async_commit();
+  int buf = 0;
+  for (; tile < num_tiles; tile += gridDim.x, buf ^= 1) {
+    const long long nxt = tile + gridDim.x;
+    if (nxt < num_tiles) load_tile(nxt, buf ^ 1);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    const __nv_bfloat16* vb = Vs + (size_t)buf * a.K * 64 * WG_LD;
+    const __nv_bfloat16* hb = Hs + (size_t)buf * 64 * WG_LD;
+    // A operand: V_k[f rows 16wm.., n]; B operand: h[g rows 32wn.., n] (both n-contiguous = K-contiguous)
+    const uint32_t a_off = (uint32_t)((16 * wm + (lane & 7) + 8 * ((lane >> 3) & 1)) * WG_LD + 8 * (lane >> 4)) * 2;
+    const uint32_t b_addr = smem_u32(hb + (32 * wn + (lane & 7) + 8 * (lane >> 4)) * WG_LD + 8 * ((lane >> 3) & 1));
+#pragma unroll
+    for (int ks = 0; ks < WG_NT / 16; ++ks) {
+      uint32_t bf0[4], bf1[4];
+      ldsm_x4(bf0, b_addr + ks * 32);
+      ldsm_x4(bf1, b_addr + ks * 32 + 16 * WG_LD * 2);
+#pragma unroll
+      for (int k = 0; k < WG_MAXK; ++k) {
+        if (k < a.K) {
+          uint32_t af[4];
+          ldsm_x4(af, smem_u32(vb + (size_t)k * 64 * WG_LD) + a_off + ks * 32);
+          mma_bf16(acc[k][0], af, bf0[0], bf0[1]);
+          mma_bf16(acc[k][1], af, bf0[2], bf0[3]);
+          mma_bf16(acc[k][2], af, bf1[0], bf1[1]);
+          mma_bf16(acc[k][3], af, bf1[2], bf1[3]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  cp_async_wait<0>();
+  // accumulate into this CTA's private slice: part[cta][k][f][g]
+  float* mine = a.part + (size_t)blockIdx.x * a.K * a.F * a.F;
+  const int f0 = 16 * wm + (lane >> 2);
+#pragma unroll
+  for (int k = 0; k < WG_MAXK; ++k) {
+    if (k < a.K) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int g = 32 * wn + 8 * j + 2 * (lane & 3);
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const int f = f0 + 8 * hh;
+          if (f < a.F && g < a.F) {
+            float* o = mine + ((size_t)k * a.F + f) * a.F + g;
+            o[0] += acc[k][j][2 * hh];
+            o[1] += acc[k][j][2 * hh + 1];
+          }
+        }
+      }
+    }
+  }
+}
+
+// dW[f, k, g] += sum_cta part[cta][k][f][g]
+__global__ void wgrad_reduce_kernel(const float* __restrict__ part, float* dW, int ncta, int K, int F) {
+  const int total = K * F * F;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int c = 0; c < ncta; ++c) s += part[(size_t)c * total + i];
+    const int g = i % F, f = (i / F) % F, k = i / (F * F);
+    dW[((size_t)f * K + k) * F + g] += s;
+  }
+}
+
+// =====================================================================================================
+// dpre kernel (one time step): dpre = (dH_t + dh_rec) * (1 - h_t^2), plus every reduction that needs dpre
+// =====================================================================================================
+struct DpreArgs {
+  const float* dH; long long dH_bstride;        // dH[b, t]  : [F][N] at dH + b*bstride
+  const float* Ht; long long H_bstride;         // h_t[b]
+  const float* dhrec;                           // [B][F][N] or null (t = T-1)
+  __nv_bfloat16* v0;                            // out: bf16 dpre [B][F][N]
+  const float* gi; const float* gf; long long gate_stride;
+  const float* A; const float* bias; int Kin, G, F, N;
+  const float* x0; long long x0_bstride; const float* zx; long long zx_kstride, zx_bstride;
+  float* dgi; float* dgf;                       // [.. b*gate_stride]: dgi += <dpre, a + bias>; dgf += <dpre, bias> (bias part only)
+  float* dA;                                    // [F][Kin][G]  += gi * sum_n dpre zx_k
+  float* dbias;                                 // [F]          += (gi + gf) * sum_n dpre
+  long long B;
+};
+constexpr int DP_FC = 8;   // features per CTA
+
+__global__ void __launch_bounds__(256) dpre_kernel(const DpreArgs a) {
+  __shared__ float red[8][DP_FC * 34];           // per warp: per f: sum_dp, and Kin*G (<=32) sums, + dgi slot
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int KG = a.Kin * a.G;
+  const int fgroups = a.F / DP_FC;
+  for (long long item = blockIdx.x; item < a.B * fgroups; item += gridDim.x) {
+    const long long b = item / fgroups;
+    const int f0 = (int)(item % fgroups) * DP_FC;
+    const float vgi = a.gi ? a.gi[b * a.gate_stride] : 1.f;
+    float s_dp[DP_FC], s_gi = 0.f;
+    float s_a[DP_FC];        // only used when KG == 1..: generic path accumulates into smem below
+#pragma unroll
+    for (int i = 0; i < DP_FC; ++i) { s_dp[i] = 0.f; s_a[i] = 0.f; }
+    // per-thread partial of sum_n dpre[f,n] * zx_kg[n] : kept in registers for up to 8 (k,g) pairs per pass
+    float s_z[DP_FC][8];
+    for (int kg0 = 0; kg0 < KG; kg0 += 8) {
+#pragma unroll
+      for (int i = 0; i < DP_FC; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s_z[i][j] = 0.f;
+      for (int n = tid; n < a.N; n += 256) {
+        float z[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int kg = kg0 + j;
+          if (kg < KG) {
+            const int k = kg / a.G, g = kg % a.G;
+            z[j] = (k == 0) ? a.x0[b * a.x0_bstride + (size_t)g * a.N + n]
+                            : a.zx[(size_t)(k - 1) * a.zx_kstride + b * a.zx_bstride + (size_t)g * a.N + n];
+          } else z[j] = 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < DP_FC; ++i) {
+          const int f = f0 + i;
+          const size_t o = (size_t)f * a.N + n;
+          const float hv = a.Ht[b * a.H_bstride + o];
+          float dh = a.dH[b * a.dH_bstride + o];
+          if (a.dhrec) dh += a.dhrec[((size_t)b * a.F) * a.N + o];
+          const float dp = dh * (1.f - hv * hv);
+          if (kg0 == 0) {
+            a.v0[((size_t)b * a.F) * a.N + o] = __float2bfloat16(dp);
+            s_dp[i] += dp;
+          }
+          float ax = 0.f;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            s_z[i][j] = fmaf(dp, z[j], s_z[i][j]);
+            if (kg0 + j < KG) ax = fmaf(a.A[(f * a.Kin) * a.G + kg0 + j], z[j], ax);
+          }
+          s_a[i] = fmaf(dp, ax, s_a[i]);
+        }
+      }
+      // reduce the (k,g) partials of this pass
+#pragma unroll
+      for (int i = 0; i < DP_FC; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float v = warp_sum_f(s_z[i][j]);
+          if (lane == 0) red[warp][i * 34 + 1 + ((kg0 + j) & 31)] = v;
+        }
+      __syncthreads();
+      for (int idx = tid; idx < DP_FC * 8; idx += 256) {
+        const int i = idx / 8, j = idx % 8;
+        if (kg0 + j < KG && a.dA) {
+          float s = 0.f;
+          for (int w = 0; w < 8; ++w) s += red[w][i * 34 + 1 + ((kg0 + j) & 31)];
+          atomicAdd(a.dA + (size_t)(f0 + i) * KG + kg0 + j, vgi * s);
+        }
+      }
+      __syncthreads();
+    }
+    // sum_n dpre per f, and <dpre, a> per sample
+#pragma unroll
+    for (int i = 0; i < DP_FC; ++i) {
+      const float v = warp_sum_f(s_dp[i]);
+      const float w = warp_sum_f(s_a[i]);
+      if (lane == 0) { red[warp][i * 34] = v; red[warp][i * 34 + 33] = w; }
+    }
+    __syncthreads();
+    if (tid < DP_FC) {
+      float sdp = 0.f, sa = 0.f;
+      for (int w = 0; w < 8; ++w) { sdp += red[w][tid * 34]; sa += red[w][tid * 34 + 33]; }
+      const int f = f0 + tid;
+      const float bb = a.bias ? a.bias[f] : 0.f;
+      const float vgf = a.gf ? a.gf[b * a.gate_stride] : 1.f;
+      if (a.dbias) atomicAdd(a.dbias + f, (vgi + vgf) * sdp);
+      if (a.dgi) atomicAdd(a.dgi + b * a.gate_stride, sa + bb * sdp);
+      if (a.dgf) atomicAdd(a.dgf + b * a.gate_stride, bb * sdp);
+    }
+    __syncthreads();
+    (void)s_gi;
+  }
+}
+
+// =====================================================================================================
+// time gates (graphML.py:2357-2374), evaluated for all (b, t) at once: they depend on (x_t, h0) only
+//   u = tanh(sum_{k,g} A_g[f,k,g] zx_k + c0[b,f,n]),   logit[b,t] = sum_{f,n} Wg[f,n] u
+// CTA = (n-tile of 128, chunk of TG_FC features, b-split); thread = one n.
+// =====================================================================================================
+constexpr int TG_FC = 4;
+struct GateArgs {
+  const float* A; int Kin, G, F, N; long long B, T;
+  const float* X;                 // [B,T,G,N]
+  const float* zx;                // [Kin-1][B*T*G][N]
+  const float* c0;                // [B,F,N]  (includes both bias terms)
+  const float* Wg;                // [F*N]
+  float* logit;                   // fwd: [B,T] += partial
+  const float* dl;                // bwd: dlogit [B,T]
+  float* dWg;                     // bwd: [F*N] +=
+  float* dc0;                     // bwd: [B,F,N] = sum_t dpre_u
+  float* dA;                      // bwd: [F,Kin,G] +=
+  int bsplit;
+};
+
+template <bool BWD>
+__global__ void __launch_bounds__(128) time_gate_kernel(const GateArgs a) {
+  __shared__ float red[4][TG_FC * 33];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n = blockIdx.x * 128 + tid;
+  const int f0 = blockIdx.y * TG_FC;
+  const int KG = a.Kin * a.G;
+  const long long bchunk = (a.B + a.bsplit - 1) / a.bsplit;
+  const long long b_lo = blockIdx.z * bchunk, b_hi = min(a.B, b_lo + bchunk);
+  float wA[TG_FC][32];
+#pragma unroll
+  for (int i = 0; i < TG_FC; ++i)
+#pragma unroll
+    for (int j = 0; j < 32; ++j) wA[i][j] = (j < KG) ? a.A[(size_t)(f0 + i) * KG + j] : 0.f;
+  float wg[TG_FC], dwg[TG_FC], sA[TG_FC][32];
+#pragma unroll
+  for (int i = 0; i < TG_FC; ++i) {
+    wg[i] = a.Wg[(size_t)(f0 + i) * a.N + n]; dwg[i] = 0.f;
+    if (BWD) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) sA[i][j] = 0.f;
+    }
+  }
+  for (long long b = b_lo; b < b_hi; ++b) {
+    float c0v[TG_FC], dc0v[TG_FC];
+#pragma unroll
+    for (int i = 0; i < TG_FC; ++i) { c0v[i] = a.c0[((size_t)b * a.F + f0 + i) * a.N + n]; dc0v[i] = 0.f; }
+    for (long long t = 0; t < a.T; ++t) {
+      float z[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        if (j < KG) {
+          const int k = j / a.G, g = j % a.G;
+          const size_t row = ((size_t)b * a.T + t) * a.G + g;
+          z[j] = (k == 0) ? a.X[row * a.N + n] : a.zx[((size_t)(k - 1) * a.B * a.T * a.G + row) * a.N + n];
+        } else z[j] = 0.f;
+      }
+      const float dlv = BWD ? a.dl[b * a.T + t] : 0.f;
+      float part = 0.f;
+#pragma unroll
+      for (int i = 0; i < TG_FC; ++i) {
+        float pre = c0v[i];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) if (j < KG) pre = fmaf(wA[i][j], z[j], pre);
+        const float u = tanhf(pre);
+        if (!BWD) part = fmaf(wg[i], u, part);
+        else {
+          dwg[i] = fmaf(dlv, u, dwg[i]);
+          const float dpu = dlv * wg[i] * (1.f - u * u);
+          dc0v[i] += dpu;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) if (j < KG) sA[i][j] = fmaf(dpu, z[j], sA[i][j]);
+        }
+      }
+      if (!BWD) {
+        part = warp_sum_f(part);
+        if (lane == 0) atomicAdd(a.logit + b * a.T + t, part);
+      }
+    }
+    if (BWD) {
+#pragma unroll
+      for (int i = 0; i < TG_FC; ++i) a.dc0[((size_t)b * a.F + f0 + i) * a.N + n] = dc0v[i];
+    }
+  }
+  if (BWD) {
+#pragma unroll
+    for (int i = 0; i < TG_FC; ++i) atomicAdd(a.dWg + (size_t)(f0 + i) * a.N + n, dwg[i]);
+#pragma unroll
+    for (int i = 0; i < TG_FC; ++i)
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        if (j < KG) {
+          const float v = warp_sum_f(sA[i][j]);
+          if (lane == 0) red[warp][i * 33 + j] = v;
+        }
+      }
+    __syncthreads();
+    for (int idx = tid; idx < TG_FC * KG; idx += 128) {
+      const int i = idx / KG, j = idx % KG;
+      atomicAdd(a.dA + (size_t)(f0 + i) * KG + j, red[0][i * 33 + j] + red[1][i * 33 + j] + red[2][i * 33 + j] + red[3][i * 33 + j]);
+    }
+  }
+}
+
+// g = sigmoid(logit + c)      /     dl = dg g (1-g), dc += sum dl
+__global__ void gate_sigmoid_kernel(const float* __restrict__ logit, const float* __restrict__ c, float* __restrict__ g, long long n) {
+  const float cv = c ? c[0] : 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    g[i] = 1.f / (1.f + expf(-(logit[i] + cv)));
+}
+__global__ void gate_dlogit_kernel(const float* __restrict__ dg, const float* __restrict__ g, float* __restrict__ dl, float* dc, long long n) {
+  __shared__ float red[32];
+  float s = 0.f;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) { const float v = g[i]; const float d = dg[i] * v * (1.f - v); dl[i] = d; s += d; }
+  s = warp_sum_f(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0 && dc) { float t = 0.f; for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w]; atomicAdd(dc, t); }
+}
+// out[f] += scale * sum_{b,n} in[b,f,n]
+__global__ void rowsum_bfn_kernel(const float* __restrict__ in, float* out, long long B, int F, int N, float scale) {
+  __shared__ float red[8];
+  for (long long item = blockIdx.x; item < B * F; item += gridDim.x) {
+    const int f = (int)(item % F);
+    const float* p = in + item * N;
+    float s = 0.f;
+    for (int n = threadIdx.x; n < N; n += blockDim.x) s += p[n];
+    s = warp_sum_f(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) { float t = 0.f; for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w]; atomicAdd(out + f, scale * t); }
+    __syncthreads();
+  }
+}
+
+}  // namespace tc
+}  // namespace gcrnn

@@ -65,6 +65,10 @@ int         gcrnn_abi_version(void);
 const char* gcrnn_last_error(void);
 /* number of CUDA kernels this library has launched in this process (bench.py's `gpu_launches`) */
 uint64_t    gcrnn_debug_launch_count(void);
+/* the dominant kernel on its own (unit tests, roofline timing): out = A @ S (backward=0) or A @ S^T (backward=1),
+ * A: device bf16 [M, N] row-major; out_bf16 / out_f32: device [M, N], either may be NULL.  Needs keep_dense. */
+int         gcrnn_debug_shift_gemm(const gcrnn_graph* g, int32_t backward, const void* A_bf16, int64_t M,
+                                   void* out_bf16, float* out_f32, void* stream);
 
 /* ---- graph -------------------------------------------------------------------------------------- */
 /* E operators in CSR, HOST arrays: rowptr[e] has N+1 entries, entry (i, colidx[p]) = S_e[i, j] = vals[p].
