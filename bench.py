@@ -1,0 +1,302 @@
+#!/usr/bin/env python
+"""bench.py — gated-GCRNN sequences/second, forward+backward (BASELINE.json metric).
+
+Workload (N=1): cfg3 of SURVEY.md §8d — synthetic dense graph N=1024 (density 0.3, S = W/lambda_max), F=64 state
+features, G=1 input feature, K=5 taps, T=64, global batch 4096 sequences, time-gated GGCRNNCell, random-init
+weights (reference init, seed 0), X ~ N(0,1), h0 = 0, dH = ones.  A "step" = forward + backward of the whole
+global batch (in micro-batches that fit HBM) + one all-reduce of the parameter-gradient bucket when N > 1
+(batch sharded over ranks: strong scaling, configs[3]).
+
+    python bench.py --gpus 1 --steps 3 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+    python bench.py --impl reference        # the reference algorithm on the host CPUs (oracle port), bounded sample
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_SEQ_FWD_BWD = 82.82e9      # SURVEY.md §8d, cfg3 (G=1): algorithmic flops per sequence, fwd+bwd
+CFG3 = dict(N=1024, F=64, G=1, K=5, T=64, B=4096, density=0.3)
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return dict(hbm=d['hbm_gbs'], bf16=d['bf16_tflops'], bf16_sustained=d['bf16_tflops_sustained'], src='measured')
+    return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, src='fallback')
+
+
+# ------------------------------------------------------------------------------------------------------
+# CPU arm: the reference algorithm (oracle port, fp64 as the reference scripts run it) on a bounded sample
+# ------------------------------------------------------------------------------------------------------
+def cpu_sample(cfg, Bs, Ts, repeats, warm=1):
+    import torch
+    from oracle import gcrnn_oracle as orc
+    import gated_gcrnns_b200 as gg
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    S = gg.graphs.dense_random(cfg['N'], cfg['density'], seed=0).double()
+    torch.manual_seed(0)
+    prev = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)
+    try:
+        p = orc.init_cell_params(cfg['G'], cfg['F'], cfg['K'], cfg['K'], cfg['N'], True, None, 1, True)
+    finally:
+        torch.set_default_dtype(prev)
+    X = torch.randn(Bs, Ts, cfg['G'], cfg['N'], dtype=torch.float64)
+    h0 = torch.zeros(Bs, cfg['F'], cfg['N'], dtype=torch.float64)
+    dH = torch.ones(Bs, Ts, cfg['F'], cfg['N'], dtype=torch.float64)
+    times = []
+    for i in range(warm + repeats):
+        t0 = time.perf_counter()
+        orc.cell_forward_backward(p, S, X, h0, dH, True, None)
+        dt = time.perf_counter() - t0
+        if i >= warm:
+            times.append(dt)
+    return times, cores
+
+
+def cpu_baseline_dict(cfg, times, cores, Bs, Ts):
+    best = min(times)
+    seqs = Bs / (best * cfg['T'] / Ts)          # linear extrapolation in T (recurrence cost is linear in B*T)
+    return dict(value=seqs, unit='sequences/s', cores=cores, kind='port',
+                sample=f'oracle port (fp64, torch CPU, {cores} threads) of the reference GGCRNNCell fwd+bwd on cfg3 shapes with '
+                       f'B={Bs}, T={Ts} of {cfg["T"]}; min of {len(times)} runs = {best:.3f} s, extrapolated linearly in T')
+
+
+def run_reference(args):
+    cfg = dict(CFG3)
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    Bs, Ts = args.cpu_batch, args.cpu_T
+    times, cores = cpu_sample(cfg, Bs, Ts, args.steps, warm=max(args.warmup, 1))
+    ms = 1e3 * statistics.mean(times)
+    seqs = Bs / (statistics.mean(times) * cfg['T'] / Ts)
+    cb = cpu_baseline_dict(cfg, times, cores, Bs, Ts)
+    cb['value'] = seqs
+    out = dict(impl='reference', metric='GCRNN sequences/sec fwd+bwd', value=seqs, unit='sequences/s', n_gpus=args.gpus,
+               steps=args.steps, warmup=args.warmup, ms_per_step=ms, higher_is_better=True, scaling='strong',
+               vs_baseline=None, dtype='f64', data='synthetic',
+               config=dict(workload='cfg3: dense N=1024 F=64 G=1 K=5 T=64 time-gated GGCRNNCell, global batch 4096',
+                           sample=f'B={Bs}, T={Ts} per step on the host CPUs'),
+               cpu_baseline=cb, e2e=dict(value=seqs, unit='sequences/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+               gpu_launches=0)
+    print(json.dumps(out), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------
+# clocks sampler
+# ------------------------------------------------------------------------------------------------------
+class Clocks(threading.Thread):
+    REASONS = {0x1: 'gpu_idle', 0x2: 'applications_clocks_setting', 0x4: 'sw_power_cap', 0x8: 'hw_slowdown',
+               0x10: 'sync_boost', 0x20: 'sw_thermal_slowdown', 0x40: 'hw_thermal_slowdown', 0x80: 'hw_power_brake_slowdown',
+               0x100: 'display_clock_setting'}
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.mask, self.stop_flag, self.max_mhz = index, [], 0, False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        while not self.stop_flag and self.nv is not None:
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                self.mask |= int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def result(self):
+        self.stop_flag = True
+        if self.nv is None or not self.samples:
+            return dict(sm_mhz=None, sm_max_mhz=self.max_mhz, reasons=['unavailable'])
+        reasons = [n for b, n in self.REASONS.items() if self.mask & b and n != 'gpu_idle']
+        return dict(sm_mhz=statistics.median(self.samples), sm_max_mhz=self.max_mhz, reasons=reasons)
+
+
+# ------------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import gated_gcrnns_b200 as gg
+    from gated_gcrnns_b200 import _lib, graph as ggraph
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    assert torch.cuda.is_available(), 'bench.py needs a GPU (no CPU fallback); use --impl reference for the CPU arm'
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    assert world == args.gpus, f'--gpus {args.gpus} but WORLD_SIZE={world}'
+
+    cfg = dict(CFG3)
+    cfg['B'] = args.batch
+    N, F, G, K, T = cfg['N'], cfg['F'], cfg['G'], cfg['K'], cfg['T']
+    lo, hi = gg.dist.shard_range(cfg['B'], rank, world)
+    Bl = hi - lo
+    mb = min(args.microbatch, Bl)
+    assert Bl % mb == 0, 'local batch must be a multiple of the micro-batch'
+    gg.set_precision(args.precision)
+    S = gg.graphs.dense_random(N, cfg['density'], seed=0)
+    torch.manual_seed(0)
+    cell = gg.GGCRNNCell(G, F, K, K, torch.tanh, True, None, 1, True)
+    cell.addGSO(S)
+    cell = cell.to(dev)
+    used = [dict(cell.named_parameters())[n] for _, _, n in gg.cell_param_slots(True, None, True)]
+    gen = torch.Generator(device='cpu').manual_seed(1234 + rank)
+    X_host = torch.randn(Bl, T, G, N, generator=gen).pin_memory()
+    h0_host = torch.zeros(mb, F, N).pin_memory()
+    X_dev = X_host.to(dev)
+    h0_dev = torch.zeros(mb, F, N, device=dev)
+    dH = torch.ones(mb, T, F, N, device=dev)
+    L = _lib.lib()
+
+    def step(host_inputs):
+        for p in used:
+            p.grad = None
+        for i in range(0, Bl, mb):
+            if host_inputs:
+                x = X_host[i:i + mb].to(dev, non_blocking=True)
+                h = h0_host.to(dev, non_blocking=True)
+            else:
+                x, h = X_dev[i:i + mb], h0_dev
+            H = cell(x, h)
+            torch.autograd.backward(H, dH)
+            del H
+        bucket = torch.cat([p.grad.reshape(-1) for p in used])
+        if world > 1:
+            dist.all_reduce(bucket)
+        if host_inputs:
+            return bucket.to('cpu', non_blocking=False)          # D2H read of the step's result
+        return bucket
+
+    def timed(host_inputs, steps, warmup):
+        for _ in range(warmup):
+            step(host_inputs)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        clk = Clocks(local)
+        clk.start()
+        l0 = L.gcrnn_debug_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step(host_inputs)
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        launches = L.gcrnn_debug_launch_count() - l0
+        c = clk.result()
+        t = torch.tensor([ms], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item(), launches, c
+
+    ms_dev, launches, clocks = timed(False, args.steps, args.warmup)
+    ms_e2e, _, _ = timed(True, args.steps, max(1, args.warmup - 2))
+    seqs = cfg['B'] * args.steps / (ms_dev * 1e-3)
+    seqs_e2e = cfg['B'] * args.steps / (ms_e2e * 1e-3)
+
+    # ---- roofline of the dominant kernel (tcgen05 shift GEMM), timed live with CUDA events on its stream -------------
+    pk = peaks()
+    roof = None
+    if args.precision != 'fp32':
+        g = ggraph.get(cell.S, dev, keep_dense=True)
+        R = mb * F
+        A = torch.randn(R, N, device=dev).to(torch.bfloat16)
+        out = torch.empty(R, N, dtype=torch.bfloat16, device=dev)
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        reps = 40
+
+        def one():
+            _lib.check(L.gcrnn_debug_shift_gemm(g.ptr, 0, C.c_void_p(A.data_ptr()), R, C.c_void_p(out.data_ptr()), C.c_void_p(0), st), 'gemm')
+        for _ in range(5):
+            one()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            one()
+        e1.record()
+        torch.cuda.synchronize()
+        t_k = e0.elapsed_time(e1) * 1e-3 / reps
+        ach = 2.0 * R * N * N / t_k / 1e12
+        step_ach = FLOP_PER_SEQ_FWD_BWD * seqs / world / 1e12
+        roof = dict(bound='tensor', achieved=ach, peak=pk['bf16'], unit='TFLOP/s', frac=ach / pk['bf16'], traffic=None,
+                    kernel=f'shift_gemm_kernel<256> [{R}x{N}]x[{N}x{N}] bf16, {t_k * 1e6:.1f} us/launch, peak = {pk["src"]} burst bf16',
+                    step_achieved=step_ach, step_peak=pk['bf16_sustained'], step_frac=step_ach / pk['bf16_sustained'],
+                    step_note='algorithmic 82.82 GFLOP/sequence fwd+bwd x sequences/s per GPU vs sustained bf16 peak (' + pk['src'] + ')')
+    else:
+        step_ach = FLOP_PER_SEQ_FWD_BWD * seqs / world / 1e12
+        roof = dict(bound='tensor', achieved=step_ach, peak=pk['bf16_sustained'], unit='TFLOP/s', frac=step_ach / pk['bf16_sustained'],
+                    traffic=None, kernel='fp32 sparse exact path (no tensor cores); whole-step algorithmic flops')
+
+    cb = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        times, cores = cpu_sample(dict(CFG3), args.cpu_batch, args.cpu_T, 2)
+        cb = cpu_baseline_dict(dict(CFG3), times, cores, args.cpu_batch, args.cpu_T)
+
+    if rank == 0:
+        out = dict(metric='GCRNN sequences/sec fwd+bwd', value=seqs, unit='sequences/s', n_gpus=world, steps=args.steps,
+                   warmup=args.warmup, ms_per_step=ms_dev / args.steps, higher_is_better=True, scaling='strong',
+                   vs_baseline=None, dtype='bf16' if args.precision != 'fp32' else 'f32', data='synthetic',
+                   config=dict(workload='cfg3: dense N=1024 F=64 G=1 K=5 T=64 time-gated GGCRNNCell fwd+bwd',
+                               global_batch=cfg['B'], per_gpu_batch=Bl, microbatch=mb, precision=args.precision,
+                               parallelism=f'dp{world} (batch sharded, one gradient all-reduce per step)',
+                               l2='inputs larger than L2 (X 1 GiB, H 8.6 GB per micro-batch); no explicit flush'),
+                   roofline=roof, cpu_baseline=cb, clocks=clocks,
+                   e2e=dict(value=seqs_e2e, unit='sequences/s', h2d_bytes_per_step=int(X_host.numel() * 4 + (Bl // mb) * h0_host.numel() * 4),
+                            d2h_bytes_per_step=int(sum(p.numel() for p in used) * 4), ms_per_step=ms_e2e / args.steps),
+                   gpu_launches=int(launches))
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--batch', type=int, default=CFG3['B'], help='global batch (sequences per step); default = cfg3')
+    ap.add_argument('--microbatch', type=int, default=512)
+    ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
+    ap.add_argument('--cpu-batch', type=int, default=4)
+    ap.add_argument('--cpu-T', type=int, default=4)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -59,7 +59,263 @@ void shift_gemm(const gcrnn_graph* g, bool backward, const __nv_bfloat16* A, lon
   }
 }
 
+
+// ---- launch helpers -------------------------------------------------------------------------------------------
+static void launched() { ++g_launches; CUDA_OK(cudaGetLastError()); }
+static void cvt_bf16(const float* in, __nv_bfloat16* out, __nv_bfloat16* out_lo, long long n, cudaStream_t st) {
+  GCRNN_CHECK(n % 4 == 0, "cvt_bf16: length must be a multiple of 4");
+  cvt_bf16_kernel<<<(unsigned)std::min<long long>((n / 4 + 255) / 256, 148 * 16), 256, 0, st>>>(in, out, out_lo, n / 4);
+  launched();
+}
+static void prep_weight(const float* W, __nv_bfloat16* out, int F, int K, int G, int ld, int mode, cudaStream_t st) {
+  CUDA_OK(cudaMemsetAsync(out, 0, (size_t)64 * ld * sizeof(__nv_bfloat16), st));
+  prep_weight_kernel<<<(F * K * G + 255) / 256, 256, 0, st>>>(W, out, F, K, G, ld, mode);
+  launched();
+}
+
+struct TcDims {
+  int N, F, G, Kin, Kst, sms;
+  long long B, T, R, RX, BT;
+  bool tg, bias;
+};
+static TcDims tc_dims(const gcrnn_cell* c, int64_t B, int64_t T) {
+  TcDims d;
+  d.N = c->g->N; d.F = c->d.F; d.G = c->d.G; d.Kin = c->d.Kin; d.Kst = c->d.Kst;
+  d.B = B; d.T = T; d.R = B * d.F; d.RX = B * T * d.G; d.BT = B * T;
+  d.tg = c->d.time_gating != 0; d.bias = c->d.bias != 0;
+  GCRNN_CHECK(c->d.E == 1 && c->d.spatial_gating == GCRNN_SPATIAL_NONE, "tensor-core path: E == 1, no spatial gating");
+  GCRNN_CHECK(d.F % 16 == 0 && d.F <= 64, "tensor-core path: F must be a multiple of 16 and <= 64 (F=%d)", d.F);
+  GCRNN_CHECK(d.N % 128 == 0, "tensor-core path: N %% 128 == 0 (N=%d)", d.N);
+  GCRNN_CHECK(d.Kin * d.G <= 32, "tensor-core path: Kin*G <= 32 (got %d); use the fp32 path", d.Kin * d.G);
+  GCRNN_CHECK(d.Kst >= 1 && d.Kst <= WG_MAXK && d.Kst + 2 <= 8, "tensor-core path: Kst <= %d", WG_MAXK);
+  GCRNN_CHECK(B > 0 && T > 0, "empty batch or sequence");
+  d.sms = 0;
+  return d;
+}
+
+struct TcSaved {
+  float* zx;   // [Kin-1][RX][N]
+  float* gt;   // [2][B][T]
+  void layout(Arena& a, const TcDims& d) {
+    zx = a.get<float>((size_t)(d.Kin - 1) * d.RX * d.N);
+    gt = d.tg ? a.get<float>(2 * d.BT) : nullptr;
+  }
+};
+
+// z_k = z_{k-1} @ S (forward) or @ S^T (backward), k = 1..K-1, bf16 slabs [K-1][rows][N]
+static void chain(const gcrnn_graph* g, bool backward, const __nv_bfloat16* z0, __nv_bfloat16* zc, int K, long long rows, cudaStream_t st) {
+  const __nv_bfloat16* prev = z0;
+  for (int k = 1; k < K; ++k) {
+    __nv_bfloat16* out = zc + (size_t)(k - 1) * rows * g->N;
+    shift_gemm(g, backward, prev, rows, out, nullptr, st);
+    prev = out;
+  }
+}
+
+// slabs [z0hi, z0hi, z0lo, z1, ..., z_{K-1}] (see prep_weight_kernel)
+static ContractArgs contract_base(const TcDims& d, const __nv_bfloat16* W, int ldw, const __nv_bfloat16* z0, const __nv_bfloat16* z0_lo,
+                                  const __nv_bfloat16* zc) {
+  ContractArgs a{};
+  a.W = W; a.ldw = ldw; a.K = d.Kst + 2; a.C = d.F; a.M = d.F; a.N = d.N; a.B = d.B;
+  a.slab[0] = z0; a.slab[1] = z0; a.slab[2] = z0_lo;
+  for (int k = 1; k < d.Kst; ++k) a.slab[k + 2] = zc + (size_t)(k - 1) * d.R * d.N;
+  return a;
+}
+
+static void gate_launch(bool bwd, const GateArgs& ga, const TcDims& d, cudaStream_t st) {
+  dim3 grid(d.N / 128, d.F / TG_FC, ga.bsplit);
+  const int KG = d.Kin * d.G;
+  if (!bwd) { if (KG <= 8) time_gate_kernel<false, 8><<<grid, 128, 0, st>>>(ga); else time_gate_kernel<false, 32><<<grid, 128, 0, st>>>(ga); }
+  else      { if (KG <= 8) time_gate_kernel<true, 8><<<grid, 128, 0, st>>>(ga);  else time_gate_kernel<true, 32><<<grid, 128, 0, st>>>(ga); }
+  launched();
+}
+
 }  // namespace tc
+
+using namespace tc;
+
+size_t cell_forward_tc(const gcrnn_cell* cell, const gcrnn_cell_params* p, const float* X, const float* h0, float* H,
+                       void* saved, size_t savedb, size_t* saved_used, void* ws, size_t wsb, int64_t B, int64_t T,
+                       cudaStream_t st) {
+  TcDims d = tc_dims(cell, B, T);
+  const gcrnn_graph* g = cell->g;
+  Arena a(ws, wsb);
+  TcSaved s;
+  { Arena sa(saved, savedb); s.layout(sa, d); if (saved_used) *saved_used = sa.off; }
+  GCRNN_CHECK(a.dry() || saved, "forward needs the `saved` buffer");
+  const int ldw = (d.Kst + 2) * d.F + 8;
+  __nv_bfloat16* xb0 = a.get<__nv_bfloat16>((size_t)d.RX * d.N);
+  __nv_bfloat16* xb1 = a.get<__nv_bfloat16>((size_t)d.RX * d.N);
+  __nv_bfloat16* hb0 = a.get<__nv_bfloat16>((size_t)d.R * d.N);
+  __nv_bfloat16* hb1 = a.get<__nv_bfloat16>((size_t)d.R * d.N);
+  __nv_bfloat16* hl0 = a.get<__nv_bfloat16>((size_t)d.R * d.N);
+  __nv_bfloat16* hl1 = a.get<__nv_bfloat16>((size_t)d.R * d.N);
+  __nv_bfloat16* zb = a.get<__nv_bfloat16>((size_t)(d.Kst - 1) * d.R * d.N);
+  __nv_bfloat16* Wb = a.get<__nv_bfloat16>((size_t)64 * ldw);
+  float* c0 = d.tg ? a.get<float>((size_t)d.R * d.N) : nullptr;
+  float* logit = d.tg ? a.get<float>(2 * d.BT) : nullptr;
+  if (a.dry()) return a.off;
+  d.sms = num_sms(g->device);
+  const long long FN = (long long)d.F * d.N, GN = (long long)d.G * d.N;
+
+  // ---- x_t S^k for every (b, t): one batched chain (rows = B*T*G) ------------------------------------------------
+  if (d.Kin > 1) {
+    cvt_bf16(X, xb0, nullptr, d.RX * d.N, st);
+    __nv_bfloat16* cur = xb0; __nv_bfloat16* nxt = xb1;
+    for (int k = 1; k < d.Kin; ++k) {
+      shift_gemm(g, false, cur, d.RX, (k < d.Kin - 1) ? nxt : nullptr, s.zx + (size_t)(k - 1) * d.RX * d.N, st);
+      std::swap(cur, nxt);
+    }
+  }
+  cvt_bf16(h0, hb0, hl0, d.R * d.N, st);
+  // ---- time gates (graphML.py:2357-2374): depend on (x_t, h0) only -> all (b, t) at once ---------------------------
+  if (d.tg) {
+    chain(g, false, hb0, zb, d.Kst, d.R, st);
+    CUDA_OK(cudaMemsetAsync(logit, 0, 2 * d.BT * sizeof(float), st));
+    for (int gi = 0; gi < 2; ++gi) {
+      prep_weight(p->t_weight_B[gi], Wb, d.F, d.Kst, d.F, ldw, 0, st);
+      ContractArgs ca = contract_base(d, Wb, ldw, hb0, hl0, zb);
+      ca.out_f32 = c0; ca.out_bstride = FN; ca.bias = p->t_bias[gi]; ca.bias_scale = 2.f;   // bias enters twice (:2421-2422)
+      launch_contract<EPI_PLAIN>(ca, d.sms, st);
+      GateArgs ga{};
+      ga.A = p->t_weight_A[gi]; ga.Kin = d.Kin; ga.G = d.G; ga.F = d.F; ga.N = d.N; ga.B = d.B; ga.T = d.T;
+      ga.X = X; ga.zx = s.zx; ga.c0 = c0; ga.Wg = p->t_mlp_w[gi]; ga.logit = logit + gi * d.BT;
+      ga.bsplit = (int)std::min<long long>(d.B, 16);
+      gate_launch(false, ga, d, st);
+      gate_sigmoid_kernel<<<(unsigned)((d.BT + 255) / 256), 256, 0, st>>>(logit + gi * d.BT, p->t_mlp_b[gi], s.gt + gi * d.BT, d.BT);
+      launched();
+    }
+  }
+  // ---- the recurrence -------------------------------------------------------------------------------------------
+  prep_weight(p->weight_B, Wb, d.F, d.Kst, d.F, ldw, 0, st);
+  __nv_bfloat16* hb[2] = {hb0, hb1};
+  __nv_bfloat16* hl[2] = {hl0, hl1};
+  for (long long t = 0; t < d.T; ++t) {
+    const __nv_bfloat16* hprev = hb[t & 1];
+    if (!(t == 0 && d.tg)) chain(g, false, hprev, zb, d.Kst, d.R, st);      // at t = 0 the gates' h0 chain is still in zb
+    ContractArgs ca = contract_base(d, Wb, ldw, hprev, hl[t & 1], zb);
+    ca.out_f32 = H + t * FN; ca.out_bstride = d.T * FN; ca.out_bf16 = hb[(t + 1) & 1]; ca.out_bf16_lo = hl[(t + 1) & 1];
+    ca.bias = p->bias;
+    ca.gi = d.tg ? s.gt + t : nullptr; ca.gf = d.tg ? s.gt + d.BT + t : nullptr; ca.gate_stride = d.T;
+    ca.A = p->weight_A; ca.Kin = d.Kin; ca.G = d.G;
+    ca.x0 = X + t * GN; ca.x0_bstride = d.T * GN;
+    ca.zx = s.zx + t * GN; ca.zx_kstride = d.RX * d.N; ca.zx_bstride = d.T * GN;
+    launch_contract<EPI_FWD>(ca, d.sms, st);
+  }
+  return a.off;
+}
+
+size_t cell_backward_tc(const gcrnn_cell* cell, const gcrnn_cell_params* p, const float* X, const float* h0,
+                        const float* H, const float* dH, const void* saved, size_t savedb,
+                        const gcrnn_cell_params* gr, float* dX, float* dh0, void* ws, size_t wsb, int64_t B,
+                        int64_t T, cudaStream_t st) {
+  TcDims d = tc_dims(cell, B, T);
+  const gcrnn_graph* g = cell->g;
+  Arena a(ws, wsb);
+  TcSaved s;
+  { Arena sa(const_cast<void*>(saved), savedb); s.layout(sa, d); }
+  GCRNN_CHECK(a.dry() || saved, "backward needs the buffer written by forward");
+  const int ldw = (d.Kst + 2) * d.F + 8;
+  const int max_sms = 256;
+  __nv_bfloat16* vb0 = a.get<__nv_bfloat16>((size_t)d.R * d.N);
+  __nv_bfloat16* vl0 = a.get<__nv_bfloat16>((size_t)d.R * d.N);
+  __nv_bfloat16* vb = a.get<__nv_bfloat16>((size_t)(d.Kst - 1) * d.R * d.N);
+  float* dhrec = a.get<float>((size_t)d.R * d.N);
+  __nv_bfloat16* WTb = a.get<__nv_bfloat16>((size_t)64 * ldw);
+  float* part = a.get<float>((size_t)max_sms * d.Kst * d.F * d.F);
+  float *dgt = nullptr, *c0 = nullptr, *dc0 = nullptr, *dl = nullptr;
+  __nv_bfloat16* Wb = nullptr;
+  if (d.tg) {
+    dgt = a.get<float>(2 * d.BT); c0 = a.get<float>((size_t)d.R * d.N); dc0 = a.get<float>((size_t)d.R * d.N);
+    dl = a.get<float>(d.BT); Wb = a.get<__nv_bfloat16>((size_t)64 * ldw);
+  }
+  if (a.dry()) return a.off;
+  GCRNN_CHECK(dX == nullptr, "the tensor-core path does not produce dX (the reference never asks for it: train_rnn.py:256); "
+                             "use precision fp32 for input gradients");
+  d.sms = num_sms(g->device);
+  GCRNN_CHECK(d.sms <= max_sms, "unexpected SM count %d", d.sms);
+  const long long FN = (long long)d.F * d.N, GN = (long long)d.G * d.N;
+  const size_t part_bytes = (size_t)d.sms * d.Kst * d.F * d.F * sizeof(float);
+
+  auto wgrad = [&](const float* hsrc, long long hstride, const float* scale, long long sstride) {
+    WgradArgs w{};
+    w.v0 = vb0; w.vc = vb; w.h = hsrc; w.h_bstride = hstride; w.scale = scale; w.scale_stride = sstride;
+    w.part = part; w.K = d.Kst; w.F = d.F; w.N = d.N; w.B = d.B;
+    const size_t sm = ((size_t)2 * d.Kst * 64 * WG_LD + (size_t)2 * 64 * WG_LD) * sizeof(__nv_bfloat16);
+    CUDA_OK(cudaFuncSetAttribute(wgrad_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    wgrad_mma_kernel<<<d.sms, 256, sm, st>>>(w);
+    launched();
+  };
+  auto wgrad_flush = [&](float* dW) {
+    if (dW) { wgrad_reduce_kernel<<<(d.Kst * d.F * d.F + 255) / 256, 256, 0, st>>>(part, dW, d.sms, d.Kst, d.F); launched(); }
+    CUDA_OK(cudaMemsetAsync(part, 0, part_bytes, st));
+  };
+
+  CUDA_OK(cudaMemsetAsync(part, 0, part_bytes, st));
+  if (d.tg) CUDA_OK(cudaMemsetAsync(dgt, 0, 2 * d.BT * sizeof(float), st));
+  prep_weight(p->weight_B, WTb, d.F, d.Kst, d.F, ldw, 1, st);
+
+  // ---- reverse-time sweep -------------------------------------------------------------------------------------------
+  for (long long t = d.T - 1; t >= 0; --t) {
+    const float* hprev = t > 0 ? H + (t - 1) * FN : h0;
+    const long long hstride = t > 0 ? d.T * FN : FN;
+    DpreArgs da{};
+    da.dH = dH + t * FN; da.dH_bstride = d.T * FN; da.Ht = H + t * FN; da.H_bstride = d.T * FN;
+    da.dhrec = (t == d.T - 1) ? nullptr : dhrec; da.v0 = vb0; da.v0_lo = vl0;
+    da.gi = d.tg ? s.gt + t : nullptr; da.gf = d.tg ? s.gt + d.BT + t : nullptr; da.gate_stride = d.T;
+    da.A = p->weight_A; da.bias = p->bias; da.Kin = d.Kin; da.G = d.G; da.F = d.F; da.N = d.N;
+    da.x0 = X + t * GN; da.x0_bstride = d.T * GN; da.zx = s.zx + t * GN; da.zx_kstride = d.RX * d.N; da.zx_bstride = d.T * GN;
+    da.dgi = d.tg ? dgt + t : nullptr; da.dgf = d.tg ? dgt + d.BT + t : nullptr;
+    da.dA = gr->weight_A; da.dbias = gr->bias; da.B = d.B;
+    dpre_kernel<<<(unsigned)std::min<long long>(d.B * (d.F / DP_FC), 148 * 8), 256, 0, st>>>(da);
+    launched();
+    chain(g, true, vb0, vb, d.Kst, d.R, st);
+    ContractArgs ca = contract_base(d, WTb, ldw, vb0, vl0, vb);
+    ca.out_f32 = dhrec; ca.out_bstride = FN; ca.gf = d.tg ? s.gt + d.BT + t : nullptr; ca.gate_stride = d.T;
+    ca.hprev = hprev; ca.hprev_bstride = hstride; ca.dgf = d.tg ? dgt + d.BT + t : nullptr; ca.accumulate = 0;
+    launch_contract<EPI_BWD>(ca, d.sms, st);
+    if (gr->weight_B) wgrad(hprev, hstride, d.tg ? s.gt + d.BT + t : nullptr, d.T);
+  }
+  wgrad_flush(gr->weight_B);
+
+  // ---- time gates, batched over (b, t) -----------------------------------------------------------------------------------
+  if (d.tg) {
+    __nv_bfloat16* hb0 = vb0;                  // reuse: bf16 h0 and its chain live where the v slabs were
+    for (int gi = 0; gi < 2; ++gi) {
+      cvt_bf16(h0, hb0, vl0, d.R * d.N, st);
+      chain(g, false, hb0, vb, d.Kst, d.R, st);
+      prep_weight(p->t_weight_B[gi], Wb, d.F, d.Kst, d.F, ldw, 0, st);
+      ContractArgs cc = contract_base(d, Wb, ldw, hb0, vl0, vb);
+      cc.out_f32 = c0; cc.out_bstride = FN; cc.bias = p->t_bias[gi]; cc.bias_scale = 2.f;
+      launch_contract<EPI_PLAIN>(cc, d.sms, st);
+      gate_dlogit_kernel<<<1, 1024, 0, st>>>(dgt + gi * d.BT, s.gt + gi * d.BT, dl, gr->t_mlp_b[gi], d.BT);
+      launched();
+      GateArgs ga{};
+      ga.A = p->t_weight_A[gi]; ga.Kin = d.Kin; ga.G = d.G; ga.F = d.F; ga.N = d.N; ga.B = d.B; ga.T = d.T;
+      ga.X = X; ga.zx = s.zx; ga.c0 = c0; ga.Wg = p->t_mlp_w[gi]; ga.dl = dl;
+      ga.dWg = gr->t_mlp_w[gi]; ga.dc0 = dc0; ga.dA = gr->t_weight_A[gi];
+      ga.bsplit = (int)std::min<long long>(d.B, 16);
+      GCRNN_CHECK(ga.dWg && ga.dA, "time-gate gradient buffers missing");
+      gate_launch(true, ga, d, st);
+      if (gr->t_bias[gi]) {
+        rowsum_bfn_kernel<<<(unsigned)std::min<long long>(d.R, 148 * 8), 256, 0, st>>>(dc0, gr->t_bias[gi], d.B, d.F, d.N, 2.f);
+        launched();
+      }
+      // h0 path of the sub-cell: v_k = dc0 (S^T)^k ; dB_g,k = v_k h0^T ; dh0 += sum_k B_g,k^T v_k
+      cvt_bf16(dc0, vb0, vl0, d.R * d.N, st);
+      chain(g, true, vb0, vb, d.Kst, d.R, st);
+      if (gr->t_weight_B[gi]) { wgrad(h0, FN, nullptr, 0); wgrad_flush(gr->t_weight_B[gi]); }
+      if (dh0) {
+        prep_weight(p->t_weight_B[gi], Wb, d.F, d.Kst, d.F, ldw, 1, st);
+        ContractArgs cb = contract_base(d, Wb, ldw, vb0, vl0, vb);
+        cb.out_f32 = dhrec; cb.out_bstride = FN; cb.hprev = h0; cb.hprev_bstride = FN; cb.accumulate = 1;
+        launch_contract<EPI_BWD>(cb, d.sms, st);
+      }
+    }
+  }
+  if (dh0) CUDA_OK(cudaMemcpyAsync(dh0, dhrec, (size_t)d.R * d.N * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return a.off;
+}
 
 void tc_prepare_graph(gcrnn_graph* g, const float* S) {
   const int N = g->N;

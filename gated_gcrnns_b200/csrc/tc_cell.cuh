@@ -43,25 +43,41 @@ __device__ __forceinline__ float warp_sum_f(float v) {
 }
 
 // ---- fp32 -> bf16 ---------------------------------------------------------------------------------------------
-__global__ void cvt_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n4) {
+// x = hi + lo with hi = bf16(x), lo = bf16(x - hi): two bf16 slabs carry ~16 mantissa bits of the fp32 value
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16(x);
+  lo = __float2bfloat16(x - __bfloat162float(hi));
+}
+__global__ void cvt_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ out_lo, long long n4) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     const float4 v = reinterpret_cast<const float4*>(in)[i];
-    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
-    uint2 u; u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
-    reinterpret_cast<uint2*>(out)[i] = u;
+    __nv_bfloat16 h[4], l[4];
+    split_bf16(v.x, h[0], l[0]); split_bf16(v.y, h[1], l[1]); split_bf16(v.z, h[2], l[2]); split_bf16(v.w, h[3], l[3]);
+    reinterpret_cast<uint2*>(out)[i] = *reinterpret_cast<uint2*>(h);
+    if (out_lo) reinterpret_cast<uint2*>(out_lo)[i] = *reinterpret_cast<uint2*>(l);
   }
 }
 
 // ---- weight preparation: W[f, k, g] fp32 -> bf16 [rows][ld] ------------------------------------------------------
 // mode 0: out[f][k*G + g] = W[f,k,g]          (forward contraction, rows = output features)
 // mode 1: out[g][k*F + f] = W[f,k,g]          (data-gradient contraction, rows = input features)
+// Tap 0 (the unshifted term, by far the largest) is carried as hi/lo pairs on BOTH operands:
+//   W0 z0 ~= W0hi z0hi + W0lo z0hi + W0hi z0lo, i.e. slab order [z0hi, z0hi, z0lo, z1, ..., z_{K-1}] against
+//   weight columns          [W0hi, W0lo, W0hi, W1, ..., W_{K-1}]   (K + 2 slabs of C channels each).
 __global__ void prep_weight_kernel(const float* __restrict__ W, __nv_bfloat16* __restrict__ out, int F, int K, int G, int ld, int mode) {
   const int total = F * K * G;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int g = i % G, k = (i / G) % K, f = i / (G * K);
     const float v = W[i];
-    if (mode == 0) out[f * ld + k * G + g] = __float2bfloat16(v);
-    else out[g * ld + k * F + f] = __float2bfloat16(v);
+    const int row = mode == 0 ? f : g, col = mode == 0 ? g : f, C = mode == 0 ? G : F;
+    __nv_bfloat16* o = out + (size_t)row * ld + col;
+    if (k == 0) {
+      __nv_bfloat16 hi, lo;
+      split_bf16(v, hi, lo);
+      o[0] = hi; o[C] = lo; o[2 * C] = hi;
+    } else {
+      o[(size_t)(k + 2) * C] = __float2bfloat16(v);
+    }
   }
 }
 
@@ -75,16 +91,16 @@ constexpr int CT_THREADS = 256;
 enum { EPI_PLAIN = 0, EPI_FWD = 1, EPI_BWD = 2 };
 
 struct ContractArgs {
-  const __nv_bfloat16* W;    // [M][ldw] bf16
-  const __nv_bfloat16* z0;   // slab 0            [B][C][N]
-  const __nv_bfloat16* zc;   // slabs 1..K-1      [K-1][B][C][N]
+  const __nv_bfloat16* W;    // [M][ldw] bf16, columns = slab-major
+  const __nv_bfloat16* slab[8];   // K slabs, each [B][C][N] bf16 (see prep_weight_kernel for the order)
   int K, C, M, N, ldw;
   long long B;
   // EPI_PLAIN: out_f32[b,m,n] = acc + bias_scale * bias[m]
   // EPI_FWD  : h = tanh(gi (a + bias) + gf (acc + bias)), a = sum_{k,g} A[m,k,g] zx_k[(b,t,g), n]
   // EPI_BWD  : dgf[b] += <acc, hprev[b]> ; out_f32[b,m,n] = gf[b] * acc (+ out_f32 if accumulate)
   float* out_f32; long long out_bstride;      // sample stride of out_f32 (H uses T*F*N)
-  __nv_bfloat16* out_bf16;                    // [B][M][N] or null
+  __nv_bfloat16* out_bf16;                    // [B][M][N] or null: hi part of the new state
+  __nv_bfloat16* out_bf16_lo;                 // lo part
   const float* bias; float bias_scale;
   const float* gi; const float* gf; long long gate_stride;     // gate value of sample b at gi[b*gate_stride]
   const float* A; int Kin, G;                                   // [M][Kin][G] fp32
@@ -128,7 +144,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) contract_mma_kernel(const Contr
     for (int i = tid; i < KK * 8; i += CT_THREADS) {
       const int row = i >> 3, ch = i & 7;
       const int k = row / a.C, c = row % a.C;
-      const __nv_bfloat16* src = (k == 0 ? a.z0 : a.zc + (size_t)(k - 1) * a.B * a.C * a.N) + ((size_t)(b * a.C + c) * a.N + n0 + ch * 8);
+      const __nv_bfloat16* src = a.slab[k] + ((size_t)(b * a.C + c) * a.N + n0 + ch * 8);
       cp_async16(smem_u32(dst + row * CT_ZLD + ch * 8), src);
     }
   };
@@ -202,7 +218,11 @@ __global__ void __launch_bounds__(CT_THREADS, 1) contract_mma_kernel(const Contr
           v0 = tanhf(vgi * (ax[hh][0] + bb) + vgf * (v0 + bb));
           v1 = tanhf(vgi * (ax[hh][1] + bb) + vgf * (v1 + bb));
           *reinterpret_cast<float2*>(a.out_f32 + b * a.out_bstride + (size_t)m * a.N + n) = make_float2(v0, v1);
-          *reinterpret_cast<__nv_bfloat162*>(a.out_bf16 + ((size_t)b * a.M + m) * a.N + n) = __floats2bfloat162_rn(v0, v1);
+          __nv_bfloat16 h0, l0, h1, l1;
+          split_bf16(v0, h0, l0); split_bf16(v1, h1, l1);
+          const size_t oo = ((size_t)b * a.M + m) * a.N + n;
+          *reinterpret_cast<__nv_bfloat162*>(a.out_bf16 + oo) = __halves2bfloat162(h0, h1);
+          *reinterpret_cast<__nv_bfloat162*>(a.out_bf16_lo + oo) = __halves2bfloat162(l0, l1);
         } else {
           const float2 hp = *reinterpret_cast<const float2*>(a.hprev + b * a.hprev_bstride + (size_t)m * a.N + n);
           part = fmaf(v0, hp.x, fmaf(v1, hp.y, part));
@@ -377,7 +397,8 @@ struct DpreArgs {
   const float* dH; long long dH_bstride;        // dH[b, t]  : [F][N] at dH + b*bstride
   const float* Ht; long long H_bstride;         // h_t[b]
   const float* dhrec;                           // [B][F][N] or null (t = T-1)
-  __nv_bfloat16* v0;                            // out: bf16 dpre [B][F][N]
+  __nv_bfloat16* v0;                            // out: bf16 dpre [B][F][N] (hi part)
+  __nv_bfloat16* v0_lo;                         // lo part
   const float* gi; const float* gf; long long gate_stride;
   const float* A; const float* bias; int Kin, G, F, N;
   const float* x0; long long x0_bstride; const float* zx; long long zx_kstride, zx_bstride;
@@ -397,7 +418,7 @@ __global__ void __launch_bounds__(256) dpre_kernel(const DpreArgs a) {
     const long long b = item / fgroups;
     const int f0 = (int)(item % fgroups) * DP_FC;
     const float vgi = a.gi ? a.gi[b * a.gate_stride] : 1.f;
-    float s_dp[DP_FC], s_gi = 0.f;
+    float s_dp[DP_FC];
     float s_a[DP_FC];        // only used when KG == 1..: generic path accumulates into smem below
 #pragma unroll
     for (int i = 0; i < DP_FC; ++i) { s_dp[i] = 0.f; s_a[i] = 0.f; }
@@ -428,7 +449,10 @@ __global__ void __launch_bounds__(256) dpre_kernel(const DpreArgs a) {
           if (a.dhrec) dh += a.dhrec[((size_t)b * a.F) * a.N + o];
           const float dp = dh * (1.f - hv * hv);
           if (kg0 == 0) {
-            a.v0[((size_t)b * a.F) * a.N + o] = __float2bfloat16(dp);
+            __nv_bfloat16 hi, lo;
+            split_bf16(dp, hi, lo);
+            a.v0[((size_t)b * a.F) * a.N + o] = hi;
+            a.v0_lo[((size_t)b * a.F) * a.N + o] = lo;
             s_dp[i] += dp;
           }
           float ax = 0.f;
@@ -478,7 +502,7 @@ __global__ void __launch_bounds__(256) dpre_kernel(const DpreArgs a) {
       if (a.dgf) atomicAdd(a.dgf + b * a.gate_stride, bb * sdp);
     }
     __syncthreads();
-    (void)s_gi;
+
   }
 }
 
@@ -487,7 +511,7 @@ __global__ void __launch_bounds__(256) dpre_kernel(const DpreArgs a) {
 //   u = tanh(sum_{k,g} A_g[f,k,g] zx_k + c0[b,f,n]),   logit[b,t] = sum_{f,n} Wg[f,n] u
 // CTA = (n-tile of 128, chunk of TG_FC features, b-split); thread = one n.
 // =====================================================================================================
-constexpr int TG_FC = 4;
+constexpr int TG_FC = 8;
 struct GateArgs {
   const float* A; int Kin, G, F, N; long long B, T;
   const float* X;                 // [B,T,G,N]
@@ -502,27 +526,28 @@ struct GateArgs {
   int bsplit;
 };
 
-template <bool BWD>
+template <bool BWD, int KGMAX>
 __global__ void __launch_bounds__(128) time_gate_kernel(const GateArgs a) {
-  __shared__ float red[4][TG_FC * 33];
+  __shared__ float red[4][TG_FC * (KGMAX + 1)];
+  __shared__ float red1[4];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n = blockIdx.x * 128 + tid;
   const int f0 = blockIdx.y * TG_FC;
   const int KG = a.Kin * a.G;
   const long long bchunk = (a.B + a.bsplit - 1) / a.bsplit;
   const long long b_lo = blockIdx.z * bchunk, b_hi = min(a.B, b_lo + bchunk);
-  float wA[TG_FC][32];
+  float wA[TG_FC][KGMAX];
 #pragma unroll
   for (int i = 0; i < TG_FC; ++i)
 #pragma unroll
-    for (int j = 0; j < 32; ++j) wA[i][j] = (j < KG) ? a.A[(size_t)(f0 + i) * KG + j] : 0.f;
-  float wg[TG_FC], dwg[TG_FC], sA[TG_FC][32];
+    for (int j = 0; j < KGMAX; ++j) wA[i][j] = (j < KG) ? a.A[(size_t)(f0 + i) * KG + j] : 0.f;
+  float wg[TG_FC], dwg[TG_FC], sA[BWD ? TG_FC : 1][BWD ? KGMAX : 1];
 #pragma unroll
   for (int i = 0; i < TG_FC; ++i) {
     wg[i] = a.Wg[(size_t)(f0 + i) * a.N + n]; dwg[i] = 0.f;
     if (BWD) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) sA[i][j] = 0.f;
+      for (int j = 0; j < KGMAX; ++j) sA[BWD ? i : 0][BWD ? j : 0] = 0.f;
     }
   }
   for (long long b = b_lo; b < b_hi; ++b) {
@@ -530,9 +555,9 @@ __global__ void __launch_bounds__(128) time_gate_kernel(const GateArgs a) {
 #pragma unroll
     for (int i = 0; i < TG_FC; ++i) { c0v[i] = a.c0[((size_t)b * a.F + f0 + i) * a.N + n]; dc0v[i] = 0.f; }
     for (long long t = 0; t < a.T; ++t) {
-      float z[32];
+      float z[KGMAX];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
+      for (int j = 0; j < KGMAX; ++j) {
         if (j < KG) {
           const int k = j / a.G, g = j % a.G;
           const size_t row = ((size_t)b * a.T + t) * a.G + g;
@@ -545,7 +570,7 @@ __global__ void __launch_bounds__(128) time_gate_kernel(const GateArgs a) {
       for (int i = 0; i < TG_FC; ++i) {
         float pre = c0v[i];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) if (j < KG) pre = fmaf(wA[i][j], z[j], pre);
+        for (int j = 0; j < KGMAX; ++j) pre = fmaf(wA[i][j], z[j], pre);
         const float u = tanhf(pre);
         if (!BWD) part = fmaf(wg[i], u, part);
         else {
@@ -553,12 +578,15 @@ __global__ void __launch_bounds__(128) time_gate_kernel(const GateArgs a) {
           const float dpu = dlv * wg[i] * (1.f - u * u);
           dc0v[i] += dpu;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) if (j < KG) sA[i][j] = fmaf(dpu, z[j], sA[i][j]);
+          for (int j = 0; j < KGMAX; ++j) sA[BWD ? i : 0][BWD ? j : 0] = fmaf(dpu, z[j], sA[BWD ? i : 0][BWD ? j : 0]);
         }
       }
       if (!BWD) {
         part = warp_sum_f(part);
-        if (lane == 0) atomicAdd(a.logit + b * a.T + t, part);
+        if (lane == 0) red1[warp] = part;
+        __syncthreads();
+        if (tid == 0) atomicAdd(a.logit + b * a.T + t, red1[0] + red1[1] + red1[2] + red1[3]);
+        __syncthreads();
       }
     }
     if (BWD) {
@@ -572,16 +600,15 @@ __global__ void __launch_bounds__(128) time_gate_kernel(const GateArgs a) {
 #pragma unroll
     for (int i = 0; i < TG_FC; ++i)
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        if (j < KG) {
-          const float v = warp_sum_f(sA[i][j]);
-          if (lane == 0) red[warp][i * 33 + j] = v;
-        }
+      for (int j = 0; j < KGMAX; ++j) {
+        const float v = warp_sum_f(sA[BWD ? i : 0][BWD ? j : 0]);
+        if (lane == 0) red[warp][i * (KGMAX + 1) + j] = v;
       }
     __syncthreads();
     for (int idx = tid; idx < TG_FC * KG; idx += 128) {
       const int i = idx / KG, j = idx % KG;
-      atomicAdd(a.dA + (size_t)(f0 + i) * KG + j, red[0][i * 33 + j] + red[1][i * 33 + j] + red[2][i * 33 + j] + red[3][i * 33 + j]);
+      const int o = i * (KGMAX + 1) + j;
+      atomicAdd(a.dA + (size_t)(f0 + i) * KG + j, red[0][o] + red[1][o] + red[2][o] + red[3][o]);
     }
   }
 }

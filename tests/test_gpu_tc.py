@@ -39,3 +39,104 @@ def test_shift_gemm_matches_torch(N, M):
         scale = ref.abs().max().item()
         assert (of - ref).abs().max().item() / scale < 1e-5, (N, M, backward)
         assert (ob.float() - ref).abs().max().item() / scale < 2 ** -8
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the tensor-core cell path.  Stated bound for bf16 operands (8-bit mantissa) with fp32 accumulation, fp32
+# state and fp32 gates: max-norm error relative to max|ref| <= 3e-2 on H and <= 6e-2 on parameter gradients
+# (measured values are ~10x smaller, see profiles/); the fp32 path's 1e-5 / 1e-4 bound does NOT apply here.
+# ---------------------------------------------------------------------------------------------------------
+TC_TOL_H, TC_TOL_G = 3e-2, 6e-2
+
+
+def _relerr(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
+
+
+def _make_cell(S, G, F, K, tg, prec, seed=0):
+    torch.manual_seed(seed)
+    cell = gg.GGCRNNCell(G, F, K, K, torch.tanh, tg, None, 1, True)
+    cell.addGSO(S)
+    gg.set_precision(prec)
+    return cell.to(DEV)
+
+
+@pytest.mark.parametrize('tg', [False, True])
+@pytest.mark.parametrize('N,F,K,T,B,G', [(256, 32, 3, 5, 8, 1), (128, 16, 4, 3, 5, 2), (512, 64, 5, 4, 6, 1)])
+def test_tc_cell_matches_fp32_path(tg, N, F, K, T, B, G):
+    S = gg.graphs.dense_random(N, 0.3, seed=1)
+    torch.manual_seed(3)
+    X, h0, dH = torch.randn(B, T, G, N, device=DEV), 0.3 * torch.randn(B, F, N, device=DEV), torch.randn(B, T, F, N, device=DEV)
+    out = {}
+    try:
+        for prec in ('fp32', 'bf16'):
+            cell = _make_cell(S, G, F, K, tg, prec)
+            hh = h0.clone().requires_grad_(True)
+            H = cell(X, hh)
+            (H * dH).sum().backward()
+            out[prec] = (H.detach(), {k: v.grad for k, v in cell.named_parameters()}, hh.grad)
+    finally:
+        gg.set_precision('fp32')
+    H32, g32, dh32 = out['fp32']
+    Hb, gb, dhb = out['bf16']
+    errs = {'H': _relerr(Hb, H32), 'dh0': _relerr(dhb, dh32)}
+    for k in g32:
+        if g32[k] is None:
+            assert gb[k] is None
+        else:
+            errs[k] = _relerr(gb[k], g32[k])
+    print('tc-vs-fp32', dict(tg=tg, N=N, F=F, K=K, T=T, B=B, G=G), {k: f'{v:.2e}' for k, v in errs.items()})
+    assert errs['H'] < TC_TOL_H, errs
+    bad = {k: v for k, v in errs.items() if k != 'H' and v > TC_TOL_G}
+    assert not bad, errs
+
+
+def test_tc_cell_vs_fp64_oracle_reduced_cfg3():
+    """cfg3's shapes with a small batch: N=1024, F=64, K=5, G=1, time-gated, against the fp64 oracle."""
+    from oracle import gcrnn_oracle as orc
+    N, F, K, T, B = 1024, 64, 5, 6, 2
+    S = gg.graphs.dense_random(N, 0.3, seed=0)
+    try:
+        cell = _make_cell(S, 1, F, K, True, 'bf16')
+        torch.manual_seed(5)
+        X, h0, dH = torch.randn(B, T, 1, N), torch.zeros(B, F, N), torch.randn(B, T, F, N)
+        p = {k: v.detach().double().cpu() for k, v in cell.state_dict().items()}
+        Href, gref = orc.cell_forward_backward(p, S.double(), X.double(), h0.double(), dH.double(), True, None)
+        H = cell(X.to(DEV), h0.to(DEV))
+        (H * dH.to(DEV)).sum().backward()
+    finally:
+        gg.set_precision('fp32')
+    errs = {'H': _relerr(H, Href)}
+    for k, v in cell.named_parameters():
+        if gref[k] is None:
+            assert v.grad is None
+        else:
+            errs[k] = _relerr(v.grad, gref[k])
+    print('tc-vs-fp64', {k: f'{v:.2e}' for k, v in errs.items()})
+    assert errs['H'] < TC_TOL_H, errs
+    assert all(v < TC_TOL_G for k, v in errs.items() if k != 'H'), errs
+
+
+def test_tc_cell_long_horizon_contractive():
+    """With the reference init the state map has gain > 1 (weight_B ~ U(+-1/sqrt(G*Kin)) over F inputs), so ANY
+    rounding difference grows with T.  With a contractive recurrence (weight_B scaled by 0.2) the bf16 path must
+    stay within 1e-2 of the fp32 path over T = 48 steps."""
+    N, F, K, T, B = 256, 32, 4, 48, 4
+    S = gg.graphs.dense_random(N, 0.3, seed=2)
+    torch.manual_seed(11)
+    X, h0 = torch.randn(B, T, 1, N, device=DEV), torch.zeros(B, F, N, device=DEV)
+    out = {}
+    try:
+        for prec in ('fp32', 'bf16'):
+            cell = _make_cell(S, 1, F, K, True, prec, seed=9)
+            with torch.no_grad():
+                cell.weight_B.mul_(0.2)
+            H = cell(X, h0)
+            H.square().sum().backward()
+            out[prec] = (H.detach(), cell.weight_B.grad.clone(), cell.weight_A.grad.clone())
+    finally:
+        gg.set_precision('fp32')
+    e = [_relerr(a, b) for a, b in zip(out['bf16'], out['fp32'])]
+    print('tc-long-horizon', [f'{v:.2e}' for v in e])
+    assert e[0] < 1e-2 and e[1] < 3e-2 and e[2] < 3e-2, e
