@@ -53,6 +53,7 @@ struct gcrnn_graph {
   int max_row_deg = 0;
   // dense copies for the tensor-core path (E == 1): row-major [Npad, Npad] bf16, zero padded
   int Npad = 0;
+  float dense_scale = 1.f;            // S_bf16 = bf16(S / dense_scale), dense_scale = max|S|
   __nv_bfloat16* S_bf16 = nullptr;    // S    (K-major B operand of the backward shift  g @ S^T)
   __nv_bfloat16* St_bf16 = nullptr;   // S^T  (K-major B operand of the forward shift   z @ S)
   std::vector<void*> owned;           // every device allocation, for destroy

@@ -2,6 +2,8 @@
 // The graph shift z @ S (Utils/graphML.py:123) runs on tcgen05 (tc_gemm.cuh); see DESIGN.md §TC-path.
 #include "tc_gemm.cuh"
 #include "tc_cell.cuh"
+#include <cmath>
+#include <algorithm>
 
 namespace gcrnn {
 namespace tc {
@@ -48,7 +50,7 @@ void shift_gemm(const gcrnn_graph* g, bool backward, const __nv_bfloat16* A, lon
   GCRNN_CHECK(g->S_bf16 && g->St_bf16, "graph has no dense bf16 operator");
   GCRNN_CHECK(M > 0 && M < (1ll << 31), "row count out of range");
   const __nv_bfloat16* Bop = backward ? g->S_bf16 : g->St_bf16;
-  EpiStore epi{out_bf16, out_f32, (long long)N};
+  EpiStore epi{out_bf16, out_f32, (long long)N, g->dense_scale};
   const int sms = num_sms(g->device);
   if (N % 256 == 0) {
     CUtensorMap tmA = make_tmap_bf16(A, M, N, BM), tmB = make_tmap_bf16(Bop, N, N, 256);
@@ -62,9 +64,9 @@ void shift_gemm(const gcrnn_graph* g, bool backward, const __nv_bfloat16* A, lon
 
 // ---- launch helpers -------------------------------------------------------------------------------------------
 static void launched() { ++g_launches; CUDA_OK(cudaGetLastError()); }
-static void cvt_bf16(const float* in, __nv_bfloat16* out, __nv_bfloat16* out_lo, long long n, cudaStream_t st) {
+static void cvt_bf16(const float* in, __nv_bfloat16* out, long long n, cudaStream_t st) {
   GCRNN_CHECK(n % 4 == 0, "cvt_bf16: length must be a multiple of 4");
-  cvt_bf16_kernel<<<(unsigned)std::min<long long>((n / 4 + 255) / 256, 148 * 16), 256, 0, st>>>(in, out, out_lo, n / 4);
+  cvt_bf16_kernel<<<(unsigned)std::min<long long>((n / 4 + 255) / 256, 148 * 16), 256, 0, st>>>(in, out, n / 4);
   launched();
 }
 static void prep_weight(const float* W, __nv_bfloat16* out, int F, int K, int G, int ld, int mode, cudaStream_t st) {
@@ -87,7 +89,7 @@ static TcDims tc_dims(const gcrnn_cell* c, int64_t B, int64_t T) {
   GCRNN_CHECK(d.F % 16 == 0 && d.F <= 64, "tensor-core path: F must be a multiple of 16 and <= 64 (F=%d)", d.F);
   GCRNN_CHECK(d.N % 128 == 0, "tensor-core path: N %% 128 == 0 (N=%d)", d.N);
   GCRNN_CHECK(d.Kin * d.G <= 32, "tensor-core path: Kin*G <= 32 (got %d); use the fp32 path", d.Kin * d.G);
-  GCRNN_CHECK(d.Kst >= 1 && d.Kst <= WG_MAXK && d.Kst + 2 <= 8, "tensor-core path: Kst <= %d", WG_MAXK);
+  GCRNN_CHECK(d.Kst >= 1 && d.Kst <= WG_MAXK, "tensor-core path: Kst <= %d", WG_MAXK);
   GCRNN_CHECK(B > 0 && T > 0, "empty batch or sequence");
   d.sms = 0;
   return d;
@@ -112,13 +114,11 @@ static void chain(const gcrnn_graph* g, bool backward, const __nv_bfloat16* z0, 
   }
 }
 
-// slabs [z0hi, z0hi, z0lo, z1, ..., z_{K-1}] (see prep_weight_kernel)
-static ContractArgs contract_base(const TcDims& d, const __nv_bfloat16* W, int ldw, const __nv_bfloat16* z0, const __nv_bfloat16* z0_lo,
-                                  const __nv_bfloat16* zc) {
+static ContractArgs contract_base(const TcDims& d, const __nv_bfloat16* W, int ldw, const __nv_bfloat16* z0, const __nv_bfloat16* zc) {
   ContractArgs a{};
-  a.W = W; a.ldw = ldw; a.K = d.Kst + 2; a.C = d.F; a.M = d.F; a.N = d.N; a.B = d.B;
-  a.slab[0] = z0; a.slab[1] = z0; a.slab[2] = z0_lo;
-  for (int k = 1; k < d.Kst; ++k) a.slab[k + 2] = zc + (size_t)(k - 1) * d.R * d.N;
+  a.W = W; a.ldw = ldw; a.K = d.Kst; a.C = d.F; a.M = d.F; a.N = d.N; a.B = d.B;
+  a.slab[0] = z0;
+  for (int k = 1; k < d.Kst; ++k) a.slab[k] = zc + (size_t)(k - 1) * d.R * d.N;
   return a;
 }
 
@@ -143,13 +143,11 @@ size_t cell_forward_tc(const gcrnn_cell* cell, const gcrnn_cell_params* p, const
   TcSaved s;
   { Arena sa(saved, savedb); s.layout(sa, d); if (saved_used) *saved_used = sa.off; }
   GCRNN_CHECK(a.dry() || saved, "forward needs the `saved` buffer");
-  const int ldw = (d.Kst + 2) * d.F + 8;
+  const int ldw = d.Kst * d.F + 8;
   __nv_bfloat16* xb0 = a.get<__nv_bfloat16>((size_t)d.RX * d.N);
   __nv_bfloat16* xb1 = a.get<__nv_bfloat16>((size_t)d.RX * d.N);
   __nv_bfloat16* hb0 = a.get<__nv_bfloat16>((size_t)d.R * d.N);
   __nv_bfloat16* hb1 = a.get<__nv_bfloat16>((size_t)d.R * d.N);
-  __nv_bfloat16* hl0 = a.get<__nv_bfloat16>((size_t)d.R * d.N);
-  __nv_bfloat16* hl1 = a.get<__nv_bfloat16>((size_t)d.R * d.N);
   __nv_bfloat16* zb = a.get<__nv_bfloat16>((size_t)(d.Kst - 1) * d.R * d.N);
   __nv_bfloat16* Wb = a.get<__nv_bfloat16>((size_t)64 * ldw);
   float* c0 = d.tg ? a.get<float>((size_t)d.R * d.N) : nullptr;
@@ -160,21 +158,21 @@ size_t cell_forward_tc(const gcrnn_cell* cell, const gcrnn_cell_params* p, const
 
   // ---- x_t S^k for every (b, t): one batched chain (rows = B*T*G) ------------------------------------------------
   if (d.Kin > 1) {
-    cvt_bf16(X, xb0, nullptr, d.RX * d.N, st);
+    cvt_bf16(X, xb0, d.RX * d.N, st);
     __nv_bfloat16* cur = xb0; __nv_bfloat16* nxt = xb1;
     for (int k = 1; k < d.Kin; ++k) {
       shift_gemm(g, false, cur, d.RX, (k < d.Kin - 1) ? nxt : nullptr, s.zx + (size_t)(k - 1) * d.RX * d.N, st);
       std::swap(cur, nxt);
     }
   }
-  cvt_bf16(h0, hb0, hl0, d.R * d.N, st);
+  cvt_bf16(h0, hb0, d.R * d.N, st);
   // ---- time gates (graphML.py:2357-2374): depend on (x_t, h0) only -> all (b, t) at once ---------------------------
   if (d.tg) {
     chain(g, false, hb0, zb, d.Kst, d.R, st);
     CUDA_OK(cudaMemsetAsync(logit, 0, 2 * d.BT * sizeof(float), st));
     for (int gi = 0; gi < 2; ++gi) {
       prep_weight(p->t_weight_B[gi], Wb, d.F, d.Kst, d.F, ldw, 0, st);
-      ContractArgs ca = contract_base(d, Wb, ldw, hb0, hl0, zb);
+      ContractArgs ca = contract_base(d, Wb, ldw, hb0, zb);
       ca.out_f32 = c0; ca.out_bstride = FN; ca.bias = p->t_bias[gi]; ca.bias_scale = 2.f;   // bias enters twice (:2421-2422)
       launch_contract<EPI_PLAIN>(ca, d.sms, st);
       GateArgs ga{};
@@ -189,12 +187,11 @@ size_t cell_forward_tc(const gcrnn_cell* cell, const gcrnn_cell_params* p, const
   // ---- the recurrence -------------------------------------------------------------------------------------------
   prep_weight(p->weight_B, Wb, d.F, d.Kst, d.F, ldw, 0, st);
   __nv_bfloat16* hb[2] = {hb0, hb1};
-  __nv_bfloat16* hl[2] = {hl0, hl1};
   for (long long t = 0; t < d.T; ++t) {
     const __nv_bfloat16* hprev = hb[t & 1];
     if (!(t == 0 && d.tg)) chain(g, false, hprev, zb, d.Kst, d.R, st);      // at t = 0 the gates' h0 chain is still in zb
-    ContractArgs ca = contract_base(d, Wb, ldw, hprev, hl[t & 1], zb);
-    ca.out_f32 = H + t * FN; ca.out_bstride = d.T * FN; ca.out_bf16 = hb[(t + 1) & 1]; ca.out_bf16_lo = hl[(t + 1) & 1];
+    ContractArgs ca = contract_base(d, Wb, ldw, hprev, zb);
+    ca.out_f32 = H + t * FN; ca.out_bstride = d.T * FN; ca.out_bf16 = hb[(t + 1) & 1];
     ca.bias = p->bias;
     ca.gi = d.tg ? s.gt + t : nullptr; ca.gf = d.tg ? s.gt + d.BT + t : nullptr; ca.gate_stride = d.T;
     ca.A = p->weight_A; ca.Kin = d.Kin; ca.G = d.G;
@@ -215,10 +212,9 @@ size_t cell_backward_tc(const gcrnn_cell* cell, const gcrnn_cell_params* p, cons
   TcSaved s;
   { Arena sa(const_cast<void*>(saved), savedb); s.layout(sa, d); }
   GCRNN_CHECK(a.dry() || saved, "backward needs the buffer written by forward");
-  const int ldw = (d.Kst + 2) * d.F + 8;
+  const int ldw = d.Kst * d.F + 8;
   const int max_sms = 256;
   __nv_bfloat16* vb0 = a.get<__nv_bfloat16>((size_t)d.R * d.N);
-  __nv_bfloat16* vl0 = a.get<__nv_bfloat16>((size_t)d.R * d.N);
   __nv_bfloat16* vb = a.get<__nv_bfloat16>((size_t)(d.Kst - 1) * d.R * d.N);
   float* dhrec = a.get<float>((size_t)d.R * d.N);
   __nv_bfloat16* WTb = a.get<__nv_bfloat16>((size_t)64 * ldw);
@@ -261,16 +257,16 @@ size_t cell_backward_tc(const gcrnn_cell* cell, const gcrnn_cell_params* p, cons
     const long long hstride = t > 0 ? d.T * FN : FN;
     DpreArgs da{};
     da.dH = dH + t * FN; da.dH_bstride = d.T * FN; da.Ht = H + t * FN; da.H_bstride = d.T * FN;
-    da.dhrec = (t == d.T - 1) ? nullptr : dhrec; da.v0 = vb0; da.v0_lo = vl0;
+    da.dhrec = (t == d.T - 1) ? nullptr : dhrec; da.v0 = vb0;
     da.gi = d.tg ? s.gt + t : nullptr; da.gf = d.tg ? s.gt + d.BT + t : nullptr; da.gate_stride = d.T;
     da.A = p->weight_A; da.bias = p->bias; da.Kin = d.Kin; da.G = d.G; da.F = d.F; da.N = d.N;
     da.x0 = X + t * GN; da.x0_bstride = d.T * GN; da.zx = s.zx + t * GN; da.zx_kstride = d.RX * d.N; da.zx_bstride = d.T * GN;
     da.dgi = d.tg ? dgt + t : nullptr; da.dgf = d.tg ? dgt + d.BT + t : nullptr;
     da.dA = gr->weight_A; da.dbias = gr->bias; da.B = d.B;
-    dpre_kernel<<<(unsigned)std::min<long long>(d.B * (d.F / DP_FC), 148 * 8), 256, 0, st>>>(da);
+    dpre_kernel<<<(unsigned)std::min<long long>(d.B * (d.F / DP_FC), 148 * 32), 256, 0, st>>>(da);
     launched();
     chain(g, true, vb0, vb, d.Kst, d.R, st);
-    ContractArgs ca = contract_base(d, WTb, ldw, vb0, vl0, vb);
+    ContractArgs ca = contract_base(d, WTb, ldw, vb0, vb);
     ca.out_f32 = dhrec; ca.out_bstride = FN; ca.gf = d.tg ? s.gt + d.BT + t : nullptr; ca.gate_stride = d.T;
     ca.hprev = hprev; ca.hprev_bstride = hstride; ca.dgf = d.tg ? dgt + d.BT + t : nullptr; ca.accumulate = 0;
     launch_contract<EPI_BWD>(ca, d.sms, st);
@@ -282,10 +278,10 @@ size_t cell_backward_tc(const gcrnn_cell* cell, const gcrnn_cell_params* p, cons
   if (d.tg) {
     __nv_bfloat16* hb0 = vb0;                  // reuse: bf16 h0 and its chain live where the v slabs were
     for (int gi = 0; gi < 2; ++gi) {
-      cvt_bf16(h0, hb0, vl0, d.R * d.N, st);
+      cvt_bf16(h0, hb0, d.R * d.N, st);
       chain(g, false, hb0, vb, d.Kst, d.R, st);
       prep_weight(p->t_weight_B[gi], Wb, d.F, d.Kst, d.F, ldw, 0, st);
-      ContractArgs cc = contract_base(d, Wb, ldw, hb0, vl0, vb);
+      ContractArgs cc = contract_base(d, Wb, ldw, hb0, vb);
       cc.out_f32 = c0; cc.out_bstride = FN; cc.bias = p->t_bias[gi]; cc.bias_scale = 2.f;
       launch_contract<EPI_PLAIN>(cc, d.sms, st);
       gate_dlogit_kernel<<<1, 1024, 0, st>>>(dgt + gi * d.BT, s.gt + gi * d.BT, dl, gr->t_mlp_b[gi], d.BT);
@@ -302,12 +298,12 @@ size_t cell_backward_tc(const gcrnn_cell* cell, const gcrnn_cell_params* p, cons
         launched();
       }
       // h0 path of the sub-cell: v_k = dc0 (S^T)^k ; dB_g,k = v_k h0^T ; dh0 += sum_k B_g,k^T v_k
-      cvt_bf16(dc0, vb0, vl0, d.R * d.N, st);
+      cvt_bf16(dc0, vb0, d.R * d.N, st);
       chain(g, true, vb0, vb, d.Kst, d.R, st);
       if (gr->t_weight_B[gi]) { wgrad(h0, FN, nullptr, 0); wgrad_flush(gr->t_weight_B[gi]); }
       if (dh0) {
         prep_weight(p->t_weight_B[gi], Wb, d.F, d.Kst, d.F, ldw, 1, st);
-        ContractArgs cb = contract_base(d, Wb, ldw, vb0, vl0, vb);
+        ContractArgs cb = contract_base(d, Wb, ldw, vb0, vb);
         cb.out_f32 = dhrec; cb.out_bstride = FN; cb.hprev = h0; cb.hprev_bstride = FN; cb.accumulate = 1;
         launch_contract<EPI_BWD>(cb, d.sms, st);
       }
@@ -321,9 +317,12 @@ void tc_prepare_graph(gcrnn_graph* g, const float* S) {
   const int N = g->N;
   GCRNN_CHECK(N % 128 == 0, "the tensor-core path needs N %% 128 == 0 (N=%d)", N);
   std::vector<__nv_bfloat16> s((size_t)N * N), st((size_t)N * N);
+  float mx = 0.f;
+  for (size_t i = 0; i < (size_t)N * N; ++i) mx = std::max(mx, std::fabs(S[i]));
+  g->dense_scale = mx > 0.f ? mx : 1.f;
   for (int i = 0; i < N; ++i)
     for (int j = 0; j < N; ++j) {
-      __nv_bfloat16 v = __float2bfloat16(S[(size_t)i * N + j]);
+      __nv_bfloat16 v = __float2bfloat16(S[(size_t)i * N + j] / g->dense_scale);
       s[(size_t)i * N + j] = v;
       st[(size_t)j * N + i] = v;
     }

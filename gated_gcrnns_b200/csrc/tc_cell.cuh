@@ -43,41 +43,30 @@ __device__ __forceinline__ float warp_sum_f(float v) {
 }
 
 // ---- fp32 -> bf16 ---------------------------------------------------------------------------------------------
-// x = hi + lo with hi = bf16(x), lo = bf16(x - hi): two bf16 slabs carry ~16 mantissa bits of the fp32 value
-__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
-  hi = __float2bfloat16(x);
-  lo = __float2bfloat16(x - __bfloat162float(hi));
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));   // MUFU.TANH, |err| <= 2^-10.99: below the bf16 operand noise
+  return y;
 }
-__global__ void cvt_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ out_lo, long long n4) {
+__global__ void cvt_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n4) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     const float4 v = reinterpret_cast<const float4*>(in)[i];
-    __nv_bfloat16 h[4], l[4];
-    split_bf16(v.x, h[0], l[0]); split_bf16(v.y, h[1], l[1]); split_bf16(v.z, h[2], l[2]); split_bf16(v.w, h[3], l[3]);
-    reinterpret_cast<uint2*>(out)[i] = *reinterpret_cast<uint2*>(h);
-    if (out_lo) reinterpret_cast<uint2*>(out_lo)[i] = *reinterpret_cast<uint2*>(l);
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 u; u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
+    reinterpret_cast<uint2*>(out)[i] = u;
   }
 }
 
 // ---- weight preparation: W[f, k, g] fp32 -> bf16 [rows][ld] ------------------------------------------------------
 // mode 0: out[f][k*G + g] = W[f,k,g]          (forward contraction, rows = output features)
 // mode 1: out[g][k*F + f] = W[f,k,g]          (data-gradient contraction, rows = input features)
-// Tap 0 (the unshifted term, by far the largest) is carried as hi/lo pairs on BOTH operands:
-//   W0 z0 ~= W0hi z0hi + W0lo z0hi + W0hi z0lo, i.e. slab order [z0hi, z0hi, z0lo, z1, ..., z_{K-1}] against
-//   weight columns          [W0hi, W0lo, W0hi, W1, ..., W_{K-1}]   (K + 2 slabs of C channels each).
 __global__ void prep_weight_kernel(const float* __restrict__ W, __nv_bfloat16* __restrict__ out, int F, int K, int G, int ld, int mode) {
   const int total = F * K * G;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int g = i % G, k = (i / G) % K, f = i / (G * K);
     const float v = W[i];
-    const int row = mode == 0 ? f : g, col = mode == 0 ? g : f, C = mode == 0 ? G : F;
-    __nv_bfloat16* o = out + (size_t)row * ld + col;
-    if (k == 0) {
-      __nv_bfloat16 hi, lo;
-      split_bf16(v, hi, lo);
-      o[0] = hi; o[C] = lo; o[2 * C] = hi;
-    } else {
-      o[(size_t)(k + 2) * C] = __float2bfloat16(v);
-    }
+    if (mode == 0) out[(size_t)f * ld + k * G + g] = __float2bfloat16(v);
+    else out[(size_t)g * ld + k * F + f] = __float2bfloat16(v);
   }
 }
 
@@ -92,15 +81,14 @@ enum { EPI_PLAIN = 0, EPI_FWD = 1, EPI_BWD = 2 };
 
 struct ContractArgs {
   const __nv_bfloat16* W;    // [M][ldw] bf16, columns = slab-major
-  const __nv_bfloat16* slab[8];   // K slabs, each [B][C][N] bf16 (see prep_weight_kernel for the order)
+  const __nv_bfloat16* slab[8];   // K slabs (taps), each [B][C][N] bf16
   int K, C, M, N, ldw;
   long long B;
   // EPI_PLAIN: out_f32[b,m,n] = acc + bias_scale * bias[m]
   // EPI_FWD  : h = tanh(gi (a + bias) + gf (acc + bias)), a = sum_{k,g} A[m,k,g] zx_k[(b,t,g), n]
   // EPI_BWD  : dgf[b] += <acc, hprev[b]> ; out_f32[b,m,n] = gf[b] * acc (+ out_f32 if accumulate)
   float* out_f32; long long out_bstride;      // sample stride of out_f32 (H uses T*F*N)
-  __nv_bfloat16* out_bf16;                    // [B][M][N] or null: hi part of the new state
-  __nv_bfloat16* out_bf16_lo;                 // lo part
+  __nv_bfloat16* out_bf16;                    // [B][M][N] or null: bf16 copy of the new state (next step's GEMM operand)
   const float* bias; float bias_scale;
   const float* gi; const float* gf; long long gate_stride;     // gate value of sample b at gi[b*gate_stride]
   const float* A; int Kin, G;                                   // [M][Kin][G] fp32
@@ -118,6 +106,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) contract_mma_kernel(const Contr
   __nv_bfloat16* Zs = Ws + 64 * a.ldw;                                            // [2][KK][CT_ZLD]
   float* fs = reinterpret_cast<float*>(Zs + 2 * (size_t)KK * CT_ZLD);             // A [M*Kin*G], bias [M], red[8]
   float* As = fs; float* bs = fs + 64 * 32; float* red = bs + 64;
+  float* Xs = red + 8;                                                            // [2][32][CT_NT] zx tile (EPI_FWD)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int wm = warp & 3, wn = warp >> 2;
@@ -146,6 +135,16 @@ __global__ void __launch_bounds__(CT_THREADS, 1) contract_mma_kernel(const Contr
       const int k = row / a.C, c = row % a.C;
       const __nv_bfloat16* src = a.slab[k] + ((size_t)(b * a.C + c) * a.N + n0 + ch * 8);
       cp_async16(smem_u32(dst + row * CT_ZLD + ch * 8), src);
+    }
+    if (EPI == EPI_FWD) {      // x_t S^k rows of this sample: [Kin*G][64] fp32
+      const int KG = a.Kin * a.G;
+      for (int i = tid; i < KG * (CT_NT / 4); i += CT_THREADS) {
+        const int kg = i / (CT_NT / 4), c4 = i % (CT_NT / 4);
+        const int k = kg / a.G, g = kg % a.G;
+        const float* zp = (k == 0) ? a.x0 + b * a.x0_bstride + (size_t)g * a.N
+                                   : a.zx + (size_t)(k - 1) * a.zx_kstride + b * a.zx_bstride + (size_t)g * a.N;
+        cp_async16(smem_u32(Xs + ((size_t)buf * 32 + kg) * CT_NT + c4 * 4), zp + n0 + c4 * 4);
+      }
     }
   };
 
@@ -193,17 +192,16 @@ __global__ void __launch_bounds__(CT_THREADS, 1) contract_mma_kernel(const Contr
       const int n = nb + 8 * j;
       float ax[2][2] = {{0.f, 0.f}, {0.f, 0.f}};   // [row half][col] input-filter term
       if (EPI == EPI_FWD) {
-        for (int k = 0; k < a.Kin; ++k)
-          for (int g = 0; g < a.G; ++g) {
-            const float* zp = (k == 0) ? a.x0 + b * a.x0_bstride + (size_t)g * a.N
-                                       : a.zx + (size_t)(k - 1) * a.zx_kstride + b * a.zx_bstride + (size_t)g * a.N;
-            const float2 z = *reinterpret_cast<const float2*>(zp + n);
+        const int KG = a.Kin * a.G;
+        const float* xt = Xs + (size_t)buf * 32 * CT_NT + (n - n0);
+        for (int kg = 0; kg < KG; ++kg) {
+          const float2 z = *reinterpret_cast<const float2*>(xt + kg * CT_NT);
 #pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-              const int m = m0 + 8 * hh;
-              if (m < a.M) { const float w = As[(m * a.Kin + k) * a.G + g]; ax[hh][0] = fmaf(w, z.x, ax[hh][0]); ax[hh][1] = fmaf(w, z.y, ax[hh][1]); }
-            }
+          for (int hh = 0; hh < 2; ++hh) {
+            const int m = m0 + 8 * hh;
+            if (m < a.M) { const float w = As[m * KG + kg]; ax[hh][0] = fmaf(w, z.x, ax[hh][0]); ax[hh][1] = fmaf(w, z.y, ax[hh][1]); }
           }
+        }
       }
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
@@ -215,14 +213,10 @@ __global__ void __launch_bounds__(CT_THREADS, 1) contract_mma_kernel(const Contr
           *reinterpret_cast<float2*>(a.out_f32 + b * a.out_bstride + (size_t)m * a.N + n) = make_float2(v0, v1);
         } else if (EPI == EPI_FWD) {
           const float bb = bs[m];
-          v0 = tanhf(vgi * (ax[hh][0] + bb) + vgf * (v0 + bb));
-          v1 = tanhf(vgi * (ax[hh][1] + bb) + vgf * (v1 + bb));
+          v0 = tanh_fast(vgi * (ax[hh][0] + bb) + vgf * (v0 + bb));
+          v1 = tanh_fast(vgi * (ax[hh][1] + bb) + vgf * (v1 + bb));
           *reinterpret_cast<float2*>(a.out_f32 + b * a.out_bstride + (size_t)m * a.N + n) = make_float2(v0, v1);
-          __nv_bfloat16 h0, l0, h1, l1;
-          split_bf16(v0, h0, l0); split_bf16(v1, h1, l1);
-          const size_t oo = ((size_t)b * a.M + m) * a.N + n;
-          *reinterpret_cast<__nv_bfloat162*>(a.out_bf16 + oo) = __halves2bfloat162(h0, h1);
-          *reinterpret_cast<__nv_bfloat162*>(a.out_bf16_lo + oo) = __halves2bfloat162(l0, l1);
+          *reinterpret_cast<__nv_bfloat162*>(a.out_bf16 + ((size_t)b * a.M + m) * a.N + n) = __floats2bfloat162_rn(v0, v1);
         } else {
           const float2 hp = *reinterpret_cast<const float2*>(a.hprev + b * a.hprev_bstride + (size_t)m * a.N + n);
           part = fmaf(v0, hp.x, fmaf(v1, hp.y, part));
@@ -245,7 +239,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) contract_mma_kernel(const Contr
 }
 
 inline size_t contract_smem_bytes(int K, int C, int ldw) {
-  return (size_t)64 * ldw * 2 + (size_t)2 * K * C * CT_ZLD * 2 + (64 * 32 + 64 + 8) * sizeof(float);
+  return (size_t)64 * ldw * 2 + (size_t)2 * K * C * CT_ZLD * 2 + (64 * 32 + 64 + 8 + 2 * 32 * CT_NT) * sizeof(float);
 }
 
 template <int EPI>
@@ -391,14 +385,14 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ part, float* dW, i
 }
 
 // =====================================================================================================
-// dpre kernel (one time step): dpre = (dH_t + dh_rec) * (1 - h_t^2), plus every reduction that needs dpre
+// dpre kernel (one time step): dpre = (dH_t + dh_rec) * (1 - h_t^2), plus every reduction that needs dpre.
+// One warp per (b, f) row, 8 rows (features) of one sample per CTA; float4 streams, warp-shuffle reductions.
 // =====================================================================================================
 struct DpreArgs {
   const float* dH; long long dH_bstride;        // dH[b, t]  : [F][N] at dH + b*bstride
   const float* Ht; long long H_bstride;         // h_t[b]
   const float* dhrec;                           // [B][F][N] or null (t = T-1)
-  __nv_bfloat16* v0;                            // out: bf16 dpre [B][F][N] (hi part)
-  __nv_bfloat16* v0_lo;                         // lo part
+  __nv_bfloat16* v0;                            // out: bf16 dpre [B][F][N]
   const float* gi; const float* gf; long long gate_stride;
   const float* A; const float* bias; int Kin, G, F, N;
   const float* x0; long long x0_bstride; const float* zx; long long zx_kstride, zx_bstride;
@@ -407,102 +401,77 @@ struct DpreArgs {
   float* dbias;                                 // [F]          += (gi + gf) * sum_n dpre
   long long B;
 };
-constexpr int DP_FC = 8;   // features per CTA
+constexpr int DP_FC = 8;      // features (warps) per CTA
+constexpr int DP_KG = 8;      // (k, g) pairs handled per pass
 
 __global__ void __launch_bounds__(256) dpre_kernel(const DpreArgs a) {
-  __shared__ float red[8][DP_FC * 34];           // per warp: per f: sum_dp, and Kin*G (<=32) sums, + dgi slot
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  __shared__ float s_gi[DP_FC];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int KG = a.Kin * a.G;
   const int fgroups = a.F / DP_FC;
+  const int N4 = a.N / 4;
   for (long long item = blockIdx.x; item < a.B * fgroups; item += gridDim.x) {
     const long long b = item / fgroups;
-    const int f0 = (int)(item % fgroups) * DP_FC;
+    const int f = (int)(item % fgroups) * DP_FC + warp;
     const float vgi = a.gi ? a.gi[b * a.gate_stride] : 1.f;
-    float s_dp[DP_FC];
-    float s_a[DP_FC];        // only used when KG == 1..: generic path accumulates into smem below
+    const float vgf = a.gf ? a.gf[b * a.gate_stride] : 1.f;
+    const float4* pdH = reinterpret_cast<const float4*>(a.dH + b * a.dH_bstride + (size_t)f * a.N);
+    const float4* pH = reinterpret_cast<const float4*>(a.Ht + b * a.H_bstride + (size_t)f * a.N);
+    const float4* pR = a.dhrec ? reinterpret_cast<const float4*>(a.dhrec + ((size_t)b * a.F + f) * a.N) : nullptr;
+    uint2* pV = reinterpret_cast<uint2*>(a.v0 + ((size_t)b * a.F + f) * a.N);
+    float sdp = 0.f, sa = 0.f;
+    for (int kg0 = 0; kg0 < KG || kg0 == 0; kg0 += DP_KG) {
+      float sz[DP_KG];
 #pragma unroll
-    for (int i = 0; i < DP_FC; ++i) { s_dp[i] = 0.f; s_a[i] = 0.f; }
-    // per-thread partial of sum_n dpre[f,n] * zx_kg[n] : kept in registers for up to 8 (k,g) pairs per pass
-    float s_z[DP_FC][8];
-    for (int kg0 = 0; kg0 < KG; kg0 += 8) {
+      for (int j = 0; j < DP_KG; ++j) sz[j] = 0.f;
+      for (int i = lane; i < N4; i += 32) {
+        const float4 hv = pH[i];
+        float4 d = pdH[i];
+        if (pR) { const float4 r = pR[i]; d.x += r.x; d.y += r.y; d.z += r.z; d.w += r.w; }
+        d.x *= 1.f - hv.x * hv.x; d.y *= 1.f - hv.y * hv.y; d.z *= 1.f - hv.z * hv.z; d.w *= 1.f - hv.w * hv.w;
+        if (kg0 == 0) {
+          __nv_bfloat162 p = __floats2bfloat162_rn(d.x, d.y), q = __floats2bfloat162_rn(d.z, d.w);
+          uint2 u; u.x = *reinterpret_cast<uint32_t*>(&p); u.y = *reinterpret_cast<uint32_t*>(&q);
+          pV[i] = u;
+          sdp += (d.x + d.y) + (d.z + d.w);
+        }
 #pragma unroll
-      for (int i = 0; i < DP_FC; ++i)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) s_z[i][j] = 0.f;
-      for (int n = tid; n < a.N; n += 256) {
-        float z[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < DP_KG; ++j) {
           const int kg = kg0 + j;
           if (kg < KG) {
             const int k = kg / a.G, g = kg % a.G;
-            z[j] = (k == 0) ? a.x0[b * a.x0_bstride + (size_t)g * a.N + n]
-                            : a.zx[(size_t)(k - 1) * a.zx_kstride + b * a.zx_bstride + (size_t)g * a.N + n];
-          } else z[j] = 0.f;
-        }
-#pragma unroll
-        for (int i = 0; i < DP_FC; ++i) {
-          const int f = f0 + i;
-          const size_t o = (size_t)f * a.N + n;
-          const float hv = a.Ht[b * a.H_bstride + o];
-          float dh = a.dH[b * a.dH_bstride + o];
-          if (a.dhrec) dh += a.dhrec[((size_t)b * a.F) * a.N + o];
-          const float dp = dh * (1.f - hv * hv);
-          if (kg0 == 0) {
-            __nv_bfloat16 hi, lo;
-            split_bf16(dp, hi, lo);
-            a.v0[((size_t)b * a.F) * a.N + o] = hi;
-            a.v0_lo[((size_t)b * a.F) * a.N + o] = lo;
-            s_dp[i] += dp;
+            const float* zp = (k == 0) ? a.x0 + b * a.x0_bstride + (size_t)g * a.N
+                                       : a.zx + (size_t)(k - 1) * a.zx_kstride + b * a.zx_bstride + (size_t)g * a.N;
+            const float4 z = reinterpret_cast<const float4*>(zp)[i];
+            sz[j] = fmaf(d.x, z.x, fmaf(d.y, z.y, fmaf(d.z, z.z, fmaf(d.w, z.w, sz[j]))));
           }
-          float ax = 0.f;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            s_z[i][j] = fmaf(dp, z[j], s_z[i][j]);
-            if (kg0 + j < KG) ax = fmaf(a.A[(f * a.Kin) * a.G + kg0 + j], z[j], ax);
-          }
-          s_a[i] = fmaf(dp, ax, s_a[i]);
         }
       }
-      // reduce the (k,g) partials of this pass
 #pragma unroll
-      for (int i = 0; i < DP_FC; ++i)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float v = warp_sum_f(s_z[i][j]);
-          if (lane == 0) red[warp][i * 34 + 1 + ((kg0 + j) & 31)] = v;
-        }
-      __syncthreads();
-      for (int idx = tid; idx < DP_FC * 8; idx += 256) {
-        const int i = idx / 8, j = idx % 8;
-        if (kg0 + j < KG && a.dA) {
-          float s = 0.f;
-          for (int w = 0; w < 8; ++w) s += red[w][i * 34 + 1 + ((kg0 + j) & 31)];
-          atomicAdd(a.dA + (size_t)(f0 + i) * KG + kg0 + j, vgi * s);
+      for (int j = 0; j < DP_KG; ++j) {
+        const int kg = kg0 + j;
+        if (kg < KG) {
+          const float v = warp_sum_f(sz[j]);
+          sa = fmaf(a.A[(size_t)f * KG + kg], v, sa);                  // <dpre, A(S)x> = sum_kg A[f,kg] <dpre, zx_kg>
+          if (lane == 0 && a.dA) atomicAdd(a.dA + (size_t)f * KG + kg, vgi * v);
         }
       }
-      __syncthreads();
     }
-    // sum_n dpre per f, and <dpre, a> per sample
-#pragma unroll
-    for (int i = 0; i < DP_FC; ++i) {
-      const float v = warp_sum_f(s_dp[i]);
-      const float w = warp_sum_f(s_a[i]);
-      if (lane == 0) { red[warp][i * 34] = v; red[warp][i * 34 + 33] = w; }
-    }
-    __syncthreads();
-    if (tid < DP_FC) {
-      float sdp = 0.f, sa = 0.f;
-      for (int w = 0; w < 8; ++w) { sdp += red[w][tid * 34]; sa += red[w][tid * 34 + 33]; }
-      const int f = f0 + tid;
-      const float bb = a.bias ? a.bias[f] : 0.f;
-      const float vgf = a.gf ? a.gf[b * a.gate_stride] : 1.f;
+    sdp = warp_sum_f(sdp);
+    const float bb = a.bias ? a.bias[f] : 0.f;
+    if (lane == 0) {
       if (a.dbias) atomicAdd(a.dbias + f, (vgi + vgf) * sdp);
-      if (a.dgi) atomicAdd(a.dgi + b * a.gate_stride, sa + bb * sdp);
+      s_gi[warp] = sa + bb * sdp;
       if (a.dgf) atomicAdd(a.dgf + b * a.gate_stride, bb * sdp);
     }
     __syncthreads();
-
+    if (threadIdx.x == 0 && a.dgi) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < DP_FC; ++w) t += s_gi[w];
+      atomicAdd(a.dgi + b * a.gate_stride, t);
+    }
+    __syncthreads();
   }
 }
 
@@ -526,10 +495,11 @@ struct GateArgs {
   int bsplit;
 };
 
+constexpr int TG_TT = 4;     // time steps in flight per thread (memory-level parallelism)
+
 template <bool BWD, int KGMAX>
 __global__ void __launch_bounds__(128) time_gate_kernel(const GateArgs a) {
   __shared__ float red[4][TG_FC * (KGMAX + 1)];
-  __shared__ float red1[4];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n = blockIdx.x * 128 + tid;
   const int f0 = blockIdx.y * TG_FC;
@@ -550,43 +520,51 @@ __global__ void __launch_bounds__(128) time_gate_kernel(const GateArgs a) {
       for (int j = 0; j < KGMAX; ++j) sA[BWD ? i : 0][BWD ? j : 0] = 0.f;
     }
   }
+  const size_t kstride = (size_t)a.B * a.T * a.G * a.N;
   for (long long b = b_lo; b < b_hi; ++b) {
     float c0v[TG_FC], dc0v[TG_FC];
 #pragma unroll
     for (int i = 0; i < TG_FC; ++i) { c0v[i] = a.c0[((size_t)b * a.F + f0 + i) * a.N + n]; dc0v[i] = 0.f; }
-    for (long long t = 0; t < a.T; ++t) {
-      float z[KGMAX];
+    for (long long t0 = 0; t0 < a.T; t0 += TG_TT) {
+      float z[TG_TT][KGMAX], dlv[TG_TT];
 #pragma unroll
-      for (int j = 0; j < KGMAX; ++j) {
-        if (j < KG) {
-          const int k = j / a.G, g = j % a.G;
-          const size_t row = ((size_t)b * a.T + t) * a.G + g;
-          z[j] = (k == 0) ? a.X[row * a.N + n] : a.zx[((size_t)(k - 1) * a.B * a.T * a.G + row) * a.N + n];
-        } else z[j] = 0.f;
-      }
-      const float dlv = BWD ? a.dl[b * a.T + t] : 0.f;
-      float part = 0.f;
+      for (int tt = 0; tt < TG_TT; ++tt) {
+        const long long t = t0 + tt;
+        const bool ok = t < a.T;
+        dlv[tt] = (BWD && ok) ? a.dl[b * a.T + t] : 0.f;
 #pragma unroll
-      for (int i = 0; i < TG_FC; ++i) {
-        float pre = c0v[i];
-#pragma unroll
-        for (int j = 0; j < KGMAX; ++j) pre = fmaf(wA[i][j], z[j], pre);
-        const float u = tanhf(pre);
-        if (!BWD) part = fmaf(wg[i], u, part);
-        else {
-          dwg[i] = fmaf(dlv, u, dwg[i]);
-          const float dpu = dlv * wg[i] * (1.f - u * u);
-          dc0v[i] += dpu;
-#pragma unroll
-          for (int j = 0; j < KGMAX; ++j) sA[BWD ? i : 0][BWD ? j : 0] = fmaf(dpu, z[j], sA[BWD ? i : 0][BWD ? j : 0]);
+        for (int j = 0; j < KGMAX; ++j) {
+          if (j < KG && ok) {
+            const int k = j / a.G, g = j % a.G;
+            const size_t row = ((size_t)b * a.T + t) * a.G + g;
+            z[tt][j] = (k == 0) ? a.X[row * a.N + n] : a.zx[(size_t)(k - 1) * kstride + row * a.N + n];
+          } else z[tt][j] = 0.f;
         }
       }
-      if (!BWD) {
-        part = warp_sum_f(part);
-        if (lane == 0) red1[warp] = part;
-        __syncthreads();
-        if (tid == 0) atomicAdd(a.logit + b * a.T + t, red1[0] + red1[1] + red1[2] + red1[3]);
-        __syncthreads();
+#pragma unroll
+      for (int tt = 0; tt < TG_TT; ++tt) {
+        if (t0 + tt < a.T) {
+          float part = 0.f;
+#pragma unroll
+          for (int i = 0; i < TG_FC; ++i) {
+            float pre = c0v[i];
+#pragma unroll
+            for (int j = 0; j < KGMAX; ++j) pre = fmaf(wA[i][j], z[tt][j], pre);
+            const float u = tanh_fast(pre);
+            if (!BWD) part = fmaf(wg[i], u, part);
+            else {
+              dwg[i] = fmaf(dlv[tt], u, dwg[i]);
+              const float dpu = dlv[tt] * wg[i] * (1.f - u * u);
+              dc0v[i] += dpu;
+#pragma unroll
+              for (int j = 0; j < KGMAX; ++j) sA[BWD ? i : 0][BWD ? j : 0] = fmaf(dpu, z[tt][j], sA[BWD ? i : 0][BWD ? j : 0]);
+            }
+          }
+          if (!BWD) {
+            part = warp_sum_f(part);
+            if (lane == 0) atomicAdd(a.logit + b * a.T + t0 + tt, part);
+          }
+        }
       }
     }
     if (BWD) {

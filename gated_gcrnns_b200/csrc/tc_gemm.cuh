@@ -122,7 +122,10 @@ struct EpiStore {
   __nv_bfloat16* out_bf16;   // [M, ld] or null
   float* out_f32;            // [M, ld] or null
   long long ld;
-  __device__ __forceinline__ void operator()(int row, int col0, const float* v) const {
+  float scale;               // the bf16 operator holds S / scale (exact for unweighted graphs); undone here in fp32
+  __device__ __forceinline__ void operator()(int row, int col0, float* v) const {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] *= scale;
     if (out_bf16) {
       uint4* dst = reinterpret_cast<uint4*>(out_bf16 + (long long)row * ld + col0);
 #pragma unroll

@@ -26,11 +26,14 @@ def _gemm(g, A_bf16, backward, want_f32=True, want_bf16=True):
 
 @pytest.mark.parametrize('N,M', [(256, 128), (128, 300), (1024, 128 * 5 + 17), (512, 4096)])
 def test_shift_gemm_matches_torch(N, M):
-    """Operands are exactly representable bf16 values, so the only difference to an fp32 matmul of the same
-    operands is accumulation order: tolerance 1e-5 relative to max|ref| (fp32 out), 2^-8 for the bf16 copy."""
+    """The library keeps the operator as bf16(S / max|S|) and multiplies by max|S| in the fp32 epilogue (exact for
+    unweighted graphs).  Against an fp32 matmul with that same effective operator the only difference is accumulation
+    order: tolerance 1e-5 relative to max|ref| (fp32 out), 2^-8 for the bf16 copy."""
     torch.manual_seed(N + M)
-    S = (torch.randn(N, N) * (torch.rand(N, N) < 0.3)).to(torch.bfloat16).float() / 16
+    S = torch.randn(N, N) * (torch.rand(N, N) < 0.3) / 16
     g = ggraph.from_dense(S.reshape(1, N, N), DEV, keep_dense=True)
+    mx = S.abs().max()
+    S = (S / mx).to(torch.bfloat16).float() * mx
     A = torch.randn(M, N, device=DEV).to(torch.bfloat16)
     for backward in (False, True):
         ob, of = _gemm(g, A, backward)
