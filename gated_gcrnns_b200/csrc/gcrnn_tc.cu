@@ -2,6 +2,8 @@
 // The graph shift z @ S (Utils/graphML.py:123) runs on tcgen05 (tc_gemm.cuh); see DESIGN.md §TC-path.
 #include "tc_gemm.cuh"
 #include "tc_cell.cuh"
+#include "tc_tap.cuh"
+#include <cstdlib>
 #include <cmath>
 #include <algorithm>
 
@@ -69,7 +71,7 @@ static void cvt_bf16(const float* in, __nv_bfloat16* out, long long n, cudaStrea
   cvt_bf16_kernel<<<(unsigned)std::min<long long>((n / 4 + 255) / 256, 148 * 16), 256, 0, st>>>(in, out, n / 4);
   launched();
 }
-static void prep_weight(const float* W, __nv_bfloat16* out, int F, int K, int G, int ld, int mode, cudaStream_t st) {
+[[maybe_unused]] static void prep_weight(const float* W, __nv_bfloat16* out, int F, int K, int G, int ld, int mode, cudaStream_t st) {
   CUDA_OK(cudaMemsetAsync(out, 0, (size_t)64 * ld * sizeof(__nv_bfloat16), st));
   prep_weight_kernel<<<(F * K * G + 255) / 256, 256, 0, st>>>(W, out, F, K, G, ld, mode);
   launched();
@@ -122,6 +124,59 @@ static ContractArgs contract_base(const TcDims& d, const __nv_bfloat16* W, int l
   return a;
 }
 
+static bool use_tap_gemm() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("GCRNN_TC_CONTRACT"); v = (e && std::string(e) == "mma") ? 0 : 1; }
+  return v == 1;
+}
+
+// tap contraction on tcgen05 (tc_tap.cuh).  Wp: prepared bf16 weights [M][KB*64] (zero padded), ca: the same
+// argument block the mma.sync variant takes (slab pointers + epilogue operands).
+template <int EPI>
+static void launch_tap(const ContractArgs& ca, const __nv_bfloat16* Wp, int sms, cudaStream_t st) {
+  TapArgs t{};
+  t.K = ca.K; t.C = ca.C; t.M = ca.M; t.N = ca.N; t.KB = (ca.K * ca.C + 63) / 64; t.B = ca.B; t.R = ca.B * ca.C;
+  GCRNN_CHECK(t.KB <= TAP_MAX_KB && (ca.C == 16 || ca.C == 32 || ca.C == 64) && ca.M % 16 == 0 && ca.M <= 64 && ca.N % TAP_BM == 0,
+              "tap_gemm: unsupported sizes K=%d C=%d M=%d N=%d", ca.K, ca.C, ca.M, ca.N);
+  t.out_f32 = ca.out_f32; t.out_bstride = ca.out_bstride; t.out_bf16 = ca.out_bf16; t.bias = ca.bias; t.bias_scale = ca.bias_scale;
+  t.gi = ca.gi; t.gf = ca.gf; t.gate_stride = ca.gate_stride; t.A = ca.A; t.Kin = ca.Kin; t.G = ca.G;
+  t.x0 = ca.x0; t.x0_bstride = ca.x0_bstride; t.zx = ca.zx; t.zx_kstride = ca.zx_kstride; t.zx_bstride = ca.zx_bstride;
+  t.hprev = ca.hprev; t.hprev_bstride = ca.hprev_bstride; t.dgf = ca.dgf; t.accumulate = ca.accumulate;
+  for (int k = 2; k < ca.K; ++k)
+    GCRNN_CHECK(ca.slab[k] == ca.slab[1] + (size_t)(k - 1) * t.R * ca.N, "tap_gemm: slabs 1..K-1 must be contiguous");
+  const CUtensorMap tm0 = make_tmap_bf16(ca.slab[0], t.R, ca.N, ca.C);
+  const CUtensorMap tmc = ca.K > 1 ? make_tmap_bf16(ca.slab[1], (long long)(ca.K - 1) * t.R, ca.N, ca.C) : tm0;
+  const CUtensorMap tmW = make_tmap_bf16(Wp, ca.M, (long long)t.KB * 64, ca.M);
+  const long long tiles = ca.B * (ca.N / TAP_BM);
+  const int grid = (int)std::min<long long>(tiles, sms);
+  const bool small = (EPI != TAP_FWD) || ca.Kin * ca.G <= 8;
+  if (small) {
+    auto kern = tap_gemm_kernel<EPI, 8>;
+    CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TAP_SMEM));
+    kern<<<grid, NUM_THREADS, TAP_SMEM, st>>>(tm0, tmc, tmW, t);
+  } else {
+    auto kern = tap_gemm_kernel<EPI, 32>;
+    CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TAP_SMEM));
+    kern<<<grid, NUM_THREADS, TAP_SMEM, st>>>(tm0, tmc, tmW, t);
+  }
+  launched();
+}
+
+// weights for either contraction kernel: returns the leading dimension used
+static int prep_contract_weight(const float* W, __nv_bfloat16* out, int F, int K, int ldw_mma, int mode, cudaStream_t st) {
+  const int ld = use_tap_gemm() ? ((K * F + 63) / 64) * 64 : ldw_mma;
+  CUDA_OK(cudaMemsetAsync(out, 0, (size_t)64 * (((K * F + 63) / 64) * 64 + 8) * sizeof(__nv_bfloat16), st));
+  prep_weight_kernel<<<(F * K * F + 255) / 256, 256, 0, st>>>(W, out, F, K, F, ld, mode);
+  launched();
+  return ld;
+}
+
+template <int EPI_MMA, int EPI_TAP>
+static void contract(ContractArgs& ca, const __nv_bfloat16* Wp, int ld, int sms, cudaStream_t st) {
+  if (use_tap_gemm()) launch_tap<EPI_TAP>(ca, Wp, sms, st);
+  else { ca.W = Wp; ca.ldw = ld; launch_contract<EPI_MMA>(ca, sms, st); }
+}
+
 static void gate_launch(bool bwd, const GateArgs& ga, const TcDims& d, cudaStream_t st) {
   dim3 grid(d.N / 128, d.F / TG_FC, ga.bsplit);
   const int KG = d.Kin * d.G;
@@ -149,7 +204,8 @@ size_t cell_forward_tc(const gcrnn_cell* cell, const gcrnn_cell_params* p, const
   __nv_bfloat16* hb0 = a.get<__nv_bfloat16>((size_t)d.R * d.N);
   __nv_bfloat16* hb1 = a.get<__nv_bfloat16>((size_t)d.R * d.N);
   __nv_bfloat16* zb = a.get<__nv_bfloat16>((size_t)(d.Kst - 1) * d.R * d.N);
-  __nv_bfloat16* Wb = a.get<__nv_bfloat16>((size_t)64 * ldw);
+  const size_t wbuf = (size_t)64 * (((d.Kst * d.F + 63) / 64) * 64 + 8);
+  __nv_bfloat16* Wb = a.get<__nv_bfloat16>(wbuf);
   float* c0 = d.tg ? a.get<float>((size_t)d.R * d.N) : nullptr;
   float* logit = d.tg ? a.get<float>(2 * d.BT) : nullptr;
   if (a.dry()) return a.off;
@@ -171,10 +227,10 @@ size_t cell_forward_tc(const gcrnn_cell* cell, const gcrnn_cell_params* p, const
     chain(g, false, hb0, zb, d.Kst, d.R, st);
     CUDA_OK(cudaMemsetAsync(logit, 0, 2 * d.BT * sizeof(float), st));
     for (int gi = 0; gi < 2; ++gi) {
-      prep_weight(p->t_weight_B[gi], Wb, d.F, d.Kst, d.F, ldw, 0, st);
-      ContractArgs ca = contract_base(d, Wb, ldw, hb0, zb);
+      const int ldg = prep_contract_weight(p->t_weight_B[gi], Wb, d.F, d.Kst, ldw, 0, st);
+      ContractArgs ca = contract_base(d, Wb, ldg, hb0, zb);
       ca.out_f32 = c0; ca.out_bstride = FN; ca.bias = p->t_bias[gi]; ca.bias_scale = 2.f;   // bias enters twice (:2421-2422)
-      launch_contract<EPI_PLAIN>(ca, d.sms, st);
+      contract<EPI_PLAIN, TAP_PLAIN>(ca, Wb, ldg, d.sms, st);
       GateArgs ga{};
       ga.A = p->t_weight_A[gi]; ga.Kin = d.Kin; ga.G = d.G; ga.F = d.F; ga.N = d.N; ga.B = d.B; ga.T = d.T;
       ga.X = X; ga.zx = s.zx; ga.c0 = c0; ga.Wg = p->t_mlp_w[gi]; ga.logit = logit + gi * d.BT;
@@ -185,19 +241,19 @@ size_t cell_forward_tc(const gcrnn_cell* cell, const gcrnn_cell_params* p, const
     }
   }
   // ---- the recurrence -------------------------------------------------------------------------------------------
-  prep_weight(p->weight_B, Wb, d.F, d.Kst, d.F, ldw, 0, st);
+  const int ldm = prep_contract_weight(p->weight_B, Wb, d.F, d.Kst, ldw, 0, st);
   __nv_bfloat16* hb[2] = {hb0, hb1};
   for (long long t = 0; t < d.T; ++t) {
     const __nv_bfloat16* hprev = hb[t & 1];
     if (!(t == 0 && d.tg)) chain(g, false, hprev, zb, d.Kst, d.R, st);      // at t = 0 the gates' h0 chain is still in zb
-    ContractArgs ca = contract_base(d, Wb, ldw, hprev, zb);
+    ContractArgs ca = contract_base(d, Wb, ldm, hprev, zb);
     ca.out_f32 = H + t * FN; ca.out_bstride = d.T * FN; ca.out_bf16 = hb[(t + 1) & 1];
     ca.bias = p->bias;
     ca.gi = d.tg ? s.gt + t : nullptr; ca.gf = d.tg ? s.gt + d.BT + t : nullptr; ca.gate_stride = d.T;
     ca.A = p->weight_A; ca.Kin = d.Kin; ca.G = d.G;
     ca.x0 = X + t * GN; ca.x0_bstride = d.T * GN;
     ca.zx = s.zx + t * GN; ca.zx_kstride = d.RX * d.N; ca.zx_bstride = d.T * GN;
-    launch_contract<EPI_FWD>(ca, d.sms, st);
+    contract<EPI_FWD, TAP_FWD>(ca, Wb, ldm, d.sms, st);
   }
   return a.off;
 }
@@ -217,13 +273,14 @@ size_t cell_backward_tc(const gcrnn_cell* cell, const gcrnn_cell_params* p, cons
   __nv_bfloat16* vb0 = a.get<__nv_bfloat16>((size_t)d.R * d.N);
   __nv_bfloat16* vb = a.get<__nv_bfloat16>((size_t)(d.Kst - 1) * d.R * d.N);
   float* dhrec = a.get<float>((size_t)d.R * d.N);
-  __nv_bfloat16* WTb = a.get<__nv_bfloat16>((size_t)64 * ldw);
+  const size_t wbuf = (size_t)64 * (((d.Kst * d.F + 63) / 64) * 64 + 8);
+  __nv_bfloat16* WTb = a.get<__nv_bfloat16>(wbuf);
   float* part = a.get<float>((size_t)max_sms * d.Kst * d.F * d.F);
   float *dgt = nullptr, *c0 = nullptr, *dc0 = nullptr, *dl = nullptr;
   __nv_bfloat16* Wb = nullptr;
   if (d.tg) {
     dgt = a.get<float>(2 * d.BT); c0 = a.get<float>((size_t)d.R * d.N); dc0 = a.get<float>((size_t)d.R * d.N);
-    dl = a.get<float>(d.BT); Wb = a.get<__nv_bfloat16>((size_t)64 * ldw);
+    dl = a.get<float>(d.BT); Wb = a.get<__nv_bfloat16>(wbuf);
   }
   if (a.dry()) return a.off;
   GCRNN_CHECK(dX == nullptr, "the tensor-core path does not produce dX (the reference never asks for it: train_rnn.py:256); "
@@ -249,7 +306,7 @@ size_t cell_backward_tc(const gcrnn_cell* cell, const gcrnn_cell_params* p, cons
 
   CUDA_OK(cudaMemsetAsync(part, 0, part_bytes, st));
   if (d.tg) CUDA_OK(cudaMemsetAsync(dgt, 0, 2 * d.BT * sizeof(float), st));
-  prep_weight(p->weight_B, WTb, d.F, d.Kst, d.F, ldw, 1, st);
+  const int ldt = prep_contract_weight(p->weight_B, WTb, d.F, d.Kst, ldw, 1, st);
 
   // ---- reverse-time sweep -------------------------------------------------------------------------------------------
   for (long long t = d.T - 1; t >= 0; --t) {
@@ -266,10 +323,10 @@ size_t cell_backward_tc(const gcrnn_cell* cell, const gcrnn_cell_params* p, cons
     dpre_kernel<<<(unsigned)std::min<long long>(d.B * (d.F / DP_FC), 148 * 32), 256, 0, st>>>(da);
     launched();
     chain(g, true, vb0, vb, d.Kst, d.R, st);
-    ContractArgs ca = contract_base(d, WTb, ldw, vb0, vb);
+    ContractArgs ca = contract_base(d, WTb, ldt, vb0, vb);
     ca.out_f32 = dhrec; ca.out_bstride = FN; ca.gf = d.tg ? s.gt + d.BT + t : nullptr; ca.gate_stride = d.T;
     ca.hprev = hprev; ca.hprev_bstride = hstride; ca.dgf = d.tg ? dgt + d.BT + t : nullptr; ca.accumulate = 0;
-    launch_contract<EPI_BWD>(ca, d.sms, st);
+    contract<EPI_BWD, TAP_BWD>(ca, WTb, ldt, d.sms, st);
     if (gr->weight_B) wgrad(hprev, hstride, d.tg ? s.gt + d.BT + t : nullptr, d.T);
   }
   wgrad_flush(gr->weight_B);
@@ -280,10 +337,10 @@ size_t cell_backward_tc(const gcrnn_cell* cell, const gcrnn_cell_params* p, cons
     for (int gi = 0; gi < 2; ++gi) {
       cvt_bf16(h0, hb0, d.R * d.N, st);
       chain(g, false, hb0, vb, d.Kst, d.R, st);
-      prep_weight(p->t_weight_B[gi], Wb, d.F, d.Kst, d.F, ldw, 0, st);
-      ContractArgs cc = contract_base(d, Wb, ldw, hb0, vb);
+      const int ldg = prep_contract_weight(p->t_weight_B[gi], Wb, d.F, d.Kst, ldw, 0, st);
+      ContractArgs cc = contract_base(d, Wb, ldg, hb0, vb);
       cc.out_f32 = c0; cc.out_bstride = FN; cc.bias = p->t_bias[gi]; cc.bias_scale = 2.f;
-      launch_contract<EPI_PLAIN>(cc, d.sms, st);
+      contract<EPI_PLAIN, TAP_PLAIN>(cc, Wb, ldg, d.sms, st);
       gate_dlogit_kernel<<<1, 1024, 0, st>>>(dgt + gi * d.BT, s.gt + gi * d.BT, dl, gr->t_mlp_b[gi], d.BT);
       launched();
       GateArgs ga{};
@@ -302,10 +359,10 @@ size_t cell_backward_tc(const gcrnn_cell* cell, const gcrnn_cell_params* p, cons
       chain(g, true, vb0, vb, d.Kst, d.R, st);
       if (gr->t_weight_B[gi]) { wgrad(h0, FN, nullptr, 0); wgrad_flush(gr->t_weight_B[gi]); }
       if (dh0) {
-        prep_weight(p->t_weight_B[gi], Wb, d.F, d.Kst, d.F, ldw, 1, st);
-        ContractArgs cb = contract_base(d, Wb, ldw, vb0, vb);
+        const int ldb = prep_contract_weight(p->t_weight_B[gi], Wb, d.F, d.Kst, ldw, 1, st);
+        ContractArgs cb = contract_base(d, Wb, ldb, vb0, vb);
         cb.out_f32 = dhrec; cb.out_bstride = FN; cb.hprev = h0; cb.hprev_bstride = FN; cb.accumulate = 1;
-        launch_contract<EPI_BWD>(cb, d.sms, st);
+        contract<EPI_BWD, TAP_BWD>(cb, Wb, ldb, d.sms, st);
       }
     }
   }

@@ -1,0 +1,231 @@
+// tcgen05 tap contraction for sm_100a (per sample b):   Y^T[n, m] = sum_{k,c} Z_k[b, c, n] * W[m, k*C + c]
+//
+// This is the reference's `y = z.reshape(B,N,EKG) @ h.reshape(F,EKG)^T` (Utils/graphML.py:134-135) with the K
+// shifted signals kept as K separate bf16 slabs [B][C][N] (no `cat`).  The contraction index (k, c) runs over slab
+// ROWS, and n is contiguous in memory, so the signal tile is an MN-major ("transposed") UMMA operand:
+//   A (M = 128 nodes, K = 64 (k,c) rows)  : TMA boxes {64 n, C rows} -> smem [64 rows][128 B] SW128, MN-major descriptor
+//   B (N = M_out features, K = 64)        : prepared weights W[m][k*C+c], K-major SW128, resident in smem for the CTA
+//   D (TMEM)                              : lane = node n, column = output feature m  (fp32)
+// so an epilogue thread owns ONE node and all output features: stores to [b, m, n] are coalesced across the warp.
+// Same warp-specialised persistent structure as tc_gemm.cuh (TMA producer warp, single-thread MMA issuer,
+// 4 epilogue warps, double-buffered TMEM accumulators).  It is HBM-bound (reads K slabs once); the MMAs are ~5 % of
+// the tile time.  Fused epilogues: EPI_FWD (input filter + bias + time gates + tanh, writes H[b,t] and the bf16 state),
+// EPI_BWD (dg_f reduction, dh_rec = g_f q), EPI_PLAIN (gate sub-cell term).
+#pragma once
+#include "tc_gemm.cuh"
+
+namespace gcrnn {
+namespace tc {
+
+constexpr int TAP_BM = 128;        // nodes per tile
+constexpr int TAP_STAGES = 8;      // ring of 64-row stages (16 KB each)
+constexpr int TAP_STAGE_BYTES = 2 * 64 * 128;
+constexpr int TAP_MAX_KB = 6;      // K*C <= 384 contraction rows
+
+enum { TAP_PLAIN = 0, TAP_FWD = 1, TAP_BWD = 2 };
+
+struct TapArgs {
+  int K, C, M, N, KB;              // slabs, channels per slab, output features, nodes, ceil(K*C/64)
+  long long B, R;                  // samples, rows per slab (B*C)
+  // epilogue
+  float* out_f32; long long out_bstride;
+  __nv_bfloat16* out_bf16;
+  const float* bias; float bias_scale;
+  const float* gi; const float* gf; long long gate_stride;
+  const float* A; int Kin, G;
+  const float* x0; long long x0_bstride;
+  const float* zx; long long zx_kstride, zx_bstride;
+  const float* hprev; long long hprev_bstride;
+  float* dgf; int accumulate;
+};
+
+__device__ __forceinline__ float tap_tanh(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// MN-major, 128B-swizzled operand: 64-element (128 B) blocks along M at stride LBO, 8-row groups along K at stride SBO
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__host__ __device__ constexpr uint32_t make_idesc_bf16_amn(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+template <int EPI, int KGM>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+tap_gemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tmc,
+                const __grid_constant__ CUtensorMap tmW, const TapArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sW = smem;                                              // [KB][64 rows][128 B]
+  uint8_t* sA = smem + TAP_MAX_KB * 8192;                          // [STAGES][2 halves][64 rows][128 B]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sA + TAP_STAGES * TAP_STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + TAP_STAGES;
+  uint64_t* tmem_full = empty_bar + TAP_STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint64_t* w_bar = tmem_empty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
+  float* sAw = reinterpret_cast<float*>(tmem_slot + 4);            // [M][Kin*G] input-filter taps (<= 64*32)
+  float* sBias = sAw + 64 * 32;                                    // [64]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_n = a.N / TAP_BM;
+  const long long num_tiles = a.B * tiles_n;
+  const int KK = a.K * a.C;
+  const int acc_stride = a.M < 32 ? 32 : a.M;                      // TMEM columns per accumulator stage
+  const uint32_t tmem_cols = (2 * acc_stride <= 32) ? 32 : (2 * acc_stride <= 64) ? 64 : 128;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tm0); tma_prefetch_desc(&tmc); tma_prefetch_desc(&tmW);
+    for (int s = 0; s < TAP_STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tmem_full + s, 1); mbar_init(tmem_empty + s, 128); }
+    mbar_init(w_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+  if (EPI == TAP_FWD) for (int i = threadIdx.x; i < a.M * a.Kin * a.G; i += NUM_THREADS) sAw[i] = a.A[i];
+  for (int i = threadIdx.x; i < 64; i += NUM_THREADS) sBias[i] = (a.bias && i < a.M) ? a.bias[i] : 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      mbar_expect_tx(w_bar, (uint32_t)(a.KB * a.M * 128));
+      for (int kb = 0; kb < a.KB; ++kb) tma_load_2d(sW + kb * 8192, &tmW, w_bar, kb * 64, 0);
+      int stage = 0; uint32_t phase = 0;
+      for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const long long b = tile / tiles_n;
+        const int n0 = (int)(tile % tiles_n) * TAP_BM;
+        for (int s = 0; s < a.KB; ++s) {
+          const int rows = min(64, KK - 64 * s);
+          mbar_wait(empty_bar + stage, phase ^ 1);
+          uint8_t* dst = sA + stage * TAP_STAGE_BYTES;
+          mbar_expect_tx(full_bar + stage, (uint32_t)(2 * rows * 128));
+          for (int r0 = 0; r0 < rows; r0 += a.C) {                 // one box per slab touched by this stage
+            const int k = (64 * s + r0) / a.C;
+            const CUtensorMap* tm = (k == 0) ? &tm0 : &tmc;
+            const int row = (k == 0) ? (int)(b * a.C) : (int)((long long)(k - 1) * a.R + b * a.C);
+            tma_load_2d(dst + r0 * 128, tm, full_bar + stage, n0, row);
+            tma_load_2d(dst + 8192 + r0 * 128, tm, full_bar + stage, n0 + 64, row);
+          }
+          if (++stage == TAP_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16_amn(TAP_BM, a.M);
+      mbar_wait(w_bar, 0);
+      tc_fence_after();
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(tmem_empty + acc, acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * acc_stride);
+        for (int s = 0; s < a.KB; ++s) {
+          const int rows = min(64, KK - 64 * s);
+          mbar_wait(full_bar + stage, phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(sA + stage * TAP_STAGE_BYTES);
+          const uint32_t sb = smem_u32(sW + s * 8192);
+          for (int j = 0; j < rows / 16; ++j) {
+            const uint64_t adesc = make_mnmajor_sw128_desc(sa + j * 2048, 8192);   // 16 K-rows = 2048 B
+            const uint64_t bdesc = make_kmajor_sw128_desc(sb) + (uint64_t)(2 * j); // 16 bf16 = 32 B along K
+            umma_f16(d_tmem, adesc, bdesc, idesc, (s | j) != 0);
+          }
+          umma_commit(empty_bar + stage);
+          if (++stage == TAP_STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(tmem_full + acc);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===== epilogue warps 2..5: thread <-> node =====
+    const int q = warp & 3;
+    const int KG = a.Kin * a.G;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const long long b = tile / tiles_n;
+      const int n = (int)(tile % tiles_n) * TAP_BM + q * 32 + lane;
+      // operands that do not depend on the accumulator: fetch before waiting for the MMAs
+      float z[KGM];
+      float vgi = 1.f, vgf = 1.f;
+      if (EPI != TAP_PLAIN) {
+        if (a.gi) vgi = a.gi[b * a.gate_stride];
+        if (a.gf) vgf = a.gf[b * a.gate_stride];
+      }
+      if (EPI == TAP_FWD) {
+#pragma unroll
+        for (int kg = 0; kg < KGM; ++kg) {
+          if (kg < KG) {
+            const int k = kg / a.G, g = kg % a.G;
+            z[kg] = (k == 0) ? a.x0[b * a.x0_bstride + (size_t)g * a.N + n]
+                             : a.zx[(size_t)(k - 1) * a.zx_kstride + b * a.zx_bstride + (size_t)g * a.N + n];
+          } else z[kg] = 0.f;
+        }
+      }
+      mbar_wait(tmem_full + acc, acc_phase);
+      tc_fence_after();
+      const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * acc_stride);
+      float part = 0.f;
+      for (int c = 0; c < a.M; c += 32) {
+        float v[32];
+        tmem_ld32(t0 + (uint32_t)c, v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int m = c + i;
+          if (m < a.M) {
+            if (EPI == TAP_PLAIN) {
+              a.out_f32[b * a.out_bstride + (size_t)m * a.N + n] = v[i] + a.bias_scale * sBias[m];
+            } else if (EPI == TAP_FWD) {
+              float ax = 0.f;
+#pragma unroll
+              for (int kg = 0; kg < KGM; ++kg) if (kg < KG) ax = fmaf(sAw[m * KG + kg], z[kg], ax);
+              const float bb = sBias[m];
+              const float h = tap_tanh(vgi * (ax + bb) + vgf * (v[i] + bb));
+              a.out_f32[b * a.out_bstride + (size_t)m * a.N + n] = h;
+              a.out_bf16[((size_t)b * a.M + m) * a.N + n] = __float2bfloat16(h);
+            } else {
+              const float hp = a.hprev[b * a.hprev_bstride + (size_t)m * a.N + n];
+              part = fmaf(v[i], hp, part);
+              float* o = a.out_f32 + b * a.out_bstride + (size_t)m * a.N + n;
+              float r = vgf * v[i];
+              if (a.accumulate) r += *o;
+              *o = r;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tmem_empty + acc);
+      if (EPI == TAP_BWD && a.dgf) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        if (lane == 0) atomicAdd(a.dgf + b * a.gate_stride, part);
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, tmem_cols); }
+}
+
+constexpr int TAP_SMEM = TAP_MAX_KB * 8192 + TAP_STAGES * TAP_STAGE_BYTES + 256 + (64 * 32 + 64) * 4 + 1024;
+
+}  // namespace tc
+}  // namespace gcrnn
