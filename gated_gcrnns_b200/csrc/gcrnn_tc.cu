@@ -153,11 +153,11 @@ static void launch_tap(const ContractArgs& ca, const __nv_bfloat16* Wp, int sms,
   if (small) {
     auto kern = tap_gemm_kernel<EPI, 8>;
     CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TAP_SMEM));
-    kern<<<grid, NUM_THREADS, TAP_SMEM, st>>>(tm0, tmc, tmW, t);
+    kern<<<grid, TAP_THREADS, TAP_SMEM, st>>>(tm0, tmc, tmW, t);
   } else {
     auto kern = tap_gemm_kernel<EPI, 32>;
     CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TAP_SMEM));
-    kern<<<grid, NUM_THREADS, TAP_SMEM, st>>>(tm0, tmc, tmW, t);
+    kern<<<grid, TAP_THREADS, TAP_SMEM, st>>>(tm0, tmc, tmW, t);
   }
   launched();
 }

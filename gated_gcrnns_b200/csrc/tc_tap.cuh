@@ -21,6 +21,7 @@ constexpr int TAP_BM = 128;        // nodes per tile
 constexpr int TAP_STAGES = 8;      // ring of 64-row stages (16 KB each)
 constexpr int TAP_STAGE_BYTES = 2 * 64 * 128;
 constexpr int TAP_MAX_KB = 6;      // K*C <= 384 contraction rows
+constexpr int TAP_THREADS = 64 + 16 * 32;   // TMA warp + MMA warp + 16 epilogue warps
 
 enum { TAP_PLAIN = 0, TAP_FWD = 1, TAP_BWD = 2 };
 
@@ -45,6 +46,17 @@ __device__ __forceinline__ float tap_tanh(float x) {
   return y;
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 // MN-major, 128B-swizzled operand: 64-element (128 B) blocks along M at stride LBO, 8-row groups along K at stride SBO
 __device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
   uint64_t d = 0;
@@ -60,7 +72,7 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16_amn(int M, int N) {
 }
 
 template <int EPI, int KGM>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(TAP_THREADS, 1)
 tap_gemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tmc,
                 const __grid_constant__ CUtensorMap tmW, const TapArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -86,13 +98,13 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tm0); tma_prefetch_desc(&tmc); tma_prefetch_desc(&tmW);
     for (int s = 0; s < TAP_STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tmem_full + s, 1); mbar_init(tmem_empty + s, 128); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tmem_full + s, 1); mbar_init(tmem_empty + s, 128 * ((a.M + 15) / 16)); }
     mbar_init(w_bar, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
-  if (EPI == TAP_FWD) for (int i = threadIdx.x; i < a.M * a.Kin * a.G; i += NUM_THREADS) sAw[i] = a.A[i];
-  for (int i = threadIdx.x; i < 64; i += NUM_THREADS) sBias[i] = (a.bias && i < a.M) ? a.bias[i] : 0.f;
+  if (EPI == TAP_FWD) for (int i = threadIdx.x; i < a.M * a.Kin * a.G; i += TAP_THREADS) sAw[i] = a.A[i];
+  for (int i = threadIdx.x; i < 64; i += TAP_THREADS) sBias[i] = (a.bias && i < a.M) ? a.bias[i] : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -154,70 +166,82 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__
       }
     }
   } else {
-    // ===== epilogue warps 2..5: thread <-> node =====
+    // ===== 16 epilogue warps: TMEM lane quarter q = warp % 4 (thread <-> node), feature group cg = 16 columns =====
     const int q = warp & 3;
-    const int KG = a.Kin * a.G;
-    int acc = 0; uint32_t acc_phase = 0;
-    for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const long long b = tile / tiles_n;
-      const int n = (int)(tile % tiles_n) * TAP_BM + q * 32 + lane;
-      // operands that do not depend on the accumulator: fetch before waiting for the MMAs
-      float z[KGM];
-      float vgi = 1.f, vgf = 1.f;
-      if (EPI != TAP_PLAIN) {
-        if (a.gi) vgi = a.gi[b * a.gate_stride];
-        if (a.gf) vgf = a.gf[b * a.gate_stride];
-      }
-      if (EPI == TAP_FWD) {
-#pragma unroll
-        for (int kg = 0; kg < KGM; ++kg) {
-          if (kg < KG) {
-            const int k = kg / a.G, g = kg % a.G;
-            z[kg] = (k == 0) ? a.x0[b * a.x0_bstride + (size_t)g * a.N + n]
-                             : a.zx[(size_t)(k - 1) * a.zx_kstride + b * a.zx_bstride + (size_t)g * a.N + n];
-          } else z[kg] = 0.f;
+    const int cg = (warp - 2) >> 2;
+    const int m0 = cg * 16;
+    if (m0 < a.M) {
+      const int KG = a.Kin * a.G;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const long long b = tile / tiles_n;
+        const int n = (int)(tile % tiles_n) * TAP_BM + q * 32 + lane;
+        // operands that do not depend on the accumulator are fetched before waiting for the MMAs
+        float z[KGM], hp[16];
+        float vgi = 1.f, vgf = 1.f;
+        if (EPI != TAP_PLAIN) {
+          if (a.gi) vgi = __ldg(a.gi + b * a.gate_stride);
+          if (a.gf) vgf = __ldg(a.gf + b * a.gate_stride);
         }
-      }
-      mbar_wait(tmem_full + acc, acc_phase);
-      tc_fence_after();
-      const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * acc_stride);
-      float part = 0.f;
-      for (int c = 0; c < a.M; c += 32) {
-        float v[32];
-        tmem_ld32(t0 + (uint32_t)c, v);
+        if (EPI == TAP_FWD) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int m = c + i;
-          if (m < a.M) {
-            if (EPI == TAP_PLAIN) {
-              a.out_f32[b * a.out_bstride + (size_t)m * a.N + n] = v[i] + a.bias_scale * sBias[m];
-            } else if (EPI == TAP_FWD) {
-              float ax = 0.f;
-#pragma unroll
-              for (int kg = 0; kg < KGM; ++kg) if (kg < KG) ax = fmaf(sAw[m * KG + kg], z[kg], ax);
-              const float bb = sBias[m];
-              const float h = tap_tanh(vgi * (ax + bb) + vgf * (v[i] + bb));
-              a.out_f32[b * a.out_bstride + (size_t)m * a.N + n] = h;
-              a.out_bf16[((size_t)b * a.M + m) * a.N + n] = __float2bfloat16(h);
-            } else {
-              const float hp = a.hprev[b * a.hprev_bstride + (size_t)m * a.N + n];
-              part = fmaf(v[i], hp, part);
-              float* o = a.out_f32 + b * a.out_bstride + (size_t)m * a.N + n;
-              float r = vgf * v[i];
-              if (a.accumulate) r += *o;
-              *o = r;
-            }
+          for (int kg = 0; kg < KGM; ++kg) {
+            if (kg < KG) {
+              const int k = kg / a.G, g = kg % a.G;
+              z[kg] = (k == 0) ? __ldg(a.x0 + b * a.x0_bstride + (size_t)g * a.N + n)
+                               : __ldg(a.zx + (size_t)(k - 1) * a.zx_kstride + b * a.zx_bstride + (size_t)g * a.N + n);
+            } else z[kg] = 0.f;
           }
         }
-      }
-      tc_fence_before();
-      mbar_arrive(tmem_empty + acc);
-      if (EPI == TAP_BWD && a.dgf) {
+        if (EPI == TAP_BWD) {
+          const float* hb = a.hprev + b * a.hprev_bstride + (size_t)m0 * a.N + n;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-        if (lane == 0) atomicAdd(a.dgf + b * a.gate_stride, part);
+          for (int i = 0; i < 16; ++i) hp[i] = __ldg(hb + (size_t)i * a.N);
+        }
+        mbar_wait(tmem_full + acc, acc_phase);
+        tc_fence_after();
+        float v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * acc_stride + m0), v);
+        tc_fence_before();
+        mbar_arrive(tmem_empty + acc);                  // accumulator values are in registers: release the TMEM stage early
+        float* of = a.out_f32 + b * a.out_bstride + (size_t)m0 * a.N + n;
+        if (EPI == TAP_PLAIN) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) of[(size_t)i * a.N] = v[i] + a.bias_scale * sBias[m0 + i];
+        } else if (EPI == TAP_FWD) {
+          __nv_bfloat16* ob = a.out_bf16 + ((size_t)b * a.M + m0) * a.N + n;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float ax = 0.f;
+#pragma unroll
+            for (int kg = 0; kg < KGM; ++kg) if (kg < KG) ax = fmaf(sAw[(m0 + i) * KG + kg], z[kg], ax);
+            const float bb = sBias[m0 + i];
+            const float h = tap_tanh(vgi * (ax + bb) + vgf * (v[i] + bb));
+            of[(size_t)i * a.N] = h;
+            ob[(size_t)i * a.N] = __float2bfloat16(h);
+          }
+        } else {
+          float part = 0.f;
+          float old[16];
+          if (a.accumulate) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) old[i] = of[(size_t)i * a.N];
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            part = fmaf(v[i], hp[i], part);
+            float r = vgf * v[i];
+            if (a.accumulate) r += old[i];
+            of[(size_t)i * a.N] = r;
+          }
+          if (a.dgf) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+            if (lane == 0) atomicAdd(a.dgf + b * a.gate_stride, part);
+          }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
   tc_fence_before();
