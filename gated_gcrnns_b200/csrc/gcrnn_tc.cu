@@ -71,12 +71,6 @@ static void cvt_bf16(const float* in, __nv_bfloat16* out, long long n, cudaStrea
   cvt_bf16_kernel<<<(unsigned)std::min<long long>((n / 4 + 255) / 256, 148 * 16), 256, 0, st>>>(in, out, n / 4);
   launched();
 }
-[[maybe_unused]] static void prep_weight(const float* W, __nv_bfloat16* out, int F, int K, int G, int ld, int mode, cudaStream_t st) {
-  CUDA_OK(cudaMemsetAsync(out, 0, (size_t)64 * ld * sizeof(__nv_bfloat16), st));
-  prep_weight_kernel<<<(F * K * G + 255) / 256, 256, 0, st>>>(W, out, F, K, G, ld, mode);
-  launched();
-}
-
 struct TcDims {
   int N, F, G, Kin, Kst, sms;
   long long B, T, R, RX, BT;
@@ -98,11 +92,13 @@ static TcDims tc_dims(const gcrnn_cell* c, int64_t B, int64_t T) {
 }
 
 struct TcSaved {
-  float* zx;   // [Kin-1][RX][N]
-  float* gt;   // [2][B][T]
+  float* zx;            // [Kin-1][RX][N]   x_t S^k, k >= 1
+  float* gt;            // [2][B][T]        time-gate values
+  __nv_bfloat16* Hb;    // [T][R][N]        bf16 copy of every state (GEMM / wgrad operand)
   void layout(Arena& a, const TcDims& d) {
     zx = a.get<float>((size_t)(d.Kin - 1) * d.RX * d.N);
     gt = d.tg ? a.get<float>(2 * d.BT) : nullptr;
+    Hb = a.get<__nv_bfloat16>((size_t)d.T * d.R * d.N);
   }
 };
 
@@ -116,18 +112,12 @@ static void chain(const gcrnn_graph* g, bool backward, const __nv_bfloat16* z0, 
   }
 }
 
-static ContractArgs contract_base(const TcDims& d, const __nv_bfloat16* W, int ldw, const __nv_bfloat16* z0, const __nv_bfloat16* zc) {
+static ContractArgs contract_base(const TcDims& d, const __nv_bfloat16* z0, const __nv_bfloat16* zc) {
   ContractArgs a{};
-  a.W = W; a.ldw = ldw; a.K = d.Kst; a.C = d.F; a.M = d.F; a.N = d.N; a.B = d.B;
+  a.K = d.Kst; a.C = d.F; a.M = d.F; a.N = d.N; a.B = d.B;
   a.slab[0] = z0;
   for (int k = 1; k < d.Kst; ++k) a.slab[k] = zc + (size_t)(k - 1) * d.R * d.N;
   return a;
-}
-
-static bool use_tap_gemm() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("GCRNN_TC_CONTRACT"); v = (e && std::string(e) == "mma") ? 0 : 1; }
-  return v == 1;
 }
 
 // tap contraction on tcgen05 (tc_tap.cuh).  Wp: prepared bf16 weights [M][KB*64] (zero padded), ca: the same
@@ -141,7 +131,7 @@ static void launch_tap(const ContractArgs& ca, const __nv_bfloat16* Wp, int sms,
   t.out_f32 = ca.out_f32; t.out_bstride = ca.out_bstride; t.out_bf16 = ca.out_bf16; t.bias = ca.bias; t.bias_scale = ca.bias_scale;
   t.gi = ca.gi; t.gf = ca.gf; t.gate_stride = ca.gate_stride; t.A = ca.A; t.Kin = ca.Kin; t.G = ca.G;
   t.x0 = ca.x0; t.x0_bstride = ca.x0_bstride; t.zx = ca.zx; t.zx_kstride = ca.zx_kstride; t.zx_bstride = ca.zx_bstride;
-  t.hprev = ca.hprev; t.hprev_bstride = ca.hprev_bstride; t.dgf = ca.dgf; t.accumulate = ca.accumulate;
+  t.hprev = ca.hprev; t.hprev_bstride = ca.hprev_bstride; t.dgf = ca.dgf; t.accumulate = ca.accumulate; t.scaled_chain = ca.scaled_chain;
   for (int k = 2; k < ca.K; ++k)
     GCRNN_CHECK(ca.slab[k] == ca.slab[1] + (size_t)(k - 1) * t.R * ca.N, "tap_gemm: slabs 1..K-1 must be contiguous");
   const CUtensorMap tm0 = make_tmap_bf16(ca.slab[0], t.R, ca.N, ca.C);
@@ -162,19 +152,27 @@ static void launch_tap(const ContractArgs& ca, const __nv_bfloat16* Wp, int sms,
   launched();
 }
 
-// weights for either contraction kernel: returns the leading dimension used
-static int prep_contract_weight(const float* W, __nv_bfloat16* out, int F, int K, int ldw_mma, int mode, cudaStream_t st) {
-  const int ld = use_tap_gemm() ? ((K * F + 63) / 64) * 64 : ldw_mma;
-  CUDA_OK(cudaMemsetAsync(out, 0, (size_t)64 * (((K * F + 63) / 64) * 64 + 8) * sizeof(__nv_bfloat16), st));
+// prepared bf16 weights [64][KB*64] (zero padded): mode 0 rows = output features, mode 1 rows = input features
+static int prep_contract_weight(const float* W, __nv_bfloat16* out, int F, int K, int mode, cudaStream_t st) {
+  const int ld = ((K * F + 63) / 64) * 64;
+  CUDA_OK(cudaMemsetAsync(out, 0, (size_t)64 * ld * sizeof(__nv_bfloat16), st));
   prep_weight_kernel<<<(F * K * F + 255) / 256, 256, 0, st>>>(W, out, F, K, F, ld, mode);
   launched();
   return ld;
 }
 
-template <int EPI_MMA, int EPI_TAP>
-static void contract(ContractArgs& ca, const __nv_bfloat16* Wp, int ld, int sms, cudaStream_t st) {
-  if (use_tap_gemm()) launch_tap<EPI_TAP>(ca, Wp, sms, st);
-  else { ca.W = Wp; ca.ldw = ld; launch_contract<EPI_MMA>(ca, sms, st); }
+// dB_k += sum_{b,n} V_k h^T on tcgen05 (F = 64): hb = bf16 h_{t-1} [R][N]
+static void launch_wgrad_tc(const TcDims& d, const __nv_bfloat16* v0, const __nv_bfloat16* vc, const __nv_bfloat16* hb, float* part,
+                            cudaStream_t st) {
+  WgradTcArgs w{};
+  w.K = d.Kst; w.N = d.N; w.B = d.B; w.R = d.R; w.part = part;
+  const CUtensorMap tm0 = make_tmap_bf16(v0, d.R, d.N, 64);
+  const CUtensorMap tmc = d.Kst > 1 ? make_tmap_bf16(vc, (long long)(d.Kst - 1) * d.R, d.N, 64) : tm0;
+  const CUtensorMap tmH = make_tmap_bf16(hb, d.R, d.N, 64);
+  const int sm = WT_STAGES * wt_stage_bytes(d.Kst) + 256 + 1024;
+  CUDA_OK(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+  wgrad_tc_kernel<<<d.sms, NUM_THREADS, sm, st>>>(tm0, tmc, tmH, w);
+  launched();
 }
 
 static void gate_launch(bool bwd, const GateArgs& ga, const TcDims& d, cudaStream_t st) {
@@ -198,13 +196,11 @@ size_t cell_forward_tc(const gcrnn_cell* cell, const gcrnn_cell_params* p, const
   TcSaved s;
   { Arena sa(saved, savedb); s.layout(sa, d); if (saved_used) *saved_used = sa.off; }
   GCRNN_CHECK(a.dry() || saved, "forward needs the `saved` buffer");
-  const int ldw = d.Kst * d.F + 8;
   __nv_bfloat16* xb0 = a.get<__nv_bfloat16>((size_t)d.RX * d.N);
   __nv_bfloat16* xb1 = a.get<__nv_bfloat16>((size_t)d.RX * d.N);
   __nv_bfloat16* hb0 = a.get<__nv_bfloat16>((size_t)d.R * d.N);
-  __nv_bfloat16* hb1 = a.get<__nv_bfloat16>((size_t)d.R * d.N);
   __nv_bfloat16* zb = a.get<__nv_bfloat16>((size_t)(d.Kst - 1) * d.R * d.N);
-  const size_t wbuf = (size_t)64 * (((d.Kst * d.F + 63) / 64) * 64 + 8);
+  const size_t wbuf = (size_t)64 * (((d.Kst * d.F + 63) / 64) * 64);
   __nv_bfloat16* Wb = a.get<__nv_bfloat16>(wbuf);
   float* c0 = d.tg ? a.get<float>((size_t)d.R * d.N) : nullptr;
   float* logit = d.tg ? a.get<float>(2 * d.BT) : nullptr;
@@ -227,10 +223,10 @@ size_t cell_forward_tc(const gcrnn_cell* cell, const gcrnn_cell_params* p, const
     chain(g, false, hb0, zb, d.Kst, d.R, st);
     CUDA_OK(cudaMemsetAsync(logit, 0, 2 * d.BT * sizeof(float), st));
     for (int gi = 0; gi < 2; ++gi) {
-      const int ldg = prep_contract_weight(p->t_weight_B[gi], Wb, d.F, d.Kst, ldw, 0, st);
-      ContractArgs ca = contract_base(d, Wb, ldg, hb0, zb);
+      prep_contract_weight(p->t_weight_B[gi], Wb, d.F, d.Kst, 0, st);
+      ContractArgs ca = contract_base(d, hb0, zb);
       ca.out_f32 = c0; ca.out_bstride = FN; ca.bias = p->t_bias[gi]; ca.bias_scale = 2.f;   // bias enters twice (:2421-2422)
-      contract<EPI_PLAIN, TAP_PLAIN>(ca, Wb, ldg, d.sms, st);
+      launch_tap<TAP_PLAIN>(ca, Wb, d.sms, st);
       GateArgs ga{};
       ga.A = p->t_weight_A[gi]; ga.Kin = d.Kin; ga.G = d.G; ga.F = d.F; ga.N = d.N; ga.B = d.B; ga.T = d.T;
       ga.X = X; ga.zx = s.zx; ga.c0 = c0; ga.Wg = p->t_mlp_w[gi]; ga.logit = logit + gi * d.BT;
@@ -241,19 +237,18 @@ size_t cell_forward_tc(const gcrnn_cell* cell, const gcrnn_cell_params* p, const
     }
   }
   // ---- the recurrence -------------------------------------------------------------------------------------------
-  const int ldm = prep_contract_weight(p->weight_B, Wb, d.F, d.Kst, ldw, 0, st);
-  __nv_bfloat16* hb[2] = {hb0, hb1};
+  prep_contract_weight(p->weight_B, Wb, d.F, d.Kst, 0, st);
   for (long long t = 0; t < d.T; ++t) {
-    const __nv_bfloat16* hprev = hb[t & 1];
+    const __nv_bfloat16* hprev = t == 0 ? hb0 : s.Hb + (size_t)(t - 1) * d.R * d.N;
     if (!(t == 0 && d.tg)) chain(g, false, hprev, zb, d.Kst, d.R, st);      // at t = 0 the gates' h0 chain is still in zb
-    ContractArgs ca = contract_base(d, Wb, ldm, hprev, zb);
-    ca.out_f32 = H + t * FN; ca.out_bstride = d.T * FN; ca.out_bf16 = hb[(t + 1) & 1];
+    ContractArgs ca = contract_base(d, hprev, zb);
+    ca.out_f32 = H + t * FN; ca.out_bstride = d.T * FN; ca.out_bf16 = s.Hb + (size_t)t * d.R * d.N;
     ca.bias = p->bias;
     ca.gi = d.tg ? s.gt + t : nullptr; ca.gf = d.tg ? s.gt + d.BT + t : nullptr; ca.gate_stride = d.T;
     ca.A = p->weight_A; ca.Kin = d.Kin; ca.G = d.G;
     ca.x0 = X + t * GN; ca.x0_bstride = d.T * GN;
     ca.zx = s.zx + t * GN; ca.zx_kstride = d.RX * d.N; ca.zx_bstride = d.T * GN;
-    contract<EPI_FWD, TAP_FWD>(ca, Wb, ldm, d.sms, st);
+    launch_tap<TAP_FWD>(ca, Wb, d.sms, st);
   }
   return a.off;
 }
@@ -268,12 +263,12 @@ size_t cell_backward_tc(const gcrnn_cell* cell, const gcrnn_cell_params* p, cons
   TcSaved s;
   { Arena sa(const_cast<void*>(saved), savedb); s.layout(sa, d); }
   GCRNN_CHECK(a.dry() || saved, "backward needs the buffer written by forward");
-  const int ldw = d.Kst * d.F + 8;
   const int max_sms = 256;
   __nv_bfloat16* vb0 = a.get<__nv_bfloat16>((size_t)d.R * d.N);
   __nv_bfloat16* vb = a.get<__nv_bfloat16>((size_t)(d.Kst - 1) * d.R * d.N);
   float* dhrec = a.get<float>((size_t)d.R * d.N);
-  const size_t wbuf = (size_t)64 * (((d.Kst * d.F + 63) / 64) * 64 + 8);
+  const size_t wbuf = (size_t)64 * (((d.Kst * d.F + 63) / 64) * 64);
+  __nv_bfloat16* hb0 = a.get<__nv_bfloat16>((size_t)d.R * d.N);
   __nv_bfloat16* WTb = a.get<__nv_bfloat16>(wbuf);
   float* part = a.get<float>((size_t)max_sms * d.Kst * d.F * d.F);
   float *dgt = nullptr, *c0 = nullptr, *dc0 = nullptr, *dl = nullptr;
@@ -290,9 +285,11 @@ size_t cell_backward_tc(const gcrnn_cell* cell, const gcrnn_cell_params* p, cons
   const long long FN = (long long)d.F * d.N, GN = (long long)d.G * d.N;
   const size_t part_bytes = (size_t)d.sms * d.Kst * d.F * d.F * sizeof(float);
 
-  auto wgrad = [&](const float* hsrc, long long hstride, const float* scale, long long sstride) {
+  // dB_k += sum_{b,n} V_k h^T with the (already g_f-scaled) adjoint chain in vb0/vb
+  auto wgrad = [&](const float* h32, long long hstride, const __nv_bfloat16* h16) {
+    if (d.F == 64) { launch_wgrad_tc(d, vb0, vb, h16, part, st); return; }
     WgradArgs w{};
-    w.v0 = vb0; w.vc = vb; w.h = hsrc; w.h_bstride = hstride; w.scale = scale; w.scale_stride = sstride;
+    w.v0 = vb0; w.vc = vb; w.h = h32; w.h_bstride = hstride; w.scale = nullptr; w.scale_stride = 0;
     w.part = part; w.K = d.Kst; w.F = d.F; w.N = d.N; w.B = d.B;
     const size_t sm = ((size_t)2 * d.Kst * 64 * WG_LD + (size_t)2 * 64 * WG_LD) * sizeof(__nv_bfloat16);
     CUDA_OK(cudaFuncSetAttribute(wgrad_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
@@ -306,12 +303,14 @@ size_t cell_backward_tc(const gcrnn_cell* cell, const gcrnn_cell_params* p, cons
 
   CUDA_OK(cudaMemsetAsync(part, 0, part_bytes, st));
   if (d.tg) CUDA_OK(cudaMemsetAsync(dgt, 0, 2 * d.BT * sizeof(float), st));
-  const int ldt = prep_contract_weight(p->weight_B, WTb, d.F, d.Kst, ldw, 1, st);
+  prep_contract_weight(p->weight_B, WTb, d.F, d.Kst, 1, st);
+  cvt_bf16(h0, hb0, d.R * d.N, st);
 
   // ---- reverse-time sweep -------------------------------------------------------------------------------------------
   for (long long t = d.T - 1; t >= 0; --t) {
     const float* hprev = t > 0 ? H + (t - 1) * FN : h0;
     const long long hstride = t > 0 ? d.T * FN : FN;
+    const __nv_bfloat16* hprev16 = t > 0 ? s.Hb + (size_t)(t - 1) * d.R * d.N : hb0;
     DpreArgs da{};
     da.dH = dH + t * FN; da.dH_bstride = d.T * FN; da.Ht = H + t * FN; da.H_bstride = d.T * FN;
     da.dhrec = (t == d.T - 1) ? nullptr : dhrec; da.v0 = vb0;
@@ -323,24 +322,23 @@ size_t cell_backward_tc(const gcrnn_cell* cell, const gcrnn_cell_params* p, cons
     dpre_kernel<<<(unsigned)std::min<long long>(d.B * (d.F / DP_FC), 148 * 32), 256, 0, st>>>(da);
     launched();
     chain(g, true, vb0, vb, d.Kst, d.R, st);
-    ContractArgs ca = contract_base(d, WTb, ldt, vb0, vb);
+    ContractArgs ca = contract_base(d, vb0, vb);
     ca.out_f32 = dhrec; ca.out_bstride = FN; ca.gf = d.tg ? s.gt + d.BT + t : nullptr; ca.gate_stride = d.T;
     ca.hprev = hprev; ca.hprev_bstride = hstride; ca.dgf = d.tg ? dgt + d.BT + t : nullptr; ca.accumulate = 0;
-    contract<EPI_BWD, TAP_BWD>(ca, WTb, ldt, d.sms, st);
-    if (gr->weight_B) wgrad(hprev, hstride, d.tg ? s.gt + d.BT + t : nullptr, d.T);
+    ca.scaled_chain = 1;                       // dpre_kernel wrote g_f * dpre: acc = g_f q = dh_{t-1} directly
+    launch_tap<TAP_BWD>(ca, WTb, d.sms, st);
+    if (gr->weight_B) wgrad(hprev, hstride, hprev16);
   }
   wgrad_flush(gr->weight_B);
 
   // ---- time gates, batched over (b, t) -----------------------------------------------------------------------------------
   if (d.tg) {
-    __nv_bfloat16* hb0 = vb0;                  // reuse: bf16 h0 and its chain live where the v slabs were
     for (int gi = 0; gi < 2; ++gi) {
-      cvt_bf16(h0, hb0, d.R * d.N, st);
-      chain(g, false, hb0, vb, d.Kst, d.R, st);
-      const int ldg = prep_contract_weight(p->t_weight_B[gi], Wb, d.F, d.Kst, ldw, 0, st);
-      ContractArgs cc = contract_base(d, Wb, ldg, hb0, vb);
+      chain(g, false, hb0, vb, d.Kst, d.R, st);  // the v slabs are free here: they hold h0's forward chain for a moment
+      prep_contract_weight(p->t_weight_B[gi], Wb, d.F, d.Kst, 0, st);
+      ContractArgs cc = contract_base(d, hb0, vb);
       cc.out_f32 = c0; cc.out_bstride = FN; cc.bias = p->t_bias[gi]; cc.bias_scale = 2.f;
-      contract<EPI_PLAIN, TAP_PLAIN>(cc, Wb, ldg, d.sms, st);
+      launch_tap<TAP_PLAIN>(cc, Wb, d.sms, st);
       gate_dlogit_kernel<<<1, 1024, 0, st>>>(dgt + gi * d.BT, s.gt + gi * d.BT, dl, gr->t_mlp_b[gi], d.BT);
       launched();
       GateArgs ga{};
@@ -357,12 +355,12 @@ size_t cell_backward_tc(const gcrnn_cell* cell, const gcrnn_cell_params* p, cons
       // h0 path of the sub-cell: v_k = dc0 (S^T)^k ; dB_g,k = v_k h0^T ; dh0 += sum_k B_g,k^T v_k
       cvt_bf16(dc0, vb0, d.R * d.N, st);
       chain(g, true, vb0, vb, d.Kst, d.R, st);
-      if (gr->t_weight_B[gi]) { wgrad(h0, FN, nullptr, 0); wgrad_flush(gr->t_weight_B[gi]); }
+      if (gr->t_weight_B[gi]) { wgrad(h0, FN, hb0); wgrad_flush(gr->t_weight_B[gi]); }
       if (dh0) {
-        const int ldb = prep_contract_weight(p->t_weight_B[gi], Wb, d.F, d.Kst, ldw, 1, st);
-        ContractArgs cb = contract_base(d, Wb, ldb, vb0, vb);
+        prep_contract_weight(p->t_weight_B[gi], Wb, d.F, d.Kst, 1, st);
+        ContractArgs cb = contract_base(d, vb0, vb);
         cb.out_f32 = dhrec; cb.out_bstride = FN; cb.hprev = h0; cb.hprev_bstride = FN; cb.accumulate = 1;
-        contract<EPI_BWD, TAP_BWD>(cb, Wb, ldb, d.sms, st);
+        launch_tap<TAP_BWD>(cb, Wb, d.sms, st);
       }
     }
   }

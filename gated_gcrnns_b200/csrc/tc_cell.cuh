@@ -71,13 +71,8 @@ __global__ void prep_weight_kernel(const float* __restrict__ W, __nv_bfloat16* _
 }
 
 // =====================================================================================================
-// contract_mma: Y[b, m, n] = sum_{k, c} W[m, k*C + c] * Z_k[b, c, n]      (per sample; mma.sync bf16)
+// argument block of the tap contraction  Y[b, m, n] = sum_{k, c} W[m, k*C + c] * Z_k[b, c, n]  (kernel: tc_tap.cuh)
 // =====================================================================================================
-constexpr int CT_NT = 64;          // n columns per tile
-constexpr int CT_ZLD = CT_NT + 8;  // padded smem row (144 B: conflict-free ldmatrix)
-constexpr int CT_THREADS = 256;
-
-enum { EPI_PLAIN = 0, EPI_FWD = 1, EPI_BWD = 2 };
 
 struct ContractArgs {
   const __nv_bfloat16* W;    // [M][ldw] bf16, columns = slab-major
@@ -95,167 +90,8 @@ struct ContractArgs {
   const float* x0; long long x0_bstride;                        // zx_0 = X[b, t]: [G][N] at x0 + b*x0_bstride
   const float* zx; long long zx_kstride, zx_bstride;            // zx_k (k>=1) at zx + (k-1)*kstride + b*bstride
   const float* hprev; long long hprev_bstride;                  // EPI_BWD: fp32 h_{t-1}[b] = hprev + b*bstride
-  float* dgf; int accumulate;
+  float* dgf; int accumulate; int scaled_chain;
 };
-
-template <int EPI>
-__global__ void __launch_bounds__(CT_THREADS, 1) contract_mma_kernel(const ContractArgs a) {
-  extern __shared__ __align__(16) uint8_t ct_smem[];
-  const int KK = a.K * a.C;
-  __nv_bfloat16* Ws = reinterpret_cast<__nv_bfloat16*>(ct_smem);                 // [64][ldw]
-  __nv_bfloat16* Zs = Ws + 64 * a.ldw;                                            // [2][KK][CT_ZLD]
-  float* fs = reinterpret_cast<float*>(Zs + 2 * (size_t)KK * CT_ZLD);             // A [M*Kin*G], bias [M], red[8]
-  float* As = fs; float* bs = fs + 64 * 32; float* red = bs + 64;
-  float* Xs = red + 8;                                                            // [2][32][CT_NT] zx tile (EPI_FWD)
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int wm = warp & 3, wn = warp >> 2;
-  const int tiles_n = a.N / CT_NT;
-  const long long num_tiles = a.B * tiles_n;
-
-  // weights (once per CTA)
-  {
-    const int chunks_per_row = a.ldw / 8;
-    for (int i = tid; i < 64 * chunks_per_row; i += CT_THREADS) {
-      const int r = i / chunks_per_row, c = i % chunks_per_row;
-      if (r < a.M) cp_async16(smem_u32(Ws + r * a.ldw + c * 8), a.W + (size_t)r * a.ldw + c * 8);
-      else *reinterpret_cast<uint4*>(Ws + r * a.ldw + c * 8) = make_uint4(0, 0, 0, 0);
-    }
-    if (EPI == EPI_FWD) {
-      for (int i = tid; i < a.M * a.Kin * a.G; i += CT_THREADS) As[i] = a.A[i];
-    }
-    if (EPI != EPI_BWD) for (int i = tid; i < 64; i += CT_THREADS) bs[i] = (a.bias && i < a.M) ? a.bias[i] : 0.f;
-  }
-  auto load_tile = [&](long long tile, int buf) {
-    const long long b = tile / tiles_n;
-    const int n0 = (int)(tile % tiles_n) * CT_NT;
-    __nv_bfloat16* dst = Zs + (size_t)buf * KK * CT_ZLD;
-    for (int i = tid; i < KK * 8; i += CT_THREADS) {
-      const int row = i >> 3, ch = i & 7;
-      const int k = row / a.C, c = row % a.C;
-      const __nv_bfloat16* src = a.slab[k] + ((size_t)(b * a.C + c) * a.N + n0 + ch * 8);
-      cp_async16(smem_u32(dst + row * CT_ZLD + ch * 8), src);
-    }
-    if (EPI == EPI_FWD) {      // x_t S^k rows of this sample: [Kin*G][64] fp32
-      const int KG = a.Kin * a.G;
-      for (int i = tid; i < KG * (CT_NT / 4); i += CT_THREADS) {
-        const int kg = i / (CT_NT / 4), c4 = i % (CT_NT / 4);
-        const int k = kg / a.G, g = kg % a.G;
-        const float* zp = (k == 0) ? a.x0 + b * a.x0_bstride + (size_t)g * a.N
-                                   : a.zx + (size_t)(k - 1) * a.zx_kstride + b * a.zx_bstride + (size_t)g * a.N;
-        cp_async16(smem_u32(Xs + ((size_t)buf * 32 + kg) * CT_NT + c4 * 4), zp + n0 + c4 * 4);
-      }
-    }
-  };
-
-  long long tile = blockIdx.x;
-  if (tile < num_tiles) load_tile(tile, 0);
-  cp_async_commit();
-  int buf = 0;
-  for (; tile < num_tiles; tile += gridDim.x, buf ^= 1) {
-    const long long nxt = tile + gridDim.x;
-    if (nxt < num_tiles) load_tile(nxt, buf ^ 1);
-    cp_async_commit();
-    cp_async_wait<1>();
-    __syncthreads();
-
-    const long long b = tile / tiles_n;
-    const int n0 = (int)(tile % tiles_n) * CT_NT;
-    const __nv_bfloat16* Zb = Zs + (size_t)buf * KK * CT_ZLD;
-    float acc[4][4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
-    const uint32_t a_addr = smem_u32(Ws + (16 * wm + (lane & 7) + 8 * ((lane >> 3) & 1)) * a.ldw + 8 * (lane >> 4));
-    const uint32_t b_addr = smem_u32(Zb + ((lane & 7) + 8 * ((lane >> 3) & 1)) * CT_ZLD + 32 * wn + 8 * (lane >> 4));
-    for (int ks = 0; ks < KK / 16; ++ks) {
-      uint32_t af[4], bf0[4], bf1[4];
-      ldsm_x4(af, a_addr + ks * 32);
-      ldsm_x4_t(bf0, b_addr + ks * 16 * CT_ZLD * 2);
-      ldsm_x4_t(bf1, b_addr + ks * 16 * CT_ZLD * 2 + 32);
-      mma_bf16(acc[0], af, bf0[0], bf0[1]);
-      mma_bf16(acc[1], af, bf0[2], bf0[3]);
-      mma_bf16(acc[2], af, bf1[0], bf1[1]);
-      mma_bf16(acc[3], af, bf1[2], bf1[3]);
-    }
-
-    // ---- epilogue: this thread holds rows m0, m0+8 and columns nb + 8*j + {0,1}, j = 0..3 ----
-    const int m0 = 16 * wm + (lane >> 2);
-    const int nb = n0 + 32 * wn + 2 * (lane & 3);
-    float part = 0.f;
-    float vgi = 1.f, vgf = 1.f;
-    if (EPI == EPI_FWD || EPI == EPI_BWD) {
-      if (a.gi) vgi = a.gi[b * a.gate_stride];
-      if (a.gf) vgf = a.gf[b * a.gate_stride];
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int n = nb + 8 * j;
-      float ax[2][2] = {{0.f, 0.f}, {0.f, 0.f}};   // [row half][col] input-filter term
-      if (EPI == EPI_FWD) {
-        const int KG = a.Kin * a.G;
-        const float* xt = Xs + (size_t)buf * 32 * CT_NT + (n - n0);
-        for (int kg = 0; kg < KG; ++kg) {
-          const float2 z = *reinterpret_cast<const float2*>(xt + kg * CT_NT);
-#pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
-            const int m = m0 + 8 * hh;
-            if (m < a.M) { const float w = As[m * KG + kg]; ax[hh][0] = fmaf(w, z.x, ax[hh][0]); ax[hh][1] = fmaf(w, z.y, ax[hh][1]); }
-          }
-        }
-      }
-#pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        const int m = m0 + 8 * hh;
-        if (m >= a.M) continue;
-        float v0 = acc[j][2 * hh], v1 = acc[j][2 * hh + 1];
-        if (EPI == EPI_PLAIN) {
-          v0 += a.bias_scale * bs[m]; v1 += a.bias_scale * bs[m];
-          *reinterpret_cast<float2*>(a.out_f32 + b * a.out_bstride + (size_t)m * a.N + n) = make_float2(v0, v1);
-        } else if (EPI == EPI_FWD) {
-          const float bb = bs[m];
-          v0 = tanh_fast(vgi * (ax[hh][0] + bb) + vgf * (v0 + bb));
-          v1 = tanh_fast(vgi * (ax[hh][1] + bb) + vgf * (v1 + bb));
-          *reinterpret_cast<float2*>(a.out_f32 + b * a.out_bstride + (size_t)m * a.N + n) = make_float2(v0, v1);
-          *reinterpret_cast<__nv_bfloat162*>(a.out_bf16 + ((size_t)b * a.M + m) * a.N + n) = __floats2bfloat162_rn(v0, v1);
-        } else {
-          const float2 hp = *reinterpret_cast<const float2*>(a.hprev + b * a.hprev_bstride + (size_t)m * a.N + n);
-          part = fmaf(v0, hp.x, fmaf(v1, hp.y, part));
-          float* o = a.out_f32 + b * a.out_bstride + (size_t)m * a.N + n;
-          float2 r = make_float2(vgf * v0, vgf * v1);
-          if (a.accumulate) { const float2 old = *reinterpret_cast<float2*>(o); r.x += old.x; r.y += old.y; }
-          *reinterpret_cast<float2*>(o) = r;
-        }
-      }
-    }
-    if (EPI == EPI_BWD && a.dgf) {
-      part = warp_sum_f(part);
-      if (lane == 0) red[warp] = part;
-      __syncthreads();
-      if (tid == 0) { float s = 0.f; for (int w = 0; w < CT_THREADS / 32; ++w) s += red[w]; atomicAdd(a.dgf + b * a.gate_stride, s); }
-    }
-    __syncthreads();   // everyone is done with Zs[buf] (and red) before it is refilled
-  }
-  cp_async_wait<0>();
-}
-
-inline size_t contract_smem_bytes(int K, int C, int ldw) {
-  return (size_t)64 * ldw * 2 + (size_t)2 * K * C * CT_ZLD * 2 + (64 * 32 + 64 + 8 + 2 * 32 * CT_NT) * sizeof(float);
-}
-
-template <int EPI>
-void launch_contract(const ContractArgs& a, int sms, cudaStream_t st) {
-  GCRNN_CHECK(a.M <= 64 && a.M % 16 == 0 && a.C % 16 == 0 && a.N % CT_NT == 0, "contract_mma: unsupported sizes M=%d C=%d N=%d", a.M, a.C, a.N);
-  GCRNN_CHECK(EPI != EPI_FWD || a.Kin * a.G <= 32, "tensor-core path supports Kin*G <= 32 (got %d)", a.Kin * a.G);
-  const size_t sm = contract_smem_bytes(a.K, a.C, a.ldw);
-  GCRNN_CHECK(sm <= 220 * 1024, "contract_mma: taps do not fit in shared memory (%zu B)", sm);
-  auto kern = contract_mma_kernel<EPI>;
-  CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-  const long long tiles = a.B * (a.N / CT_NT);
-  const int grid = (int)std::min<long long>(tiles, sms);
-  kern<<<grid, CT_THREADS, sm, st>>>(a);
-  ++g_launches;
-  CUDA_OK(cudaGetLastError());
-}
 
 // =====================================================================================================
 // wgrad_mma: part[cta][k][f][g] += sum_{b in cta's tiles} scale[b] * sum_n V_k[b,f,n] * h[b,g,n]
@@ -392,7 +228,7 @@ struct DpreArgs {
   const float* dH; long long dH_bstride;        // dH[b, t]  : [F][N] at dH + b*bstride
   const float* Ht; long long H_bstride;         // h_t[b]
   const float* dhrec;                           // [B][F][N] or null (t = T-1)
-  __nv_bfloat16* v0;                            // out: bf16 dpre [B][F][N]
+  __nv_bfloat16* v0;                            // out: bf16 (g_f * dpre) [B][F][N]: input of the adjoint chain (scaled)
   const float* gi; const float* gf; long long gate_stride;
   const float* A; const float* bias; int Kin, G, F, N;
   const float* x0; long long x0_bstride; const float* zx; long long zx_kstride, zx_bstride;
@@ -430,7 +266,7 @@ __global__ void __launch_bounds__(256) dpre_kernel(const DpreArgs a) {
         if (pR) { const float4 r = pR[i]; d.x += r.x; d.y += r.y; d.z += r.z; d.w += r.w; }
         d.x *= 1.f - hv.x * hv.x; d.y *= 1.f - hv.y * hv.y; d.z *= 1.f - hv.z * hv.z; d.w *= 1.f - hv.w * hv.w;
         if (kg0 == 0) {
-          __nv_bfloat162 p = __floats2bfloat162_rn(d.x, d.y), q = __floats2bfloat162_rn(d.z, d.w);
+          __nv_bfloat162 p = __floats2bfloat162_rn(vgf * d.x, vgf * d.y), q = __floats2bfloat162_rn(vgf * d.z, vgf * d.w);
           uint2 u; u.x = *reinterpret_cast<uint32_t*>(&p); u.y = *reinterpret_cast<uint32_t*>(&q);
           pV[i] = u;
           sdp += (d.x + d.y) + (d.z + d.w);

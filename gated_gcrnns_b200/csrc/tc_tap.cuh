@@ -38,6 +38,7 @@ struct TapArgs {
   const float* zx; long long zx_kstride, zx_bstride;
   const float* hprev; long long hprev_bstride;
   float* dgf; int accumulate;
+  int scaled_chain;              // TAP_BWD: the chain input was g_f * dpre, so acc = g_f q already
 };
 
 __device__ __forceinline__ float tap_tanh(float x) {
@@ -230,17 +231,130 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             part = fmaf(v[i], hp[i], part);
-            float r = vgf * v[i];
+            float r = a.scaled_chain ? v[i] : vgf * v[i];
             if (a.accumulate) r += old[i];
             of[(size_t)i * a.N] = r;
           }
           if (a.dgf) {
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+            if (a.scaled_chain) part = vgf > 1e-30f ? part / vgf : 0.f;      // <q, h> = <g_f q, h> / g_f
             if (lane == 0) atomicAdd(a.dgf + b * a.gate_stride, part);
           }
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, tmem_cols); }
+}
+
+// =====================================================================================================
+// wgrad on tcgen05 (F = 64):  dB_k[f, g] += sum_{b, n} V_k[b, f, n] * h[b, g, n]   for all K taps at once
+//   A (K-major): the K slabs' [64 f x 64 n] boxes stacked in smem -> pairs of taps form M = 128 operands
+//   B (K-major): h_{t-1} bf16 [64 g x 64 n];  D_p (TMEM, 64 columns per tap pair) accumulates over the CTA's
+//   whole list of (sample, 64-node block) tiles; one read-modify-write of the CTA's private partial at the end.
+// =====================================================================================================
+constexpr int WT_STAGES = 4;
+struct WgradTcArgs {
+  int K, N; long long B, R;
+  float* part;                 // [grid][K][64][64]
+};
+__host__ __device__ constexpr int wt_stage_bytes(int K) { return (K + 1) * 8192; }
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tmc,
+                const __grid_constant__ CUtensorMap tmH, const WgradTcArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int stage_bytes = wt_stage_bytes(a.K);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + WT_STAGES * stage_bytes);
+  uint64_t* empty_bar = full_bar + WT_STAGES;
+  uint64_t* done_bar = empty_bar + WT_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done_bar + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_n = a.N / 64;
+  const long long num_tiles = a.B * tiles_n;
+  const int NP = (a.K + 1) / 2;
+  const uint32_t tmem_cols = NP * 64 <= 64 ? 64 : NP * 64 <= 128 ? 128 : 256;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tm0); tma_prefetch_desc(&tmc); tma_prefetch_desc(&tmH);
+    for (int s = 0; s < WT_STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
+    mbar_init(done_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const bool has_work = (long long)blockIdx.x < num_tiles;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const long long b = tile / tiles_n;
+        const int n0 = (int)(tile % tiles_n) * 64;
+        mbar_wait(empty_bar + stage, phase ^ 1);
+        uint8_t* dst = smem + stage * stage_bytes;
+        mbar_expect_tx(full_bar + stage, (uint32_t)stage_bytes);
+        for (int k = 0; k < a.K; ++k) {
+          const CUtensorMap* tm = (k == 0) ? &tm0 : &tmc;
+          const int row = (k == 0) ? (int)(b * 64) : (int)((long long)(k - 1) * a.R + b * 64);
+          tma_load_2d(dst + k * 8192, tm, full_bar + stage, n0, row);
+        }
+        tma_load_2d(dst + a.K * 8192, &tmH, full_bar + stage, n0, (int)(b * 64));
+        if (++stage == WT_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, 64);
+      int stage = 0; uint32_t phase = 0;
+      bool first = true;
+      for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(full_bar + stage, phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * stage_bytes);
+        const uint64_t bdesc = make_kmajor_sw128_desc(sa + a.K * 8192);
+        for (int p = 0; p < NP; ++p) {
+          const uint64_t adesc = make_kmajor_sw128_desc(sa + p * 16384);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            umma_f16(tmem_base + (uint32_t)(p * 64), adesc + (uint64_t)(2 * j), bdesc + (uint64_t)(2 * j), idesc, !(first && j == 0));
+        }
+        first = false;
+        umma_commit(empty_bar + stage);
+        if (++stage == WT_STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(done_bar);
+    }
+  } else if (has_work) {
+    // epilogue: TMEM lane = row of the stacked pair (tap 2p rows 0..63, tap 2p+1 rows 64..127), column = g
+    const int q = warp & 3;
+    mbar_wait(done_bar, 0);
+    tc_fence_after();
+    float* mine = a.part + (size_t)blockIdx.x * a.K * 64 * 64;
+    const int row = q * 32 + lane;
+    for (int p = 0; p < NP; ++p) {
+      const int k = 2 * p + (row >> 6);
+      const int f = row & 63;
+      for (int c = 0; c < 64; c += 32) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(p * 64 + c), v);
+        if (k < a.K) {
+          float4* o = reinterpret_cast<float4*>(mine + ((size_t)k * 64 + f) * 64 + c);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float4 t = o[i];
+            t.x += v[4 * i]; t.y += v[4 * i + 1]; t.z += v[4 * i + 2]; t.w += v[4 * i + 3];
+            o[i] = t;
+          }
+        }
       }
     }
   }
