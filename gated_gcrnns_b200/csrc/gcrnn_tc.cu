@@ -132,6 +132,7 @@ static void launch_tap(const ContractArgs& ca, const __nv_bfloat16* Wp, int sms,
   t.gi = ca.gi; t.gf = ca.gf; t.gate_stride = ca.gate_stride; t.A = ca.A; t.Kin = ca.Kin; t.G = ca.G;
   t.x0 = ca.x0; t.x0_bstride = ca.x0_bstride; t.zx = ca.zx; t.zx_kstride = ca.zx_kstride; t.zx_bstride = ca.zx_bstride;
   t.hprev = ca.hprev; t.hprev_bstride = ca.hprev_bstride; t.dgf = ca.dgf; t.accumulate = ca.accumulate; t.scaled_chain = ca.scaled_chain;
+  t.dHn = ca.dHn; t.dHn_bstride = ca.dHn_bstride; t.gfn = ca.gfn; t.red = ca.red;
   for (int k = 2; k < ca.K; ++k)
     GCRNN_CHECK(ca.slab[k] == ca.slab[1] + (size_t)(k - 1) * t.R * ca.N, "tap_gemm: slabs 1..K-1 must be contiguous");
   const CUtensorMap tm0 = make_tmap_bf16(ca.slab[0], t.R, ca.N, ca.C);
@@ -139,7 +140,8 @@ static void launch_tap(const ContractArgs& ca, const __nv_bfloat16* Wp, int sms,
   const CUtensorMap tmW = make_tmap_bf16(Wp, ca.M, (long long)t.KB * 64, ca.M);
   const long long tiles = ca.B * (ca.N / TAP_BM);
   const int grid = (int)std::min<long long>(tiles, sms);
-  const bool small = (EPI != TAP_FWD) || ca.Kin * ca.G <= 8;
+  const bool small = (EPI != TAP_FWD && EPI != TAP_BWDF) || ca.Kin * ca.G <= 8;
+  GCRNN_CHECK(EPI != TAP_BWDF || ca.Kin * ca.G <= 7, "fused backward epilogue needs Kin*G <= 7");
   if (small) {
     auto kern = tap_gemm_kernel<EPI, 8>;
     CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TAP_SMEM));
@@ -265,6 +267,8 @@ size_t cell_backward_tc(const gcrnn_cell* cell, const gcrnn_cell_params* p, cons
   GCRNN_CHECK(a.dry() || saved, "backward needs the buffer written by forward");
   const int max_sms = 256;
   __nv_bfloat16* vb0 = a.get<__nv_bfloat16>((size_t)d.R * d.N);
+  __nv_bfloat16* vb0b = a.get<__nv_bfloat16>((size_t)d.R * d.N);
+  float* red = a.get<float>((size_t)d.R * 8);
   __nv_bfloat16* vb = a.get<__nv_bfloat16>((size_t)(d.Kst - 1) * d.R * d.N);
   float* dhrec = a.get<float>((size_t)d.R * d.N);
   const size_t wbuf = (size_t)64 * (((d.Kst * d.F + 63) / 64) * 64);
@@ -286,10 +290,10 @@ size_t cell_backward_tc(const gcrnn_cell* cell, const gcrnn_cell_params* p, cons
   const size_t part_bytes = (size_t)d.sms * d.Kst * d.F * d.F * sizeof(float);
 
   // dB_k += sum_{b,n} V_k h^T with the (already g_f-scaled) adjoint chain in vb0/vb
-  auto wgrad = [&](const float* h32, long long hstride, const __nv_bfloat16* h16) {
-    if (d.F == 64) { launch_wgrad_tc(d, vb0, vb, h16, part, st); return; }
+  auto wgrad_v = [&](const __nv_bfloat16* v0p, const float* h32, long long hstride, const __nv_bfloat16* h16) {
+    if (d.F == 64) { launch_wgrad_tc(d, v0p, vb, h16, part, st); return; }
     WgradArgs w{};
-    w.v0 = vb0; w.vc = vb; w.h = h32; w.h_bstride = hstride; w.scale = nullptr; w.scale_stride = 0;
+    w.v0 = v0p; w.vc = vb; w.h = h32; w.h_bstride = hstride; w.scale = nullptr; w.scale_stride = 0;
     w.part = part; w.K = d.Kst; w.F = d.F; w.N = d.N; w.B = d.B;
     const size_t sm = ((size_t)2 * d.Kst * 64 * WG_LD + (size_t)2 * 64 * WG_LD) * sizeof(__nv_bfloat16);
     CUDA_OK(cudaFuncSetAttribute(wgrad_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
@@ -307,13 +311,12 @@ size_t cell_backward_tc(const gcrnn_cell* cell, const gcrnn_cell_params* p, cons
   cvt_bf16(h0, hb0, d.R * d.N, st);
 
   // ---- reverse-time sweep -------------------------------------------------------------------------------------------
-  for (long long t = d.T - 1; t >= 0; --t) {
-    const float* hprev = t > 0 ? H + (t - 1) * FN : h0;
-    const long long hstride = t > 0 ? d.T * FN : FN;
-    const __nv_bfloat16* hprev16 = t > 0 ? s.Hb + (size_t)(t - 1) * d.R * d.N : hb0;
+  CUDA_OK(cudaMemsetAsync(red, 0, (size_t)d.R * 8 * sizeof(float), st));
+  const bool can_fuse = d.Kin * d.G <= 7;
+  auto run_dpre = [&](long long t, const float* dhrec_in, __nv_bfloat16* v0_out) {
     DpreArgs da{};
     da.dH = dH + t * FN; da.dH_bstride = d.T * FN; da.Ht = H + t * FN; da.H_bstride = d.T * FN;
-    da.dhrec = (t == d.T - 1) ? nullptr : dhrec; da.v0 = vb0;
+    da.dhrec = dhrec_in; da.v0 = v0_out;
     da.gi = d.tg ? s.gt + t : nullptr; da.gf = d.tg ? s.gt + d.BT + t : nullptr; da.gate_stride = d.T;
     da.A = p->weight_A; da.bias = p->bias; da.Kin = d.Kin; da.G = d.G; da.F = d.F; da.N = d.N;
     da.x0 = X + t * GN; da.x0_bstride = d.T * GN; da.zx = s.zx + t * GN; da.zx_kstride = d.RX * d.N; da.zx_bstride = d.T * GN;
@@ -321,13 +324,39 @@ size_t cell_backward_tc(const gcrnn_cell* cell, const gcrnn_cell_params* p, cons
     da.dA = gr->weight_A; da.dbias = gr->bias; da.B = d.B;
     dpre_kernel<<<(unsigned)std::min<long long>(d.B * (d.F / DP_FC), 148 * 32), 256, 0, st>>>(da);
     launched();
-    chain(g, true, vb0, vb, d.Kst, d.R, st);
-    ContractArgs ca = contract_base(d, vb0, vb);
-    ca.out_f32 = dhrec; ca.out_bstride = FN; ca.gf = d.tg ? s.gt + d.BT + t : nullptr; ca.gate_stride = d.T;
-    ca.hprev = hprev; ca.hprev_bstride = hstride; ca.dgf = d.tg ? dgt + d.BT + t : nullptr; ca.accumulate = 0;
-    ca.scaled_chain = 1;                       // dpre_kernel wrote g_f * dpre: acc = g_f q = dh_{t-1} directly
-    launch_tap<TAP_BWD>(ca, WTb, d.sms, st);
-    if (gr->weight_B) wgrad(hprev, hstride, hprev16);
+  };
+  __nv_bfloat16* v0cur = vb0; __nv_bfloat16* v0nxt = vb0b;
+  run_dpre(d.T - 1, nullptr, v0cur);
+  for (long long t = d.T - 1; t >= 0; --t) {
+    const float* hprev = t > 0 ? H + (t - 1) * FN : h0;
+    const long long hstride = t > 0 ? d.T * FN : FN;
+    const __nv_bfloat16* hprev16 = t > 0 ? s.Hb + (size_t)(t - 1) * d.R * d.N : hb0;
+    chain(g, true, v0cur, vb, d.Kst, d.R, st);
+    ContractArgs ca = contract_base(d, v0cur, vb);
+    ca.gf = d.tg ? s.gt + d.BT + t : nullptr; ca.gate_stride = d.T;
+    ca.hprev = hprev; ca.hprev_bstride = hstride; ca.dgf = d.tg ? dgt + d.BT + t : nullptr;
+    ca.scaled_chain = 1;                       // the chain input is g_f * dpre: acc = g_f q = dh_{t-1} directly
+    if (t > 0 && can_fuse) {
+      // fused: the epilogue forms step t-1's dpre, its bf16 chain input and the per-(b, f) sums it needs
+      ca.dHn = dH + (t - 1) * FN; ca.dHn_bstride = d.T * FN;
+      ca.gfn = d.tg ? s.gt + d.BT + (t - 1) : nullptr;
+      ca.Kin = d.Kin; ca.G = d.G;
+      ca.x0 = X + (t - 1) * GN; ca.x0_bstride = d.T * GN;
+      ca.zx = s.zx + (t - 1) * GN; ca.zx_kstride = d.RX * d.N; ca.zx_bstride = d.T * GN;
+      ca.out_bf16 = v0nxt; ca.red = red;
+      launch_tap<TAP_BWDF>(ca, WTb, d.sms, st);
+      dpre_finish_kernel<<<(unsigned)((d.B + 7) / 8), 64, 0, st>>>(red, d.tg ? s.gt + (t - 1) : nullptr, d.tg ? s.gt + d.BT + (t - 1) : nullptr,
+                                                                   d.T, p->weight_A, p->bias, gr->weight_A, gr->bias,
+                                                                   d.tg ? dgt + (t - 1) : nullptr, d.tg ? dgt + d.BT + (t - 1) : nullptr,
+                                                                   d.B, d.F, d.Kin * d.G, 8);
+      launched();
+    } else {
+      ca.out_f32 = dhrec; ca.out_bstride = FN; ca.accumulate = 0;
+      launch_tap<TAP_BWD>(ca, WTb, d.sms, st);
+      if (t > 0) run_dpre(t - 1, dhrec, v0nxt);
+    }
+    if (gr->weight_B) wgrad_v(v0cur, hprev, hstride, hprev16);
+    std::swap(v0cur, v0nxt);
   }
   wgrad_flush(gr->weight_B);
 
@@ -355,7 +384,7 @@ size_t cell_backward_tc(const gcrnn_cell* cell, const gcrnn_cell_params* p, cons
       // h0 path of the sub-cell: v_k = dc0 (S^T)^k ; dB_g,k = v_k h0^T ; dh0 += sum_k B_g,k^T v_k
       cvt_bf16(dc0, vb0, d.R * d.N, st);
       chain(g, true, vb0, vb, d.Kst, d.R, st);
-      if (gr->t_weight_B[gi]) { wgrad(h0, FN, hb0); wgrad_flush(gr->t_weight_B[gi]); }
+      if (gr->t_weight_B[gi]) { wgrad_v(vb0, h0, FN, hb0); wgrad_flush(gr->t_weight_B[gi]); }
       if (dh0) {
         prep_contract_weight(p->t_weight_B[gi], Wb, d.F, d.Kst, 1, st);
         ContractArgs cb = contract_base(d, vb0, vb);

@@ -91,6 +91,7 @@ struct ContractArgs {
   const float* zx; long long zx_kstride, zx_bstride;            // zx_k (k>=1) at zx + (k-1)*kstride + b*bstride
   const float* hprev; long long hprev_bstride;                  // EPI_BWD: fp32 h_{t-1}[b] = hprev + b*bstride
   float* dgf; int accumulate; int scaled_chain;
+  const float* dHn; long long dHn_bstride; const float* gfn; float* red;   // fused backward epilogue (tc_tap.cuh TAP_BWDF)
 };
 
 // =====================================================================================================

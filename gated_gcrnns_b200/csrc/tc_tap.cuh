@@ -23,7 +23,7 @@ constexpr int TAP_STAGE_BYTES = 2 * 64 * 128;
 constexpr int TAP_MAX_KB = 6;      // K*C <= 384 contraction rows
 constexpr int TAP_THREADS = 64 + 16 * 32;   // TMA warp + MMA warp + 16 epilogue warps
 
-enum { TAP_PLAIN = 0, TAP_FWD = 1, TAP_BWD = 2 };
+enum { TAP_PLAIN = 0, TAP_FWD = 1, TAP_BWD = 2, TAP_BWDF = 3 };   // BWDF: BWD fused with the next step's dpre
 
 struct TapArgs {
   int K, C, M, N, KB;              // slabs, channels per slab, output features, nodes, ceil(K*C/64)
@@ -39,7 +39,28 @@ struct TapArgs {
   const float* hprev; long long hprev_bstride;
   float* dgf; int accumulate;
   int scaled_chain;              // TAP_BWD: the chain input was g_f * dpre, so acc = g_f q already
+  // TAP_BWDF (step t): additionally forms step t-1's  dpre = (dH_{t-1} + acc) (1 - h_{t-1}^2), writes
+  // out_bf16 = bf16(gf_{t-1} dpre) (the next chain input) and accumulates red[b][m][0] = sum_n dpre,
+  // red[b][m][1+kg] = sum_n dpre * zx_kg (x0 / zx then point at step t-1's rows)
+  const float* dHn; long long dHn_bstride;
+  const float* gfn;              // gf[b, t-1] at gfn[b * gate_stride] (null: 1)
+  float* red;                    // [B][M][8]
 };
+
+// sum over the 32 lanes of 32 per-lane quantities with 31 shuffles: afterwards lane l holds the total of x[l] in x[0]
+__device__ __forceinline__ float warp_transpose_sum32(float* x, int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int i = 0; i < s; ++i) {
+      const float send = up ? x[i] : x[i + s];
+      const float keep = up ? x[i + s] : x[i];
+      x[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  return x[0];
+}
 
 __device__ __forceinline__ float tap_tanh(float x) {
   float y;
@@ -92,6 +113,11 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_n = a.N / TAP_BM;
   const long long num_tiles = a.B * tiles_n;
+  // contiguous tile range per CTA: consecutive tiles are the node blocks of one sample (per-sample reductions
+  // are then accumulated in registers and flushed once per sample)
+  const long long per_cta = (num_tiles + gridDim.x - 1) / gridDim.x;
+  const long long tile_lo = blockIdx.x * per_cta;
+  const long long tile_hi = tile_lo + per_cta < num_tiles ? tile_lo + per_cta : num_tiles;
   const int KK = a.K * a.C;
   const int acc_stride = a.M < 32 ? 32 : a.M;                      // TMEM columns per accumulator stage
   const uint32_t tmem_cols = (2 * acc_stride <= 32) ? 32 : (2 * acc_stride <= 64) ? 64 : 128;
@@ -117,7 +143,7 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__
       mbar_expect_tx(w_bar, (uint32_t)(a.KB * a.M * 128));
       for (int kb = 0; kb < a.KB; ++kb) tma_load_2d(sW + kb * 8192, &tmW, w_bar, kb * 64, 0);
       int stage = 0; uint32_t phase = 0;
-      for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (long long tile = tile_lo; tile < tile_hi; ++tile) {
         const long long b = tile / tiles_n;
         const int n0 = (int)(tile % tiles_n) * TAP_BM;
         for (int s = 0; s < a.KB; ++s) {
@@ -144,7 +170,7 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__
       tc_fence_after();
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (long long tile = tile_lo; tile < tile_hi; ++tile) {
         mbar_wait(tmem_empty + acc, acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * acc_stride);
@@ -174,7 +200,9 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__
     if (m0 < a.M) {
       const int KG = a.Kin * a.G;
       int acc = 0; uint32_t acc_phase = 0;
-      for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      long long cur_b = -1;
+      float racc[4] = {0.f, 0.f, 0.f, 0.f};
+      for (long long tile = tile_lo; tile < tile_hi; ++tile) {
         const long long b = tile / tiles_n;
         const int n = (int)(tile % tiles_n) * TAP_BM + q * 32 + lane;
         // operands that do not depend on the accumulator are fetched before waiting for the MMAs
@@ -194,10 +222,34 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__
             } else z[kg] = 0.f;
           }
         }
-        if (EPI == TAP_BWD) {
+        float dhn[16];
+        float vgfn = 1.f;
+        if (EPI == TAP_BWD || EPI == TAP_BWDF) {
           const float* hb = a.hprev + b * a.hprev_bstride + (size_t)m0 * a.N + n;
 #pragma unroll
           for (int i = 0; i < 16; ++i) hp[i] = __ldg(hb + (size_t)i * a.N);
+        }
+        if (EPI == TAP_BWDF) {
+          const float* db = a.dHn + b * a.dHn_bstride + (size_t)m0 * a.N + n;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) dhn[i] = __ldg(db + (size_t)i * a.N);
+          if (a.gfn) vgfn = __ldg(a.gfn + b * a.gate_stride);
+#pragma unroll
+          for (int kg = 0; kg < KGM; ++kg) {
+            if (kg < KG) {
+              const int k = kg / a.G, g = kg % a.G;
+              z[kg] = (k == 0) ? __ldg(a.x0 + b * a.x0_bstride + (size_t)g * a.N + n)
+                               : __ldg(a.zx + (size_t)(k - 1) * a.zx_kstride + b * a.zx_bstride + (size_t)g * a.N + n);
+            } else z[kg] = 0.f;
+          }
+          if (b != cur_b) {                       // new sample: flush the per-sample sums of the previous one
+            if (cur_b >= 0) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) atomicAdd(a.red + ((size_t)cur_b * a.M + m0 + 4 * j + (lane >> 3)) * 8 + (lane & 7), racc[j]);
+            }
+            cur_b = b;
+            racc[0] = racc[1] = racc[2] = racc[3] = 0.f;
+          }
         }
         mbar_wait(tmem_full + acc, acc_phase);
         tc_fence_after();
@@ -220,6 +272,30 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__
             const float h = tap_tanh(vgi * (ax + bb) + vgf * (v[i] + bb));
             of[(size_t)i * a.N] = h;
             ob[(size_t)i * a.N] = __float2bfloat16(h);
+          }
+        } else if (EPI == TAP_BWDF) {
+          float part = 0.f;
+          __nv_bfloat16* ob = a.out_bf16 + ((size_t)b * a.M + m0) * a.N + n;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {                 // 4 features x 8 kinds = 32 per-lane quantities per group
+            float x[32];
+#pragma unroll
+            for (int ii = 0; ii < 4; ++ii) {
+              const int i = 4 * j + ii;
+              part = fmaf(v[i], hp[i], part);
+              const float dp = (dhn[i] + v[i]) * (1.f - hp[i] * hp[i]);
+              ob[(size_t)i * a.N] = __float2bfloat16(vgfn * dp);
+              x[8 * ii] = dp;
+#pragma unroll
+              for (int kg = 0; kg < 7; ++kg) x[8 * ii + 1 + kg] = (kg < KGM && kg < KG) ? dp * z[kg < KGM ? kg : 0] : 0.f;
+            }
+            racc[j] += warp_transpose_sum32(x, lane);
+          }
+          if (a.dgf) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+            part = vgf > 1e-30f ? part / vgf : 0.f;
+            if (lane == 0) atomicAdd(a.dgf + b * a.gate_stride, part);
           }
         } else {
           float part = 0.f;
@@ -244,12 +320,61 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
+      if (EPI == TAP_BWDF && cur_b >= 0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) atomicAdd(a.red + ((size_t)cur_b * a.M + m0 + 4 * j + (lane >> 3)) * 8 + (lane & 7), racc[j]);
+      }
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, tmem_cols); }
 }
+
+// consumes (and clears) red[b][m][8] of one time step: dA += gi sz, dbias += (gi + gf) sdp,
+// dgi[b] += sum_m (bias sdp + sum_kg A sz), dgf[b] += sum_m bias sdp        (block = 64 threads = features)
+__global__ void dpre_finish_kernel(float* __restrict__ red, const float* __restrict__ gi, const float* __restrict__ gf,
+                                   long long gate_stride, const float* __restrict__ A, const float* __restrict__ bias,
+                                   float* dA, float* dbias, float* dgi, float* dgf, long long B, int M, int KG, int bchunk) {
+  __shared__ float sh[2][2];
+  const int m = threadIdx.x;
+  const long long b0 = (long long)blockIdx.x * bchunk, b1 = b0 + bchunk < B ? b0 + bchunk : B;
+  float aA[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, abias = 0.f;
+  float wA[7];
+#pragma unroll
+  for (int kg = 0; kg < 7; ++kg) wA[kg] = (m < M && kg < KG) ? A[(size_t)m * KG + kg] : 0.f;
+  const float bb = (bias && m < M) ? bias[m] : 0.f;
+  for (long long b = b0; b < b1; ++b) {
+    const float vgi = gi ? gi[b * gate_stride] : 1.f, vgf = gf ? gf[b * gate_stride] : 1.f;
+    float si = 0.f, sf = 0.f;
+    if (m < M) {
+      float4* r = reinterpret_cast<float4*>(red + ((size_t)b * M + m) * 8);
+      const float4 r0 = r[0], r1 = r[1];
+      r[0] = make_float4(0.f, 0.f, 0.f, 0.f); r[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float sz[7] = {r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+      const float sdp = r0.x;
+      abias += (vgi + vgf) * sdp;
+      float dot = 0.f;
+#pragma unroll
+      for (int kg = 0; kg < 7; ++kg) { aA[kg] = fmaf(vgi, sz[kg], aA[kg]); dot = fmaf(wA[kg], sz[kg], dot); }
+      si = bb * sdp + dot; sf = bb * sdp;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { si += __shfl_xor_sync(0xffffffffu, si, o); sf += __shfl_xor_sync(0xffffffffu, sf, o); }
+    if ((threadIdx.x & 31) == 0) { sh[threadIdx.x >> 5][0] = si; sh[threadIdx.x >> 5][1] = sf; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      if (dgi) atomicAdd(dgi + b * gate_stride, sh[0][0] + sh[1][0]);
+      if (dgf) atomicAdd(dgf + b * gate_stride, sh[0][1] + sh[1][1]);
+    }
+    __syncthreads();
+  }
+  if (m < M) {
+    if (dbias) atomicAdd(dbias + m, abias);
+    if (dA) for (int kg = 0; kg < KG; ++kg) atomicAdd(dA + (size_t)m * KG + kg, aA[kg]);
+  }
+}
+
 
 // =====================================================================================================
 // wgrad on tcgen05 (F = 64):  dB_k[f, g] += sum_{b, n} V_k[b, f, n] * h[b, g, n]   for all K taps at once
