@@ -177,11 +177,19 @@ static void launch_wgrad_tc(const TcDims& d, const __nv_bfloat16* v0, const __nv
   launched();
 }
 
-static void gate_launch(bool bwd, const GateArgs& ga, const TcDims& d, cudaStream_t st) {
-  dim3 grid(d.N / 128, d.F / TG_FC, ga.bsplit);
-  const int KG = d.Kin * d.G;
-  if (!bwd) { if (KG <= 8) time_gate_kernel<false, 8><<<grid, 128, 0, st>>>(ga); else time_gate_kernel<false, 32><<<grid, 128, 0, st>>>(ga); }
-  else      { if (KG <= 8) time_gate_kernel<true, 8><<<grid, 128, 0, st>>>(ga);  else time_gate_kernel<true, 32><<<grid, 128, 0, st>>>(ga); }
+static void gate_launch(bool bwd, GateArgs ga, const TcDims& d, cudaStream_t st) {
+  GCRNN_CHECK(d.F % TG_FQ == 0 && d.F / TG_FQ <= 16 && d.N % TG_NT == 0, "time gate kernel: unsupported F=%d N=%d", d.F, d.N);
+  const size_t sm = gate_smem_bytes(d.T, d.Kin * d.G, d.F);
+  GCRNN_CHECK(sm <= 200 * 1024, "time gate kernel: T*Kin*G too large for shared memory staging (%zu B)", sm);
+  ga.bchunk = (int)std::max<long long>(1, std::min<long long>(16, d.B / 32));
+  dim3 grid(d.N / TG_NT, (unsigned)((d.B + ga.bchunk - 1) / ga.bchunk));
+  if (!bwd) {
+    CUDA_OK(cudaFuncSetAttribute(time_gate_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    time_gate_kernel<false><<<grid, 256, sm, st>>>(ga);
+  } else {
+    CUDA_OK(cudaFuncSetAttribute(time_gate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    time_gate_kernel<true><<<grid, 256, sm, st>>>(ga);
+  }
   launched();
 }
 
@@ -232,7 +240,6 @@ size_t cell_forward_tc(const gcrnn_cell* cell, const gcrnn_cell_params* p, const
       GateArgs ga{};
       ga.A = p->t_weight_A[gi]; ga.Kin = d.Kin; ga.G = d.G; ga.F = d.F; ga.N = d.N; ga.B = d.B; ga.T = d.T;
       ga.X = X; ga.zx = s.zx; ga.c0 = c0; ga.Wg = p->t_mlp_w[gi]; ga.logit = logit + gi * d.BT;
-      ga.bsplit = (int)std::min<long long>(d.B, 16);
       gate_launch(false, ga, d, st);
       gate_sigmoid_kernel<<<(unsigned)((d.BT + 255) / 256), 256, 0, st>>>(logit + gi * d.BT, p->t_mlp_b[gi], s.gt + gi * d.BT, d.BT);
       launched();
@@ -374,7 +381,6 @@ size_t cell_backward_tc(const gcrnn_cell* cell, const gcrnn_cell_params* p, cons
       ga.A = p->t_weight_A[gi]; ga.Kin = d.Kin; ga.G = d.G; ga.F = d.F; ga.N = d.N; ga.B = d.B; ga.T = d.T;
       ga.X = X; ga.zx = s.zx; ga.c0 = c0; ga.Wg = p->t_mlp_w[gi]; ga.dl = dl;
       ga.dWg = gr->t_mlp_w[gi]; ga.dc0 = dc0; ga.dA = gr->t_weight_A[gi];
-      ga.bsplit = (int)std::min<long long>(d.B, 16);
       GCRNN_CHECK(ga.dWg && ga.dA, "time-gate gradient buffers missing");
       gate_launch(true, ga, d, st);
       if (gr->t_bias[gi]) {
