@@ -173,6 +173,7 @@ def run_ours(args):
     L = _lib.lib()
 
     def step(host_inputs):
+        nonlocal Bl
         for p in used:
             p.grad = None
         for i in range(0, Bl, mb):
@@ -218,6 +219,11 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return t.item(), launches, c
 
+    if args.once:                    # profiling aid (ncu --set full): one forward+backward of one micro-batch, no timing
+        Bl = mb
+        step(False)
+        torch.cuda.synchronize()
+        return
     ms_dev, launches, clocks = timed(False, args.steps, args.warmup)
     ms_e2e, _, _ = timed(True, args.steps, max(1, args.warmup - 2))
     seqs = cfg['B'] * args.steps / (ms_dev * 1e-3)
@@ -291,6 +297,7 @@ def main():
     ap.add_argument('--cpu-batch', type=int, default=4)
     ap.add_argument('--cpu-T', type=int, default=4)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--once', action='store_true', help='run one micro-batch forward+backward and exit (for ncu captures)')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

@@ -6,6 +6,7 @@
 namespace gcrnn {
 static thread_local char g_err[1024] = "";
 unsigned long long g_launches = 0;
+int g_opt_gemm_pair = 0;
 void set_last_error(const char* fmt, ...) {
   va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof g_err, fmt, ap); va_end(ap);
 }
@@ -29,6 +30,10 @@ extern "C" {
 int gcrnn_abi_version(void) { return GCRNN_ABI_VERSION; }
 const char* gcrnn_last_error(void) { return g_err; }
 uint64_t gcrnn_debug_launch_count(void) { return g_launches; }
+int gcrnn_debug_set_option(const char* name, int32_t value) {
+  if (name && std::string(name) == "gemm_pair") { int old = gcrnn::g_opt_gemm_pair; gcrnn::g_opt_gemm_pair = value; return old; }
+  return -1;
+}
 
 int gcrnn_graph_create_csr(gcrnn_graph** out, int32_t N, int32_t E, const int64_t* const* rowptr,
                            const int32_t* const* colidx, const float* const* vals, int32_t device) {

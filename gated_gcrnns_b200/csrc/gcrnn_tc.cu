@@ -1,8 +1,10 @@
 // Dense tensor-core path (bf16 operands, fp32 accumulate) of the gated GCRNN recurrence for sm_100a.
 // The graph shift z @ S (Utils/graphML.py:123) runs on tcgen05 (tc_gemm.cuh); see DESIGN.md §TC-path.
 #include "tc_gemm.cuh"
+#include "tc_gemm2.cuh"
 #include "tc_cell.cuh"
 #include "tc_tap.cuh"
+#include "tc_gate.cuh"
 #include <cstdlib>
 #include <cmath>
 #include <algorithm>
@@ -54,7 +56,10 @@ void shift_gemm(const gcrnn_graph* g, bool backward, const __nv_bfloat16* A, lon
   const __nv_bfloat16* Bop = backward ? g->S_bf16 : g->St_bf16;
   EpiStore epi{out_bf16, out_f32, (long long)N, g->dense_scale};
   const int sms = num_sms(g->device);
-  if (N % 256 == 0) {
+  if (N % 256 == 0 && g_opt_gemm_pair && M > 128) {
+    CUtensorMap tmA = make_tmap_bf16(A, M, N, 128), tmB = make_tmap_bf16(Bop, N, N, 128);
+    launch_shift_gemm2<EpiStore>(tmA, tmB, epi, (int)M, N, sms, st);
+  } else if (N % 256 == 0) {
     CUtensorMap tmA = make_tmap_bf16(A, M, N, BM), tmB = make_tmap_bf16(Bop, N, N, 256);
     launch_shift_gemm<256, EpiStore>(tmA, tmB, epi, (int)M, N, sms, st);
   } else {
@@ -177,18 +182,59 @@ static void launch_wgrad_tc(const TcDims& d, const __nv_bfloat16* v0, const __nv
   launched();
 }
 
-static void gate_launch(bool bwd, GateArgs ga, const TcDims& d, cudaStream_t st) {
-  GCRNN_CHECK(d.F % TG_FQ == 0 && d.F / TG_FQ <= 16 && d.N % TG_NT == 0, "time gate kernel: unsupported F=%d N=%d", d.F, d.N);
-  const size_t sm = gate_smem_bytes(d.T, d.Kin * d.G, d.F);
-  GCRNN_CHECK(sm <= 200 * 1024, "time gate kernel: T*Kin*G too large for shared memory staging (%zu B)", sm);
-  ga.bchunk = (int)std::max<long long>(1, std::min<long long>(16, d.B / 32));
-  dim3 grid(d.N / TG_NT, (unsigned)((d.B + ga.bchunk - 1) / ga.bchunk));
+template <int KG>
+static void gate_launch_kg(bool bwd, const GateArgs& ga, int grid, size_t sm, cudaStream_t st) {
   if (!bwd) {
-    CUDA_OK(cudaFuncSetAttribute(time_gate_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    time_gate_kernel<false><<<grid, 256, sm, st>>>(ga);
+    CUDA_OK(cudaFuncSetAttribute(time_gate_fwd_kernel<KG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    time_gate_fwd_kernel<KG><<<grid, 256, sm, st>>>(ga);
   } else {
-    CUDA_OK(cudaFuncSetAttribute(time_gate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    time_gate_kernel<true><<<grid, 256, sm, st>>>(ga);
+    CUDA_OK(cudaFuncSetAttribute(time_gate_bwd_kernel<KG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    time_gate_bwd_kernel<KG><<<grid, 256, sm, st>>>(ga);
+  }
+}
+
+static void gate_launch(bool bwd, GateArgs ga, const TcDims& d, cudaStream_t st) {
+  GCRNN_CHECK(d.F % TG_FQ == 0 && d.F / TG_FQ <= TG_FMAX && d.N % TG_NT == 0, "time gate kernel: unsupported F=%d N=%d", d.F, d.N);
+  const int KG = d.Kin * d.G;
+  if (KG > 8) {                      // generic kernel: taps in shared memory
+    const size_t sm = gate_generic_smem_bytes(d.T, KG, d.F);
+    GCRNN_CHECK(sm <= 200 * 1024, "time gate kernel: T*Kin*G too large for shared memory staging (%zu B)", sm);
+    ga.bchunk = (int)std::max<long long>(1, std::min<long long>(16, d.B / 32));
+    dim3 grid(d.N / TG_NT, (unsigned)((d.B + ga.bchunk - 1) / ga.bchunk));
+    if (!bwd) {
+      CUDA_OK(cudaFuncSetAttribute(time_gate_generic_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      time_gate_generic_kernel<false><<<grid, 256, sm, st>>>(ga);
+    } else {
+      CUDA_OK(cudaFuncSetAttribute(time_gate_generic_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      time_gate_generic_kernel<true><<<grid, 256, sm, st>>>(ga);
+    }
+    launched();
+    return;
+  }
+  // staging plan: whole sequences double-buffered if they fit, else single-buffered, else chunks of time steps
+  const size_t budget = 200 * 1024;
+  const int T = (int)d.T;
+  if (gate_smem_bytes(T, KG, d.F, 2) <= budget) { ga.TC = T; ga.nbuf = 2; }
+  else if (gate_smem_bytes(T, KG, d.F, 1) <= budget) { ga.TC = T; ga.nbuf = 1; }
+  else {
+    ga.nbuf = 2; ga.TC = T;
+    while (ga.TC > 1 && gate_smem_bytes(ga.TC, KG, d.F, 2) > budget) ga.TC = (ga.TC + 1) / 2;
+  }
+  ga.nchunks = (T + ga.TC - 1) / ga.TC;
+  const size_t sm = gate_smem_bytes(ga.TC, KG, d.F, ga.nbuf);
+  GCRNN_CHECK(sm <= budget, "time gate kernel: Kin*G*F too large for shared memory staging (%zu B)", sm);
+  if (bwd && ga.nchunks > 1) CUDA_OK(cudaMemsetAsync(ga.dc0, 0, (size_t)d.R * d.N * sizeof(float), st));
+  const long long items = d.B * ga.nchunks * (d.N / TG_NT);
+  const int grid = (int)std::min<long long>(items, d.sms);
+  switch (KG) {
+    case 1: gate_launch_kg<1>(bwd, ga, grid, sm, st); break;
+    case 2: gate_launch_kg<2>(bwd, ga, grid, sm, st); break;
+    case 3: gate_launch_kg<3>(bwd, ga, grid, sm, st); break;
+    case 4: gate_launch_kg<4>(bwd, ga, grid, sm, st); break;
+    case 5: gate_launch_kg<5>(bwd, ga, grid, sm, st); break;
+    case 6: gate_launch_kg<6>(bwd, ga, grid, sm, st); break;
+    case 7: gate_launch_kg<7>(bwd, ga, grid, sm, st); break;
+    default: gate_launch_kg<8>(bwd, ga, grid, sm, st); break;
   }
   launched();
 }

@@ -312,142 +312,6 @@ __global__ void __launch_bounds__(256) dpre_kernel(const DpreArgs a) {
   }
 }
 
-// =====================================================================================================
-// time gates (graphML.py:2357-2374), evaluated for all (b, t) at once: they depend on (x_t, h0) only
-//   u = tanh(sum_{k,g} A_g[f,k,g] zx_k + c0[b,f,n]),   logit[b,t] = sum_{f,n} Wg[f,n] u
-// CTA = (n-tile of 128, chunk of TG_FC features, b-split); thread = one n.
-// =====================================================================================================
-// CTA = (tile of 64 nodes, chunk of samples), 256 threads = 64 nodes x 4 feature groups (F/4 features each, <= 16).
-// For every sample the x_t S^k rows of ALL T steps are staged once in shared memory ([T][Kin*G][64] fp32), so the
-// L2 sees them once; taps A and dlogit are shared-memory broadcasts; the only per-thread state is c0/Wg (registers).
-constexpr int TG_NT = 64;
-constexpr int TG_FQ = 4;
-struct GateArgs {
-  const float* A; int Kin, G, F, N; long long B, T;
-  const float* X;                 // [B,T,G,N]
-  const float* zx;                // [Kin-1][B*T*G][N]
-  const float* c0;                // [B,F,N]  (includes both bias terms)
-  const float* Wg;                // [F*N]
-  float* logit;                   // fwd: [B,T] += partial
-  const float* dl;                // bwd: dlogit [B,T]
-  float* dWg;                     // bwd: [F*N] +=
-  float* dc0;                     // bwd: [B,F,N] = sum_t dpre_u
-  float* dA;                      // bwd: [F,Kin,G] +=
-  int bchunk;
-};
-inline size_t gate_smem_bytes(long long T, int KG, int F) {
-  return ((size_t)T * KG * TG_NT + (size_t)F * KG + 8 * (size_t)T + (size_t)T + (size_t)F * KG) * sizeof(float);
-}
-
-template <bool BWD>
-__global__ void __launch_bounds__(256) time_gate_kernel(const GateArgs a) {
-  extern __shared__ __align__(16) float gsm[];
-  const int KG = a.Kin * a.G;
-  const int T = (int)a.T;
-  float* zs = gsm;                          // [T][KG][64]
-  float* As = zs + (size_t)T * KG * TG_NT;  // [F][KG]
-  float* plog = As + a.F * KG;              // [8 warps][T]   (fwd)
-  float* dls = plog + 8 * T;                // [T]            (bwd)
-  float* dAs = dls + T;                     // [F][KG]        (bwd)
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int nl = tid & 63, fq = tid >> 6;
-  const int n = blockIdx.x * TG_NT + nl;
-  const int FG = a.F / TG_FQ;               // features per thread (<= 16)
-  const int f0 = fq * FG;
-  const long long b_lo = (long long)blockIdx.y * a.bchunk, b_hi = min(a.B, b_lo + a.bchunk);
-  for (int i = tid; i < a.F * KG; i += 256) { As[i] = a.A[i]; if (BWD) dAs[i] = 0.f; }
-  float wg[16], dwg[16];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) { wg[i] = i < FG ? a.Wg[(size_t)(f0 + i) * a.N + n] : 0.f; dwg[i] = 0.f; }
-  const size_t kstride = (size_t)a.B * a.T * a.G * a.N;
-  for (long long b = b_lo; b < b_hi; ++b) {
-    __syncthreads();                        // previous sample's readers are done with zs / plog / dls
-    // stage x_t S^k for all t: zs[t][kg][0..63]
-    for (int i = tid; i < T * KG * (TG_NT / 4); i += 256) {
-      const int c4 = i % (TG_NT / 4), kg = (i / (TG_NT / 4)) % KG, t = i / ((TG_NT / 4) * KG);
-      const int k = kg / a.G, g = kg % a.G;
-      const size_t row = ((size_t)b * a.T + t) * a.G + g;
-      const float* src = (k == 0) ? a.X + row * a.N : a.zx + (size_t)(k - 1) * kstride + row * a.N;
-      cp_async16(smem_u32(zs + ((size_t)t * KG + kg) * TG_NT + c4 * 4), src + blockIdx.x * TG_NT + c4 * 4);
-    }
-    cp_async_commit();
-    if (BWD) for (int t = tid; t < T; t += 256) dls[t] = a.dl[b * a.T + t];
-    float c0v[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) c0v[i] = i < FG ? a.c0[((size_t)b * a.F + f0 + i) * a.N + n] : 0.f;
-    cp_async_wait<0>();
-    __syncthreads();
-    if (!BWD) {
-      for (int t = 0; t < T; ++t) {
-        const float* zt = zs + (size_t)t * KG * TG_NT + nl;
-        float part = 0.f;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          if (i < FG) {
-            float pre = c0v[i];
-            const float* ap = As + (f0 + i) * KG;
-#pragma unroll 5
-            for (int kg = 0; kg < KG; ++kg) pre = fmaf(ap[kg], zt[kg * TG_NT], pre);
-            part = fmaf(wg[i], tanh_fast(pre), part);
-          }
-        }
-        part = warp_sum_f(part);
-        if (lane == 0) plog[warp * T + t] = part;
-      }
-      __syncthreads();
-      for (int t = tid; t < T; t += 256) {
-        float sacc = 0.f;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) sacc += plog[w * T + t];
-        atomicAdd(a.logit + b * a.T + t, sacc);
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        if (i < FG) {
-          const float* ap = As + (f0 + i) * KG;
-          float dc0 = 0.f, dw = 0.f;
-          float sA[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-          for (int t = 0; t < T; ++t) {
-            const float* zt = zs + (size_t)t * KG * TG_NT + nl;
-            float pre = c0v[i];
-#pragma unroll 5
-            for (int kg = 0; kg < KG; ++kg) pre = fmaf(ap[kg], zt[kg * TG_NT], pre);
-            const float u = tanh_fast(pre);
-            const float dlv = dls[t];
-            dw = fmaf(dlv, u, dw);
-            const float dpu = dlv * wg[i] * (1.f - u * u);
-            dc0 += dpu;
-            if (KG <= 8) {
-#pragma unroll
-              for (int kg = 0; kg < 8; ++kg) if (kg < KG) sA[kg] = fmaf(dpu, zt[kg * TG_NT], sA[kg]);
-            } else {
-              for (int kg = 0; kg < KG; ++kg) atomicAdd(dAs + (f0 + i) * KG + kg, dpu * zt[kg * TG_NT]);
-            }
-          }
-          dwg[i] += dw;
-          a.dc0[((size_t)b * a.F + f0 + i) * a.N + n] = dc0;
-          if (KG <= 8) {
-#pragma unroll
-            for (int kg = 0; kg < 8; ++kg) {
-              if (kg < KG) {
-                const float v = warp_sum_f(sA[kg]);
-                if (lane == 0) atomicAdd(dAs + (f0 + i) * KG + kg, v);
-              }
-            }
-          }
-        }
-      }
-    }
-  }
-  if (BWD) {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) if (i < FG) atomicAdd(a.dWg + (size_t)(f0 + i) * a.N + n, dwg[i]);
-    __syncthreads();
-    for (int i = tid; i < a.F * KG; i += 256) atomicAdd(a.dA + i, dAs[i]);
-  }
-}
-
 // g = sigmoid(logit + c)      /     dl = dg g (1-g), dc += sum dl
 __global__ void gate_sigmoid_kernel(const float* __restrict__ logit, const float* __restrict__ c, float* __restrict__ g, long long n) {
   const float cv = c ? c[0] : 0.f;

@@ -70,6 +70,10 @@ uint64_t    gcrnn_debug_launch_count(void);
 int         gcrnn_debug_shift_gemm(const gcrnn_graph* g, int32_t backward, const void* A_bf16, int64_t M,
                                    void* out_bf16, float* out_f32, void* stream);
 
+/* tuning switches for tests and A/B measurements (process-wide): name = "gemm_pair" (1: CTA-pair cta_group::2 shift
+ * GEMM when the shape allows, 0: single-CTA kernel).  Returns the previous value, or -1 for an unknown name. */
+int         gcrnn_debug_set_option(const char* name, int32_t value);
+
 /* ---- graph -------------------------------------------------------------------------------------- */
 /* E operators in CSR, HOST arrays: rowptr[e] has N+1 entries, entry (i, colidx[p]) = S_e[i, j] = vals[p].
  * Row-vector convention of the reference: shift is z <- z @ S_e (graphML.py:123). */
