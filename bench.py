@@ -171,6 +171,12 @@ def run_ours(args):
     h0_dev = torch.zeros(mb, F, N, device=dev)
     dH = torch.ones(mb, T, F, N, device=dev)
     L = _lib.lib()
+    if args.gemm_pair is not None:
+        L.gcrnn_debug_set_option(b'gemm_pair', args.gemm_pair)
+    if args.bwd_fused is not None:
+        L.gcrnn_debug_set_option(b'bwd_fused', args.bwd_fused)
+    pair = L.gcrnn_debug_set_option(b'gemm_pair', 1)
+    L.gcrnn_debug_set_option(b'gemm_pair', pair)
 
     def step(host_inputs):
         nonlocal Bl
@@ -255,7 +261,8 @@ def run_ours(args):
         ach = 2.0 * R * N * N / t_k / 1e12
         step_ach = FLOP_PER_SEQ_FWD_BWD * seqs / world / 1e12
         roof = dict(bound='tensor', achieved=ach, peak=pk['bf16'], unit='TFLOP/s', frac=ach / pk['bf16'], traffic=None,
-                    kernel=f'shift_gemm_kernel<256> [{R}x{N}]x[{N}x{N}] bf16, {t_k * 1e6:.1f} us/launch, peak = {pk["src"]} burst bf16',
+                    kernel=f'{"shift_gemm2_kernel (cta_group::2, 256x256 pair tiles)" if pair else "shift_gemm_kernel<256> (cta_group::1)"} '
+                           f'[{R}x{N}]x[{N}x{N}] bf16, {t_k * 1e6:.1f} us/launch, peak = {pk["src"]} burst bf16',
                     step_achieved=step_ach, step_peak=pk['bf16_sustained'], step_frac=step_ach / pk['bf16_sustained'],
                     step_note='algorithmic 82.82 GFLOP/sequence fwd+bwd x sequences/s per GPU vs sustained bf16 peak (' + pk['src'] + ')')
     else:
@@ -297,6 +304,8 @@ def main():
     ap.add_argument('--cpu-batch', type=int, default=4)
     ap.add_argument('--cpu-T', type=int, default=4)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--gemm-pair', type=int, default=None, help='A/B switch: 1 = CTA-pair shift GEMM, 0 = single-CTA')
+    ap.add_argument('--bwd-fused', type=int, default=None, help='A/B switch: 1 = fused reverse-time step kernel, 0 = separate kernels')
     ap.add_argument('--once', action='store_true', help='run one micro-batch forward+backward and exit (for ncu captures)')
     args = ap.parse_args()
     if args.impl == 'reference':

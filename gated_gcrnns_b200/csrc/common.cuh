@@ -14,6 +14,7 @@ namespace gcrnn {
 
 // ---- error handling: C++ exceptions never cross the ABI; api.cu converts them to codes ----------------
 void set_last_error(const char* fmt, ...);
+extern int g_opt_bwd_fused;            // 1: fused reverse-time step kernel (tc_bwd.cuh) when the shape allows
 extern int g_opt_gemm_pair;             // 1: use the CTA-pair (cta_group::2) shift GEMM when the shape allows
 extern unsigned long long g_launches;   // kernels launched by this library (gcrnn_debug_launch_count)
 

@@ -5,6 +5,7 @@
 #include "tc_cell.cuh"
 #include "tc_tap.cuh"
 #include "tc_gate.cuh"
+#include "tc_bwd.cuh"
 #include <cstdlib>
 #include <cmath>
 #include <algorithm>
@@ -145,17 +146,32 @@ static void launch_tap(const ContractArgs& ca, const __nv_bfloat16* Wp, int sms,
   const CUtensorMap tmW = make_tmap_bf16(Wp, ca.M, (long long)t.KB * 64, ca.M);
   const long long tiles = ca.B * (ca.N / TAP_BM);
   const int grid = (int)std::min<long long>(tiles, sms);
-  const bool small = (EPI != TAP_FWD && EPI != TAP_BWDF) || ca.Kin * ca.G <= 8;
   GCRNN_CHECK(EPI != TAP_BWDF || ca.Kin * ca.G <= 7, "fused backward epilogue needs Kin*G <= 7");
-  if (small) {
-    auto kern = tap_gemm_kernel<EPI, 8>;
-    CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TAP_SMEM));
-    kern<<<grid, TAP_THREADS, TAP_SMEM, st>>>(tm0, tmc, tmW, t);
+  GCRNN_CHECK((EPI != TAP_FWD && EPI != TAP_BWDF) || ca.x0_bstride == ca.zx_bstride, "x0 / zx rows must share one sample stride");
+  const int KG = ca.Kin * ca.G;
+#define TAP_LAUNCH(KGM_, EXACT_)                                                                          \
+  do {                                                                                                    \
+    auto kern = tap_gemm_kernel<EPI, KGM_, EXACT_>;                                                       \
+    CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TAP_SMEM));           \
+    kern<<<grid, TAP_THREADS, TAP_SMEM, st>>>(tm0, tmc, tmW, t);                                          \
+  } while (0)
+  if (EPI == TAP_FWD && KG >= 1 && KG <= 8) {
+    switch (KG) {
+      case 1: TAP_LAUNCH(1, true); break;
+      case 2: TAP_LAUNCH(2, true); break;
+      case 3: TAP_LAUNCH(3, true); break;
+      case 4: TAP_LAUNCH(4, true); break;
+      case 5: TAP_LAUNCH(5, true); break;
+      case 6: TAP_LAUNCH(6, true); break;
+      case 7: TAP_LAUNCH(7, true); break;
+      default: TAP_LAUNCH(8, true); break;
+    }
+  } else if (EPI == TAP_FWD) {
+    TAP_LAUNCH(32, false);
   } else {
-    auto kern = tap_gemm_kernel<EPI, 32>;
-    CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TAP_SMEM));
-    kern<<<grid, TAP_THREADS, TAP_SMEM, st>>>(tm0, tmc, tmW, t);
+    TAP_LAUNCH(8, false);
   }
+#undef TAP_LAUNCH
   launched();
 }
 
@@ -179,6 +195,41 @@ static void launch_wgrad_tc(const TcDims& d, const __nv_bfloat16* v0, const __nv
   const int sm = WT_STAGES * wt_stage_bytes(d.Kst) + 256 + 1024;
   CUDA_OK(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
   wgrad_tc_kernel<<<d.sms, NUM_THREADS, sm, st>>>(tm0, tmc, tmH, w);
+  launched();
+}
+
+// fused reverse-time step (tc_bwd.cuh), F = 64
+template <int KG>
+static void bwd_fused_launch_kg(const CUtensorMap& tm0, const CUtensorMap& tmc, const CUtensorMap& tmH, const CUtensorMap& tmZ,
+                                const CUtensorMap& tmW, const BwdFusedArgs& a, int grid, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    CUDA_OK(cudaFuncSetAttribute(bwd_fused_kernel<KG>, cudaFuncAttributeMaxDynamicSharedMemorySize, BF_SMEM));
+    configured = true;
+  }
+  bwd_fused_kernel<KG><<<grid, BF_THREADS, BF_SMEM, st>>>(tm0, tmc, tmH, tmZ, tmW, a);
+}
+static void launch_bwd_fused(const TcDims& d, BwdFusedArgs a, const __nv_bfloat16* v0, const __nv_bfloat16* vc, const __nv_bfloat16* hb,
+                             const __nv_bfloat16* Zs, const __nv_bfloat16* Wp, cudaStream_t st) {
+  a.K = d.Kst; a.N = d.N; a.KB = d.Kst; a.B = d.B; a.R = d.R; a.G = d.G;
+  const CUtensorMap tm0 = make_tmap_bf16(v0, d.R, d.N, 64);
+  const CUtensorMap tmc = d.Kst > 1 ? make_tmap_bf16(vc, (long long)(d.Kst - 1) * d.R, d.N, 64) : tm0;
+  const CUtensorMap tmH = make_tmap_bf16(hb, d.R, d.N, 64);
+  const CUtensorMap tmZ = make_tmap_bf16(Zs, d.BT * BF_ZROWS, d.N, BF_ZROWS);
+  const CUtensorMap tmW = make_tmap_bf16(Wp, 64, (long long)d.Kst * 64, 64);
+  const long long tiles = d.B * (d.N / 128);
+  const int grid = (int)std::min<long long>(tiles, d.sms);
+  switch (d.Kin * d.G) {
+    case 1: bwd_fused_launch_kg<1>(tm0, tmc, tmH, tmZ, tmW, a, grid, st); break;
+    case 2: bwd_fused_launch_kg<2>(tm0, tmc, tmH, tmZ, tmW, a, grid, st); break;
+    case 3: bwd_fused_launch_kg<3>(tm0, tmc, tmH, tmZ, tmW, a, grid, st); break;
+    case 4: bwd_fused_launch_kg<4>(tm0, tmc, tmH, tmZ, tmW, a, grid, st); break;
+    case 5: bwd_fused_launch_kg<5>(tm0, tmc, tmH, tmZ, tmW, a, grid, st); break;
+    case 6: bwd_fused_launch_kg<6>(tm0, tmc, tmH, tmZ, tmW, a, grid, st); break;
+    case 7: bwd_fused_launch_kg<7>(tm0, tmc, tmH, tmZ, tmW, a, grid, st); break;
+    case 8: bwd_fused_launch_kg<8>(tm0, tmc, tmH, tmZ, tmW, a, grid, st); break;
+    default: GCRNN_CHECK(false, "fused backward step: Kin*G must be <= 8");
+  }
   launched();
 }
 
@@ -328,6 +379,9 @@ size_t cell_backward_tc(const gcrnn_cell* cell, const gcrnn_cell_params* p, cons
   __nv_bfloat16* hb0 = a.get<__nv_bfloat16>((size_t)d.R * d.N);
   __nv_bfloat16* WTb = a.get<__nv_bfloat16>(wbuf);
   float* part = a.get<float>((size_t)max_sms * d.Kst * d.F * d.F);
+  const bool fused = g_opt_bwd_fused && d.F == 64 && d.Kin * d.G <= 8 && d.Kst <= 6 && d.N % 128 == 0;
+  __nv_bfloat16* Zs = fused ? a.get<__nv_bfloat16>((size_t)d.BT * BF_ZROWS * d.N) : nullptr;
+  float* partA = fused ? a.get<float>((size_t)max_sms * 64 * BF_ZROWS) : nullptr;
   float *dgt = nullptr, *c0 = nullptr, *dc0 = nullptr, *dl = nullptr;
   __nv_bfloat16* Wb = nullptr;
   if (d.tg) {
@@ -374,17 +428,42 @@ size_t cell_backward_tc(const gcrnn_cell* cell, const gcrnn_cell_params* p, cons
     da.A = p->weight_A; da.bias = p->bias; da.Kin = d.Kin; da.G = d.G; da.F = d.F; da.N = d.N;
     da.x0 = X + t * GN; da.x0_bstride = d.T * GN; da.zx = s.zx + t * GN; da.zx_kstride = d.RX * d.N; da.zx_bstride = d.T * GN;
     da.dgi = d.tg ? dgt + t : nullptr; da.dgf = d.tg ? dgt + d.BT + t : nullptr;
-    da.dA = gr->weight_A; da.dbias = gr->bias; da.B = d.B;
+    da.dA = fused ? nullptr : gr->weight_A; da.dbias = fused ? nullptr : gr->bias; da.B = d.B;   // fused: MMA3 covers every step
     dpre_kernel<<<(unsigned)std::min<long long>(d.B * (d.F / DP_FC), 148 * 32), 256, 0, st>>>(da);
     launched();
   };
   __nv_bfloat16* v0cur = vb0; __nv_bfloat16* v0nxt = vb0b;
   run_dpre(d.T - 1, nullptr, v0cur);
+  if (fused) {
+    CUDA_OK(cudaMemsetAsync(partA, 0, (size_t)d.sms * 64 * BF_ZROWS * sizeof(float), st));
+    zs_build_kernel<<<148 * 8, 256, 0, st>>>(X, s.zx, d.RX * d.N, d.G, d.Kin * d.G, d.tg ? s.gt : nullptr, d.tg ? s.gt + d.BT : nullptr,
+                                              Zs, d.BT, d.N);
+    launched();
+  }
   for (long long t = d.T - 1; t >= 0; --t) {
     const float* hprev = t > 0 ? H + (t - 1) * FN : h0;
     const long long hstride = t > 0 ? d.T * FN : FN;
     const __nv_bfloat16* hprev16 = t > 0 ? s.Hb + (size_t)(t - 1) * d.R * d.N : hb0;
     chain(g, true, v0cur, vb, d.Kst, d.R, st);
+    if (fused) {
+      BwdFusedArgs fa{};
+      fa.last = t == 0; fa.dh0 = dh0 ? dhrec : nullptr;
+      fa.gf = d.tg ? s.gt + d.BT + t : nullptr; fa.gate_stride = d.T; fa.dgf = d.tg ? dgt + d.BT + t : nullptr;
+      fa.hprev = hprev; fa.hprev_bstride = hstride;
+      if (t > 0) {
+        fa.dHn = dH + (t - 1) * FN; fa.dHn_bstride = d.T * FN;
+        fa.gfn = d.tg ? s.gt + d.BT + (t - 1) : nullptr;
+        fa.dgin = d.tg ? dgt + (t - 1) : nullptr; fa.dgfn = d.tg ? dgt + d.BT + (t - 1) : nullptr;
+        fa.A = p->weight_A; fa.x0 = X + (t - 1) * GN; fa.zx = s.zx + (t - 1) * GN; fa.zx_kstride = d.RX * d.N; fa.z_bstride = d.T * GN;
+        fa.v0_out = v0nxt;
+      }
+      fa.bias = p->bias;
+      fa.zs_row0 = t * BF_ZROWS; fa.zs_rowb = d.T * BF_ZROWS;
+      fa.part = part; fa.partA = partA;
+      launch_bwd_fused(d, fa, v0cur, vb, hprev16, Zs, WTb, st);
+      std::swap(v0cur, v0nxt);
+      continue;
+    }
     ContractArgs ca = contract_base(d, v0cur, vb);
     ca.gf = d.tg ? s.gt + d.BT + t : nullptr; ca.gate_stride = d.T;
     ca.hprev = hprev; ca.hprev_bstride = hstride; ca.dgf = d.tg ? dgt + d.BT + t : nullptr;
@@ -412,6 +491,10 @@ size_t cell_backward_tc(const gcrnn_cell* cell, const gcrnn_cell_params* p, cons
     std::swap(v0cur, v0nxt);
   }
   wgrad_flush(gr->weight_B);
+  if (fused) {
+    dax_reduce_kernel<<<(64 * BF_ZROWS + 255) / 256, 256, 0, st>>>(partA, gr->weight_A, gr->bias, d.sms, d.Kin * d.G);
+    launched();
+  }
 
   // ---- time gates, batched over (b, t) -----------------------------------------------------------------------------------
   if (d.tg) {

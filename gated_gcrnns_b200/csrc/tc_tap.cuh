@@ -93,12 +93,15 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16_amn(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-template <int EPI, int KGM>
+// KGM: number of (k, g) input-filter taps the epilogue is unrolled for.  EXACT: Kin*G == KGM (no predicates in the
+// unrolled tap loops); otherwise KGM is an upper bound.
+template <int EPI, int KGM, bool EXACT>
 __global__ void __launch_bounds__(TAP_THREADS, 1)
 tap_gemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tmc,
                 const __grid_constant__ CUtensorMap tmW, const TapArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024 B alignment by OFFSET (not by integer round-trip) so the compiler keeps the shared address space: LDS, not LD
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sW = smem;                                              // [KB][64 rows][128 B]
   uint8_t* sA = smem + TAP_MAX_KB * 8192;                          // [STAGES][2 halves][64 rows][128 B]
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(sA + TAP_STAGES * TAP_STAGE_BYTES);
@@ -109,6 +112,7 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
   float* sAw = reinterpret_cast<float*>(tmem_slot + 4);            // [M][Kin*G] input-filter taps (<= 64*32)
   float* sBias = sAw + 64 * 32;                                    // [64]
+  const float** sZb = reinterpret_cast<const float**>(sBias + 64); // [32] base pointer of input row (k, g): X or zx slab
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_n = a.N / TAP_BM;
@@ -131,6 +135,12 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__
   }
   if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
   if (EPI == TAP_FWD) for (int i = threadIdx.x; i < a.M * a.Kin * a.G; i += TAP_THREADS) sAw[i] = a.A[i];
+  if (EPI == TAP_FWD || EPI == TAP_BWDF) {
+    for (int kg = threadIdx.x; kg < a.Kin * a.G; kg += TAP_THREADS) {
+      const int k = kg / a.G, g = kg % a.G;
+      sZb[kg] = (k == 0 ? a.x0 : a.zx + (size_t)(k - 1) * a.zx_kstride) + (size_t)g * a.N;
+    }
+  }
   for (int i = threadIdx.x; i < 64; i += TAP_THREADS) sBias[i] = (a.bias && i < a.M) ? a.bias[i] : 0.f;
   tc_fence_before();
   __syncthreads();
@@ -198,7 +208,7 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__
     const int cg = (warp - 2) >> 2;
     const int m0 = cg * 16;
     if (m0 < a.M) {
-      const int KG = a.Kin * a.G;
+      const int KG = EXACT ? KGM : a.Kin * a.G;
       int acc = 0; uint32_t acc_phase = 0;
       long long cur_b = -1;
       float racc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -213,14 +223,9 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__
           if (a.gf) vgf = __ldg(a.gf + b * a.gate_stride);
         }
         if (EPI == TAP_FWD) {
+          const size_t zo = (size_t)b * a.x0_bstride + n;      // x0_bstride == zx_bstride (rows of one [B,T,G,N] layout)
 #pragma unroll
-          for (int kg = 0; kg < KGM; ++kg) {
-            if (kg < KG) {
-              const int k = kg / a.G, g = kg % a.G;
-              z[kg] = (k == 0) ? __ldg(a.x0 + b * a.x0_bstride + (size_t)g * a.N + n)
-                               : __ldg(a.zx + (size_t)(k - 1) * a.zx_kstride + b * a.zx_bstride + (size_t)g * a.N + n);
-            } else z[kg] = 0.f;
-          }
+          for (int kg = 0; kg < KGM; ++kg) z[kg] = (kg < KG) ? __ldg(sZb[kg] + zo) : 0.f;
         }
         float dhn[16];
         float vgfn = 1.f;
@@ -234,13 +239,10 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__
 #pragma unroll
           for (int i = 0; i < 16; ++i) dhn[i] = __ldg(db + (size_t)i * a.N);
           if (a.gfn) vgfn = __ldg(a.gfn + b * a.gate_stride);
+          {
+            const size_t zo = (size_t)b * a.x0_bstride + n;
 #pragma unroll
-          for (int kg = 0; kg < KGM; ++kg) {
-            if (kg < KG) {
-              const int k = kg / a.G, g = kg % a.G;
-              z[kg] = (k == 0) ? __ldg(a.x0 + b * a.x0_bstride + (size_t)g * a.N + n)
-                               : __ldg(a.zx + (size_t)(k - 1) * a.zx_kstride + b * a.zx_bstride + (size_t)g * a.N + n);
-            } else z[kg] = 0.f;
+            for (int kg = 0; kg < KGM; ++kg) z[kg] = (kg < KG) ? __ldg(sZb[kg] + zo) : 0.f;
           }
           if (b != cur_b) {                       // new sample: flush the per-sample sums of the previous one
             if (cur_b >= 0) {
@@ -263,13 +265,15 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__
           for (int i = 0; i < 16; ++i) of[(size_t)i * a.N] = v[i] + a.bias_scale * sBias[m0 + i];
         } else if (EPI == TAP_FWD) {
           __nv_bfloat16* ob = a.out_bf16 + ((size_t)b * a.M + m0) * a.N + n;
+          const float* aw = sAw + m0 * KG;
+          const float gsum = vgi + vgf;
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             float ax = 0.f;
 #pragma unroll
-            for (int kg = 0; kg < KGM; ++kg) if (kg < KG) ax = fmaf(sAw[(m0 + i) * KG + kg], z[kg], ax);
-            const float bb = sBias[m0 + i];
-            const float h = tap_tanh(vgi * (ax + bb) + vgf * (v[i] + bb));
+            for (int kg = 0; kg < KGM; ++kg) if (kg < KG) ax = fmaf(aw[i * KG + kg], z[kg], ax);
+            // gi (ax + b) + gf (v + b)
+            const float h = tap_tanh(fmaf(vgi, ax, fmaf(vgf, v[i], gsum * sBias[m0 + i])));
             of[(size_t)i * a.N] = h;
             ob[(size_t)i * a.N] = __float2bfloat16(h);
           }
@@ -488,7 +492,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, tmem_cols); }
 }
 
-constexpr int TAP_SMEM = TAP_MAX_KB * 8192 + TAP_STAGES * TAP_STAGE_BYTES + 256 + (64 * 32 + 64) * 4 + 1024;
+constexpr int TAP_SMEM = TAP_MAX_KB * 8192 + TAP_STAGES * TAP_STAGE_BYTES + 256 + (64 * 32 + 64) * 4 + 32 * 8 + 1024;
 
 }  // namespace tc
 }  // namespace gcrnn

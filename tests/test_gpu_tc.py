@@ -24,8 +24,13 @@ def _gemm(g, A_bf16, backward, want_f32=True, want_bf16=True):
     return ob, of
 
 
-@pytest.mark.parametrize('N,M', [(256, 128), (128, 300), (1024, 128 * 5 + 17), (512, 4096)])
-def test_shift_gemm_matches_torch(N, M):
+def _set_opt(name, value):
+    return _lib.lib().gcrnn_debug_set_option(name.encode(), int(value))
+
+
+@pytest.mark.parametrize('pair', [0, 1])
+@pytest.mark.parametrize('N,M', [(256, 128), (128, 300), (1024, 128 * 5 + 17), (512, 4096), (1024, 256 * 75 + 130)])
+def test_shift_gemm_matches_torch(N, M, pair):
     """The library keeps the operator as bf16(S / max|S|) and multiplies by max|S| in the fp32 epilogue (exact for
     unweighted graphs).  Against an fp32 matmul with that same effective operator the only difference is accumulation
     order: tolerance 1e-5 relative to max|ref| (fp32 out), 2^-8 for the bf16 copy."""
@@ -35,13 +40,17 @@ def test_shift_gemm_matches_torch(N, M):
     mx = S.abs().max()
     S = (S / mx).to(torch.bfloat16).float() * mx
     A = torch.randn(M, N, device=DEV).to(torch.bfloat16)
-    for backward in (False, True):
-        ob, of = _gemm(g, A, backward)
-        Sd = S.to(DEV)
-        ref = A.float() @ (Sd.t() if backward else Sd)
-        scale = ref.abs().max().item()
-        assert (of - ref).abs().max().item() / scale < 1e-5, (N, M, backward)
-        assert (ob.float() - ref).abs().max().item() / scale < 2 ** -8
+    old = _set_opt('gemm_pair', pair)          # 1: CTA-pair (cta_group::2) kernel where the shape allows it
+    try:
+        for backward in (False, True):
+            ob, of = _gemm(g, A, backward)
+            Sd = S.to(DEV)
+            ref = A.float() @ (Sd.t() if backward else Sd)
+            scale = ref.abs().max().item()
+            assert (of - ref).abs().max().item() / scale < 1e-5, (N, M, backward)
+            assert (ob.float() - ref).abs().max().item() / scale < 2 ** -8
+    finally:
+        _set_opt('gemm_pair', old)
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -120,6 +129,35 @@ def test_tc_cell_matches_fp32_path(tg, N, F, K, T, B, G):
     assert errs['H'] < tol_h, errs
     bad = {k: v for k, v in errs.items() if k != 'H' and v > tol_g}
     assert not bad, errs
+
+
+@pytest.mark.parametrize('tg', [False, True])
+@pytest.mark.parametrize('N,K,T,B,G', [(512, 5, 4, 6, 1), (256, 4, 3, 5, 2), (1024, 2, 2, 3, 1)])
+def test_tc_fused_backward_step_matches_unfused(tg, N, K, T, B, G):
+    """F = 64: the fused reverse-time kernel (tensor-core weight/tap gradients, tc_bwd.cuh) against the separate
+    tap-contraction + wgrad kernels.  Both are bf16-operand paths with the same forward, so they agree much more tightly
+    than either does with fp32: 1e-2 of max|ref| on every gradient."""
+    F = 64
+    S = gg.graphs.dense_random(N, 0.3, seed=4)
+    torch.manual_seed(6)
+    X, h0, dH = torch.randn(B, T, G, N, device=DEV), 0.3 * torch.randn(B, F, N, device=DEV), torch.randn(B, T, F, N, device=DEV)
+    out = {}
+    old = _set_opt('bwd_fused', 1)
+    try:
+        for fused in (0, 1):
+            _set_opt('bwd_fused', fused)
+            cell = _make_cell(S, G, F, K, tg, 'bf16')
+            hh = h0.clone().requires_grad_(True)
+            H = cell(X, hh)
+            (H * dH).sum().backward()
+            out[fused] = ({k: v.grad for k, v in cell.named_parameters()}, hh.grad)
+    finally:
+        _set_opt('bwd_fused', old)
+        gg.set_precision('fp32')
+    errs = {'dh0': _relerr(out[1][1], out[0][1])}
+    errs.update(_grad_errs(out[1][0], out[0][0]))
+    _log('tc-fused-vs-unfused', dict(tg=tg, N=N, K=K, T=T, B=B, G=G), {k: f'{v:.2e}' for k, v in errs.items()})
+    assert all(v < 1e-2 for v in errs.values()), errs
 
 
 def test_tc_cell_vs_fp64_oracle_reduced_cfg3():
