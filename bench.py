@@ -292,6 +292,114 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+
+# ------------------------------------------------------------------------------------------------------
+# secondary workload: cfg5 (sparse kNN graph, CSR SpMM path, edge-gated) — HBM-bound; `--workload cfg5`
+# ------------------------------------------------------------------------------------------------------
+CFG5 = dict(N=100_000, knn=16, F=32, G=1, K=3, T=32, B=256, mb=32)
+BYTES_PER_SEQ_CFG5 = 42 * 32 * (32 * 100_000 * 4)      # 42 P per (sample, step), P = F*N*4 B, T = 32 -> 17.2 GB
+
+
+def run_cfg5(args):
+    import torch
+    import torch.distributed as dist
+    import gated_gcrnns_b200 as gg
+    from gated_gcrnns_b200 import _lib
+    world = int(os.environ.get('WORLD_SIZE', '1')); rank = int(os.environ.get('RANK', '0')); local = int(os.environ.get('LOCAL_RANK', '0'))
+    assert torch.cuda.is_available(), 'bench.py needs a GPU (no CPU fallback)'
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    cfg = dict(CFG5)
+    if args.batch != CFG3['B']:
+        cfg['B'] = args.batch
+    N, F, G, K, T = cfg['N'], cfg['F'], cfg['G'], cfg['K'], cfg['T']
+    lo, hi = gg.dist.shard_range(cfg['B'], rank, world)
+    Bl = hi - lo
+    mb = min(cfg['mb'], Bl)
+    assert Bl % mb == 0
+    gg.set_precision('fp32')
+    rp, ci, va = gg.graphs.knn_csr(N, cfg['knn'], seed=0)
+    S = gg.graphs.csr_to_torch_sparse(rp, ci, va, N)
+    torch.manual_seed(0)
+    cell = gg.GGCRNNCell(G, F, K, K, torch.tanh, False, 'edge', 1, True)
+    cell.addGSO(S)
+    cell = cell.to(dev)
+    used = [dict(cell.named_parameters())[n] for _, _, n in gg.cell_param_slots(False, 'edge', True)]
+    gen = torch.Generator(device='cpu').manual_seed(1234 + rank)
+    X_host = torch.randn(Bl, T, G, N, generator=gen).pin_memory()
+    X_dev = X_host.to(dev)
+    h0 = torch.zeros(mb, F, N, device=dev)
+    dH = torch.ones(mb, T, F, N, device=dev)
+    L = _lib.lib()
+
+    def step(host_inputs):
+        for p in used:
+            p.grad = None
+        for i in range(0, Bl, mb):
+            x = X_host[i:i + mb].to(dev, non_blocking=True) if host_inputs else X_dev[i:i + mb]
+            H = cell(x, h0)
+            torch.autograd.backward(H, dH)
+            del H
+        bucket = torch.cat([p.grad.reshape(-1) for p in used])
+        if world > 1:
+            dist.all_reduce(bucket)
+        return bucket.to('cpu') if host_inputs else bucket
+
+    def timed(host_inputs, steps, warmup):
+        for _ in range(warmup):
+            step(host_inputs)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        clk = Clocks(local); clk.start()
+        l0 = L.gcrnn_debug_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step(host_inputs)
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item(), L.gcrnn_debug_launch_count() - l0, clk.result()
+
+    if args.once:
+        Bl = mb
+        step(False)
+        torch.cuda.synchronize()
+        return
+    ms_dev, launches, clocks = timed(False, args.steps, args.warmup)
+    ms_e2e, _, _ = timed(True, args.steps, 1)
+    seqs = cfg['B'] * args.steps / (ms_dev * 1e-3)
+    seqs_e2e = cfg['B'] * args.steps / (ms_e2e * 1e-3)
+    pk = peaks()
+    ach = BYTES_PER_SEQ_CFG5 * seqs / world / 1e9
+    if rank == 0:
+        out = dict(metric='GCRNN sequences/sec fwd+bwd', value=seqs, unit='sequences/s', n_gpus=world, steps=args.steps, warmup=args.warmup,
+                   ms_per_step=ms_dev / args.steps, higher_is_better=True, scaling='strong', vs_baseline=None, dtype='f32', data='synthetic',
+                   config=dict(workload='cfg5: sparse directed 16-NN graph N=100000 (CSR SpMM path), F=32 G=1 K=3 T=32 edge-gated GGCRNNCell fwd+bwd',
+                               global_batch=cfg['B'], per_gpu_batch=Bl, microbatch=mb, precision='fp32',
+                               parallelism=f'dp{world} (batch sharded, one gradient all-reduce per step)',
+                               l2='per-micro-batch working set (H 13 GB) larger than L2; no explicit flush'),
+                   roofline=dict(bound='hbm', achieved=ach, peak=pk['hbm'], unit='GB/s', frac=ach / pk['hbm'], traffic=None,
+                                 kernel='whole step: algorithmic 17.2 GB per sequence (42 passes over an [F,N] fp32 signal per (sample, step), '
+                                        'SURVEY.md 8d) x sequences/s per GPU, peak = ' + pk['src'] + ' HBM copy bandwidth'),
+                   cpu_baseline=None, clocks=clocks,
+                   e2e=dict(value=seqs_e2e, unit='sequences/s', h2d_bytes_per_step=int(X_host.numel() * 4),
+                            d2h_bytes_per_step=int(sum(p.numel() for p in used) * 4), ms_per_step=ms_e2e / args.steps),
+                   gpu_launches=int(launches))
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -299,17 +407,20 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=CFG3['B'], help='global batch (sequences per step); default = cfg3')
-    ap.add_argument('--microbatch', type=int, default=512)
+    ap.add_argument('--microbatch', type=int, default=1024)
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
     ap.add_argument('--cpu-batch', type=int, default=4)
     ap.add_argument('--cpu-T', type=int, default=4)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--gemm-pair', type=int, default=None, help='A/B switch: 1 = CTA-pair shift GEMM, 0 = single-CTA')
     ap.add_argument('--bwd-fused', type=int, default=None, help='A/B switch: 1 = fused reverse-time step kernel, 0 = separate kernels')
+    ap.add_argument('--workload', default='cfg3', choices=['cfg3', 'cfg5'], help='cfg3 = the headline dense config; cfg5 = sparse kNN graph')
     ap.add_argument('--once', action='store_true', help='run one micro-batch forward+backward and exit (for ncu captures)')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)
+    elif args.workload == 'cfg5':
+        run_cfg5(args)
     else:
         run_ours(args)
 
