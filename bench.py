@@ -282,7 +282,7 @@ def run_ours(args):
                    config=dict(workload='cfg3: dense N=1024 F=64 G=1 K=5 T=64 time-gated GGCRNNCell fwd+bwd',
                                global_batch=cfg['B'], per_gpu_batch=Bl, microbatch=mb, precision=args.precision,
                                parallelism=f'dp{world} (batch sharded, one gradient all-reduce per step)',
-                               l2='inputs larger than L2 (X 1 GiB, H 8.6 GB per micro-batch); no explicit flush'),
+                               l2=f'inputs larger than L2 (X 1 GiB, H {mb * T * F * N * 4 / 1e9:.1f} GB per micro-batch); no explicit flush'),
                    roofline=roof, cpu_baseline=cb, clocks=clocks,
                    e2e=dict(value=seqs_e2e, unit='sequences/s', h2d_bytes_per_step=int(X_host.numel() * 4 + (Bl // mb) * h0_host.numel() * 4),
                             d2h_bytes_per_step=int(sum(p.numel() for p in used) * 4), ms_per_step=ms_e2e / args.steps),

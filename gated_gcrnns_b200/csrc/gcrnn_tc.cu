@@ -59,7 +59,8 @@ void shift_gemm(const gcrnn_graph* g, bool backward, const __nv_bfloat16* A, lon
   const int sms = num_sms(g->device);
   if (N % 256 == 0 && g_opt_gemm_pair && M > 128) {
     CUtensorMap tmA = make_tmap_bf16(A, M, N, 128), tmB = make_tmap_bf16(Bop, N, N, 128);
-    launch_shift_gemm2<EpiStore>(tmA, tmB, epi, (int)M, N, sms, st);
+    CUtensorMap tmC = out_bf16 ? make_tmap_bf16(out_bf16, M, N, 32) : tmA;      // bf16 output tiles leave through TMA stores
+    launch_shift_gemm2<EpiStore>(tmA, tmB, tmC, epi, (int)M, N, sms, st);
   } else if (N % 256 == 0) {
     CUtensorMap tmA = make_tmap_bf16(A, M, N, BM), tmB = make_tmap_bf16(Bop, N, N, 256);
     launch_shift_gemm<256, EpiStore>(tmA, tmB, epi, (int)M, N, sms, st);

@@ -10,7 +10,8 @@
 //     CTAs complete on the LEADER's full barrier; `tcgen05.commit ... multicast::cluster` releases the smem stage
 //     in both CTAs and publishes the accumulator to both epilogues.
 // Structure per CTA (192 threads): warp 0 TMA producer, warp 1 MMA issuer (leader only) + TMEM allocator,
-// warps 2..5 epilogue; 6-stage smem ring (32 KB per stage), 2 TMEM accumulator stages (512 columns).
+// warps 2..5 epilogue (TMEM -> registers -> swizzled smem staging -> TMA bulk store); 6-stage smem ring (32 KB per
+// stage), 2 TMEM accumulator stages (512 columns).
 #pragma once
 #include "tc_gemm.cuh"
 
@@ -21,7 +22,8 @@ constexpr int G2_BN = 256;
 constexpr int G2_STAGES = 6;
 constexpr int G2_HALF_BYTES = 128 * BK * 2;             // one 128-row K-major SW128 tile = 16 KB
 constexpr int G2_STAGE_BYTES = 2 * G2_HALF_BYTES;       // A tile + B half
-constexpr int G2_SMEM = G2_STAGES * G2_STAGE_BYTES + 256 + 1024;
+constexpr int G2_OUT_BYTES = 4 * 2 * 4096;               // 4 epilogue warps x 2 staging buffers x [32 rows][128 B]
+constexpr int G2_SMEM = G2_STAGES * G2_STAGE_BYTES + G2_OUT_BYTES + 256 + 1024;
 constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;             // clears the CTA-rank bit of a shared::cluster address
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -58,12 +60,24 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & PEER_MASK) : "memory");
 }
 
+// bulk tensor store smem -> global (bf16 output tile through the TMA unit instead of 16 B-per-lane strided STGs:
+// with direct stores the kernel was bound by the epilogue's store path, not by the tensor pipe — see profiles/)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(tm), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N_> __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N_) : "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 template <class Epi>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
-shift_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, Epi epi, int M, int N) {
+shift_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                   const __grid_constant__ CUtensorMap tmC, Epi epi, int M, int N) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + G2_STAGES * G2_STAGE_BYTES);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sOut = smem + G2_STAGES * G2_STAGE_BYTES;                 // [4 warps][2][32 rows][128 B] SW128
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sOut + G2_OUT_BYTES);
   uint64_t* empty_bar = full_bar + G2_STAGES;
   uint64_t* tmem_full = empty_bar + G2_STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -138,6 +152,9 @@ shift_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   } else {
     // ===== epilogue warps 2..5 (both CTAs): own 128 rows, TMEM lane quarter = warp % 4 =====
     const int q = warp & 3;
+    const bool via_tma = epi.out_f32 == nullptr;      // bf16-only output (every GEMM of the recurrence): TMA store
+    uint8_t* stage_out = sOut + q * 8192;
+    int ob = 0;
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = pair; tile < num_tiles; tile += npairs) {
       const int m0 = (tile / tiles_n) * 256 + (int)rank * 128, n0 = (tile % tiles_n) * G2_BN;
@@ -145,17 +162,53 @@ shift_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       tc_fence_after();
       const int row = m0 + q * 32 + lane;
       const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * G2_BN);
+      if (via_tma) {
 #pragma unroll 1
-      for (int c = 0; c < G2_BN / 32; ++c) {
-        float v[32];
-        tmem_ld32(t0 + (uint32_t)(c * 32), v);
-        if (row < M) epi(row, n0 + c * 32, v);
+        for (int c = 0; c < G2_BN / 64; ++c) {
+          float v[64];
+          tmem_ld32(t0 + (uint32_t)(c * 64), v);
+          tmem_ld32(t0 + (uint32_t)(c * 64 + 32), v + 32);
+          if (c == G2_BN / 64 - 1) {                  // accumulator fully read: hand the TMEM stage back early
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(tmem_empty + acc);
+          }
+          if (lane == 0) tma_store_wait_read<1>();     // the store that last used this staging buffer has read it
+          __syncwarp();
+          uint8_t* dst = stage_out + ob * 4096 + lane * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            __nv_bfloat162 a = __floats2bfloat162_rn(v[8 * j + 0] * epi.scale, v[8 * j + 1] * epi.scale);
+            __nv_bfloat162 b = __floats2bfloat162_rn(v[8 * j + 2] * epi.scale, v[8 * j + 3] * epi.scale);
+            __nv_bfloat162 cc = __floats2bfloat162_rn(v[8 * j + 4] * epi.scale, v[8 * j + 5] * epi.scale);
+            __nv_bfloat162 d = __floats2bfloat162_rn(v[8 * j + 6] * epi.scale, v[8 * j + 7] * epi.scale);
+            uint4 u;
+            u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
+            u.z = *reinterpret_cast<uint32_t*>(&cc); u.w = *reinterpret_cast<uint32_t*>(&d);
+            *reinterpret_cast<uint4*>(dst + ((j ^ (lane & 7)) << 4)) = u;       // 128 B swizzle
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmC, stage_out + ob * 4096, n0 + c * 64, m0 + q * 32);   // rows >= M are clipped by the TMA unit
+            tma_store_commit();
+          }
+          ob ^= 1;
+        }
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < G2_BN / 32; ++c) {
+          float v[32];
+          tmem_ld32(t0 + (uint32_t)(c * 32), v);
+          if (row < M) epi(row, n0 + c * 32, v);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(tmem_empty + acc);
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_leader(tmem_empty + acc);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (lane == 0) tma_store_wait_all();
   }
   tc_fence_before();
   __syncthreads();
@@ -164,7 +217,8 @@ shift_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 }
 
 template <class Epi>
-void launch_shift_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Epi& epi, int M, int N, int num_sms, cudaStream_t st) {
+void launch_shift_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const Epi& epi, int M, int N, int num_sms,
+                        cudaStream_t st) {
   auto kern = shift_gemm2_kernel<Epi>;
   static bool configured = false;
   if (!configured) {
@@ -174,7 +228,7 @@ void launch_shift_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Ep
   const int tiles = ((M + 255) / 256) * (N / G2_BN);
   int pairs = num_sms / 2;
   if (tiles < pairs) pairs = tiles;
-  kern<<<2 * pairs, NUM_THREADS, G2_SMEM, st>>>(tmA, tmB, epi, M, N);
+  kern<<<2 * pairs, NUM_THREADS, G2_SMEM, st>>>(tmA, tmB, tmC, epi, M, N);
   ++g_launches;
   CUDA_OK(cudaGetLastError());
 }
