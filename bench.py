@@ -35,41 +35,82 @@ def peaks():
     return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, src='fallback')
 
 
+def ncu_traffic(files, kernel_substr):
+    """dram__bytes_read.sum + dram__bytes_write.sum (bytes per launch) of the first matching kernel row in a committed
+    `ncu --set full ... --page raw --csv` export under profiles/ (captured with `bench.py --once`, same launch shape)."""
+    import csv
+    unit = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+    for f in files:
+        path = os.path.join(ROOT, 'profiles', f)
+        if not os.path.isfile(path):
+            continue
+        rows = list(csv.reader(open(path)))
+        if len(rows) < 3:
+            continue
+        hdr, units = rows[0], dict(zip(rows[0], rows[1]))
+        for r in rows[2:]:
+            d = dict(zip(hdr, r))
+            if kernel_substr in d.get('Kernel Name', '') and 'dram__bytes_read.sum' in d:
+                tot = sum(float(d[k].replace(',', '')) * unit.get(units[k], 1.0) for k in ('dram__bytes_read.sum', 'dram__bytes_write.sum'))
+                return tot, f
+    return None, None
+
+
 # ------------------------------------------------------------------------------------------------------
 # CPU arm: the reference algorithm (oracle port, fp64 as the reference scripts run it) on a bounded sample
 # ------------------------------------------------------------------------------------------------------
 def cpu_sample(cfg, Bs, Ts, repeats, warm=1):
+    """Time forward+backward of the time-gated cell on the host CPUs, fp64 (as the reference scripts run it).
+
+    kind 'reference': the UNMODIFIED reference `Utils.graphML.GGCRNNCell` from the git-ignored copy under baseline/_ref
+    (staged by `__graft_entry__.build()`); kind 'port': the oracle's restatement when no copy travelled with the repo."""
     import torch
-    from oracle import gcrnn_oracle as orc
+    from oracle import gcrnn_oracle as orc, ref_shim
     import gated_gcrnns_b200 as gg
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     S = gg.graphs.dense_random(cfg['N'], cfg['density'], seed=0).double()
+    X = torch.randn(Bs, Ts, cfg['G'], cfg['N'], dtype=torch.float64)
+    h0 = torch.zeros(Bs, cfg['F'], cfg['N'], dtype=torch.float64)
+    dH = torch.ones(Bs, Ts, cfg['F'], cfg['N'], dtype=torch.float64)
     torch.manual_seed(0)
     prev = torch.get_default_dtype()
     torch.set_default_dtype(torch.float64)
     try:
-        p = orc.init_cell_params(cfg['G'], cfg['F'], cfg['K'], cfg['K'], cfg['N'], True, None, 1, True)
+        if ref_shim.available():
+            kind = 'reference'
+            gml = ref_shim.load()
+            cell = gml.GGCRNNCell(cfg['G'], cfg['F'], cfg['K'], cfg['K'], torch.tanh, True, None, 1, True)
+            cell.addGSO(S)
+
+            def run():
+                cell.zero_grad()
+                torch.autograd.backward(cell(X, h0), dH)
+        else:
+            kind = 'port'
+            p = orc.init_cell_params(cfg['G'], cfg['F'], cfg['K'], cfg['K'], cfg['N'], True, None, 1, True)
+
+            def run():
+                orc.cell_forward_backward(p, S, X, h0, dH, True, None)
+        times = []
+        for i in range(warm + repeats):
+            t0 = time.perf_counter()
+            run()
+            dt = time.perf_counter() - t0
+            if i >= warm:
+                times.append(dt)
     finally:
         torch.set_default_dtype(prev)
-    X = torch.randn(Bs, Ts, cfg['G'], cfg['N'], dtype=torch.float64)
-    h0 = torch.zeros(Bs, cfg['F'], cfg['N'], dtype=torch.float64)
-    dH = torch.ones(Bs, Ts, cfg['F'], cfg['N'], dtype=torch.float64)
-    times = []
-    for i in range(warm + repeats):
-        t0 = time.perf_counter()
-        orc.cell_forward_backward(p, S, X, h0, dH, True, None)
-        dt = time.perf_counter() - t0
-        if i >= warm:
-            times.append(dt)
-    return times, cores
+    return times, cores, kind
 
 
-def cpu_baseline_dict(cfg, times, cores, Bs, Ts):
+def cpu_baseline_dict(cfg, times, cores, Bs, Ts, kind):
     best = min(times)
     seqs = Bs / (best * cfg['T'] / Ts)          # linear extrapolation in T (recurrence cost is linear in B*T)
-    return dict(value=seqs, unit='sequences/s', cores=cores, kind='port',
-                sample=f'oracle port (fp64, torch CPU, {cores} threads) of the reference GGCRNNCell fwd+bwd on cfg3 shapes with '
+    what = ('unmodified reference Utils.graphML.GGCRNNCell (copy of the reference tree staged under baseline/_ref)' if kind == 'reference'
+            else 'oracle port of the reference GGCRNNCell')
+    return dict(value=seqs, unit='sequences/s', cores=cores, kind=kind,
+                sample=f'{what}, fp64, torch CPU with {cores} threads, fwd+bwd on cfg3 shapes with '
                        f'B={Bs}, T={Ts} of {cfg["T"]}; min of {len(times)} runs = {best:.3f} s, extrapolated linearly in T')
 
 
@@ -79,10 +120,10 @@ def run_reference(args):
     if rank != 0:
         return
     Bs, Ts = args.cpu_batch, args.cpu_T
-    times, cores = cpu_sample(cfg, Bs, Ts, args.steps, warm=max(args.warmup, 1))
+    times, cores, kind = cpu_sample(cfg, Bs, Ts, args.steps, warm=min(max(args.warmup, 1), 2))
     ms = 1e3 * statistics.mean(times)
     seqs = Bs / (statistics.mean(times) * cfg['T'] / Ts)
-    cb = cpu_baseline_dict(cfg, times, cores, Bs, Ts)
+    cb = cpu_baseline_dict(cfg, times, cores, Bs, Ts, kind)
     cb['value'] = seqs
     out = dict(impl='reference', metric='GCRNN sequences/sec fwd+bwd', value=seqs, unit='sequences/s', n_gpus=args.gpus,
                steps=args.steps, warmup=args.warmup, ms_per_step=ms, higher_is_better=True, scaling='strong',
@@ -260,7 +301,10 @@ def run_ours(args):
         t_k = e0.elapsed_time(e1) * 1e-3 / reps
         ach = 2.0 * R * N * N / t_k / 1e12
         step_ach = FLOP_PER_SEQ_FWD_BWD * seqs / world / 1e12
-        roof = dict(bound='tensor', achieved=ach, peak=pk['bf16'], unit='TFLOP/s', frac=ach / pk['bf16'], traffic=None,
+        traffic, tsrc = ncu_traffic(['r01_ncu_gemm2_mb%d.raw.csv' % mb, 'r01_ncu_gemm2_tma_store.raw.csv'], 'shift_gemm2_kernel' if pair else 'shift_gemm_kernel')
+        roof = dict(bound='tensor', achieved=ach, peak=pk['bf16'], unit='TFLOP/s', frac=ach / pk['bf16'], traffic=traffic,
+                    traffic_note=(f'DRAM read+write bytes per launch from profiles/{tsrc} (ncu --set full); algorithmic operand bytes per launch '
+                                  f'at this shape = {(2 * R * N * 2 + N * N * 2) / 1e6:.0f} MB' if tsrc else None),
                     kernel=f'{"shift_gemm2_kernel (cta_group::2, 256x256 pair tiles)" if pair else "shift_gemm_kernel<256> (cta_group::1)"} '
                            f'[{R}x{N}]x[{N}x{N}] bf16, {t_k * 1e6:.1f} us/launch, peak = {pk["src"]} burst bf16',
                     step_achieved=step_ach, step_peak=pk['bf16_sustained'], step_frac=step_ach / pk['bf16_sustained'],
@@ -272,8 +316,8 @@ def run_ours(args):
 
     cb = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        times, cores = cpu_sample(dict(CFG3), args.cpu_batch, args.cpu_T, 2)
-        cb = cpu_baseline_dict(dict(CFG3), times, cores, args.cpu_batch, args.cpu_T)
+        times, cores, kind = cpu_sample(dict(CFG3), args.cpu_batch, args.cpu_T, 2)
+        cb = cpu_baseline_dict(dict(CFG3), times, cores, args.cpu_batch, args.cpu_T, kind)
 
     if rank == 0:
         out = dict(metric='GCRNN sequences/sec fwd+bwd', value=seqs, unit='sequences/s', n_gpus=world, steps=args.steps,
@@ -409,8 +453,8 @@ def main():
     ap.add_argument('--batch', type=int, default=CFG3['B'], help='global batch (sequences per step); default = cfg3')
     ap.add_argument('--microbatch', type=int, default=1024)
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
-    ap.add_argument('--cpu-batch', type=int, default=4)
-    ap.add_argument('--cpu-T', type=int, default=4)
+    ap.add_argument('--cpu-batch', type=int, default=16)
+    ap.add_argument('--cpu-T', type=int, default=8)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--gemm-pair', type=int, default=None, help='A/B switch: 1 = CTA-pair shift GEMM, 0 = single-CTA')
     ap.add_argument('--bwd-fused', type=int, default=None, help='A/B switch: 1 = fused reverse-time step kernel, 0 = separate kernels')
