@@ -8,6 +8,7 @@ static thread_local char g_err[1024] = "";
 unsigned long long g_launches = 0;
 int g_opt_gemm_pair = 1;
 int g_opt_bwd_fused = 1;
+int g_opt_sparse_fused = 1;
 void set_last_error(const char* fmt, ...) {
   va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof g_err, fmt, ap); va_end(ap);
 }
@@ -33,6 +34,7 @@ const char* gcrnn_last_error(void) { return g_err; }
 uint64_t gcrnn_debug_launch_count(void) { return g_launches; }
 int gcrnn_debug_set_option(const char* name, int32_t value) {
   if (name && std::string(name) == "bwd_fused") { int old = gcrnn::g_opt_bwd_fused; gcrnn::g_opt_bwd_fused = value; return old; }
+  if (name && std::string(name) == "sparse_fused") { int old = gcrnn::g_opt_sparse_fused; gcrnn::g_opt_sparse_fused = value; return old; }
   if (name && std::string(name) == "gemm_pair") { int old = gcrnn::g_opt_gemm_pair; gcrnn::g_opt_gemm_pair = value; return old; }
   return -1;
 }

@@ -15,6 +15,7 @@ namespace gcrnn {
 // ---- error handling: C++ exceptions never cross the ABI; api.cu converts them to codes ----------------
 void set_last_error(const char* fmt, ...);
 extern int g_opt_bwd_fused;            // 1: fused reverse-time step kernel (tc_bwd.cuh) when the shape allows
+extern int g_opt_sparse_fused;         // 1: fused F == 32 edge-gated sparse kernels (sp32_kernels.cuh) when the shape allows
 extern int g_opt_gemm_pair;             // 1: use the CTA-pair (cta_group::2) shift GEMM when the shape allows
 extern unsigned long long g_launches;   // kernels launched by this library (gcrnn_debug_launch_count)
 
@@ -52,6 +53,7 @@ struct gcrnn_graph {
   int *att_rptr = nullptr, *att_col = nullptr;          // row i -> columns j
   float* att_val = nullptr;                             // S'_ij
   int *att_cptr = nullptr, *att_crow = nullptr, *att_ceid = nullptr;  // column j -> (row i, edge id)
+  float* att_cval = nullptr;                            // S'_ij in column order (same order as att_crow)
   int max_row_deg = 0;
   // dense copies for the tensor-core path (E == 1): row-major [Npad, Npad] bf16, zero padded
   int Npad = 0;

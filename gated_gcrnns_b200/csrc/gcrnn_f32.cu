@@ -3,6 +3,8 @@
 // (attention), :2336-2428 (GGCRNNCell.forward); see DESIGN.md for the restructuring (gates hoisted out of the
 // recurrence because they depend on (x_t, h0) only; recompute-from-H backward).
 #include "kernels_f32.cuh"
+#include "sp32_kernels.cuh"
+#include <climits>
 
 namespace gcrnn {
 using namespace k;
@@ -366,9 +368,189 @@ void node_head_fwd(const Ctx& c, const CellDims& d, const float* ubuf, const flo
 
 }  // namespace
 
+// ===================================================================================================
+// fused edge-gated path for F == 32 (sp32_kernels.cuh): 4 kernels per forward step, 5 per backward step
+// ===================================================================================================
+namespace {
+
+bool edge32_ok(const gcrnn_cell* cell) {
+  const gcrnn_cell_desc& d = cell->d;
+  const gcrnn_graph* g = cell->g;
+  return g_opt_sparse_fused && d.spatial_gating == GCRNN_SPATIAL_EDGE && !d.time_gating && d.E == 1 && g->E == 1 && d.F == 32 &&
+         d.Kst >= 2 && d.Kst <= 4 && d.Kin * d.G <= e32::MAXKG && g->max_row_deg <= 32 && (long long)g->N * 32 < INT_MAX;
+}
+
+// extra state the fused forward leaves for the fused backward (appended after the generic `Saved` block)
+struct Saved32 {
+  float *zc, *wu_a, *wu_r; float4* info; uint2* masks;
+  void layout(Arena& a, const CellDims& d) {
+    zc = a.get<float>((size_t)(d.Kst - 2) * d.TB * d.NF);     // z_1 .. z_{Kst-2} of every step
+    wu_a = a.get<float>(d.TB * d.NF);
+    wu_r = a.get<float>(d.TB * d.NF);
+    info = a.get<float4>(2 * d.TB * d.N);
+    masks = a.get<uint2>(d.TB * d.N);
+  }
+};
+
+int sm_count() {
+  static int n = 0;
+  if (!n) { int dev = 0; CUDA_OK(cudaGetDevice(&dev)); CUDA_OK(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev)); }
+  return n;
+}
+template <class K>
+int persistent_grid(K kernel, int block, long long tasks_per_block_unit, long long tasks) {
+  int occ = 1;
+  CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, block, 0));
+  long long g = (long long)sm_count() * std::max(occ, 1);
+  const long long need = (tasks + tasks_per_block_unit - 1) / tasks_per_block_unit;
+  return (int)std::max<long long>(1, std::min(g, need));
+}
+
+void spmm32(const Ctx& c, const Gather& op, const float* in, float* out, long long R) {
+  const long long RN = R * c.g->N;
+  e32::spmm32_k<<<persistent_grid(e32::spmm32_k, 256, 8, RN), 256, 0, c.st>>>(op.ptr, op.idx, op.val, in, out, c.g->N, RN);
+  check_launch();
+}
+
+e32::Chain x_taps(const CellDims& d, const Saved& s, long long t) {
+  e32::Chain xs{};
+  for (int k = 0; k < d.Kin; ++k)
+    xs.p[k] = (k == 0 ? s.Xn : s.zx + (long long)(k - 1) * d.TB * d.NG) + t * d.B * d.NG;
+  return xs;
+}
+
+template <int KST>
+void e32_forward_steps(const Ctx& c, const CellDims& d, const gcrnn_cell_params* p, const Saved& s, const Saved32& x,
+                       const float* prep, float4* rc) {
+  const gcrnn_graph* g = c.g;
+  const long long BN = d.B * d.N, BNF = d.B * d.NF;
+  const Gather& fw = g->fwd[0];
+  const int g_filter = persistent_grid(e32::filter_fwd_k<KST>, 128, 4, BN);
+  const int g_agg = persistent_grid(e32::aggregate_k, 256, 8, BN);
+  for (long long t = 0; t < d.T; ++t) {
+    e32::Chain zc{};
+    zc.p[0] = t == 0 ? s.h0n : s.Hn + (t - 1) * BNF;
+    for (int k = 1; k <= KST - 2; ++k) {
+      float* out = x.zc + ((long long)(k - 1) * d.T + t) * BNF;
+      spmm32(c, fw, zc.p[k - 1], out, d.B);
+      zc.p[k] = out;
+    }
+    float* wa = x.wu_a + t * BNF; float* wr = x.wu_r + t * BNF;
+    float4* info = x.info + 2 * t * BN;
+    e32::filter_fwd_k<KST><<<g_filter, 128, 0, c.st>>>(fw.ptr, fw.idx, fw.val, zc, x_taps(d, s, t), d.Kin, d.G, prep,
+                                                       p->e_mixer[0], p->e_mixer[1], wa, wr, rc, d.N, BN);
+    check_launch();
+    e32::rowstats_k<<<grid1d(BN, 256), 256, 0, c.st>>>(g->att_rptr, g->att_col, rc, info, d.N, BN);
+    check_launch();
+    e32::aggregate_k<<<g_agg, 256, 0, c.st>>>(g->att_cptr, g->att_crow, g->att_cval, info, wa, wr, s.Hn + t * BNF,
+                                              x.masks + t * BN, d.N, BN);
+    check_launch();
+  }
+}
+
+size_t cell_forward_e32(const gcrnn_cell* cell, const gcrnn_cell_params* p, const float* X, const float* h0, float* H,
+                        void* saved, size_t savedb, size_t* saved_used, void* ws, size_t wsb, int64_t B, int64_t T,
+                        cudaStream_t st) {
+  const CellDims d = dims_of(cell, B, T);
+  Arena a(ws, wsb);
+  Ctx c{cell->g, st, a.dry()};
+  Saved s; Saved32 x;
+  {
+    Arena sa(saved, savedb);
+    s.layout(sa, d); x.layout(sa, d);
+    if (saved_used) *saved_used = sa.off;
+  }
+  GCRNN_CHECK(a.dry() || saved, "forward needs the `saved` buffer (see gcrnn_cell_workspace_bytes)");
+  float* prep = a.get<float>(e32::PrepLayout::TOTAL);
+  float4* rc = a.get<float4>(d.B * d.N);
+  if (a.dry()) return a.off;
+  transpose(c, X, nullptr, s.Xn, d.G, d.N, d.B, d.T, d.T * d.NG, d.NG, d.NG, d.B * d.NG);          // [B,T,G,N] -> [T,B,N,G]
+  transpose(c, h0, nullptr, s.h0n, d.F, d.N, d.B, 1, d.NF, 0, d.NF, 0);                            // [B,F,N]  -> [B,N,F]
+  shift_chain(c, s.Xn, s.zx, d.E, d.Kin, d.G, d.TB);
+  e32::prep_k<<<1, 1024, 0, st>>>(p->weight_A, p->weight_B, p->bias, p->e_weight[0], p->e_weight[1], prep, d.Kin * d.G, d.Kst);
+  check_launch();
+  switch (d.Kst) {
+    case 2: e32_forward_steps<2>(c, d, p, s, x, prep, rc); break;
+    case 3: e32_forward_steps<3>(c, d, p, s, x, prep, rc); break;
+    default: e32_forward_steps<4>(c, d, p, s, x, prep, rc); break;
+  }
+  transpose(c, s.Hn, nullptr, H, d.N, d.F, d.T, d.B, d.B * d.NF, d.NF, d.NF, d.T * d.NF);           // [T,B,N,F] -> [B,T,F,N]
+  return a.off;
+}
+
+struct Bwd32Bufs { float *dpre, *pa, *pr, *dd, *wch, *dhrec, *acc; float2* dr; };
+
+template <int KST>
+void e32_backward_steps(const Ctx& c, const CellDims& d, const gcrnn_cell_params* p, const Saved& s, const Saved32& x,
+                        const float* dH, const Bwd32Bufs& b) {
+  const gcrnn_graph* g = c.g;
+  const long long BN = d.B * d.N, BNF = d.B * d.NF;
+  const Gather& fw = g->fwd[0];
+  const Gather& bw = g->bwd[0];
+  const int g_dpre = (int)std::min<long long>(d.B * ((d.N + 31) / 32), (long long)sm_count() * 8);
+  const int g_rows = persistent_grid(e32::bwd_rows_k, 256, 8, BN);
+  const int g_node = persistent_grid(e32::bwd_node_k<KST>, 128, 4, BN);
+  const int g_dh = persistent_grid(e32::dh_k<KST>, 128, 4, BN);
+  for (long long t = d.T - 1; t >= 0; --t) {
+    const float* hn = s.Hn + t * BNF;
+    const float* wa = x.wu_a + t * BNF; const float* wr = x.wu_r + t * BNF;
+    const float4* info = x.info + 2 * t * BN;
+    e32::dpre_k<<<g_dpre, 256, 0, c.st>>>(dH + t * d.NF, d.T * d.NF, t == d.T - 1 ? nullptr : b.dhrec, hn, b.dpre, d.N, d.B);
+    check_launch();
+    zero(c, b.dr, BN * sizeof(float2));
+    e32::bwd_rows_k<<<g_rows, 256, 0, c.st>>>(g->att_rptr, g->att_col, g->att_val, info, x.masks + t * BN, wa, wr, b.dpre,
+                                              p->e_mixer[0], p->e_mixer[1], b.pa, b.pr, reinterpret_cast<float*>(b.dr), b.acc, d.N, BN);
+    check_launch();
+    e32::Chain zc{};
+    zc.p[0] = t == 0 ? s.h0n : s.Hn + (t - 1) * BNF;
+    for (int k = 1; k <= KST - 2; ++k) zc.p[k] = x.zc + ((long long)(k - 1) * d.T + t) * BNF;
+    e32::bwd_node_k<KST><<<g_node, 128, 0, c.st>>>(fw.ptr, fw.idx, fw.val, zc, x_taps(d, s, t), d.Kin, d.G, b.pa, b.pr, b.dr, wa, wr,
+                                                   p->e_mixer[0], p->e_mixer[1], p->e_weight[1], b.dd, b.acc, d.N, BN);
+    check_launch();
+    e32::Chain wc{};
+    wc.p[0] = b.dd;
+    for (int k = 1; k <= KST - 2; ++k) {
+      float* out = b.wch + (long long)(k - 1) * BNF;
+      spmm32(c, bw, wc.p[k - 1], out, d.B);
+      wc.p[k] = out;
+    }
+    e32::dh_k<KST><<<g_dh, 128, 0, c.st>>>(bw.ptr, bw.idx, bw.val, wc, p->weight_B, b.dhrec, d.N, BN);
+    check_launch();
+  }
+}
+
+size_t cell_backward_e32(const gcrnn_cell* cell, const gcrnn_cell_params* p, const float* dH, const void* saved, size_t savedb,
+                         const gcrnn_cell_params* gr, float* dh0, void* ws, size_t wsb, int64_t B, int64_t T, cudaStream_t st) {
+  const CellDims d = dims_of(cell, B, T);
+  Arena a(ws, wsb);
+  Ctx c{cell->g, st, a.dry()};
+  Saved s; Saved32 x;
+  { Arena sa(const_cast<void*>(saved), savedb); s.layout(sa, d); x.layout(sa, d); }
+  Bwd32Bufs b;
+  b.dpre = a.get<float>(d.B * d.NF); b.pa = a.get<float>(d.B * d.NF); b.pr = a.get<float>(d.B * d.NF);
+  b.dd = a.get<float>(d.B * d.NF); b.wch = a.get<float>((size_t)(d.Kst - 2) * d.B * d.NF); b.dhrec = a.get<float>(d.B * d.NF);
+  b.dr = a.get<float2>(d.B * d.N); b.acc = a.get<float>(e32::AccLayout::TOTAL);
+  if (a.dry()) return a.off;
+  zero(c, b.acc, e32::AccLayout::TOTAL * sizeof(float));
+  switch (d.Kst) {
+    case 2: e32_backward_steps<2>(c, d, p, s, x, dH, b); break;
+    case 3: e32_backward_steps<3>(c, d, p, s, x, dH, b); break;
+    default: e32_backward_steps<4>(c, d, p, s, x, dH, b); break;
+  }
+  e32::finalize_k<<<1, 1024, 0, st>>>(b.acc, p->weight_A, p->weight_B, p->bias, p->e_weight[0], p->e_weight[1], gr->weight_A,
+                                      gr->weight_B, gr->bias, gr->e_mixer[0], gr->e_weight[0], gr->e_mixer[1], gr->e_weight[1],
+                                      d.Kin * d.G, d.Kst);
+  check_launch();
+  if (dh0) transpose(c, b.dhrec, nullptr, dh0, d.N, d.F, d.B, 1, d.NF, 0, d.NF, 0);
+  return a.off;
+}
+
+}  // namespace
+
 size_t cell_forward_f32(const gcrnn_cell* cell, const gcrnn_cell_params* p, const float* X, const float* h0, float* H,
                         void* saved, size_t savedb, size_t* saved_used, void* ws, size_t wsb, int64_t B, int64_t T,
                         cudaStream_t st) {
+  if (edge32_ok(cell)) return cell_forward_e32(cell, p, X, h0, H, saved, savedb, saved_used, ws, wsb, B, T, st);
   const CellDims d = dims_of(cell, B, T);
   Arena a(ws, wsb);
   Ctx c{cell->g, st, a.dry()};
@@ -438,6 +620,15 @@ size_t cell_backward_f32(const gcrnn_cell* cell, const gcrnn_cell_params* p, con
                          int64_t T, cudaStream_t st) {
   (void)X; (void)h0; (void)H;
   const CellDims d = dims_of(cell, B, T);
+  if (edge32_ok(cell)) {
+    // the fused backward has no dX; a caller that wants it gets the generic sweep, which only reads the generic part of
+    // `saved` (a prefix of what the fused forward wrote).  The scratch query must cover whichever of the two is larger.
+    size_t need_saved = 0;
+    { Arena sa(nullptr, 0); Saved s0; Saved32 x0; s0.layout(sa, d); x0.layout(sa, d); need_saved = sa.off; }
+    const bool dry = ws == nullptr;
+    if (!dX && (dry || savedb >= need_saved))
+      return cell_backward_e32(cell, p, dH, saved, savedb, gr, dh0, ws, wsb, B, T, st);
+  }
   Arena a(ws, wsb);
   Ctx c{cell->g, st, a.dry()};
   const gcrnn_graph* g = cell->g;

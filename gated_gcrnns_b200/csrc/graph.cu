@@ -70,12 +70,14 @@ static void build_attention_pattern(gcrnn_graph* g, const HostCsr& s) {
   g->att_rptr = upload(g, a.ptr); g->att_col = upload(g, a.idx); g->att_val = upload(g, a.val);
   // column view carrying (row, edge id)
   std::vector<int> cptr(N + 1, 0), crow(a.idx.size()), ceid(a.idx.size());
+  std::vector<float> cval(a.idx.size());
   for (size_t p = 0; p < a.idx.size(); ++p) cptr[a.idx[p] + 1]++;
   for (int i = 0; i < N; ++i) cptr[i + 1] += cptr[i];
   std::vector<int> cur(cptr.begin(), cptr.end() - 1);
   for (int i = 0; i < N; ++i)
-    for (int p = a.ptr[i]; p < a.ptr[i + 1]; ++p) { int q = cur[a.idx[p]]++; crow[q] = i; ceid[q] = p; }
+    for (int p = a.ptr[i]; p < a.ptr[i + 1]; ++p) { int q = cur[a.idx[p]]++; crow[q] = i; ceid[q] = p; cval[q] = a.val[p]; }
   g->att_cptr = upload(g, cptr); g->att_crow = upload(g, crow); g->att_ceid = upload(g, ceid);
+  g->att_cval = upload(g, cval);
 }
 
 gcrnn_graph* graph_from_host_csr(int N, int E, const std::vector<HostCsr>& ops, int device) {

@@ -1,0 +1,132 @@
+"""GPU: the fused F == 32 edge-gated sparse kernels (csrc/sp32_kernels.cuh, the cfg5 path) against the fp64 oracle and
+against the generic per-op kernels of the same library.
+
+Tolerances as in test_gpu_parity.py (fp32 exact path vs fp64 reference, max-norm relative to max|ref|):
+  H : 1e-5      parameter gradients and dh0 : 1e-4
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+import gated_gcrnns_b200 as gg
+from gated_gcrnns_b200 import _lib
+from oracle import gcrnn_oracle as orc
+
+pytestmark = pytest.mark.gpu
+TOL_OUT, TOL_GRAD = 1e-5, 1e-4
+DEV = 'cuda:0'
+
+
+def relerr(a, b):
+    a = a.detach().cpu().double().numpy()
+    b = b.detach().cpu().double().numpy()
+    assert a.shape == b.shape
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
+
+
+def ragged_graph(N, seed, max_out=31, hub=True):
+    """Non-symmetric sparse S with out-degrees 0..max_out (row degree of S+I <= 32), one hub column of in-degree > 32,
+    a node whose only edge is the added self loop, and one explicit diagonal entry."""
+    rng = np.random.RandomState(seed)
+    S = np.zeros((N, N))
+    for i in range(N):
+        deg = rng.randint(0, max_out + 1) if i > 2 else (0, max_out, 16)[i]
+        cols = rng.choice(np.delete(np.arange(N), i), size=deg, replace=False)
+        S[i, cols] = rng.rand(deg) + 0.1
+    if hub:
+        rows = rng.choice(np.arange(3, N), size=min(N - 3, 45), replace=False)
+        for i in rows:
+            if S[i, 7] == 0 and (S[i] != 0).sum() < max_out:
+                S[i, 7] = rng.rand() + 0.1
+    if (S[5] != 0).sum() < max_out:
+        S[5, 5] = 0.37
+    S = S / np.abs(np.linalg.eigvals(S)).max()
+    return torch.tensor(S).reshape(1, N, N)
+
+
+def run_case(N, G_, Kin, Kst, T, B, bias, seed, need_x=False):
+    torch.manual_seed(seed)
+    F_ = 32
+    S = ragged_graph(N, seed)
+    prev = torch.get_default_dtype(); torch.set_default_dtype(torch.float64)
+    try:
+        p = orc.init_cell_params(G_, F_, Kin, Kst, N, False, 'edge', 1, bias)
+    finally:
+        torch.set_default_dtype(prev)
+    X, h0, dH = torch.randn(B, T, G_, N).double(), 0.3 * torch.randn(B, F_, N).double(), torch.randn(B, T, F_, N).double()
+    Href, gref = orc.cell_forward_backward(p, S, X, h0, dH, False, 'edge', input_grads=True)
+    cell = gg.GGCRNNCell(G_, F_, Kin, Kst, torch.tanh, False, 'edge', 1, bias)
+    cell.addGSO(S)
+    cell.load_state_dict({k: v for k, v in p.items()})
+    cell = cell.to(device=DEV, dtype=torch.float32)
+    Xg = X.float().to(DEV).requires_grad_(need_x)
+    hg = h0.float().to(DEV).requires_grad_(True)
+    L = _lib.lib()
+    l0 = L.gcrnn_debug_launch_count()
+    H = cell(Xg, hg)
+    (H * dH.float().to(DEV)).sum().backward()
+    torch.cuda.synchronize()
+    launches = L.gcrnn_debug_launch_count() - l0
+    errs = {'H': relerr(H, Href), 'dh0': relerr(hg.grad, gref['__h0'])}
+    if need_x:
+        errs['dX'] = relerr(Xg.grad, gref['__X'])
+    for k, v in cell.named_parameters():
+        if gref[k] is None:
+            assert v.grad is None
+        else:
+            errs[k] = relerr(v.grad, gref[k])
+    bad = {k: v for k, v in errs.items() if v > (TOL_OUT if k == 'H' else TOL_GRAD)}
+    assert not bad, bad
+    return launches, H.detach(), {k: v.grad.detach().clone() for k, v in cell.named_parameters() if v.grad is not None}
+
+
+@pytest.mark.parametrize('G_,Kin,Kst,bias', [(1, 3, 3, True), (2, 4, 2, True), (1, 2, 4, False), (3, 5, 3, True)])
+def test_fused_edge32_vs_oracle(G_, Kin, Kst, bias):
+    launches, _, _ = run_case(N=150, G_=G_, Kin=Kin, Kst=Kst, T=5, B=3, bias=bias, seed=11 + Kst)
+    # 4 + (Kst - 2) kernels per forward step and 4 + (Kst - 2) + 1 memset-free kernels per backward step, plus set-up
+    assert launches < 5 * (10 + 2 * (Kst - 2)) + 12 + 2 * Kin, f'the fused kernels did not run ({launches} launches)'
+
+
+def test_fused_matches_generic_kernels_and_falls_back_for_dX():
+    L = _lib.lib()
+    old = L.gcrnn_debug_set_option(b'sparse_fused', 0)
+    try:
+        lg, Hg, gg_ = run_case(N=130, G_=1, Kin=3, Kst=3, T=4, B=2, bias=True, seed=5)
+    finally:
+        L.gcrnn_debug_set_option(b'sparse_fused', old)
+    lf, Hf, gf = run_case(N=130, G_=1, Kin=3, Kst=3, T=4, B=2, bias=True, seed=5)
+    assert lf < lg
+    assert relerr(Hf, Hg) < 2e-6
+    for k in gg_:
+        assert relerr(gf[k], gg_[k]) < 2e-5, k
+    # dX requested: fused forward, generic reverse sweep on the prefix of the saved state
+    run_case(N=130, G_=2, Kin=3, Kst=3, T=4, B=2, bias=True, seed=6, need_x=True)
+
+
+def test_fused_large_knn_properties():
+    """cfg5-like sizes (N = 20000 here): finite outputs, |h| <= 1, and batch-sample independence (sample b of a
+    batch equals the same sample run alone), which a mis-indexed gather or a cross-sample race would break."""
+    N, F_, K, T, B = 20000, 32, 3, 3, 3
+    rp, ci, va = gg.graphs.knn_csr(N, 16, seed=1, power_iters=10)
+    S = gg.graphs.csr_to_torch_sparse(rp, ci, va, N)
+    torch.manual_seed(0)
+    cell = gg.GGCRNNCell(1, F_, K, K, torch.tanh, False, 'edge', 1, True)
+    cell.addGSO(S)
+    cell = cell.to(DEV)
+    X = torch.randn(B, T, 1, N, device=DEV)
+    h0 = 0.1 * torch.randn(B, F_, N, device=DEV)
+    H = cell(X, h0)
+    H.sum().backward()
+    g_all = cell.weight_B.grad.clone()
+    assert torch.isfinite(H).all() and H.abs().max() <= 1.0
+    cell.zero_grad()
+    acc = torch.zeros_like(g_all)
+    for b in range(B):
+        cell.zero_grad()
+        Hb = cell(X[b:b + 1], h0[b:b + 1])
+        assert torch.allclose(Hb[0], H[b].detach(), rtol=0, atol=2e-6)
+        Hb.sum().backward()
+        acc += cell.weight_B.grad
+    assert relerr(acc, g_all) < 1e-4
