@@ -377,7 +377,8 @@ bool edge32_ok(const gcrnn_cell* cell) {
   const gcrnn_cell_desc& d = cell->d;
   const gcrnn_graph* g = cell->g;
   return g_opt_sparse_fused && d.spatial_gating == GCRNN_SPATIAL_EDGE && !d.time_gating && d.E == 1 && g->E == 1 && d.F == 32 &&
-         d.Kst >= 2 && d.Kst <= 4 && d.Kin * d.G <= e32::MAXKG && g->max_row_deg <= 32 && (long long)g->N * 32 < INT_MAX;
+         d.Kst >= 2 && d.Kst <= 4 && d.Kin * d.G <= e32::MAXKG && d.Kin <= e32::MAXK && g->max_row_deg <= 32 && g->N >= 64 &&
+         (long long)g->N * 32 < INT_MAX;
 }
 
 // extra state the fused forward leaves for the fused backward (appended after the generic `Saved` block)
@@ -398,9 +399,10 @@ int sm_count() {
   return n;
 }
 template <class K>
-int persistent_grid(K kernel, int block, long long tasks_per_block_unit, long long tasks) {
+int persistent_grid(K kernel, int block, long long tasks_per_block_unit, long long tasks, size_t dyn_smem = 0) {
   int occ = 1;
-  CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, block, 0));
+  if (dyn_smem > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
+  CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, block, dyn_smem));
   long long g = (long long)sm_count() * std::max(occ, 1);
   const long long need = (tasks + tasks_per_block_unit - 1) / tasks_per_block_unit;
   return (int)std::max<long long>(1, std::min(g, need));
@@ -408,7 +410,7 @@ int persistent_grid(K kernel, int block, long long tasks_per_block_unit, long lo
 
 void spmm32(const Ctx& c, const Gather& op, const float* in, float* out, long long R) {
   const long long RN = R * c.g->N;
-  e32::spmm32_k<<<persistent_grid(e32::spmm32_k, 256, 8, RN), 256, 0, c.st>>>(op.ptr, op.idx, op.val, in, out, c.g->N, RN);
+  e32::spmm32_k<<<persistent_grid(e32::spmm32_k, 256, 8, RN), 256, 0, c.st>>>(e32::Gather3{op.ptr, op.idx, op.val}, in, out, c.g->N, RN);
   check_launch();
 }
 
@@ -426,7 +428,9 @@ void e32_forward_steps(const Ctx& c, const CellDims& d, const gcrnn_cell_params*
   const long long BN = d.B * d.N, BNF = d.B * d.NF;
   const Gather& fw = g->fwd[0];
   const int g_filter = persistent_grid(e32::filter_fwd_k<KST>, 128, 4, BN);
-  const int g_agg = persistent_grid(e32::aggregate_k, 256, 8, BN);
+  const size_t agg_smem = (size_t)4 * 2 * e32::AGG_STAGE * sizeof(float);
+  const int g_agg = persistent_grid(e32::aggregate_k, 128, 4, BN, agg_smem);
+  const e32::Gather3 gop{fw.ptr, fw.idx, fw.val};
   for (long long t = 0; t < d.T; ++t) {
     e32::Chain zc{};
     zc.p[0] = t == 0 ? s.h0n : s.Hn + (t - 1) * BNF;
@@ -437,12 +441,12 @@ void e32_forward_steps(const Ctx& c, const CellDims& d, const gcrnn_cell_params*
     }
     float* wa = x.wu_a + t * BNF; float* wr = x.wu_r + t * BNF;
     float4* info = x.info + 2 * t * BN;
-    e32::filter_fwd_k<KST><<<g_filter, 128, 0, c.st>>>(fw.ptr, fw.idx, fw.val, zc, x_taps(d, s, t), d.Kin, d.G, prep,
+    e32::filter_fwd_k<KST><<<g_filter, 128, 0, c.st>>>(gop, zc, x_taps(d, s, t), d.Kin, d.G, prep,
                                                        p->e_mixer[0], p->e_mixer[1], wa, wr, rc, d.N, BN);
     check_launch();
     e32::rowstats_k<<<grid1d(BN, 256), 256, 0, c.st>>>(g->att_rptr, g->att_col, rc, info, d.N, BN);
     check_launch();
-    e32::aggregate_k<<<g_agg, 256, 0, c.st>>>(g->att_cptr, g->att_crow, g->att_cval, info, wa, wr, s.Hn + t * BNF,
+    e32::aggregate_k<<<g_agg, 128, agg_smem, c.st>>>(g->att_cptr, g->att_crow, g->att_cval, info, wa, wr, s.Hn + t * BNF,
                                               x.masks + t * BN, d.N, BN);
     check_launch();
   }
@@ -478,7 +482,7 @@ size_t cell_forward_e32(const gcrnn_cell* cell, const gcrnn_cell_params* p, cons
   return a.off;
 }
 
-struct Bwd32Bufs { float *dpre, *pa, *pr, *dd, *wch, *dhrec, *acc; float2* dr; };
+struct Bwd32Bufs { float *dya, *dyr, *pa, *pr, *dd, *wch, *dhrec, *acc; float2* dr; };
 
 template <int KST>
 void e32_backward_steps(const Ctx& c, const CellDims& d, const gcrnn_cell_params* p, const Saved& s, const Saved32& x,
@@ -488,23 +492,26 @@ void e32_backward_steps(const Ctx& c, const CellDims& d, const gcrnn_cell_params
   const Gather& fw = g->fwd[0];
   const Gather& bw = g->bwd[0];
   const int g_dpre = (int)std::min<long long>(d.B * ((d.N + 31) / 32), (long long)sm_count() * 8);
-  const int g_rows = persistent_grid(e32::bwd_rows_k, 256, 8, BN);
+  const size_t rows_smem = (size_t)4 * 2 * e32::ROWS_STAGE * sizeof(float);
+  const int g_rows = persistent_grid(e32::bwd_rows_k, 128, 4, BN, rows_smem);
+  const e32::Gather3 gfw{fw.ptr, fw.idx, fw.val}, gbw{bw.ptr, bw.idx, bw.val};
   const int g_node = persistent_grid(e32::bwd_node_k<KST>, 128, 4, BN);
   const int g_dh = persistent_grid(e32::dh_k<KST>, 128, 4, BN);
   for (long long t = d.T - 1; t >= 0; --t) {
     const float* hn = s.Hn + t * BNF;
     const float* wa = x.wu_a + t * BNF; const float* wr = x.wu_r + t * BNF;
     const float4* info = x.info + 2 * t * BN;
-    e32::dpre_k<<<g_dpre, 256, 0, c.st>>>(dH + t * d.NF, d.T * d.NF, t == d.T - 1 ? nullptr : b.dhrec, hn, b.dpre, d.N, d.B);
+    e32::dpre_k<<<g_dpre, 256, 0, c.st>>>(dH + t * d.NF, d.T * d.NF, t == d.T - 1 ? nullptr : b.dhrec, hn, x.masks + t * BN, b.dya, b.dyr,
+                                          d.N, d.B);
     check_launch();
     zero(c, b.dr, BN * sizeof(float2));
-    e32::bwd_rows_k<<<g_rows, 256, 0, c.st>>>(g->att_rptr, g->att_col, g->att_val, info, x.masks + t * BN, wa, wr, b.dpre,
+    e32::bwd_rows_k<<<g_rows, 128, rows_smem, c.st>>>(g->att_rptr, g->att_col, g->att_val, info, wa, wr, b.dya, b.dyr,
                                               p->e_mixer[0], p->e_mixer[1], b.pa, b.pr, reinterpret_cast<float*>(b.dr), b.acc, d.N, BN);
     check_launch();
     e32::Chain zc{};
     zc.p[0] = t == 0 ? s.h0n : s.Hn + (t - 1) * BNF;
     for (int k = 1; k <= KST - 2; ++k) zc.p[k] = x.zc + ((long long)(k - 1) * d.T + t) * BNF;
-    e32::bwd_node_k<KST><<<g_node, 128, 0, c.st>>>(fw.ptr, fw.idx, fw.val, zc, x_taps(d, s, t), d.Kin, d.G, b.pa, b.pr, b.dr, wa, wr,
+    e32::bwd_node_k<KST><<<g_node, 128, 0, c.st>>>(gfw, zc, x_taps(d, s, t), d.Kin, d.G, b.pa, b.pr, b.dr, wa, wr,
                                                    p->e_mixer[0], p->e_mixer[1], p->e_weight[1], b.dd, b.acc, d.N, BN);
     check_launch();
     e32::Chain wc{};
@@ -514,7 +521,7 @@ void e32_backward_steps(const Ctx& c, const CellDims& d, const gcrnn_cell_params
       spmm32(c, bw, wc.p[k - 1], out, d.B);
       wc.p[k] = out;
     }
-    e32::dh_k<KST><<<g_dh, 128, 0, c.st>>>(bw.ptr, bw.idx, bw.val, wc, p->weight_B, b.dhrec, d.N, BN);
+    e32::dh_k<KST><<<g_dh, 128, 0, c.st>>>(gbw, wc, p->weight_B, b.dhrec, d.N, BN);
     check_launch();
   }
 }
@@ -527,7 +534,7 @@ size_t cell_backward_e32(const gcrnn_cell* cell, const gcrnn_cell_params* p, con
   Saved s; Saved32 x;
   { Arena sa(const_cast<void*>(saved), savedb); s.layout(sa, d); x.layout(sa, d); }
   Bwd32Bufs b;
-  b.dpre = a.get<float>(d.B * d.NF); b.pa = a.get<float>(d.B * d.NF); b.pr = a.get<float>(d.B * d.NF);
+  b.dya = a.get<float>(d.B * d.NF); b.dyr = a.get<float>(d.B * d.NF); b.pa = a.get<float>(d.B * d.NF); b.pr = a.get<float>(d.B * d.NF);
   b.dd = a.get<float>(d.B * d.NF); b.wch = a.get<float>((size_t)(d.Kst - 2) * d.B * d.NF); b.dhrec = a.get<float>(d.B * d.NF);
   b.dr = a.get<float2>(d.B * d.N); b.acc = a.get<float>(e32::AccLayout::TOTAL);
   if (a.dry()) return a.off;

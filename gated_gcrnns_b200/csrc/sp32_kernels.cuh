@@ -1,7 +1,7 @@
 // Fused fp32 kernels of the sparse EDGE-GATED recurrence for F == 32 state features (the cfg5 shape of SURVEY.md §8d:
-// CSR kNN graph, N = 1e5).  One warp owns one (sample, node) pair and lane == feature, so a node's signal is one
-// coalesced 128-byte row and every neighbour gather is one full cache line.  Blocks walk CONTIGUOUS node ranges so
-// that, with a locality-preserving node ordering, neighbour rows are re-used out of L1/L2 instead of HBM.
+// CSR kNN graph, N = 1e5).  One warp owns one (sample, node) pair, a node's signal is one coalesced 128-byte row and
+// every neighbour gather is one full cache line.  Blocks walk CONTIGUOUS node ranges so that, with a locality-
+// preserving node ordering, neighbour rows are re-used out of L1/L2 instead of HBM.
 //
 // Reference op sites (Utils/graphML.py): LSIGF shift :123 + contraction :134-139; graphAttention :586-625 with
 // S' = S + I :577, leaky_relu(0.2) :603, masked softmax over j :611-622, aggregation over i :625; relu :2101;
@@ -12,6 +12,10 @@
 //   * the weight gradients of BOTH the filter taps and the attention weight follow from one accumulated
 //     outer product  M_k = sum_n dWu[n] (x) z_k[n]:   dB_k = W^T M_k,  dW = sum_k M_k B_k^T + (sum_n dWu) b^T;
 //   * dh_{t-1} = sum_k B_k^T (d S^T^k) with d = W^T dWu : the adjoint chain shifts ONE signal, then contracts.
+//
+// Two lane layouts are used.  "F-layout": lane == feature (contractions, whose weights sit in registers).
+// "Q-layout": lane = 8 g + c reads the 16-byte chunk c of row (4 i + g) — one LDS.128 / LDG.128 covers FOUR neighbour
+// rows — and a 3-shuffle reduce-scatter over the four groups leaves feature FEAT(lane) = 4 c + g on each lane.
 #pragma once
 #include "common.cuh"
 
@@ -22,7 +26,7 @@ constexpr int F = 32;
 constexpr int MAXKG = 16;           // Kin * G input taps handled by the fused kernels
 constexpr int MAXK = 5;             // state taps
 struct Chain { const float* p[MAXK]; };
-struct ChainMut { float* p[MAXK]; };
+struct Gather3 { const int* ptr; const int* idx; const float* val; };
 
 // small per-call scratch of accumulated reductions (floats)
 struct AccLayout {
@@ -45,15 +49,17 @@ struct PrepLayout {
   static constexpr int TOTAL = CA0 + 32;
 };
 
+__device__ __forceinline__ int feat_of_lane(int lane) { return 4 * (lane & 7) + (lane >> 3); }
+__device__ __forceinline__ int lane_of_feat(int f) { return 8 * (f & 3) + (f >> 2); }
 __device__ __forceinline__ float leaky(float x) { return x > 0.f ? x : 0.2f * x; }
-__device__ __forceinline__ float wsum(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
 __device__ __forceinline__ float hsum(float v) {     // sum within each 16-lane half
 #pragma unroll
   for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float osum(float v) {     // sum within each 8-lane group
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
 // Sum four per-lane values over the warp with 6 shuffles: totals land on lanes 0 (v0), 16 (v1), 8 (v2), 24 (v3).
@@ -66,68 +72,184 @@ __device__ __forceinline__ float wsum4(float v0, float v1, float v2, float v3, i
   for (int o = 4; o > 0; o >>= 1) k += __shfl_xor_sync(0xffffffffu, k, o);
   return k;
 }
-// prod[s] summed over lanes, result of slot L on lane L (31 shuffles for 32 slots)
-template <int M>
-__device__ __forceinline__ void tree_step(float (&prod)[32], int lane) {
-  const bool up = lane & M;
-#pragma unroll
-  for (int k = 0; k < M; ++k) {
-    const float lo = prod[k], hi = prod[k + M];
-    prod[k] = (up ? hi : lo) + __shfl_xor_sync(0xffffffffu, up ? lo : hi, M);
-  }
+// Q-layout reduce-scatter: every lane holds a float4 partial of chunk c = lane & 7; returns the total of feature
+// FEAT(lane) = 4 c + g summed over the four groups g = lane >> 3  (3 shuffles)
+__device__ __forceinline__ float rs4(const float4& a, int lane) {
+  const bool hi = lane & 16, odd = lane & 8;
+  float k0 = (hi ? a.z : a.x) + __shfl_xor_sync(0xffffffffu, hi ? a.x : a.z, 16);
+  float k1 = (hi ? a.w : a.y) + __shfl_xor_sync(0xffffffffu, hi ? a.y : a.w, 16);
+  return (odd ? k1 : k0) + __shfl_xor_sync(0xffffffffu, odd ? k0 : k1, 8);
 }
-__device__ __forceinline__ float tree32(float (&prod)[32], int lane) {
-  tree_step<16>(prod, lane); tree_step<8>(prod, lane); tree_step<4>(prod, lane); tree_step<2>(prod, lane); tree_step<1>(prod, lane);
-  return prod[0];
+__device__ __forceinline__ void fma4(float4& acc, float s, const float4& x) {
+  acc.x = fmaf(s, x.x, acc.x); acc.y = fmaf(s, x.y, acc.y); acc.z = fmaf(s, x.z, acc.z); acc.w = fmaf(s, x.w, acc.w);
 }
+__device__ __forceinline__ float dot4(const float4& a, const float4& b) {
+  return fmaf(a.w, b.w, fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)));
+}
+// acc2 += w2 * (v0, v1) on the packed fp32 pipe (one issue slot for two FMAs)
+__device__ __forceinline__ void fma2(float2& acc, const float2& w, float v0, float v1) { acc = __ffma2_rn(w, make_float2(v0, v1), acc); }
+// tanh for x >= 0 (sum of two relus): 1 - 2 / (e^{2x} + 1) with MUFU exp / rcp; abs. error ~1e-7
+__device__ __forceinline__ float tanh_pos(float x) { return 1.f - __fdividef(2.f, __expf(2.f * x) + 1.f); }
 
-// contiguous task range of this block; (r, n) of a task advanced incrementally (no 64-bit division per task)
-struct Walk {
-  long long task, hi, r;
-  int n, N, step;
-  __device__ __forceinline__ Walk(long long total, int N_, int warp, int nwarps) : N(N_), step(nwarps) {
+__device__ __forceinline__ void cp_async16(float* smem, const float* gmem) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int NPEND>
+__device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(NPEND) : "memory"); }
+
+// ---- software pipeline ---------------------------------------------------------------------------------------------
+// A warp walking "row pointers -> edge list -> neighbour rows -> math" one task at a time exposes three dependent
+// global-load latencies per task.  Instead each warp runs a 4-stage pipeline over ITS task sequence: iteration `it`
+// loads the row pointers of task it+3 (S0), the edge list of task it+2 (S1), issues cp.async copies of every row task
+// it+1 needs into a warp-private double-buffered shared-memory stage (S2), and computes task it (S3).
+struct Tk { int r, n; };
+// this warp's task sequence inside the block's CONTIGUOUS task range: first + j * nw, j = 0 .. niter-1
+struct WarpTasks {
+  Tk t0, t1, t2, t3;           // coordinates of the tasks of stages S0 .. S3 in the current iteration
+  int niter, nw, N;
+  __device__ __forceinline__ WarpTasks(long long total, int N_, int warp, int nwarps) : nw(nwarps), N(N_) {
     const long long per = (total + gridDim.x - 1) / gridDim.x;
     const long long lo = (long long)blockIdx.x * per;
-    hi = lo + per < total ? lo + per : total;
-    task = lo + warp;
-    r = task / N; n = (int)(task - r * N);
+    const long long hi = lo + per < total ? lo + per : total;
+    const long long first = lo + warp;
+    niter = hi > first ? (int)((hi - first + nwarps - 1) / nwarps) : 0;
+    t0.r = (int)(first / N); t0.n = (int)(first - (long long)t0.r * N);
+    t1 = t2 = t3 = t0;
   }
-  __device__ __forceinline__ bool ok() const { return task < hi; }
-  __device__ __forceinline__ void next() {
-    task += step; n += step;
-    while (n >= N) { n -= N; ++r; }
+  __device__ __forceinline__ void advance() {          // needs nw <= N
+    t3 = t2; t2 = t1; t1 = t0;
+    t0.n += nw;
+    if (t0.n >= N) { t0.n -= N; ++t0.r; }
+  }
+  __device__ __forceinline__ size_t row(const Tk& t) const { return (size_t)t.r * N + t.n; }      // task index
+  __device__ __forceinline__ size_t sample(const Tk& t) const { return (size_t)t.r * N; }
+};
+
+// Pipeline for "NS streamed rows + one gathered row" tasks:  gathered[f] = sum_p val[p] * gsrc[r, idx[p], f].
+// The first 32 edges of a destination go through the cp.async stage, a longer tail is fetched synchronously.
+template <int NS>
+struct GatherPipe {
+  static constexpr int ROWS = NS + 32;
+  float* wbuf;                                  // this warp's stage: [2][ROWS][32]
+  Gather3 op;
+  const float* gsrc;                            // gathered array [R, N, 32]
+  const float* srow[NS];                        // streamed arrays [R, N, 32]
+  const float* aux; int aux_stride;             // optional per-lane scalar of the task: aux[task * aux_stride]
+  int lane;
+  int a_p0, a_deg, b_p0, b_deg, b_mi, c_p0, c_deg, d_p0, d_deg;
+  float b_mv, c_mv, d_mv, c_aux, d_aux;
+
+  __device__ __forceinline__ void init(float* buf, const Gather3& g, const float* gathered_from, int lane_) {
+    wbuf = buf; op = g; gsrc = gathered_from; aux = nullptr; aux_stride = 0; lane = lane_;
+    a_p0 = a_deg = b_p0 = b_deg = b_mi = c_p0 = c_deg = d_p0 = d_deg = 0;
+    b_mv = c_mv = d_mv = c_aux = d_aux = 0.f;
+    for (int i = lane; i < 2 * ROWS * 32; i += 32) buf[i] = 0.f;     // stale rows are multiplied by 0: keep them finite
+    __syncwarp();
+  }
+  // runs S2, S1, S0 of iteration `it`; afterwards d_* describe task `it` (coordinates wt.t3)
+  __device__ __forceinline__ void advance(int it, const WarpTasks& wt) {
+    d_p0 = c_p0; d_deg = c_deg; d_mv = c_mv; d_aux = c_aux;
+    {                                           // S2: task it + 1
+      const int j = it + 1;
+      c_p0 = b_p0; c_deg = b_deg; c_mv = b_mv; c_aux = 0.f;
+      if (j >= 0 && j < wt.niter) {
+        const size_t task = wt.row(wt.t2);
+        float* dst = wbuf + (j & 1) * (ROWS * 32) + lane * 4;           // + row * 32
+        const int g = lane >> 3, ch = (lane & 7) * 4;
+#pragma unroll
+        for (int k0 = 0; k0 < NS; k0 += 4) {
+          const int k = k0 + g;
+          const float* sp = srow[0];
+#pragma unroll
+          for (int m = 1; m < NS; ++m) if (k == m) sp = srow[m];
+          if (k < NS) cp_async16(dst + k0 * 32, sp + task * 32 + ch);
+        }
+        const int cnt = min(b_deg, 32);
+        const float* gb = gsrc + wt.sample(wt.t2) * 32 + ch;
+        float* gd = dst + NS * 32;
+        for (int q0 = 0; q0 < cnt; q0 += 4) {
+          const int src = __shfl_sync(0xffffffffu, b_mi, (q0 + g) & 31);
+          if (q0 + g < cnt) cp_async16(gd + q0 * 32, gb + (size_t)src * 32);
+        }
+        if (aux) c_aux = __ldg(aux + task * aux_stride);
+      }
+      cp_commit();
+    }
+    {                                           // S1: task it + 2
+      const int j = it + 2;
+      b_p0 = a_p0; b_deg = a_deg; b_mi = 0; b_mv = 0.f;
+      if (j >= 0 && j < wt.niter && lane < min(a_deg, 32)) { b_mi = __ldg(op.idx + a_p0 + lane); b_mv = __ldg(op.val + a_p0 + lane); }
+    }
+    {                                           // S0: task it + 3
+      a_p0 = 0; a_deg = 0;
+      if (it + 3 < wt.niter) { a_p0 = __ldg(op.ptr + wt.t0.n); a_deg = __ldg(op.ptr + wt.t0.n + 1) - a_p0; }
+    }
+  }
+  // S3 helpers (call after advance(it), it >= 0)
+  __device__ __forceinline__ const float* rows(int it) const { return wbuf + (it & 1) * (ROWS * 32); }
+  // value of feature FEAT(lane) of the gathered row (waits for the stage of task `it`)
+  __device__ __forceinline__ float gathered(int it, const WarpTasks& wt) {
+    cp_wait<1>();
+    __syncwarp();
+    const int g = lane >> 3;
+    const float4* gr = reinterpret_cast<const float4*>(rows(it) + NS * 32) + lane;   // row q0 + g, chunk c : + q0 * 8
+    const int cnt = min(d_deg, 32);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int q0 = 0; q0 < cnt; q0 += 4)
+      fma4(acc, __shfl_sync(0xffffffffu, d_mv, (q0 + g) & 31), gr[q0 * 8]);     // val = 0 beyond the edge list
+    if (d_deg > 32) {                            // rare long tail: synchronous
+      const float4* base = reinterpret_cast<const float4*>(gsrc + wt.sample(wt.t3) * 32) + (lane & 7);
+      for (int pb = d_p0 + 32; pb < d_p0 + d_deg; pb += 32) {
+        const int c2 = min(32, d_p0 + d_deg - pb);
+        int mi = 0; float mv = 0.f;
+        if (lane < c2) { mi = __ldg(op.idx + pb + lane); mv = __ldg(op.val + pb + lane); }
+        for (int q0 = 0; q0 < c2; q0 += 4) {
+          const int src = __shfl_sync(0xffffffffu, mi, (q0 + g) & 31);
+          fma4(acc, __shfl_sync(0xffffffffu, mv, (q0 + g) & 31), __ldg(base + (size_t)src * 8));
+        }
+      }
+    }
+    return rs4(acc, lane);
   }
 };
 
-// acc = sum_p val[p] * rows[idx[p]][lane] over the edges p0..p1 of one destination node (sequential order in p)
-__device__ __forceinline__ float gather_row(const int* __restrict__ idx, const float* __restrict__ val, int p0, int p1,
-                                            const float* __restrict__ rows /* + sample offset + lane */, int lane) {
-  float acc = 0.f;
-  for (int pb = p0; pb < p1; pb += 32) {
-    const int cnt = min(32, p1 - pb);
-    int mi = 0; float mv = 0.f;
-    if (lane < cnt) { mi = __ldg(idx + pb + lane); mv = __ldg(val + pb + lane); }
-    int q = 0;
-    for (; q + 8 <= cnt; q += 8) {
-      float x[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) x[u] = __ldg(rows + (size_t)__shfl_sync(0xffffffffu, mi, q + u) * 32);
-#pragma unroll
-      for (int u = 0; u < 8; ++u) acc = fmaf(__shfl_sync(0xffffffffu, mv, q + u), x[u], acc);
-    }
-    for (; q < cnt; ++q)
-      acc = fmaf(__shfl_sync(0xffffffffu, mv, q), __ldg(rows + (size_t)__shfl_sync(0xffffffffu, mi, q) * 32), acc);
-  }
-  return acc;
-}
-
 // ---- sparse shift of a 32-channel node-major signal: out[r,d,:] = sum_p val[p] in[r, idx[p], :] ----------------
-__global__ void __launch_bounds__(256) spmm32_k(const int* __restrict__ ptr, const int* __restrict__ idx,
-                                                const float* __restrict__ val, const float* __restrict__ in,
-                                                float* __restrict__ out, int N, long long RN) {
-  const int lane = threadIdx.x & 31;
-  for (Walk w(RN, N, threadIdx.x >> 5, blockDim.x >> 5); w.ok(); w.next())
-    out[w.task * 32 + lane] = gather_row(idx, val, __ldg(ptr + w.n), __ldg(ptr + w.n + 1), in + w.r * N * 32 + lane, lane);
+// register pipeline (row pointers two tasks ahead, edge list one task ahead), Q-layout LDG.128 gathers
+__global__ void __launch_bounds__(256) spmm32_k(Gather3 op, const float* __restrict__ in, float* __restrict__ out, int N, long long RN) {
+  const int lane = threadIdx.x & 31, g = lane >> 3;
+  const int fo = feat_of_lane(lane);
+  WarpTasks wt(RN, N, threadIdx.x >> 5, blockDim.x >> 5);
+  int a_p0 = 0, a_deg = 0, b_p0 = 0, b_deg = 0, b_mi = 0; float b_mv = 0.f;
+  wt.advance();                                  // this kernel has 3 stages: t1 (row pointers), t2 (edge list), t3 (compute)
+  for (int it = -2; it < wt.niter; ++it) {
+    const int d_p0 = b_p0, d_deg = b_deg, d_mi = b_mi; const float d_mv = b_mv;
+    b_p0 = a_p0; b_deg = a_deg; b_mi = 0; b_mv = 0.f;
+    if (it + 1 >= 0 && it + 1 < wt.niter && lane < min(a_deg, 32)) { b_mi = __ldg(op.idx + a_p0 + lane); b_mv = __ldg(op.val + a_p0 + lane); }
+    a_p0 = 0; a_deg = 0;
+    if (it + 2 < wt.niter) { a_p0 = __ldg(op.ptr + wt.t1.n); a_deg = __ldg(op.ptr + wt.t1.n + 1) - a_p0; }
+    if (it >= 0) {
+      const float4* base = reinterpret_cast<const float4*>(in + wt.sample(wt.t3) * 32) + (lane & 7);
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int pb = 0; pb < d_deg; pb += 32) {
+        int mi = d_mi; float mv = d_mv;
+        const int cnt = min(32, d_deg - pb);
+        if (pb > 0) { mi = 0; mv = 0.f; if (lane < cnt) { mi = __ldg(op.idx + d_p0 + pb + lane); mv = __ldg(op.val + d_p0 + pb + lane); } }
+        int q0 = 0;
+        for (; q0 + 8 <= cnt; q0 += 8) {          // two independent 4-row gathers in flight
+          const float4 x0 = __ldg(base + (size_t)__shfl_sync(0xffffffffu, mi, q0 + g) * 8);
+          const float4 x1 = __ldg(base + (size_t)__shfl_sync(0xffffffffu, mi, q0 + 4 + g) * 8);
+          fma4(acc, __shfl_sync(0xffffffffu, mv, q0 + g), x0);
+          fma4(acc, __shfl_sync(0xffffffffu, mv, q0 + 4 + g), x1);
+        }
+        for (; q0 < cnt; q0 += 4)
+          fma4(acc, __shfl_sync(0xffffffffu, mv, (q0 + g) & 31), __ldg(base + (size_t)__shfl_sync(0xffffffffu, mi, (q0 + g) & 31) * 8));
+      }
+      out[wt.row(wt.t3) * 32 + fo] = rs4(acc, lane);
+    }
+    wt.advance();
+  }
 }
 
 // ---- folded forward weights (one block) -------------------------------------------------------------------------
@@ -140,10 +262,10 @@ __global__ void prep_k(const float* __restrict__ A, const float* __restrict__ Bw
     for (int m = 0; m < 32; ++m) a = fmaf(Wr[f * 32 + m], Bw[m * KF + kg], a);
     prep[PrepLayout::CR + o] = a;
   }
-  for (int o = threadIdx.x; o < KG * 32; o += blockDim.x) {
+  for (int o = threadIdx.x; o < MAXKG * 32; o += blockDim.x) {       // zero padded to MAXKG taps
     const int f = o & 31, kg = o >> 5;
     float a = 0.f;
-    for (int m = 0; m < 32; ++m) a = fmaf(Wa[f * 32 + m], A[m * KG + kg], a);
+    if (kg < KG) for (int m = 0; m < 32; ++m) a = fmaf(Wa[f * 32 + m], A[m * KG + kg], a);
     prep[PrepLayout::CA + o] = a;
   }
   if (threadIdx.x < 32) {
@@ -154,52 +276,76 @@ __global__ void prep_k(const float* __restrict__ A, const float* __restrict__ Bw
   }
 }
 
+// lane kg < KG carries input tap kg = k * G + g of the task: pointer to it for task 0, stride G per task
+__device__ __forceinline__ const float* tap_pointer(const Chain& xs, int lane, int KG, int G) {
+  if (lane >= KG) return nullptr;
+  const int k = lane / G;
+  const float* xp = xs.p[0];
+#pragma unroll
+  for (int m = 1; m < MAXK; ++m) if (k == m) xp = xs.p[m];
+  return xp + (lane - k * G);
+}
+
 // ---- forward, stage 1: both filters folded into the attention mixing; scores ------------------------------------
 // Wu_r = sum_k Cr_k z_k + cr0 (z_{KST-1} gathered on the fly), Wu_a = Ca x-taps + ca0, rc = (a1.Wu_a, a2.Wu_a, a1.Wu_r, a2.Wu_r)
 template <int KST>
-__global__ void __launch_bounds__(128) filter_fwd_k(const int* __restrict__ ptr, const int* __restrict__ idx, const float* __restrict__ val,
-                                                    Chain zc /* z_0 .. z_{KST-2}, [B,N,32] */, Chain xs /* x taps of this step, [B,N,G] */,
-                                                    int Kin, int G, const float* __restrict__ prep,
+__global__ void __launch_bounds__(128) filter_fwd_k(Gather3 gop, Chain zc /* z_0 .. z_{KST-2}, [B,N,32] */,
+                                                    Chain xs /* x taps of this step, [B,N,G] */, int Kin, int G,
+                                                    const float* __restrict__ prep,
                                                     const float* __restrict__ mix_a, const float* __restrict__ mix_r,
                                                     float* __restrict__ wu_a, float* __restrict__ wu_r, float4* __restrict__ rc,
                                                     int N, long long RN) {
-  __shared__ __align__(16) float zs[4][KST][32];
+  constexpr int NS = KST - 1;
+  using Pipe = GatherPipe<NS>;
+  __shared__ __align__(16) float bufs[4][2 * Pipe::ROWS * 32];
+  __shared__ __align__(16) float zl[4][32];
   __shared__ float cas[MAXKG * 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int fo = feat_of_lane(lane);
   const int KG = Kin * G;
-  for (int i = threadIdx.x; i < KG * 32; i += blockDim.x) cas[i] = prep[PrepLayout::CA + i];
-  float cr[KST * 32];
+  for (int i = threadIdx.x; i < MAXKG * 32; i += blockDim.x) cas[i] = prep[PrepLayout::CA + i];
+  float2 cr[KST * 16];                                // cr[k*16 + i] = (Cr[k][2i][lane], Cr[k][2i+1][lane])
 #pragma unroll
-  for (int i = 0; i < KST * 32; ++i) cr[i] = prep[PrepLayout::CR + i * 32 + lane];
+  for (int i = 0; i < KST * 16; ++i) cr[i] = make_float2(prep[PrepLayout::CR + (2 * i) * 32 + lane], prep[PrepLayout::CR + (2 * i + 1) * 32 + lane]);
   const float cr0 = prep[PrepLayout::CR0 + lane], ca0 = prep[PrepLayout::CA0 + lane];
   const float a1a = mix_a[lane], a2a = mix_a[32 + lane], a1r = mix_r[lane], a2r = mix_r[32 + lane];
+  WarpTasks wt(RN, N, warp, blockDim.x >> 5);
+  Pipe pipe;
+  pipe.init(bufs[warp], gop, zc.p[NS - 1], lane);
+#pragma unroll
+  for (int k = 0; k < NS; ++k) pipe.srow[k] = zc.p[k];
+  pipe.aux = tap_pointer(xs, lane, KG, G); pipe.aux_stride = G;
   __syncthreads();
-  for (Walk w(RN, N, warp, blockDim.x >> 5); w.ok(); w.next()) {
-    const long long o = w.task * 32 + lane;
-#pragma unroll
-    for (int k = 0; k < KST - 1; ++k) zs[warp][k][lane] = zc.p[k][o];
-    if (KST > 1)
-      zs[warp][KST - 1][lane] = gather_row(idx, val, __ldg(ptr + w.n), __ldg(ptr + w.n + 1), zc.p[KST > 1 ? KST - 2 : 0] + w.r * N * 32 + lane, lane);
+  for (int it = -3; it < wt.niter; ++it, wt.advance()) {
+    pipe.advance(it, wt);
+    if (it < 0) continue;
+    zl[warp][fo] = pipe.gathered(it, wt);
     __syncwarp();
-    float ar = cr0;
+    const float* rows = pipe.rows(it);
+    float2 ar = make_float2(cr0, 0.f);
 #pragma unroll
-    for (int k = 0; k < KST; ++k)
+    for (int k = 0; k < KST; ++k) {
+      const float* zr = k < NS ? rows + k * 32 : zl[warp];
 #pragma unroll
       for (int g4 = 0; g4 < 8; ++g4) {
-        const float4 v = *reinterpret_cast<const float4*>(&zs[warp][k][g4 * 4]);
-        ar = fmaf(cr[k * 32 + g4 * 4 + 0], v.x, ar); ar = fmaf(cr[k * 32 + g4 * 4 + 1], v.y, ar);
-        ar = fmaf(cr[k * 32 + g4 * 4 + 2], v.z, ar); ar = fmaf(cr[k * 32 + g4 * 4 + 3], v.w, ar);
+        const float4 v = *reinterpret_cast<const float4*>(zr + g4 * 4);
+        fma2(ar, cr[k * 16 + g4 * 2], v.x, v.y);
+        fma2(ar, cr[k * 16 + g4 * 2 + 1], v.z, v.w);
       }
-    __syncwarp();
-    float aa = ca0;
-    for (int k = 0; k < Kin; ++k) {
-      const float* xp = xs.p[k] + w.task * G;
-      for (int g = 0; g < G; ++g) aa = fmaf(cas[(k * G + g) * 32 + lane], __ldg(xp + g), aa);
     }
-    wu_a[o] = aa; wu_r[o] = ar;
-    const float s = wsum4(a1a * aa, a2a * aa, a1r * ar, a2r * ar, lane);   // lanes 0, 16, 8, 24
-    if ((lane & 7) == 0) reinterpret_cast<float*>(rc + w.task)[(lane >> 4) | ((lane >> 2) & 2)] = s;
+    const float arr = ar.x + ar.y;
+    float aa = ca0;
+    for (int kg = 0; kg < KG; kg += 4) {              // taps padded with zero weights / zero values
+#pragma unroll
+      for (int u = 0; u < 4; ++u) aa = fmaf(cas[(kg + u) * 32 + lane], __shfl_sync(0xffffffffu, pipe.d_aux, kg + u), aa);
+    }
+    const size_t o = wt.row(wt.t3) * 32 + lane;
+    wu_a[o] = aa; wu_r[o] = arr;
+    const float s4 = wsum4(a1a * aa, a2a * aa, a1r * arr, a2r * arr, lane);   // lanes 0, 16, 8, 24
+    if ((lane & 7) == 0) reinterpret_cast<float*>(rc + wt.row(wt.t3))[(lane >> 4) | ((lane >> 2) & 2)] = s4;
+    __syncwarp();
   }
+  cp_wait<0>();
 }
 
 // ---- forward, stage 2: per-row softmax statistics of both gates --------------------------------------------------
@@ -219,7 +365,7 @@ __global__ void __launch_bounds__(256) rowstats_k(const int* __restrict__ rptr, 
     float da = 0.f, dr = 0.f;
     for (int p = p0; p < p1; ++p) {
       const float4 o = rcr[__ldg(col + p)];
-      da += expf(leaky(me.y + o.x) - ma); dr += expf(leaky(me.w + o.z) - mr);
+      da += __expf(leaky(me.y + o.x) - ma); dr += __expf(leaky(me.w + o.z) - mr);
     }
     info[2 * t] = make_float4(me.x, me.y, ma, 1.f / da);
     info[2 * t + 1] = make_float4(me.z, me.w, mr, 1.f / dr);
@@ -228,59 +374,114 @@ __global__ void __launch_bounds__(256) rowstats_k(const int* __restrict__ rptr, 
 
 // ---- forward, stage 3: attention aggregation of both gates + relu + tanh update -----------------------------------
 // y_g[j,:] = relu( sum_{i -> j} S'_ij alpha^g_ij Wu_g[i,:] ),  h = tanh(y_a + y_r);  masks = sign bits of the two relus
-__global__ void __launch_bounds__(256) aggregate_k(const int* __restrict__ cptr, const int* __restrict__ crow, const float* __restrict__ cval,
+// (bit l of a mask word belongs to feature FEAT(l)).  4 warps / block, dynamic shared memory: per warp
+// [2 stages][2 gates][32 rows][32] floats (64 KB per block).
+constexpr int AGG_STAGE = 2 * 32 * 32;
+__global__ void __launch_bounds__(128) aggregate_k(const int* __restrict__ cptr, const int* __restrict__ crow, const float* __restrict__ cval,
                                                    const float4* __restrict__ info, const float* __restrict__ wu_a, const float* __restrict__ wu_r,
                                                    float* __restrict__ hn, uint2* __restrict__ masks, int N, long long RN) {
-  const int lane = threadIdx.x & 31;
-  for (Walk w(RN, N, threadIdx.x >> 5, blockDim.x >> 5); w.ok(); w.next()) {
-    const long long rb = w.r * N;
-    const float rja = info[2 * w.task].x, rjr = info[2 * w.task + 1].x;
-    const float* pa = wu_a + rb * 32 + lane;
-    const float* pr = wu_r + rb * 32 + lane;
-    const int q0 = __ldg(cptr + w.n), q1 = __ldg(cptr + w.n + 1);
-    float acc_a = 0.f, acc_r = 0.f;
-    for (int qb = q0; qb < q1; qb += 32) {
-      const int cnt = min(32, q1 - qb);
-      int mi = 0; float ca = 0.f, cr = 0.f;
-      if (lane < cnt) {
-        mi = __ldg(crow + qb + lane);
-        const float v = __ldg(cval + qb + lane);
-        const float4 sa = info[2 * (rb + mi)], sr = info[2 * (rb + mi) + 1];
-        ca = v * (expf(leaky(sa.y + rja) - sa.z) * sa.w);
-        cr = v * (expf(leaky(sr.y + rjr) - sr.z) * sr.w);
-      }
-      int q = 0;
-      for (; q + 4 <= cnt; q += 4) {
-        float xa[4], xr[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const size_t off = (size_t)__shfl_sync(0xffffffffu, mi, q + u) * 32;
-          xa[u] = __ldg(pa + off); xr[u] = __ldg(pr + off);
+  extern __shared__ __align__(16) float dyn[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 3, ch = (lane & 7) * 4, fo = feat_of_lane(lane);
+  float* wbuf = dyn + (size_t)warp * 2 * AGG_STAGE;
+  for (int i = lane; i < 2 * AGG_STAGE; i += 32) wbuf[i] = 0.f;
+  __syncwarp();
+  WarpTasks wt(RN, N, warp, blockDim.x >> 5);
+  int a_p0 = 0, a_deg = 0, b_p0 = 0, b_deg = 0, b_mi = 0, c_p0 = 0, c_deg = 0;
+  float b_v = 0.f, c_v = 0.f, c_rja = 0.f, c_rjr = 0.f;
+  float4 c_sa = make_float4(0.f, 0.f, 0.f, 1.f), c_sr = c_sa;
+  for (int it = -3; it < wt.niter; ++it, wt.advance()) {
+    const int d_p0 = c_p0, d_deg = c_deg;
+    const float d_v = c_v, d_rja = c_rja, d_rjr = c_rjr;
+    const float4 d_sa = c_sa, d_sr = c_sr;
+    {                                             // S2: task it + 1
+      const int j = it + 1;
+      c_p0 = b_p0; c_deg = b_deg; c_v = b_v;
+      if (j >= 0 && j < wt.niter) {
+        const size_t rb = wt.sample(wt.t2);
+        float* dst = wbuf + (j & 1) * AGG_STAGE + lane * 4;
+        const int cnt = min(b_deg, 32);
+        const float* ga = wu_a + rb * 32 + ch;
+        const float* gr = wu_r + rb * 32 + ch;
+        for (int q0 = 0; q0 < cnt; q0 += 4) {
+          const int src = __shfl_sync(0xffffffffu, b_mi, (q0 + g) & 31);
+          if (q0 + g < cnt) {
+            cp_async16(dst + q0 * 32, ga + (size_t)src * 32);
+            cp_async16(dst + (32 + q0) * 32, gr + (size_t)src * 32);
+          }
         }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          acc_a = fmaf(__shfl_sync(0xffffffffu, ca, q + u), xa[u], acc_a);
-          acc_r = fmaf(__shfl_sync(0xffffffffu, cr, q + u), xr[u], acc_r);
-        }
+        if (lane < cnt) { c_sa = info[2 * (rb + b_mi)]; c_sr = info[2 * (rb + b_mi) + 1]; }
+        const size_t task = wt.row(wt.t2);
+        c_rja = info[2 * task].x; c_rjr = info[2 * task + 1].x;
       }
-      for (; q < cnt; ++q) {
-        const size_t off = (size_t)__shfl_sync(0xffffffffu, mi, q) * 32;
-        acc_a = fmaf(__shfl_sync(0xffffffffu, ca, q), __ldg(pa + off), acc_a);
-        acc_r = fmaf(__shfl_sync(0xffffffffu, cr, q), __ldg(pr + off), acc_r);
+      cp_commit();
+    }
+    {                                             // S1: task it + 2
+      const int j = it + 2;
+      b_p0 = a_p0; b_deg = a_deg; b_mi = 0; b_v = 0.f;
+      if (j >= 0 && j < wt.niter && lane < min(a_deg, 32)) { b_mi = __ldg(crow + a_p0 + lane); b_v = __ldg(cval + a_p0 + lane); }
+    }
+    {                                             // S0: task it + 3
+      a_p0 = 0; a_deg = 0;
+      if (it + 3 < wt.niter) { a_p0 = __ldg(cptr + wt.t0.n); a_deg = __ldg(cptr + wt.t0.n + 1) - a_p0; }
+    }
+    if (it < 0) continue;
+    // S3
+    const int cnt = min(d_deg, 32);
+    float ca = 0.f, cr = 0.f;                      // alpha * S' of edge `lane` (0 beyond the edge list)
+    if (lane < cnt) {
+      ca = d_v * (__expf(leaky(d_sa.y + d_rja) - d_sa.z) * d_sa.w);
+      cr = d_v * (__expf(leaky(d_sr.y + d_rjr) - d_sr.z) * d_sr.w);
+    }
+    cp_wait<1>();
+    __syncwarp();
+    const float4* ra = reinterpret_cast<const float4*>(wbuf + (it & 1) * AGG_STAGE) + lane;     // row q0 + g: + q0 * 8
+    const float4* rr = ra + 32 * 8;
+    float4 acc_a = make_float4(0.f, 0.f, 0.f, 0.f), acc_r = acc_a;
+    for (int q0 = 0; q0 < cnt; q0 += 4) {
+      fma4(acc_a, __shfl_sync(0xffffffffu, ca, (q0 + g) & 31), ra[q0 * 8]);
+      fma4(acc_r, __shfl_sync(0xffffffffu, cr, (q0 + g) & 31), rr[q0 * 8]);
+    }
+    if (d_deg > 32) {                              // rare long tail (hub columns): synchronous
+      const size_t rb = wt.sample(wt.t3);
+      const float4* pa = reinterpret_cast<const float4*>(wu_a + rb * 32) + (lane & 7);
+      const float4* pr = reinterpret_cast<const float4*>(wu_r + rb * 32) + (lane & 7);
+      for (int qb = d_p0 + 32; qb < d_p0 + d_deg; qb += 32) {
+        const int c2 = min(32, d_p0 + d_deg - qb);
+        int mi = 0; float xa = 0.f, xr = 0.f;
+        if (lane < c2) {
+          mi = __ldg(crow + qb + lane);
+          const float v = __ldg(cval + qb + lane);
+          const float4 sa = info[2 * (rb + mi)], sr = info[2 * (rb + mi) + 1];
+          xa = v * (__expf(leaky(sa.y + d_rja) - sa.z) * sa.w);
+          xr = v * (__expf(leaky(sr.y + d_rjr) - sr.z) * sr.w);
+        }
+        for (int q0 = 0; q0 < c2; q0 += 4) {
+          const size_t off = (size_t)__shfl_sync(0xffffffffu, mi, (q0 + g) & 31) * 8;
+          fma4(acc_a, __shfl_sync(0xffffffffu, xa, (q0 + g) & 31), __ldg(pa + off));
+          fma4(acc_r, __shfl_sync(0xffffffffu, xr, (q0 + g) & 31), __ldg(pr + off));
+        }
       }
     }
-    const unsigned ba = __ballot_sync(0xffffffffu, acc_a > 0.f), br = __ballot_sync(0xffffffffu, acc_r > 0.f);
-    hn[w.task * 32 + lane] = tanhf(fmaxf(acc_a, 0.f) + fmaxf(acc_r, 0.f));
-    if (lane == 0) masks[w.task] = make_uint2(ba, br);
+    const float ya = rs4(acc_a, lane), yr = rs4(acc_r, lane);          // feature FEAT(lane)
+    const unsigned ba = __ballot_sync(0xffffffffu, ya > 0.f), br = __ballot_sync(0xffffffffu, yr > 0.f);
+    const size_t task = wt.row(wt.t3);
+    hn[task * 32 + fo] = tanh_pos(fmaxf(ya, 0.f) + fmaxf(yr, 0.f));
+    if (lane == 0) masks[task] = make_uint2(ba, br);
+    __syncwarp();
   }
+  cp_wait<0>();
 }
 
-// ---- backward, stage 0: dpre[r,n,f] = (dH[b,t,f,n] + dhrec[r,n,f]) (1 - h^2)   (tile transpose of the reference layout) ----
+// ---- backward, stage 0: g = (dH[b,t,f,n] + dhrec[r,n,f]) (1 - h^2);  dya = g [y_a > 0], dyr = g [y_r > 0] ----------------
+// (tile transpose of the reference layout; the relu masks of the two gates are applied here, once, instead of per edge)
 __global__ void __launch_bounds__(256) dpre_k(const float* __restrict__ dHt /* dH + t*F*N */, long long sample_stride,
                                               const float* __restrict__ dhrec, const float* __restrict__ hn,
-                                              float* __restrict__ dpre, int N, long long R) {
+                                              const uint2* __restrict__ masks, float* __restrict__ dya, float* __restrict__ dyr,
+                                              int N, long long R) {
   __shared__ float tile[32][33];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int bit = lane_of_feat(lane);
   const int tiles_n = (N + 31) / 32;
   const long long tiles = R * tiles_n;
   for (long long tl = blockIdx.x; tl < tiles; tl += gridDim.x) {
@@ -290,98 +491,132 @@ __global__ void __launch_bounds__(256) dpre_k(const float* __restrict__ dHt /* d
     __syncthreads();
     for (int nn = warp; nn < 32; nn += 8)
       if (n0 + nn < N) {
-        const long long o = (r * N + n0 + nn) * 32 + lane;
+        const long long task = r * N + n0 + nn;
+        const long long o = task * 32 + lane;
         const float h = hn[o];
-        float g = tile[lane][nn];
-        if (dhrec) g += dhrec[o];
-        dpre[o] = g * (1.f - h * h);
+        float gq = tile[lane][nn];
+        if (dhrec) gq += dhrec[o];
+        gq *= 1.f - h * h;
+        const uint2 mk = masks[task];
+        dya[o] = ((mk.x >> bit) & 1u) ? gq : 0.f;
+        dyr[o] = ((mk.y >> bit) & 1u) ? gq : 0.f;
       }
     __syncthreads();
   }
 }
 
 // ---- backward, stage 1 (per source row i, both gates): softmax / leaky backward, partial dWu ---------------------------
-// lanes 0-15 hold the edges of the row for the input gate, lanes 16-31 the same edges for the forget gate.
-// Requires row degree of S + I <= 32 (two chunks of 16 edges).
-__global__ void __launch_bounds__(256) bwd_rows_k(const int* __restrict__ rptr, const int* __restrict__ col, const float* __restrict__ val,
-                                                  const float4* __restrict__ info, const uint2* __restrict__ masks,
-                                                  const float* __restrict__ wu_a, const float* __restrict__ wu_r,
-                                                  const float* __restrict__ dpre, const float* __restrict__ mix_a, const float* __restrict__ mix_r,
+// Edge-distributed data: lanes 0-15 hold edges e (and 16+e) of the row for the input gate, lanes 16-31 the same edges
+// for the forget gate.  Row data: Q-layout.  Requires row degree of S + I <= 32.  4 warps / block, dynamic shared
+// memory per warp: [2 stages][dya rows 32 | dyr rows 32 | Wu_a row | Wu_r row][32] floats.
+constexpr int ROWS_STAGE = (2 * 32 + 2) * 32;
+__global__ void __launch_bounds__(128) bwd_rows_k(const int* __restrict__ rptr, const int* __restrict__ col, const float* __restrict__ val,
+                                                  const float4* __restrict__ info, const float* __restrict__ wu_a, const float* __restrict__ wu_r,
+                                                  const float* __restrict__ dya, const float* __restrict__ dyr,
+                                                  const float* __restrict__ mix_a, const float* __restrict__ mix_r,
                                                   float* __restrict__ pa, float* __restrict__ pr, float* __restrict__ dr /* [R*N][2], zeroed */,
                                                   float* __restrict__ acc, int N, long long RN) {
-  __shared__ float red[8][64];
+  extern __shared__ __align__(16) float dyn[];
+  __shared__ float red[4][64];
+  __shared__ float sdot[4][2][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int half = lane >> 4, e = lane & 15;
-  const float a2a = mix_a[32 + lane], a2r = mix_r[32 + lane];
+  const int g = lane >> 3, ch = (lane & 7) * 4, fo = feat_of_lane(lane);
+  float* wbuf = dyn + (size_t)warp * 2 * ROWS_STAGE;
+  for (int i = lane; i < 2 * ROWS_STAGE; i += 32) wbuf[i] = 0.f;
+  __syncwarp();
+  const float a2a = mix_a[32 + fo], a2r = mix_r[32 + fo];
   float m2a = 0.f, m2r = 0.f;
-  for (Walk w(RN, N, warp, blockDim.x >> 5); w.ok(); w.next()) {
-    const long long rb = w.r * N;
-    const long long o = w.task * 32 + lane;
-    const float wua = wu_a[o], wur = wu_r[o];
-    const float4 mine = info[2 * w.task + half];
-    const int p0 = __ldg(rptr + w.n), deg = __ldg(rptr + w.n + 1) - p0;
-    const float* dp = dpre + rb * 32 + lane;
-    float al[2], dal[2], slope[2]; int jj[2]; bool valid[2];
-    float parta = 0.f, partr = 0.f;
+  WarpTasks wt(RN, N, warp, blockDim.x >> 5);
+  int a_p0 = 0, a_deg = 0, b_deg = 0, b_j0 = 0, b_j1 = 0, c_deg = 0, c_j0 = 0, c_j1 = 0;
+  float b_v0 = 0.f, b_v1 = 0.f, c_v0 = 0.f, c_v1 = 0.f, c_rj0 = 0.f, c_rj1 = 0.f;
+  float4 c_mine = make_float4(0.f, 0.f, 0.f, 1.f);
+  for (int it = -3; it < wt.niter; ++it, wt.advance()) {
+    const int d_deg = c_deg, d_j0 = c_j0, d_j1 = c_j1;
+    const float d_v0 = c_v0, d_v1 = c_v1, d_rj0 = c_rj0, d_rj1 = c_rj1;
+    const float4 mine = c_mine;
+    {                                             // S2: task it + 1
+      const int j = it + 1;
+      c_deg = b_deg; c_j0 = b_j0; c_j1 = b_j1; c_v0 = b_v0; c_v1 = b_v1;
+      c_rj0 = c_rj1 = 0.f;
+      if (j >= 0 && j < wt.niter) {
+        const size_t rb = wt.sample(wt.t2), task = wt.row(wt.t2);
+        float* dst = wbuf + (j & 1) * ROWS_STAGE + lane * 4;
+        const float* ga = dya + rb * 32 + ch;
+        const float* gr = dyr + rb * 32 + ch;
+        for (int q0 = 0; q0 < b_deg; q0 += 4) {     // rows q0 + g; q0 < 16: chunk 0, else chunk 1
+          const int src = __shfl_sync(0xffffffffu, q0 < 16 ? b_j0 : b_j1, (q0 + g) & 15);
+          if (q0 + g < b_deg) {
+            cp_async16(dst + q0 * 32, ga + (size_t)src * 32);
+            cp_async16(dst + (32 + q0) * 32, gr + (size_t)src * 32);
+          }
+        }
+        if (g < 2) cp_async16(dst + 64 * 32, (g == 0 ? wu_a : wu_r) + task * 32 + ch);     // rows 64 (Wu_a), 65 (Wu_r)
+        if (e < b_deg) c_rj0 = info[2 * (rb + b_j0) + half].x;
+        if (16 + e < b_deg) c_rj1 = info[2 * (rb + b_j1) + half].x;
+        c_mine = info[2 * task + half];
+      }
+      cp_commit();
+    }
+    {                                             // S1: task it + 2
+      const int j = it + 2;
+      b_deg = a_deg; b_j0 = b_j1 = 0; b_v0 = b_v1 = 0.f;
+      if (j >= 0 && j < wt.niter) {
+        if (e < a_deg) { b_j0 = __ldg(col + a_p0 + e); b_v0 = __ldg(val + a_p0 + e); }
+        if (16 + e < a_deg) { b_j1 = __ldg(col + a_p0 + 16 + e); b_v1 = __ldg(val + a_p0 + 16 + e); }
+      }
+    }
+    {                                             // S0: task it + 3
+      a_p0 = 0; a_deg = 0;
+      if (it + 3 < wt.niter) { a_p0 = __ldg(rptr + wt.t0.n); a_deg = __ldg(rptr + wt.t0.n + 1) - a_p0; }
+    }
+    if (it < 0) continue;
+    // S3 -- edge coefficients in the (half, e) layout
+    float al[2], slope[2], coef[2];
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
-      const int cnt = min(16, max(0, deg - c * 16));          // warp-uniform
-      valid[c] = e < cnt;
-      int j = 0; float v = 0.f; unsigned mk = 0u; float coef = 0.f;
-      al[c] = 0.f; slope[c] = 0.f; dal[c] = 0.f;
-      if (valid[c]) {
-        j = __ldg(col + p0 + c * 16 + e); v = __ldg(val + p0 + c * 16 + e);
-        const float rj = info[2 * (rb + j) + half].x;
-        const uint2 m2 = masks[rb + j];
-        mk = half ? m2.y : m2.x;
-        const float s = mine.y + rj;
-        al[c] = expf(leaky(s) - mine.z) * mine.w;
-        slope[c] = s > 0.f ? 1.f : 0.2f;
-        coef = v * al[c];
-      }
-      jj[c] = j;
-      if (cnt == 0) continue;
-      float dot;
-      if (cnt > 2) {
-        float prod[32];
-#pragma unroll
-        for (int q = 0; q < 16; ++q) {
-          if (q < cnt) {
-            const int jq = __shfl_sync(0xffffffffu, j, q);
-            const unsigned mka = __shfl_sync(0xffffffffu, mk, q), mkr = __shfl_sync(0xffffffffu, mk, 16 + q);
-            const float ca = __shfl_sync(0xffffffffu, coef, q), cr = __shfl_sync(0xffffffffu, coef, 16 + q);
-            const float d = __ldg(dp + (size_t)jq * 32);
-            const float dya = ((mka >> lane) & 1u) ? d : 0.f, dyr = ((mkr >> lane) & 1u) ? d : 0.f;
-            prod[q] = dya * wua; prod[16 + q] = dyr * wur;
-            parta = fmaf(ca, dya, parta); partr = fmaf(cr, dyr, partr);
-          } else { prod[q] = 0.f; prod[16 + q] = 0.f; }
-        }
-        dot = tree32(prod, lane);                          // lane (half, e): <dy_g[j_e], Wu_g[i]>
-      } else {
-        dot = 0.f;
-        for (int q = 0; q < cnt; ++q) {
-          const int jq = __shfl_sync(0xffffffffu, j, q);
-          const unsigned mka = __shfl_sync(0xffffffffu, mk, q), mkr = __shfl_sync(0xffffffffu, mk, 16 + q);
-          const float ca = __shfl_sync(0xffffffffu, coef, q), cr = __shfl_sync(0xffffffffu, coef, 16 + q);
-          const float d = __ldg(dp + (size_t)jq * 32);
-          const float dya = ((mka >> lane) & 1u) ? d : 0.f, dyr = ((mkr >> lane) & 1u) ? d : 0.f;
-          parta = fmaf(ca, dya, parta); partr = fmaf(cr, dyr, partr);
-          const float da = wsum(dya * wua), drr = wsum(dyr * wur);
-          if (e == q) dot = half ? drr : da;
-        }
-      }
-      dal[c] = v * dot;                                      // d alpha_ij = S'_ij <dy_j, Wu_i>
+      const bool valid = c * 16 + e < d_deg;
+      const float sc = mine.y + (c ? d_rj1 : d_rj0);
+      al[c] = valid ? __expf(leaky(sc) - mine.z) * mine.w : 0.f;
+      slope[c] = valid ? (sc > 0.f ? 1.f : 0.2f) : 0.f;
+      coef[c] = (c ? d_v1 : d_v0) * al[c];
     }
-    const float S = hsum(fmaf(al[0], dal[0], al[1] * dal[1]));
-    const float ds0 = al[0] * (dal[0] - S) * slope[0], ds1 = al[1] * (dal[1] - S) * slope[1];
+    cp_wait<1>();
+    __syncwarp();
+    const float4* st = reinterpret_cast<const float4*>(wbuf + (it & 1) * ROWS_STAGE);
+    const float4 wua4 = st[64 * 8 + (lane & 7)], wur4 = st[65 * 8 + (lane & 7)];
+    const float4* ra = st + lane;                  // row q0 + g, chunk c: + q0 * 8
+    const float4* rr = ra + 32 * 8;
+    float4 parta = make_float4(0.f, 0.f, 0.f, 0.f), partr = parta;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const int cnt = min(16, max(0, d_deg - c * 16));          // warp-uniform
+      for (int q0 = 0; q0 < cnt; q0 += 4) {
+        const float4 xa = ra[(c * 16 + q0) * 8], xr = rr[(c * 16 + q0) * 8];
+        fma4(parta, __shfl_sync(0xffffffffu, coef[c], (q0 + g) & 15), xa);            // coef = 0 beyond the edge list
+        fma4(partr, __shfl_sync(0xffffffffu, coef[c], 16 + ((q0 + g) & 15)), xr);
+        const float da = osum(dot4(xa, wua4)), dr_ = osum(dot4(xr, wur4));            // <dy_g[j], Wu_g[i]> on all 8 lanes of the group
+        if ((lane & 7) == 0) { sdot[warp][0][c * 16 + q0 + g] = da; sdot[warp][1][c * 16 + q0 + g] = dr_; }
+      }
+    }
+    __syncwarp();
+    const float dal0 = d_v0 * sdot[warp][half][e], dal1 = d_v1 * sdot[warp][half][16 + e];   // d alpha_ij = S'_ij <dy_j, Wu_i>
+    const float S = hsum((e < d_deg ? al[0] * dal0 : 0.f) + (16 + e < d_deg ? al[1] * dal1 : 0.f));
+    const float ds0 = e < d_deg ? al[0] * (dal0 - S) * slope[0] : 0.f;
+    const float ds1 = 16 + e < d_deg ? al[1] * (dal1 - S) * slope[1] : 0.f;
     const float dc = hsum(ds0 + ds1);                        // d c_i of this half's gate
-    if (valid[0]) atomicAdd(dr + 2 * (rb + jj[0]) + half, ds0);
-    if (valid[1]) atomicAdd(dr + 2 * (rb + jj[1]) + half, ds1);
+    const size_t rb = wt.sample(wt.t3);
+    if (e < d_deg) atomicAdd(dr + 2 * (rb + d_j0) + half, ds0);
+    if (16 + e < d_deg) atomicAdd(dr + 2 * (rb + d_j1) + half, ds1);
     const float dca = __shfl_sync(0xffffffffu, dc, 0), dcr = __shfl_sync(0xffffffffu, dc, 16);
-    pa[o] = fmaf(a2a, dca, parta); pr[o] = fmaf(a2r, dcr, partr);
-    m2a = fmaf(dca, wua, m2a); m2r = fmaf(dcr, wur, m2r);
+    const size_t o = wt.row(wt.t3) * 32 + fo;
+    const float* wrow = reinterpret_cast<const float*>(st + 64 * 8);
+    pa[o] = fmaf(a2a, dca, rs4(parta, lane)); pr[o] = fmaf(a2r, dcr, rs4(partr, lane));
+    m2a = fmaf(dca, wrow[fo], m2a); m2r = fmaf(dcr, wrow[32 + fo], m2r);
+    __syncwarp();
   }
-  red[warp][lane] = m2a; red[warp][32 + lane] = m2r;
+  cp_wait<0>();
+  red[warp][fo] = m2a; red[warp][32 + fo] = m2r;
   __syncthreads();
   if (threadIdx.x < 64) {
     float s = 0.f;
@@ -392,65 +627,90 @@ __global__ void __launch_bounds__(256) bwd_rows_k(const int* __restrict__ rptr, 
 
 // ---- backward, stage 2 (per node): finish dWu, accumulate the outer products, d = W_r^T dWu_r ----------------------------
 template <int KST>
-__global__ void __launch_bounds__(128) bwd_node_k(const int* __restrict__ ptr, const int* __restrict__ idx, const float* __restrict__ val,
-                                                  Chain zc, Chain xs, int Kin, int G,
+__global__ void __launch_bounds__(128) bwd_node_k(Gather3 gop, Chain zc, Chain xs, int Kin, int G,
                                                   const float* __restrict__ pa, const float* __restrict__ pr, const float2* __restrict__ dr,
                                                   const float* __restrict__ wu_a, const float* __restrict__ wu_r,
                                                   const float* __restrict__ mix_a, const float* __restrict__ mix_r, const float* __restrict__ Wr,
                                                   float* __restrict__ dout, float* __restrict__ acc, int N, long long RN) {
-  __shared__ __align__(16) float zs[4][KST][32];
+  constexpr int NZ = KST - 1;                  // streamed taps z_0 .. z_{KST-2}
+  constexpr int NS = NZ + 4;                   // + pa, pr, Wu_a, Wu_r rows of the node
+  using Pipe = GatherPipe<NS>;
+  static_assert(4 * 2 * Pipe::ROWS * 32 >= KST * 32 * 32, "stage buffers double as the block reduction scratch");
+  __shared__ __align__(16) float bufs[4][2 * Pipe::ROWS * 32];
+  __shared__ __align__(16) float zl[4][32];
   __shared__ __align__(16) float dws[4][32];
-  __shared__ float wrs[32 * 32];
-  __shared__ float red[KST * 32 * 32];
+  __shared__ __align__(8) float2 wrs[16 * 32];     // wrs[i*32 + g] = (Wr[2i][g], Wr[2i+1][g])
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int fo = feat_of_lane(lane);
   const int KG = Kin * G;
-  for (int i = threadIdx.x; i < 1024; i += blockDim.x) wrs[i] = Wr[i];
-  for (int i = threadIdx.x; i < KST * 1024; i += blockDim.x) red[i] = 0.f;
+  for (int i = threadIdx.x; i < 512; i += blockDim.x) wrs[i] = make_float2(Wr[(2 * (i >> 5)) * 32 + (i & 31)], Wr[(2 * (i >> 5) + 1) * 32 + (i & 31)]);
   const float a1a = mix_a[lane], a1r = mix_r[lane];
-  float M[KST * 32];
+  float2 M[KST * 16];                          // M[k*16 + i] = (M_k[f=lane][2i], M_k[f=lane][2i+1])
 #pragma unroll
-  for (int i = 0; i < KST * 32; ++i) M[i] = 0.f;
+  for (int i = 0; i < KST * 16; ++i) M[i] = make_float2(0.f, 0.f);
   float Ma[MAXKG];
 #pragma unroll
   for (int i = 0; i < MAXKG; ++i) Ma[i] = 0.f;
   float suma = 0.f, sumr = 0.f, m1a = 0.f, m1r = 0.f;
-  __syncthreads();
-  for (Walk w(RN, N, warp, blockDim.x >> 5); w.ok(); w.next()) {
-    const long long o = w.task * 32 + lane;
-    const float2 drn = dr[w.task];
-    const float dwa = fmaf(a1a, drn.x, pa[o]), dwr = fmaf(a1r, drn.y, pr[o]);
-    m1a = fmaf(drn.x, wu_a[o], m1a); m1r = fmaf(drn.y, wu_r[o], m1r);
-    suma += dwa; sumr += dwr;
+  WarpTasks wt(RN, N, warp, blockDim.x >> 5);
+  Pipe pipe;
+  pipe.init(bufs[warp], gop, zc.p[NZ - 1], lane);
 #pragma unroll
-    for (int k = 0; k < KST - 1; ++k) zs[warp][k][lane] = zc.p[k][o];
-    if (KST > 1)
-      zs[warp][KST - 1][lane] = gather_row(idx, val, __ldg(ptr + w.n), __ldg(ptr + w.n + 1), zc.p[KST > 1 ? KST - 2 : 0] + w.r * N * 32 + lane, lane);
+  for (int k = 0; k < NZ; ++k) pipe.srow[k] = zc.p[k];
+  pipe.srow[NZ] = pa; pipe.srow[NZ + 1] = pr; pipe.srow[NZ + 2] = wu_a; pipe.srow[NZ + 3] = wu_r;
+  pipe.aux = tap_pointer(xs, lane, KG, G); pipe.aux_stride = G;      // lanes 0..KG-1: x taps; lanes 16 / 17: (dr_a, dr_r)
+  if (lane == 16 || lane == 17) { pipe.aux = reinterpret_cast<const float*>(dr) + (lane - 16); pipe.aux_stride = 2; }
+  __syncthreads();
+  for (int it = -3; it < wt.niter; ++it, wt.advance()) {
+    pipe.advance(it, wt);
+    if (it < 0) continue;
+    zl[warp][fo] = pipe.gathered(it, wt);
+    const float* rows = pipe.rows(it);
+    const float drx = __shfl_sync(0xffffffffu, pipe.d_aux, 16), dry = __shfl_sync(0xffffffffu, pipe.d_aux, 17);
+    const float dwa = fmaf(a1a, drx, rows[NZ * 32 + lane]), dwr = fmaf(a1r, dry, rows[(NZ + 1) * 32 + lane]);
+    m1a = fmaf(drx, rows[(NZ + 2) * 32 + lane], m1a); m1r = fmaf(dry, rows[(NZ + 3) * 32 + lane], m1r);
+    suma += dwa; sumr += dwr;
     dws[warp][lane] = dwr;
     __syncwarp();
+    const float2 dwr2 = make_float2(dwr, dwr);
 #pragma unroll
-    for (int k = 0; k < KST; ++k)
+    for (int k = 0; k < KST; ++k) {
+      const float* zr = k < NZ ? rows + k * 32 : zl[warp];
 #pragma unroll
       for (int g4 = 0; g4 < 8; ++g4) {
-        const float4 v = *reinterpret_cast<const float4*>(&zs[warp][k][g4 * 4]);
-        M[k * 32 + g4 * 4 + 0] = fmaf(dwr, v.x, M[k * 32 + g4 * 4 + 0]); M[k * 32 + g4 * 4 + 1] = fmaf(dwr, v.y, M[k * 32 + g4 * 4 + 1]);
-        M[k * 32 + g4 * 4 + 2] = fmaf(dwr, v.z, M[k * 32 + g4 * 4 + 2]); M[k * 32 + g4 * 4 + 3] = fmaf(dwr, v.w, M[k * 32 + g4 * 4 + 3]);
+        const float4 v = *reinterpret_cast<const float4*>(zr + g4 * 4);
+        M[k * 16 + g4 * 2] = __ffma2_rn(dwr2, make_float2(v.x, v.y), M[k * 16 + g4 * 2]);
+        M[k * 16 + g4 * 2 + 1] = __ffma2_rn(dwr2, make_float2(v.z, v.w), M[k * 16 + g4 * 2 + 1]);
       }
-    float d = 0.f;
+    }
+    float2 d2 = make_float2(0.f, 0.f);
 #pragma unroll
     for (int f4 = 0; f4 < 8; ++f4) {
       const float4 v = *reinterpret_cast<const float4*>(&dws[warp][f4 * 4]);
-      d = fmaf(wrs[(f4 * 4 + 0) * 32 + lane], v.x, d); d = fmaf(wrs[(f4 * 4 + 1) * 32 + lane], v.y, d);
-      d = fmaf(wrs[(f4 * 4 + 2) * 32 + lane], v.z, d); d = fmaf(wrs[(f4 * 4 + 3) * 32 + lane], v.w, d);
+      fma2(d2, wrs[(f4 * 2) * 32 + lane], v.x, v.y);
+      fma2(d2, wrs[(f4 * 2 + 1) * 32 + lane], v.z, v.w);
     }
-    dout[o] = d;
+    dout[wt.row(wt.t3) * 32 + lane] = d2.x + d2.y;
+    const float tapv = lane < KG ? pipe.d_aux : 0.f;
+#pragma unroll
+    for (int kg = 0; kg < MAXKG; kg += 4)
+      if (kg < KG) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) Ma[kg + u] = fmaf(dwa, __shfl_sync(0xffffffffu, tapv, kg + u), Ma[kg + u]);
+      }
     __syncwarp();
-#pragma unroll
-    for (int kg = 0; kg < MAXKG; ++kg)
-      if (kg < KG) Ma[kg] = fmaf(dwa, __ldg(xs.p[kg / G] + w.task * G + (kg % G)), Ma[kg]);
   }
-  // block reduction (shared atomics), then one global atomic per output per block
+  cp_wait<0>();
+  // block reduction in the (now idle) stage buffers, then one global atomic per output per block
+  __syncthreads();
+  float* red = &bufs[0][0];
+  for (int i = threadIdx.x; i < KST * 1024; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
 #pragma unroll
-  for (int i = 0; i < KST * 32; ++i) atomicAdd(&red[i * 32 + lane], M[i]);
+  for (int i = 0; i < KST * 16; ++i) {           // M[k*16+i] covers g = 2i, 2i+1 of tap k: acc index ((k*32+g)*32 + f)
+    atomicAdd(&red[(2 * i) * 32 + lane], M[i].x);
+    atomicAdd(&red[(2 * i + 1) * 32 + lane], M[i].y);
+  }
   __syncthreads();
   for (int i = threadIdx.x; i < KST * 1024; i += blockDim.x) atomicAdd(acc + AccLayout::M + i, red[i]);
 #pragma unroll
@@ -462,35 +722,46 @@ __global__ void __launch_bounds__(128) bwd_node_k(const int* __restrict__ ptr, c
 
 // ---- backward, stage 3: dh_{t-1}[n,g] = sum_k sum_f B[f,k,g] w_k[n,f],  w_0 = d, w_k = w_{k-1} S^T (last one gathered here) ----
 template <int KST>
-__global__ void __launch_bounds__(128) dh_k(const int* __restrict__ ptr, const int* __restrict__ idx, const float* __restrict__ val,
-                                            Chain wc /* w_0 .. w_{KST-2} */, const float* __restrict__ Bw, float* __restrict__ dh,
-                                            int N, long long RN) {
-  __shared__ __align__(16) float zs[4][KST][32];
+__global__ void __launch_bounds__(128) dh_k(Gather3 gop, Chain wc /* w_0 .. w_{KST-2} */, const float* __restrict__ Bw,
+                                            float* __restrict__ dh, int N, long long RN) {
+  constexpr int NS = KST - 1;
+  using Pipe = GatherPipe<NS>;
+  __shared__ __align__(16) float bufs[4][2 * Pipe::ROWS * 32];
+  __shared__ __align__(16) float zl[4][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float bt[KST * 32];
+  const int fo = feat_of_lane(lane);
+  float2 bt[KST * 16];                           // bt[k*16 + i] = (B[2i, k, lane], B[2i+1, k, lane])
 #pragma unroll
   for (int k = 0; k < KST; ++k)
 #pragma unroll
-    for (int f = 0; f < 32; ++f) bt[k * 32 + f] = Bw[f * (KST * 32) + k * 32 + lane];
-  for (Walk w(RN, N, warp, blockDim.x >> 5); w.ok(); w.next()) {
-    const long long o = w.task * 32 + lane;
+    for (int i = 0; i < 16; ++i)
+      bt[k * 16 + i] = make_float2(Bw[(2 * i) * (KST * 32) + k * 32 + lane], Bw[(2 * i + 1) * (KST * 32) + k * 32 + lane]);
+  WarpTasks wt(RN, N, warp, blockDim.x >> 5);
+  Pipe pipe;
+  pipe.init(bufs[warp], gop, wc.p[NS - 1], lane);
 #pragma unroll
-    for (int k = 0; k < KST - 1; ++k) zs[warp][k][lane] = wc.p[k][o];
-    if (KST > 1)
-      zs[warp][KST - 1][lane] = gather_row(idx, val, __ldg(ptr + w.n), __ldg(ptr + w.n + 1), wc.p[KST > 1 ? KST - 2 : 0] + w.r * N * 32 + lane, lane);
+  for (int k = 0; k < NS; ++k) pipe.srow[k] = wc.p[k];
+  for (int it = -3; it < wt.niter; ++it, wt.advance()) {
+    pipe.advance(it, wt);
+    if (it < 0) continue;
+    zl[warp][fo] = pipe.gathered(it, wt);
     __syncwarp();
-    float a = 0.f;
+    const float* rows = pipe.rows(it);
+    float2 a = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int k = 0; k < KST; ++k)
+    for (int k = 0; k < KST; ++k) {
+      const float* zr = k < NS ? rows + k * 32 : zl[warp];
 #pragma unroll
       for (int f4 = 0; f4 < 8; ++f4) {
-        const float4 v = *reinterpret_cast<const float4*>(&zs[warp][k][f4 * 4]);
-        a = fmaf(bt[k * 32 + f4 * 4 + 0], v.x, a); a = fmaf(bt[k * 32 + f4 * 4 + 1], v.y, a);
-        a = fmaf(bt[k * 32 + f4 * 4 + 2], v.z, a); a = fmaf(bt[k * 32 + f4 * 4 + 3], v.w, a);
+        const float4 v = *reinterpret_cast<const float4*>(zr + f4 * 4);
+        fma2(a, bt[k * 16 + f4 * 2], v.x, v.y);
+        fma2(a, bt[k * 16 + f4 * 2 + 1], v.z, v.w);
       }
-    dh[o] = a;
+    }
+    dh[wt.row(wt.t3) * 32 + lane] = a.x + a.y;
     __syncwarp();
   }
+  cp_wait<0>();
 }
 
 // ---- backward, last: turn the accumulated reductions into parameter gradients (one block; grads are += ) ---------------
