@@ -322,18 +322,18 @@ __global__ void __launch_bounds__(128) filter_fwd_k(Gather3 gop, Chain zc /* z_0
     zl[warp][fo] = pipe.gathered(it, wt);
     __syncwarp();
     const float* rows = pipe.rows(it);
-    float2 ar = make_float2(cr0, 0.f);
+    float2 ar[4] = {make_float2(cr0, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};   // 4 independent chains
 #pragma unroll
     for (int k = 0; k < KST; ++k) {
       const float* zr = k < NS ? rows + k * 32 : zl[warp];
 #pragma unroll
       for (int g4 = 0; g4 < 8; ++g4) {
         const float4 v = *reinterpret_cast<const float4*>(zr + g4 * 4);
-        fma2(ar, cr[k * 16 + g4 * 2], v.x, v.y);
-        fma2(ar, cr[k * 16 + g4 * 2 + 1], v.z, v.w);
+        fma2(ar[(2 * g4) & 3], cr[k * 16 + g4 * 2], v.x, v.y);
+        fma2(ar[(2 * g4 + 1) & 3], cr[k * 16 + g4 * 2 + 1], v.z, v.w);
       }
     }
-    const float arr = ar.x + ar.y;
+    const float arr = ((ar[0].x + ar[0].y) + (ar[1].x + ar[1].y)) + ((ar[2].x + ar[2].y) + (ar[3].x + ar[3].y));
     float aa = ca0;
     for (int kg = 0; kg < KG; kg += 4) {              // taps padded with zero weights / zero values
 #pragma unroll
@@ -591,12 +591,23 @@ __global__ void __launch_bounds__(128) bwd_rows_k(const int* __restrict__ rptr, 
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
       const int cnt = min(16, max(0, d_deg - c * 16));          // warp-uniform
-      for (int q0 = 0; q0 < cnt; q0 += 4) {
+      for (int q0 = 0; q0 < cnt; q0 += 8) {         // rows q0 + g and q0 + 4 + g (stale rows beyond cnt: coef = 0, dots unused)
         const float4 xa = ra[(c * 16 + q0) * 8], xr = rr[(c * 16 + q0) * 8];
+        const float4 ya = ra[(c * 16 + q0 + 4) * 8], yr = rr[(c * 16 + q0 + 4) * 8];
         fma4(parta, __shfl_sync(0xffffffffu, coef[c], (q0 + g) & 15), xa);            // coef = 0 beyond the edge list
         fma4(partr, __shfl_sync(0xffffffffu, coef[c], 16 + ((q0 + g) & 15)), xr);
-        const float da = osum(dot4(xa, wua4)), dr_ = osum(dot4(xr, wur4));            // <dy_g[j], Wu_g[i]> on all 8 lanes of the group
-        if ((lane & 7) == 0) { sdot[warp][0][c * 16 + q0 + g] = da; sdot[warp][1][c * 16 + q0 + g] = dr_; }
+        fma4(parta, __shfl_sync(0xffffffffu, coef[c], (q0 + 4 + g) & 15), ya);
+        fma4(partr, __shfl_sync(0xffffffffu, coef[c], 16 + ((q0 + 4 + g) & 15)), yr);
+        float d0 = dot4(xa, wua4), d1 = dot4(xr, wur4), d2 = dot4(ya, wua4), d3 = dot4(yr, wur4);   // <dy_g[j], Wu_g[i]>
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {             // four independent 8-lane reductions
+          d0 += __shfl_xor_sync(0xffffffffu, d0, o); d1 += __shfl_xor_sync(0xffffffffu, d1, o);
+          d2 += __shfl_xor_sync(0xffffffffu, d2, o); d3 += __shfl_xor_sync(0xffffffffu, d3, o);
+        }
+        if ((lane & 7) == 0) {
+          sdot[warp][0][c * 16 + q0 + g] = d0; sdot[warp][1][c * 16 + q0 + g] = d1;
+          if (q0 + 4 < 16) { sdot[warp][0][c * 16 + q0 + 4 + g] = d2; sdot[warp][1][c * 16 + q0 + 4 + g] = d3; }
+        }
       }
     }
     __syncwarp();
@@ -627,7 +638,7 @@ __global__ void __launch_bounds__(128) bwd_rows_k(const int* __restrict__ rptr, 
 
 // ---- backward, stage 2 (per node): finish dWu, accumulate the outer products, d = W_r^T dWu_r ----------------------------
 template <int KST>
-__global__ void __launch_bounds__(128) bwd_node_k(Gather3 gop, Chain zc, Chain xs, int Kin, int G,
+__global__ void __launch_bounds__(128, 3) bwd_node_k(Gather3 gop, Chain zc, Chain xs, int Kin, int G,
                                                   const float* __restrict__ pa, const float* __restrict__ pr, const float2* __restrict__ dr,
                                                   const float* __restrict__ wu_a, const float* __restrict__ wu_r,
                                                   const float* __restrict__ mix_a, const float* __restrict__ mix_r, const float* __restrict__ Wr,
@@ -683,14 +694,14 @@ __global__ void __launch_bounds__(128) bwd_node_k(Gather3 gop, Chain zc, Chain x
         M[k * 16 + g4 * 2 + 1] = __ffma2_rn(dwr2, make_float2(v.z, v.w), M[k * 16 + g4 * 2 + 1]);
       }
     }
-    float2 d2 = make_float2(0.f, 0.f);
+    float2 d2[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
 #pragma unroll
     for (int f4 = 0; f4 < 8; ++f4) {
       const float4 v = *reinterpret_cast<const float4*>(&dws[warp][f4 * 4]);
-      fma2(d2, wrs[(f4 * 2) * 32 + lane], v.x, v.y);
-      fma2(d2, wrs[(f4 * 2 + 1) * 32 + lane], v.z, v.w);
+      fma2(d2[(2 * f4) & 3], wrs[(f4 * 2) * 32 + lane], v.x, v.y);
+      fma2(d2[(2 * f4 + 1) & 3], wrs[(f4 * 2 + 1) * 32 + lane], v.z, v.w);
     }
-    dout[wt.row(wt.t3) * 32 + lane] = d2.x + d2.y;
+    dout[wt.row(wt.t3) * 32 + lane] = ((d2[0].x + d2[0].y) + (d2[1].x + d2[1].y)) + ((d2[2].x + d2[2].y) + (d2[3].x + d2[3].y));
     const float tapv = lane < KG ? pipe.d_aux : 0.f;
 #pragma unroll
     for (int kg = 0; kg < MAXKG; kg += 4)
@@ -747,18 +758,18 @@ __global__ void __launch_bounds__(128) dh_k(Gather3 gop, Chain wc /* w_0 .. w_{K
     zl[warp][fo] = pipe.gathered(it, wt);
     __syncwarp();
     const float* rows = pipe.rows(it);
-    float2 a = make_float2(0.f, 0.f);
+    float2 a[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};     // 4 independent chains
 #pragma unroll
     for (int k = 0; k < KST; ++k) {
       const float* zr = k < NS ? rows + k * 32 : zl[warp];
 #pragma unroll
       for (int f4 = 0; f4 < 8; ++f4) {
         const float4 v = *reinterpret_cast<const float4*>(zr + f4 * 4);
-        fma2(a, bt[k * 16 + f4 * 2], v.x, v.y);
-        fma2(a, bt[k * 16 + f4 * 2 + 1], v.z, v.w);
+        fma2(a[(2 * f4) & 3], bt[k * 16 + f4 * 2], v.x, v.y);
+        fma2(a[(2 * f4 + 1) & 3], bt[k * 16 + f4 * 2 + 1], v.z, v.w);
       }
     }
-    dh[wt.row(wt.t3) * 32 + lane] = a.x + a.y;
+    dh[wt.row(wt.t3) * 32 + lane] = ((a[0].x + a[0].y) + (a[1].x + a[1].y)) + ((a[2].x + a[2].y) + (a[3].x + a[3].y));
     __syncwarp();
   }
   cp_wait<0>();
