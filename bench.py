@@ -59,7 +59,7 @@ def ncu_traffic(files, kernel_substr):
 # ------------------------------------------------------------------------------------------------------
 # CPU arm: the reference algorithm (oracle port, fp64 as the reference scripts run it) on a bounded sample
 # ------------------------------------------------------------------------------------------------------
-def cpu_sample(cfg, Bs, Ts, repeats, warm=1):
+def cpu_sample(cfg, Bs, Ts, repeats, warm=1, S=None, tg=True, sg=None):
     """Time forward+backward of the time-gated cell on the host CPUs, fp64 (as the reference scripts run it).
 
     kind 'reference': the UNMODIFIED reference `Utils.graphML.GGCRNNCell` from the git-ignored copy under baseline/_ref
@@ -69,7 +69,8 @@ def cpu_sample(cfg, Bs, Ts, repeats, warm=1):
     import gated_gcrnns_b200 as gg
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    S = gg.graphs.dense_random(cfg['N'], cfg['density'], seed=0).double()
+    if S is None:
+        S = gg.graphs.dense_random(cfg['N'], cfg['density'], seed=0).double()
     X = torch.randn(Bs, Ts, cfg['G'], cfg['N'], dtype=torch.float64)
     h0 = torch.zeros(Bs, cfg['F'], cfg['N'], dtype=torch.float64)
     dH = torch.ones(Bs, Ts, cfg['F'], cfg['N'], dtype=torch.float64)
@@ -80,7 +81,7 @@ def cpu_sample(cfg, Bs, Ts, repeats, warm=1):
         if ref_shim.available():
             kind = 'reference'
             gml = ref_shim.load()
-            cell = gml.GGCRNNCell(cfg['G'], cfg['F'], cfg['K'], cfg['K'], torch.tanh, True, None, 1, True)
+            cell = gml.GGCRNNCell(cfg['G'], cfg['F'], cfg['K'], cfg['K'], torch.tanh, tg, sg, 1, True)
             cell.addGSO(S)
 
             def run():
@@ -88,10 +89,10 @@ def cpu_sample(cfg, Bs, Ts, repeats, warm=1):
                 torch.autograd.backward(cell(X, h0), dH)
         else:
             kind = 'port'
-            p = orc.init_cell_params(cfg['G'], cfg['F'], cfg['K'], cfg['K'], cfg['N'], True, None, 1, True)
+            p = orc.init_cell_params(cfg['G'], cfg['F'], cfg['K'], cfg['K'], cfg['N'], tg, sg, 1, True)
 
             def run():
-                orc.cell_forward_backward(p, S, X, h0, dH, True, None)
+                orc.cell_forward_backward(p, S, X, h0, dH, tg, sg)
         times = []
         for i in range(warm + repeats):
             t0 = time.perf_counter()
@@ -469,6 +470,80 @@ def run_cfg5(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------------
+# small reference configurations (parity + latency cases of SURVEY.md 8d; launch-bound, no roofline claim):
+#   cfg1      time-gated cell on the N=80 SBM graph of kStepPredGRNNs.py (F=20, K=5, T=5, B=100)
+#   cfg2-node / cfg2-edge   node- / edge-gated cell on the Adj.p seismograph graph (N=59, F=20, K=4, T=20, B=100)
+# The graphs come from the committed golden fixtures (generated from the reference), signals are synthetic.
+# ------------------------------------------------------------------------------------------------------
+SMALL = {'cfg1': ('cell_cfg1_time', True, None, 5, 5), 'cfg2-node': ('cell_cfg2_node', False, 'node', 4, 20),
+         'cfg2-edge': ('cell_cfg2_edge', False, 'edge', 4, 20)}
+
+
+def run_small(args):
+    import numpy as np
+    import torch
+    import gated_gcrnns_b200 as gg
+    from gated_gcrnns_b200 import _lib
+    fixture, tg, sg, K, T = SMALL[args.workload]
+    assert torch.cuda.is_available(), 'bench.py needs a GPU (no CPU fallback)'
+    dev = torch.device('cuda', 0)
+    S = torch.tensor(np.load(os.path.join(ROOT, 'tests', 'golden', fixture + '.npz'), allow_pickle=True)['S'])
+    N, F, G, B = S.shape[-1], 20, 1, 100
+    gg.set_precision('fp32')
+    torch.manual_seed(0)
+    cell = gg.GGCRNNCell(G, F, K, K, torch.tanh, tg, sg, 1, True)
+    cell.addGSO(S)
+    cell = cell.to(dev)
+    X_host = torch.randn(B, T, G, N).pin_memory()
+    h0_host = torch.zeros(B, F, N).pin_memory()
+    X_dev, h0_dev = X_host.to(dev), h0_host.to(dev)
+    dH = torch.ones(B, T, F, N, device=dev)
+    L = _lib.lib()
+
+    def step(host):
+        cell.zero_grad(set_to_none=True)
+        x, h = (X_host.to(dev, non_blocking=True), h0_host.to(dev, non_blocking=True)) if host else (X_dev, h0_dev)
+        H = cell(x, h)
+        torch.autograd.backward(H, dH)
+        g = cell.weight_B.grad
+        return g.cpu() if host else g
+
+    def timed(host, steps, warmup):
+        for _ in range(warmup):
+            step(host)
+        torch.cuda.synchronize()
+        clk = Clocks(0); clk.start()
+        l0 = L.gcrnn_debug_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step(host)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1), L.gcrnn_debug_launch_count() - l0, clk.result()
+
+    steps = max(args.steps, 20)
+    ms, launches, clocks = timed(False, steps, max(args.warmup, 5))
+    ms_e, _, _ = timed(True, steps, 3)
+    cb = None
+    if not args.no_cpu_baseline:
+        cfg = dict(N=N, F=F, G=G, K=K, T=T, density=None)
+        times, cores, kind = cpu_sample(cfg, B, T, 3, warm=1, S=S.double(), tg=tg, sg=sg)
+        cb = cpu_baseline_dict(cfg, times, cores, B, T, kind)
+        cb['sample'] = cb['sample'].replace('cfg3 shapes', args.workload + ' shapes (full size, no extrapolation)')
+    out = dict(metric='GCRNN sequences/sec fwd+bwd', value=B * steps / (ms * 1e-3), unit='sequences/s', n_gpus=1, steps=steps,
+               warmup=max(args.warmup, 5), ms_per_step=ms / steps, higher_is_better=True, scaling='strong', vs_baseline=None, dtype='f32',
+               data='synthetic',
+               config=dict(workload=f'{args.workload}: N={N} F={F} G={G} K={K} T={T} B={B} time_gating={tg} spatial_gating={sg}, fp32 sparse exact path',
+                           l2='working set fits L2 (launch/latency-bound case; no roofline claim, SURVEY.md 8d)'),
+               roofline=None, cpu_baseline=cb, clocks=clocks,
+               e2e=dict(value=B * steps / (ms_e * 1e-3), unit='sequences/s', h2d_bytes_per_step=int(X_host.numel() * 4 + h0_host.numel() * 4),
+                        d2h_bytes_per_step=int(cell.weight_B.numel() * 4), ms_per_step=ms_e / steps),
+               gpu_launches=int(launches))
+    print(json.dumps(out), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -483,13 +558,16 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--gemm-pair', type=int, default=None, help='A/B switch: 1 = CTA-pair shift GEMM, 0 = single-CTA')
     ap.add_argument('--bwd-fused', type=int, default=None, help='A/B switch: 1 = fused reverse-time step kernel, 0 = separate kernels')
-    ap.add_argument('--workload', default='cfg3', choices=['cfg3', 'cfg5'], help='cfg3 = the headline dense config; cfg5 = sparse kNN graph')
+    ap.add_argument('--workload', default='cfg3', choices=['cfg3', 'cfg5', 'cfg1', 'cfg2-node', 'cfg2-edge'],
+                    help='cfg3 = the headline dense config; cfg5 = sparse kNN graph; cfg1 / cfg2-* = the small reference configurations')
     ap.add_argument('--once', action='store_true', help='run one micro-batch forward+backward and exit (for ncu captures)')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)
     elif args.workload == 'cfg5':
         run_cfg5(args)
+    elif args.workload in SMALL:
+        run_small(args)
     else:
         run_ours(args)
 
