@@ -22,7 +22,7 @@ SYMBOLS = [
     'gcrnn_graph_create_csr', 'gcrnn_graph_create_dense', 'gcrnn_graph_destroy', 'gcrnn_graph_info',
     'gcrnn_lsigf_workspace_bytes', 'gcrnn_lsigf_forward', 'gcrnn_lsigf_backward',
     'gcrnn_gat_workspace_bytes', 'gcrnn_gat_forward', 'gcrnn_gat_backward',
-    'gcrnn_cell_create', 'gcrnn_cell_destroy', 'gcrnn_cell_workspace_bytes',
+    'gcrnn_cell_create', 'gcrnn_cell_destroy', 'gcrnn_cell_set_option', 'gcrnn_cell_get_option', 'gcrnn_cell_workspace_bytes',
     'gcrnn_cell_forward', 'gcrnn_cell_backward',
     'gcrnn_comm_unique_id', 'gcrnn_comm_create', 'gcrnn_comm_destroy', 'gcrnn_allreduce_sum',
 ]
@@ -88,6 +88,8 @@ def lib():
                                      C.c_size_t, _P]
     L.gcrnn_cell_create.argtypes = [C.POINTER(_P), C.POINTER(CellDesc), _P]
     L.gcrnn_cell_destroy.argtypes = [_P]
+    L.gcrnn_cell_set_option.argtypes = [_P, C.c_char_p, C.c_int32]
+    L.gcrnn_cell_get_option.argtypes = [_P, C.c_char_p, C.POINTER(C.c_int32)]
     L.gcrnn_cell_workspace_bytes.argtypes = [_P, C.c_int64, C.c_int64, C.c_int32, C.POINTER(C.c_size_t),
                                              C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
     L.gcrnn_cell_forward.argtypes = [_P, C.POINTER(CellParams), _P, _P, _P, _P, C.c_size_t, _P, C.c_size_t,

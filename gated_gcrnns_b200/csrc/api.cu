@@ -140,6 +140,25 @@ int gcrnn_cell_destroy(gcrnn_cell* c) {
   delete c;
   API_END
 }
+int gcrnn_cell_set_option(gcrnn_cell* c, const char* name, int32_t value) {
+  API_BEGIN
+  GCRNN_CHECK(c && name, "null argument");
+  const std::string n(name);
+  if (n == "need_dx") c->need_dx = value != 0;
+  else if (n == "path") { GCRNN_CHECK(value >= -1 && value <= GCRNN_PATH_NODE32, "bad path %d", value); c->forced_path = value; }
+  else GCRNN_CHECK(false, "unknown cell option '%s'", name);
+  API_END
+}
+int gcrnn_cell_get_option(const gcrnn_cell* c, const char* name, int32_t* value) {
+  API_BEGIN
+  GCRNN_CHECK(c && name && value, "null argument");
+  const std::string n(name);
+  if (n == "need_dx") *value = c->need_dx;
+  else if (n == "path") *value = c->forced_path;
+  else if (n == "last_path") *value = c->last_path;
+  else GCRNN_CHECK(false, "unknown cell option '%s'", name);
+  API_END
+}
 int gcrnn_cell_workspace_bytes(const gcrnn_cell* c, int64_t B, int64_t T, int32_t need_input_grads, size_t* saved_bytes,
                                size_t* fwd_bytes, size_t* bwd_bytes) {
   API_BEGIN

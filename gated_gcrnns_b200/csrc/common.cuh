@@ -66,6 +66,10 @@ struct gcrnn_graph {
 struct gcrnn_cell {
   gcrnn_cell_desc d;
   const gcrnn_graph* g = nullptr;
+  // execution-path selection of the fp32 sparse path (gcrnn_cell_set_option / gcrnn_cell_get_option)
+  mutable int need_dx = 0;        // hint for the next forward: the caller will ask backward for dX
+  mutable int forced_path = -1;   // -1: choose automatically; otherwise GCRNN_PATH_*
+  mutable int last_path = 0;      // path taken by the last forward
 };
 
 namespace gcrnn {

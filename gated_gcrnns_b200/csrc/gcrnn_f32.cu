@@ -554,10 +554,25 @@ size_t cell_backward_e32(const gcrnn_cell* cell, const gcrnn_cell_params* p, con
 
 }  // namespace
 
+namespace {
+// which path a forward takes (GCRNN_PATH_*): the fused per-node kernels when the shape allows, else the generic kernels
+int pick_path(const gcrnn_cell* cell) {
+  if (cell->forced_path >= 0) {
+    if (cell->forced_path == GCRNN_PATH_NODE32) GCRNN_CHECK(edge32_ok(cell), "path NODE32 does not support this cell");
+    return cell->forced_path;
+  }
+  return edge32_ok(cell) ? GCRNN_PATH_NODE32 : GCRNN_PATH_GENERIC;
+}
+}  // namespace
+
 size_t cell_forward_f32(const gcrnn_cell* cell, const gcrnn_cell_params* p, const float* X, const float* h0, float* H,
                         void* saved, size_t savedb, size_t* saved_used, void* ws, size_t wsb, int64_t B, int64_t T,
                         cudaStream_t st) {
-  if (edge32_ok(cell)) return cell_forward_e32(cell, p, X, h0, H, saved, savedb, saved_used, ws, wsb, B, T, st);
+  {
+    const int path = pick_path(cell);
+    if (ws != nullptr) cell->last_path = path;
+    if (path == GCRNN_PATH_NODE32) return cell_forward_e32(cell, p, X, h0, H, saved, savedb, saved_used, ws, wsb, B, T, st);
+  }
   const CellDims d = dims_of(cell, B, T);
   Arena a(ws, wsb);
   Ctx c{cell->g, st, a.dry()};
@@ -627,14 +642,11 @@ size_t cell_backward_f32(const gcrnn_cell* cell, const gcrnn_cell_params* p, con
                          int64_t T, cudaStream_t st) {
   (void)X; (void)h0; (void)H;
   const CellDims d = dims_of(cell, B, T);
-  if (edge32_ok(cell)) {
-    // the fused backward has no dX; a caller that wants it gets the generic sweep, which only reads the generic part of
-    // `saved` (a prefix of what the fused forward wrote).  The scratch query must cover whichever of the two is larger.
-    size_t need_saved = 0;
-    { Arena sa(nullptr, 0); Saved s0; Saved32 x0; s0.layout(sa, d); x0.layout(sa, d); need_saved = sa.off; }
-    const bool dry = ws == nullptr;
-    if (!dX && (dry || savedb >= need_saved))
-      return cell_backward_e32(cell, p, dH, saved, savedb, gr, dh0, ws, wsb, B, T, st);
+  {
+    // backward runs on the path whose saved state the forward wrote (the autograd glue forces it).  NODE32 has no dX: the
+    // generic sweep then runs on the generic prefix of what NODE32's forward saved.
+    const int path = pick_path(cell);
+    if (path == GCRNN_PATH_NODE32 && !dX) return cell_backward_e32(cell, p, dH, saved, savedb, gr, dh0, ws, wsb, B, T, st);
   }
   Arena a(ws, wsb);
   Ctx c{cell->g, st, a.dry()};

@@ -72,6 +72,20 @@ __device__ __forceinline__ float wsum4(float v0, float v1, float v2, float v3, i
   for (int o = 4; o > 0; o >>= 1) k += __shfl_xor_sync(0xffffffffu, k, o);
   return k;
 }
+// prod[s] summed over lanes, result of slot L on lane L (31 shuffles for 32 slots): the "transposed" warp reduction
+template <int M>
+__device__ __forceinline__ void tree_step(float (&prod)[32], int lane) {
+  const bool up = lane & M;
+#pragma unroll
+  for (int k = 0; k < M; ++k) {
+    const float lo = prod[k], hi = prod[k + M];
+    prod[k] = (up ? hi : lo) + __shfl_xor_sync(0xffffffffu, up ? lo : hi, M);
+  }
+}
+__device__ __forceinline__ float tree32(float (&prod)[32], int lane) {
+  tree_step<16>(prod, lane); tree_step<8>(prod, lane); tree_step<4>(prod, lane); tree_step<2>(prod, lane); tree_step<1>(prod, lane);
+  return prod[0];
+}
 // Q-layout reduce-scatter: every lane holds a float4 partial of chunk c = lane & 7; returns the total of feature
 // FEAT(lane) = 4 c + g summed over the four groups g = lane >> 3  (3 shuffles)
 __device__ __forceinline__ float rs4(const float4& a, int lane) {

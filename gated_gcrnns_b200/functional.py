@@ -212,6 +212,14 @@ class CellHandle:
     def ptr(self):
         return C.c_void_p(self.handle)
 
+    def set_option(self, name: str, value: int):
+        _lib.check(_lib.lib().gcrnn_cell_set_option(self.ptr, name.encode(), int(value)), 'cell_set_option')
+
+    def get_option(self, name: str) -> int:
+        v = C.c_int32()
+        _lib.check(_lib.lib().gcrnn_cell_get_option(self.ptr, name.encode(), C.byref(v)), 'cell_get_option')
+        return v.value
+
     def workspace(self, B, T, input_grads):
         s, f, b = C.c_size_t(), C.c_size_t(), C.c_size_t()
         _lib.check(_lib.lib().gcrnn_cell_workspace_bytes(self.ptr, B, T, int(input_grads), C.byref(s), C.byref(f),
@@ -234,6 +242,10 @@ class _CellFn(torch.autograd.Function):
         X32, h32 = _f32(X, dev), _f32(h0, dev)
         p32 = [_f32(p, dev) for p in params]
         H = torch.empty(B, T, cell.F, cell.N, dtype=torch.float32, device=dev)
+        # execution-path selection (fp32 sparse precision): tell the library whether backward will want dX, let it choose,
+        # and remember the choice so that backward runs on the path whose saved state this forward wrote
+        cell.set_option('path', -1)
+        cell.set_option('need_dx', int(ctx.needs_input_grad[1]))
         sb, fb, _ = cell.workspace(B, T, False)
         saved = _bytes(sb, dev)
         ws = _bytes(fb, dev)
@@ -241,6 +253,7 @@ class _CellFn(torch.autograd.Function):
         _lib.check(_lib.lib().gcrnn_cell_forward(cell.ptr, C.byref(st), _ptr(X32), _ptr(h32), _ptr(H), _ptr(saved),
                                                  saved.numel(), _ptr(ws), ws.numel(), B, T, _stream(dev)), 'cell_forward')
         ctx.cell = cell
+        ctx.path = cell.get_option('last_path')
         ctx.types = (X.dtype, h0.dtype, [p.dtype for p in params], [p.shape for p in params])
         ctx.save_for_backward(X32, h32, H, saved, *p32)
         return H.to(X.dtype) if X.dtype != torch.float32 else H
@@ -263,11 +276,13 @@ class _CellFn(torch.autograd.Function):
         pst = _fill_struct(cell.slots, p32)
         dX = torch.empty_like(X32) if need_x else None
         dh0 = torch.empty_like(h32) if need_h else None
+        cell.set_option('path', ctx.path)
         _, _, bb = cell.workspace(B, T, need_x or need_h)
         ws = _bytes(bb, dev)
         _lib.check(_lib.lib().gcrnn_cell_backward(cell.ptr, C.byref(pst), _ptr(X32), _ptr(h32), _ptr(H), _ptr(dH32),
                                                   _ptr(saved), saved.numel(), C.byref(gst), _ptr(dX), _ptr(dh0), _ptr(ws),
                                                   ws.numel(), B, T, _stream(dev)), 'cell_backward')
+        cell.set_option('path', -1)
         _dist.allreduce_bucket(bucket)
         grads = [v.reshape(s).to(d) for v, s, d in zip(views, pshapes, pds)]
         return (None, dX.to(xd) if need_x else None, dh0.to(hd) if need_h else None, *grads)

@@ -111,6 +111,18 @@ int gcrnn_gat_backward(const gcrnn_graph* g, const float* mixer, const float* we
 /* ---- the gated GCRNN cell --------------------------------------------------------------------------- */
 int gcrnn_cell_create(gcrnn_cell** out, const gcrnn_cell_desc* desc, const gcrnn_graph* g);
 int gcrnn_cell_destroy(gcrnn_cell* c);
+/* Execution paths of the fp32 sparse precision (same results within the stated fp32 tolerance):
+ *   GENERIC  per-op kernels, any shape / gating mode, supports dX;
+ *   NODE32   fused edge-gated kernels for F == 32, one warp per (sample, node) (csrc/sp32_kernels.cuh); a dX request makes
+ *            backward run the generic sweep on the generic prefix of the saved state.
+ * Options (per cell handle, used from one host thread at a time):
+ *   "path"      (set)  -1 = automatic (default), otherwise force GCRNN_PATH_* — the autograd glue forces backward onto the path
+ *                      its forward took;
+ *   "need_dx"   (set)  hint for the next forward: backward will be asked for dX (reserved for paths that cannot serve it);
+ *   "last_path" (get)  path taken by the last forward on this handle. */
+enum { GCRNN_PATH_GENERIC = 0, GCRNN_PATH_NODE32 = 1 };
+int gcrnn_cell_set_option(gcrnn_cell* c, const char* name, int32_t value);
+int gcrnn_cell_get_option(const gcrnn_cell* c, const char* name, int32_t* value);
 /* saved_bytes: buffer written by forward and read by backward; fwd/bwd_bytes: scratch. */
 int gcrnn_cell_workspace_bytes(const gcrnn_cell* c, int64_t B, int64_t T, int32_t need_input_grads,
                                size_t* saved_bytes, size_t* fwd_bytes, size_t* bwd_bytes);

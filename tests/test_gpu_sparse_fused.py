@@ -46,7 +46,10 @@ def ragged_graph(N, seed, max_out=31, hub=True):
     return torch.tensor(S).reshape(1, N, N)
 
 
-def run_case(N, G_, Kin, Kst, T, B, bias, seed, need_x=False):
+PATH_GENERIC, PATH_NODE32 = 0, 1
+
+
+def run_case(N, G_, Kin, Kst, T, B, bias, seed, need_x=False, expect_path=None):
     torch.manual_seed(seed)
     F_ = 32
     S = ragged_graph(N, seed)
@@ -69,6 +72,9 @@ def run_case(N, G_, Kin, Kst, T, B, bias, seed, need_x=False):
     (H * dH.float().to(DEV)).sum().backward()
     torch.cuda.synchronize()
     launches = L.gcrnn_debug_launch_count() - l0
+    if expect_path is not None:
+        took = cell._handle(torch.device(DEV)).get_option('last_path')
+        assert took == expect_path, f'forward took path {took}, expected {expect_path}'
     errs = {'H': relerr(H, Href), 'dh0': relerr(hg.grad, gref['__h0'])}
     if need_x:
         errs['dX'] = relerr(Xg.grad, gref['__X'])
@@ -84,7 +90,7 @@ def run_case(N, G_, Kin, Kst, T, B, bias, seed, need_x=False):
 
 @pytest.mark.parametrize('G_,Kin,Kst,bias', [(1, 3, 3, True), (2, 4, 2, True), (1, 2, 4, False), (3, 5, 3, True)])
 def test_fused_edge32_vs_oracle(G_, Kin, Kst, bias):
-    launches, _, _ = run_case(N=150, G_=G_, Kin=Kin, Kst=Kst, T=5, B=3, bias=bias, seed=11 + Kst)
+    launches, _, _ = run_case(N=150, G_=G_, Kin=Kin, Kst=Kst, T=5, B=3, bias=bias, seed=11 + Kst, expect_path=PATH_NODE32)
     # 4 + (Kst - 2) kernels per forward step and 4 + (Kst - 2) + 1 memset-free kernels per backward step, plus set-up
     assert launches < 5 * (10 + 2 * (Kst - 2)) + 12 + 2 * Kin, f'the fused kernels did not run ({launches} launches)'
 
@@ -93,7 +99,7 @@ def test_fused_matches_generic_kernels_and_falls_back_for_dX():
     L = _lib.lib()
     old = L.gcrnn_debug_set_option(b'sparse_fused', 0)
     try:
-        lg, Hg, gg_ = run_case(N=130, G_=1, Kin=3, Kst=3, T=4, B=2, bias=True, seed=5)
+        lg, Hg, gg_ = run_case(N=130, G_=1, Kin=3, Kst=3, T=4, B=2, bias=True, seed=5, expect_path=PATH_GENERIC)
     finally:
         L.gcrnn_debug_set_option(b'sparse_fused', old)
     lf, Hf, gf = run_case(N=130, G_=1, Kin=3, Kst=3, T=4, B=2, bias=True, seed=5)
@@ -130,3 +136,4 @@ def test_fused_large_knn_properties():
         Hb.sum().backward()
         acc += cell.weight_B.grad
     assert relerr(acc, g_all) < 1e-4
+
