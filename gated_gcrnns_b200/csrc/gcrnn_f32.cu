@@ -492,7 +492,8 @@ void e32_backward_steps(const Ctx& c, const CellDims& d, const gcrnn_cell_params
   const Gather& fw = g->fwd[0];
   const Gather& bw = g->bwd[0];
   const int g_dpre = (int)std::min<long long>(d.B * ((d.N + 31) / 32), (long long)sm_count() * 8);
-  const size_t rows_smem = (size_t)4 * 2 * e32::ROWS_STAGE * sizeof(float);
+  const int rows_cap = (g->max_row_deg + 3) & ~3;                    // staged rows per gate in bwd_rows_k
+  const size_t rows_smem = (size_t)4 * 2 * e32::rows_stage_floats(rows_cap) * sizeof(float);
   const int g_rows = persistent_grid(e32::bwd_rows_k, 128, 4, BN, rows_smem);
   const e32::Gather3 gfw{fw.ptr, fw.idx, fw.val}, gbw{bw.ptr, bw.idx, bw.val};
   const int g_node = persistent_grid(e32::bwd_node_k<KST>, 128, 4, BN);
@@ -506,7 +507,7 @@ void e32_backward_steps(const Ctx& c, const CellDims& d, const gcrnn_cell_params
     check_launch();
     zero(c, b.dr, BN * sizeof(float2));
     e32::bwd_rows_k<<<g_rows, 128, rows_smem, c.st>>>(g->att_rptr, g->att_col, g->att_val, info, wa, wr, b.dya, b.dyr,
-                                              p->e_mixer[0], p->e_mixer[1], b.pa, b.pr, reinterpret_cast<float*>(b.dr), b.acc, d.N, BN);
+                                              p->e_mixer[0], p->e_mixer[1], b.pa, b.pr, reinterpret_cast<float*>(b.dr), b.acc, rows_cap, d.N, BN);
     check_launch();
     e32::Chain zc{};
     zc.p[0] = t == 0 ? s.h0n : s.Hn + (t - 1) * BNF;

@@ -118,6 +118,7 @@ __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0
 // global-load latencies per task.  Instead each warp runs a 4-stage pipeline over ITS task sequence: iteration `it`
 // loads the row pointers of task it+3 (S0), the edge list of task it+2 (S1), issues cp.async copies of every row task
 // it+1 needs into a warp-private double-buffered shared-memory stage (S2), and computes task it (S3).
+constexpr int CAP = 24;             // neighbour rows per task that go through the cp.async stage (a longer edge list: synchronous tail)
 struct Tk { int r, n; };
 // this warp's task sequence inside the block's CONTIGUOUS task range: first + j * nw, j = 0 .. niter-1
 struct WarpTasks {
@@ -142,10 +143,10 @@ struct WarpTasks {
 };
 
 // Pipeline for "NS streamed rows + one gathered row" tasks:  gathered[f] = sum_p val[p] * gsrc[r, idx[p], f].
-// The first 32 edges of a destination go through the cp.async stage, a longer tail is fetched synchronously.
+// The first CAP edges of a destination go through the cp.async stage, a longer tail is fetched synchronously.
 template <int NS>
 struct GatherPipe {
-  static constexpr int ROWS = NS + 32;
+  static constexpr int ROWS = NS + CAP;
   float* wbuf;                                  // this warp's stage: [2][ROWS][32]
   Gather3 op;
   const float* gsrc;                            // gathered array [R, N, 32]
@@ -180,7 +181,7 @@ struct GatherPipe {
           for (int m = 1; m < NS; ++m) if (k == m) sp = srow[m];
           if (k < NS) cp_async16(dst + k0 * 32, sp + task * 32 + ch);
         }
-        const int cnt = min(b_deg, 32);
+        const int cnt = min(b_deg, CAP);
         const float* gb = gsrc + wt.sample(wt.t2) * 32 + ch;
         float* gd = dst + NS * 32;
         for (int q0 = 0; q0 < cnt; q0 += 4) {
@@ -209,13 +210,13 @@ struct GatherPipe {
     __syncwarp();
     const int g = lane >> 3;
     const float4* gr = reinterpret_cast<const float4*>(rows(it) + NS * 32) + lane;   // row q0 + g, chunk c : + q0 * 8
-    const int cnt = min(d_deg, 32);
+    const int cnt = min(d_deg, CAP);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int q0 = 0; q0 < cnt; q0 += 4)
       fma4(acc, __shfl_sync(0xffffffffu, d_mv, (q0 + g) & 31), gr[q0 * 8]);     // val = 0 beyond the edge list
-    if (d_deg > 32) {                            // rare long tail: synchronous
+    if (d_deg > CAP) {                           // rare long tail: synchronous
       const float4* base = reinterpret_cast<const float4*>(gsrc + wt.sample(wt.t3) * 32) + (lane & 7);
-      for (int pb = d_p0 + 32; pb < d_p0 + d_deg; pb += 32) {
+      for (int pb = d_p0 + CAP; pb < d_p0 + d_deg; pb += 32) {
         const int c2 = min(32, d_p0 + d_deg - pb);
         int mi = 0; float mv = 0.f;
         if (lane < c2) { mi = __ldg(op.idx + pb + lane); mv = __ldg(op.val + pb + lane); }
@@ -389,8 +390,8 @@ __global__ void __launch_bounds__(256) rowstats_k(const int* __restrict__ rptr, 
 // ---- forward, stage 3: attention aggregation of both gates + relu + tanh update -----------------------------------
 // y_g[j,:] = relu( sum_{i -> j} S'_ij alpha^g_ij Wu_g[i,:] ),  h = tanh(y_a + y_r);  masks = sign bits of the two relus
 // (bit l of a mask word belongs to feature FEAT(l)).  4 warps / block, dynamic shared memory: per warp
-// [2 stages][2 gates][32 rows][32] floats (64 KB per block).
-constexpr int AGG_STAGE = 2 * 32 * 32;
+// [2 stages][2 gates][CAP rows][32] floats (48 KB per block).
+constexpr int AGG_STAGE = 2 * CAP * 32;
 __global__ void __launch_bounds__(128) aggregate_k(const int* __restrict__ cptr, const int* __restrict__ crow, const float* __restrict__ cval,
                                                    const float4* __restrict__ info, const float* __restrict__ wu_a, const float* __restrict__ wu_r,
                                                    float* __restrict__ hn, uint2* __restrict__ masks, int N, long long RN) {
@@ -414,14 +415,14 @@ __global__ void __launch_bounds__(128) aggregate_k(const int* __restrict__ cptr,
       if (j >= 0 && j < wt.niter) {
         const size_t rb = wt.sample(wt.t2);
         float* dst = wbuf + (j & 1) * AGG_STAGE + lane * 4;
-        const int cnt = min(b_deg, 32);
+        const int cnt = min(b_deg, CAP);
         const float* ga = wu_a + rb * 32 + ch;
         const float* gr = wu_r + rb * 32 + ch;
         for (int q0 = 0; q0 < cnt; q0 += 4) {
           const int src = __shfl_sync(0xffffffffu, b_mi, (q0 + g) & 31);
           if (q0 + g < cnt) {
             cp_async16(dst + q0 * 32, ga + (size_t)src * 32);
-            cp_async16(dst + (32 + q0) * 32, gr + (size_t)src * 32);
+            cp_async16(dst + (CAP + q0) * 32, gr + (size_t)src * 32);
           }
         }
         if (lane < cnt) { c_sa = info[2 * (rb + b_mi)]; c_sr = info[2 * (rb + b_mi) + 1]; }
@@ -441,7 +442,7 @@ __global__ void __launch_bounds__(128) aggregate_k(const int* __restrict__ cptr,
     }
     if (it < 0) continue;
     // S3
-    const int cnt = min(d_deg, 32);
+    const int cnt = min(d_deg, CAP);
     float ca = 0.f, cr = 0.f;                      // alpha * S' of edge `lane` (0 beyond the edge list)
     if (lane < cnt) {
       ca = d_v * (__expf(leaky(d_sa.y + d_rja) - d_sa.z) * d_sa.w);
@@ -450,17 +451,17 @@ __global__ void __launch_bounds__(128) aggregate_k(const int* __restrict__ cptr,
     cp_wait<1>();
     __syncwarp();
     const float4* ra = reinterpret_cast<const float4*>(wbuf + (it & 1) * AGG_STAGE) + lane;     // row q0 + g: + q0 * 8
-    const float4* rr = ra + 32 * 8;
+    const float4* rr = ra + CAP * 8;
     float4 acc_a = make_float4(0.f, 0.f, 0.f, 0.f), acc_r = acc_a;
     for (int q0 = 0; q0 < cnt; q0 += 4) {
       fma4(acc_a, __shfl_sync(0xffffffffu, ca, (q0 + g) & 31), ra[q0 * 8]);
       fma4(acc_r, __shfl_sync(0xffffffffu, cr, (q0 + g) & 31), rr[q0 * 8]);
     }
-    if (d_deg > 32) {                              // rare long tail (hub columns): synchronous
+    if (d_deg > CAP) {                             // rare long tail (hub columns): synchronous
       const size_t rb = wt.sample(wt.t3);
       const float4* pa = reinterpret_cast<const float4*>(wu_a + rb * 32) + (lane & 7);
       const float4* pr = reinterpret_cast<const float4*>(wu_r + rb * 32) + (lane & 7);
-      for (int qb = d_p0 + 32; qb < d_p0 + d_deg; qb += 32) {
+      for (int qb = d_p0 + CAP; qb < d_p0 + d_deg; qb += 32) {
         const int c2 = min(32, d_p0 + d_deg - qb);
         int mi = 0; float xa = 0.f, xr = 0.f;
         if (lane < c2) {
@@ -522,20 +523,21 @@ __global__ void __launch_bounds__(256) dpre_k(const float* __restrict__ dHt /* d
 // ---- backward, stage 1 (per source row i, both gates): softmax / leaky backward, partial dWu ---------------------------
 // Edge-distributed data: lanes 0-15 hold edges e (and 16+e) of the row for the input gate, lanes 16-31 the same edges
 // for the forget gate.  Row data: Q-layout.  Requires row degree of S + I <= 32.  4 warps / block, dynamic shared
-// memory per warp: [2 stages][dya rows 32 | dyr rows 32 | Wu_a row | Wu_r row][32] floats.
-constexpr int ROWS_STAGE = (2 * 32 + 2) * 32;
+// memory per warp: [2 stages][dya rows R | dyr rows R | Wu_a row | Wu_r row][32] floats, R = max row degree rounded up to 4.
+__host__ __device__ inline int rows_stage_floats(int R) { return (2 * R + 2) * 32; }
 __global__ void __launch_bounds__(128) bwd_rows_k(const int* __restrict__ rptr, const int* __restrict__ col, const float* __restrict__ val,
                                                   const float4* __restrict__ info, const float* __restrict__ wu_a, const float* __restrict__ wu_r,
                                                   const float* __restrict__ dya, const float* __restrict__ dyr,
                                                   const float* __restrict__ mix_a, const float* __restrict__ mix_r,
                                                   float* __restrict__ pa, float* __restrict__ pr, float* __restrict__ dr /* [R*N][2], zeroed */,
-                                                  float* __restrict__ acc, int N, long long RN) {
+                                                  float* __restrict__ acc, int R, int N, long long RN) {
   extern __shared__ __align__(16) float dyn[];
   __shared__ float red[4][64];
   __shared__ float sdot[4][2][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int half = lane >> 4, e = lane & 15;
   const int g = lane >> 3, ch = (lane & 7) * 4, fo = feat_of_lane(lane);
+  const int ROWS_STAGE = rows_stage_floats(R);
   float* wbuf = dyn + (size_t)warp * 2 * ROWS_STAGE;
   for (int i = lane; i < 2 * ROWS_STAGE; i += 32) wbuf[i] = 0.f;
   __syncwarp();
@@ -562,10 +564,10 @@ __global__ void __launch_bounds__(128) bwd_rows_k(const int* __restrict__ rptr, 
           const int src = __shfl_sync(0xffffffffu, q0 < 16 ? b_j0 : b_j1, (q0 + g) & 15);
           if (q0 + g < b_deg) {
             cp_async16(dst + q0 * 32, ga + (size_t)src * 32);
-            cp_async16(dst + (32 + q0) * 32, gr + (size_t)src * 32);
+            cp_async16(dst + (R + q0) * 32, gr + (size_t)src * 32);
           }
         }
-        if (g < 2) cp_async16(dst + 64 * 32, (g == 0 ? wu_a : wu_r) + task * 32 + ch);     // rows 64 (Wu_a), 65 (Wu_r)
+        if (g < 2) cp_async16(dst + 2 * R * 32, (g == 0 ? wu_a : wu_r) + task * 32 + ch);  // rows 2R (Wu_a), 2R+1 (Wu_r)
         if (e < b_deg) c_rj0 = info[2 * (rb + b_j0) + half].x;
         if (16 + e < b_deg) c_rj1 = info[2 * (rb + b_j1) + half].x;
         c_mine = info[2 * task + half];
@@ -598,16 +600,18 @@ __global__ void __launch_bounds__(128) bwd_rows_k(const int* __restrict__ rptr, 
     cp_wait<1>();
     __syncwarp();
     const float4* st = reinterpret_cast<const float4*>(wbuf + (it & 1) * ROWS_STAGE);
-    const float4 wua4 = st[64 * 8 + (lane & 7)], wur4 = st[65 * 8 + (lane & 7)];
+    const float4 wua4 = st[2 * R * 8 + (lane & 7)], wur4 = st[(2 * R + 1) * 8 + (lane & 7)];
     const float4* ra = st + lane;                  // row q0 + g, chunk c: + q0 * 8
-    const float4* rr = ra + 32 * 8;
+    const float4* rr = ra + R * 8;
     float4 parta = make_float4(0.f, 0.f, 0.f, 0.f), partr = parta;
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
       const int cnt = min(16, max(0, d_deg - c * 16));          // warp-uniform
       for (int q0 = 0; q0 < cnt; q0 += 8) {         // rows q0 + g and q0 + 4 + g (stale rows beyond cnt: coef = 0, dots unused)
         const float4 xa = ra[(c * 16 + q0) * 8], xr = rr[(c * 16 + q0) * 8];
-        const float4 ya = ra[(c * 16 + q0 + 4) * 8], yr = rr[(c * 16 + q0 + 4) * 8];
+        const bool two = q0 + 4 < cnt;               // warp-uniform: the second 4-row group exists
+        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 ya = two ? ra[(c * 16 + q0 + 4) * 8] : zero4, yr = two ? rr[(c * 16 + q0 + 4) * 8] : zero4;
         fma4(parta, __shfl_sync(0xffffffffu, coef[c], (q0 + g) & 15), xa);            // coef = 0 beyond the edge list
         fma4(partr, __shfl_sync(0xffffffffu, coef[c], 16 + ((q0 + g) & 15)), xr);
         fma4(parta, __shfl_sync(0xffffffffu, coef[c], (q0 + 4 + g) & 15), ya);
@@ -635,7 +639,7 @@ __global__ void __launch_bounds__(128) bwd_rows_k(const int* __restrict__ rptr, 
     if (16 + e < d_deg) atomicAdd(dr + 2 * (rb + d_j1) + half, ds1);
     const float dca = __shfl_sync(0xffffffffu, dc, 0), dcr = __shfl_sync(0xffffffffu, dc, 16);
     const size_t o = wt.row(wt.t3) * 32 + fo;
-    const float* wrow = reinterpret_cast<const float*>(st + 64 * 8);
+    const float* wrow = reinterpret_cast<const float*>(st + 2 * R * 8);
     pa[o] = fmaf(a2a, dca, rs4(parta, lane)); pr[o] = fmaf(a2r, dcr, rs4(partr, lane));
     m2a = fmaf(dca, wrow[fo], m2a); m2r = fmaf(dcr, wrow[32 + fo], m2r);
     __syncwarp();
