@@ -9,6 +9,7 @@ unsigned long long g_launches = 0;
 int g_opt_gemm_pair = 1;
 int g_opt_bwd_fused = 1;
 int g_opt_sparse_fused = 1;
+int g_opt_graph_capture = 1;
 void set_last_error(const char* fmt, ...) {
   va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof g_err, fmt, ap); va_end(ap);
 }
@@ -27,6 +28,88 @@ using namespace gcrnn;
     catch (...) { set_last_error("unknown error"); return -1; }                      \
   return 0;
 
+// ---- CUDA-graph replay of small fp32 cell calls ------------------------------------------------------------------------
+// The reference's own configurations (N = 59 / 80 nodes) are launch-bound: a forward+backward is
+// 150-1000 tiny kernels.  A forward (or backward) call is a pure function of its pointer set and sizes, and PyTorch's caching
+// allocator hands a training loop the same pointers step after step, so the launch sequence is captured once per key into a
+// CUDA graph and replayed afterwards.  Capture runs on a side stream (torch's default stream is the legacy stream, which cannot
+// be captured) fenced by events against the caller's stream; a key miss simply captures again (8 entries, LRU).
+namespace {
+constexpr int GK_PTRS = 72;
+struct GraphKey {
+  const void* p[GK_PTRS]; int64_t B, T; int kind, path;
+  bool operator==(const GraphKey& o) const { return memcmp(this, &o, sizeof(GraphKey)) == 0; }
+};
+struct GraphEntry { GraphKey key; cudaGraphExec_t exec; unsigned long long launches; uint64_t stamp; int last_path; };
+struct GraphCache {
+  std::vector<GraphEntry> entries;
+  cudaStream_t side = nullptr; cudaEvent_t ev_in = nullptr, ev_out = nullptr; uint64_t clock = 0;
+  ~GraphCache() {
+    for (auto& e : entries) cudaGraphExecDestroy(e.exec);
+    if (ev_in) cudaEventDestroy(ev_in);
+    if (ev_out) cudaEventDestroy(ev_out);
+    if (side) cudaStreamDestroy(side);
+  }
+};
+void key_params(GraphKey& k, int& n, const gcrnn_cell_params* p) {
+  static_assert(sizeof(gcrnn_cell_params) % sizeof(void*) == 0, "parameter block is an array of pointers");
+  const void* const* q = reinterpret_cast<const void* const*>(p);
+  for (size_t i = 0; i < sizeof(gcrnn_cell_params) / sizeof(void*); ++i) { GCRNN_CHECK(n < GK_PTRS, "graph key overflow"); k.p[n++] = q[i]; }
+}
+bool graph_eligible(const gcrnn_cell* c, int64_t B, int64_t T) {
+  return g_opt_graph_capture && c->d.precision == GCRNN_PREC_FP32 &&
+         (long long)B * T * c->g->N * c->d.F <= (1ll << 22);
+}
+// run `body(stream)` through the cache; body only enqueues work on the stream it is given
+template <class Body>
+void run_graphed(const gcrnn_cell* c, const GraphKey& key, cudaStream_t user, Body&& body) {
+  if (!c->graph_cache) c->graph_cache = new GraphCache();
+  GraphCache& gc = *static_cast<GraphCache*>(c->graph_cache);
+  if (!gc.side) {
+    CUDA_OK(cudaStreamCreateWithFlags(&gc.side, cudaStreamNonBlocking));
+    CUDA_OK(cudaEventCreateWithFlags(&gc.ev_in, cudaEventDisableTiming));
+    CUDA_OK(cudaEventCreateWithFlags(&gc.ev_out, cudaEventDisableTiming));
+  }
+  CUDA_OK(cudaEventRecord(gc.ev_in, user));
+  CUDA_OK(cudaStreamWaitEvent(gc.side, gc.ev_in, 0));
+  GraphEntry* hit = nullptr;
+  for (auto& e : gc.entries) if (e.key == key) { hit = &e; break; }
+  if (!hit) {
+    const unsigned long long l0 = g_launches;
+    CUDA_OK(cudaStreamBeginCapture(gc.side, cudaStreamCaptureModeThreadLocal));
+    cudaGraph_t graph = nullptr;
+    try {
+      body(gc.side);
+    } catch (...) {
+      cudaStreamEndCapture(gc.side, &graph);
+      if (graph) cudaGraphDestroy(graph);
+      cudaGetLastError();
+      throw;
+    }
+    CUDA_OK(cudaStreamEndCapture(gc.side, &graph));
+    GraphEntry e{key, nullptr, g_launches - l0, 0, c->last_path};
+    g_launches = l0;                                  // counted again at every replay, including the first one below
+    cudaError_t st = cudaGraphInstantiate(&e.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    CUDA_OK(st);
+    if (gc.entries.size() >= 8) {
+      size_t old = 0;
+      for (size_t i = 1; i < gc.entries.size(); ++i) if (gc.entries[i].stamp < gc.entries[old].stamp) old = i;
+      cudaGraphExecDestroy(gc.entries[old].exec);
+      gc.entries.erase(gc.entries.begin() + old);
+    }
+    gc.entries.push_back(e);
+    hit = &gc.entries.back();
+  }
+  hit->stamp = ++gc.clock;
+  if (key.kind == 0) c->last_path = hit->last_path;
+  CUDA_OK(cudaGraphLaunch(hit->exec, gc.side));
+  g_launches += hit->launches;
+  CUDA_OK(cudaEventRecord(gc.ev_out, gc.side));
+  CUDA_OK(cudaStreamWaitEvent(user, gc.ev_out, 0));
+}
+}  // namespace
+
 extern "C" {
 
 int gcrnn_abi_version(void) { return GCRNN_ABI_VERSION; }
@@ -35,6 +118,7 @@ uint64_t gcrnn_debug_launch_count(void) { return g_launches; }
 int gcrnn_debug_set_option(const char* name, int32_t value) {
   if (name && std::string(name) == "bwd_fused") { int old = gcrnn::g_opt_bwd_fused; gcrnn::g_opt_bwd_fused = value; return old; }
   if (name && std::string(name) == "sparse_fused") { int old = gcrnn::g_opt_sparse_fused; gcrnn::g_opt_sparse_fused = value; return old; }
+  if (name && std::string(name) == "graph_capture") { int old = gcrnn::g_opt_graph_capture; gcrnn::g_opt_graph_capture = value; return old; }
   if (name && std::string(name) == "gemm_pair") { int old = gcrnn::g_opt_gemm_pair; gcrnn::g_opt_gemm_pair = value; return old; }
   return -1;
 }
@@ -137,6 +221,7 @@ int gcrnn_cell_create(gcrnn_cell** out, const gcrnn_cell_desc* d, const gcrnn_gr
 }
 int gcrnn_cell_destroy(gcrnn_cell* c) {
   API_BEGIN
+  if (c) { cudaSetDevice(c->g->device); delete static_cast<GraphCache*>(c->graph_cache); }
   delete c;
   API_END
 }
@@ -183,7 +268,15 @@ int gcrnn_cell_forward(gcrnn_cell* c, const gcrnn_cell_params* p, const float* X
   GCRNN_CHECK(c && p && X && h0 && H && ws && saved, "null argument");
   CUDA_OK(cudaSetDevice(c->g->device));
   if (c->d.precision == GCRNN_PREC_BF16_TC) cell_forward_tc(c, p, X, h0, H, saved, savedb, nullptr, ws, wsb, B, T, (cudaStream_t)stream);
-  else cell_forward_f32(c, p, X, h0, H, saved, savedb, nullptr, ws, wsb, B, T, (cudaStream_t)stream);
+  else if (graph_eligible(c, B, T)) {
+    GraphKey key; memset(&key, 0, sizeof key);
+    int n = 0;
+    key_params(key, n, p);
+    key.p[n++] = X; key.p[n++] = h0; key.p[n++] = H; key.p[n++] = saved; key.p[n++] = ws;
+    key.p[n++] = (const void*)savedb; key.p[n++] = (const void*)wsb;
+    key.B = B; key.T = T; key.kind = 0; key.path = c->forced_path;
+    run_graphed(c, key, (cudaStream_t)stream, [&](cudaStream_t st) { cell_forward_f32(c, p, X, h0, H, saved, savedb, nullptr, ws, wsb, B, T, st); });
+  } else cell_forward_f32(c, p, X, h0, H, saved, savedb, nullptr, ws, wsb, B, T, (cudaStream_t)stream);
   API_END
 }
 int gcrnn_cell_backward(gcrnn_cell* c, const gcrnn_cell_params* p, const float* X, const float* h0, const float* H,
@@ -193,7 +286,17 @@ int gcrnn_cell_backward(gcrnn_cell* c, const gcrnn_cell_params* p, const float* 
   GCRNN_CHECK(c && p && X && h0 && H && dH && saved && grads && ws, "null argument");
   CUDA_OK(cudaSetDevice(c->g->device));
   if (c->d.precision == GCRNN_PREC_BF16_TC) cell_backward_tc(c, p, X, h0, H, dH, saved, savedb, grads, dX, dh0, ws, wsb, B, T, (cudaStream_t)stream);
-  else cell_backward_f32(c, p, X, h0, H, dH, saved, savedb, grads, dX, dh0, ws, wsb, B, T, (cudaStream_t)stream);
+  else if (graph_eligible(c, B, T)) {
+    GraphKey key; memset(&key, 0, sizeof key);
+    int n = 0;
+    key_params(key, n, p);
+    key_params(key, n, grads);
+    key.p[n++] = X; key.p[n++] = h0; key.p[n++] = H; key.p[n++] = dH; key.p[n++] = saved; key.p[n++] = dX; key.p[n++] = dh0; key.p[n++] = ws;
+    key.p[n++] = (const void*)savedb; key.p[n++] = (const void*)wsb;
+    key.B = B; key.T = T; key.kind = 1; key.path = c->forced_path;
+    run_graphed(c, key, (cudaStream_t)stream,
+                [&](cudaStream_t st) { cell_backward_f32(c, p, X, h0, H, dH, saved, savedb, grads, dX, dh0, ws, wsb, B, T, st); });
+  } else cell_backward_f32(c, p, X, h0, H, dH, saved, savedb, grads, dX, dh0, ws, wsb, B, T, (cudaStream_t)stream);
   API_END
 }
 

@@ -16,6 +16,7 @@ namespace gcrnn {
 void set_last_error(const char* fmt, ...);
 extern int g_opt_bwd_fused;            // 1: fused reverse-time step kernel (tc_bwd.cuh) when the shape allows
 extern int g_opt_sparse_fused;         // 1: fused F == 32 edge-gated sparse kernels (sp32_kernels.cuh) when the shape allows
+extern int g_opt_graph_capture;        // 1: replay small fp32 cell calls as CUDA graphs keyed by their pointer set (api.cu)
 extern int g_opt_gemm_pair;             // 1: use the CTA-pair (cta_group::2) shift GEMM when the shape allows
 extern unsigned long long g_launches;   // kernels launched by this library (gcrnn_debug_launch_count)
 
@@ -70,6 +71,7 @@ struct gcrnn_cell {
   mutable int need_dx = 0;        // hint for the next forward: the caller will ask backward for dX
   mutable int forced_path = -1;   // -1: choose automatically; otherwise GCRNN_PATH_*
   mutable int last_path = 0;      // path taken by the last forward
+  mutable void* graph_cache = nullptr;   // api.cu: CUDA graphs of small (launch-bound) fp32 forward / backward calls
 };
 
 namespace gcrnn {

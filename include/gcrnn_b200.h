@@ -72,7 +72,8 @@ int         gcrnn_debug_shift_gemm(const gcrnn_graph* g, int32_t backward, const
 
 /* tuning switches for tests and A/B measurements (process-wide): name = "gemm_pair" (1: CTA-pair cta_group::2 shift
  * GEMM when the shape allows, 0: single-CTA kernel), "bwd_fused" (fused reverse-time step kernel of the tensor-core path),
- * "sparse_fused" (fused F == 32 edge-gated kernels of the sparse fp32 path; 0 = the generic per-op kernels).  Returns the previous value, or -1 for an unknown name. */
+ * "sparse_fused" (fused F == 32 edge-gated kernels of the sparse fp32 path; 0 = the generic per-op kernels),
+ * "graph_capture" (small fp32 cell calls are captured once per pointer set into a CUDA graph and replayed; 0 = direct launches).  Returns the previous value, or -1 for an unknown name. */
 int         gcrnn_debug_set_option(const char* name, int32_t value);
 
 /* ---- graph -------------------------------------------------------------------------------------- */

@@ -161,3 +161,36 @@ def test_linearity_of_lsigf_large():
     Sd = S.to_dense().double()
     yref = orc.lsigf(h.cpu().double(), Sd.reshape(1, N, N), x1.cpu().double())
     assert relerr(gg.LSIGF(h, g, x1), yref) < TOL_OUT
+
+
+def test_graph_replay_matches_direct_launches():
+    """Small fp32 calls are captured into CUDA graphs keyed by their pointer set (csrc/api.cu): replays must launch the same
+    kernels and give bit-identical results to direct launches, also when the data behind the pointers changes."""
+    from gated_gcrnns_b200 import _lib
+    L = _lib.lib()
+    c = G.load('cell_cfg2_edge')
+    m = G.cell_meta(c)
+    cell = build_cell(m, torch.tensor(c['S']), c['param'])
+    X, h0, dH = f32(c['X']), f32(c['h0']), f32(c['dH'])
+
+    def run(x):
+        cell.zero_grad()
+        l0 = L.gcrnn_debug_launch_count()
+        H = cell(x, h0)
+        (H * dH).sum().backward()
+        torch.cuda.synchronize()
+        return H.detach().clone(), cell.weight_B.grad.clone(), L.gcrnn_debug_launch_count() - l0
+
+    old = L.gcrnn_debug_set_option(b'graph_capture', 0)
+    try:
+        Hd, gd, ld = run(X)
+        Hd2, gd2, _ = run(2 * X)
+    finally:
+        L.gcrnn_debug_set_option(b'graph_capture', old)
+    assert L.gcrnn_debug_set_option(b'graph_capture', 1) in (0, 1)
+    outs = [run(X), run(2 * X), run(X), run(X)]
+    assert all(o[2] == ld for o in outs), [o[2] for o in outs]
+    assert torch.equal(outs[0][0], Hd) and torch.equal(outs[2][0], Hd) and torch.equal(outs[3][0], Hd)
+    assert torch.equal(outs[1][0], Hd2)
+    assert relerr(outs[3][1], gd) < 1e-6 and relerr(outs[1][1], gd2) < 1e-6      # float atomics: order may differ in the last bits
+    L.gcrnn_debug_set_option(b'graph_capture', old)
