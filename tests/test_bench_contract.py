@@ -1,0 +1,29 @@
+"""CPU: bench.py's reference arm prints ONE JSON line with the keys the driver reads (metric, value, e2e, cpu_baseline, ...)."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reference_arm_json_contract():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '1',
+                          '--cpu-batch', '1', '--cpu-T', '1'], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith('{')]
+    assert len(lines) == 1, out.stdout
+    d = json.loads(lines[0])
+    assert d['impl'] == 'reference' and d['metric'] == 'GCRNN sequences/sec fwd+bwd' and d['unit'] == 'sequences/s'
+    assert d['value'] > 0 and d['higher_is_better'] is True and d['n_gpus'] == 1
+    assert d['e2e'] == dict(value=d['value'], unit='sequences/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0)
+    cb = d['cpu_baseline']
+    assert cb['kind'] in ('reference', 'port') and cb['cores'] >= 1 and cb['value'] == d['value'] and 'sample' in cb
+    assert 'workload' in d['config']
+
+
+def test_traffic_reader_finds_committed_export():
+    sys.path.insert(0, ROOT)
+    import bench
+    t, src = bench.ncu_traffic(['r01_ncu_gemm2_mb1024.raw.csv'], 'shift_gemm2_kernel')
+    assert src is not None and 50e6 < t < 600e6

@@ -204,3 +204,36 @@ def test_tc_cell_long_horizon_contractive():
     e = [_relerr(a, b) for a, b in zip(out['bf16'], out['fp32'])]
     _log('tc-long-horizon', [f'{v:.2e}' for v in e])
     assert e[0] < 1e-2 and e[1] < 3e-2 and e[2] < 3e-2, e
+
+
+def test_tc_full_size_batch_properties():
+    """cfg3 at FULL per-sequence size (N=1024, F=64, K=5, T=64, time-gated) through size-independent properties of the
+    recurrence: every sequence is independent of its batch mates (a sample run in a batch of 48 equals the same sample
+    in a batch of 16), gradients are additive over a partition of the batch, and |h| <= 1.  The recurrence is made
+    contractive (weight_B x 0.2) so that reduction-order differences of the gate sums are not amplified over 64 steps.
+    Tolerance 2^-8 = one bf16 ulp: a 1e-7 difference in a gate (summation order depends on the batch split) occasionally flips
+    the bf16 rounding of a state element that feeds the next shift GEMM."""
+    N, F, K, T, B = 1024, 64, 5, 64, 48
+    S = gg.graphs.dense_random(N, 0.3, seed=0)
+    try:
+        cell = _make_cell(S, 1, F, K, True, 'bf16')
+        with torch.no_grad():
+            cell.weight_B.mul_(0.2)
+        torch.manual_seed(17)
+        X, h0 = torch.randn(B, T, 1, N, device=DEV), torch.zeros(B, F, N, device=DEV)
+        dH = torch.randn(B, T, F, N, device=DEV) / (T * N)
+        res = []
+        for lo, hi in ((0, B), (0, 16), (16, B)):
+            cell.zero_grad()
+            H = cell(X[lo:hi], h0[lo:hi])
+            (H * dH[lo:hi]).sum().backward()
+            res.append((H.detach(), {k: v.grad.clone() for k, v in cell.named_parameters() if v.grad is not None}))
+    finally:
+        gg.set_precision('fp32')
+    Hall, gall = res[0]
+    assert torch.isfinite(Hall).all() and Hall.abs().max() <= 1.0
+    eh = (_relerr(res[1][0], Hall[:16]), _relerr(res[2][0], Hall[16:]))
+    errs = {k: _relerr(res[1][1][k] + res[2][1][k], gall[k]) for k in gall}
+    _log('tc-full-size-additivity', eh, {k: f'{v:.2e}' for k, v in errs.items()})
+    assert max(eh) < 2 ** -8, eh
+    assert all(v < 2 ** -8 for v in errs.values()), errs
