@@ -356,7 +356,7 @@ def run_ours(args):
                    roofline=roof, cpu_baseline=cb, clocks=clocks,
                    e2e=dict(value=seqs_e2e, unit='sequences/s', h2d_bytes_per_step=int(X_host.numel() * 4 + (Bl // mb) * h0_host.numel() * 4),
                             d2h_bytes_per_step=int(sum(p.numel() for p in used) * 4), ms_per_step=ms_e2e / args.steps),
-                   gpu_launches=int(launches))
+                   gpu_launches=int(launches), peak_hbm_gb=round(torch.cuda.max_memory_allocated() / 1e9, 1))
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -551,7 +551,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=CFG3['B'], help='global batch (sequences per step); default = cfg3')
-    ap.add_argument('--microbatch', type=int, default=1024)
+    ap.add_argument('--microbatch', type=int, default=2048)
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
     ap.add_argument('--cpu-batch', type=int, default=16)
     ap.add_argument('--cpu-T', type=int, default=8)
