@@ -137,3 +137,45 @@ def test_fused_large_knn_properties():
         acc += cell.weight_B.grad
     assert relerr(acc, g_all) < 1e-4
 
+
+@pytest.mark.parametrize('N,B,T', [(2000, 3, 3), (100_000, 2, 2)])
+def test_cfg5_generator_vs_sparse_fp64_oracle(N, B, T):
+    """cfg5's own graph family (directed 16-NN, Hilbert order) at N = 2000 and at the FULL N = 100000, edge-gated,
+    F = 32, K = 3, against the sparse fp64 restatement of the reference (the dense reference cannot hold N = 1e5)."""
+    F_, K = 32, 3
+    rp, ci, va = gg.graphs.knn_csr(N, 16, seed=3, power_iters=10)
+    S = gg.graphs.csr_to_torch_sparse(rp, ci, va, N)
+    torch.manual_seed(0)
+    prev = torch.get_default_dtype(); torch.set_default_dtype(torch.float64)
+    try:
+        p = orc.init_cell_params(1, F_, K, K, N, False, 'edge', 1, True)
+    finally:
+        torch.set_default_dtype(prev)
+    X, h0, dH = torch.randn(B, T, 1, N).double(), 0.1 * torch.randn(B, F_, N).double(), torch.randn(B, T, F_, N).double()
+    Href, gref = orc.cell_forward_backward(p, [S.double().to_sparse_coo().coalesce()], X, h0, dH, False, 'edge', input_grads=True)
+    cell = gg.GGCRNNCell(1, F_, K, K, torch.tanh, False, 'edge', 1, True)
+    cell.addGSO(S)
+    cell.load_state_dict(p)
+    cell = cell.to(device=DEV, dtype=torch.float32)
+    hg = h0.float().to(DEV).requires_grad_(True)
+    H = cell(X.float().to(DEV), hg)
+    (H * dH.float().to(DEV)).sum().backward()
+    assert cell._handle(torch.device(DEV)).get_option('last_path') == PATH_NODE32
+    errs = {'H': relerr(H, Href)}
+    for k, v in cell.named_parameters():
+        if gref[k] is not None:
+            errs[k] = relerr(v.grad, gref[k])
+    # dh0 is compared element-wise.  relu / leaky_relu have kinks: with 6.4e6 outputs and 6.8e6 attention edges at N = 1e5 a handful
+    # of pre-activations land within fp32 rounding of 0, where fp32 and fp64 legitimately pick different one-sided derivatives;
+    # each such event perturbs the gradient in one 2-hop neighbourhood (a few hundred elements, one tight cluster of node indices
+    # - tools/dbg_cfg5_parity.py prints them) and shifts the parameter gradients, which sum over all nodes, by ~1e-3 of their scale.
+    # So: all but 1e-3 of the dh0 elements must meet the 1e-4 bound, and at full size the parameter gradients get 2e-3.
+    ref = gref['__h0']
+    d = (hg.grad.detach().cpu().double() - ref).abs() / ref.abs().max()
+    frac_bad = float((d > TOL_GRAD).double().mean())
+    errs['dh0_frac_above_tol'] = frac_bad
+    tol_g = TOL_GRAD if N <= 2000 else 2e-3
+    assert errs['H'] < TOL_OUT, errs
+    assert frac_bad < (1e-9 if N <= 2000 else 1e-3), errs
+    bad = {k: v for k, v in errs.items() if k not in ('H', 'dh0_frac_above_tol') and v > tol_g}
+    assert not bad, errs
