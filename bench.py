@@ -560,8 +560,15 @@ def main():
     ap.add_argument('--bwd-fused', type=int, default=None, help='A/B switch: 1 = fused reverse-time step kernel, 0 = separate kernels')
     ap.add_argument('--workload', default='cfg3', choices=['cfg3', 'cfg5', 'cfg1', 'cfg2-node', 'cfg2-edge'],
                     help='cfg3 = the headline dense config; cfg5 = sparse kNN graph; cfg1 / cfg2-* = the small reference configurations')
+    ap.add_argument('--opt', action='append', default=[], metavar='NAME=VALUE',
+                    help='library debug option (gcrnn_debug_set_option), e.g. sparse_v2=0 for the first-generation sparse kernels')
     ap.add_argument('--once', action='store_true', help='run one micro-batch forward+backward and exit (for ncu captures)')
     args = ap.parse_args()
+    if args.opt and args.impl != 'reference':
+        from gated_gcrnns_b200 import _lib
+        for kv in args.opt:
+            name, value = kv.split('=')
+            assert _lib.lib().gcrnn_debug_set_option(name.encode(), int(value)) != -1 or int(value) == -1, f'unknown option {name}'
     if args.impl == 'reference':
         run_reference(args)
     elif args.workload == 'cfg5':

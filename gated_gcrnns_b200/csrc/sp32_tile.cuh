@@ -1,0 +1,536 @@
+// Second generation of the fused fp32 kernels of the sparse EDGE-GATED recurrence (F == 32, cfg5 of SURVEY.md §8d).
+// Same algebra, same HBM arrays and the same accumulator layout as sp32_kernels.cuh (which stays selectable through
+// gcrnn_debug_set_option("sparse_v2", mask) for A/B tests); what changes is the work decomposition, chosen from the ncu
+// exports of the first generation (profiles/r01_ncu_sparse_*): those kernels were issue-bound at 330-670 warp
+// instructions per (sample, node) with 12 resident warps, not HBM-bound.
+//
+//   * Gathers: EIGHT lanes own one destination node (lane = 16-byte chunk of the 128-byte row), four nodes per warp.
+//     A neighbour row is one LDG.128 per lane with no index/value shuffles and no final reduce-scatter
+//     (~8 instructions per edge per FOUR nodes instead of ~11 per edge per node).
+//   * Contractions: a block stages a tile of 64 consecutive nodes ([64][K*32] inputs, gathered tap included) in shared
+//     memory and runs a register-tiled fp32 GEMM against weights that live in shared memory ONCE per block: a thread
+//     owns 4 nodes x 4 outputs and issues packed FFMA2 over input pairs, so no thread carries the 96 weights in
+//     registers (that is what capped the first generation at 3 blocks per SM).
+//   * Weight-gradient outer products (M_k = sum_n dWu[n] (x) z_k[n]) are the transposed GEMM of the same tile, kept in
+//     registers across all tiles of a block.
+//
+// Reference op sites (Utils/graphML.py): LSIGF shift :123 + contraction :134-139; graphAttention :586-625 with
+// S' = S + I :577, leaky_relu(0.2) :603, masked softmax over j :611-622, aggregation over i :625; relu :2101;
+// cell update h = tanh(Q_i(a) + Q_f(r)) :2402-2423.
+#pragma once
+#include "sp32_kernels.cuh"
+
+namespace gcrnn {
+namespace e32 {
+
+constexpr int TM = 64;                                  // nodes per tile
+constexpr int XS_LD = 16;                               // x taps per node in shared memory (zero padded, == MAXKG)
+constexpr int LDD = 36;                                 // row stride of the [TM][32] tiles (== 4 mod 32: conflict-free LDS.128)
+__host__ __device__ constexpr int lda_of(int kst) { return kst * 32 + 4; }
+
+struct Range { long long lo, hi; int per_sample; };
+// contiguous range of `unit`-node groups for this block (neighbouring groups share neighbour rows: L1/L2 reuse)
+__device__ __forceinline__ Range block_range(long long R, int N, int unit) {
+  const int per_sample = (N + unit - 1) / unit;
+  const long long total = R * per_sample, per = (total + gridDim.x - 1) / gridDim.x;
+  const long long lo = (long long)blockIdx.x * per;
+  return Range{lo, lo + per < total ? lo + per : total, per_sample};
+}
+__device__ __forceinline__ float4 f4zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ float4 f4add(const float4& a, const float4& b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ float gsum8(float v, unsigned gmask) {       // sum over the 8 lanes of a node group
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) v += __shfl_xor_sync(gmask, v, o);
+  return v;
+}
+// eight per-lane partial sums -> total of slot c on lane c of the 8-lane group (7 shuffles)
+template <int M>
+__device__ __forceinline__ void tree8_step(float (&v)[8], int c, unsigned gmask) {
+  const bool up = c & M;
+#pragma unroll
+  for (int k = 0; k < M; ++k) {
+    const float lo = v[k], hi = v[k + M];
+    v[k] = (up ? hi : lo) + __shfl_xor_sync(gmask, up ? lo : hi, M);
+  }
+}
+__device__ __forceinline__ float tree8(float (&v)[8], int c, unsigned gmask) {
+  tree8_step<4>(v, c, gmask); tree8_step<2>(v, c, gmask); tree8_step<1>(v, c, gmask);
+  return v[0];
+}
+
+// sum_p val[p] * src[idx[p]] for this lane's 16-byte chunk; `base` = sample base (float4 units) + chunk
+__device__ __forceinline__ float4 gather_chunk(const Gather3& op, const float4* __restrict__ base, int n) {
+  int p = __ldg(op.ptr + n);
+  const int p1 = __ldg(op.ptr + n + 1);
+  float4 a0 = f4zero(), a1 = f4zero();
+  for (; p + 4 <= p1; p += 4) {
+    const int i0 = __ldg(op.idx + p), i1 = __ldg(op.idx + p + 1), i2 = __ldg(op.idx + p + 2), i3 = __ldg(op.idx + p + 3);
+    const float v0 = __ldg(op.val + p), v1 = __ldg(op.val + p + 1), v2 = __ldg(op.val + p + 2), v3 = __ldg(op.val + p + 3);
+    const float4 x0 = __ldg(base + (size_t)i0 * 8), x1 = __ldg(base + (size_t)i1 * 8);
+    const float4 x2 = __ldg(base + (size_t)i2 * 8), x3 = __ldg(base + (size_t)i3 * 8);
+    fma4(a0, v0, x0); fma4(a1, v1, x1); fma4(a0, v2, x2); fma4(a1, v3, x3);
+  }
+  for (; p < p1; ++p) fma4(a0, __ldg(op.val + p), __ldg(base + (size_t)__ldg(op.idx + p) * 8));
+  return f4add(a0, a1);
+}
+
+// ---- sparse shift of a 32-channel node-major signal: out[r,d,:] = sum_p val[p] in[r, idx[p], :] ----------------
+__global__ void __launch_bounds__(256, 6) spmm32_v2_k(Gather3 op, const float* __restrict__ in, float* __restrict__ out, int N, long long R) {
+  const int c = threadIdx.x & 7, slot = threadIdx.x >> 3;
+  const Range rg = block_range(R, N, 32);
+  for (long long g = rg.lo; g < rg.hi; ++g) {
+    const long long r = g / rg.per_sample;
+    const int n = (int)(g - r * rg.per_sample) * 32 + slot;
+    if (n >= N) continue;
+    const size_t rb = (size_t)r * N;
+    const float4 a = gather_chunk(op, reinterpret_cast<const float4*>(in + rb * 32) + c, n);
+    reinterpret_cast<float4*>(out + (rb + n) * 32)[c] = a;
+  }
+}
+
+// ---- tile staging helpers (128-thread blocks) --------------------------------------------------------------------
+// rows n0 .. n0+63 of a [R,N,32] array -> tile[node][col0 .. col0+31]  (zero rows beyond N)
+__device__ __forceinline__ void stage_rows(float* tile, int ld, int col0, const float* __restrict__ src, size_t rb, int n0, int N) {
+  const float4* s4 = reinterpret_cast<const float4*>(src + (rb + n0) * 32);
+  float4 v[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int idx = threadIdx.x + 128 * q;
+    v[q] = (n0 + (idx >> 3) < N) ? __ldg(s4 + idx) : f4zero();
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int idx = threadIdx.x + 128 * q;
+    *reinterpret_cast<float4*>(tile + (idx >> 3) * ld + col0 + (idx & 7) * 4) = v[q];
+  }
+}
+// gathered rows (src S)[n0 .. n0+63] -> tile[node][col0 .. col0+31]
+__device__ __forceinline__ void stage_gather(float* tile, int ld, int col0, const Gather3& op, const float* __restrict__ src, size_t rb, int n0, int N) {
+  const int c = threadIdx.x & 7;
+  const float4* base = reinterpret_cast<const float4*>(src + rb * 32) + c;
+#pragma unroll 1
+  for (int q = 0; q < 4; ++q) {
+    const int node = (threadIdx.x >> 3) + 16 * q;
+    float4 a = f4zero();
+    if (n0 + node < N) a = gather_chunk(op, base, n0 + node);
+    *reinterpret_cast<float4*>(tile + node * ld + col0 + c * 4) = a;
+  }
+}
+// x taps of the tile's nodes -> Xs[node][kg], kg = k * G + g, zero padded to XS_LD
+__device__ __forceinline__ void stage_taps(float* Xs, const Chain& xs, int KG, int G, size_t rb, int n0, int N) {
+  for (int idx = threadIdx.x; idx < TM * XS_LD; idx += 128) {
+    const int node = idx >> 4, kg = idx & 15;
+    float v = 0.f;
+    if (kg < KG && n0 + node < N) {
+      const int k = kg / G, g = kg - k * G;
+      const float* xp = xs.p[0];
+#pragma unroll
+      for (int m = 1; m < MAXK; ++m) if (k == m) xp = xs.p[m];
+      v = __ldg(xp + (rb + n0 + node) * G + g);
+    }
+    Xs[idx] = v;
+  }
+}
+// weights w[kk][f] (kk < KK inputs, 32 outputs) -> shared "pair" layout: float4 ((kp*2 + half)*8 + fg) =
+// (w[2kp][f0], w[2kp+1][f0], w[2kp][f0+1], w[2kp+1][f0+1]),  f0 = 4 fg + 2 half
+template <class W>
+__device__ __forceinline__ void stage_weights(float* Ws, int KK, W w) {
+  for (int o = threadIdx.x; o < KK * 32; o += 128) {
+    const int q = o & 3, fg = (o >> 2) & 7, half = (o >> 5) & 1, kp = o >> 6;
+    Ws[o] = w(2 * kp + (q & 1), 4 * fg + 2 * half + (q >> 1));
+  }
+}
+// o[i][j] = sum_kk tile[warp*16 + ngl + 4i][kk] * w[kk][4 fg + j]   (thread = 4 nodes x 4 outputs, FFMA2 over input pairs)
+template <int KK>
+__device__ __forceinline__ void tile_contract(const float* __restrict__ tile, int ld, const float* __restrict__ Ws, float (&o)[4][4]) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, fg = lane & 7, ngl = lane >> 3;
+  const float* arow = tile + (warp * 16 + ngl) * ld;
+  const float4* wp = reinterpret_cast<const float4*>(Ws) + fg;
+  float2 acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = make_float2(0.f, 0.f);
+#pragma unroll 2
+  for (int kq = 0; kq < KK / 4; ++kq) {
+    float4 a[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const float4*>(arow + 4 * i * ld + 4 * kq);
+    const float4 w00 = wp[(4 * kq + 0) * 8], w01 = wp[(4 * kq + 1) * 8], w10 = wp[(4 * kq + 2) * 8], w11 = wp[(4 * kq + 3) * 8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 lo = make_float2(a[i].x, a[i].y), hi = make_float2(a[i].z, a[i].w);
+      acc[i][0] = __ffma2_rn(make_float2(w00.x, w00.y), lo, acc[i][0]);
+      acc[i][1] = __ffma2_rn(make_float2(w00.z, w00.w), lo, acc[i][1]);
+      acc[i][2] = __ffma2_rn(make_float2(w01.x, w01.y), lo, acc[i][2]);
+      acc[i][3] = __ffma2_rn(make_float2(w01.z, w01.w), lo, acc[i][3]);
+      acc[i][0] = __ffma2_rn(make_float2(w10.x, w10.y), hi, acc[i][0]);
+      acc[i][1] = __ffma2_rn(make_float2(w10.z, w10.w), hi, acc[i][1]);
+      acc[i][2] = __ffma2_rn(make_float2(w11.x, w11.y), hi, acc[i][2]);
+      acc[i][3] = __ffma2_rn(make_float2(w11.z, w11.w), hi, acc[i][3]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[i][j] = acc[i][j].x + acc[i][j].y;
+}
+
+// ---- gather + contraction over a tile -----------------------------------------------------------------------------
+// GC_FILTER (forward stage 1): Wu_r = sum_k Cr_k z_k + cr0 (z_{KST-1} = z_{KST-2} S gathered into the tile),
+//   Wu_a = Ca x-taps + ca0, rc = (a1.Wu_a, a2.Wu_a, a1.Wu_r, a2.Wu_r);  weights from the folded `prep` block.
+// GC_DH (backward stage 3): dh_{t-1}[n,g] = sum_k sum_f B[f,k,g] w_k[n,f], w_{KST-1} = w_{KST-2} S^T gathered into the tile.
+enum { GC_FILTER = 0, GC_DH = 1 };
+template <int KST>
+__host__ __device__ constexpr int gc_smem_floats(int mode) {
+  return KST * 32 * 32 + TM * lda_of(KST) + (mode == GC_FILTER ? TM * XS_LD + MAXKG * 32 : 0);
+}
+template <int KST, int MODE>
+__global__ void __launch_bounds__(128, 4) gather_contract_k(Gather3 gop, Chain zc, Chain xs, int Kin, int G,
+                                                            const float* __restrict__ wsrc /* FILTER: prep, DH: weight_B */,
+                                                            const float* __restrict__ mix_a, const float* __restrict__ mix_r,
+                                                            float* __restrict__ out_a /* FILTER: Wu_a */, float* __restrict__ out /* FILTER: Wu_r, DH: dh */,
+                                                            float4* __restrict__ rc, int N, long long R) {
+  constexpr int KK = KST * 32, LDA = lda_of(KST), NS = KST - 1;
+  extern __shared__ __align__(16) float dyn[];
+  float* Ws = dyn;                       // [KK/2][2][8] float4
+  float* As = Ws + KK * 32;              // [TM][LDA]
+  float* Xs = As + TM * LDA;             // FILTER: [TM][XS_LD]
+  float* Cas = Xs + TM * XS_LD;          // FILTER: [MAXKG][32]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, fg = lane & 7, ngl = lane >> 3;
+  const int KG = Kin * G;
+  if (MODE == GC_FILTER) {
+    stage_weights(Ws, KK, [&](int kk, int f) { return wsrc[PrepLayout::CR + kk * 32 + f]; });
+    for (int i = threadIdx.x; i < MAXKG * 32; i += 128) Cas[i] = wsrc[PrepLayout::CA + i];
+  } else {
+    stage_weights(Ws, KK, [&](int kk, int f) { return wsrc[(kk & 31) * KK + (kk >> 5) * 32 + f]; });   // B[f_in, k, g_out]
+  }
+  float4 c0r = f4zero(), c0a = f4zero(), a1a = f4zero(), a2a = f4zero(), a1r = f4zero(), a2r = f4zero();
+  if (MODE == GC_FILTER) {
+    c0r = *reinterpret_cast<const float4*>(wsrc + PrepLayout::CR0 + 4 * fg);
+    c0a = *reinterpret_cast<const float4*>(wsrc + PrepLayout::CA0 + 4 * fg);
+    a1a = *reinterpret_cast<const float4*>(mix_a + 4 * fg); a2a = *reinterpret_cast<const float4*>(mix_a + 32 + 4 * fg);
+    a1r = *reinterpret_cast<const float4*>(mix_r + 4 * fg); a2r = *reinterpret_cast<const float4*>(mix_r + 32 + 4 * fg);
+  }
+  const Range rg = block_range(R, N, TM);
+  for (long long tile = rg.lo; tile < rg.hi; ++tile) {
+    const long long r = tile / rg.per_sample;
+    const int n0 = (int)(tile - r * rg.per_sample) * TM;
+    const size_t rb = (size_t)r * N;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) stage_rows(As, LDA, s * 32, zc.p[s], rb, n0, N);
+    if (MODE == GC_FILTER) stage_taps(Xs, xs, KG, G, rb, n0, N);
+    stage_gather(As, LDA, NS * 32, gop, zc.p[NS - 1], rb, n0, N);
+    __syncthreads();
+    float o[4][4];
+    tile_contract<KK>(As, LDA, Ws, o);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int node = warp * 16 + ngl + 4 * i, n = n0 + node;
+      if (MODE == GC_FILTER) {
+        const float4 wr = make_float4(o[i][0] + c0r.x, o[i][1] + c0r.y, o[i][2] + c0r.z, o[i][3] + c0r.w);
+        float4 wa = c0a;
+        for (int kg = 0; kg < KG; ++kg) fma4(wa, Xs[node * XS_LD + kg], *reinterpret_cast<const float4*>(Cas + kg * 32 + 4 * fg));
+        float s1 = dot4(a1a, wa), s2 = dot4(a2a, wa), s3 = dot4(a1r, wr), s4 = dot4(a2r, wr);
+#pragma unroll
+        for (int of = 4; of > 0; of >>= 1) {
+          s1 += __shfl_xor_sync(0xffffffffu, s1, of); s2 += __shfl_xor_sync(0xffffffffu, s2, of);
+          s3 += __shfl_xor_sync(0xffffffffu, s3, of); s4 += __shfl_xor_sync(0xffffffffu, s4, of);
+        }
+        if (n < N) {
+          reinterpret_cast<float4*>(out_a + (rb + n) * 32)[fg] = wa;
+          reinterpret_cast<float4*>(out + (rb + n) * 32)[fg] = wr;
+          if (fg == 0) rc[rb + n] = make_float4(s1, s2, s3, s4);
+        }
+      } else if (n < N) {
+        reinterpret_cast<float4*>(out + (rb + n) * 32)[fg] = make_float4(o[i][0], o[i][1], o[i][2], o[i][3]);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---- forward, stage 3: attention aggregation of both gates + relu + tanh update -----------------------------------
+// y_g[j,:] = relu( sum_{i -> j} S'_ij alpha^g_ij Wu_g[i,:] ),  h = tanh(y_a + y_r);  masks = sign bits of the two relus
+// (bit 8 i + c of a mask word belongs to feature 4 c + i, the layout dpre_k reads).  Eight lanes per destination j: lane c
+// computes alpha S' of edge (batch + c) once, the group then walks the batch with width-8 shuffles.
+__global__ void __launch_bounds__(256, 4) aggregate_v2_k(const int* __restrict__ cptr, const int* __restrict__ crow, const float* __restrict__ cval,
+                                                         const float4* __restrict__ info, const float* __restrict__ wu_a, const float* __restrict__ wu_r,
+                                                         float* __restrict__ hn, uint2* __restrict__ masks, int N, long long R) {
+  const int lane = threadIdx.x & 31, c = threadIdx.x & 7, slot = threadIdx.x >> 3;
+  const unsigned gmask = 0xFFu << (lane & 24);
+  const Range rg = block_range(R, N, 32);
+  for (long long g = rg.lo; g < rg.hi; ++g) {
+    const long long r = g / rg.per_sample;
+    const int j = (int)(g - r * rg.per_sample) * 32 + slot;
+    if (j >= N) continue;                                       // uniform within the 8-lane group
+    const size_t rb = (size_t)r * N;
+    const int p0 = __ldg(cptr + j), p1 = __ldg(cptr + j + 1);
+    const float rja = info[2 * (rb + j)].x, rjr = info[2 * (rb + j) + 1].x;
+    const float4* pa = reinterpret_cast<const float4*>(wu_a + rb * 32) + c;
+    const float4* pr = reinterpret_cast<const float4*>(wu_r + rb * 32) + c;
+    float4 acc_a = f4zero(), acc_r = f4zero();
+    for (int pb = p0; pb < p1; pb += 8) {
+      const int cnt = min(8, p1 - pb);
+      int mi = 0; float ca = 0.f, cr = 0.f;                     // idle lanes: row 0 of the sample with coefficient 0
+      if (c < cnt) {
+        mi = __ldg(crow + pb + c);
+        const float v = __ldg(cval + pb + c);
+        const float4 sa = info[2 * (rb + mi)], sr = info[2 * (rb + mi) + 1];
+        ca = v * (__expf(leaky(sa.y + rja) - sa.z) * sa.w);
+        cr = v * (__expf(leaky(sr.y + rjr) - sr.z) * sr.w);
+      }
+#pragma unroll
+      for (int e0 = 0; e0 < 8; e0 += 4) {
+        if (e0 < cnt) {                                         // group-uniform; four edges in flight
+          int ii[4]; float wa[4], wr[4]; float4 xa[4], xr[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            ii[u] = __shfl_sync(gmask, mi, e0 + u, 8);
+            wa[u] = __shfl_sync(gmask, ca, e0 + u, 8); wr[u] = __shfl_sync(gmask, cr, e0 + u, 8);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) { xa[u] = __ldg(pa + (size_t)ii[u] * 8); xr[u] = __ldg(pr + (size_t)ii[u] * 8); }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) { fma4(acc_a, wa[u], xa[u]); fma4(acc_r, wr[u], xr[u]); }
+        }
+      }
+    }
+    unsigned ma = (acc_a.x > 0.f ? 1u : 0u) | (acc_a.y > 0.f ? 0x100u : 0u) | (acc_a.z > 0.f ? 0x10000u : 0u) | (acc_a.w > 0.f ? 0x1000000u : 0u);
+    unsigned mr = (acc_r.x > 0.f ? 1u : 0u) | (acc_r.y > 0.f ? 0x100u : 0u) | (acc_r.z > 0.f ? 0x10000u : 0u) | (acc_r.w > 0.f ? 0x1000000u : 0u);
+    ma = __reduce_or_sync(gmask, ma << c); mr = __reduce_or_sync(gmask, mr << c);
+    float4 h;
+    h.x = tanh_pos(fmaxf(acc_a.x, 0.f) + fmaxf(acc_r.x, 0.f)); h.y = tanh_pos(fmaxf(acc_a.y, 0.f) + fmaxf(acc_r.y, 0.f));
+    h.z = tanh_pos(fmaxf(acc_a.z, 0.f) + fmaxf(acc_r.z, 0.f)); h.w = tanh_pos(fmaxf(acc_a.w, 0.f) + fmaxf(acc_r.w, 0.f));
+    reinterpret_cast<float4*>(hn + (rb + j) * 32)[c] = h;
+    if (c == 0) masks[rb + j] = make_uint2(ma, mr);
+  }
+}
+
+// ---- backward, stage 1 (per source row i, both gates): softmax / leaky backward, partial dWu ---------------------------
+//   al_ij = softmax_j(leaky(c_i + r_j)),  dal_ij = S'_ij <dy_g[j], Wu_g[i]>,  ds_ij = al (dal - sum_j al dal) leaky',
+//   dr_j += ds_ij (atomics), dc_i = sum_j ds_ij,  p_g[i,:] = sum_j S'_ij al_ij dy_g[j,:] + a2_g dc_i,  m2_g += dc_i Wu_g[i,:]
+// Eight lanes per row; lane c keeps the edge data of edges c, 8 + c, 16 + c, 24 + c (row degree of S + I <= 32); the
+// eight dot products of a batch are reduced "transposed" (7 shuffles) so that edge (batch + c) lands on lane c.
+__global__ void __launch_bounds__(256, 2) bwd_rows_v2_k(const int* __restrict__ rptr, const int* __restrict__ col, const float* __restrict__ val,
+                                                        const float4* __restrict__ info, const float* __restrict__ wu_a, const float* __restrict__ wu_r,
+                                                        const float* __restrict__ dya, const float* __restrict__ dyr,
+                                                        const float* __restrict__ mix_a, const float* __restrict__ mix_r,
+                                                        float* __restrict__ pa, float* __restrict__ pr, float2* __restrict__ dr /* [R*N], zeroed */,
+                                                        float* __restrict__ acc, int N, long long R) {
+  __shared__ float red[8][64];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, c = threadIdx.x & 7, slot = threadIdx.x >> 3;
+  const unsigned gmask = 0xFFu << (lane & 24);
+  const float4 a2a = *reinterpret_cast<const float4*>(mix_a + 32 + 4 * c), a2r = *reinterpret_cast<const float4*>(mix_r + 32 + 4 * c);
+  float4 m2a = f4zero(), m2r = f4zero();
+  const Range rg = block_range(R, N, 32);
+  for (long long g = rg.lo; g < rg.hi; ++g) {
+    const long long r = g / rg.per_sample;
+    const int i = (int)(g - r * rg.per_sample) * 32 + slot;
+    if (i >= N) continue;                                       // uniform within the 8-lane group
+    const size_t rb = (size_t)r * N;
+    const int p0 = __ldg(rptr + i), deg = __ldg(rptr + i + 1) - p0;
+    const float4 mine_a = info[2 * (rb + i)], mine_r = info[2 * (rb + i) + 1];
+    const float4 wua = reinterpret_cast<const float4*>(wu_a + (rb + i) * 32)[c], wur = reinterpret_cast<const float4*>(wu_r + (rb + i) * 32)[c];
+    const float4* ga = reinterpret_cast<const float4*>(dya + rb * 32) + c;
+    const float4* gr = reinterpret_cast<const float4*>(dyr + rb * 32) + c;
+    float4 parta = f4zero(), partr = f4zero();
+    float tSa = 0.f, tSr = 0.f;
+    int jj[4]; float ala[4], alr[4], dala[4], dalr[4], sla[4], slr[4];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      jj[b] = 0; ala[b] = alr[b] = dala[b] = dalr[b] = sla[b] = slr[b] = 0.f;
+      if (8 * b < deg) {                                        // group-uniform
+        const int cnt = min(8, deg - 8 * b);
+        float v = 0.f, coa = 0.f, cor = 0.f;
+        if (c < cnt) {
+          jj[b] = __ldg(col + p0 + 8 * b + c);
+          v = __ldg(val + p0 + 8 * b + c);
+          const float sca = mine_a.y + info[2 * (rb + jj[b])].x, scr = mine_r.y + info[2 * (rb + jj[b]) + 1].x;
+          ala[b] = __expf(leaky(sca) - mine_a.z) * mine_a.w; sla[b] = sca > 0.f ? 1.f : 0.2f;
+          alr[b] = __expf(leaky(scr) - mine_r.z) * mine_r.w; slr[b] = scr > 0.f ? 1.f : 0.2f;
+          coa = v * ala[b]; cor = v * alr[b];
+        }
+        float pda[8], pdr[8];
+#pragma unroll
+        for (int e0 = 0; e0 < 8; e0 += 4) {
+          if (e0 < cnt) {                                       // group-uniform; idle edges: row 0 with coefficient 0
+            int ii[4]; float wa[4], wr[4]; float4 xa[4], xr[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              ii[u] = __shfl_sync(gmask, jj[b], e0 + u, 8);
+              wa[u] = __shfl_sync(gmask, coa, e0 + u, 8); wr[u] = __shfl_sync(gmask, cor, e0 + u, 8);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { xa[u] = __ldg(ga + (size_t)ii[u] * 8); xr[u] = __ldg(gr + (size_t)ii[u] * 8); }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              fma4(parta, wa[u], xa[u]); fma4(partr, wr[u], xr[u]);
+              pda[e0 + u] = dot4(xa[u], wua); pdr[e0 + u] = dot4(xr[u], wur);
+            }
+          } else {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { pda[e0 + u] = 0.f; pdr[e0 + u] = 0.f; }
+          }
+        }
+        dala[b] = v * tree8(pda, c, gmask); dalr[b] = v * tree8(pdr, c, gmask);     // v == 0 on idle lanes
+        tSa = fmaf(ala[b], dala[b], tSa); tSr = fmaf(alr[b], dalr[b], tSr);
+      }
+    }
+    const float Sa = gsum8(tSa, gmask), Sr = gsum8(tSr, gmask);
+    float dca = 0.f, dcr = 0.f;
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+      if (8 * b + c < deg) {
+        const float dsa = ala[b] * (dala[b] - Sa) * sla[b], dsr = alr[b] * (dalr[b] - Sr) * slr[b];
+        atomicAdd(dr + rb + jj[b], make_float2(dsa, dsr));
+        dca += dsa; dcr += dsr;
+      }
+    dca = gsum8(dca, gmask); dcr = gsum8(dcr, gmask);
+    fma4(parta, dca, a2a); fma4(partr, dcr, a2r);
+    reinterpret_cast<float4*>(pa + (rb + i) * 32)[c] = parta;
+    reinterpret_cast<float4*>(pr + (rb + i) * 32)[c] = partr;
+    fma4(m2a, dca, wua); fma4(m2r, dcr, wur);
+  }
+  // lanes c, c+8, c+16, c+24 of a warp hold the same features
+  float m[8] = {m2a.x, m2a.y, m2a.z, m2a.w, m2r.x, m2r.y, m2r.z, m2r.w};
+#pragma unroll
+  for (int q = 0; q < 8; ++q) { m[q] += __shfl_xor_sync(0xffffffffu, m[q], 8); m[q] += __shfl_xor_sync(0xffffffffu, m[q], 16); }
+  if (lane < 8) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { red[warp][4 * lane + q] = m[q]; red[warp][32 + 4 * lane + q] = m[4 + q]; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += red[k][threadIdx.x];
+    atomicAdd(acc + (threadIdx.x < 32 ? AccLayout::M2A + threadIdx.x : AccLayout::M2R + threadIdx.x - 32), s);
+  }
+}
+
+// ---- backward, stage 2 (per tile): finish dWu, accumulate the outer products, d = W_r^T dWu_r ----------------------------
+//   dWu_g[n,:] = p_g[n,:] + a1_g dr_g[n];  m1_g += dr_g[n] Wu_g[n,:];  sum_g += dWu_g[n,:]
+//   M_k[f][g] += dWu_r[n,f] z_k[n,g] (z_{KST-1} gathered into the tile);  Ma[kg][f] += dWu_a[n,f] x[n,kg];  dout[n,:] = W_r^T dWu_r[n,:]
+template <int KST>
+__host__ __device__ constexpr int bwd_node_smem_floats() { return 32 * 32 + TM * lda_of(KST) + 2 * TM * LDD + TM * XS_LD; }
+template <int KST>
+__global__ void __launch_bounds__(128, 3) bwd_node_v2_k(Gather3 gop, Chain zc, Chain xs, int Kin, int G,
+                                                        const float* __restrict__ pa, const float* __restrict__ pr, const float2* __restrict__ dr,
+                                                        const float* __restrict__ wu_a, const float* __restrict__ wu_r,
+                                                        const float* __restrict__ mix_a, const float* __restrict__ mix_r, const float* __restrict__ Wr,
+                                                        float* __restrict__ dout, float* __restrict__ acc, int N, long long R) {
+  constexpr int KK = KST * 32, LDA = lda_of(KST), NS = KST - 1;
+  constexpr int KPT = KK / 16;                 // z columns per thread in the outer-product stage (pairs: KST float2)
+  extern __shared__ __align__(16) float dyn[];
+  float* Ws = dyn;                             // W_r in pair layout (32 inputs f, 32 outputs m)
+  float* As = Ws + 32 * 32;                    // [TM][LDA]  z_0 .. z_{KST-1}
+  float* Ds = As + TM * LDA;                   // [TM][LDD]  dWu_r
+  float* Da = Ds + TM * LDD;                   // [TM][LDD]  dWu_a
+  float* Xs = Da + TM * LDD;                   // [TM][XS_LD]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, fg = lane & 7, ngl = lane >> 3;
+  const int c = threadIdx.x & 7;
+  const int KG = Kin * G;
+  stage_weights(Ws, 32, [&](int f, int m) { return Wr[f * 32 + m]; });
+  const float4 a1a = *reinterpret_cast<const float4*>(mix_a + 4 * c), a1r = *reinterpret_cast<const float4*>(mix_r + 4 * c);
+  float4 m1a = f4zero(), m1r = f4zero();
+  float2 M[4][KST];                            // M[fi][u]: f = 4 ft + fi, kk = KPT kt + 2u (+1)
+#pragma unroll
+  for (int fi = 0; fi < 4; ++fi)
+#pragma unroll
+    for (int u = 0; u < KST; ++u) M[fi][u] = make_float2(0.f, 0.f);
+  float Ma[MAXKG];
+#pragma unroll
+  for (int i = 0; i < MAXKG; ++i) Ma[i] = 0.f;
+  float suma = 0.f, sumr = 0.f;
+  const int ft = threadIdx.x & 7, kt = threadIdx.x >> 3;
+  const Range rg = block_range(R, N, TM);
+  for (long long tile = rg.lo; tile < rg.hi; ++tile) {
+    const long long r = tile / rg.per_sample;
+    const int n0 = (int)(tile - r * rg.per_sample) * TM;
+    const size_t rb = (size_t)r * N;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) stage_rows(As, LDA, s * 32, zc.p[s], rb, n0, N);
+    stage_taps(Xs, xs, KG, G, rb, n0, N);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {                // finish dWu of both gates for (node, chunk c)
+      const int node = (threadIdx.x >> 3) + 16 * q, n = n0 + node;
+      float4 dwa = f4zero(), dwr = f4zero();
+      if (n < N) {
+        const size_t o = (rb + n) * 8 + c;
+        const float2 d2 = dr[rb + n];
+        dwa = __ldg(reinterpret_cast<const float4*>(pa) + o); dwr = __ldg(reinterpret_cast<const float4*>(pr) + o);
+        fma4(dwa, d2.x, a1a); fma4(dwr, d2.y, a1r);
+        fma4(m1a, d2.x, __ldg(reinterpret_cast<const float4*>(wu_a) + o)); fma4(m1r, d2.y, __ldg(reinterpret_cast<const float4*>(wu_r) + o));
+      }
+      *reinterpret_cast<float4*>(Da + node * LDD + 4 * c) = dwa;
+      *reinterpret_cast<float4*>(Ds + node * LDD + 4 * c) = dwr;
+    }
+    stage_gather(As, LDA, NS * 32, gop, zc.p[NS - 1], rb, n0, N);
+    __syncthreads();
+    {                                            // d = W_r^T dWu_r
+      float o[4][4];
+      tile_contract<32>(Ds, LDD, Ws, o);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int n = n0 + warp * 16 + ngl + 4 * i;
+        if (n < N) reinterpret_cast<float4*>(dout + (rb + n) * 32)[fg] = make_float4(o[i][0], o[i][1], o[i][2], o[i][3]);
+      }
+    }
+    {                                            // outer products: thread = 4 outputs f x KPT inputs kk, reduction over the tile's nodes
+      const float* dp = Ds + 4 * ft;
+      const float* zp = As + KPT * kt;
+#pragma unroll 4
+      for (int node = 0; node < TM; ++node) {
+        const float4 d4 = *reinterpret_cast<const float4*>(dp + node * LDD);
+#pragma unroll
+        for (int u = 0; u < KST; ++u) {
+          const float2 z2 = *reinterpret_cast<const float2*>(zp + node * LDA + 2 * u);
+          M[0][u] = __ffma2_rn(make_float2(d4.x, d4.x), z2, M[0][u]);
+          M[1][u] = __ffma2_rn(make_float2(d4.y, d4.y), z2, M[1][u]);
+          M[2][u] = __ffma2_rn(make_float2(d4.z, d4.z), z2, M[2][u]);
+          M[3][u] = __ffma2_rn(make_float2(d4.w, d4.w), z2, M[3][u]);
+        }
+      }
+    }
+    {                                            // input-tap outer products and column sums: thread = feature `lane`, 16 nodes of the warp
+#pragma unroll 4
+      for (int q = 0; q < 16; ++q) {
+        const int node = warp * 16 + q;
+        const float da = Da[node * LDD + lane];
+        suma += da; sumr += Ds[node * LDD + lane];
+#pragma unroll
+        for (int kg = 0; kg < MAXKG; kg += 4)
+          if (kg < KG) {
+            const float4 x4 = *reinterpret_cast<const float4*>(Xs + node * XS_LD + kg);
+            Ma[kg] = fmaf(da, x4.x, Ma[kg]); Ma[kg + 1] = fmaf(da, x4.y, Ma[kg + 1]);
+            Ma[kg + 2] = fmaf(da, x4.z, Ma[kg + 2]); Ma[kg + 3] = fmaf(da, x4.w, Ma[kg + 3]);
+          }
+      }
+    }
+    __syncthreads();
+  }
+  // every thread owns distinct M entries of the block: one global atomic per entry per block
+#pragma unroll
+  for (int fi = 0; fi < 4; ++fi)
+#pragma unroll
+    for (int u = 0; u < KST; ++u) {
+      const int kk = KPT * kt + 2 * u, f = 4 * ft + fi;
+      atomicAdd(acc + AccLayout::M + kk * 32 + f, M[fi][u].x);
+      atomicAdd(acc + AccLayout::M + (kk + 1) * 32 + f, M[fi][u].y);
+    }
+#pragma unroll
+  for (int kg = 0; kg < MAXKG; ++kg)
+    if (kg < KG) atomicAdd(acc + AccLayout::MA + kg * 32 + lane, Ma[kg]);
+  atomicAdd(acc + AccLayout::SUMA + lane, suma); atomicAdd(acc + AccLayout::SUMR + lane, sumr);
+  float m[8] = {m1a.x, m1a.y, m1a.z, m1a.w, m1r.x, m1r.y, m1r.z, m1r.w};
+#pragma unroll
+  for (int q = 0; q < 8; ++q) { m[q] += __shfl_xor_sync(0xffffffffu, m[q], 8); m[q] += __shfl_xor_sync(0xffffffffu, m[q], 16); }
+  if (lane < 8) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { atomicAdd(acc + AccLayout::M1A + 4 * lane + q, m[q]); atomicAdd(acc + AccLayout::M1R + 4 * lane + q, m[4 + q]); }
+  }
+}
+
+}  // namespace e32
+}  // namespace gcrnn

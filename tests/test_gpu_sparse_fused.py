@@ -95,6 +95,34 @@ def test_fused_edge32_vs_oracle(G_, Kin, Kst, bias):
     assert launches < 5 * (10 + 2 * (Kst - 2)) + 12 + 2 * Kin, f'the fused kernels did not run ({launches} launches)'
 
 
+@pytest.mark.parametrize('mask', [0, 1, 2, 4, 8, 16, 32])
+def test_fused_stage_generations_vs_oracle(mask):
+    """The fused path has two generations of every stage (sp32_kernels.cuh: warp per node; sp32_tile.cuh: 8 lanes per node +
+    shared-memory tile contractions).  The default (all second generation, mask 63) is what every other test here runs; this one
+    holds each stage's second-generation kernel ALONE (bits: 1 spmm, 2 filter, 4 aggregate, 8 bwd_rows, 16 bwd_node, 32 dh) and the
+    all-first-generation path (0) to the same oracle bounds, on a graph whose N is not a multiple of the tile size."""
+    L = _lib.lib()
+    old = L.gcrnn_debug_set_option(b'sparse_v2', mask)
+    try:
+        run_case(N=203, G_=2, Kin=3, Kst=3, T=4, B=3, bias=True, seed=21, expect_path=PATH_NODE32)
+        if mask in (2, 16, 32):
+            run_case(N=97, G_=1, Kin=2, Kst=4, T=3, B=2, bias=True, seed=22, expect_path=PATH_NODE32)
+            run_case(N=131, G_=3, Kin=4, Kst=2, T=3, B=2, bias=False, seed=23, expect_path=PATH_NODE32)
+    finally:
+        L.gcrnn_debug_set_option(b'sparse_v2', old)
+
+
+@pytest.mark.parametrize('bps', [1, 2, 4])
+def test_fused_tile_kernels_any_residency(bps):
+    """Results must not depend on how many tile-kernel blocks share an SM (grid size / shared-memory carve-out option)."""
+    L = _lib.lib()
+    old = L.gcrnn_debug_set_option(b'sparse_v2_bps', bps)
+    try:
+        run_case(N=300, G_=1, Kin=3, Kst=3, T=3, B=2, bias=True, seed=31, expect_path=PATH_NODE32)
+    finally:
+        L.gcrnn_debug_set_option(b'sparse_v2_bps', old)
+
+
 def test_fused_matches_generic_kernels_and_falls_back_for_dX():
     L = _lib.lib()
     old = L.gcrnn_debug_set_option(b'sparse_fused', 0)
