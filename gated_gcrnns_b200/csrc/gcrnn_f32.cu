@@ -423,15 +423,21 @@ int tile_grid(K kernel, int block, size_t dyn_smem, int blocks_per_sm, long long
   return (int)std::max<long long>(1, std::min<long long>((long long)sm_count() * occ, units));
 }
 enum { V2_SPMM = 1, V2_FILTER = 2, V2_AGG = 4, V2_ROWS = 8, V2_NODE = 16, V2_DH = 32 };
-inline bool v2(int bit) { return (g_opt_sparse_v2 & bit) != 0; }
+// the aggregate and bwd_rows stages share the layout of the saved softmax statistics: they switch generation together
+inline bool v2(int bit) {
+  int m = g_opt_sparse_v2;
+  if ((m & (V2_AGG | V2_ROWS)) != (V2_AGG | V2_ROWS)) m &= ~(V2_AGG | V2_ROWS);
+  return (m & bit) != 0;
+}
 inline int tile_bps() { return std::max(1, std::min(4, g_opt_sparse_v2_bps)); }
+inline int tile_nt() { return g_opt_sparse_v2_nt == 128 ? 128 : 256; }
 
 void spmm32(const Ctx& c, const Gather& op, const float* in, float* out, long long R) {
   const long long RN = R * c.g->N;
   const e32::Gather3 g3{op.ptr, op.idx, op.val};
   if (v2(V2_SPMM)) {
-    const long long groups = R * ((c.g->N + 31) / 32);
-    e32::spmm32_v2_k<<<tile_grid(e32::spmm32_v2_k, 256, 0, 6, groups), 256, 0, c.st>>>(g3, in, out, c.g->N, R);
+    const long long groups = R * ((c.g->N + 63) / 64);
+    e32::spmm32_v2_k<<<tile_grid(e32::spmm32_v2_k, 256, 0, 3, groups), 256, 0, c.st>>>(g3, in, out, c.g->N, R);
   } else {
     e32::spmm32_k<<<persistent_grid(e32::spmm32_k, 256, 8, RN), 256, 0, c.st>>>(g3, in, out, c.g->N, RN);
   }
@@ -455,9 +461,13 @@ void e32_forward_steps(const Ctx& c, const CellDims& d, const gcrnn_cell_params*
   const size_t agg_smem = (size_t)4 * 2 * e32::AGG_STAGE * sizeof(float);
   const int g_agg = persistent_grid(e32::aggregate_k, 128, 4, BN, agg_smem);
   const e32::Gather3 gop{fw.ptr, fw.idx, fw.val};
-  const long long tiles = d.B * ((d.N + e32::TM - 1) / e32::TM), groups = d.B * ((d.N + 31) / 32);
-  const size_t gc_smem = (size_t)e32::gc_smem_floats<KST>(e32::GC_FILTER) * sizeof(float);
-  const int g_filter2 = v2(V2_FILTER) ? tile_grid(e32::gather_contract_k<KST, e32::GC_FILTER>, 128, gc_smem, tile_bps(), tiles) : 0;
+  const bool wide = tile_nt() == 256;            // 256-thread blocks on 128-node tiles, else 128 threads on 64 nodes
+  const int TMv = wide ? 128 : 64;
+  const long long tiles = d.B * ((d.N + TMv - 1) / TMv), groups = d.B * ((d.N + 31) / 32);
+  const size_t gc_smem = (size_t)(wide ? e32::gc_smem_floats<KST, 256>(e32::GC_FILTER) : e32::gc_smem_floats<KST, 128>(e32::GC_FILTER)) * sizeof(float);
+  const int g_filter2 = !v2(V2_FILTER) ? 0
+                        : wide ? tile_grid(e32::gather_contract_k<KST, e32::GC_FILTER, 256>, 256, gc_smem, std::min(2, tile_bps()), tiles)
+                               : tile_grid(e32::gather_contract_k<KST, e32::GC_FILTER, 128>, 128, gc_smem, tile_bps(), tiles);
   const int g_agg2 = v2(V2_AGG) ? tile_grid(e32::aggregate_v2_k, 256, 0, 4, groups) : 0;
   for (long long t = 0; t < d.T; ++t) {
     e32::Chain zc{};
@@ -470,17 +480,20 @@ void e32_forward_steps(const Ctx& c, const CellDims& d, const gcrnn_cell_params*
     float* wa = x.wu_a + t * BNF; float* wr = x.wu_r + t * BNF;
     float4* info = x.info + 2 * t * BN;
     if (v2(V2_FILTER))
-      e32::gather_contract_k<KST, e32::GC_FILTER><<<g_filter2, 128, gc_smem, c.st>>>(gop, zc, x_taps(d, s, t), d.Kin, d.G, prep,
-                                                       p->e_mixer[0], p->e_mixer[1], wa, wr, rc, d.N, d.B);
+      (wide ? e32::gather_contract_k<KST, e32::GC_FILTER, 256> : e32::gather_contract_k<KST, e32::GC_FILTER, 128>)
+          <<<g_filter2, wide ? 256 : 128, gc_smem, c.st>>>(gop, zc, x_taps(d, s, t), d.Kin, d.G, prep, p->e_mixer[0], p->e_mixer[1], wa, wr, rc, d.N, d.B);
     else
       e32::filter_fwd_k<KST><<<g_filter, 128, 0, c.st>>>(gop, zc, x_taps(d, s, t), d.Kin, d.G, prep,
                                                        p->e_mixer[0], p->e_mixer[1], wa, wr, rc, d.N, BN);
     check_launch();
-    e32::rowstats_k<<<grid1d(BN, 256), 256, 0, c.st>>>(g->att_rptr, g->att_col, rc, info, d.N, BN);
+    if (v2(V2_AGG))               // compact statistics layout inside the same `info` block: BN float4 (cl) + BN float2 (rr)
+      e32::rowstats_v2_k<<<grid1d(BN, 256), 256, 0, c.st>>>(g->att_rptr, g->att_col, rc, info, reinterpret_cast<float2*>(info + BN), d.N, BN);
+    else
+      e32::rowstats_k<<<grid1d(BN, 256), 256, 0, c.st>>>(g->att_rptr, g->att_col, rc, info, d.N, BN);
     check_launch();
     if (v2(V2_AGG))
-      e32::aggregate_v2_k<<<g_agg2, 256, 0, c.st>>>(g->att_cptr, g->att_crow, g->att_cval, info, wa, wr, s.Hn + t * BNF,
-                                                    x.masks + t * BN, d.N, d.B);
+      e32::aggregate_v2_k<<<g_agg2, 256, 0, c.st>>>(g->att_cptr, g->att_crow, g->att_cval, info, reinterpret_cast<const float2*>(info + BN),
+                                                    wa, wr, s.Hn + t * BNF, x.masks + t * BN, d.N, d.B);
     else
       e32::aggregate_k<<<g_agg, 128, agg_smem, c.st>>>(g->att_cptr, g->att_crow, g->att_cval, info, wa, wr, s.Hn + t * BNF,
                                               x.masks + t * BN, d.N, BN);
@@ -534,11 +547,17 @@ void e32_backward_steps(const Ctx& c, const CellDims& d, const gcrnn_cell_params
   const e32::Gather3 gfw{fw.ptr, fw.idx, fw.val}, gbw{bw.ptr, bw.idx, bw.val};
   const int g_node = persistent_grid(e32::bwd_node_k<KST>, 128, 4, BN);
   const int g_dh = persistent_grid(e32::dh_k<KST>, 128, 4, BN);
-  const long long tiles = d.B * ((d.N + e32::TM - 1) / e32::TM), groups = d.B * ((d.N + 31) / 32);
-  const size_t dh_smem = (size_t)e32::gc_smem_floats<KST>(e32::GC_DH) * sizeof(float);
-  const size_t node_smem = (size_t)e32::bwd_node_smem_floats<KST>() * sizeof(float);
-  const int g_dh2 = v2(V2_DH) ? tile_grid(e32::gather_contract_k<KST, e32::GC_DH>, 128, dh_smem, tile_bps(), tiles) : 0;
-  const int g_node2 = v2(V2_NODE) ? tile_grid(e32::bwd_node_v2_k<KST>, 128, node_smem, std::min(3, tile_bps()), tiles) : 0;
+  const bool wide = tile_nt() == 256;
+  const int TMv = wide ? 128 : 64;
+  const long long tiles = d.B * ((d.N + TMv - 1) / TMv), groups = d.B * ((d.N + 31) / 32);
+  const size_t dh_smem = (size_t)(wide ? e32::gc_smem_floats<KST, 256>(e32::GC_DH) : e32::gc_smem_floats<KST, 128>(e32::GC_DH)) * sizeof(float);
+  const size_t node_smem = (size_t)(wide ? e32::bwd_node_smem_floats<KST, 256>() : e32::bwd_node_smem_floats<KST, 128>()) * sizeof(float);
+  const int g_dh2 = !v2(V2_DH) ? 0
+                    : wide ? tile_grid(e32::gather_contract_k<KST, e32::GC_DH, 256>, 256, dh_smem, std::min(2, tile_bps()), tiles)
+                           : tile_grid(e32::gather_contract_k<KST, e32::GC_DH, 128>, 128, dh_smem, tile_bps(), tiles);
+  const int g_node2 = !v2(V2_NODE) ? 0
+                      : wide ? tile_grid(e32::bwd_node_v2_k<KST, 256>, 256, node_smem, std::min(2, tile_bps()), tiles)
+                             : tile_grid(e32::bwd_node_v2_k<KST, 128>, 128, node_smem, std::min(3, tile_bps()), tiles);
   const int g_rows2 = v2(V2_ROWS) ? tile_grid(e32::bwd_rows_v2_k, 256, 0, 2, groups) : 0;
   for (long long t = d.T - 1; t >= 0; --t) {
     const float* hn = s.Hn + t * BNF;
@@ -549,7 +568,7 @@ void e32_backward_steps(const Ctx& c, const CellDims& d, const gcrnn_cell_params
     check_launch();
     zero(c, b.dr, BN * sizeof(float2));
     if (v2(V2_ROWS))
-      e32::bwd_rows_v2_k<<<g_rows2, 256, 0, c.st>>>(g->att_rptr, g->att_col, g->att_val, info, wa, wr, b.dya, b.dyr,
+      e32::bwd_rows_v2_k<<<g_rows2, 256, 0, c.st>>>(g->att_rptr, g->att_col, g->att_val, info, reinterpret_cast<const float2*>(info + BN), wa, wr, b.dya, b.dyr,
                                                     p->e_mixer[0], p->e_mixer[1], b.pa, b.pr, b.dr, b.acc, d.N, d.B);
     else
       e32::bwd_rows_k<<<g_rows, 128, rows_smem, c.st>>>(g->att_rptr, g->att_col, g->att_val, info, wa, wr, b.dya, b.dyr,
@@ -559,8 +578,9 @@ void e32_backward_steps(const Ctx& c, const CellDims& d, const gcrnn_cell_params
     zc.p[0] = t == 0 ? s.h0n : s.Hn + (t - 1) * BNF;
     for (int k = 1; k <= KST - 2; ++k) zc.p[k] = x.zc + ((long long)(k - 1) * d.T + t) * BNF;
     if (v2(V2_NODE))
-      e32::bwd_node_v2_k<KST><<<g_node2, 128, node_smem, c.st>>>(gfw, zc, x_taps(d, s, t), d.Kin, d.G, b.pa, b.pr, b.dr, wa, wr,
-                                                   p->e_mixer[0], p->e_mixer[1], p->e_weight[1], b.dd, b.acc, d.N, d.B);
+      (wide ? e32::bwd_node_v2_k<KST, 256> : e32::bwd_node_v2_k<KST, 128>)
+          <<<g_node2, wide ? 256 : 128, node_smem, c.st>>>(gfw, zc, x_taps(d, s, t), d.Kin, d.G, b.pa, b.pr, b.dr, wa, wr,
+                                                           p->e_mixer[0], p->e_mixer[1], p->e_weight[1], b.dd, b.acc, d.N, d.B);
     else
       e32::bwd_node_k<KST><<<g_node, 128, 0, c.st>>>(gfw, zc, x_taps(d, s, t), d.Kin, d.G, b.pa, b.pr, b.dr, wa, wr,
                                                    p->e_mixer[0], p->e_mixer[1], p->e_weight[1], b.dd, b.acc, d.N, BN);
@@ -573,8 +593,8 @@ void e32_backward_steps(const Ctx& c, const CellDims& d, const gcrnn_cell_params
       wc.p[k] = out;
     }
     if (v2(V2_DH))
-      e32::gather_contract_k<KST, e32::GC_DH><<<g_dh2, 128, dh_smem, c.st>>>(gbw, wc, e32::Chain{}, 0, 1, p->weight_B, nullptr, nullptr,
-                                                                             nullptr, b.dhrec, nullptr, d.N, d.B);
+      (wide ? e32::gather_contract_k<KST, e32::GC_DH, 256> : e32::gather_contract_k<KST, e32::GC_DH, 128>)
+          <<<g_dh2, wide ? 256 : 128, dh_smem, c.st>>>(gbw, wc, e32::Chain{}, 0, 1, p->weight_B, nullptr, nullptr, nullptr, b.dhrec, nullptr, d.N, d.B);
     else
       e32::dh_k<KST><<<g_dh, 128, 0, c.st>>>(gbw, wc, p->weight_B, b.dhrec, d.N, BN);
     check_launch();

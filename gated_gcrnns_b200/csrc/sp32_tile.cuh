@@ -5,8 +5,9 @@
 // instructions per (sample, node) with 12 resident warps, not HBM-bound.
 //
 //   * Gathers: EIGHT lanes own one destination node (lane = 16-byte chunk of the 128-byte row), four nodes per warp.
-//     A neighbour row is one LDG.128 per lane with no index/value shuffles and no final reduce-scatter
-//     (~8 instructions per edge per FOUR nodes instead of ~11 per edge per node).
+//     A neighbour row is one LDG.128 per lane with no final reduce-scatter; (index, value) pairs are loaded once per batch
+//     of eight edges (lane = edge) and broadcast with width-8 shuffles; several nodes of a thread run in lockstep so that
+//     8-16 row loads are in flight per thread (the kernels are latency-bound, not issue-bound).
 //   * Contractions: a block stages a tile of 64 consecutive nodes ([64][K*32] inputs, gathered tap included) in shared
 //     memory and runs a register-tiled fp32 GEMM against weights that live in shared memory ONCE per block: a thread
 //     owns 4 nodes x 4 outputs and issues packed FFMA2 over input pairs, so no thread carries the 96 weights in
@@ -23,19 +24,26 @@
 namespace gcrnn {
 namespace e32 {
 
-constexpr int TM = 64;                                  // nodes per tile
+// tile kernels: NT threads stage and contract a tile of TM = NT / 2 consecutive nodes (NT = 128 or 256)
 constexpr int XS_LD = 16;                               // x taps per node in shared memory (zero padded, == MAXKG)
 constexpr int LDD = 36;                                 // row stride of the [TM][32] tiles (== 4 mod 32: conflict-free LDS.128)
 __host__ __device__ constexpr int lda_of(int kst) { return kst * 32 + 4; }
 
-struct Range { long long lo, hi; int per_sample; };
-// contiguous range of `unit`-node groups for this block (neighbouring groups share neighbour rows: L1/L2 reuse)
-__device__ __forceinline__ Range block_range(long long R, int N, int unit) {
-  const int per_sample = (N + unit - 1) / unit;
-  const long long total = R * per_sample, per = (total + gridDim.x - 1) / gridDim.x;
-  const long long lo = (long long)blockIdx.x * per;
-  return Range{lo, lo + per < total ? lo + per : total, per_sample};
-}
+// contiguous range of `unit`-node groups for this block (neighbouring groups share neighbour rows: L1/L2 reuse);
+// walked as (sample r, group u within the sample) so that the loop carries no 64-bit division
+struct Walk {
+  long long left; long long r; int u, per_sample;
+  __device__ __forceinline__ Walk(long long R, int N, int unit) {
+    per_sample = (N + unit - 1) / unit;
+    const long long total = R * per_sample, per = (total + gridDim.x - 1) / gridDim.x;
+    const long long lo = (long long)blockIdx.x * per;
+    const long long hi = lo + per < total ? lo + per : total;
+    left = hi > lo ? hi - lo : 0;
+    r = lo / per_sample; u = (int)(lo - r * per_sample);
+  }
+  __device__ __forceinline__ bool more() const { return left > 0; }
+  __device__ __forceinline__ void next() { --left; if (++u == per_sample) { u = 0; ++r; } }
+};
 __device__ __forceinline__ float4 f4zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
 __device__ __forceinline__ float4 f4add(const float4& a, const float4& b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 __device__ __forceinline__ float gsum8(float v, unsigned gmask) {       // sum over the 8 lanes of a node group
@@ -58,84 +66,129 @@ __device__ __forceinline__ float tree8(float (&v)[8], int c, unsigned gmask) {
   return v[0];
 }
 
-// sum_p val[p] * src[idx[p]] for this lane's 16-byte chunk; `base` = sample base (float4 units) + chunk
-__device__ __forceinline__ float4 gather_chunk(const Gather3& op, const float4* __restrict__ base, int n) {
-  int p = __ldg(op.ptr + n);
-  const int p1 = __ldg(op.ptr + n + 1);
-  float4 a0 = f4zero(), a1 = f4zero();
-  for (; p + 4 <= p1; p += 4) {
-    const int i0 = __ldg(op.idx + p), i1 = __ldg(op.idx + p + 1), i2 = __ldg(op.idx + p + 2), i3 = __ldg(op.idx + p + 3);
-    const float v0 = __ldg(op.val + p), v1 = __ldg(op.val + p + 1), v2 = __ldg(op.val + p + 2), v3 = __ldg(op.val + p + 3);
-    const float4 x0 = __ldg(base + (size_t)i0 * 8), x1 = __ldg(base + (size_t)i1 * 8);
-    const float4 x2 = __ldg(base + (size_t)i2 * 8), x3 = __ldg(base + (size_t)i3 * 8);
-    fma4(a0, v0, x0); fma4(a1, v1, x1); fma4(a0, v2, x2); fma4(a1, v3, x3);
+// Gather of NQ destination nodes per 8-lane group in lockstep:  acc[q] = sum_p val[p] * src[idx[p]] (this lane's 16-byte chunk).
+// Lane c loads (idx, val) of edge (batch + c) ONCE per batch of eight edges (coalesced; the next batch is prefetched) and the
+// group walks the batch with width-8 shuffles: per-edge index loads would cost as many L1 wavefronts as the rows themselves.
+// NQ * NU row loads are in flight per thread.  n[q] < 0: no node.  `base` = sample base (float4 units) + chunk.
+template <int NQ, int NU>
+__device__ __forceinline__ void gather_nodes(const Gather3& op, const float4* __restrict__ base, const int (&n)[NQ], float4 (&acc)[NQ],
+                                             unsigned gmask, int c) {
+  int p0[NQ], deg[NQ], md = 0;
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    p0[q] = 0; deg[q] = 0; acc[q] = f4zero();
+    if (n[q] >= 0) { p0[q] = __ldg(op.ptr + n[q]); deg[q] = __ldg(op.ptr + n[q] + 1) - p0[q]; }
+    md = max(md, deg[q]);
   }
-  for (; p < p1; ++p) fma4(a0, __ldg(op.val + p), __ldg(base + (size_t)__ldg(op.idx + p) * 8));
-  return f4add(a0, a1);
+  int mi[NQ]; float mv[NQ];
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    mi[q] = 0; mv[q] = 0.f;
+    if (c < deg[q]) { mi[q] = __ldg(op.idx + p0[q] + c); mv[q] = __ldg(op.val + p0[q] + c); }
+  }
+  for (int pb = 0; pb < md; pb += 8) {               // md is uniform within the 8-lane group
+    int ni[NQ]; float nv[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      ni[q] = 0; nv[q] = 0.f;
+      if (pb + 8 + c < deg[q]) { ni[q] = __ldg(op.idx + p0[q] + pb + 8 + c); nv[q] = __ldg(op.val + p0[q] + pb + 8 + c); }
+    }
+#pragma unroll
+    for (int e0 = 0; e0 < 8; e0 += NU) {
+      if (pb + e0 < md) {
+        float4 x[NQ][NU]; float w[NQ][NU];
+#pragma unroll
+        for (int u = 0; u < NU; ++u)
+#pragma unroll
+          for (int q = 0; q < NQ; ++q) {
+            const int ii = __shfl_sync(gmask, mi[q], e0 + u, 8);
+            w[q][u] = __shfl_sync(gmask, mv[q], e0 + u, 8);
+            x[q][u] = f4zero();
+            if (pb + e0 + u < deg[q]) x[q][u] = __ldg(base + (size_t)ii * 8);     // group-uniform predicate: idle slots cost no wavefront
+          }
+#pragma unroll
+        for (int u = 0; u < NU; ++u)
+#pragma unroll
+          for (int q = 0; q < NQ; ++q) fma4(acc[q], w[q][u], x[q][u]);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) { mi[q] = ni[q]; mv[q] = nv[q]; }
+  }
 }
 
 // ---- sparse shift of a 32-channel node-major signal: out[r,d,:] = sum_p val[p] in[r, idx[p], :] ----------------
-__global__ void __launch_bounds__(256, 6) spmm32_v2_k(Gather3 op, const float* __restrict__ in, float* __restrict__ out, int N, long long R) {
-  const int c = threadIdx.x & 7, slot = threadIdx.x >> 3;
-  const Range rg = block_range(R, N, 32);
-  for (long long g = rg.lo; g < rg.hi; ++g) {
-    const long long r = g / rg.per_sample;
-    const int n = (int)(g - r * rg.per_sample) * 32 + slot;
-    if (n >= N) continue;
-    const size_t rb = (size_t)r * N;
-    const float4 a = gather_chunk(op, reinterpret_cast<const float4*>(in + rb * 32) + c, n);
-    reinterpret_cast<float4*>(out + (rb + n) * 32)[c] = a;
+// 256 threads = 32 groups of 8 lanes; a group owns two nodes (64 nodes per block pass)
+__global__ void __launch_bounds__(256, 3) spmm32_v2_k(Gather3 op, const float* __restrict__ in, float* __restrict__ out, int N, long long R) {
+  const int lane = threadIdx.x & 31, c = threadIdx.x & 7, slot = threadIdx.x >> 3;
+  const unsigned gmask = 0xFFu << (lane & 24);
+  for (Walk w(R, N, 64); w.more(); w.next()) {
+    const size_t rb = (size_t)w.r * N;
+    int n[2]; float4 a[2];
+    n[0] = w.u * 64 + slot; n[1] = n[0] + 32;
+    if (n[0] >= N) n[0] = -1;
+    if (n[1] >= N) n[1] = -1;
+    gather_nodes<2, 4>(op, reinterpret_cast<const float4*>(in + rb * 32) + c, n, a, gmask, c);
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+      if (n[q] >= 0) reinterpret_cast<float4*>(out + (rb + n[q]) * 32)[c] = a[q];
   }
 }
 
-// ---- tile staging helpers (128-thread blocks) --------------------------------------------------------------------
-// rows n0 .. n0+63 of a [R,N,32] array -> tile[node][col0 .. col0+31]  (zero rows beyond N)
-__device__ __forceinline__ void stage_rows(float* tile, int ld, int col0, const float* __restrict__ src, size_t rb, int n0, int N) {
-  const float4* s4 = reinterpret_cast<const float4*>(src + (rb + n0) * 32);
-  float4 v[4];
+// ---- tile staging helpers (NT-thread blocks, TM = NT / 2 nodes) ----------------------------------------------------
+// rows n0 .. n0+TM-1 of a [R,N,32] array -> tile[node][col0 .. col0+31] by cp.async (zero rows beyond N); the caller
+// commits / waits, so the copies fly while the block gathers
+template <int NT>
+__device__ __forceinline__ void stage_rows_async(float* tile, int ld, int col0, const float* __restrict__ src, size_t rb, int n0, int N) {
+  const float* s = src + (rb + n0) * 32;
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
-    const int idx = threadIdx.x + 128 * q;
-    v[q] = (n0 + (idx >> 3) < N) ? __ldg(s4 + idx) : f4zero();
-  }
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const int idx = threadIdx.x + 128 * q;
-    *reinterpret_cast<float4*>(tile + (idx >> 3) * ld + col0 + (idx & 7) * 4) = v[q];
+    const int idx = threadIdx.x + NT * q, node = idx >> 3, ch = (idx & 7) * 4;
+    float* dst = tile + node * ld + col0 + ch;
+    if (n0 + node < N) cp_async16(dst, s + node * 32 + ch);
+    else *reinterpret_cast<float4*>(dst) = f4zero();
   }
 }
-// gathered rows (src S)[n0 .. n0+63] -> tile[node][col0 .. col0+31]
-__device__ __forceinline__ void stage_gather(float* tile, int ld, int col0, const Gather3& op, const float* __restrict__ src, size_t rb, int n0, int N) {
-  const int c = threadIdx.x & 7;
-  const float4* base = reinterpret_cast<const float4*>(src + rb * 32) + c;
-#pragma unroll 1
-  for (int q = 0; q < 4; ++q) {
-    const int node = (threadIdx.x >> 3) + 16 * q;
-    float4 a = f4zero();
-    if (n0 + node < N) a = gather_chunk(op, base, n0 + node);
-    *reinterpret_cast<float4*>(tile + node * ld + col0 + c * 4) = a;
-  }
-}
-// x taps of the tile's nodes -> Xs[node][kg], kg = k * G + g, zero padded to XS_LD
-__device__ __forceinline__ void stage_taps(float* Xs, const Chain& xs, int KG, int G, size_t rb, int n0, int N) {
-  for (int idx = threadIdx.x; idx < TM * XS_LD; idx += 128) {
-    const int node = idx >> 4, kg = idx & 15;
-    float v = 0.f;
-    if (kg < KG && n0 + node < N) {
-      const int k = kg / G, g = kg - k * G;
-      const float* xp = xs.p[0];
+// gathered rows (src S)[n0 .. n0+TM-1] into registers: a thread's four nodes (slot + NT/8 * q) run in lockstep
+template <int NT, int NU>
+__device__ __forceinline__ void gather_tile(float4 (&a)[4], const Gather3& op, const float* __restrict__ src, size_t rb, int n0, int N) {
+  const int c = threadIdx.x & 7, slot = threadIdx.x >> 3;
+  const unsigned gmask = 0xFFu << (threadIdx.x & 24);
+  int n[4];
 #pragma unroll
-      for (int m = 1; m < MAXK; ++m) if (k == m) xp = xs.p[m];
-      v = __ldg(xp + (rb + n0 + node) * G + g);
-    }
-    Xs[idx] = v;
+  for (int q = 0; q < 4; ++q) { n[q] = n0 + slot + (NT / 8) * q; if (n[q] >= N) n[q] = -1; }
+  gather_nodes<4, NU>(op, reinterpret_cast<const float4*>(src + rb * 32) + c, n, a, gmask, c);
+}
+template <int NT>
+__device__ __forceinline__ void store_tile(float* tile, int ld, int col0, const float4 (&a)[4]) {
+  const int c = threadIdx.x & 7, slot = threadIdx.x >> 3;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(tile + (slot + (NT / 8) * q) * ld + col0 + c * 4) = a[q];
+}
+// x taps of the tile's nodes -> Xs[node][kg], kg = k * G + g, zero padded to XS_LD.  A thread always serves the same kg
+// (NT is a multiple of XS_LD): `xp` = its tap array + g, or nullptr beyond KG (tap_slot(), computed once per kernel).
+__device__ __forceinline__ const float* tap_slot(const Chain& xs, int KG, int G) {
+  const int kg = threadIdx.x & (XS_LD - 1);
+  if (kg >= KG) return nullptr;
+  const int k = kg / G;
+  const float* xp = xs.p[0];
+#pragma unroll
+  for (int m = 1; m < MAXK; ++m) if (k == m) xp = xs.p[m];
+  return xp + (kg - k * G);
+}
+template <int NT>
+__device__ __forceinline__ void stage_taps(float* Xs, const float* __restrict__ xp, int G, size_t rb, int n0, int N) {
+#pragma unroll
+  for (int i = 0; i < (NT / 2) * XS_LD / NT; ++i) {
+    const int idx = threadIdx.x + NT * i, node = idx >> 4;
+    Xs[idx] = (xp != nullptr && n0 + node < N) ? __ldg(xp + (rb + n0 + node) * G) : 0.f;
   }
 }
 // weights w[kk][f] (kk < KK inputs, 32 outputs) -> shared "pair" layout: float4 ((kp*2 + half)*8 + fg) =
 // (w[2kp][f0], w[2kp+1][f0], w[2kp][f0+1], w[2kp+1][f0+1]),  f0 = 4 fg + 2 half
 template <class W>
 __device__ __forceinline__ void stage_weights(float* Ws, int KK, W w) {
-  for (int o = threadIdx.x; o < KK * 32; o += 128) {
+  for (int o = threadIdx.x; o < KK * 32; o += blockDim.x) {
     const int q = o & 3, fg = (o >> 2) & 7, half = (o >> 5) & 1, kp = o >> 6;
     Ws[o] = w(2 * kp + (q & 1), 4 * fg + 2 * half + (q >> 1));
   }
@@ -181,49 +234,59 @@ __device__ __forceinline__ void tile_contract(const float* __restrict__ tile, in
 //   Wu_a = Ca x-taps + ca0, rc = (a1.Wu_a, a2.Wu_a, a1.Wu_r, a2.Wu_r);  weights from the folded `prep` block.
 // GC_DH (backward stage 3): dh_{t-1}[n,g] = sum_k sum_f B[f,k,g] w_k[n,f], w_{KST-1} = w_{KST-2} S^T gathered into the tile.
 enum { GC_FILTER = 0, GC_DH = 1 };
-template <int KST>
+template <int KST, int NT>
 __host__ __device__ constexpr int gc_smem_floats(int mode) {
-  return KST * 32 * 32 + TM * lda_of(KST) + (mode == GC_FILTER ? TM * XS_LD + MAXKG * 32 : 0);
+  return KST * 32 * 32 + (NT / 2) * lda_of(KST) + (mode == GC_FILTER ? (NT / 2) * XS_LD + MAXKG * 32 + 6 * 32 : 0);
 }
-template <int KST, int MODE>
-__global__ void __launch_bounds__(128, 4) gather_contract_k(Gather3 gop, Chain zc, Chain xs, int Kin, int G,
+template <int KST, int MODE, int NT>
+__global__ void __launch_bounds__(NT, 512 / NT) gather_contract_k(Gather3 gop, Chain zc, Chain xs, int Kin, int G,
                                                             const float* __restrict__ wsrc /* FILTER: prep, DH: weight_B */,
                                                             const float* __restrict__ mix_a, const float* __restrict__ mix_r,
                                                             float* __restrict__ out_a /* FILTER: Wu_a */, float* __restrict__ out /* FILTER: Wu_r, DH: dh */,
                                                             float4* __restrict__ rc, int N, long long R) {
-  constexpr int KK = KST * 32, LDA = lda_of(KST), NS = KST - 1;
+  constexpr int KK = KST * 32, LDA = lda_of(KST), NS = KST - 1, TM = NT / 2;
   extern __shared__ __align__(16) float dyn[];
   float* Ws = dyn;                       // [KK/2][2][8] float4
   float* As = Ws + KK * 32;              // [TM][LDA]
   float* Xs = As + TM * LDA;             // FILTER: [TM][XS_LD]
   float* Cas = Xs + TM * XS_LD;          // FILTER: [MAXKG][32]
+  float* Cst = Cas + MAXKG * 32;         // FILTER: cr0, ca0, a1_a, a2_a, a1_r, a2_r  [6][32]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, fg = lane & 7, ngl = lane >> 3;
   const int KG = Kin * G;
+  const float* xp = nullptr;
   if (MODE == GC_FILTER) {
     stage_weights(Ws, KK, [&](int kk, int f) { return wsrc[PrepLayout::CR + kk * 32 + f]; });
-    for (int i = threadIdx.x; i < MAXKG * 32; i += 128) Cas[i] = wsrc[PrepLayout::CA + i];
+    for (int i = threadIdx.x; i < MAXKG * 32; i += NT) Cas[i] = wsrc[PrepLayout::CA + i];
+    if (threadIdx.x < 32) {
+      Cst[threadIdx.x] = wsrc[PrepLayout::CR0 + threadIdx.x]; Cst[32 + threadIdx.x] = wsrc[PrepLayout::CA0 + threadIdx.x];
+      Cst[64 + threadIdx.x] = mix_a[threadIdx.x]; Cst[96 + threadIdx.x] = mix_a[32 + threadIdx.x];
+      Cst[128 + threadIdx.x] = mix_r[threadIdx.x]; Cst[160 + threadIdx.x] = mix_r[32 + threadIdx.x];
+    }
+    xp = tap_slot(xs, KG, G);
   } else {
     stage_weights(Ws, KK, [&](int kk, int f) { return wsrc[(kk & 31) * KK + (kk >> 5) * 32 + f]; });   // B[f_in, k, g_out]
   }
-  float4 c0r = f4zero(), c0a = f4zero(), a1a = f4zero(), a2a = f4zero(), a1r = f4zero(), a2r = f4zero();
-  if (MODE == GC_FILTER) {
-    c0r = *reinterpret_cast<const float4*>(wsrc + PrepLayout::CR0 + 4 * fg);
-    c0a = *reinterpret_cast<const float4*>(wsrc + PrepLayout::CA0 + 4 * fg);
-    a1a = *reinterpret_cast<const float4*>(mix_a + 4 * fg); a2a = *reinterpret_cast<const float4*>(mix_a + 32 + 4 * fg);
-    a1r = *reinterpret_cast<const float4*>(mix_r + 4 * fg); a2r = *reinterpret_cast<const float4*>(mix_r + 32 + 4 * fg);
-  }
-  const Range rg = block_range(R, N, TM);
-  for (long long tile = rg.lo; tile < rg.hi; ++tile) {
-    const long long r = tile / rg.per_sample;
-    const int n0 = (int)(tile - r * rg.per_sample) * TM;
-    const size_t rb = (size_t)r * N;
+  for (Walk w(R, N, TM); w.more(); w.next()) {
+    const int n0 = w.u * TM;
+    const size_t rb = (size_t)w.r * N;
 #pragma unroll
-    for (int s = 0; s < NS; ++s) stage_rows(As, LDA, s * 32, zc.p[s], rb, n0, N);
-    if (MODE == GC_FILTER) stage_taps(Xs, xs, KG, G, rb, n0, N);
-    stage_gather(As, LDA, NS * 32, gop, zc.p[NS - 1], rb, n0, N);
+    for (int s = 0; s < NS; ++s) stage_rows_async<NT>(As, LDA, s * 32, zc.p[s], rb, n0, N);
+    cp_commit();
+    if (MODE == GC_FILTER) stage_taps<NT>(Xs, xp, G, rb, n0, N);
+    {
+      float4 gz[4];
+      gather_tile<NT, 4>(gz, gop, zc.p[NS - 1], rb, n0, N);
+      store_tile<NT>(As, LDA, NS * 32, gz);
+    }
+    cp_wait<0>();
     __syncthreads();
     float o[4][4];
     tile_contract<KK>(As, LDA, Ws, o);
+    float4 c0r, c0a, a1a, a2a, a1r, a2r;
+    if (MODE == GC_FILTER) {
+      const float4* c4 = reinterpret_cast<const float4*>(Cst) + fg;
+      c0r = c4[0]; c0a = c4[8]; a1a = c4[16]; a2a = c4[24]; a1r = c4[32]; a2r = c4[40];
+    }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int node = warp * 16 + ngl + 4 * i, n = n0 + node;
@@ -250,23 +313,48 @@ __global__ void __launch_bounds__(128, 4) gather_contract_k(Gather3 gop, Chain z
   }
 }
 
+// ---- forward, stage 2: per-row softmax statistics of both gates, compact layout ---------------------------------------
+// cl[r*N+i] = (c_a, lse_a, c_r, lse_r) with lse = log sum_j exp(e_ij) over the pattern of S + I, e_ij = leaky(c_i + r_j), so that
+// alpha_ij = exp(e_ij - lse_i) needs ONE 16-byte load per (edge, source row);  rr[r*N+j] = (r_a, r_r).
+__global__ void __launch_bounds__(256) rowstats_v2_k(const int* __restrict__ rptr, const int* __restrict__ col, const float4* __restrict__ rc,
+                                                     float4* __restrict__ cl, float2* __restrict__ rr, int N, long long RN) {
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < RN; t += (long long)gridDim.x * blockDim.x) {
+    const long long r = t / N; const int i = (int)(t - r * N);
+    const float4* rcr = rc + r * N;
+    const float4 me = rcr[i];
+    const int p0 = __ldg(rptr + i), p1 = __ldg(rptr + i + 1);
+    float ma = -INFINITY, mr = -INFINITY;
+    for (int p = p0; p < p1; ++p) {
+      const float4 o = rcr[__ldg(col + p)];
+      ma = fmaxf(ma, leaky(me.y + o.x)); mr = fmaxf(mr, leaky(me.w + o.z));
+    }
+    float da = 0.f, dr = 0.f;
+    for (int p = p0; p < p1; ++p) {
+      const float4 o = rcr[__ldg(col + p)];
+      da += __expf(leaky(me.y + o.x) - ma); dr += __expf(leaky(me.w + o.z) - mr);
+    }
+    cl[t] = make_float4(me.y, ma + logf(da), me.w, mr + logf(dr));
+    rr[t] = make_float2(me.x, me.z);
+  }
+}
+
 // ---- forward, stage 3: attention aggregation of both gates + relu + tanh update -----------------------------------
 // y_g[j,:] = relu( sum_{i -> j} S'_ij alpha^g_ij Wu_g[i,:] ),  h = tanh(y_a + y_r);  masks = sign bits of the two relus
 // (bit 8 i + c of a mask word belongs to feature 4 c + i, the layout dpre_k reads).  Eight lanes per destination j: lane c
 // computes alpha S' of edge (batch + c) once, the group then walks the batch with width-8 shuffles.
 __global__ void __launch_bounds__(256, 4) aggregate_v2_k(const int* __restrict__ cptr, const int* __restrict__ crow, const float* __restrict__ cval,
-                                                         const float4* __restrict__ info, const float* __restrict__ wu_a, const float* __restrict__ wu_r,
+                                                         const float4* __restrict__ cl, const float2* __restrict__ rr,
+                                                         const float* __restrict__ wu_a, const float* __restrict__ wu_r,
                                                          float* __restrict__ hn, uint2* __restrict__ masks, int N, long long R) {
   const int lane = threadIdx.x & 31, c = threadIdx.x & 7, slot = threadIdx.x >> 3;
   const unsigned gmask = 0xFFu << (lane & 24);
-  const Range rg = block_range(R, N, 32);
-  for (long long g = rg.lo; g < rg.hi; ++g) {
-    const long long r = g / rg.per_sample;
-    const int j = (int)(g - r * rg.per_sample) * 32 + slot;
+  for (Walk w(R, N, 32); w.more(); w.next()) {
+    const int j = w.u * 32 + slot;
     if (j >= N) continue;                                       // uniform within the 8-lane group
-    const size_t rb = (size_t)r * N;
+    const size_t rb = (size_t)w.r * N;
     const int p0 = __ldg(cptr + j), p1 = __ldg(cptr + j + 1);
-    const float rja = info[2 * (rb + j)].x, rjr = info[2 * (rb + j) + 1].x;
+    const float2 rj = rr[rb + j];
+    const float rja = rj.x, rjr = rj.y;
     const float4* pa = reinterpret_cast<const float4*>(wu_a + rb * 32) + c;
     const float4* pr = reinterpret_cast<const float4*>(wu_r + rb * 32) + c;
     float4 acc_a = f4zero(), acc_r = f4zero();
@@ -276,9 +364,9 @@ __global__ void __launch_bounds__(256, 4) aggregate_v2_k(const int* __restrict__
       if (c < cnt) {
         mi = __ldg(crow + pb + c);
         const float v = __ldg(cval + pb + c);
-        const float4 sa = info[2 * (rb + mi)], sr = info[2 * (rb + mi) + 1];
-        ca = v * (__expf(leaky(sa.y + rja) - sa.z) * sa.w);
-        cr = v * (__expf(leaky(sr.y + rjr) - sr.z) * sr.w);
+        const float4 s4 = cl[rb + mi];                           // (c_a, lse_a, c_r, lse_r) of source row mi
+        ca = v * __expf(leaky(s4.x + rja) - s4.y);
+        cr = v * __expf(leaky(s4.z + rjr) - s4.w);
       }
 #pragma unroll
       for (int e0 = 0; e0 < 8; e0 += 4) {
@@ -313,7 +401,8 @@ __global__ void __launch_bounds__(256, 4) aggregate_v2_k(const int* __restrict__
 // Eight lanes per row; lane c keeps the edge data of edges c, 8 + c, 16 + c, 24 + c (row degree of S + I <= 32); the
 // eight dot products of a batch are reduced "transposed" (7 shuffles) so that edge (batch + c) lands on lane c.
 __global__ void __launch_bounds__(256, 2) bwd_rows_v2_k(const int* __restrict__ rptr, const int* __restrict__ col, const float* __restrict__ val,
-                                                        const float4* __restrict__ info, const float* __restrict__ wu_a, const float* __restrict__ wu_r,
+                                                        const float4* __restrict__ cl, const float2* __restrict__ rr,
+                                                        const float* __restrict__ wu_a, const float* __restrict__ wu_r,
                                                         const float* __restrict__ dya, const float* __restrict__ dyr,
                                                         const float* __restrict__ mix_a, const float* __restrict__ mix_r,
                                                         float* __restrict__ pa, float* __restrict__ pr, float2* __restrict__ dr /* [R*N], zeroed */,
@@ -323,14 +412,12 @@ __global__ void __launch_bounds__(256, 2) bwd_rows_v2_k(const int* __restrict__ 
   const unsigned gmask = 0xFFu << (lane & 24);
   const float4 a2a = *reinterpret_cast<const float4*>(mix_a + 32 + 4 * c), a2r = *reinterpret_cast<const float4*>(mix_r + 32 + 4 * c);
   float4 m2a = f4zero(), m2r = f4zero();
-  const Range rg = block_range(R, N, 32);
-  for (long long g = rg.lo; g < rg.hi; ++g) {
-    const long long r = g / rg.per_sample;
-    const int i = (int)(g - r * rg.per_sample) * 32 + slot;
+  for (Walk w(R, N, 32); w.more(); w.next()) {
+    const int i = w.u * 32 + slot;
     if (i >= N) continue;                                       // uniform within the 8-lane group
-    const size_t rb = (size_t)r * N;
+    const size_t rb = (size_t)w.r * N;
     const int p0 = __ldg(rptr + i), deg = __ldg(rptr + i + 1) - p0;
-    const float4 mine_a = info[2 * (rb + i)], mine_r = info[2 * (rb + i) + 1];
+    const float4 mine = cl[rb + i];                              // (c_a, lse_a, c_r, lse_r) of this row
     const float4 wua = reinterpret_cast<const float4*>(wu_a + (rb + i) * 32)[c], wur = reinterpret_cast<const float4*>(wu_r + (rb + i) * 32)[c];
     const float4* ga = reinterpret_cast<const float4*>(dya + rb * 32) + c;
     const float4* gr = reinterpret_cast<const float4*>(dyr + rb * 32) + c;
@@ -346,9 +433,10 @@ __global__ void __launch_bounds__(256, 2) bwd_rows_v2_k(const int* __restrict__ 
         if (c < cnt) {
           jj[b] = __ldg(col + p0 + 8 * b + c);
           v = __ldg(val + p0 + 8 * b + c);
-          const float sca = mine_a.y + info[2 * (rb + jj[b])].x, scr = mine_r.y + info[2 * (rb + jj[b]) + 1].x;
-          ala[b] = __expf(leaky(sca) - mine_a.z) * mine_a.w; sla[b] = sca > 0.f ? 1.f : 0.2f;
-          alr[b] = __expf(leaky(scr) - mine_r.z) * mine_r.w; slr[b] = scr > 0.f ? 1.f : 0.2f;
+          const float2 rj = rr[rb + jj[b]];
+          const float sca = mine.x + rj.x, scr = mine.z + rj.y;
+          ala[b] = __expf(leaky(sca) - mine.y); sla[b] = sca > 0.f ? 1.f : 0.2f;
+          alr[b] = __expf(leaky(scr) - mine.w); slr[b] = scr > 0.f ? 1.f : 0.2f;
           coa = v * ala[b]; cor = v * alr[b];
         }
         float pda[8], pdr[8];
@@ -412,49 +500,50 @@ __global__ void __launch_bounds__(256, 2) bwd_rows_v2_k(const int* __restrict__ 
 // ---- backward, stage 2 (per tile): finish dWu, accumulate the outer products, d = W_r^T dWu_r ----------------------------
 //   dWu_g[n,:] = p_g[n,:] + a1_g dr_g[n];  m1_g += dr_g[n] Wu_g[n,:];  sum_g += dWu_g[n,:]
 //   M_k[f][g] += dWu_r[n,f] z_k[n,g] (z_{KST-1} gathered into the tile);  Ma[kg][f] += dWu_a[n,f] x[n,kg];  dout[n,:] = W_r^T dWu_r[n,:]
-template <int KST>
-__host__ __device__ constexpr int bwd_node_smem_floats() { return 32 * 32 + TM * lda_of(KST) + 2 * TM * LDD + TM * XS_LD; }
-template <int KST>
-__global__ void __launch_bounds__(128, 3) bwd_node_v2_k(Gather3 gop, Chain zc, Chain xs, int Kin, int G,
+// dWu_a only feeds the small input-tap products: it is parked in the tile's gathered column block, consumed, and only then
+// overwritten by the gathered tap (which waits in registers meanwhile) - no shared memory of its own.
+template <int KST, int NT>
+__host__ __device__ constexpr int bwd_node_smem_floats() { return 32 * 32 + (NT / 2) * lda_of(KST) + (NT / 2) * LDD + (NT / 2) * XS_LD + MAXKG * 32; }
+template <int KST, int NT>
+__global__ void __launch_bounds__(NT, NT == 128 ? 3 : 2) bwd_node_v2_k(Gather3 gop, Chain zc, Chain xs, int Kin, int G,
                                                         const float* __restrict__ pa, const float* __restrict__ pr, const float2* __restrict__ dr,
                                                         const float* __restrict__ wu_a, const float* __restrict__ wu_r,
                                                         const float* __restrict__ mix_a, const float* __restrict__ mix_r, const float* __restrict__ Wr,
                                                         float* __restrict__ dout, float* __restrict__ acc, int N, long long R) {
-  constexpr int KK = KST * 32, LDA = lda_of(KST), NS = KST - 1;
+  constexpr int KK = KST * 32, LDA = lda_of(KST), NS = KST - 1, TM = NT / 2;
   constexpr int KPT = KK / 16;                 // z columns per thread in the outer-product stage (pairs: KST float2)
   extern __shared__ __align__(16) float dyn[];
   float* Ws = dyn;                             // W_r in pair layout (32 inputs f, 32 outputs m)
   float* As = Ws + 32 * 32;                    // [TM][LDA]  z_0 .. z_{KST-1}
   float* Ds = As + TM * LDA;                   // [TM][LDD]  dWu_r
-  float* Da = Ds + TM * LDD;                   // [TM][LDD]  dWu_a
-  float* Xs = Da + TM * LDD;                   // [TM][XS_LD]
+  float* Xs = Ds + TM * LDD;                   // [TM][XS_LD]
+  float* Mas = Xs + TM * XS_LD;                // [MAXKG][32] block accumulators of the input-tap products
+  float* Da = As + NS * 32;                    // dWu_a parked in the gathered column block (row stride LDA)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, fg = lane & 7, ngl = lane >> 3;
-  const int c = threadIdx.x & 7;
+  const int c = threadIdx.x & 7, slot = threadIdx.x >> 3;
   const int KG = Kin * G;
   stage_weights(Ws, 32, [&](int f, int m) { return Wr[f * 32 + m]; });
-  const float4 a1a = *reinterpret_cast<const float4*>(mix_a + 4 * c), a1r = *reinterpret_cast<const float4*>(mix_r + 4 * c);
+  const float* xp = tap_slot(xs, KG, G);
+  for (int i = threadIdx.x; i < MAXKG * 32; i += NT) Mas[i] = 0.f;
   float4 m1a = f4zero(), m1r = f4zero();
-  float2 M[4][KST];                            // M[fi][u]: f = 4 ft + fi, kk = KPT kt + 2u (+1)
+  float2 M[4][KST];                            // M[fi][u]: f = 4 ft + fi, kk = KPT kt + 2u (+1), partial over this thread's 64-node half
 #pragma unroll
   for (int fi = 0; fi < 4; ++fi)
 #pragma unroll
     for (int u = 0; u < KST; ++u) M[fi][u] = make_float2(0.f, 0.f);
-  float Ma[MAXKG];
-#pragma unroll
-  for (int i = 0; i < MAXKG; ++i) Ma[i] = 0.f;
   float suma = 0.f, sumr = 0.f;
-  const int ft = threadIdx.x & 7, kt = threadIdx.x >> 3;
-  const Range rg = block_range(R, N, TM);
-  for (long long tile = rg.lo; tile < rg.hi; ++tile) {
-    const long long r = tile / rg.per_sample;
-    const int n0 = (int)(tile - r * rg.per_sample) * TM;
-    const size_t rb = (size_t)r * N;
+  const int ft = threadIdx.x & 7, kt = (threadIdx.x >> 3) & 15, nh = threadIdx.x >> 7;
+  for (Walk w(R, N, TM); w.more(); w.next()) {
+    const int n0 = w.u * TM;
+    const size_t rb = (size_t)w.r * N;
 #pragma unroll
-    for (int s = 0; s < NS; ++s) stage_rows(As, LDA, s * 32, zc.p[s], rb, n0, N);
-    stage_taps(Xs, xs, KG, G, rb, n0, N);
+    for (int s = 0; s < NS; ++s) stage_rows_async<NT>(As, LDA, s * 32, zc.p[s], rb, n0, N);
+    cp_commit();
+    stage_taps<NT>(Xs, xp, G, rb, n0, N);
+    const float4 a1a = __ldg(reinterpret_cast<const float4*>(mix_a) + c), a1r = __ldg(reinterpret_cast<const float4*>(mix_r) + c);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {                // finish dWu of both gates for (node, chunk c)
-      const int node = (threadIdx.x >> 3) + 16 * q, n = n0 + node;
+      const int node = slot + (NT / 8) * q, n = n0 + node;
       float4 dwa = f4zero(), dwr = f4zero();
       if (n < N) {
         const size_t o = (rb + n) * 8 + c;
@@ -463,10 +552,27 @@ __global__ void __launch_bounds__(128, 3) bwd_node_v2_k(Gather3 gop, Chain zc, C
         fma4(dwa, d2.x, a1a); fma4(dwr, d2.y, a1r);
         fma4(m1a, d2.x, __ldg(reinterpret_cast<const float4*>(wu_a) + o)); fma4(m1r, d2.y, __ldg(reinterpret_cast<const float4*>(wu_r) + o));
       }
-      *reinterpret_cast<float4*>(Da + node * LDD + 4 * c) = dwa;
+      *reinterpret_cast<float4*>(Da + node * LDA + 4 * c) = dwa;
       *reinterpret_cast<float4*>(Ds + node * LDD + 4 * c) = dwr;
     }
-    stage_gather(As, LDA, NS * 32, gop, zc.p[NS - 1], rb, n0, N);
+    float4 gz[4];
+    gather_tile<NT, 2>(gz, gop, zc.p[NS - 1], rb, n0, N);
+    __syncthreads();
+    {                                            // input-tap outer products and column sums: thread = feature `lane`, 16 nodes of the warp
+      const float* dap = Da + warp * 16 * LDA + lane;
+      const float* xsp = Xs + warp * 16 * XS_LD;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) { suma += dap[q * LDA]; sumr += Ds[(warp * 16 + q) * LDD + lane]; }
+      for (int kg = 0; kg < KG; ++kg) {
+        float m = 0.f;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) m = fmaf(dap[q * LDA], xsp[q * XS_LD + kg], m);
+        atomicAdd(Mas + kg * 32 + lane, m);
+      }
+    }
+    __syncthreads();
+    store_tile<NT>(As, LDA, NS * 32, gz);
+    cp_wait<0>();
     __syncthreads();
     {                                            // d = W_r^T dWu_r
       float o[4][4];
@@ -477,11 +583,11 @@ __global__ void __launch_bounds__(128, 3) bwd_node_v2_k(Gather3 gop, Chain zc, C
         if (n < N) reinterpret_cast<float4*>(dout + (rb + n) * 32)[fg] = make_float4(o[i][0], o[i][1], o[i][2], o[i][3]);
       }
     }
-    {                                            // outer products: thread = 4 outputs f x KPT inputs kk, reduction over the tile's nodes
-      const float* dp = Ds + 4 * ft;
-      const float* zp = As + KPT * kt;
+    {                                            // outer products: thread = 4 outputs f x KPT inputs kk, reduction over 64 nodes of the tile
+      const float* dp = Ds + nh * 64 * LDD + 4 * ft;
+      const float* zp = As + nh * 64 * LDA + KPT * kt;
 #pragma unroll 4
-      for (int node = 0; node < TM; ++node) {
+      for (int node = 0; node < 64; ++node) {
         const float4 d4 = *reinterpret_cast<const float4*>(dp + node * LDD);
 #pragma unroll
         for (int u = 0; u < KST; ++u) {
@@ -493,24 +599,9 @@ __global__ void __launch_bounds__(128, 3) bwd_node_v2_k(Gather3 gop, Chain zc, C
         }
       }
     }
-    {                                            // input-tap outer products and column sums: thread = feature `lane`, 16 nodes of the warp
-#pragma unroll 4
-      for (int q = 0; q < 16; ++q) {
-        const int node = warp * 16 + q;
-        const float da = Da[node * LDD + lane];
-        suma += da; sumr += Ds[node * LDD + lane];
-#pragma unroll
-        for (int kg = 0; kg < MAXKG; kg += 4)
-          if (kg < KG) {
-            const float4 x4 = *reinterpret_cast<const float4*>(Xs + node * XS_LD + kg);
-            Ma[kg] = fmaf(da, x4.x, Ma[kg]); Ma[kg + 1] = fmaf(da, x4.y, Ma[kg + 1]);
-            Ma[kg + 2] = fmaf(da, x4.z, Ma[kg + 2]); Ma[kg + 3] = fmaf(da, x4.w, Ma[kg + 3]);
-          }
-      }
-    }
     __syncthreads();
   }
-  // every thread owns distinct M entries of the block: one global atomic per entry per block
+  // partial sums of distinct M entries (per 64-node half): one global atomic per entry per thread
 #pragma unroll
   for (int fi = 0; fi < 4; ++fi)
 #pragma unroll
@@ -519,9 +610,7 @@ __global__ void __launch_bounds__(128, 3) bwd_node_v2_k(Gather3 gop, Chain zc, C
       atomicAdd(acc + AccLayout::M + kk * 32 + f, M[fi][u].x);
       atomicAdd(acc + AccLayout::M + (kk + 1) * 32 + f, M[fi][u].y);
     }
-#pragma unroll
-  for (int kg = 0; kg < MAXKG; ++kg)
-    if (kg < KG) atomicAdd(acc + AccLayout::MA + kg * 32 + lane, Ma[kg]);
+  for (int i = threadIdx.x; i < KG * 32; i += NT) atomicAdd(acc + AccLayout::MA + i, Mas[i]);   // last tile ended with a barrier
   atomicAdd(acc + AccLayout::SUMA + lane, suma); atomicAdd(acc + AccLayout::SUMR + lane, sumr);
   float m[8] = {m1a.x, m1a.y, m1a.z, m1a.w, m1r.x, m1r.y, m1r.z, m1r.w};
 #pragma unroll
