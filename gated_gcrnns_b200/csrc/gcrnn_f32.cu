@@ -429,8 +429,7 @@ inline bool v2(int bit) {
   if ((m & (V2_AGG | V2_ROWS)) != (V2_AGG | V2_ROWS)) m &= ~(V2_AGG | V2_ROWS);
   return (m & bit) != 0;
 }
-inline int tile_bps() { return std::max(1, std::min(4, g_opt_sparse_v2_bps)); }
-inline int tile_nt() { return g_opt_sparse_v2_nt == 128 ? 128 : 256; }
+inline int tile_bps() { return std::max(1, std::min(2, g_opt_sparse_v2_bps)); }
 
 void spmm32(const Ctx& c, const Gather& op, const float* in, float* out, long long R) {
   const long long RN = R * c.g->N;
@@ -461,13 +460,11 @@ void e32_forward_steps(const Ctx& c, const CellDims& d, const gcrnn_cell_params*
   const size_t agg_smem = (size_t)4 * 2 * e32::AGG_STAGE * sizeof(float);
   const int g_agg = persistent_grid(e32::aggregate_k, 128, 4, BN, agg_smem);
   const e32::Gather3 gop{fw.ptr, fw.idx, fw.val};
-  const bool wide = tile_nt() == 256;            // 256-thread blocks on 128-node tiles, else 128 threads on 64 nodes
-  const int TMv = wide ? 128 : 64;
-  const long long tiles = d.B * ((d.N + TMv - 1) / TMv), groups = d.B * ((d.N + 31) / 32);
-  const size_t gc_smem = (size_t)(wide ? e32::gc_smem_floats<KST, 256>(e32::GC_FILTER) : e32::gc_smem_floats<KST, 128>(e32::GC_FILTER)) * sizeof(float);
-  const int g_filter2 = !v2(V2_FILTER) ? 0
-                        : wide ? tile_grid(e32::gather_contract_k<KST, e32::GC_FILTER, 256>, 256, gc_smem, std::min(2, tile_bps()), tiles)
-                               : tile_grid(e32::gather_contract_k<KST, e32::GC_FILTER, 128>, 128, gc_smem, tile_bps(), tiles);
+  const bool tc = g_opt_sparse_v2_tc != 0;        // 3xTF32 mma.sync contraction, else packed FFMA2
+  const long long tiles = d.B * ((d.N + 127) / 128), groups = d.B * ((d.N + 31) / 32);      // 256-thread blocks on 128-node tiles
+  const size_t gc_smem = (size_t)e32::gc_smem_floats<KST, 256>(e32::GC_FILTER) * sizeof(float);
+  auto k_filter = tc ? e32::gather_contract_k<KST, e32::GC_FILTER, 256, true> : e32::gather_contract_k<KST, e32::GC_FILTER, 256, false>;
+  const int g_filter2 = v2(V2_FILTER) ? tile_grid(k_filter, 256, gc_smem, tile_bps(), tiles) : 0;
   const int g_agg2 = v2(V2_AGG) ? tile_grid(e32::aggregate_v2_k, 256, 0, 4, groups) : 0;
   for (long long t = 0; t < d.T; ++t) {
     e32::Chain zc{};
@@ -480,8 +477,7 @@ void e32_forward_steps(const Ctx& c, const CellDims& d, const gcrnn_cell_params*
     float* wa = x.wu_a + t * BNF; float* wr = x.wu_r + t * BNF;
     float4* info = x.info + 2 * t * BN;
     if (v2(V2_FILTER))
-      (wide ? e32::gather_contract_k<KST, e32::GC_FILTER, 256> : e32::gather_contract_k<KST, e32::GC_FILTER, 128>)
-          <<<g_filter2, wide ? 256 : 128, gc_smem, c.st>>>(gop, zc, x_taps(d, s, t), d.Kin, d.G, prep, p->e_mixer[0], p->e_mixer[1], wa, wr, rc, d.N, d.B);
+      k_filter<<<g_filter2, 256, gc_smem, c.st>>>(gop, zc, x_taps(d, s, t), d.Kin, d.G, prep, p->e_mixer[0], p->e_mixer[1], wa, wr, rc, d.N, d.B);
     else
       e32::filter_fwd_k<KST><<<g_filter, 128, 0, c.st>>>(gop, zc, x_taps(d, s, t), d.Kin, d.G, prep,
                                                        p->e_mixer[0], p->e_mixer[1], wa, wr, rc, d.N, BN);
@@ -547,17 +543,14 @@ void e32_backward_steps(const Ctx& c, const CellDims& d, const gcrnn_cell_params
   const e32::Gather3 gfw{fw.ptr, fw.idx, fw.val}, gbw{bw.ptr, bw.idx, bw.val};
   const int g_node = persistent_grid(e32::bwd_node_k<KST>, 128, 4, BN);
   const int g_dh = persistent_grid(e32::dh_k<KST>, 128, 4, BN);
-  const bool wide = tile_nt() == 256;
-  const int TMv = wide ? 128 : 64;
-  const long long tiles = d.B * ((d.N + TMv - 1) / TMv), groups = d.B * ((d.N + 31) / 32);
-  const size_t dh_smem = (size_t)(wide ? e32::gc_smem_floats<KST, 256>(e32::GC_DH) : e32::gc_smem_floats<KST, 128>(e32::GC_DH)) * sizeof(float);
-  const size_t node_smem = (size_t)(wide ? e32::bwd_node_smem_floats<KST, 256>() : e32::bwd_node_smem_floats<KST, 128>()) * sizeof(float);
-  const int g_dh2 = !v2(V2_DH) ? 0
-                    : wide ? tile_grid(e32::gather_contract_k<KST, e32::GC_DH, 256>, 256, dh_smem, std::min(2, tile_bps()), tiles)
-                           : tile_grid(e32::gather_contract_k<KST, e32::GC_DH, 128>, 128, dh_smem, tile_bps(), tiles);
-  const int g_node2 = !v2(V2_NODE) ? 0
-                      : wide ? tile_grid(e32::bwd_node_v2_k<KST, 256>, 256, node_smem, std::min(2, tile_bps()), tiles)
-                             : tile_grid(e32::bwd_node_v2_k<KST, 128>, 128, node_smem, std::min(3, tile_bps()), tiles);
+  const bool tc = g_opt_sparse_v2_tc != 0;
+  const long long tiles = d.B * ((d.N + 127) / 128), groups = d.B * ((d.N + 31) / 32);
+  const size_t dh_smem = (size_t)e32::gc_smem_floats<KST, 256>(e32::GC_DH) * sizeof(float);
+  const size_t node_smem = (size_t)e32::bwd_node_smem_floats<KST, 256>() * sizeof(float);
+  auto k_dh = tc ? e32::gather_contract_k<KST, e32::GC_DH, 256, true> : e32::gather_contract_k<KST, e32::GC_DH, 256, false>;
+  auto k_node = tc ? e32::bwd_node_v2_k<KST, 256, true> : e32::bwd_node_v2_k<KST, 256, false>;
+  const int g_dh2 = v2(V2_DH) ? tile_grid(k_dh, 256, dh_smem, tile_bps(), tiles) : 0;
+  const int g_node2 = v2(V2_NODE) ? tile_grid(k_node, 256, node_smem, tile_bps(), tiles) : 0;
   const int g_rows2 = v2(V2_ROWS) ? tile_grid(e32::bwd_rows_v2_k, 256, 0, 2, groups) : 0;
   for (long long t = d.T - 1; t >= 0; --t) {
     const float* hn = s.Hn + t * BNF;
@@ -578,8 +571,7 @@ void e32_backward_steps(const Ctx& c, const CellDims& d, const gcrnn_cell_params
     zc.p[0] = t == 0 ? s.h0n : s.Hn + (t - 1) * BNF;
     for (int k = 1; k <= KST - 2; ++k) zc.p[k] = x.zc + ((long long)(k - 1) * d.T + t) * BNF;
     if (v2(V2_NODE))
-      (wide ? e32::bwd_node_v2_k<KST, 256> : e32::bwd_node_v2_k<KST, 128>)
-          <<<g_node2, wide ? 256 : 128, node_smem, c.st>>>(gfw, zc, x_taps(d, s, t), d.Kin, d.G, b.pa, b.pr, b.dr, wa, wr,
+      k_node<<<g_node2, 256, node_smem, c.st>>>(gfw, zc, x_taps(d, s, t), d.Kin, d.G, b.pa, b.pr, b.dr, wa, wr,
                                                            p->e_mixer[0], p->e_mixer[1], p->e_weight[1], b.dd, b.acc, d.N, d.B);
     else
       e32::bwd_node_k<KST><<<g_node, 128, 0, c.st>>>(gfw, zc, x_taps(d, s, t), d.Kin, d.G, b.pa, b.pr, b.dr, wa, wr,
@@ -593,8 +585,7 @@ void e32_backward_steps(const Ctx& c, const CellDims& d, const gcrnn_cell_params
       wc.p[k] = out;
     }
     if (v2(V2_DH))
-      (wide ? e32::gather_contract_k<KST, e32::GC_DH, 256> : e32::gather_contract_k<KST, e32::GC_DH, 128>)
-          <<<g_dh2, wide ? 256 : 128, dh_smem, c.st>>>(gbw, wc, e32::Chain{}, 0, 1, p->weight_B, nullptr, nullptr, nullptr, b.dhrec, nullptr, d.N, d.B);
+      k_dh<<<g_dh2, 256, dh_smem, c.st>>>(gbw, wc, e32::Chain{}, 0, 1, p->weight_B, nullptr, nullptr, nullptr, b.dhrec, nullptr, d.N, d.B);
     else
       e32::dh_k<KST><<<g_dh, 128, 0, c.st>>>(gbw, wc, p->weight_B, b.dhrec, d.N, BN);
     check_launch();

@@ -26,8 +26,10 @@ namespace e32 {
 
 // tile kernels: NT threads stage and contract a tile of TM = NT / 2 consecutive nodes (NT = 128 or 256)
 constexpr int XS_LD = 16;                               // x taps per node in shared memory (zero padded, == MAXKG)
-constexpr int LDD = 36;                                 // row stride of the [TM][32] tiles (== 4 mod 32: conflict-free LDS.128)
-__host__ __device__ constexpr int lda_of(int kst) { return kst * 32 + 4; }
+// row strides == 8 (mod 32): conflict-free for the LDS.128 rows of the FFMA2 contraction AND for both mma fragment patterns
+// (A: bank 8 g + t, B of the transposed product: bank 8 t + g)
+constexpr int LDD = 40;                                 // row stride of the [TM][32] tiles
+__host__ __device__ constexpr int lda_of(int kst) { return kst * 32 + 8; }
 
 // contiguous range of `unit`-node groups for this block (neighbouring groups share neighbour rows: L1/L2 reuse);
 // walked as (sample r, group u within the sample) so that the loop carries no 64-bit division
@@ -69,7 +71,8 @@ __device__ __forceinline__ float tree8(float (&v)[8], int c, unsigned gmask) {
 // Gather of NQ destination nodes per 8-lane group in lockstep:  acc[q] = sum_p val[p] * src[idx[p]] (this lane's 16-byte chunk).
 // Lane c loads (idx, val) of edge (batch + c) ONCE per batch of eight edges (coalesced; the next batch is prefetched) and the
 // group walks the batch with width-8 shuffles: per-edge index loads would cost as many L1 wavefronts as the rows themselves.
-// NQ * NU row loads are in flight per thread.  n[q] < 0: no node.  `base` = sample base (float4 units) + chunk.
+// NQ * NU row loads are in flight per thread.  Idle slots read row 0 of the sample with coefficient 0 (predicating them costs
+// more instructions than it saves wavefronts).  n[q] < 0: no node.  `base` = sample base (float4 units) + chunk.
 template <int NQ, int NU>
 __device__ __forceinline__ void gather_nodes(const Gather3& op, const float4* __restrict__ base, const int (&n)[NQ], float4 (&acc)[NQ],
                                              unsigned gmask, int c) {
@@ -103,8 +106,7 @@ __device__ __forceinline__ void gather_nodes(const Gather3& op, const float4* __
           for (int q = 0; q < NQ; ++q) {
             const int ii = __shfl_sync(gmask, mi[q], e0 + u, 8);
             w[q][u] = __shfl_sync(gmask, mv[q], e0 + u, 8);
-            x[q][u] = f4zero();
-            if (pb + e0 + u < deg[q]) x[q][u] = __ldg(base + (size_t)ii * 8);     // group-uniform predicate: idle slots cost no wavefront
+            x[q][u] = __ldg(base + (size_t)ii * 8);          // idle slots: row 0 of the sample (one shared line) with coefficient 0
           }
 #pragma unroll
         for (int u = 0; u < NU; ++u)
@@ -229,6 +231,57 @@ __device__ __forceinline__ void tile_contract(const float* __restrict__ tile, in
     for (int j = 0; j < 4; ++j) o[i][j] = acc[i][j].x + acc[i][j].y;
 }
 
+
+// ---- 3xTF32 tensor-core contraction (mma.sync.m16n8k8, fp32 accumulate) ---------------------------------------------------
+// x = hi + lo with hi = tf32(x), lo = tf32(x - hi): a b ~= a_lo b_hi + a_hi b_lo + a_hi b_hi keeps ~2^-21 relative error per
+// product, i.e. fp32-class accuracy (the stated 1e-5 / 1e-4 bounds of the fp32 path hold, see tests), while the operands come
+// out of shared memory as conflict-free fragments: 12 wavefronts per 16 x 32 x 8 block instead of 32 for the FFMA2 tile.
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+  const float r = x - __uint_as_float(hi);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void mma3(float (&d)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4], uint32_t bh0, uint32_t bh1, uint32_t bl0, uint32_t bl1) {
+  mma_tf32(d, al, bh0, bh1); mma_tf32(d, ah, bl0, bl1); mma_tf32(d, ah, bh0, bh1);      // small terms first
+}
+// weights w[kk][f] -> shared fragment layout: float4 ((ks*2 + half)*32 + lane) = (w[kk][g], w[kk][8+g], w[kk][16+g], w[kk][24+g]),
+// kk = 8 ks + t + 4 half, g = lane >> 2, t = lane & 3  (the b0 / b1 registers of the four 8-wide output tiles)
+template <class W>
+__device__ __forceinline__ void stage_weights_tc(float* Ws, int KK, W w) {
+  for (int o = threadIdx.x; o < KK * 32; o += blockDim.x) {
+    const int nt = o & 3, lane = (o >> 2) & 31, half = (o >> 7) & 1, ks = o >> 8;
+    Ws[o] = w(8 * ks + (lane & 3) + 4 * half, 8 * nt + (lane >> 2));
+  }
+}
+// d[nt][.] = rows (warp*16 + g, warp*16 + g + 8) x columns (8 nt + 2 t, + 1) of  tile[16 rows of the warp][KK] * w[KK][32]
+template <int KK>
+__device__ __forceinline__ void tile_contract_tc(const float* __restrict__ tile, int ld, const float* __restrict__ Ws, float (&d)[4][4]) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  const float* ap = tile + (warp * 16 + g) * ld + t;
+  const float4* wp = reinterpret_cast<const float4*>(Ws) + lane;
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) { d[nt][0] = d[nt][1] = d[nt][2] = d[nt][3] = 0.f; }
+#pragma unroll 2
+  for (int ks = 0; ks < KK / 8; ++ks) {
+    uint32_t ah[4], al[4];
+    split_tf32(ap[8 * ks], ah[0], al[0]); split_tf32(ap[8 * ld + 8 * ks], ah[1], al[1]);
+    split_tf32(ap[8 * ks + 4], ah[2], al[2]); split_tf32(ap[8 * ld + 8 * ks + 4], ah[3], al[3]);
+    const float4 w0 = wp[(2 * ks) * 32], w1 = wp[(2 * ks + 1) * 32];
+    const float b0[4] = {w0.x, w0.y, w0.z, w0.w}, b1[4] = {w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      uint32_t bh0, bl0, bh1, bl1;
+      split_tf32(b0[nt], bh0, bl0); split_tf32(b1[nt], bh1, bl1);
+      mma3(d[nt], ah, al, bh0, bh1, bl0, bl1);
+    }
+  }
+}
+
 // ---- gather + contraction over a tile -----------------------------------------------------------------------------
 // GC_FILTER (forward stage 1): Wu_r = sum_k Cr_k z_k + cr0 (z_{KST-1} = z_{KST-2} S gathered into the tile),
 //   Wu_a = Ca x-taps + ca0, rc = (a1.Wu_a, a2.Wu_a, a1.Wu_r, a2.Wu_r);  weights from the folded `prep` block.
@@ -238,7 +291,7 @@ template <int KST, int NT>
 __host__ __device__ constexpr int gc_smem_floats(int mode) {
   return KST * 32 * 32 + (NT / 2) * lda_of(KST) + (mode == GC_FILTER ? (NT / 2) * XS_LD + MAXKG * 32 + 6 * 32 : 0);
 }
-template <int KST, int MODE, int NT>
+template <int KST, int MODE, int NT, bool TC>
 __global__ void __launch_bounds__(NT, 512 / NT) gather_contract_k(Gather3 gop, Chain zc, Chain xs, int Kin, int G,
                                                             const float* __restrict__ wsrc /* FILTER: prep, DH: weight_B */,
                                                             const float* __restrict__ mix_a, const float* __restrict__ mix_r,
@@ -254,8 +307,9 @@ __global__ void __launch_bounds__(NT, 512 / NT) gather_contract_k(Gather3 gop, C
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, fg = lane & 7, ngl = lane >> 3;
   const int KG = Kin * G;
   const float* xp = nullptr;
+  auto wf = [&](int kk, int f) { return MODE == GC_FILTER ? wsrc[PrepLayout::CR + kk * 32 + f] : wsrc[(kk & 31) * KK + (kk >> 5) * 32 + f]; };   // DH: B[f_in, k, g_out]
+  if (TC) stage_weights_tc(Ws, KK, wf); else stage_weights(Ws, KK, wf);
   if (MODE == GC_FILTER) {
-    stage_weights(Ws, KK, [&](int kk, int f) { return wsrc[PrepLayout::CR + kk * 32 + f]; });
     for (int i = threadIdx.x; i < MAXKG * 32; i += NT) Cas[i] = wsrc[PrepLayout::CA + i];
     if (threadIdx.x < 32) {
       Cst[threadIdx.x] = wsrc[PrepLayout::CR0 + threadIdx.x]; Cst[32 + threadIdx.x] = wsrc[PrepLayout::CA0 + threadIdx.x];
@@ -263,8 +317,6 @@ __global__ void __launch_bounds__(NT, 512 / NT) gather_contract_k(Gather3 gop, C
       Cst[128 + threadIdx.x] = mix_r[threadIdx.x]; Cst[160 + threadIdx.x] = mix_r[32 + threadIdx.x];
     }
     xp = tap_slot(xs, KG, G);
-  } else {
-    stage_weights(Ws, KK, [&](int kk, int f) { return wsrc[(kk & 31) * KK + (kk >> 5) * 32 + f]; });   // B[f_in, k, g_out]
   }
   for (Walk w(R, N, TM); w.more(); w.next()) {
     const int n0 = w.u * TM;
@@ -280,33 +332,81 @@ __global__ void __launch_bounds__(NT, 512 / NT) gather_contract_k(Gather3 gop, C
     }
     cp_wait<0>();
     __syncthreads();
-    float o[4][4];
-    tile_contract<KK>(As, LDA, Ws, o);
-    float4 c0r, c0a, a1a, a2a, a1r, a2r;
-    if (MODE == GC_FILTER) {
-      const float4* c4 = reinterpret_cast<const float4*>(Cst) + fg;
-      c0r = c4[0]; c0a = c4[8]; a1a = c4[16]; a2a = c4[24]; a1r = c4[32]; a2r = c4[40];
-    }
+    if (TC) {
+      float dd[4][4];
+      tile_contract_tc<KK>(As, LDA, Ws, dd);
+      const int g = lane >> 2, t = lane & 3;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int node = warp * 16 + ngl + 4 * i, n = n0 + node;
+      for (int h = 0; h < 2; ++h) {                 // rows g and g + 8 of the warp's 16 nodes
+        const int node = warp * 16 + g + 8 * h, n = n0 + node;
+        if (MODE == GC_FILTER) {
+          float s1 = 0.f, s2 = 0.f, s3 = 0.f, s4 = 0.f;
+          float2 wr2[4], wa2[4];
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) {
+            const int f = 8 * nt + 2 * t;
+            const float2 cr0 = *reinterpret_cast<const float2*>(Cst + f), ca0 = *reinterpret_cast<const float2*>(Cst + 32 + f);
+            wr2[nt] = make_float2(dd[nt][2 * h] + cr0.x, dd[nt][2 * h + 1] + cr0.y);
+            float2 wa = ca0;
+            for (int kg = 0; kg < KG; ++kg) {
+              const float xv = Xs[node * XS_LD + kg];
+              const float2 cw = *reinterpret_cast<const float2*>(Cas + kg * 32 + f);
+              wa.x = fmaf(xv, cw.x, wa.x); wa.y = fmaf(xv, cw.y, wa.y);
+            }
+            wa2[nt] = wa;
+            const float2 m1a = *reinterpret_cast<const float2*>(Cst + 64 + f), m2a = *reinterpret_cast<const float2*>(Cst + 96 + f);
+            const float2 m1r = *reinterpret_cast<const float2*>(Cst + 128 + f), m2r = *reinterpret_cast<const float2*>(Cst + 160 + f);
+            s1 = fmaf(m1a.x, wa.x, fmaf(m1a.y, wa.y, s1)); s2 = fmaf(m2a.x, wa.x, fmaf(m2a.y, wa.y, s2));
+            s3 = fmaf(m1r.x, wr2[nt].x, fmaf(m1r.y, wr2[nt].y, s3)); s4 = fmaf(m2r.x, wr2[nt].x, fmaf(m2r.y, wr2[nt].y, s4));
+          }
+#pragma unroll
+          for (int of = 2; of > 0; of >>= 1) {
+            s1 += __shfl_xor_sync(0xffffffffu, s1, of); s2 += __shfl_xor_sync(0xffffffffu, s2, of);
+            s3 += __shfl_xor_sync(0xffffffffu, s3, of); s4 += __shfl_xor_sync(0xffffffffu, s4, of);
+          }
+          if (n < N) {
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+              *reinterpret_cast<float2*>(out_a + (rb + n) * 32 + 8 * nt + 2 * t) = wa2[nt];
+              *reinterpret_cast<float2*>(out + (rb + n) * 32 + 8 * nt + 2 * t) = wr2[nt];
+            }
+            if (t == 0) rc[rb + n] = make_float4(s1, s2, s3, s4);
+          }
+        } else if (n < N) {
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt)
+            *reinterpret_cast<float2*>(out + (rb + n) * 32 + 8 * nt + 2 * t) = make_float2(dd[nt][2 * h], dd[nt][2 * h + 1]);
+        }
+      }
+    } else {
+      float o[4][4];
+      tile_contract<KK>(As, LDA, Ws, o);
+      float4 c0r, c0a, a1a, a2a, a1r, a2r;
       if (MODE == GC_FILTER) {
-        const float4 wr = make_float4(o[i][0] + c0r.x, o[i][1] + c0r.y, o[i][2] + c0r.z, o[i][3] + c0r.w);
-        float4 wa = c0a;
-        for (int kg = 0; kg < KG; ++kg) fma4(wa, Xs[node * XS_LD + kg], *reinterpret_cast<const float4*>(Cas + kg * 32 + 4 * fg));
-        float s1 = dot4(a1a, wa), s2 = dot4(a2a, wa), s3 = dot4(a1r, wr), s4 = dot4(a2r, wr);
-#pragma unroll
-        for (int of = 4; of > 0; of >>= 1) {
-          s1 += __shfl_xor_sync(0xffffffffu, s1, of); s2 += __shfl_xor_sync(0xffffffffu, s2, of);
-          s3 += __shfl_xor_sync(0xffffffffu, s3, of); s4 += __shfl_xor_sync(0xffffffffu, s4, of);
+        const float4* c4 = reinterpret_cast<const float4*>(Cst) + fg;
+        c0r = c4[0]; c0a = c4[8]; a1a = c4[16]; a2a = c4[24]; a1r = c4[32]; a2r = c4[40];
+      }
+  #pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int node = warp * 16 + ngl + 4 * i, n = n0 + node;
+        if (MODE == GC_FILTER) {
+          const float4 wr = make_float4(o[i][0] + c0r.x, o[i][1] + c0r.y, o[i][2] + c0r.z, o[i][3] + c0r.w);
+          float4 wa = c0a;
+          for (int kg = 0; kg < KG; ++kg) fma4(wa, Xs[node * XS_LD + kg], *reinterpret_cast<const float4*>(Cas + kg * 32 + 4 * fg));
+          float s1 = dot4(a1a, wa), s2 = dot4(a2a, wa), s3 = dot4(a1r, wr), s4 = dot4(a2r, wr);
+  #pragma unroll
+          for (int of = 4; of > 0; of >>= 1) {
+            s1 += __shfl_xor_sync(0xffffffffu, s1, of); s2 += __shfl_xor_sync(0xffffffffu, s2, of);
+            s3 += __shfl_xor_sync(0xffffffffu, s3, of); s4 += __shfl_xor_sync(0xffffffffu, s4, of);
+          }
+          if (n < N) {
+            reinterpret_cast<float4*>(out_a + (rb + n) * 32)[fg] = wa;
+            reinterpret_cast<float4*>(out + (rb + n) * 32)[fg] = wr;
+            if (fg == 0) rc[rb + n] = make_float4(s1, s2, s3, s4);
+          }
+        } else if (n < N) {
+          reinterpret_cast<float4*>(out + (rb + n) * 32)[fg] = make_float4(o[i][0], o[i][1], o[i][2], o[i][3]);
         }
-        if (n < N) {
-          reinterpret_cast<float4*>(out_a + (rb + n) * 32)[fg] = wa;
-          reinterpret_cast<float4*>(out + (rb + n) * 32)[fg] = wr;
-          if (fg == 0) rc[rb + n] = make_float4(s1, s2, s3, s4);
-        }
-      } else if (n < N) {
-        reinterpret_cast<float4*>(out + (rb + n) * 32)[fg] = make_float4(o[i][0], o[i][1], o[i][2], o[i][3]);
       }
     }
     __syncthreads();
@@ -504,7 +604,7 @@ __global__ void __launch_bounds__(256, 2) bwd_rows_v2_k(const int* __restrict__ 
 // overwritten by the gathered tap (which waits in registers meanwhile) - no shared memory of its own.
 template <int KST, int NT>
 __host__ __device__ constexpr int bwd_node_smem_floats() { return 32 * 32 + (NT / 2) * lda_of(KST) + (NT / 2) * LDD + (NT / 2) * XS_LD + MAXKG * 32; }
-template <int KST, int NT>
+template <int KST, int NT, bool TC>
 __global__ void __launch_bounds__(NT, NT == 128 ? 3 : 2) bwd_node_v2_k(Gather3 gop, Chain zc, Chain xs, int Kin, int G,
                                                         const float* __restrict__ pa, const float* __restrict__ pr, const float2* __restrict__ dr,
                                                         const float* __restrict__ wu_a, const float* __restrict__ wu_r,
@@ -522,9 +622,16 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 3 : 2) bwd_node_v2_k(Gather3 g
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, fg = lane & 7, ngl = lane >> 3;
   const int c = threadIdx.x & 7, slot = threadIdx.x >> 3;
   const int KG = Kin * G;
-  stage_weights(Ws, 32, [&](int f, int m) { return Wr[f * 32 + m]; });
+  auto wf = [&](int f, int m) { return Wr[f * 32 + m]; };
+  if (TC) stage_weights_tc(Ws, 32, wf); else stage_weights(Ws, 32, wf);
   const float* xp = tap_slot(xs, KG, G);
   for (int i = threadIdx.x; i < MAXKG * 32; i += NT) Mas[i] = 0.f;
+  // tensor-core outer products: warp = (16-feature half mh, quarter kq of the KK inputs), K dimension = the tile's nodes
+  static_assert(!TC || NT == 256, "the mma outer-product mapping assumes 8 warps");
+  const int mh = warp & 1, kq = warp >> 1;
+  float Mt[KST][4];
+#pragma unroll
+  for (int u = 0; u < KST; ++u) { Mt[u][0] = Mt[u][1] = Mt[u][2] = Mt[u][3] = 0.f; }
   float4 m1a = f4zero(), m1r = f4zero();
   float2 M[4][KST];                            // M[fi][u]: f = 4 ft + fi, kk = KPT kt + 2u (+1), partial over this thread's 64-node half
 #pragma unroll
@@ -574,42 +681,86 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 3 : 2) bwd_node_v2_k(Gather3 g
     store_tile<NT>(As, LDA, NS * 32, gz);
     cp_wait<0>();
     __syncthreads();
-    {                                            // d = W_r^T dWu_r
-      float o[4][4];
-      tile_contract<32>(Ds, LDD, Ws, o);
+    if (TC) {
+      {                                          // d = W_r^T dWu_r
+        float dd[4][4];
+        tile_contract_tc<32>(Ds, LDD, Ws, dd);
+        const int g = lane >> 2, t = lane & 3;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int n = n0 + warp * 16 + ngl + 4 * i;
-        if (n < N) reinterpret_cast<float4*>(dout + (rb + n) * 32)[fg] = make_float4(o[i][0], o[i][1], o[i][2], o[i][3]);
+        for (int h = 0; h < 2; ++h) {
+          const int n = n0 + warp * 16 + g + 8 * h;
+          if (n < N) {
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt)
+              *reinterpret_cast<float2*>(dout + (rb + n) * 32 + 8 * nt + 2 * t) = make_float2(dd[nt][2 * h], dd[nt][2 * h + 1]);
+          }
+        }
       }
-    }
-    {                                            // outer products: thread = 4 outputs f x KPT inputs kk, reduction over 64 nodes of the tile
-      const float* dp = Ds + nh * 64 * LDD + 4 * ft;
-      const float* zp = As + nh * 64 * LDA + KPT * kt;
-#pragma unroll 4
-      for (int node = 0; node < 64; ++node) {
-        const float4 d4 = *reinterpret_cast<const float4*>(dp + node * LDD);
+      {                                          // M[f][kk] += sum_node dWu_r[node][f] z[node][kk]  as  (Ds^T) (As)
+        const int g = lane >> 2, t = lane & 3;
+        const float* ap = Ds + t * LDD + 16 * mh + g;
+        const float* bp = As + t * LDA + kq * (KK / 4) + g;
+#pragma unroll 2
+        for (int ks = 0; ks < TM / 8; ++ks) {
+          uint32_t ah[4], al[4];
+          split_tf32(ap[(8 * ks) * LDD], ah[0], al[0]); split_tf32(ap[(8 * ks) * LDD + 8], ah[1], al[1]);
+          split_tf32(ap[(8 * ks + 4) * LDD], ah[2], al[2]); split_tf32(ap[(8 * ks + 4) * LDD + 8], ah[3], al[3]);
 #pragma unroll
-        for (int u = 0; u < KST; ++u) {
-          const float2 z2 = *reinterpret_cast<const float2*>(zp + node * LDA + 2 * u);
-          M[0][u] = __ffma2_rn(make_float2(d4.x, d4.x), z2, M[0][u]);
-          M[1][u] = __ffma2_rn(make_float2(d4.y, d4.y), z2, M[1][u]);
-          M[2][u] = __ffma2_rn(make_float2(d4.z, d4.z), z2, M[2][u]);
-          M[3][u] = __ffma2_rn(make_float2(d4.w, d4.w), z2, M[3][u]);
+          for (int u = 0; u < KST; ++u) {
+            uint32_t bh0, bl0, bh1, bl1;
+            split_tf32(bp[(8 * ks) * LDA + 8 * u], bh0, bl0); split_tf32(bp[(8 * ks + 4) * LDA + 8 * u], bh1, bl1);
+            mma3(Mt[u], ah, al, bh0, bh1, bl0, bl1);
+          }
+        }
+      }
+    } else {
+      {                                            // d = W_r^T dWu_r
+        float o[4][4];
+        tile_contract<32>(Ds, LDD, Ws, o);
+  #pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int n = n0 + warp * 16 + ngl + 4 * i;
+          if (n < N) reinterpret_cast<float4*>(dout + (rb + n) * 32)[fg] = make_float4(o[i][0], o[i][1], o[i][2], o[i][3]);
+        }
+      }
+      {                                            // outer products: thread = 4 outputs f x KPT inputs kk, reduction over 64 nodes of the tile
+        const float* dp = Ds + nh * 64 * LDD + 4 * ft;
+        const float* zp = As + nh * 64 * LDA + KPT * kt;
+  #pragma unroll 4
+        for (int node = 0; node < 64; ++node) {
+          const float4 d4 = *reinterpret_cast<const float4*>(dp + node * LDD);
+  #pragma unroll
+          for (int u = 0; u < KST; ++u) {
+            const float2 z2 = *reinterpret_cast<const float2*>(zp + node * LDA + 2 * u);
+            M[0][u] = __ffma2_rn(make_float2(d4.x, d4.x), z2, M[0][u]);
+            M[1][u] = __ffma2_rn(make_float2(d4.y, d4.y), z2, M[1][u]);
+            M[2][u] = __ffma2_rn(make_float2(d4.z, d4.z), z2, M[2][u]);
+            M[3][u] = __ffma2_rn(make_float2(d4.w, d4.w), z2, M[3][u]);
+          }
         }
       }
     }
     __syncthreads();
   }
   // partial sums of distinct M entries (per 64-node half): one global atomic per entry per thread
-#pragma unroll
-  for (int fi = 0; fi < 4; ++fi)
+  if (TC) {
+    const int g = lane >> 2, t = lane & 3;
 #pragma unroll
     for (int u = 0; u < KST; ++u) {
-      const int kk = KPT * kt + 2 * u, f = 4 * ft + fi;
-      atomicAdd(acc + AccLayout::M + kk * 32 + f, M[fi][u].x);
-      atomicAdd(acc + AccLayout::M + (kk + 1) * 32 + f, M[fi][u].y);
+      const int kk = kq * (KK / 4) + 8 * u + 2 * t, f = 16 * mh + g;
+      atomicAdd(acc + AccLayout::M + kk * 32 + f, Mt[u][0]); atomicAdd(acc + AccLayout::M + (kk + 1) * 32 + f, Mt[u][1]);
+      atomicAdd(acc + AccLayout::M + kk * 32 + f + 8, Mt[u][2]); atomicAdd(acc + AccLayout::M + (kk + 1) * 32 + f + 8, Mt[u][3]);
     }
+  } else {
+#pragma unroll
+    for (int fi = 0; fi < 4; ++fi)
+#pragma unroll
+      for (int u = 0; u < KST; ++u) {
+        const int kk = KPT * kt + 2 * u, f = 4 * ft + fi;
+        atomicAdd(acc + AccLayout::M + kk * 32 + f, M[fi][u].x);
+        atomicAdd(acc + AccLayout::M + (kk + 1) * 32 + f, M[fi][u].y);
+      }
+  }
   for (int i = threadIdx.x; i < KG * 32; i += NT) atomicAdd(acc + AccLayout::MA + i, Mas[i]);   // last tile ended with a barrier
   atomicAdd(acc + AccLayout::SUMA + lane, suma); atomicAdd(acc + AccLayout::SUMR + lane, sumr);
   float m[8] = {m1a.x, m1a.y, m1a.z, m1a.w, m1r.x, m1r.y, m1r.z, m1r.w};

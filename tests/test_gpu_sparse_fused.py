@@ -112,20 +112,21 @@ def test_fused_stage_generations_vs_oracle(mask):
         L.gcrnn_debug_set_option(b'sparse_v2', old)
 
 
-@pytest.mark.parametrize('nt,bps', [(128, 1), (128, 4), (256, 1), (256, 2)])
-def test_fused_tile_kernels_any_block_shape(nt, bps):
-    """The tile kernels come in two block shapes (128 threads on 64-node tiles, 256 threads on 128-node tiles) and any number
-    of resident blocks per SM (grid size / shared-memory carve-out): results must not depend on either."""
+@pytest.mark.parametrize('tc,bps', [(1, 1), (1, 2), (0, 1), (0, 2)])
+def test_fused_tile_kernels_contraction_modes(tc, bps):
+    """The tile kernels contract either on tensor cores (3xTF32 mma.sync with error compensation, the default) or with packed
+    fp32 FFMA2, at any number of resident blocks per SM (grid size / shared-memory carve-out): both hold the fp32 path's bounds
+    (1e-5 on H, 1e-4 on gradients vs the fp64 oracle) for every supported tap count."""
     L = _lib.lib()
     old_bps = L.gcrnn_debug_set_option(b'sparse_v2_bps', bps)
-    old_nt = L.gcrnn_debug_set_option(b'sparse_v2_nt', nt)
+    old_tc = L.gcrnn_debug_set_option(b'sparse_v2_tc', tc)
     try:
         run_case(N=300, G_=1, Kin=3, Kst=3, T=3, B=2, bias=True, seed=31, expect_path=PATH_NODE32)
         run_case(N=200, G_=2, Kin=2, Kst=4, T=2, B=2, bias=True, seed=32, expect_path=PATH_NODE32)
         run_case(N=170, G_=4, Kin=4, Kst=2, T=2, B=2, bias=True, seed=33, expect_path=PATH_NODE32)
     finally:
         L.gcrnn_debug_set_option(b'sparse_v2_bps', old_bps)
-        L.gcrnn_debug_set_option(b'sparse_v2_nt', old_nt)
+        L.gcrnn_debug_set_option(b'sparse_v2_tc', old_tc)
 
 
 def test_fused_matches_generic_kernels_and_falls_back_for_dX():
