@@ -12,6 +12,7 @@ int g_opt_sparse_fused = 1;
 int g_opt_sparse_v2 = 63;
 int g_opt_sparse_v2_bps = 2;
 int g_opt_sparse_v2_tc = 1;
+int g_opt_sparse_v2_rows_bps = 2;
 int g_opt_graph_capture = 1;
 void set_last_error(const char* fmt, ...) {
   va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof g_err, fmt, ap); va_end(ap);
@@ -122,6 +123,7 @@ int gcrnn_debug_set_option(const char* name, int32_t value) {
   if (name && std::string(name) == "bwd_fused") { int old = gcrnn::g_opt_bwd_fused; gcrnn::g_opt_bwd_fused = value; return old; }
   if (name && std::string(name) == "sparse_fused") { int old = gcrnn::g_opt_sparse_fused; gcrnn::g_opt_sparse_fused = value; return old; }
   if (name && std::string(name) == "sparse_v2") { int old = gcrnn::g_opt_sparse_v2; gcrnn::g_opt_sparse_v2 = value; return old; }
+  if (name && std::string(name) == "sparse_v2_rows_bps") { int old = gcrnn::g_opt_sparse_v2_rows_bps; gcrnn::g_opt_sparse_v2_rows_bps = value; return old; }
   if (name && std::string(name) == "sparse_v2_tc") { int old = gcrnn::g_opt_sparse_v2_tc; gcrnn::g_opt_sparse_v2_tc = value; return old; }
   if (name && std::string(name) == "sparse_v2_bps") { int old = gcrnn::g_opt_sparse_v2_bps; gcrnn::g_opt_sparse_v2_bps = value; return old; }
   if (name && std::string(name) == "graph_capture") { int old = gcrnn::g_opt_graph_capture; gcrnn::g_opt_graph_capture = value; return old; }

@@ -551,7 +551,8 @@ void e32_backward_steps(const Ctx& c, const CellDims& d, const gcrnn_cell_params
   auto k_node = tc ? e32::bwd_node_v2_k<KST, 256, true> : e32::bwd_node_v2_k<KST, 256, false>;
   const int g_dh2 = v2(V2_DH) ? tile_grid(k_dh, 256, dh_smem, tile_bps(), tiles) : 0;
   const int g_node2 = v2(V2_NODE) ? tile_grid(k_node, 256, node_smem, tile_bps(), tiles) : 0;
-  const int g_rows2 = v2(V2_ROWS) ? tile_grid(e32::bwd_rows_v2_k, 256, 0, 2, groups) : 0;
+  auto k_rows = g_opt_sparse_v2_rows_bps == 3 ? e32::bwd_rows_v2_k<3> : e32::bwd_rows_v2_k<2>;     // 3: more warps, some spills
+  const int g_rows2 = v2(V2_ROWS) ? tile_grid(k_rows, 256, 0, g_opt_sparse_v2_rows_bps == 3 ? 3 : 2, groups) : 0;
   for (long long t = d.T - 1; t >= 0; --t) {
     const float* hn = s.Hn + t * BNF;
     const float* wa = x.wu_a + t * BNF; const float* wr = x.wu_r + t * BNF;
@@ -561,7 +562,7 @@ void e32_backward_steps(const Ctx& c, const CellDims& d, const gcrnn_cell_params
     check_launch();
     zero(c, b.dr, BN * sizeof(float2));
     if (v2(V2_ROWS))
-      e32::bwd_rows_v2_k<<<g_rows2, 256, 0, c.st>>>(g->att_rptr, g->att_col, g->att_val, info, reinterpret_cast<const float2*>(info + BN), wa, wr, b.dya, b.dyr,
+      k_rows<<<g_rows2, 256, 0, c.st>>>(g->att_rptr, g->att_col, g->att_val, info, reinterpret_cast<const float2*>(info + BN), wa, wr, b.dya, b.dyr,
                                                     p->e_mixer[0], p->e_mixer[1], b.pa, b.pr, b.dr, b.acc, d.N, d.B);
     else
       e32::bwd_rows_k<<<g_rows, 128, rows_smem, c.st>>>(g->att_rptr, g->att_col, g->att_val, info, wa, wr, b.dya, b.dyr,

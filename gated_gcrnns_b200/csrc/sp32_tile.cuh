@@ -233,13 +233,15 @@ __device__ __forceinline__ void tile_contract(const float* __restrict__ tile, in
 
 
 // ---- 3xTF32 tensor-core contraction (mma.sync.m16n8k8, fp32 accumulate) ---------------------------------------------------
-// x = hi + lo with hi = tf32(x), lo = tf32(x - hi): a b ~= a_lo b_hi + a_hi b_lo + a_hi b_hi keeps ~2^-21 relative error per
+// x = hi + lo with hi = tf32(x), lo = x - hi (truncated to tf32 by the hardware): a b ~= a_lo b_hi + a_hi b_lo + a_hi b_hi keeps ~2^-21 relative error per
 // product, i.e. fp32-class accuracy (the stated 1e-5 / 1e-4 bounds of the fp32 path hold, see tests), while the operands come
 // out of shared memory as conflict-free fragments: 12 wavefronts per 16 x 32 x 8 block instead of 32 for the FFMA2 tile.
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
-  const float r = x - __uint_as_float(hi);
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+  // hi = x rounded to 10 mantissa bits (round half away, as cvt.rna.tf32 does - which sm_100 emulates with 4+ instructions
+  // because of its Inf/NaN path; the signals here are finite); lo = x - hi is exact in fp32 and the tensor core ignores its
+  // low 13 mantissa bits itself, so it needs no rounding of its own.  3 instructions per element.
+  hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
 }
 __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -500,7 +502,8 @@ __global__ void __launch_bounds__(256, 4) aggregate_v2_k(const int* __restrict__
 //   dr_j += ds_ij (atomics), dc_i = sum_j ds_ij,  p_g[i,:] = sum_j S'_ij al_ij dy_g[j,:] + a2_g dc_i,  m2_g += dc_i Wu_g[i,:]
 // Eight lanes per row; lane c keeps the edge data of edges c, 8 + c, 16 + c, 24 + c (row degree of S + I <= 32); the
 // eight dot products of a batch are reduced "transposed" (7 shuffles) so that edge (batch + c) lands on lane c.
-__global__ void __launch_bounds__(256, 2) bwd_rows_v2_k(const int* __restrict__ rptr, const int* __restrict__ col, const float* __restrict__ val,
+template <int BPS>
+__global__ void __launch_bounds__(256, BPS) bwd_rows_v2_k(const int* __restrict__ rptr, const int* __restrict__ col, const float* __restrict__ val,
                                                         const float4* __restrict__ cl, const float2* __restrict__ rr,
                                                         const float* __restrict__ wu_a, const float* __restrict__ wu_r,
                                                         const float* __restrict__ dya, const float* __restrict__ dyr,

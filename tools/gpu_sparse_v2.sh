@@ -1,9 +1,9 @@
 #!/bin/bash
 # sparse (cfg5) visit for the second-generation kernels: stage-by-stage parity, A/B bench, launch list, one full ncu capture
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_sparse_fused.py -q -x -k "not 100000" > gpurun_out/pytest_sparse_v2.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_sparse_v2.log
+timeout 900 python -m pytest tests/test_gpu_sparse_fused.py -q -x  > gpurun_out/pytest_sparse_v2.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_sparse_v2.log
 tail -25 gpurun_out/pytest_sparse_v2.log
-for cfgopt in ${BENCH_OPTS:-"sparse_v2_tc=1" "sparse_v2_tc=0"}; do
+for cfgopt in ${BENCH_OPTS:-"sparse_v2_tc=1" "sparse_v2_rows_bps=3"}; do
   timeout 400 python bench.py --workload cfg5 --batch 64 --steps 2 --warmup 1 --opt $cfgopt > gpurun_out/bench_cfg5_$cfgopt.json 2> gpurun_out/bench_cfg5_$cfgopt.err
   echo "== $cfgopt"; cut -c1-260 gpurun_out/bench_cfg5_$cfgopt.json; tail -3 gpurun_out/bench_cfg5_$cfgopt.err | grep -v Warn | grep -v sparse_csr
 done
