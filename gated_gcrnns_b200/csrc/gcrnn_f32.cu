@@ -33,7 +33,7 @@ void check_launch() { ++g_launches; CUDA_OK(cudaGetLastError()); }
 void transpose(const Ctx& c, const float* in, const float* add, float* out, int A, int Bd, long long R1, long long R2,
                long long is1, long long is2, long long os1, long long os2) {
   if (c.dry) return;
-  dim3 grid((Bd + 31) / 32, (A + 31) / 32, (unsigned)std::min<long long>(R1 * R2, 32768));
+  dim3 grid((Bd + 31) / 32, ((A + 31) / 32 + TRANSPOSE_TY - 1) / TRANSPOSE_TY, (unsigned)std::min<long long>(R1 * R2, 32768));
   transpose_k<<<grid, dim3(32, 8), 0, c.st>>>(in, add, out, A, Bd, R1, R2, is1, is2, os1, os2);
   check_launch();
 }

@@ -23,6 +23,8 @@ static inline int grid1d(long long total, int block, int max_blocks = 148 * 16) 
 
 // ---- batched 2-D transpose: out[r][b][a] = in[r][a][b] (+ add[r][b][a]) --------------------------------
 // r = r1*R2 + r2 with independent in/out strides so that [T,B,..] <-> [B,T,..] re-orderings fuse in.
+constexpr int TRANSPOSE_TY = 8;     // 32 x 32 tiles per block along A: a block moves 32 KB instead of 4 KB (millions of 4 KB blocks
+                                    // are bound by block scheduling, not by HBM: 1.7 TB/s measured at cfg5's H)
 __global__ void transpose_k(const float* __restrict__ in, const float* add, float* out, int A, int Bd,
                             long long R1, long long R2, long long is1, long long is2, long long os1, long long os2) {
   __shared__ float tile[32][33];
@@ -31,22 +33,26 @@ __global__ void transpose_k(const float* __restrict__ in, const float* add, floa
     const long long r1 = r / R2, r2 = r % R2;
     const float* ip = in + r1 * is1 + r2 * is2;
     const long long oo = r1 * os1 + r2 * os2;
-    const int b0 = blockIdx.x * 32, a0 = blockIdx.y * 32;
-    for (int i = threadIdx.y; i < 32; i += 8) {
-      int a = a0 + i, b = b0 + threadIdx.x;
-      if (a < A && b < Bd) tile[i][threadIdx.x] = ip[(long long)a * Bd + b];
-    }
-    __syncthreads();
-    for (int i = threadIdx.y; i < 32; i += 8) {
-      int b = b0 + i, a = a0 + threadIdx.x;
-      if (a < A && b < Bd) {
-        long long o = oo + (long long)b * A + a;
-        float v = tile[threadIdx.x][i];
-        if (add) v += add[o];
-        out[o] = v;
+    const int b0 = blockIdx.x * 32;
+    for (int ty = 0; ty < TRANSPOSE_TY; ++ty) {
+      const int a0 = (blockIdx.y * TRANSPOSE_TY + ty) * 32;
+      if (a0 >= A) break;                         // uniform across the block
+      for (int i = threadIdx.y; i < 32; i += 8) {
+        int a = a0 + i, b = b0 + threadIdx.x;
+        if (a < A && b < Bd) tile[i][threadIdx.x] = ip[(long long)a * Bd + b];
       }
+      __syncthreads();
+      for (int i = threadIdx.y; i < 32; i += 8) {
+        int b = b0 + i, a = a0 + threadIdx.x;
+        if (a < A && b < Bd) {
+          long long o = oo + (long long)b * A + a;
+          float v = tile[threadIdx.x][i];
+          if (add) v += add[o];
+          out[o] = v;
+        }
+      }
+      __syncthreads();
     }
-    __syncthreads();
   }
 }
 
