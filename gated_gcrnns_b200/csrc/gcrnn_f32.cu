@@ -33,6 +33,13 @@ void check_launch() { ++g_launches; CUDA_OK(cudaGetLastError()); }
 void transpose(const Ctx& c, const float* in, const float* add, float* out, int A, int Bd, long long R1, long long R2,
                long long is1, long long is2, long long os1, long long os2) {
   if (c.dry) return;
+  if (A == 1 || Bd == 1) {                          // nothing to transpose inside a slab: strided batch of contiguous copies
+    const long long L = (long long)A * Bd;
+    dim3 grid((unsigned)std::min<long long>((L + 1023) / 1024, 64), (unsigned)std::min<long long>(R1 * R2, 32768));
+    strided_copy_k<<<grid, 256, 0, c.st>>>(in, add, out, L, R1, R2, is1, is2, os1, os2);
+    check_launch();
+    return;
+  }
   dim3 grid((Bd + 31) / 32, ((A + 31) / 32 + TRANSPOSE_TY - 1) / TRANSPOSE_TY, (unsigned)std::min<long long>(R1 * R2, 32768));
   transpose_k<<<grid, dim3(32, 8), 0, c.st>>>(in, add, out, A, Bd, R1, R2, is1, is2, os1, os2);
   check_launch();
@@ -512,10 +519,24 @@ size_t cell_forward_e32(const gcrnn_cell* cell, const gcrnn_cell_params* p, cons
   GCRNN_CHECK(a.dry() || saved, "forward needs the `saved` buffer (see gcrnn_cell_workspace_bytes)");
   float* prep = a.get<float>(e32::PrepLayout::TOTAL);
   float4* rc = a.get<float4>(d.B * d.N);
+  // x-tap chain through a node-major detour ([T*B][N*G] -> [N][G*T*B]): a neighbour is G*T*B contiguous floats there, so the
+  // shift is a coalesced row gather instead of 4-byte gathers (L1-bound: 3.5 ms per tap at cfg5)
+  const bool detour = d.Kin > 1 && d.TB * d.G >= 32;
+  float* xa = detour ? a.get<float>(d.TB * d.NG) : nullptr;
+  float* xb = detour ? a.get<float>(d.TB * d.NG) : nullptr;
   if (a.dry()) return a.off;
   transpose(c, X, nullptr, s.Xn, d.G, d.N, d.B, d.T, d.T * d.NG, d.NG, d.NG, d.B * d.NG);          // [B,T,G,N] -> [T,B,N,G]
   transpose(c, h0, nullptr, s.h0n, d.F, d.N, d.B, 1, d.NF, 0, d.NF, 0);                            // [B,F,N]  -> [B,N,F]
-  shift_chain(c, s.Xn, s.zx, d.E, d.Kin, d.G, d.TB);
+  if (detour) {
+    transpose(c, s.Xn, nullptr, xa, (int)d.TB, (int)d.NG, 1, 1, 0, 0, 0, 0);                       // [TB][N*G] -> [N*G][TB]
+    for (int k = 1; k < d.Kin; ++k) {
+      spmm(c, cell->g->fwd[0], xa, nullptr, xb, (int)(d.G * d.TB), 1);
+      transpose(c, xb, nullptr, s.zx + (long long)(k - 1) * d.TB * d.NG, (int)d.NG, (int)d.TB, 1, 1, 0, 0, 0, 0);
+      std::swap(xa, xb);
+    }
+  } else {
+    shift_chain(c, s.Xn, s.zx, d.E, d.Kin, d.G, d.TB);
+  }
   e32::prep_k<<<1, 1024, 0, st>>>(p->weight_A, p->weight_B, p->bias, p->e_weight[0], p->e_weight[1], prep, d.Kin * d.G, d.Kst);
   check_launch();
   switch (d.Kst) {

@@ -56,6 +56,22 @@ __global__ void transpose_k(const float* __restrict__ in, const float* add, floa
   }
 }
 
+// degenerate transposes (A == 1 or Bd == 1): a strided batch of contiguous copies, out[oo + i] = in[ip + i], i < L
+__global__ void strided_copy_k(const float* __restrict__ in, const float* add, float* out, long long L,
+                               long long R1, long long R2, long long is1, long long is2, long long os1, long long os2) {
+  const long long R = R1 * R2;
+  for (long long r = blockIdx.y; r < R; r += gridDim.y) {
+    const long long r1 = r / R2, r2 = r % R2;
+    const float* ip = in + r1 * is1 + r2 * is2;
+    const long long oo = r1 * os1 + r2 * os2;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < L; i += (long long)gridDim.x * blockDim.x) {
+      float v = ip[i];
+      if (add) v += add[oo + i];
+      out[oo + i] = v;
+    }
+  }
+}
+
 // ---- sparse shift (SpMM), node-major: out[r,d,:] = add[r,d,:] + sum_p val[p] * in[r, idx[p], :] --------
 template <int VEC>
 __global__ void spmm_k(const int* __restrict__ ptr, const int* __restrict__ idx, const float* __restrict__ val,
