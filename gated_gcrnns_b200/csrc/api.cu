@@ -12,6 +12,7 @@ int g_opt_sparse_fused = 1;
 int g_opt_sparse_v2 = 63;
 int g_opt_sparse_v2_bps = 2;
 int g_opt_sparse_v2_tc = 1;
+int g_opt_sparse_v2_fuse_dpre = 1;
 int g_opt_sparse_v2_rows_bps = 2;
 int g_opt_graph_capture = 1;
 void set_last_error(const char* fmt, ...) {
@@ -124,6 +125,7 @@ int gcrnn_debug_set_option(const char* name, int32_t value) {
   if (name && std::string(name) == "sparse_fused") { int old = gcrnn::g_opt_sparse_fused; gcrnn::g_opt_sparse_fused = value; return old; }
   if (name && std::string(name) == "sparse_v2") { int old = gcrnn::g_opt_sparse_v2; gcrnn::g_opt_sparse_v2 = value; return old; }
   if (name && std::string(name) == "sparse_v2_rows_bps") { int old = gcrnn::g_opt_sparse_v2_rows_bps; gcrnn::g_opt_sparse_v2_rows_bps = value; return old; }
+  if (name && std::string(name) == "sparse_v2_fuse_dpre") { int old = gcrnn::g_opt_sparse_v2_fuse_dpre; gcrnn::g_opt_sparse_v2_fuse_dpre = value; return old; }
   if (name && std::string(name) == "sparse_v2_tc") { int old = gcrnn::g_opt_sparse_v2_tc; gcrnn::g_opt_sparse_v2_tc = value; return old; }
   if (name && std::string(name) == "sparse_v2_bps") { int old = gcrnn::g_opt_sparse_v2_bps; gcrnn::g_opt_sparse_v2_bps = value; return old; }
   if (name && std::string(name) == "graph_capture") { int old = gcrnn::g_opt_graph_capture; gcrnn::g_opt_graph_capture = value; return old; }

@@ -18,6 +18,7 @@ extern int g_opt_bwd_fused;            // 1: fused reverse-time step kernel (tc_
 extern int g_opt_sparse_fused;         // 1: fused F == 32 edge-gated sparse kernels (sp32_kernels.cuh) when the shape allows
 extern int g_opt_sparse_v2;            // bit mask: which fused sparse stages run their second-generation kernel (sp32_tile.cuh); 63 = all
 extern int g_opt_sparse_v2_rows_bps;   // resident blocks per SM of bwd_rows_v2_k (2 or 3)
+extern int g_opt_sparse_v2_fuse_dpre;  // 1: the dh kernel finishes the next reverse step's dpre in its epilogue
 extern int g_opt_sparse_v2_tc;         // 1: tile contractions on tensor cores (3xTF32 mma.sync), 0: packed FFMA2
 extern int g_opt_sparse_v2_bps;        // resident blocks per SM of the tile kernels (the rest of the 228 KB stays L1)
 extern int g_opt_graph_capture;        // 1: replay small fp32 cell calls as CUDA graphs keyed by their pointer set (api.cu)

@@ -484,7 +484,8 @@ void e32_forward_steps(const Ctx& c, const CellDims& d, const gcrnn_cell_params*
     float* wa = x.wu_a + t * BNF; float* wr = x.wu_r + t * BNF;
     float4* info = x.info + 2 * t * BN;
     if (v2(V2_FILTER))
-      k_filter<<<g_filter2, 256, gc_smem, c.st>>>(gop, zc, x_taps(d, s, t), d.Kin, d.G, prep, p->e_mixer[0], p->e_mixer[1], wa, wr, rc, d.N, d.B);
+      k_filter<<<g_filter2, 256, gc_smem, c.st>>>(gop, zc, x_taps(d, s, t), d.Kin, d.G, prep, p->e_mixer[0], p->e_mixer[1], wa, wr, rc, d.N, d.B,
+                                                  e32::DpreFuse{});
     else
       e32::filter_fwd_k<KST><<<g_filter, 128, 0, c.st>>>(gop, zc, x_taps(d, s, t), d.Kin, d.G, prep,
                                                        p->e_mixer[0], p->e_mixer[1], wa, wr, rc, d.N, BN);
@@ -571,6 +572,7 @@ void e32_backward_steps(const Ctx& c, const CellDims& d, const gcrnn_cell_params
   auto k_dh = tc ? e32::gather_contract_k<KST, e32::GC_DH, 256, true> : e32::gather_contract_k<KST, e32::GC_DH, 256, false>;
   auto k_node = tc ? e32::bwd_node_v2_k<KST, 256, true> : e32::bwd_node_v2_k<KST, 256, false>;
   const int g_dh2 = v2(V2_DH) ? tile_grid(k_dh, 256, dh_smem, tile_bps(), tiles) : 0;
+  const bool fuse_dpre = tc && v2(V2_DH) && g_opt_sparse_v2_fuse_dpre;     // dh epilogue finishes the next step's dpre (t = 0 still writes dh0)
   const int g_node2 = v2(V2_NODE) ? tile_grid(k_node, 256, node_smem, tile_bps(), tiles) : 0;
   auto k_rows = g_opt_sparse_v2_rows_bps == 3 ? e32::bwd_rows_v2_k<3> : e32::bwd_rows_v2_k<2>;     // 3: more warps, some spills
   const int g_rows2 = v2(V2_ROWS) ? tile_grid(k_rows, 256, 0, g_opt_sparse_v2_rows_bps == 3 ? 3 : 2, groups) : 0;
@@ -578,9 +580,11 @@ void e32_backward_steps(const Ctx& c, const CellDims& d, const gcrnn_cell_params
     const float* hn = s.Hn + t * BNF;
     const float* wa = x.wu_a + t * BNF; const float* wr = x.wu_r + t * BNF;
     const float4* info = x.info + 2 * t * BN;
-    e32::dpre_k<<<g_dpre, 256, 0, c.st>>>(dH + t * d.NF, d.T * d.NF, t == d.T - 1 ? nullptr : b.dhrec, hn, x.masks + t * BN, b.dya, b.dyr,
-                                          d.N, d.B);
-    check_launch();
+    if (!(fuse_dpre && t < d.T - 1)) {            // otherwise the dh kernel of step t+1 already left dya / dyr of this step
+      e32::dpre_k<<<g_dpre, 256, 0, c.st>>>(dH + t * d.NF, d.T * d.NF, t == d.T - 1 ? nullptr : b.dhrec, hn, x.masks + t * BN, b.dya, b.dyr,
+                                            d.N, d.B);
+      check_launch();
+    }
     zero(c, b.dr, BN * sizeof(float2));
     if (v2(V2_ROWS))
       k_rows<<<g_rows2, 256, 0, c.st>>>(g->att_rptr, g->att_col, g->att_val, info, reinterpret_cast<const float2*>(info + BN), wa, wr, b.dya, b.dyr,
@@ -607,7 +611,9 @@ void e32_backward_steps(const Ctx& c, const CellDims& d, const gcrnn_cell_params
       wc.p[k] = out;
     }
     if (v2(V2_DH))
-      k_dh<<<g_dh2, 256, dh_smem, c.st>>>(gbw, wc, e32::Chain{}, 0, 1, p->weight_B, nullptr, nullptr, nullptr, b.dhrec, nullptr, d.N, d.B);
+      k_dh<<<g_dh2, 256, dh_smem, c.st>>>(gbw, wc, e32::Chain{}, 0, 1, p->weight_B, nullptr, nullptr, nullptr, b.dhrec, nullptr, d.N, d.B,
+                                          (fuse_dpre && t > 0) ? e32::DpreFuse{dH + (t - 1) * d.NF, d.T * d.NF, s.Hn + (t - 1) * BNF, x.masks + (t - 1) * BN, b.dya, b.dyr}
+                                                               : e32::DpreFuse{});
     else
       e32::dh_k<KST><<<g_dh, 128, 0, c.st>>>(gbw, wc, p->weight_B, b.dhrec, d.N, BN);
     check_launch();

@@ -289,6 +289,14 @@ __device__ __forceinline__ void tile_contract_tc(const float* __restrict__ tile,
 //   Wu_a = Ca x-taps + ca0, rc = (a1.Wu_a, a2.Wu_a, a1.Wu_r, a2.Wu_r);  weights from the folded `prep` block.
 // GC_DH (backward stage 3): dh_{t-1}[n,g] = sum_k sum_f B[f,k,g] w_k[n,f], w_{KST-1} = w_{KST-2} S^T gathered into the tile.
 enum { GC_FILTER = 0, GC_DH = 1 };
+// GC_DH can finish the NEXT reverse step's dpre in its epilogue (tensor-core variant): with dh = dh_{t-1} in registers,
+//   g = (dH[b,t-1,f,n] + dh[n,f]) (1 - h_{t-1}[n,f]^2),  dya = g [y_a > 0],  dyr = g [y_r > 0]   (what dpre_k computes from a stored dh)
+// dHt == nullptr: plain mode (dh is written to `out`).
+struct DpreFuse {
+  const float* dHt; long long sample_stride;      // dH + (t-1) F N in the reference layout [B,T,F,N]
+  const float* hn; const uint2* masks;            // h_{t-1} [B,N,32] and its relu masks
+  float* dya; float* dyr;
+};
 template <int KST, int NT>
 __host__ __device__ constexpr int gc_smem_floats(int mode) {
   return KST * 32 * 32 + (NT / 2) * lda_of(KST) + (mode == GC_FILTER ? (NT / 2) * XS_LD + MAXKG * 32 + 6 * 32 : 0);
@@ -298,7 +306,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) gather_contract_k(Gather3 gop, C
                                                             const float* __restrict__ wsrc /* FILTER: prep, DH: weight_B */,
                                                             const float* __restrict__ mix_a, const float* __restrict__ mix_r,
                                                             float* __restrict__ out_a /* FILTER: Wu_a */, float* __restrict__ out /* FILTER: Wu_r, DH: dh */,
-                                                            float4* __restrict__ rc, int N, long long R) {
+                                                            float4* __restrict__ rc, int N, long long R, DpreFuse fz) {
   constexpr int KK = KST * 32, LDA = lda_of(KST), NS = KST - 1, TM = NT / 2;
   extern __shared__ __align__(16) float dyn[];
   float* Ws = dyn;                       // [KK/2][2][8] float4
@@ -375,9 +383,25 @@ __global__ void __launch_bounds__(NT, 512 / NT) gather_contract_k(Gather3 gop, C
             if (t == 0) rc[rb + n] = make_float4(s1, s2, s3, s4);
           }
         } else if (n < N) {
+          if (fz.dHt != nullptr) {                  // fused dpre of the next reverse step
+            const uint2 mk = fz.masks[rb + n];
+            const float* dHp = fz.dHt + w.r * fz.sample_stride + n;
 #pragma unroll
-          for (int nt = 0; nt < 4; ++nt)
-            *reinterpret_cast<float2*>(out + (rb + n) * 32 + 8 * nt + 2 * t) = make_float2(dd[nt][2 * h], dd[nt][2 * h + 1]);
+            for (int nt = 0; nt < 4; ++nt) {
+              const int f = 8 * nt + 2 * t;          // features f, f + 1: mask bits 8 (f & 3) + (f >> 2)
+              const size_t o = (rb + n) * 32 + f;
+              const float2 hv = *reinterpret_cast<const float2*>(fz.hn + o);
+              const float g0 = (__ldg(dHp + (size_t)f * N) + dd[nt][2 * h]) * (1.f - hv.x * hv.x);
+              const float g1 = (__ldg(dHp + (size_t)(f + 1) * N) + dd[nt][2 * h + 1]) * (1.f - hv.y * hv.y);
+              const int b0 = 8 * (f & 3) + (f >> 2), b1 = 8 * ((f + 1) & 3) + ((f + 1) >> 2);
+              *reinterpret_cast<float2*>(fz.dya + o) = make_float2(((mk.x >> b0) & 1u) ? g0 : 0.f, ((mk.x >> b1) & 1u) ? g1 : 0.f);
+              *reinterpret_cast<float2*>(fz.dyr + o) = make_float2(((mk.y >> b0) & 1u) ? g0 : 0.f, ((mk.y >> b1) & 1u) ? g1 : 0.f);
+            }
+          } else {
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt)
+              *reinterpret_cast<float2*>(out + (rb + n) * 32 + 8 * nt + 2 * t) = make_float2(dd[nt][2 * h], dd[nt][2 * h + 1]);
+          }
         }
       }
     } else {

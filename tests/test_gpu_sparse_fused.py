@@ -129,6 +129,21 @@ def test_fused_tile_kernels_contraction_modes(tc, bps):
         L.gcrnn_debug_set_option(b'sparse_v2_tc', old_tc)
 
 
+def test_fused_dpre_epilogue_matches_separate_kernel():
+    """By default the dh kernel of reverse step t finishes step t-1's dpre (dH + dh, tanh', relu masks) in its epilogue; with the
+    option off a separate dpre_k runs from a stored dh.  Same oracle bounds either way, and the two agree to rounding."""
+    L = _lib.lib()
+    _, H1, g1 = run_case(N=260, G_=1, Kin=3, Kst=3, T=6, B=3, bias=True, seed=41, expect_path=PATH_NODE32)
+    old = L.gcrnn_debug_set_option(b'sparse_v2_fuse_dpre', 0)
+    try:
+        _, H0, g0 = run_case(N=260, G_=1, Kin=3, Kst=3, T=6, B=3, bias=True, seed=41, expect_path=PATH_NODE32)
+    finally:
+        L.gcrnn_debug_set_option(b'sparse_v2_fuse_dpre', old)
+    assert torch.equal(H0, H1)
+    for k in g0:
+        assert relerr(g1[k], g0[k]) < 1e-5, k
+
+
 def test_fused_matches_generic_kernels_and_falls_back_for_dX():
     L = _lib.lib()
     old = L.gcrnn_debug_set_option(b'sparse_fused', 0)
