@@ -40,6 +40,12 @@ void transpose(const Ctx& c, const float* in, const float* add, float* out, int 
     check_launch();
     return;
   }
+  if (Bd == 32 && A >= 1024 && add == nullptr && ((uintptr_t)in % 16 == 0) && is1 % 4 == 0 && is2 % 4 == 0) {
+    const long long work = R1 * R2 * ((A + 127) / 128);
+    transpose_c32_k<<<(unsigned)std::min<long long>(work, 148LL * 64), 256, 0, c.st>>>(in, out, A, R1, R2, is1, is2, os1, os2);
+    check_launch();
+    return;
+  }
   dim3 grid((Bd + 31) / 32, ((A + 31) / 32 + TRANSPOSE_TY - 1) / TRANSPOSE_TY, (unsigned)std::min<long long>(R1 * R2, 32768));
   transpose_k<<<grid, dim3(32, 8), 0, c.st>>>(in, add, out, A, Bd, R1, R2, is1, is2, os1, os2);
   check_launch();

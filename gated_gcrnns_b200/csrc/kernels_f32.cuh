@@ -56,6 +56,44 @@ __global__ void transpose_k(const float* __restrict__ in, const float* add, floa
   }
 }
 
+// node-major -> feature-major with 32 channels: in[r][a][32] -> out[r][32][a].  A block moves a 128 x 32 tile with 16 KB of
+// float4 loads in flight (the generic 32 x 32 tiles leave HBM latency-bound at ~3 TB/s); same (r1, r2) stride interface.
+__global__ void __launch_bounds__(256) transpose_c32_k(const float* __restrict__ in, float* __restrict__ out, int A,
+                                                       long long R1, long long R2, long long is1, long long is2, long long os1, long long os2) {
+  __shared__ float tile[128][33];
+  const long long R = R1 * R2;
+  const int tiles_a = (A + 127) / 128;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (long long w = blockIdx.x; w < R * tiles_a; w += gridDim.x) {
+    const long long r = w / tiles_a; const int a0 = (int)(w - r * tiles_a) * 128;
+    const long long r1 = r / R2, r2 = r % R2;
+    const float4* ip = reinterpret_cast<const float4*>(in + r1 * is1 + r2 * is2 + (long long)a0 * 32);
+    float* op = out + r1 * os1 + r2 * os2 + a0;
+    float4 v[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int idx = threadIdx.x + 256 * q;
+      v[q] = (a0 + (idx >> 3) < A) ? __ldg(ip + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int idx = threadIdx.x + 256 * q, node = idx >> 3, c = (idx & 7) * 4;
+      tile[node][c] = v[q].x; tile[node][c + 1] = v[q].y; tile[node][c + 2] = v[q].z; tile[node][c + 3] = v[q].w;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int f = warp + 8 * j;
+#pragma unroll
+      for (int pass = 0; pass < 4; ++pass) {
+        const int node = pass * 32 + lane;
+        if (a0 + node < A) op[(long long)f * A + node] = tile[node][f];
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // degenerate transposes (A == 1 or Bd == 1): a strided batch of contiguous copies, out[oo + i] = in[ip + i], i < L
 __global__ void strided_copy_k(const float* __restrict__ in, const float* add, float* out, long long L,
                                long long R1, long long R2, long long is1, long long is2, long long os1, long long os2) {
