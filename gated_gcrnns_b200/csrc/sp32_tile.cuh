@@ -71,7 +71,7 @@ __device__ __forceinline__ float tree8(float (&v)[8], int c, unsigned gmask) {
 // Gather of NQ destination nodes per 8-lane group in lockstep:  acc[q] = sum_p val[p] * src[idx[p]] (this lane's 16-byte chunk).
 // Lane c loads (idx, val) of edge (batch + c) ONCE per batch of eight edges (coalesced; the next batch is prefetched) and the
 // group walks the batch with width-8 shuffles: per-edge index loads would cost as many L1 wavefronts as the rows themselves.
-// NQ * NU row loads are in flight per thread.  Idle slots read row 0 of the sample with coefficient 0 (predicating them costs
+// NQ * NU row loads are in flight per thread.  Must be called by all 32 lanes of a warp.  Idle slots read row 0 of the sample with coefficient 0 (predicating them costs
 // more instructions than it saves wavefronts).  n[q] < 0: no node.  `base` = sample base (float4 units) + chunk.
 template <int NQ, int NU>
 __device__ __forceinline__ void gather_nodes(const Gather3& op, const float4* __restrict__ base, const int (&n)[NQ], float4 (&acc)[NQ],
@@ -83,13 +83,15 @@ __device__ __forceinline__ void gather_nodes(const Gather3& op, const float4* __
     if (n[q] >= 0) { p0[q] = __ldg(op.ptr + n[q]); deg[q] = __ldg(op.ptr + n[q] + 1) - p0[q]; }
     md = max(md, deg[q]);
   }
+  // one trip count per WARP: its four node groups would otherwise serialise their different-length edge loops (in-degrees vary)
+  md = __reduce_max_sync(0xffffffffu, md);
   int mi[NQ]; float mv[NQ];
 #pragma unroll
   for (int q = 0; q < NQ; ++q) {
     mi[q] = 0; mv[q] = 0.f;
     if (c < deg[q]) { mi[q] = __ldg(op.idx + p0[q] + c); mv[q] = __ldg(op.val + p0[q] + c); }
   }
-  for (int pb = 0; pb < md; pb += 8) {               // md is uniform within the 8-lane group
+  for (int pb = 0; pb < md; pb += 8) {               // md is uniform within the warp
     int ni[NQ]; float nv[NQ];
 #pragma unroll
     for (int q = 0; q < NQ; ++q) {
@@ -104,8 +106,8 @@ __device__ __forceinline__ void gather_nodes(const Gather3& op, const float4* __
         for (int u = 0; u < NU; ++u)
 #pragma unroll
           for (int q = 0; q < NQ; ++q) {
-            const int ii = __shfl_sync(gmask, mi[q], e0 + u, 8);
-            w[q][u] = __shfl_sync(gmask, mv[q], e0 + u, 8);
+            const int ii = __shfl_sync(0xffffffffu, mi[q], e0 + u, 8);
+            w[q][u] = __shfl_sync(0xffffffffu, mv[q], e0 + u, 8);
             x[q][u] = __ldg(base + (size_t)ii * 8);          // idle slots: row 0 of the sample (one shared line) with coefficient 0
           }
 #pragma unroll
@@ -476,32 +478,33 @@ __global__ void __launch_bounds__(256, 4) aggregate_v2_k(const int* __restrict__
   const unsigned gmask = 0xFFu << (lane & 24);
   for (Walk w(R, N, 32); w.more(); w.next()) {
     const int j = w.u * 32 + slot;
-    if (j >= N) continue;                                       // uniform within the 8-lane group
+    const bool live = j < N;                                    // uniform within the 8-lane group
     const size_t rb = (size_t)w.r * N;
-    const int p0 = __ldg(cptr + j), p1 = __ldg(cptr + j + 1);
-    const float2 rj = rr[rb + j];
+    int p0 = 0, deg = 0;
+    float2 rj = make_float2(0.f, 0.f);
+    if (live) { p0 = __ldg(cptr + j); deg = __ldg(cptr + j + 1) - p0; rj = rr[rb + j]; }
+    const int degw = __reduce_max_sync(0xffffffffu, deg);       // one trip count per warp (in-degrees vary: no serialised groups)
     const float rja = rj.x, rjr = rj.y;
     const float4* pa = reinterpret_cast<const float4*>(wu_a + rb * 32) + c;
     const float4* pr = reinterpret_cast<const float4*>(wu_r + rb * 32) + c;
     float4 acc_a = f4zero(), acc_r = f4zero();
-    for (int pb = p0; pb < p1; pb += 8) {
-      const int cnt = min(8, p1 - pb);
+    for (int pb = 0; pb < degw; pb += 8) {
       int mi = 0; float ca = 0.f, cr = 0.f;                     // idle lanes: row 0 of the sample with coefficient 0
-      if (c < cnt) {
-        mi = __ldg(crow + pb + c);
-        const float v = __ldg(cval + pb + c);
+      if (pb + c < deg) {
+        mi = __ldg(crow + p0 + pb + c);
+        const float v = __ldg(cval + p0 + pb + c);
         const float4 s4 = cl[rb + mi];                           // (c_a, lse_a, c_r, lse_r) of source row mi
         ca = v * __expf(leaky(s4.x + rja) - s4.y);
         cr = v * __expf(leaky(s4.z + rjr) - s4.w);
       }
 #pragma unroll
       for (int e0 = 0; e0 < 8; e0 += 4) {
-        if (e0 < cnt) {                                         // group-uniform; four edges in flight
+        if (pb + e0 < degw) {                                   // warp-uniform; four edges in flight
           int ii[4]; float wa[4], wr[4]; float4 xa[4], xr[4];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            ii[u] = __shfl_sync(gmask, mi, e0 + u, 8);
-            wa[u] = __shfl_sync(gmask, ca, e0 + u, 8); wr[u] = __shfl_sync(gmask, cr, e0 + u, 8);
+            ii[u] = __shfl_sync(0xffffffffu, mi, e0 + u, 8);
+            wa[u] = __shfl_sync(0xffffffffu, ca, e0 + u, 8); wr[u] = __shfl_sync(0xffffffffu, cr, e0 + u, 8);
           }
 #pragma unroll
           for (int u = 0; u < 4; ++u) { xa[u] = __ldg(pa + (size_t)ii[u] * 8); xr[u] = __ldg(pr + (size_t)ii[u] * 8); }
@@ -516,8 +519,10 @@ __global__ void __launch_bounds__(256, 4) aggregate_v2_k(const int* __restrict__
     float4 h;
     h.x = tanh_pos(fmaxf(acc_a.x, 0.f) + fmaxf(acc_r.x, 0.f)); h.y = tanh_pos(fmaxf(acc_a.y, 0.f) + fmaxf(acc_r.y, 0.f));
     h.z = tanh_pos(fmaxf(acc_a.z, 0.f) + fmaxf(acc_r.z, 0.f)); h.w = tanh_pos(fmaxf(acc_a.w, 0.f) + fmaxf(acc_r.w, 0.f));
-    reinterpret_cast<float4*>(hn + (rb + j) * 32)[c] = h;
-    if (c == 0) masks[rb + j] = make_uint2(ma, mr);
+    if (live) {
+      reinterpret_cast<float4*>(hn + (rb + j) * 32)[c] = h;
+      if (c == 0) masks[rb + j] = make_uint2(ma, mr);
+    }
   }
 }
 
