@@ -541,16 +541,20 @@ __global__ void __launch_bounds__(256, BPS) bwd_rows_v2_k(const int* __restrict_
                                                         float* __restrict__ acc, int N, long long R) {
   __shared__ float red[8][64];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, c = threadIdx.x & 7, slot = threadIdx.x >> 3;
-  const unsigned gmask = 0xFFu << (lane & 24);
   const float4 a2a = *reinterpret_cast<const float4*>(mix_a + 32 + 4 * c), a2r = *reinterpret_cast<const float4*>(mix_r + 32 + 4 * c);
   float4 m2a = f4zero(), m2r = f4zero();
   for (Walk w(R, N, 32); w.more(); w.next()) {
     const int i = w.u * 32 + slot;
-    if (i >= N) continue;                                       // uniform within the 8-lane group
+    const bool live = i < N;                                    // uniform within the 8-lane group
     const size_t rb = (size_t)w.r * N;
-    const int p0 = __ldg(rptr + i), deg = __ldg(rptr + i + 1) - p0;
-    const float4 mine = cl[rb + i];                              // (c_a, lse_a, c_r, lse_r) of this row
-    const float4 wua = reinterpret_cast<const float4*>(wu_a + (rb + i) * 32)[c], wur = reinterpret_cast<const float4*>(wu_r + (rb + i) * 32)[c];
+    int p0 = 0, deg = 0;
+    float4 mine = f4zero(), wua = f4zero(), wur = f4zero();      // mine = (c_a, lse_a, c_r, lse_r) of this row
+    if (live) {
+      p0 = __ldg(rptr + i); deg = __ldg(rptr + i + 1) - p0;
+      mine = cl[rb + i];
+      wua = reinterpret_cast<const float4*>(wu_a + (rb + i) * 32)[c]; wur = reinterpret_cast<const float4*>(wu_r + (rb + i) * 32)[c];
+    }
+    const int degw = __reduce_max_sync(0xffffffffu, deg);       // one trip count per warp: rows of different degree do not serialise
     const float4* ga = reinterpret_cast<const float4*>(dya + rb * 32) + c;
     const float4* gr = reinterpret_cast<const float4*>(dyr + rb * 32) + c;
     float4 parta = f4zero(), partr = f4zero();
@@ -559,8 +563,8 @@ __global__ void __launch_bounds__(256, BPS) bwd_rows_v2_k(const int* __restrict_
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
       jj[b] = 0; ala[b] = alr[b] = dala[b] = dalr[b] = sla[b] = slr[b] = 0.f;
-      if (8 * b < deg) {                                        // group-uniform
-        const int cnt = min(8, deg - 8 * b);
+      if (8 * b < degw) {                                       // warp-uniform
+        const int cnt = min(8, deg - 8 * b), cntw = min(8, degw - 8 * b);
         float v = 0.f, coa = 0.f, cor = 0.f;
         if (c < cnt) {
           jj[b] = __ldg(col + p0 + 8 * b + c);
@@ -574,12 +578,12 @@ __global__ void __launch_bounds__(256, BPS) bwd_rows_v2_k(const int* __restrict_
         float pda[8], pdr[8];
 #pragma unroll
         for (int e0 = 0; e0 < 8; e0 += 4) {
-          if (e0 < cnt) {                                       // group-uniform; idle edges: row 0 with coefficient 0
+          if (e0 < cntw) {                                      // warp-uniform; idle edges: row 0 with coefficient 0
             int ii[4]; float wa[4], wr[4]; float4 xa[4], xr[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-              ii[u] = __shfl_sync(gmask, jj[b], e0 + u, 8);
-              wa[u] = __shfl_sync(gmask, coa, e0 + u, 8); wr[u] = __shfl_sync(gmask, cor, e0 + u, 8);
+              ii[u] = __shfl_sync(0xffffffffu, jj[b], e0 + u, 8);
+              wa[u] = __shfl_sync(0xffffffffu, coa, e0 + u, 8); wr[u] = __shfl_sync(0xffffffffu, cor, e0 + u, 8);
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) { xa[u] = __ldg(ga + (size_t)ii[u] * 8); xr[u] = __ldg(gr + (size_t)ii[u] * 8); }
@@ -593,11 +597,11 @@ __global__ void __launch_bounds__(256, BPS) bwd_rows_v2_k(const int* __restrict_
             for (int u = 0; u < 4; ++u) { pda[e0 + u] = 0.f; pdr[e0 + u] = 0.f; }
           }
         }
-        dala[b] = v * tree8(pda, c, gmask); dalr[b] = v * tree8(pdr, c, gmask);     // v == 0 on idle lanes
+        dala[b] = v * tree8(pda, c, 0xffffffffu); dalr[b] = v * tree8(pdr, c, 0xffffffffu);     // v == 0 on idle lanes
         tSa = fmaf(ala[b], dala[b], tSa); tSr = fmaf(alr[b], dalr[b], tSr);
       }
     }
-    const float Sa = gsum8(tSa, gmask), Sr = gsum8(tSr, gmask);
+    const float Sa = gsum8(tSa, 0xffffffffu), Sr = gsum8(tSr, 0xffffffffu);
     float dca = 0.f, dcr = 0.f;
 #pragma unroll
     for (int b = 0; b < 4; ++b)
@@ -606,10 +610,12 @@ __global__ void __launch_bounds__(256, BPS) bwd_rows_v2_k(const int* __restrict_
         atomicAdd(dr + rb + jj[b], make_float2(dsa, dsr));
         dca += dsa; dcr += dsr;
       }
-    dca = gsum8(dca, gmask); dcr = gsum8(dcr, gmask);
+    dca = gsum8(dca, 0xffffffffu); dcr = gsum8(dcr, 0xffffffffu);
     fma4(parta, dca, a2a); fma4(partr, dcr, a2r);
-    reinterpret_cast<float4*>(pa + (rb + i) * 32)[c] = parta;
-    reinterpret_cast<float4*>(pr + (rb + i) * 32)[c] = partr;
+    if (live) {
+      reinterpret_cast<float4*>(pa + (rb + i) * 32)[c] = parta;
+      reinterpret_cast<float4*>(pr + (rb + i) * 32)[c] = partr;
+    }
     fma4(m2a, dca, wua); fma4(m2r, dcr, wur);
   }
   // lanes c, c+8, c+16, c+24 of a warp hold the same features
