@@ -46,6 +46,9 @@ struct Walk {
   __device__ __forceinline__ bool more() const { return left > 0; }
   __device__ __forceinline__ void next() { --left; if (++u == per_sample) { u = 0; ++r; } }
 };
+// keep a derived base pointer materialised in one register pair (else the compiler re-adds its parts for every gathered row:
+// 3 address instructions per load instead of one IMAD.WIDE)
+template <class T> __device__ __forceinline__ const T* pin_ptr(const T* p) { asm volatile("" : "+l"(p)); return p; }
 __device__ __forceinline__ float4 f4zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
 __device__ __forceinline__ float4 f4add(const float4& a, const float4& b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 __device__ __forceinline__ float gsum8(float v, unsigned gmask) {       // sum over the 8 lanes of a node group
@@ -74,8 +77,9 @@ __device__ __forceinline__ float tree8(float (&v)[8], int c, unsigned gmask) {
 // NQ * NU row loads are in flight per thread.  Must be called by all 32 lanes of a warp.  Idle slots read row 0 of the sample with coefficient 0 (predicating them costs
 // more instructions than it saves wavefronts).  n[q] < 0: no node.  `base` = sample base (float4 units) + chunk.
 template <int NQ, int NU>
-__device__ __forceinline__ void gather_nodes(const Gather3& op, const float4* __restrict__ base, const int (&n)[NQ], float4 (&acc)[NQ],
+__device__ __forceinline__ void gather_nodes(const Gather3& op, const float4* base, const int (&n)[NQ], float4 (&acc)[NQ],
                                              unsigned gmask, int c) {
+  base = pin_ptr(base);
   int p0[NQ], deg[NQ], md = 0;
 #pragma unroll
   for (int q = 0; q < NQ; ++q) {
@@ -485,8 +489,8 @@ __global__ void __launch_bounds__(256, 4) aggregate_v2_k(const int* __restrict__
     if (live) { p0 = __ldg(cptr + j); deg = __ldg(cptr + j + 1) - p0; rj = rr[rb + j]; }
     const int degw = __reduce_max_sync(0xffffffffu, deg);       // one trip count per warp (in-degrees vary: no serialised groups)
     const float rja = rj.x, rjr = rj.y;
-    const float4* pa = reinterpret_cast<const float4*>(wu_a + rb * 32) + c;
-    const float4* pr = reinterpret_cast<const float4*>(wu_r + rb * 32) + c;
+    const float4* pa = pin_ptr(reinterpret_cast<const float4*>(wu_a + rb * 32) + c);
+    const float4* pr = pin_ptr(reinterpret_cast<const float4*>(wu_r + rb * 32) + c);
     float4 acc_a = f4zero(), acc_r = f4zero();
     for (int pb = 0; pb < degw; pb += 8) {
       int mi = 0; float ca = 0.f, cr = 0.f;                     // idle lanes: row 0 of the sample with coefficient 0
@@ -555,8 +559,8 @@ __global__ void __launch_bounds__(256, BPS) bwd_rows_v2_k(const int* __restrict_
       wua = reinterpret_cast<const float4*>(wu_a + (rb + i) * 32)[c]; wur = reinterpret_cast<const float4*>(wu_r + (rb + i) * 32)[c];
     }
     const int degw = __reduce_max_sync(0xffffffffu, deg);       // one trip count per warp: rows of different degree do not serialise
-    const float4* ga = reinterpret_cast<const float4*>(dya + rb * 32) + c;
-    const float4* gr = reinterpret_cast<const float4*>(dyr + rb * 32) + c;
+    const float4* ga = pin_ptr(reinterpret_cast<const float4*>(dya + rb * 32) + c);
+    const float4* gr = pin_ptr(reinterpret_cast<const float4*>(dyr + rb * 32) + c);
     float4 parta = f4zero(), partr = f4zero();
     float tSa = 0.f, tSr = 0.f;
     int jj[4]; float ala[4], alr[4], dala[4], dalr[4], sla[4], slr[4];
