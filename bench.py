@@ -370,6 +370,50 @@ CFG5 = dict(N=100_000, knn=16, F=32, G=1, K=3, T=32, B=256, mb=32)
 BYTES_PER_SEQ_CFG5 = 42 * 32 * (32 * 100_000 * 4)      # 42 P per (sample, step), P = F*N*4 B, T = 32 -> 17.2 GB
 
 
+def cfg5_cpu_baseline(cfg, S_csr, Bs=1, Ts=2):
+    """The reference algorithm on the host CPUs for cfg5: the dense reference cannot hold N = 1e5 (S alone is 80 GB), so this
+    times the sparse fp64 oracle port (oracle/gcrnn_oracle.py, pinned against the reference's golden vectors) on a bounded
+    sample: B = 1 sequence, T = 2 of 32 steps, forward + backward, extrapolated linearly in T."""
+    import time
+    import torch
+    from oracle import gcrnn_oracle as orc
+    N, F, G, K = cfg['N'], cfg['F'], cfg['G'], cfg['K']
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    prev = torch.get_default_dtype(); torch.set_default_dtype(torch.float64)
+    try:
+        torch.manual_seed(0)
+        p = orc.init_cell_params(G, F, K, K, N, False, 'edge', 1, True)
+    finally:
+        torch.set_default_dtype(prev)
+    S = S_csr.double().to_sparse_coo().coalesce()
+    X, h0, dH = torch.randn(Bs, Ts, G, N).double(), torch.zeros(Bs, F, N).double(), torch.ones(Bs, Ts, F, N).double()
+    times = []
+    for _ in range(2):
+        t0 = time.perf_counter()
+        orc.cell_forward_backward(p, [S], X, h0, dH, False, 'edge')
+        times.append(time.perf_counter() - t0)
+    best = min(times)
+    return dict(value=Bs / (best * cfg['T'] / Ts), unit='sequences/s', cores=cores, kind='port',
+                sample=f'sparse fp64 oracle port of the reference GGCRNNCell (edge-gated; the dense reference cannot hold N = 1e5), torch CPU '
+                       f'with {cores} threads, fwd+bwd on the cfg5 graph with B={Bs}, T={Ts} of {cfg["T"]}; min of 2 runs = {best:.2f} s, '
+                       f'extrapolated linearly in T')
+
+
+def cfg5_dram_bytes_per_sequence(cfg):
+    """Measured DRAM bytes per sequence from the committed `ncu --set full` export of one launch of every per-step kernel
+    (profiles/r01_ncu_sparse_v2.raw.csv, captured at micro-batch 32): sum over a forward + backward step, x T, / 32 sequences."""
+    per_step = [('spmm32_v2_k', 2), ('gather_contract_k<3, 0', 1), ('rowstats_v2_k', 1), ('aggregate_v2_k', 1),
+                ('bwd_rows_v2_k', 1), ('bwd_node_v2_k', 1), ('gather_contract_k<3, 1', 1)]
+    tot = 0.0
+    for name, n in per_step:
+        b, _ = ncu_traffic(['r01_ncu_sparse_v2.raw.csv'], name)
+        if b is None:
+            return None
+        tot += n * b
+    return tot * cfg['T'] / 32
+
+
 def run_cfg5(args):
     import torch
     import torch.distributed as dist
@@ -451,6 +495,10 @@ def run_cfg5(args):
     seqs_e2e = cfg['B'] * args.steps / (ms_e2e * 1e-3)
     pk = peaks()
     ach = BYTES_PER_SEQ_CFG5 * seqs / world / 1e9
+    cb = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cb = cfg5_cpu_baseline(cfg, S)
+    traffic = cfg5_dram_bytes_per_sequence(cfg) if cfg['K'] == 3 else None
     if rank == 0:
         out = dict(metric='GCRNN sequences/sec fwd+bwd', value=seqs, unit='sequences/s', n_gpus=world, steps=args.steps, warmup=args.warmup,
                    ms_per_step=ms_dev / args.steps, higher_is_better=True, scaling='strong', vs_baseline=None, dtype='f32', data='synthetic',
@@ -458,10 +506,13 @@ def run_cfg5(args):
                                global_batch=cfg['B'], per_gpu_batch=Bl, microbatch=mb, precision='fp32',
                                parallelism=f'dp{world} (batch sharded, one gradient all-reduce per step)',
                                l2='per-micro-batch working set (H 13 GB) larger than L2; no explicit flush'),
-                   roofline=dict(bound='hbm', achieved=ach, peak=pk['hbm'], unit='GB/s', frac=ach / pk['hbm'], traffic=None,
+                   roofline=dict(bound='hbm', achieved=ach, peak=pk['hbm'], unit='GB/s', frac=ach / pk['hbm'], traffic=traffic,
+                                 traffic_note='measured DRAM read+write bytes per SEQUENCE (the unit of `achieved`): per-launch bytes of the seven '
+                                              'per-step kernels from profiles/r01_ncu_sparse_v2.raw.csv (ncu --set full, micro-batch 32) x T / 32; '
+                                              'algorithmic bytes per sequence = 17.2e9',
                                  kernel='whole step: algorithmic 17.2 GB per sequence (42 passes over an [F,N] fp32 signal per (sample, step), '
                                         'SURVEY.md 8d) x sequences/s per GPU, peak = ' + pk['src'] + ' HBM copy bandwidth'),
-                   cpu_baseline=None, clocks=clocks,
+                   cpu_baseline=cb, clocks=clocks,
                    e2e=dict(value=seqs_e2e, unit='sequences/s', h2d_bytes_per_step=int(X_host.numel() * 4),
                             d2h_bytes_per_step=int(sum(p.numel() for p in used) * 4), ms_per_step=ms_e2e / args.steps),
                    gpu_launches=int(launches))
