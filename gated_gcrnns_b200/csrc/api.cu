@@ -15,6 +15,7 @@ int g_opt_sparse_v2_tc = 1;
 int g_opt_sparse_v2_fuse_dpre = 1;
 int g_opt_sparse_v2_rows_bps = 2;
 int g_opt_graph_capture = 1;
+int64_t g_opt_epoch = 0;
 void set_last_error(const char* fmt, ...) {
   va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof g_err, fmt, ap); va_end(ap);
 }
@@ -42,7 +43,7 @@ using namespace gcrnn;
 namespace {
 constexpr int GK_PTRS = 72;
 struct GraphKey {
-  const void* p[GK_PTRS]; int64_t B, T; int kind, path;
+  const void* p[GK_PTRS]; int64_t B, T; int kind, path; int64_t epoch;   // epoch: bumped by every gcrnn_debug_set_option call
   bool operator==(const GraphKey& o) const { return memcmp(this, &o, sizeof(GraphKey)) == 0; }
 };
 struct GraphEntry { GraphKey key; cudaGraphExec_t exec; unsigned long long launches; uint64_t stamp; int last_path; };
@@ -121,6 +122,7 @@ int gcrnn_abi_version(void) { return GCRNN_ABI_VERSION; }
 const char* gcrnn_last_error(void) { return g_err; }
 uint64_t gcrnn_debug_launch_count(void) { return g_launches; }
 int gcrnn_debug_set_option(const char* name, int32_t value) {
+  ++g_opt_epoch;                                    // captured graphs were built under the old options: never replay them
   if (name && std::string(name) == "bwd_fused") { int old = gcrnn::g_opt_bwd_fused; gcrnn::g_opt_bwd_fused = value; return old; }
   if (name && std::string(name) == "sparse_fused") { int old = gcrnn::g_opt_sparse_fused; gcrnn::g_opt_sparse_fused = value; return old; }
   if (name && std::string(name) == "sparse_v2") { int old = gcrnn::g_opt_sparse_v2; gcrnn::g_opt_sparse_v2 = value; return old; }
@@ -284,7 +286,7 @@ int gcrnn_cell_forward(gcrnn_cell* c, const gcrnn_cell_params* p, const float* X
     key_params(key, n, p);
     key.p[n++] = X; key.p[n++] = h0; key.p[n++] = H; key.p[n++] = saved; key.p[n++] = ws;
     key.p[n++] = (const void*)savedb; key.p[n++] = (const void*)wsb;
-    key.B = B; key.T = T; key.kind = 0; key.path = c->forced_path;
+    key.B = B; key.T = T; key.kind = 0; key.path = c->forced_path; key.epoch = g_opt_epoch;
     run_graphed(c, key, (cudaStream_t)stream, [&](cudaStream_t st) { cell_forward_f32(c, p, X, h0, H, saved, savedb, nullptr, ws, wsb, B, T, st); });
   } else cell_forward_f32(c, p, X, h0, H, saved, savedb, nullptr, ws, wsb, B, T, (cudaStream_t)stream);
   API_END
@@ -303,7 +305,7 @@ int gcrnn_cell_backward(gcrnn_cell* c, const gcrnn_cell_params* p, const float* 
     key_params(key, n, grads);
     key.p[n++] = X; key.p[n++] = h0; key.p[n++] = H; key.p[n++] = dH; key.p[n++] = saved; key.p[n++] = dX; key.p[n++] = dh0; key.p[n++] = ws;
     key.p[n++] = (const void*)savedb; key.p[n++] = (const void*)wsb;
-    key.B = B; key.T = T; key.kind = 1; key.path = c->forced_path;
+    key.B = B; key.T = T; key.kind = 1; key.path = c->forced_path; key.epoch = g_opt_epoch;
     run_graphed(c, key, (cudaStream_t)stream,
                 [&](cudaStream_t st) { cell_backward_f32(c, p, X, h0, H, dH, saved, savedb, grads, dX, dh0, ws, wsb, B, T, st); });
   } else cell_backward_f32(c, p, X, h0, H, dH, saved, savedb, grads, dX, dh0, ws, wsb, B, T, (cudaStream_t)stream);

@@ -76,6 +76,7 @@ struct gcrnn_cell {
   mutable int need_dx = 0;        // hint for the next forward: the caller will ask backward for dX
   mutable int forced_path = -1;   // -1: choose automatically; otherwise GCRNN_PATH_*
   mutable int last_path = 0;      // path taken by the last forward
+  mutable int fwd_v2_mask = 63;   // fused sparse path: stage generations the last forward used (its backward follows them)
   mutable void* graph_cache = nullptr;   // api.cu: CUDA graphs of small (launch-bound) fp32 forward / backward calls
 };
 

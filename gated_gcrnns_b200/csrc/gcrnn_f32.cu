@@ -436,12 +436,15 @@ int tile_grid(K kernel, int block, size_t dyn_smem, int blocks_per_sm, long long
   return (int)std::max<long long>(1, std::min<long long>((long long)sm_count() * occ, units));
 }
 enum { V2_SPMM = 1, V2_FILTER = 2, V2_AGG = 4, V2_ROWS = 8, V2_NODE = 16, V2_DH = 32 };
-// the aggregate and bwd_rows stages share the layout of the saved softmax statistics: they switch generation together
-inline bool v2(int bit) {
-  int m = g_opt_sparse_v2;
+// Stage mask in effect for the current call.  The aggregate and bwd_rows stages share the layout of the saved softmax
+// statistics, so they switch generation together, and a backward always follows the choice its forward made (recorded in the
+// cell) even if the debug option changed in between.
+thread_local int t_v2_mask = 63;
+inline int normalise_v2(int m) {
   if ((m & (V2_AGG | V2_ROWS)) != (V2_AGG | V2_ROWS)) m &= ~(V2_AGG | V2_ROWS);
-  return (m & bit) != 0;
+  return m;
 }
+inline bool v2(int bit) { return (t_v2_mask & bit) != 0; }
 inline int tile_bps() { return std::max(1, std::min(2, g_opt_sparse_v2_bps)); }
 
 void spmm32(const Ctx& c, const Gather& op, const float* in, float* out, long long R) {
@@ -517,6 +520,8 @@ size_t cell_forward_e32(const gcrnn_cell* cell, const gcrnn_cell_params* p, cons
   const CellDims d = dims_of(cell, B, T);
   Arena a(ws, wsb);
   Ctx c{cell->g, st, a.dry()};
+  t_v2_mask = normalise_v2(g_opt_sparse_v2);
+  if (ws != nullptr) cell->fwd_v2_mask = t_v2_mask;
   Saved s; Saved32 x;
   {
     Arena sa(saved, savedb);
@@ -631,6 +636,7 @@ size_t cell_backward_e32(const gcrnn_cell* cell, const gcrnn_cell_params* p, con
   const CellDims d = dims_of(cell, B, T);
   Arena a(ws, wsb);
   Ctx c{cell->g, st, a.dry()};
+  t_v2_mask = (normalise_v2(g_opt_sparse_v2) & ~(V2_AGG | V2_ROWS)) | (cell->fwd_v2_mask & (V2_AGG | V2_ROWS));
   Saved s; Saved32 x;
   { Arena sa(const_cast<void*>(saved), savedb); s.layout(sa, d); x.layout(sa, d); }
   Bwd32Bufs b;
