@@ -1,19 +1,25 @@
 // Second generation of the fused fp32 kernels of the sparse EDGE-GATED recurrence (F == 32, cfg5 of SURVEY.md §8d).
-// Same algebra, same HBM arrays and the same accumulator layout as sp32_kernels.cuh (which stays selectable through
+// Same algebra, same HBM arrays and the same accumulator layout as sp32_kernels.cuh (which stays selectable per stage through
 // gcrnn_debug_set_option("sparse_v2", mask) for A/B tests); what changes is the work decomposition, chosen from the ncu
-// exports of the first generation (profiles/r01_ncu_sparse_*): those kernels were issue-bound at 330-670 warp
-// instructions per (sample, node) with 12 resident warps, not HBM-bound.
+// exports of the first generation (profiles/r01_ncu_sparse_fwd/bwd*): those kernels were issue- and latency-bound at 330-670
+// warp instructions per (sample, node) with 12 resident warps, not HBM-bound.  Measured at cfg5: 130 vs 60 sequences/s.
 //
-//   * Gathers: EIGHT lanes own one destination node (lane = 16-byte chunk of the 128-byte row), four nodes per warp.
-//     A neighbour row is one LDG.128 per lane with no final reduce-scatter; (index, value) pairs are loaded once per batch
-//     of eight edges (lane = edge) and broadcast with width-8 shuffles; several nodes of a thread run in lockstep so that
-//     8-16 row loads are in flight per thread (the kernels are latency-bound, not issue-bound).
-//   * Contractions: a block stages a tile of 64 consecutive nodes ([64][K*32] inputs, gathered tap included) in shared
-//     memory and runs a register-tiled fp32 GEMM against weights that live in shared memory ONCE per block: a thread
-//     owns 4 nodes x 4 outputs and issues packed FFMA2 over input pairs, so no thread carries the 96 weights in
-//     registers (that is what capped the first generation at 3 blocks per SM).
-//   * Weight-gradient outer products (M_k = sum_n dWu[n] (x) z_k[n]) are the transposed GEMM of the same tile, kept in
-//     registers across all tiles of a block.
+//   * Gathers: EIGHT lanes own one destination node (lane = 16-byte chunk of the 128-byte row), four nodes per warp, one
+//     LDG.128 per neighbour row and no final reduce-scatter.  The edge list is loaded once per batch of eight edges (lane =
+//     edge, coalesced, next batch prefetched) and broadcast with width-8 shuffles; 2-4 nodes of a thread run in lockstep
+//     (8-16 row loads in flight per thread); ONE trip count per warp (the four node groups never serialise their different
+//     in-degrees); pinned base pointers (SHFL, IMAD.WIDE, LDG.128, SHFL + 4 FFMA per gathered row).
+//   * Contractions: a 256-thread block stages a tile of 128 consecutive nodes in shared memory (streamed taps by cp.async
+//     while the block gathers the last one) and each warp contracts its 16 nodes against weights that sit in shared memory
+//     once per block - on tensor cores with error compensation (3xTF32 mma.sync.m16n8k8, fp32 accumulate; conflict-free
+//     fragment loads, row strides == 8 mod 32).  A register-tiled packed-FFMA2 version (thread = 4 nodes x 4 outputs) is kept
+//     behind "sparse_v2_tc" = 0: it measured shared-memory-bound (every LDS.128 is four wavefronts).
+//   * Weight-gradient outer products (M_k = sum_n dWu[n] (x) z_k[n]) are the transposed mma product of the same tile
+//     (K dimension = the tile's nodes), kept in registers across all tiles of a block.
+//   * Saved softmax statistics are (c, logsumexp) per gate and row: one 16-byte load per (edge, source row).
+//   * The dh kernel's epilogue finishes the NEXT reverse step's dpre, so dh itself is never stored.
+// What bounds them now (profiles/r01_ncu_sparse_v2_summary.txt): the L1 data pipe (l1tex data-pipe wavefronts 55-83 % of peak):
+// every gathered neighbour row is one 128-byte wavefront, and shuffles / fragment loads share that pipe.
 //
 // Reference op sites (Utils/graphML.py): LSIGF shift :123 + contraction :134-139; graphAttention :586-625 with
 // S' = S + I :577, leaky_relu(0.2) :603, masked softmax over j :611-622, aggregation over i :625; relu :2101;
