@@ -7,6 +7,7 @@ namespace gcrnn {
 static thread_local char g_err[1024] = "";
 unsigned long long g_launches = 0;
 int g_opt_gemm_pair = 1;
+int g_opt_gate_fq8 = 1;
 int g_opt_bwd_fused = 1;
 int g_opt_sparse_fused = 1;
 int g_opt_sparse_v2 = 63;
@@ -131,6 +132,7 @@ int gcrnn_debug_set_option(const char* name, int32_t value) {
   if (name && std::string(name) == "sparse_v2_tc") { int old = gcrnn::g_opt_sparse_v2_tc; gcrnn::g_opt_sparse_v2_tc = value; return old; }
   if (name && std::string(name) == "sparse_v2_bps") { int old = gcrnn::g_opt_sparse_v2_bps; gcrnn::g_opt_sparse_v2_bps = value; return old; }
   if (name && std::string(name) == "graph_capture") { int old = gcrnn::g_opt_graph_capture; gcrnn::g_opt_graph_capture = value; return old; }
+  if (name && std::string(name) == "gate_fq8") { int old = gcrnn::g_opt_gate_fq8; gcrnn::g_opt_gate_fq8 = value; return old; }
   if (name && std::string(name) == "gemm_pair") { int old = gcrnn::g_opt_gemm_pair; gcrnn::g_opt_gemm_pair = value; return old; }
   return -1;
 }

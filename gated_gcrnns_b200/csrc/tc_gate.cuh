@@ -19,6 +19,7 @@ constexpr int TG_NT = 64;          // nodes per work item
 constexpr int TG_FQ = 4;           // feature groups per CTA (256 threads = 64 nodes x 4 groups)
 constexpr int TG_FMAX = 16;        // features per thread (F <= 64)
 constexpr int TG_FB = 4;           // backward: features processed together
+constexpr int TG_NWMAX = 16;       // warps per CTA of the widest variant (forward with 8 feature groups = 512 threads)
 
 struct GateArgs {
   const float* A; int Kin, G, F, N; long long B, T;
@@ -36,7 +37,7 @@ struct GateArgs {
 };
 
 inline size_t gate_smem_bytes(int TC, int KG, int F, int nbuf) {
-  return ((size_t)nbuf * TC * KG * TG_NT + 8 * (size_t)TC + 2 * (size_t)TC + 2 * (size_t)F * KG) * sizeof(float);
+  return ((size_t)nbuf * TC * KG * TG_NT + TG_NWMAX * (size_t)TC + 2 * (size_t)TC + 2 * (size_t)F * KG) * sizeof(float);
 }
 
 struct GateItem { int tile, t_lo, tn; long long b; };
@@ -52,11 +53,11 @@ __device__ __forceinline__ GateItem gate_item(const GateArgs& a, long long item)
 }
 
 // x_t S^k rows of one item -> zs[t][kg][64 nodes]  (cp.async, 16 B per request)
-template <int KG>
+template <int KG, int NTH = 256>
 __device__ __forceinline__ void gate_stage(const GateArgs& a, const GateItem& it, float* zs, int tid) {
   const size_t kstride = (size_t)a.B * a.T * a.G * a.N;
   const int total = it.tn * KG * (TG_NT / 4);
-  for (int i = tid; i < total; i += 256) {
+  for (int i = tid; i < total; i += NTH) {
     const int c4 = i % (TG_NT / 4), kg = (i / (TG_NT / 4)) % KG, t = i / ((TG_NT / 4) * KG);
     const int k = kg / a.G, g = kg % a.G;
     const size_t row = ((size_t)it.b * a.T + it.t_lo + t) * a.G + g;
@@ -65,45 +66,49 @@ __device__ __forceinline__ void gate_stage(const GateArgs& a, const GateItem& it
   }
 }
 
-template <int KG>
-__global__ void __launch_bounds__(256, 1) time_gate_fwd_kernel(const GateArgs a) {
+// FQ feature groups per CTA (64 * FQ threads, F / FQ features per thread).  FQ = 8 halves the per-thread tap registers so that
+// 16 warps are resident instead of 8: with 8 warps the kernel issues on only half of the cycles (profiles/r01_ncu_gate.raw.csv:
+// 2 warps per scheduler stalled on fixed-latency FMA -> MUFU dependencies).
+template <int KG, int FQ>
+__global__ void __launch_bounds__(64 * FQ, 1) time_gate_fwd_kernel(const GateArgs a) {
+  constexpr int NTH = 64 * FQ, NW = NTH / 32, FMAXV = 64 / FQ;
   extern __shared__ __align__(16) float gsm[];
   const int TC = a.TC;
   const size_t zbuf = (size_t)TC * KG * TG_NT;
   float* zs = gsm;                              // [nbuf][TC][KG][64]
-  float* plog = zs + a.nbuf * zbuf;             // [8 warps][TC]
+  float* plog = zs + a.nbuf * zbuf;             // [NW warps][TC]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nl = tid & 63, fq = tid >> 6;
-  const int FG = a.F / TG_FQ, f0 = fq * FG;
+  const int FG = a.F / FQ, f0 = fq * FG;
   const long long items = a.B * a.nchunks * (a.N / TG_NT);
   const long long per = (items + gridDim.x - 1) / gridDim.x;
   const long long lo = blockIdx.x * per, hi = min(items, lo + per);
   if (lo >= hi) return;
 
-  float ta[TG_FMAX][KG];
+  float ta[FMAXV][KG];
 #pragma unroll
-  for (int i = 0; i < TG_FMAX; ++i)
+  for (int i = 0; i < FMAXV; ++i)
 #pragma unroll
     for (int kg = 0; kg < KG; ++kg) ta[i][kg] = i < FG ? __ldg(a.A + (size_t)(f0 + i) * KG + kg) : 0.f;
 
-  gate_stage<KG>(a, gate_item(a, lo), zs, tid);
+  gate_stage<KG, NTH>(a, gate_item(a, lo), zs, tid);
   cp_async_commit();
   int cur_tile = -1, buf = 0;
-  float wg[TG_FMAX];
+  float wg[FMAXV];
   for (long long item = lo; item < hi; ++item) {
     const GateItem it = gate_item(a, item);
     const int n = it.tile * TG_NT + nl;
     if (it.tile != cur_tile) {
       cur_tile = it.tile;
 #pragma unroll
-      for (int i = 0; i < TG_FMAX; ++i) wg[i] = i < FG ? __ldg(a.Wg + (size_t)(f0 + i) * a.N + n) : 0.f;
+      for (int i = 0; i < FMAXV; ++i) wg[i] = i < FG ? __ldg(a.Wg + (size_t)(f0 + i) * a.N + n) : 0.f;
     }
-    float c0v[TG_FMAX];
+    float c0v[FMAXV];
 #pragma unroll
-    for (int i = 0; i < TG_FMAX; ++i) c0v[i] = i < FG ? __ldg(a.c0 + ((size_t)it.b * a.F + f0 + i) * a.N + n) : 0.f;
+    for (int i = 0; i < FMAXV; ++i) c0v[i] = i < FG ? __ldg(a.c0 + ((size_t)it.b * a.F + f0 + i) * a.N + n) : 0.f;
     cp_async_wait<0>();
     __syncthreads();                            // item's rows are visible; everyone is done with the other buffer
-    if (a.nbuf == 2 && item + 1 < hi) gate_stage<KG>(a, gate_item(a, item + 1), zs + (buf ^ 1) * zbuf, tid);
+    if (a.nbuf == 2 && item + 1 < hi) gate_stage<KG, NTH>(a, gate_item(a, item + 1), zs + (buf ^ 1) * zbuf, tid);
     cp_async_commit();
     const float* zb = zs + buf * zbuf + nl;
     for (int t0 = 0; t0 < it.tn; t0 += 32) {
@@ -117,7 +122,7 @@ __global__ void __launch_bounds__(256, 1) time_gate_fwd_kernel(const GateArgs a)
 #pragma unroll
           for (int kg = 0; kg < KG; ++kg) z[kg] = zt[kg * TG_NT];
 #pragma unroll
-          for (int ib = 0; ib < TG_FMAX; ib += 4) {
+          for (int ib = 0; ib < FMAXV; ib += 4) {
             if (ib < FG) {                      // F is a multiple of 16: a thread's features come in groups of 4
 #pragma unroll
               for (int i = ib; i < ib + 4; ++i) {
@@ -135,14 +140,14 @@ __global__ void __launch_bounds__(256, 1) time_gate_fwd_kernel(const GateArgs a)
       if (t0 + lane < it.tn) plog[warp * TC + t0 + lane] = tot;
     }
     __syncthreads();
-    for (int t = tid; t < it.tn; t += 256) {
+    for (int t = tid; t < it.tn; t += NTH) {
       float s = 0.f;
 #pragma unroll
-      for (int w = 0; w < 8; ++w) s += plog[w * TC + t];
+      for (int w = 0; w < NW; ++w) s += plog[w * TC + t];
       atomicAdd(a.logit + it.b * a.T + it.t_lo + t, s);
     }
     if (a.nbuf == 2) buf ^= 1;
-    else if (item + 1 < hi) { gate_stage<KG>(a, gate_item(a, item + 1), zs, tid); cp_async_commit(); }
+    else if (item + 1 < hi) { gate_stage<KG, NTH>(a, gate_item(a, item + 1), zs, tid); cp_async_commit(); }
   }
   cp_async_wait<0>();
 }
@@ -155,7 +160,7 @@ __global__ void __launch_bounds__(256, 1) time_gate_bwd_kernel(const GateArgs a)
   const int TC = a.TC;
   const size_t zbuf = (size_t)TC * KG * TG_NT;
   float* zs = gsm;                              // [nbuf][TC][KG][64]
-  float* dls = zs + a.nbuf * zbuf + 8 * TC;     // [2][TC]
+  float* dls = zs + a.nbuf * zbuf + TG_NWMAX * TC;     // [2][TC]
   float* As = dls + 2 * TC;                     // [F][KG]
   float* dAs = As + a.F * KG;                   // [F][KG]
   const int tid = threadIdx.x, lane = tid & 31;
