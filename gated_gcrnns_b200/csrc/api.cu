@@ -7,7 +7,7 @@ namespace gcrnn {
 static thread_local char g_err[1024] = "";
 unsigned long long g_launches = 0;
 int g_opt_gemm_pair = 1;
-int g_opt_gate_fq8 = 1;
+int g_opt_gate_fq8 = 2;
 int g_opt_bwd_fused = 1;
 int g_opt_sparse_fused = 1;
 int g_opt_sparse_v2 = 63;

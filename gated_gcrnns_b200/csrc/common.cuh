@@ -22,7 +22,7 @@ extern int g_opt_sparse_v2_fuse_dpre;  // 1: the dh kernel finishes the next rev
 extern int g_opt_sparse_v2_tc;         // 1: tile contractions on tensor cores (3xTF32 mma.sync), 0: packed FFMA2
 extern int g_opt_sparse_v2_bps;        // resident blocks per SM of the tile kernels (the rest of the 228 KB stays L1)
 extern int g_opt_graph_capture;        // 1: replay small fp32 cell calls as CUDA graphs keyed by their pointer set (api.cu)
-extern int g_opt_gate_fq8;             // 1: forward time-gate kernel with 8 feature groups (512 threads) when F % 32 == 0
+extern int g_opt_gate_fq8;             // time-gate kernels with 8 feature groups (512 threads) when F % 32 == 0: 1 = forward, 2 = forward + backward
 extern int g_opt_gemm_pair;             // 1: use the CTA-pair (cta_group::2) shift GEMM when the shape allows
 extern unsigned long long g_launches;   // kernels launched by this library (gcrnn_debug_launch_count)
 

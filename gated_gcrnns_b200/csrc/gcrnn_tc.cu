@@ -245,8 +245,13 @@ static void gate_launch_kg(bool bwd, const GateArgs& ga, int grid, size_t sm, cu
       time_gate_fwd_kernel<KG, 4><<<grid, 256, sm, st>>>(ga);
     }
   } else {
-    CUDA_OK(cudaFuncSetAttribute(time_gate_bwd_kernel<KG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    time_gate_bwd_kernel<KG><<<grid, 256, sm, st>>>(ga);
+    if (ga.F % 32 == 0 && g_opt_gate_fq8 >= 2) {
+      CUDA_OK(cudaFuncSetAttribute(time_gate_bwd_kernel<KG, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      time_gate_bwd_kernel<KG, 8><<<grid, 512, sm, st>>>(ga);
+    } else {
+      CUDA_OK(cudaFuncSetAttribute(time_gate_bwd_kernel<KG, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      time_gate_bwd_kernel<KG, 4><<<grid, 256, sm, st>>>(ga);
+    }
   }
 }
 

@@ -154,8 +154,9 @@ __global__ void __launch_bounds__(64 * FQ, 1) time_gate_fwd_kernel(const GateArg
 
 // backward: given dl[b,t] = d loss / d logit:  dpu = dl Wg (1 - u^2);  dWg += dl u;  dc0[b,f,n] = sum_t dpu;
 // dA[f,kg] += sum_{b,t,n} dpu zx_kg.   u is recomputed (one MUFU) instead of being stored (8.6 GB per gate at cfg3).
-template <int KG>
-__global__ void __launch_bounds__(256, 1) time_gate_bwd_kernel(const GateArgs a) {
+template <int KG, int FQ>
+__global__ void __launch_bounds__(64 * FQ, 1) time_gate_bwd_kernel(const GateArgs a) {
+  constexpr int NTH = 64 * FQ, FMAXV = 64 / FQ;
   extern __shared__ __align__(16) float gsm[];
   const int TC = a.TC;
   const size_t zbuf = (size_t)TC * KG * TG_NT;
@@ -165,24 +166,24 @@ __global__ void __launch_bounds__(256, 1) time_gate_bwd_kernel(const GateArgs a)
   float* dAs = As + a.F * KG;                   // [F][KG]
   const int tid = threadIdx.x, lane = tid & 31;
   const int nl = tid & 63, fq = tid >> 6;
-  const int FG = a.F / TG_FQ, f0 = fq * FG;
+  const int FG = a.F / FQ, f0 = fq * FG;
   const long long items = a.B * a.nchunks * (a.N / TG_NT);
   const long long per = (items + gridDim.x - 1) / gridDim.x;
   const long long lo = blockIdx.x * per, hi = min(items, lo + per);
   if (lo >= hi) return;
-  for (int i = tid; i < a.F * KG; i += 256) { As[i] = a.A[i]; dAs[i] = 0.f; }
+  for (int i = tid; i < a.F * KG; i += NTH) { As[i] = a.A[i]; dAs[i] = 0.f; }
 
   {
     const GateItem it = gate_item(a, lo);
-    gate_stage<KG>(a, it, zs, tid);
-    for (int t = tid; t < it.tn; t += 256) dls[t] = a.dl[it.b * a.T + it.t_lo + t];
+    gate_stage<KG, NTH>(a, it, zs, tid);
+    for (int t = tid; t < it.tn; t += NTH) dls[t] = a.dl[it.b * a.T + it.t_lo + t];
   }
   cp_async_commit();
   int cur_tile = -1, buf = 0;
-  float wg[TG_FMAX], dwg[TG_FMAX];
+  float wg[FMAXV], dwg[FMAXV];
   auto flush_dwg = [&](int tile) {
 #pragma unroll
-    for (int i = 0; i < TG_FMAX; ++i) if (i < FG) atomicAdd(a.dWg + (size_t)(f0 + i) * a.N + tile * TG_NT + nl, dwg[i]);
+    for (int i = 0; i < FMAXV; ++i) if (i < FG) atomicAdd(a.dWg + (size_t)(f0 + i) * a.N + tile * TG_NT + nl, dwg[i]);
   };
   for (long long item = lo; item < hi; ++item) {
     const GateItem it = gate_item(a, item);
@@ -191,23 +192,23 @@ __global__ void __launch_bounds__(256, 1) time_gate_bwd_kernel(const GateArgs a)
       if (cur_tile >= 0) flush_dwg(cur_tile);
       cur_tile = it.tile;
 #pragma unroll
-      for (int i = 0; i < TG_FMAX; ++i) { wg[i] = i < FG ? __ldg(a.Wg + (size_t)(f0 + i) * a.N + n) : 0.f; dwg[i] = 0.f; }
+      for (int i = 0; i < FMAXV; ++i) { wg[i] = i < FG ? __ldg(a.Wg + (size_t)(f0 + i) * a.N + n) : 0.f; dwg[i] = 0.f; }
     }
-    float c0v[TG_FMAX];
+    float c0v[FMAXV];
 #pragma unroll
-    for (int i = 0; i < TG_FMAX; ++i) c0v[i] = i < FG ? __ldg(a.c0 + ((size_t)it.b * a.F + f0 + i) * a.N + n) : 0.f;
+    for (int i = 0; i < FMAXV; ++i) c0v[i] = i < FG ? __ldg(a.c0 + ((size_t)it.b * a.F + f0 + i) * a.N + n) : 0.f;
     cp_async_wait<0>();
     __syncthreads();
     if (a.nbuf == 2 && item + 1 < hi) {
       const GateItem nx = gate_item(a, item + 1);
-      gate_stage<KG>(a, nx, zs + (buf ^ 1) * zbuf, tid);
-      for (int t = tid; t < nx.tn; t += 256) dls[(buf ^ 1) * TC + t] = a.dl[nx.b * a.T + nx.t_lo + t];
+      gate_stage<KG, NTH>(a, nx, zs + (buf ^ 1) * zbuf, tid);
+      for (int t = tid; t < nx.tn; t += NTH) dls[(buf ^ 1) * TC + t] = a.dl[nx.b * a.T + nx.t_lo + t];
     }
     cp_async_commit();
     const float* zb = zs + buf * zbuf + nl;
     const float* dlb = dls + buf * TC;
 #pragma unroll
-    for (int fb = 0; fb < TG_FMAX; fb += TG_FB) {
+    for (int fb = 0; fb < FMAXV; fb += TG_FB) {
       if (fb < FG) {
         float tb[TG_FB][KG], sA[TG_FB][KG], dw[TG_FB], dc[TG_FB];
 #pragma unroll
@@ -257,8 +258,8 @@ __global__ void __launch_bounds__(256, 1) time_gate_bwd_kernel(const GateArgs a)
       __syncthreads();
       if (item + 1 < hi) {
         const GateItem nx = gate_item(a, item + 1);
-        gate_stage<KG>(a, nx, zs, tid);
-        for (int t = tid; t < nx.tn; t += 256) dls[t] = a.dl[nx.b * a.T + nx.t_lo + t];
+        gate_stage<KG, NTH>(a, nx, zs, tid);
+        for (int t = tid; t < nx.tn; t += NTH) dls[t] = a.dl[nx.b * a.T + nx.t_lo + t];
         cp_async_commit();
       }
     }
@@ -266,7 +267,7 @@ __global__ void __launch_bounds__(256, 1) time_gate_bwd_kernel(const GateArgs a)
   cp_async_wait<0>();
   if (cur_tile >= 0) flush_dwg(cur_tile);
   __syncthreads();
-  for (int i = tid; i < a.F * KG; i += 256) atomicAdd(a.dA + i, dAs[i]);
+  for (int i = tid; i < a.F * KG; i += NTH) atomicAdd(a.dA + i, dAs[i]);
 }
 
 // =====================================================================================================
