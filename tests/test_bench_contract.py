@@ -27,3 +27,21 @@ def test_traffic_reader_finds_committed_export():
     import bench
     t, src = bench.ncu_traffic(['r01_ncu_gemm2_mb1024.raw.csv'], 'shift_gemm2_kernel')
     assert src is not None and 50e6 < t < 600e6
+
+
+def test_traffic_reader_at_the_default_launch_shape():
+    """bench.py's `roofline.traffic` must come from a capture of the SAME launch shape it times (micro-batch 2048)."""
+    sys.path.insert(0, ROOT)
+    import bench
+    t, src = bench.ncu_traffic(['r01_ncu_gemm2_mb2048.raw.csv'], 'shift_gemm2_kernel')
+    operands = 2 * (2048 * 64 * 1024) * 2 + 1024 * 1024 * 2          # bf16 A in, bf16 C out, bf16 operator
+    assert src == 'r01_ncu_gemm2_mb2048.raw.csv' and 0.5 * operands < t < 1.5 * operands
+
+
+def test_cfg5_measured_traffic_per_sequence():
+    """cfg5's roofline object reports measured DRAM bytes per sequence next to the 17.2 GB algorithmic figure; the committed
+    ncu export must contain one launch of each of the seven per-step kernels."""
+    sys.path.insert(0, ROOT)
+    import bench
+    t = bench.cfg5_dram_bytes_per_sequence(bench.CFG5)
+    assert t is not None and 0.5 * bench.BYTES_PER_SEQ_CFG5 < t < 1.5 * bench.BYTES_PER_SEQ_CFG5
