@@ -596,6 +596,9 @@ def run_small(args):
 
 
 def main():
+    # stdout carries exactly one JSON line: NCCL's own version / debug banner goes to stderr
+    if int(os.environ.get('WORLD_SIZE', '1')) > 1:
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=3)
