@@ -27,6 +27,25 @@ FLOP_PER_SEQ_FWD_BWD = 82.82e9      # SURVEY.md §8d, cfg3 (G=1): algorithmic fl
 CFG3 = dict(N=1024, F=64, G=1, K=5, T=64, B=4096, density=0.3)
 
 
+_JSON_OUT = None
+
+
+def json_only_stdout():
+    """Multi-rank runs: libraries (NCCL's version banner) write to file descriptor 1 behind Python's back.  Keep a private copy of
+    the real stdout for the ONE JSON line and point fd 1 at stderr for everything else."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), 'w')
+        os.dup2(2, 1)
+
+
+def emit(out):
+    f = _JSON_OUT or sys.stdout
+    f.write(json.dumps(out) + '\n')
+    f.flush()
+
+
 def peaks():
     p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.isfile(p):
@@ -133,7 +152,7 @@ def run_reference(args):
                            sample=f'B={Bs}, T={Ts} per step on the host CPUs'),
                cpu_baseline=cb, e2e=dict(value=seqs, unit='sequences/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                gpu_launches=0)
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -357,7 +376,7 @@ def run_ours(args):
                    e2e=dict(value=seqs_e2e, unit='sequences/s', h2d_bytes_per_step=int(X_host.numel() * 4 + (Bl // mb) * h0_host.numel() * 4),
                             d2h_bytes_per_step=int(sum(p.numel() for p in used) * 4), ms_per_step=ms_e2e / args.steps),
                    gpu_launches=int(launches), peak_hbm_gb=round(torch.cuda.max_memory_allocated() / 1e9, 1))
-        print(json.dumps(out), flush=True)
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
 
@@ -516,7 +535,7 @@ def run_cfg5(args):
                    e2e=dict(value=seqs_e2e, unit='sequences/s', h2d_bytes_per_step=int(X_host.numel() * 4),
                             d2h_bytes_per_step=int(sum(p.numel() for p in used) * 4), ms_per_step=ms_e2e / args.steps),
                    gpu_launches=int(launches))
-        print(json.dumps(out), flush=True)
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
 
@@ -592,13 +611,13 @@ def run_small(args):
                e2e=dict(value=B * steps / (ms_e * 1e-3), unit='sequences/s', h2d_bytes_per_step=int(X_host.numel() * 4 + h0_host.numel() * 4),
                         d2h_bytes_per_step=int(cell.weight_B.numel() * 4), ms_per_step=ms_e / steps),
                gpu_launches=int(launches))
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 def main():
-    # stdout carries exactly one JSON line: NCCL's own version / debug banner goes to stderr
+    # stdout carries exactly one JSON line: NCCL's own version banner (written to fd 1 by the library) goes to stderr
     if int(os.environ.get('WORLD_SIZE', '1')) > 1:
-        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
+        json_only_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=3)

@@ -45,3 +45,16 @@ def test_cfg5_measured_traffic_per_sequence():
     import bench
     t = bench.cfg5_dram_bytes_per_sequence(bench.CFG5)
     assert t is not None and 0.5 * bench.BYTES_PER_SEQ_CFG5 < t < 1.5 * bench.BYTES_PER_SEQ_CFG5
+
+
+def test_multi_rank_stdout_carries_only_the_json_line():
+    """Under torchrun, libraries write to fd 1 behind Python's back (NCCL's version banner): bench.py keeps a private copy of the real
+    stdout for its ONE JSON line and points fd 1 at stderr."""
+    code = ("import os, sys; sys.argv = ['bench.py', '--impl', 'reference', '--steps', '1', '--warmup', '1', '--cpu-batch', '1', '--cpu-T', '1'];"
+            "import bench; bench.json_only_stdout(); os.system('echo BANNER_FROM_FD1'); bench.main()")
+    env = dict(os.environ, WORLD_SIZE='2', RANK='0')
+    out = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1 and json.loads(lines[0])['impl'] == 'reference', out.stdout
+    assert 'BANNER_FROM_FD1' in out.stderr
