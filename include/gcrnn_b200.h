@@ -73,7 +73,13 @@ int         gcrnn_debug_shift_gemm(const gcrnn_graph* g, int32_t backward, const
 /* tuning switches for tests and A/B measurements (process-wide): name = "gemm_pair" (1: CTA-pair cta_group::2 shift
  * GEMM when the shape allows, 0: single-CTA kernel), "bwd_fused" (fused reverse-time step kernel of the tensor-core path),
  * "sparse_fused" (fused F == 32 edge-gated kernels of the sparse fp32 path; 0 = the generic per-op kernels),
- * "graph_capture" (small fp32 cell calls are captured once per pointer set into a CUDA graph and replayed; 0 = direct launches).  Returns the previous value, or -1 for an unknown name. */
+ * "graph_capture" (small fp32 cell calls are captured once per pointer set into a CUDA graph and replayed; 0 = direct launches),
+ * "gate_fq8" (time-gate kernels with 8 feature groups per CTA: 0 off, 1 forward, 2 forward + backward), and for the fused
+ * sparse kernels "sparse_v2" (bit mask of the stages that run their second-generation kernel: 1 shift, 2 gather-contract,
+ * 4|8 aggregate + bwd_rows, 16 bwd_node, 32 dh; 0 = all first generation), "sparse_v2_tc" (tile contractions: 1 = 3xTF32
+ * mma.sync, 0 = packed FFMA2), "sparse_v2_fuse_dpre", "sparse_v2_bps", "sparse_v2_rows_bps".  A backward always follows the
+ * stage generations its forward used; every call invalidates captured CUDA graphs.
+ * Returns the previous value, or -1 for an unknown name. */
 int         gcrnn_debug_set_option(const char* name, int32_t value);
 
 /* ---- graph -------------------------------------------------------------------------------------- */
