@@ -195,6 +195,9 @@ class Clocks(threading.Thread):
 # ------------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------------
+PREC_DTYPE = {'fp32': 'f32', 'bf16': 'bf16', 'bf16x2': 'bf16x2 (split bf16 hi+lo operands, fp32 accumulate)'}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -209,6 +212,9 @@ def run_ours(args):
     dev = torch.device('cuda', local)
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
+        # the product path: ONE all-reduce per step of every parameter gradient on one flat bucket
+        # (gated_gcrnns_b200.dist.allreduce_gradients), through torch.distributed or the library's own NCCL transport
+        gg.dist.enable(native=bool(args.native_allreduce))
     assert world == args.gpus, f'--gpus {args.gpus} but WORLD_SIZE={world}'
 
     cfg = dict(CFG3)
@@ -233,19 +239,20 @@ def run_ours(args):
     dH = torch.ones(mb, T, F, N, device=dev)
     L = _lib.lib()
     if args.gemm_pair is not None:
-        L.gcrnn_debug_set_option(b'gemm_pair', args.gemm_pair)
+        gg.options.set('gemm_pair', args.gemm_pair)
     if args.bwd_fused is not None:
-        L.gcrnn_debug_set_option(b'bwd_fused', args.bwd_fused)
-    pair = L.gcrnn_debug_set_option(b'gemm_pair', 1)
-    L.gcrnn_debug_set_option(b'gemm_pair', pair)
+        gg.options.set('bwd_fused', args.bwd_fused)
+    pair = gg.options.get('gemm_pair')
 
     # e2e leg: pinned host -> device copies of every micro-batch's X and h0 run on a side stream, double-buffered, so the
-    # PCIe transfer of micro-batch i+1 overlaps the kernels of micro-batch i (all of it inside the timed region)
+    # PCIe transfer of micro-batch i+1 overlaps the kernels of micro-batch i (all of it inside the timed region); the first
+    # micro-batch of step s+1 is prefetched while step s computes (what a training loop's data loader does)
     copy_stream = torch.cuda.Stream(device=dev)
     xbuf = [torch.empty(mb, T, G, N, device=dev) for _ in range(2)]
     hbuf = [torch.empty(mb, F, N, device=dev) for _ in range(2)]
     ready = [torch.cuda.Event() for _ in range(2)]
     freed = [torch.cuda.Event() for _ in range(2)]
+    ctr = {'mb': 0, 'prefetched': False}
 
     def prefetch(i, slot):
         with torch.cuda.stream(copy_stream):
@@ -254,22 +261,27 @@ def run_ours(args):
             hbuf[slot].copy_(h0_host, non_blocking=True)
             ready[slot].record(copy_stream)
 
-    def step(host_inputs):
-        nonlocal Bl
+    def step(host_inputs, prefetch_next=False, nb=None):
+        nb = Bl if nb is None else nb
         for p in used:
             p.grad = None
         main = torch.cuda.current_stream()
-        if host_inputs:
+        if host_inputs and not ctr['prefetched']:
             for sl in range(2):
                 freed[sl].record(main)
-            prefetch(0, 0)
-        for j, i in enumerate(range(0, Bl, mb)):
+            prefetch(0, ctr['mb'] & 1)
+        ctr['prefetched'] = False
+        for i in range(0, nb, mb):
             if host_inputs:
-                slot = j & 1
-                if i + mb < Bl:
+                slot = ctr['mb'] & 1
+                if i + mb < nb:
                     prefetch(i + mb, slot ^ 1)
+                elif prefetch_next:
+                    prefetch(0, slot ^ 1)
+                    ctr['prefetched'] = True
                 main.wait_event(ready[slot])
                 x, h = xbuf[slot], hbuf[slot]
+                ctr['mb'] += 1
             else:
                 x, h = X_dev[i:i + mb], h0_dev
             H = cell(x, h)
@@ -277,16 +289,17 @@ def run_ours(args):
             del H
             if host_inputs:
                 freed[slot].record(main)
-        bucket = torch.cat([p.grad.reshape(-1) for p in used])
         if world > 1:
-            dist.all_reduce(bucket)
+            bucket = gg.dist.allreduce_gradients(used, op='sum')      # product path: one collective per step
+        else:
+            bucket = torch.cat([p.grad.reshape(-1) for p in used])
         if host_inputs:
             return bucket.to('cpu', non_blocking=False)          # D2H read of the step's result
         return bucket
 
     def timed(host_inputs, steps, warmup):
-        for _ in range(warmup):
-            step(host_inputs)
+        for w in range(warmup):
+            step(host_inputs, prefetch_next=host_inputs)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -296,8 +309,8 @@ def run_ours(args):
         l0 = L.gcrnn_debug_launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(steps):
-            step(host_inputs)
+        for s_ in range(steps):
+            step(host_inputs, prefetch_next=host_inputs and s_ + 1 < steps)
         e1.record()
         torch.cuda.synchronize()
         if world > 1:
@@ -312,8 +325,7 @@ def run_ours(args):
         return t.item(), launches, c
 
     if args.once:                    # profiling aid (ncu --set full): one forward+backward of one micro-batch, no timing
-        Bl = mb
-        step(False)
+        step(False, nb=mb)
         torch.cuda.synchronize()
         return
     ms_dev, launches, clocks = timed(False, args.steps, args.warmup)
@@ -321,19 +333,91 @@ def run_ours(args):
     seqs = cfg['B'] * args.steps / (ms_dev * 1e-3)
     seqs_e2e = cfg['B'] * args.steps / (ms_e2e * 1e-3)
 
+    # ---- the other precisions of the same workload (device-resident inputs, short run): seq/s for EVERY mode ---------------
+    modes = {args.precision: dict(value=seqs, ms_per_step=ms_dev / args.steps, steps=args.steps)}
+    for other in [m for m in args.also if m != args.precision]:
+        gg.set_precision(other)
+        o_steps = 2 if other != 'fp32' else 1
+        if other == 'fp32':            # the exact path is ~50x slower at cfg3: time ONE micro-batch of 64 sequences
+            xs, hs, ds = X_dev[:64], h0_dev[:64], dH[:64]
+            for _ in range(2):
+                for p in used:
+                    p.grad = None
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize(); e0.record()
+                torch.autograd.backward(cell(xs, hs), ds)
+                e1.record(); torch.cuda.synchronize()
+            modes[other] = dict(value=64 * world / (e0.elapsed_time(e1) * 1e-3), ms_per_step=e0.elapsed_time(e1), steps=1,
+                                note='fp32 exact path (CUDA cores, sparse shift): one 64-sequence micro-batch per GPU, second of two runs')
+        else:
+            ms_o, _, _ = timed(False, o_steps, 1)
+            modes[other] = dict(value=cfg['B'] * o_steps / (ms_o * 1e-3), ms_per_step=ms_o / o_steps, steps=o_steps)
+    gg.set_precision(args.precision)
+
+    # ---- parity of the timed mode, measured in-run (outside the timed region) on a B = 2 slice at cfg3's own T = 64 ---------
+    # reference = this library's fp32 exact path (itself held to the fp64 oracle by tests/); errors are max-norm relative to max|ref|
+    parity = None
+    if rank == 0 and args.precision != 'fp32' and not args.no_parity:
+        def fb(prec, Tg):
+            gg.set_precision(prec)
+            for p in used:
+                p.grad = None
+            xs, hs = X_dev[:2], h0_dev[:2]
+            d2 = torch.zeros(2, T, F, N, device=dev)
+            g2 = torch.Generator(device='cpu').manual_seed(99)
+            d2[:, :Tg] = torch.randn(2, Tg, F, N, generator=g2).to(dev)
+            Hh = cell(xs, hs)
+            torch.autograd.backward(Hh, d2)
+            return Hh.detach(), torch.cat([p.grad.reshape(-1) for p in used]).clone()
+        Hr, gr16 = fb('fp32', 16)
+        Hm, gm16 = fb(args.precision, 16)
+        hmax = Hr.abs().max()
+        curve = ((Hm - Hr).abs().amax(dim=(0, 2, 3)) / hmax).tolist()
+        parity = dict(mode=args.precision, reference='fp32 exact path of this library (CUDA cores, sparse shift; pinned to the fp64 oracle by tests/)',
+                      T=T, B=2, init='reference init, seed 0', max_rel_H_first16=max(curve[:16]), max_rel_H=max(curve),
+                      max_rel_grad_T16=((gm16 - gr16).abs().max() / gr16.abs().max()).item(),
+                      H_curve_every8=[curve[t] for t in range(0, T, 8)] + [curve[-1]],
+                      note='the recurrence is chaotic under the reference init: fp32 itself drifts from fp64 (tests/test_gpu_tc.py::'
+                           'test_tc_cfg3_full_horizon_vs_oracle, profiles/r02_horizon_*.json); gradients are those of the T = 16 prefix problem')
+        gg.set_precision(args.precision)
+
+    # ---- data-parallel arithmetic check (N > 1): sharded + all-reduced gradients vs a single-rank recompute ------------------
+    grad_check = None
+    if world > 1:
+        Bc = 64
+        gc = torch.Generator(device='cpu').manual_seed(4321)
+        Xc = torch.randn(Bc, T, G, N, generator=gc).to(dev)
+        hc = torch.zeros(Bc, F, N, device=dev)
+        dc = torch.ones(Bc, T, F, N, device=dev)
+        clo, chi = gg.dist.shard_range(Bc, rank, world)
+        for p in used:
+            p.grad = None
+        torch.autograd.backward(cell(Xc[clo:chi], hc[clo:chi]), dc[clo:chi])
+        red = gg.dist.allreduce_gradients(used, op='sum').clone()
+        if rank == 0:
+            for p in used:
+                p.grad = None
+            torch.autograd.backward(cell(Xc, hc), dc)
+            full = torch.cat([p.grad.reshape(-1) for p in used])
+            grad_check = dict(B=Bc, rel_err=((red - full).abs().max() / full.abs().max()).item(),
+                              what='gradient bucket of 64 sequences sharded over the ranks and summed by gated_gcrnns_b200.dist.'
+                                   'allreduce_gradients vs the same 64 sequences on rank 0 alone (max-norm relative)')
+
     # ---- roofline of the dominant kernel (tcgen05 shift GEMM), timed live with CUDA events on its stream -------------
     pk = peaks()
     roof = None
     if args.precision != 'fp32':
+        P = 2 if args.precision == 'bf16x2' else 1
         g = ggraph.get(cell.S, dev, keep_dense=True)
+        g.set_option('gemm_pair', pair)
         R = mb * F
-        A = torch.randn(R, N, device=dev).to(torch.bfloat16)
-        out = torch.empty(R, N, dtype=torch.bfloat16, device=dev)
+        A = torch.randn(R, P * N, device=dev).to(torch.bfloat16)
+        out = torch.empty(R, P * N, dtype=torch.bfloat16, device=dev)
         st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
         reps = 40
 
         def one():
-            _lib.check(L.gcrnn_debug_shift_gemm(g.ptr, 0, C.c_void_p(A.data_ptr()), R, C.c_void_p(out.data_ptr()), C.c_void_p(0), st), 'gemm')
+            _lib.check(L.gcrnn_debug_shift_gemm(g.ptr, 0, C.c_void_p(A.data_ptr()), R, P, C.c_void_p(out.data_ptr()), P, C.c_void_p(0), st), 'gemm')
         for _ in range(5):
             one()
         torch.cuda.synchronize()
@@ -344,15 +428,22 @@ def run_ours(args):
         e1.record()
         torch.cuda.synchronize()
         t_k = e0.elapsed_time(e1) * 1e-3 / reps
-        ach = 2.0 * R * N * N / t_k / 1e12
+        ach = 2.0 * R * N * N / t_k / 1e12               # ALGORITHMIC flops of the shift (one product), whatever the operand split
+        pipe = P * ach                                   # flops the tensor pipe executed (P K-concatenated products)
         step_ach = FLOP_PER_SEQ_FWD_BWD * seqs / world / 1e12
-        traffic, tsrc = ncu_traffic(['r01_ncu_gemm2_mb%d.raw.csv' % mb, 'r01_ncu_gemm2_tma_store.raw.csv'], 'shift_gemm2_kernel' if pair else 'shift_gemm_kernel')
+        traffic, tsrc, tshape = ncu_traffic_for_shape(R, N, P, pair)
+        eq = pk['bf16'] / P
         roof = dict(bound='tensor', achieved=ach, peak=pk['bf16'], unit='TFLOP/s', frac=ach / pk['bf16'], traffic=traffic,
-                    traffic_note=(f'DRAM read+write bytes per launch from profiles/{tsrc} (ncu --set full); algorithmic operand bytes per launch '
-                                  f'at this shape = {(2 * R * N * 2 + N * N * 2) / 1e6:.0f} MB' if tsrc else None),
+                    traffic_note=tshape,
+                    tensor_pipe_achieved=pipe, tensor_pipe_frac=pipe / pk['bf16'],
+                    mode_equivalent_peak=eq, frac_of_mode_equivalent_peak=ach / eq,
+                    mode_note=(f'{args.precision}: every product runs as {P} K-concatenated bf16 MMAs into one fp32 accumulator; `achieved`/`frac` count the '
+                               f'algorithmic 2*M*N^2 flops once against the measured bf16 peak, `tensor_pipe_*` count what the tensor pipe executed, '
+                               f'`mode_equivalent_peak` = bf16 peak / {P} (SURVEY.md 8d: a tf32-class mode is held to half the bf16 peak)'),
                     kernel=f'{"shift_gemm2_kernel (cta_group::2, 256x256 pair tiles)" if pair else "shift_gemm_kernel<256> (cta_group::1)"} '
-                           f'[{R}x{N}]x[{N}x{N}] bf16, {t_k * 1e6:.1f} us/launch, peak = {pk["src"]} burst bf16',
+                           f'[{R}x{P}*{N}]x[{N}x{N}] bf16, {t_k * 1e6:.1f} us/launch, peak = {pk["src"]} burst bf16',
                     step_achieved=step_ach, step_peak=pk['bf16_sustained'], step_frac=step_ach / pk['bf16_sustained'],
+                    step_frac_of_mode_equivalent_peak=step_ach / (pk['bf16_sustained'] / P),
                     step_note='algorithmic 82.82 GFLOP/sequence fwd+bwd x sequences/s per GPU vs sustained bf16 peak (' + pk['src'] + ')')
     else:
         step_ach = FLOP_PER_SEQ_FWD_BWD * seqs / world / 1e12
@@ -367,19 +458,35 @@ def run_ours(args):
     if rank == 0:
         out = dict(metric='GCRNN sequences/sec fwd+bwd', value=seqs, unit='sequences/s', n_gpus=world, steps=args.steps,
                    warmup=args.warmup, ms_per_step=ms_dev / args.steps, higher_is_better=True, scaling='strong',
-                   vs_baseline=None, dtype='bf16' if args.precision != 'fp32' else 'f32', data='synthetic',
+                   vs_baseline=None, dtype=PREC_DTYPE[args.precision], data='synthetic',
                    config=dict(workload='cfg3: dense N=1024 F=64 G=1 K=5 T=64 time-gated GGCRNNCell fwd+bwd',
                                global_batch=cfg['B'], per_gpu_batch=Bl, microbatch=mb, precision=args.precision,
-                               parallelism=f'dp{world} (batch sharded, one gradient all-reduce per step)',
+                               parallelism=f'dp{world} (batch sharded, one gradient all-reduce per step'
+                                           + (f' through gated_gcrnns_b200.dist.allreduce_gradients, transport {"gcrnn_allreduce_sum (C ABI)" if args.native_allreduce else "torch.distributed nccl"})' if world > 1 else ')'),
                                l2=f'inputs larger than L2 (X 1 GiB, H {mb * T * F * N * 4 / 1e9:.1f} GB per micro-batch); no explicit flush'),
                    roofline=roof, cpu_baseline=cb, clocks=clocks,
                    e2e=dict(value=seqs_e2e, unit='sequences/s', h2d_bytes_per_step=int(X_host.numel() * 4 + (Bl // mb) * h0_host.numel() * 4),
                             d2h_bytes_per_step=int(sum(p.numel() for p in used) * 4), ms_per_step=ms_e2e / args.steps),
+                   modes=modes, parity=parity, grad_check=grad_check,
                    gpu_launches=int(launches), peak_hbm_gb=round(torch.cuda.max_memory_allocated() / 1e9, 1))
         emit(out)
     if world > 1:
+        gg.dist.disable()
         dist.destroy_process_group()
 
+
+def ncu_traffic_for_shape(R, N, P, pair):
+    """DRAM bytes per launch of the shift GEMM from a committed `ncu --set full` export captured at EXACTLY this launch shape
+    (rows R, planes P); None with the reason when no export of this shape is committed (never another shape's number)."""
+    name = 'shift_gemm2_kernel' if pair else 'shift_gemm_kernel'
+    fn = f'r02_ncu_gemm2_R{R}_P{P}.raw.csv' if P > 1 or not os.path.isfile(os.path.join(ROOT, 'profiles', f'r01_ncu_gemm2_mb{R // 64}.raw.csv')) \
+        else f'r01_ncu_gemm2_mb{R // 64}.raw.csv'
+    traffic, src = ncu_traffic([fn], name)
+    alg = (2 * R * N * 2 * P + N * N * 2) / 1e6
+    if src is None:
+        return None, None, f'no committed ncu --set full export for this launch shape ([{R}x{P}*{N}] bf16 in and out); algorithmic operand bytes per launch = {alg:.0f} MB'
+    return traffic, src, (f'DRAM read+write bytes per launch from profiles/{src} (ncu --set full, same launch shape [{R}x{P}*{N}]); '
+                          f'algorithmic operand bytes per launch = {alg:.0f} MB')
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -625,7 +732,13 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=CFG3['B'], help='global batch (sequences per step); default = cfg3')
     ap.add_argument('--microbatch', type=int, default=2048)
-    ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
+    ap.add_argument('--precision', default='bf16x2', choices=['bf16x2', 'bf16', 'fp32'],
+                    help='bf16x2 (default): split-bf16 tensor-core mode with the tight stated bound; bf16: plain bf16 operands '
+                         '(fast, short horizons only); fp32: exact CUDA-core path')
+    ap.add_argument('--also', default='bf16', type=lambda v: [m for m in v.split(',') if m],
+                    help='other precisions of the same workload to time briefly for the `modes` object (comma separated; "" = none)')
+    ap.add_argument('--no-parity', action='store_true', help='skip the in-run parity measurement')
+    ap.add_argument('--native-allreduce', type=int, default=0, help='N > 1: 1 = the library\'s own NCCL transport (gcrnn_allreduce_sum)')
     ap.add_argument('--cpu-batch', type=int, default=16)
     ap.add_argument('--cpu-T', type=int, default=8)
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -634,14 +747,14 @@ def main():
     ap.add_argument('--workload', default='cfg3', choices=['cfg3', 'cfg5', 'cfg1', 'cfg2-node', 'cfg2-edge'],
                     help='cfg3 = the headline dense config; cfg5 = sparse kNN graph; cfg1 / cfg2-* = the small reference configurations')
     ap.add_argument('--opt', action='append', default=[], metavar='NAME=VALUE',
-                    help='library debug option (gcrnn_debug_set_option), e.g. sparse_v2=0 for the first-generation sparse kernels')
+                    help='library tuning switch (gated_gcrnns_b200.options), e.g. sparse_v2=0 for the first-generation sparse kernels')
     ap.add_argument('--once', action='store_true', help='run one micro-batch forward+backward and exit (for ncu captures)')
     args = ap.parse_args()
     if args.opt and args.impl != 'reference':
-        from gated_gcrnns_b200 import _lib
+        import gated_gcrnns_b200 as gg
         for kv in args.opt:
             name, value = kv.split('=')
-            assert _lib.lib().gcrnn_debug_set_option(name.encode(), int(value)) != -1 or int(value) == -1, f'unknown option {name}'
+            gg.options.set(name, int(value))
     if args.impl == 'reference':
         run_reference(args)
     elif args.workload == 'cfg5':

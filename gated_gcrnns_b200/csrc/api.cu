@@ -3,20 +3,37 @@
 #include <dlfcn.h>
 #include <cstring>
 
+#include <atomic>
+#include <string>
+
 namespace gcrnn {
 static thread_local char g_err[1024] = "";
-unsigned long long g_launches = 0;
-int g_opt_gemm_pair = 1;
-int g_opt_gate_fq8 = 2;
-int g_opt_bwd_fused = 1;
-int g_opt_sparse_fused = 1;
-int g_opt_sparse_v2 = 63;
-int g_opt_sparse_v2_bps = 2;
-int g_opt_sparse_v2_tc = 1;
-int g_opt_sparse_v2_fuse_dpre = 1;
-int g_opt_sparse_v2_rows_bps = 2;
-int g_opt_graph_capture = 1;
-int64_t g_opt_epoch = 0;
+// monotonic launch statistic (gcrnn_debug_launch_count); internal linkage, atomic
+static std::atomic<unsigned long long> s_launches{0};
+unsigned long long launch_count() { return s_launches.load(std::memory_order_relaxed); }
+void count_launch(unsigned long long n) { s_launches.fetch_add(n, std::memory_order_relaxed); }
+void launch_count_rewind(unsigned long long value) { s_launches.store(value, std::memory_order_relaxed); }
+// options of the handle whose API call is executing on this thread (call-scoped; the defaults are immutable)
+static const Options k_default_options{};
+static thread_local const Options* t_opt = &k_default_options;
+const Options& opt() { return *t_opt; }
+OptScope::OptScope(const Options* o) : prev(t_opt) { t_opt = o ? o : &k_default_options; }
+OptScope::~OptScope() { t_opt = prev; }
+int* option_field(Options& o, const char* name) {
+  const std::string n(name ? name : "");
+  if (n == "bwd_fused") return &o.bwd_fused;
+  if (n == "sparse_fused") return &o.sparse_fused;
+  if (n == "sparse_v2") return &o.sparse_v2;
+  if (n == "sparse_v2_rows_bps") return &o.sparse_v2_rows_bps;
+  if (n == "sparse_v2_fuse_dpre") return &o.sparse_v2_fuse_dpre;
+  if (n == "sparse_v2_tc") return &o.sparse_v2_tc;
+  if (n == "sparse_v2_bps") return &o.sparse_v2_bps;
+  if (n == "graph_capture") return &o.graph_capture;
+  if (n == "gate_fq8") return &o.gate_fq8;
+  if (n == "gemm_pair") return &o.gemm_pair;
+  if (n == "fwd_fused") return &o.fwd_fused;
+  return nullptr;
+}
 void set_last_error(const char* fmt, ...) {
   va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof g_err, fmt, ap); va_end(ap);
 }
@@ -44,7 +61,7 @@ using namespace gcrnn;
 namespace {
 constexpr int GK_PTRS = 72;
 struct GraphKey {
-  const void* p[GK_PTRS]; int64_t B, T; int kind, path; int64_t epoch;   // epoch: bumped by every gcrnn_debug_set_option call
+  const void* p[GK_PTRS]; int64_t B, T; int kind, path, need_dx, pad; int64_t epoch;   // epoch: bumped by every option change on the cell
   bool operator==(const GraphKey& o) const { return memcmp(this, &o, sizeof(GraphKey)) == 0; }
 };
 struct GraphEntry { GraphKey key; cudaGraphExec_t exec; unsigned long long launches; uint64_t stamp; int last_path; };
@@ -64,7 +81,7 @@ void key_params(GraphKey& k, int& n, const gcrnn_cell_params* p) {
   for (size_t i = 0; i < sizeof(gcrnn_cell_params) / sizeof(void*); ++i) { GCRNN_CHECK(n < GK_PTRS, "graph key overflow"); k.p[n++] = q[i]; }
 }
 bool graph_eligible(const gcrnn_cell* c, int64_t B, int64_t T) {
-  return g_opt_graph_capture && c->d.precision == GCRNN_PREC_FP32 &&
+  return c->opt.graph_capture && c->d.precision == GCRNN_PREC_FP32 &&
          (long long)B * T * c->g->N * c->d.F <= (1ll << 22);
 }
 // run `body(stream)` through the cache; body only enqueues work on the stream it is given
@@ -82,7 +99,7 @@ void run_graphed(const gcrnn_cell* c, const GraphKey& key, cudaStream_t user, Bo
   GraphEntry* hit = nullptr;
   for (auto& e : gc.entries) if (e.key == key) { hit = &e; break; }
   if (!hit) {
-    const unsigned long long l0 = g_launches;
+    const unsigned long long l0 = launch_count();
     CUDA_OK(cudaStreamBeginCapture(gc.side, cudaStreamCaptureModeThreadLocal));
     cudaGraph_t graph = nullptr;
     try {
@@ -94,8 +111,8 @@ void run_graphed(const gcrnn_cell* c, const GraphKey& key, cudaStream_t user, Bo
       throw;
     }
     CUDA_OK(cudaStreamEndCapture(gc.side, &graph));
-    GraphEntry e{key, nullptr, g_launches - l0, 0, c->last_path};
-    g_launches = l0;                                  // counted again at every replay, including the first one below
+    GraphEntry e{key, nullptr, launch_count() - l0, 0, c->last_path};
+    launch_count_rewind(l0);                          // counted again at every replay, including the first one below
     cudaError_t st = cudaGraphInstantiate(&e.exec, graph, 0);
     cudaGraphDestroy(graph);
     CUDA_OK(st);
@@ -111,7 +128,7 @@ void run_graphed(const gcrnn_cell* c, const GraphKey& key, cudaStream_t user, Bo
   hit->stamp = ++gc.clock;
   if (key.kind == 0) c->last_path = hit->last_path;
   CUDA_OK(cudaGraphLaunch(hit->exec, gc.side));
-  g_launches += hit->launches;
+  count_launch(hit->launches);
   CUDA_OK(cudaEventRecord(gc.ev_out, gc.side));
   CUDA_OK(cudaStreamWaitEvent(user, gc.ev_out, 0));
 }
@@ -121,20 +138,14 @@ extern "C" {
 
 int gcrnn_abi_version(void) { return GCRNN_ABI_VERSION; }
 const char* gcrnn_last_error(void) { return g_err; }
-uint64_t gcrnn_debug_launch_count(void) { return g_launches; }
-int gcrnn_debug_set_option(const char* name, int32_t value) {
-  ++g_opt_epoch;                                    // captured graphs were built under the old options: never replay them
-  if (name && std::string(name) == "bwd_fused") { int old = gcrnn::g_opt_bwd_fused; gcrnn::g_opt_bwd_fused = value; return old; }
-  if (name && std::string(name) == "sparse_fused") { int old = gcrnn::g_opt_sparse_fused; gcrnn::g_opt_sparse_fused = value; return old; }
-  if (name && std::string(name) == "sparse_v2") { int old = gcrnn::g_opt_sparse_v2; gcrnn::g_opt_sparse_v2 = value; return old; }
-  if (name && std::string(name) == "sparse_v2_rows_bps") { int old = gcrnn::g_opt_sparse_v2_rows_bps; gcrnn::g_opt_sparse_v2_rows_bps = value; return old; }
-  if (name && std::string(name) == "sparse_v2_fuse_dpre") { int old = gcrnn::g_opt_sparse_v2_fuse_dpre; gcrnn::g_opt_sparse_v2_fuse_dpre = value; return old; }
-  if (name && std::string(name) == "sparse_v2_tc") { int old = gcrnn::g_opt_sparse_v2_tc; gcrnn::g_opt_sparse_v2_tc = value; return old; }
-  if (name && std::string(name) == "sparse_v2_bps") { int old = gcrnn::g_opt_sparse_v2_bps; gcrnn::g_opt_sparse_v2_bps = value; return old; }
-  if (name && std::string(name) == "graph_capture") { int old = gcrnn::g_opt_graph_capture; gcrnn::g_opt_graph_capture = value; return old; }
-  if (name && std::string(name) == "gate_fq8") { int old = gcrnn::g_opt_gate_fq8; gcrnn::g_opt_gate_fq8 = value; return old; }
-  if (name && std::string(name) == "gemm_pair") { int old = gcrnn::g_opt_gemm_pair; gcrnn::g_opt_gemm_pair = value; return old; }
-  return -1;
+uint64_t gcrnn_debug_launch_count(void) { return launch_count(); }
+int gcrnn_graph_set_option(gcrnn_graph* g, const char* name, int32_t value) {
+  API_BEGIN
+  GCRNN_CHECK(g && name, "null argument");
+  int* f = option_field(g->opt, name);
+  GCRNN_CHECK(f != nullptr, "unknown option '%s'", name);
+  *f = value; ++g->opt.epoch;
+  API_END
 }
 
 int gcrnn_graph_create_csr(gcrnn_graph** out, int32_t N, int32_t E, const int64_t* const* rowptr,
@@ -178,7 +189,7 @@ int gcrnn_lsigf_forward(const gcrnn_graph* g, const float* h, const float* bias,
   API_BEGIN
   GCRNN_CHECK(g && h && x && y && ws, "null argument");
   GCRNN_CHECK(F > 0 && K > 0 && G > 0 && B > 0, "bad sizes F=%d K=%d G=%d B=%lld", F, K, G, (long long)B);
-  CUDA_OK(cudaSetDevice(g->device));
+  DeviceScope dev_scope(g->device); OptScope opt_scope(&g->opt);
   lsigf_forward_f32(g, h, bias, x, y, F, K, G, B, ws, wsb, (cudaStream_t)stream);
   API_END
 }
@@ -186,7 +197,7 @@ int gcrnn_lsigf_backward(const gcrnn_graph* g, const float* h, const float* x, c
                          float* dbias, int32_t F, int32_t K, int32_t G, int64_t B, void* ws, size_t wsb, void* stream) {
   API_BEGIN
   GCRNN_CHECK(g && h && x && dy && ws, "null argument");
-  CUDA_OK(cudaSetDevice(g->device));
+  DeviceScope dev_scope(g->device); OptScope opt_scope(&g->opt);
   lsigf_backward_f32(g, h, x, dy, dx, dh, dbias, F, K, G, B, ws, wsb, (cudaStream_t)stream);
   API_END
 }
@@ -201,7 +212,7 @@ int gcrnn_gat_forward(const gcrnn_graph* g, const float* mixer, const float* wei
                       int32_t G, int64_t B, void* ws, size_t wsb, void* stream) {
   API_BEGIN
   GCRNN_CHECK(g && mixer && weight && x && y && ws, "null argument");
-  CUDA_OK(cudaSetDevice(g->device));
+  DeviceScope dev_scope(g->device); OptScope opt_scope(&g->opt);
   gat_forward_f32(g, mixer, weight, x, y, F, G, B, ws, wsb, (cudaStream_t)stream);
   API_END
 }
@@ -210,7 +221,7 @@ int gcrnn_gat_backward(const gcrnn_graph* g, const float* mixer, const float* we
                        void* stream) {
   API_BEGIN
   GCRNN_CHECK(g && mixer && weight && x && dy && ws, "null argument");
-  CUDA_OK(cudaSetDevice(g->device));
+  DeviceScope dev_scope(g->device); OptScope opt_scope(&g->opt);
   gat_backward_f32(g, mixer, weight, x, dy, dx, dmixer, dweight, F, G, B, ws, wsb, (cudaStream_t)stream);
   API_END
 }
@@ -222,7 +233,7 @@ int gcrnn_cell_create(gcrnn_cell** out, const gcrnn_cell_desc* d, const gcrnn_gr
   GCRNN_CHECK(d->G > 0 && d->F > 0 && d->Kin > 0 && d->Kst > 0, "bad cell sizes");
   GCRNN_CHECK(d->E == g->E, "cell E=%d does not match graph E=%d", d->E, g->E);
   GCRNN_CHECK(d->spatial_gating >= 0 && d->spatial_gating <= 2, "bad spatial_gating %d", d->spatial_gating);
-  if (d->precision == GCRNN_PREC_BF16_TC) {
+  if (d->precision == GCRNN_PREC_BF16_TC || d->precision == GCRNN_PREC_BF16X2_TC) {
     GCRNN_CHECK(g->S_bf16 != nullptr, "tensor-core precision needs a graph created with keep_dense != 0");
     GCRNN_CHECK(d->spatial_gating == GCRNN_SPATIAL_NONE, "tensor-core path supports time gating only; use fp32 for node/edge gating");
   } else {
@@ -235,7 +246,7 @@ int gcrnn_cell_create(gcrnn_cell** out, const gcrnn_cell_desc* d, const gcrnn_gr
 }
 int gcrnn_cell_destroy(gcrnn_cell* c) {
   API_BEGIN
-  if (c) { cudaSetDevice(c->g->device); delete static_cast<GraphCache*>(c->graph_cache); }
+  if (c) { DeviceScope dev_scope(c->g->device); delete static_cast<GraphCache*>(c->graph_cache); }
   delete c;
   API_END
 }
@@ -245,7 +256,11 @@ int gcrnn_cell_set_option(gcrnn_cell* c, const char* name, int32_t value) {
   const std::string n(name);
   if (n == "need_dx") c->need_dx = value != 0;
   else if (n == "path") { GCRNN_CHECK(value >= -1 && value <= GCRNN_PATH_NODE32, "bad path %d", value); c->forced_path = value; }
-  else GCRNN_CHECK(false, "unknown cell option '%s'", name);
+  else {
+    int* f = option_field(c->opt, name);
+    GCRNN_CHECK(f != nullptr, "unknown cell option '%s'", name);
+    if (*f != value) { *f = value; ++c->opt.epoch; }       // captured CUDA graphs were built under the old options
+  }
   API_END
 }
 int gcrnn_cell_get_option(const gcrnn_cell* c, const char* name, int32_t* value) {
@@ -255,7 +270,11 @@ int gcrnn_cell_get_option(const gcrnn_cell* c, const char* name, int32_t* value)
   if (n == "need_dx") *value = c->need_dx;
   else if (n == "path") *value = c->forced_path;
   else if (n == "last_path") *value = c->last_path;
-  else GCRNN_CHECK(false, "unknown cell option '%s'", name);
+  else {
+    const int* f = option_field(const_cast<gcrnn_cell*>(c)->opt, name);
+    GCRNN_CHECK(f != nullptr, "unknown cell option '%s'", name);
+    *value = *f;
+  }
   API_END
 }
 int gcrnn_cell_workspace_bytes(const gcrnn_cell* c, int64_t B, int64_t T, int32_t need_input_grads, size_t* saved_bytes,
@@ -264,7 +283,8 @@ int gcrnn_cell_workspace_bytes(const gcrnn_cell* c, int64_t B, int64_t T, int32_
   GCRNN_CHECK(c, "null cell");
   size_t su = 0, f, b;
   float* flag = need_input_grads ? (float*)1 : nullptr;
-  if (c->d.precision == GCRNN_PREC_BF16_TC) {
+  OptScope opt_scope(&c->opt);
+  if (c->d.precision != GCRNN_PREC_FP32) {
     f = cell_forward_tc(c, nullptr, nullptr, nullptr, nullptr, nullptr, 0, &su, nullptr, 0, B, T, nullptr);
     b = cell_backward_tc(c, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr, flag, flag, nullptr, 0, B, T, nullptr);
   } else {
@@ -280,15 +300,15 @@ int gcrnn_cell_forward(gcrnn_cell* c, const gcrnn_cell_params* p, const float* X
                        size_t savedb, void* ws, size_t wsb, int64_t B, int64_t T, void* stream) {
   API_BEGIN
   GCRNN_CHECK(c && p && X && h0 && H && ws && saved, "null argument");
-  CUDA_OK(cudaSetDevice(c->g->device));
-  if (c->d.precision == GCRNN_PREC_BF16_TC) cell_forward_tc(c, p, X, h0, H, saved, savedb, nullptr, ws, wsb, B, T, (cudaStream_t)stream);
+  DeviceScope dev_scope(c->g->device); OptScope opt_scope(&c->opt);
+  if (c->d.precision != GCRNN_PREC_FP32) cell_forward_tc(c, p, X, h0, H, saved, savedb, nullptr, ws, wsb, B, T, (cudaStream_t)stream);
   else if (graph_eligible(c, B, T)) {
     GraphKey key; memset(&key, 0, sizeof key);
     int n = 0;
     key_params(key, n, p);
     key.p[n++] = X; key.p[n++] = h0; key.p[n++] = H; key.p[n++] = saved; key.p[n++] = ws;
     key.p[n++] = (const void*)savedb; key.p[n++] = (const void*)wsb;
-    key.B = B; key.T = T; key.kind = 0; key.path = c->forced_path; key.epoch = g_opt_epoch;
+    key.B = B; key.T = T; key.kind = 0; key.path = c->forced_path; key.need_dx = c->need_dx; key.epoch = c->opt.epoch;
     run_graphed(c, key, (cudaStream_t)stream, [&](cudaStream_t st) { cell_forward_f32(c, p, X, h0, H, saved, savedb, nullptr, ws, wsb, B, T, st); });
   } else cell_forward_f32(c, p, X, h0, H, saved, savedb, nullptr, ws, wsb, B, T, (cudaStream_t)stream);
   API_END
@@ -298,8 +318,8 @@ int gcrnn_cell_backward(gcrnn_cell* c, const gcrnn_cell_params* p, const float* 
                         float* dh0, void* ws, size_t wsb, int64_t B, int64_t T, void* stream) {
   API_BEGIN
   GCRNN_CHECK(c && p && X && h0 && H && dH && saved && grads && ws, "null argument");
-  CUDA_OK(cudaSetDevice(c->g->device));
-  if (c->d.precision == GCRNN_PREC_BF16_TC) cell_backward_tc(c, p, X, h0, H, dH, saved, savedb, grads, dX, dh0, ws, wsb, B, T, (cudaStream_t)stream);
+  DeviceScope dev_scope(c->g->device); OptScope opt_scope(&c->opt);
+  if (c->d.precision != GCRNN_PREC_FP32) cell_backward_tc(c, p, X, h0, H, dH, saved, savedb, grads, dX, dh0, ws, wsb, B, T, (cudaStream_t)stream);
   else if (graph_eligible(c, B, T)) {
     GraphKey key; memset(&key, 0, sizeof key);
     int n = 0;
@@ -307,7 +327,7 @@ int gcrnn_cell_backward(gcrnn_cell* c, const gcrnn_cell_params* p, const float* 
     key_params(key, n, grads);
     key.p[n++] = X; key.p[n++] = h0; key.p[n++] = H; key.p[n++] = dH; key.p[n++] = saved; key.p[n++] = dX; key.p[n++] = dh0; key.p[n++] = ws;
     key.p[n++] = (const void*)savedb; key.p[n++] = (const void*)wsb;
-    key.B = B; key.T = T; key.kind = 1; key.path = c->forced_path; key.epoch = g_opt_epoch;
+    key.B = B; key.T = T; key.kind = 1; key.path = c->forced_path; key.need_dx = dX != nullptr; key.epoch = c->opt.epoch;
     run_graphed(c, key, (cudaStream_t)stream,
                 [&](cudaStream_t st) { cell_backward_f32(c, p, X, h0, H, dH, saved, savedb, grads, dX, dh0, ws, wsb, B, T, st); });
   } else cell_backward_f32(c, p, X, h0, H, dH, saved, savedb, grads, dX, dh0, ws, wsb, B, T, (cudaStream_t)stream);
@@ -354,7 +374,7 @@ int gcrnn_comm_unique_id(void* id128) {
 int gcrnn_comm_create(gcrnn_comm** out, const void* id128, int32_t rank, int32_t world, int32_t device) {
   API_BEGIN
   GCRNN_CHECK(out && id128, "null argument");
-  CUDA_OK(cudaSetDevice(device));
+  DeviceScope dev_scope(device);
   nccl_uid id; memcpy(&id, id128, 128);
   auto* c = new gcrnn_comm{nullptr, rank, world, device};
   int r = nccl().CommInitRank(&c->comm, world, id, rank);
@@ -370,7 +390,7 @@ int gcrnn_comm_destroy(gcrnn_comm* c) {
 int gcrnn_allreduce_sum(gcrnn_comm* c, float* bucket, int64_t count, void* stream) {
   API_BEGIN
   GCRNN_CHECK(c && bucket && count >= 0, "bad argument");
-  CUDA_OK(cudaSetDevice(c->device));
+  DeviceScope dev_scope(c->device);
   NCCL_OK(nccl().AllReduce(bucket, bucket, (size_t)count, /*ncclFloat32*/ 7, /*ncclSum*/ 0, c->comm, (cudaStream_t)stream));
   API_END
 }

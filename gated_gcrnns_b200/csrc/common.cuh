@@ -14,17 +14,56 @@ namespace gcrnn {
 
 // ---- error handling: C++ exceptions never cross the ABI; api.cu converts them to codes ----------------
 void set_last_error(const char* fmt, ...);
-extern int g_opt_bwd_fused;            // 1: fused reverse-time step kernel (tc_bwd.cuh) when the shape allows
-extern int g_opt_sparse_fused;         // 1: fused F == 32 edge-gated sparse kernels (sp32_kernels.cuh) when the shape allows
-extern int g_opt_sparse_v2;            // bit mask: which fused sparse stages run their second-generation kernel (sp32_tile.cuh); 63 = all
-extern int g_opt_sparse_v2_rows_bps;   // resident blocks per SM of bwd_rows_v2_k (2 or 3)
-extern int g_opt_sparse_v2_fuse_dpre;  // 1: the dh kernel finishes the next reverse step's dpre in its epilogue
-extern int g_opt_sparse_v2_tc;         // 1: tile contractions on tensor cores (3xTF32 mma.sync), 0: packed FFMA2
-extern int g_opt_sparse_v2_bps;        // resident blocks per SM of the tile kernels (the rest of the 228 KB stays L1)
-extern int g_opt_graph_capture;        // 1: replay small fp32 cell calls as CUDA graphs keyed by their pointer set (api.cu)
-extern int g_opt_gate_fq8;             // time-gate kernels with 8 feature groups (512 threads) when F % 32 == 0: 1 = forward, 2 = forward + backward
-extern int g_opt_gemm_pair;             // 1: use the CTA-pair (cta_group::2) shift GEMM when the shape allows
-extern unsigned long long g_launches;   // kernels launched by this library (gcrnn_debug_launch_count)
+// ---- tuning switches: they live ON THE HANDLE (gcrnn_cell_set_option / gcrnn_graph_set_option); the library keeps no
+// process-wide mutable state.  While an API call executes, opt() returns the options of the handle it was made on.
+struct Options {
+  int bwd_fused = 1;            // fused reverse-time step kernel (tc_bwd.cuh) when the shape allows
+  int sparse_fused = 1;         // fused F == 32 edge-gated sparse kernels (sp32_kernels.cuh) when the shape allows
+  int sparse_v2 = 63;           // bit mask: which fused sparse stages run their second-generation kernel (sp32_tile.cuh)
+  int sparse_v2_rows_bps = 2;   // resident blocks per SM of bwd_rows_v2_k (2 or 3)
+  int sparse_v2_fuse_dpre = 1;  // the dh kernel finishes the next reverse step's dpre in its epilogue
+  int sparse_v2_tc = 1;         // tile contractions on tensor cores (3xTF32 mma.sync), 0: packed FFMA2
+  int sparse_v2_bps = 2;        // resident blocks per SM of the tile kernels (the rest of the 228 KB stays L1)
+  int graph_capture = 1;        // replay small fp32 cell calls as CUDA graphs keyed by their pointer set (api.cu)
+  int gate_fq8 = 2;             // time-gate kernels with 8 feature groups (512 threads): 1 = forward, 2 = forward + backward
+  int gemm_pair = 1;            // CTA-pair (cta_group::2) shift GEMM when the shape allows
+  int fwd_fused = 1;            // forward tap contraction fused into the shift GEMMs (Horner form) when the shape allows
+  long long epoch = 0;          // bumped by every option change on the handle: captured CUDA graphs are keyed by it
+};
+const Options& opt();
+struct OptScope {
+  const Options* prev;
+  explicit OptScope(const Options* o);
+  ~OptScope();
+};
+int* option_field(Options& o, const char* name);     // nullptr for an unknown name
+
+// kernels launched by this library (gcrnn_debug_launch_count): a monotonic statistic, atomically updated
+unsigned long long launch_count();
+void count_launch(unsigned long long n = 1);
+void launch_count_rewind(unsigned long long value);   // CUDA-graph capture: captured launches are counted at replay time
+
+// cudaFuncSetAttribute is per DEVICE: one-time configuration keyed by the current device
+struct DeviceOnce {
+  unsigned long long mask = 0;
+  bool first() {
+    int d = 0;
+    cudaGetDevice(&d);
+    const unsigned long long bit = 1ull << (d & 63);
+    const unsigned long long old = __atomic_fetch_or(&mask, bit, __ATOMIC_RELAXED);
+    return (old & bit) == 0;
+  }
+};
+// the caller's current device is restored when an API call returns
+struct DeviceScope {
+  int prev = -1;
+  explicit DeviceScope(int device) {
+    cudaGetDevice(&prev);
+    if (prev != device) { cudaError_t e = cudaSetDevice(device); if (e != cudaSuccess) throw std::runtime_error(std::string("cudaSetDevice: ") + cudaGetErrorString(e)); }
+    else prev = -1;
+  }
+  ~DeviceScope() { if (prev >= 0) cudaSetDevice(prev); }
+};
 
 struct Error : std::runtime_error {
   int code;
@@ -67,7 +106,9 @@ struct gcrnn_graph {
   float dense_scale = 1.f;            // S_bf16 = bf16(S / dense_scale), dense_scale = max|S|
   __nv_bfloat16* S_bf16 = nullptr;    // S    (K-major B operand of the backward shift  g @ S^T)
   __nv_bfloat16* St_bf16 = nullptr;   // S^T  (K-major B operand of the forward shift   z @ S)
+  int s_planes = 1;                   // operator planes kept, stacked [s_planes * N][N]: 2 when S / dense_scale is not exact in bf16
   std::vector<void*> owned;           // every device allocation, for destroy
+  gcrnn::Options opt;                 // tuning switches used by calls made on the graph handle itself (gcrnn_graph_set_option)
 };
 
 struct gcrnn_cell {
@@ -78,6 +119,7 @@ struct gcrnn_cell {
   mutable int forced_path = -1;   // -1: choose automatically; otherwise GCRNN_PATH_*
   mutable int last_path = 0;      // path taken by the last forward
   mutable int fwd_v2_mask = 63;   // fused sparse path: stage generations the last forward used (its backward follows them)
+  gcrnn::Options opt;             // tuning switches of this handle (gcrnn_cell_set_option)
   mutable void* graph_cache = nullptr;   // api.cu: CUDA graphs of small (launch-bound) fp32 forward / backward calls
 };
 

@@ -28,7 +28,7 @@ void copy(const Ctx& c, void* dst, const void* src, size_t bytes) {
   if (c.dry || bytes == 0) return;
   CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, c.st));
 }
-void check_launch() { ++g_launches; CUDA_OK(cudaGetLastError()); }
+void check_launch() { count_launch(); CUDA_OK(cudaGetLastError()); }
 
 void transpose(const Ctx& c, const float* in, const float* add, float* out, int A, int Bd, long long R1, long long R2,
                long long is1, long long is2, long long os1, long long os2) {
@@ -390,7 +390,7 @@ namespace {
 bool edge32_ok(const gcrnn_cell* cell) {
   const gcrnn_cell_desc& d = cell->d;
   const gcrnn_graph* g = cell->g;
-  return g_opt_sparse_fused && d.spatial_gating == GCRNN_SPATIAL_EDGE && !d.time_gating && d.E == 1 && g->E == 1 && d.F == 32 &&
+  return opt().sparse_fused && d.spatial_gating == GCRNN_SPATIAL_EDGE && !d.time_gating && d.E == 1 && g->E == 1 && d.F == 32 &&
          d.Kst >= 2 && d.Kst <= 4 && d.Kin * d.G <= e32::MAXKG && d.Kin <= e32::MAXK && g->max_row_deg <= 32 && g->N >= 64 &&
          (long long)g->N * 32 < INT_MAX;
 }
@@ -407,9 +407,14 @@ struct Saved32 {
   }
 };
 
-int sm_count() {
-  static int n = 0;
-  if (!n) { int dev = 0; CUDA_OK(cudaGetDevice(&dev)); CUDA_OK(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev)); }
+int sm_count() {                       // of the CURRENT device (cached per device: a process may drive several)
+  static int cached[64] = {0};
+  int dev = 0;
+  CUDA_OK(cudaGetDevice(&dev));
+  if (dev < 64 && cached[dev]) return cached[dev];
+  int n = 0;
+  CUDA_OK(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+  if (dev < 64) cached[dev] = n;
   return n;
 }
 template <class K>
@@ -445,7 +450,7 @@ inline int normalise_v2(int m) {
   return m;
 }
 inline bool v2(int bit) { return (t_v2_mask & bit) != 0; }
-inline int tile_bps() { return std::max(1, std::min(2, g_opt_sparse_v2_bps)); }
+inline int tile_bps() { return std::max(1, std::min(2, opt().sparse_v2_bps)); }
 
 void spmm32(const Ctx& c, const Gather& op, const float* in, float* out, long long R) {
   const long long RN = R * c.g->N;
@@ -476,7 +481,7 @@ void e32_forward_steps(const Ctx& c, const CellDims& d, const gcrnn_cell_params*
   const size_t agg_smem = (size_t)4 * 2 * e32::AGG_STAGE * sizeof(float);
   const int g_agg = persistent_grid(e32::aggregate_k, 128, 4, BN, agg_smem);
   const e32::Gather3 gop{fw.ptr, fw.idx, fw.val};
-  const bool tc = g_opt_sparse_v2_tc != 0;        // 3xTF32 mma.sync contraction, else packed FFMA2
+  const bool tc = opt().sparse_v2_tc != 0;        // 3xTF32 mma.sync contraction, else packed FFMA2
   const long long tiles = d.B * ((d.N + 127) / 128), groups = d.B * ((d.N + 31) / 32);      // 256-thread blocks on 128-node tiles
   const size_t gc_smem = (size_t)e32::gc_smem_floats<KST, 256>(e32::GC_FILTER) * sizeof(float);
   auto k_filter = tc ? e32::gather_contract_k<KST, e32::GC_FILTER, 256, true> : e32::gather_contract_k<KST, e32::GC_FILTER, 256, false>;
@@ -520,7 +525,7 @@ size_t cell_forward_e32(const gcrnn_cell* cell, const gcrnn_cell_params* p, cons
   const CellDims d = dims_of(cell, B, T);
   Arena a(ws, wsb);
   Ctx c{cell->g, st, a.dry()};
-  t_v2_mask = normalise_v2(g_opt_sparse_v2);
+  t_v2_mask = normalise_v2(opt().sparse_v2);
   if (ws != nullptr) cell->fwd_v2_mask = t_v2_mask;
   Saved s; Saved32 x;
   {
@@ -576,17 +581,17 @@ void e32_backward_steps(const Ctx& c, const CellDims& d, const gcrnn_cell_params
   const e32::Gather3 gfw{fw.ptr, fw.idx, fw.val}, gbw{bw.ptr, bw.idx, bw.val};
   const int g_node = persistent_grid(e32::bwd_node_k<KST>, 128, 4, BN);
   const int g_dh = persistent_grid(e32::dh_k<KST>, 128, 4, BN);
-  const bool tc = g_opt_sparse_v2_tc != 0;
+  const bool tc = opt().sparse_v2_tc != 0;
   const long long tiles = d.B * ((d.N + 127) / 128), groups = d.B * ((d.N + 31) / 32);
   const size_t dh_smem = (size_t)e32::gc_smem_floats<KST, 256>(e32::GC_DH) * sizeof(float);
   const size_t node_smem = (size_t)e32::bwd_node_smem_floats<KST, 256>() * sizeof(float);
   auto k_dh = tc ? e32::gather_contract_k<KST, e32::GC_DH, 256, true> : e32::gather_contract_k<KST, e32::GC_DH, 256, false>;
   auto k_node = tc ? e32::bwd_node_v2_k<KST, 256, true> : e32::bwd_node_v2_k<KST, 256, false>;
   const int g_dh2 = v2(V2_DH) ? tile_grid(k_dh, 256, dh_smem, tile_bps(), tiles) : 0;
-  const bool fuse_dpre = tc && v2(V2_DH) && g_opt_sparse_v2_fuse_dpre;     // dh epilogue finishes the next step's dpre (t = 0 still writes dh0)
+  const bool fuse_dpre = tc && v2(V2_DH) && opt().sparse_v2_fuse_dpre;     // dh epilogue finishes the next step's dpre (t = 0 still writes dh0)
   const int g_node2 = v2(V2_NODE) ? tile_grid(k_node, 256, node_smem, tile_bps(), tiles) : 0;
-  auto k_rows = g_opt_sparse_v2_rows_bps == 3 ? e32::bwd_rows_v2_k<3> : e32::bwd_rows_v2_k<2>;     // 3: more warps, some spills
-  const int g_rows2 = v2(V2_ROWS) ? tile_grid(k_rows, 256, 0, g_opt_sparse_v2_rows_bps == 3 ? 3 : 2, groups) : 0;
+  auto k_rows = opt().sparse_v2_rows_bps == 3 ? e32::bwd_rows_v2_k<3> : e32::bwd_rows_v2_k<2>;     // 3: more warps, some spills
+  const int g_rows2 = v2(V2_ROWS) ? tile_grid(k_rows, 256, 0, opt().sparse_v2_rows_bps == 3 ? 3 : 2, groups) : 0;
   for (long long t = d.T - 1; t >= 0; --t) {
     const float* hn = s.Hn + t * BNF;
     const float* wa = x.wu_a + t * BNF; const float* wr = x.wu_r + t * BNF;
@@ -636,7 +641,7 @@ size_t cell_backward_e32(const gcrnn_cell* cell, const gcrnn_cell_params* p, con
   const CellDims d = dims_of(cell, B, T);
   Arena a(ws, wsb);
   Ctx c{cell->g, st, a.dry()};
-  t_v2_mask = (normalise_v2(g_opt_sparse_v2) & ~(V2_AGG | V2_ROWS)) | (cell->fwd_v2_mask & (V2_AGG | V2_ROWS));
+  t_v2_mask = (normalise_v2(opt().sparse_v2) & ~(V2_AGG | V2_ROWS)) | (cell->fwd_v2_mask & (V2_AGG | V2_ROWS));
   Saved s; Saved32 x;
   { Arena sa(const_cast<void*>(saved), savedb); s.layout(sa, d); x.layout(sa, d); }
   Bwd32Bufs b;

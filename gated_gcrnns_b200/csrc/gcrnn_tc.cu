@@ -47,39 +47,50 @@ int num_sms(int device) {
   return n;
 }
 
-// out = A @ (transposed ? S^T... see below).  forward shift z @ S uses Bop = S^T (stored K-major);
-// backward shift g @ S^T uses Bop = S.
-void shift_gemm(const gcrnn_graph* g, bool backward, const __nv_bfloat16* A, long long M, __nv_bfloat16* out_bf16,
+// out = A @ S (forward shift z @ S: Bop = S^T stored K-major) or A @ S^T (backward shift g @ S^T: Bop = S).
+// A: bf16 [M][Pin * N] (Pin signal planes per row), out_bf16: [M][Pout * N], out_f32: [M][N].  With split operands the product
+// is the K-concatenation  sum_a A_a S_0  (+ A_0 S_1 when the operator itself needs a residual plane: weighted graphs).
+void shift_gemm(const gcrnn_graph* g, bool backward, const __nv_bfloat16* A, long long M, int Pin, __nv_bfloat16* out_bf16, int Pout,
                 float* out_f32, cudaStream_t st) {
   const int N = g->N;
   GCRNN_CHECK(g->S_bf16 && g->St_bf16, "graph has no dense bf16 operator");
   GCRNN_CHECK(M > 0 && M < (1ll << 31), "row count out of range");
+  GCRNN_CHECK(Pin >= 1 && Pin <= MAX_PLANES && Pout >= 1 && Pout <= MAX_PLANES, "shift_gemm: 1 or 2 operand planes");
   const __nv_bfloat16* Bop = backward ? g->S_bf16 : g->St_bf16;
-  EpiStore epi{out_bf16, out_f32, (long long)N, g->dense_scale};
+  ShiftSegs segs{};
+  for (int a = 0; a < Pin; ++a) { segs.a[segs.n] = a; segs.b[segs.n] = 0; ++segs.n; }
+  if (Pin > 1 && g->s_planes > 1) { segs.a[segs.n] = 0; segs.b[segs.n] = 1; ++segs.n; }
+  EpiStore epi{out_bf16, out_f32, (long long)N, g->dense_scale, Pout};
   const int sms = num_sms(g->device);
-  if (N % 256 == 0 && g_opt_gemm_pair && M > 128) {
-    CUtensorMap tmA = make_tmap_bf16(A, M, N, 128), tmB = make_tmap_bf16(Bop, N, N, 128);
-    CUtensorMap tmC = out_bf16 ? make_tmap_bf16(out_bf16, M, N, 32) : tmA;      // bf16 output tiles leave through TMA stores
-    launch_shift_gemm2<EpiStore>(tmA, tmB, tmC, epi, (int)M, N, sms, st);
+  const bool split = Pin > 1 || Pout > 1;
+  GCRNN_CHECK(!split || N % 256 == 0, "split-bf16 operands need N %% 256 == 0 (N=%d)", N);
+  if (N % 256 == 0 && (split || (opt().gemm_pair && M > 128))) {
+    CUtensorMap tmA = make_tmap_bf16(A, M, (long long)Pin * N, 128), tmB = make_tmap_bf16(Bop, (long long)g->s_planes * N, N, 128);
+    CUtensorMap tmC = out_bf16 ? make_tmap_bf16(out_bf16, M, (long long)Pout * N, 32) : tmA;      // bf16 output tiles leave through TMA stores
+    launch_shift_gemm2<EpiStore>(tmA, tmB, tmC, epi, (int)M, N, sms, segs, Pout, st);
   } else if (N % 256 == 0) {
-    CUtensorMap tmA = make_tmap_bf16(A, M, N, BM), tmB = make_tmap_bf16(Bop, N, N, 256);
+    CUtensorMap tmA = make_tmap_bf16(A, M, N, BM), tmB = make_tmap_bf16(Bop, (long long)g->s_planes * N, N, 256);
     launch_shift_gemm<256, EpiStore>(tmA, tmB, epi, (int)M, N, sms, st);
   } else {
-    CUtensorMap tmA = make_tmap_bf16(A, M, N, BM), tmB = make_tmap_bf16(Bop, N, N, 128);
+    CUtensorMap tmA = make_tmap_bf16(A, M, N, BM), tmB = make_tmap_bf16(Bop, (long long)g->s_planes * N, N, 128);
     launch_shift_gemm<128, EpiStore>(tmA, tmB, epi, (int)M, N, sms, st);
   }
 }
 
 
 // ---- launch helpers -------------------------------------------------------------------------------------------
-static void launched() { ++g_launches; CUDA_OK(cudaGetLastError()); }
-static void cvt_bf16(const float* in, __nv_bfloat16* out, long long n, cudaStream_t st) {
-  GCRNN_CHECK(n % 4 == 0, "cvt_bf16: length must be a multiple of 4");
-  cvt_bf16_kernel<<<(unsigned)std::min<long long>((n / 4 + 255) / 256, 148 * 16), 256, 0, st>>>(in, out, n / 4);
+static void launched() { count_launch(); CUDA_OK(cudaGetLastError()); }
+// fp32 [rows][N] -> bf16 [rows][P*N]
+static void cvt_bf16(const float* in, __nv_bfloat16* out, long long rows, int N, int P, cudaStream_t st) {
+  GCRNN_CHECK(N % 4 == 0, "cvt_bf16: row length must be a multiple of 4");
+  const long long n4 = rows * (N / 4);
+  cvt_bf16_kernel<<<(unsigned)std::min<long long>((n4 + 255) / 256, 148 * 16), 256, 0, st>>>(in, out, n4, N / 4, P);
   launched();
 }
 struct TcDims {
   int N, F, G, Kin, Kst, sms;
+  int P;                 // operand planes: 1 = GCRNN_PREC_BF16_TC, 2 = GCRNN_PREC_BF16X2_TC (split hi + lo)
+  long long LD;          // bf16 row length P * N
   long long B, T, R, RX, BT;
   bool tg, bias;
 };
@@ -88,6 +99,8 @@ static TcDims tc_dims(const gcrnn_cell* c, int64_t B, int64_t T) {
   d.N = c->g->N; d.F = c->d.F; d.G = c->d.G; d.Kin = c->d.Kin; d.Kst = c->d.Kst;
   d.B = B; d.T = T; d.R = B * d.F; d.RX = B * T * d.G; d.BT = B * T;
   d.tg = c->d.time_gating != 0; d.bias = c->d.bias != 0;
+  d.P = c->d.precision == GCRNN_PREC_BF16X2_TC ? 2 : 1; d.LD = (long long)d.P * d.N;
+  GCRNN_CHECK(d.P == 1 || d.N % 256 == 0, "split-bf16 tensor-core path: N %% 256 == 0 (N=%d)", d.N);
   GCRNN_CHECK(c->d.E == 1 && c->d.spatial_gating == GCRNN_SPATIAL_NONE, "tensor-core path: E == 1, no spatial gating");
   GCRNN_CHECK(d.F % 16 == 0 && d.F <= 64, "tensor-core path: F must be a multiple of 16 and <= 64 (F=%d)", d.F);
   GCRNN_CHECK(d.N % 128 == 0, "tensor-core path: N %% 128 == 0 (N=%d)", d.N);
@@ -101,29 +114,29 @@ static TcDims tc_dims(const gcrnn_cell* c, int64_t B, int64_t T) {
 struct TcSaved {
   float* zx;            // [Kin-1][RX][N]   x_t S^k, k >= 1
   float* gt;            // [2][B][T]        time-gate values
-  __nv_bfloat16* Hb;    // [T][R][N]        bf16 copy of every state (GEMM / wgrad operand)
+  __nv_bfloat16* Hb;    // [T][R][P*N]      bf16 planes of every state (GEMM / wgrad operand)
   void layout(Arena& a, const TcDims& d) {
     zx = a.get<float>((size_t)(d.Kin - 1) * d.RX * d.N);
     gt = d.tg ? a.get<float>(2 * d.BT) : nullptr;
-    Hb = a.get<__nv_bfloat16>((size_t)d.T * d.R * d.N);
+    Hb = a.get<__nv_bfloat16>((size_t)d.T * d.R * d.LD);
   }
 };
 
-// z_k = z_{k-1} @ S (forward) or @ S^T (backward), k = 1..K-1, bf16 slabs [K-1][rows][N]
-static void chain(const gcrnn_graph* g, bool backward, const __nv_bfloat16* z0, __nv_bfloat16* zc, int K, long long rows, cudaStream_t st) {
+// z_k = z_{k-1} @ S (forward) or @ S^T (backward), k = 1..K-1, bf16 slabs [K-1][rows][P*N]
+static void chain(const gcrnn_graph* g, bool backward, const __nv_bfloat16* z0, __nv_bfloat16* zc, int K, long long rows, int P, cudaStream_t st) {
   const __nv_bfloat16* prev = z0;
   for (int k = 1; k < K; ++k) {
-    __nv_bfloat16* out = zc + (size_t)(k - 1) * rows * g->N;
-    shift_gemm(g, backward, prev, rows, out, nullptr, st);
+    __nv_bfloat16* out = zc + (size_t)(k - 1) * rows * P * g->N;
+    shift_gemm(g, backward, prev, rows, P, out, P, nullptr, st);
     prev = out;
   }
 }
 
 static ContractArgs contract_base(const TcDims& d, const __nv_bfloat16* z0, const __nv_bfloat16* zc) {
   ContractArgs a{};
-  a.K = d.Kst; a.C = d.F; a.M = d.F; a.N = d.N; a.B = d.B;
+  a.K = d.Kst; a.C = d.F; a.M = d.F; a.N = d.N; a.B = d.B; a.P = d.P;
   a.slab[0] = z0;
-  for (int k = 1; k < d.Kst; ++k) a.slab[k] = zc + (size_t)(k - 1) * d.R * d.N;
+  for (int k = 1; k < d.Kst; ++k) a.slab[k] = zc + (size_t)(k - 1) * d.R * d.LD;
   return a;
 }
 
@@ -133,6 +146,8 @@ template <int EPI>
 static void launch_tap(const ContractArgs& ca, const __nv_bfloat16* Wp, int sms, cudaStream_t st) {
   TapArgs t{};
   t.K = ca.K; t.C = ca.C; t.M = ca.M; t.N = ca.N; t.KB = (ca.K * ca.C + 63) / 64; t.B = ca.B; t.R = ca.B * ca.C;
+  t.P = ca.P; t.stages = ca.P > 1 ? 6 : TAP_STAGES; t.exact = ca.P > 1;
+  GCRNN_CHECK(ca.P >= 1 && ca.P <= MAX_PLANES, "tap_gemm: 1 or 2 operand planes");
   GCRNN_CHECK(t.KB <= TAP_MAX_KB && (ca.C == 16 || ca.C == 32 || ca.C == 64) && ca.M % 16 == 0 && ca.M <= 64 && ca.N % TAP_BM == 0,
               "tap_gemm: unsupported sizes K=%d C=%d M=%d N=%d", ca.K, ca.C, ca.M, ca.N);
   t.out_f32 = ca.out_f32; t.out_bstride = ca.out_bstride; t.out_bf16 = ca.out_bf16; t.bias = ca.bias; t.bias_scale = ca.bias_scale;
@@ -141,10 +156,13 @@ static void launch_tap(const ContractArgs& ca, const __nv_bfloat16* Wp, int sms,
   t.hprev = ca.hprev; t.hprev_bstride = ca.hprev_bstride; t.dgf = ca.dgf; t.accumulate = ca.accumulate; t.scaled_chain = ca.scaled_chain;
   t.dHn = ca.dHn; t.dHn_bstride = ca.dHn_bstride; t.gfn = ca.gfn; t.red = ca.red;
   for (int k = 2; k < ca.K; ++k)
-    GCRNN_CHECK(ca.slab[k] == ca.slab[1] + (size_t)(k - 1) * t.R * ca.N, "tap_gemm: slabs 1..K-1 must be contiguous");
-  const CUtensorMap tm0 = make_tmap_bf16(ca.slab[0], t.R, ca.N, ca.C);
-  const CUtensorMap tmc = ca.K > 1 ? make_tmap_bf16(ca.slab[1], (long long)(ca.K - 1) * t.R, ca.N, ca.C) : tm0;
-  const CUtensorMap tmW = make_tmap_bf16(Wp, ca.M, (long long)t.KB * 64, ca.M);
+    GCRNN_CHECK(ca.slab[k] == ca.slab[1] + (size_t)(k - 1) * t.R * ca.P * ca.N, "tap_gemm: slabs 1..K-1 must be contiguous");
+  const long long LD = (long long)ca.P * ca.N;
+  const CUtensorMap tm0 = make_tmap_bf16(ca.slab[0], t.R, LD, ca.C);
+  const CUtensorMap tmc = ca.K > 1 ? make_tmap_bf16(ca.slab[1], (long long)(ca.K - 1) * t.R, LD, ca.C) : tm0;
+  const CUtensorMap tmW = make_tmap_bf16(Wp, ca.M, (long long)ca.P * t.KB * 64, ca.M);
+  const int smem = tap_smem_bytes(t.P, t.KB, t.stages);
+  GCRNN_CHECK(smem <= 227 * 1024, "tap_gemm: shared memory budget exceeded (%d B)", smem);
   const long long tiles = ca.B * (ca.N / TAP_BM);
   const int grid = (int)std::min<long long>(tiles, sms);
   GCRNN_CHECK(EPI != TAP_BWDF || ca.Kin * ca.G <= 7, "fused backward epilogue needs Kin*G <= 7");
@@ -153,8 +171,9 @@ static void launch_tap(const ContractArgs& ca, const __nv_bfloat16* Wp, int sms,
 #define TAP_LAUNCH(KGM_, EXACT_)                                                                          \
   do {                                                                                                    \
     auto kern = tap_gemm_kernel<EPI, KGM_, EXACT_>;                                                       \
-    CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TAP_SMEM));           \
-    kern<<<grid, TAP_THREADS, TAP_SMEM, st>>>(tm0, tmc, tmW, t);                                          \
+    static DeviceOnce once;                                                                              \
+    if (once.first()) CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+    kern<<<grid, TAP_THREADS, smem, st>>>(tm0, tmc, tmW, t);                                              \
   } while (0)
   if (EPI == TAP_FWD && KG >= 1 && KG <= 8) {
     switch (KG) {
@@ -176,11 +195,13 @@ static void launch_tap(const ContractArgs& ca, const __nv_bfloat16* Wp, int sms,
   launched();
 }
 
-// prepared bf16 weights [64][KB*64] (zero padded): mode 0 rows = output features, mode 1 rows = input features
-static int prep_contract_weight(const float* W, __nv_bfloat16* out, int F, int K, int mode, cudaStream_t st) {
-  const int ld = ((K * F + 63) / 64) * 64;
+// prepared bf16 weights [64][P * KB*64] (zero padded; plane q at column q * KB*64): mode 0 rows = output features,
+// mode 1 rows = input features
+static size_t weight_elems(int F, int K, int P) { return (size_t)64 * P * (((K * F + 63) / 64) * 64); }
+static int prep_contract_weight(const float* W, __nv_bfloat16* out, int F, int K, int mode, int P, cudaStream_t st) {
+  const int pstride = ((K * F + 63) / 64) * 64, ld = P * pstride;
   CUDA_OK(cudaMemsetAsync(out, 0, (size_t)64 * ld * sizeof(__nv_bfloat16), st));
-  prep_weight_kernel<<<(F * K * F + 255) / 256, 256, 0, st>>>(W, out, F, K, F, ld, mode);
+  prep_weight_kernel<<<(F * K * F + 255) / 256, 256, 0, st>>>(W, out, F, K, F, ld, mode, P, pstride);
   launched();
   return ld;
 }
@@ -189,12 +210,13 @@ static int prep_contract_weight(const float* W, __nv_bfloat16* out, int F, int K
 static void launch_wgrad_tc(const TcDims& d, const __nv_bfloat16* v0, const __nv_bfloat16* vc, const __nv_bfloat16* hb, float* part,
                             cudaStream_t st) {
   WgradTcArgs w{};
-  w.K = d.Kst; w.N = d.N; w.B = d.B; w.R = d.R; w.part = part;
-  const CUtensorMap tm0 = make_tmap_bf16(v0, d.R, d.N, 64);
-  const CUtensorMap tmc = d.Kst > 1 ? make_tmap_bf16(vc, (long long)(d.Kst - 1) * d.R, d.N, 64) : tm0;
-  const CUtensorMap tmH = make_tmap_bf16(hb, d.R, d.N, 64);
+  w.K = d.Kst; w.N = d.N; w.B = d.B; w.R = d.R; w.part = part; w.P = d.P;
+  const CUtensorMap tm0 = make_tmap_bf16(v0, d.R, d.LD, 64);
+  const CUtensorMap tmc = d.Kst > 1 ? make_tmap_bf16(vc, (long long)(d.Kst - 1) * d.R, d.LD, 64) : tm0;
+  const CUtensorMap tmH = make_tmap_bf16(hb, d.R, d.LD, 64);
   const int sm = WT_STAGES * wt_stage_bytes(d.Kst) + 256 + 1024;
-  CUDA_OK(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+  static DeviceOnce once;
+  if (once.first()) CUDA_OK(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   wgrad_tc_kernel<<<d.sms, NUM_THREADS, sm, st>>>(tm0, tmc, tmH, w);
   launched();
 }
@@ -203,21 +225,25 @@ static void launch_wgrad_tc(const TcDims& d, const __nv_bfloat16* v0, const __nv
 template <int KG>
 static void bwd_fused_launch_kg(const CUtensorMap& tm0, const CUtensorMap& tmc, const CUtensorMap& tmH, const CUtensorMap& tmZ,
                                 const CUtensorMap& tmW, const BwdFusedArgs& a, int grid, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    CUDA_OK(cudaFuncSetAttribute(bwd_fused_kernel<KG>, cudaFuncAttributeMaxDynamicSharedMemorySize, BF_SMEM));
-    configured = true;
-  }
-  bwd_fused_kernel<KG><<<grid, BF_THREADS, BF_SMEM, st>>>(tm0, tmc, tmH, tmZ, tmW, a);
+  static DeviceOnce once;
+  if (once.first()) CUDA_OK(cudaFuncSetAttribute(bwd_fused_kernel<KG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  const int smem = bf_smem_bytes(a.P, a.KB, a.stages);
+  GCRNN_CHECK(smem <= 227 * 1024, "fused backward step: shared memory budget exceeded (%d B)", smem);
+  bwd_fused_kernel<KG><<<grid, BF_THREADS, smem, st>>>(tm0, tmc, tmH, tmZ, tmW, a);
+}
+// pair-stage ring depth that fits 227 KB next to P weight planes of K blocks
+static int bf_stages(int P, int K) {
+  for (int st = BF_STAGES; st >= 2; --st) if (bf_smem_bytes(P, K, st) <= 227 * 1024) return st;
+  return 0;
 }
 static void launch_bwd_fused(const TcDims& d, BwdFusedArgs a, const __nv_bfloat16* v0, const __nv_bfloat16* vc, const __nv_bfloat16* hb,
                              const __nv_bfloat16* Zs, const __nv_bfloat16* Wp, cudaStream_t st) {
-  a.K = d.Kst; a.N = d.N; a.KB = d.Kst; a.B = d.B; a.R = d.R; a.G = d.G;
-  const CUtensorMap tm0 = make_tmap_bf16(v0, d.R, d.N, 64);
-  const CUtensorMap tmc = d.Kst > 1 ? make_tmap_bf16(vc, (long long)(d.Kst - 1) * d.R, d.N, 64) : tm0;
-  const CUtensorMap tmH = make_tmap_bf16(hb, d.R, d.N, 64);
+  a.K = d.Kst; a.N = d.N; a.KB = d.Kst; a.B = d.B; a.R = d.R; a.G = d.G; a.P = d.P; a.stages = bf_stages(d.P, d.Kst);
+  const CUtensorMap tm0 = make_tmap_bf16(v0, d.R, d.LD, 64);
+  const CUtensorMap tmc = d.Kst > 1 ? make_tmap_bf16(vc, (long long)(d.Kst - 1) * d.R, d.LD, 64) : tm0;
+  const CUtensorMap tmH = make_tmap_bf16(hb, d.R, d.LD, 64);
   const CUtensorMap tmZ = make_tmap_bf16(Zs, d.BT * BF_ZROWS, d.N, BF_ZROWS);
-  const CUtensorMap tmW = make_tmap_bf16(Wp, 64, (long long)d.Kst * 64, 64);
+  const CUtensorMap tmW = make_tmap_bf16(Wp, 64, (long long)d.P * d.Kst * 64, 64);
   const long long tiles = d.B * (d.N / 128);
   const int grid = (int)std::min<long long>(tiles, d.sms);
   switch (d.Kin * d.G) {
@@ -234,30 +260,36 @@ static void launch_bwd_fused(const TcDims& d, BwdFusedArgs a, const __nv_bfloat1
   launched();
 }
 
-template <int KG>
-static void gate_launch_kg(bool bwd, const GateArgs& ga, int grid, size_t sm, cudaStream_t st) {
+template <int KG, bool EX>
+static void gate_launch_kg_ex(bool bwd, const GateArgs& ga, int grid, size_t sm, cudaStream_t st) {
   if (!bwd) {
-    if (ga.F % 32 == 0 && g_opt_gate_fq8) {           // 8 feature groups: 512 threads, half the tap registers per thread
-      CUDA_OK(cudaFuncSetAttribute(time_gate_fwd_kernel<KG, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-      time_gate_fwd_kernel<KG, 8><<<grid, 512, sm, st>>>(ga);
+    if (ga.F % 32 == 0 && opt().gate_fq8) {           // 8 feature groups: 512 threads, half the tap registers per thread
+      CUDA_OK(cudaFuncSetAttribute(time_gate_fwd_kernel<KG, 8, EX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      time_gate_fwd_kernel<KG, 8, EX><<<grid, 512, sm, st>>>(ga);
     } else {
-      CUDA_OK(cudaFuncSetAttribute(time_gate_fwd_kernel<KG, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-      time_gate_fwd_kernel<KG, 4><<<grid, 256, sm, st>>>(ga);
+      CUDA_OK(cudaFuncSetAttribute(time_gate_fwd_kernel<KG, 4, EX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      time_gate_fwd_kernel<KG, 4, EX><<<grid, 256, sm, st>>>(ga);
     }
   } else {
-    if (ga.F % 32 == 0 && g_opt_gate_fq8 >= 2) {
-      CUDA_OK(cudaFuncSetAttribute(time_gate_bwd_kernel<KG, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-      time_gate_bwd_kernel<KG, 8><<<grid, 512, sm, st>>>(ga);
+    if (ga.F % 32 == 0 && opt().gate_fq8 >= 2) {
+      CUDA_OK(cudaFuncSetAttribute(time_gate_bwd_kernel<KG, 8, EX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      time_gate_bwd_kernel<KG, 8, EX><<<grid, 512, sm, st>>>(ga);
     } else {
-      CUDA_OK(cudaFuncSetAttribute(time_gate_bwd_kernel<KG, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-      time_gate_bwd_kernel<KG, 4><<<grid, 256, sm, st>>>(ga);
+      CUDA_OK(cudaFuncSetAttribute(time_gate_bwd_kernel<KG, 4, EX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      time_gate_bwd_kernel<KG, 4, EX><<<grid, 256, sm, st>>>(ga);
     }
   }
+}
+template <int KG>
+static void gate_launch_kg(bool bwd, const GateArgs& ga, int grid, size_t sm, cudaStream_t st) {
+  if (ga.exact) gate_launch_kg_ex<KG, true>(bwd, ga, grid, sm, st);
+  else gate_launch_kg_ex<KG, false>(bwd, ga, grid, sm, st);
 }
 
 static void gate_launch(bool bwd, GateArgs ga, const TcDims& d, cudaStream_t st) {
   GCRNN_CHECK(d.F % TG_FQ == 0 && d.F / TG_FQ <= TG_FMAX && d.N % TG_NT == 0, "time gate kernel: unsupported F=%d N=%d", d.F, d.N);
   const int KG = d.Kin * d.G;
+  ga.exact = d.P > 1;
   if (KG > 8) {                      // generic kernel: taps in shared memory
     const size_t sm = gate_generic_smem_bytes(d.T, KG, d.F);
     GCRNN_CHECK(sm <= 200 * 1024, "time gate kernel: T*Kin*G too large for shared memory staging (%zu B)", sm);
@@ -310,16 +342,16 @@ size_t cell_forward_tc(const gcrnn_cell* cell, const gcrnn_cell_params* p, const
                        cudaStream_t st) {
   TcDims d = tc_dims(cell, B, T);
   const gcrnn_graph* g = cell->g;
+  const int P = d.P;
   Arena a(ws, wsb);
   TcSaved s;
   { Arena sa(saved, savedb); s.layout(sa, d); if (saved_used) *saved_used = sa.off; }
   GCRNN_CHECK(a.dry() || saved, "forward needs the `saved` buffer");
-  __nv_bfloat16* xb0 = a.get<__nv_bfloat16>((size_t)d.RX * d.N);
-  __nv_bfloat16* xb1 = a.get<__nv_bfloat16>((size_t)d.RX * d.N);
-  __nv_bfloat16* hb0 = a.get<__nv_bfloat16>((size_t)d.R * d.N);
-  __nv_bfloat16* zb = a.get<__nv_bfloat16>((size_t)(d.Kst - 1) * d.R * d.N);
-  const size_t wbuf = (size_t)64 * (((d.Kst * d.F + 63) / 64) * 64);
-  __nv_bfloat16* Wb = a.get<__nv_bfloat16>(wbuf);
+  __nv_bfloat16* xb0 = a.get<__nv_bfloat16>((size_t)d.RX * d.LD);
+  __nv_bfloat16* xb1 = a.get<__nv_bfloat16>((size_t)d.RX * d.LD);
+  __nv_bfloat16* hb0 = a.get<__nv_bfloat16>((size_t)d.R * d.LD);
+  __nv_bfloat16* zb = a.get<__nv_bfloat16>((size_t)(d.Kst - 1) * d.R * d.LD);
+  __nv_bfloat16* Wb = a.get<__nv_bfloat16>(weight_elems(d.F, d.Kst, P));
   float* c0 = d.tg ? a.get<float>((size_t)d.R * d.N) : nullptr;
   float* logit = d.tg ? a.get<float>(2 * d.BT) : nullptr;
   if (a.dry()) return a.off;
@@ -328,20 +360,20 @@ size_t cell_forward_tc(const gcrnn_cell* cell, const gcrnn_cell_params* p, const
 
   // ---- x_t S^k for every (b, t): one batched chain (rows = B*T*G) ------------------------------------------------
   if (d.Kin > 1) {
-    cvt_bf16(X, xb0, d.RX * d.N, st);
+    cvt_bf16(X, xb0, d.RX, d.N, P, st);
     __nv_bfloat16* cur = xb0; __nv_bfloat16* nxt = xb1;
     for (int k = 1; k < d.Kin; ++k) {
-      shift_gemm(g, false, cur, d.RX, (k < d.Kin - 1) ? nxt : nullptr, s.zx + (size_t)(k - 1) * d.RX * d.N, st);
+      shift_gemm(g, false, cur, d.RX, P, (k < d.Kin - 1) ? nxt : nullptr, P, s.zx + (size_t)(k - 1) * d.RX * d.N, st);
       std::swap(cur, nxt);
     }
   }
-  cvt_bf16(h0, hb0, d.R * d.N, st);
+  cvt_bf16(h0, hb0, d.R, d.N, P, st);
   // ---- time gates (graphML.py:2357-2374): depend on (x_t, h0) only -> all (b, t) at once ---------------------------
   if (d.tg) {
-    chain(g, false, hb0, zb, d.Kst, d.R, st);
+    chain(g, false, hb0, zb, d.Kst, d.R, P, st);
     CUDA_OK(cudaMemsetAsync(logit, 0, 2 * d.BT * sizeof(float), st));
     for (int gi = 0; gi < 2; ++gi) {
-      prep_contract_weight(p->t_weight_B[gi], Wb, d.F, d.Kst, 0, st);
+      prep_contract_weight(p->t_weight_B[gi], Wb, d.F, d.Kst, 0, P, st);
       ContractArgs ca = contract_base(d, hb0, zb);
       ca.out_f32 = c0; ca.out_bstride = FN; ca.bias = p->t_bias[gi]; ca.bias_scale = 2.f;   // bias enters twice (:2421-2422)
       launch_tap<TAP_PLAIN>(ca, Wb, d.sms, st);
@@ -354,12 +386,12 @@ size_t cell_forward_tc(const gcrnn_cell* cell, const gcrnn_cell_params* p, const
     }
   }
   // ---- the recurrence -------------------------------------------------------------------------------------------
-  prep_contract_weight(p->weight_B, Wb, d.F, d.Kst, 0, st);
+  prep_contract_weight(p->weight_B, Wb, d.F, d.Kst, 0, P, st);
   for (long long t = 0; t < d.T; ++t) {
-    const __nv_bfloat16* hprev = t == 0 ? hb0 : s.Hb + (size_t)(t - 1) * d.R * d.N;
-    if (!(t == 0 && d.tg)) chain(g, false, hprev, zb, d.Kst, d.R, st);      // at t = 0 the gates' h0 chain is still in zb
+    const __nv_bfloat16* hprev = t == 0 ? hb0 : s.Hb + (size_t)(t - 1) * d.R * d.LD;
+    if (!(t == 0 && d.tg)) chain(g, false, hprev, zb, d.Kst, d.R, P, st);      // at t = 0 the gates' h0 chain is still in zb
     ContractArgs ca = contract_base(d, hprev, zb);
-    ca.out_f32 = H + t * FN; ca.out_bstride = d.T * FN; ca.out_bf16 = s.Hb + (size_t)t * d.R * d.N;
+    ca.out_f32 = H + t * FN; ca.out_bstride = d.T * FN; ca.out_bf16 = s.Hb + (size_t)t * d.R * d.LD;
     ca.bias = p->bias;
     ca.gi = d.tg ? s.gt + t : nullptr; ca.gf = d.tg ? s.gt + d.BT + t : nullptr; ca.gate_stride = d.T;
     ca.A = p->weight_A; ca.Kin = d.Kin; ca.G = d.G;
@@ -376,21 +408,22 @@ size_t cell_backward_tc(const gcrnn_cell* cell, const gcrnn_cell_params* p, cons
                         int64_t T, cudaStream_t st) {
   TcDims d = tc_dims(cell, B, T);
   const gcrnn_graph* g = cell->g;
+  const int P = d.P;
   Arena a(ws, wsb);
   TcSaved s;
   { Arena sa(const_cast<void*>(saved), savedb); s.layout(sa, d); }
   GCRNN_CHECK(a.dry() || saved, "backward needs the buffer written by forward");
   const int max_sms = 256;
-  __nv_bfloat16* vb0 = a.get<__nv_bfloat16>((size_t)d.R * d.N);
-  __nv_bfloat16* vb0b = a.get<__nv_bfloat16>((size_t)d.R * d.N);
+  __nv_bfloat16* vb0 = a.get<__nv_bfloat16>((size_t)d.R * d.LD);
+  __nv_bfloat16* vb0b = a.get<__nv_bfloat16>((size_t)d.R * d.LD);
   float* red = a.get<float>((size_t)d.R * 8);
-  __nv_bfloat16* vb = a.get<__nv_bfloat16>((size_t)(d.Kst - 1) * d.R * d.N);
+  __nv_bfloat16* vb = a.get<__nv_bfloat16>((size_t)(d.Kst - 1) * d.R * d.LD);
   float* dhrec = a.get<float>((size_t)d.R * d.N);
-  const size_t wbuf = (size_t)64 * (((d.Kst * d.F + 63) / 64) * 64);
-  __nv_bfloat16* hb0 = a.get<__nv_bfloat16>((size_t)d.R * d.N);
+  const size_t wbuf = weight_elems(d.F, d.Kst, P);
+  __nv_bfloat16* hb0 = a.get<__nv_bfloat16>((size_t)d.R * d.LD);
   __nv_bfloat16* WTb = a.get<__nv_bfloat16>(wbuf);
   float* part = a.get<float>((size_t)max_sms * d.Kst * d.F * d.F);
-  const bool fused = g_opt_bwd_fused && d.F == 64 && d.Kin * d.G <= 8 && d.Kst <= 6 && d.N % 128 == 0;
+  const bool fused = opt().bwd_fused && d.F == 64 && d.Kin * d.G <= 8 && d.Kst <= 6 && d.N % 128 == 0 && bf_stages(P, d.Kst) >= 2;
   __nv_bfloat16* Zs = fused ? a.get<__nv_bfloat16>((size_t)d.BT * BF_ZROWS * d.N) : nullptr;
   float* partA = fused ? a.get<float>((size_t)max_sms * 64 * BF_ZROWS) : nullptr;
   float *dgt = nullptr, *c0 = nullptr, *dc0 = nullptr, *dl = nullptr;
@@ -412,7 +445,7 @@ size_t cell_backward_tc(const gcrnn_cell* cell, const gcrnn_cell_params* p, cons
     if (d.F == 64) { launch_wgrad_tc(d, v0p, vb, h16, part, st); return; }
     WgradArgs w{};
     w.v0 = v0p; w.vc = vb; w.h = h32; w.h_bstride = hstride; w.scale = nullptr; w.scale_stride = 0;
-    w.part = part; w.K = d.Kst; w.F = d.F; w.N = d.N; w.B = d.B;
+    w.part = part; w.K = d.Kst; w.F = d.F; w.N = d.N; w.B = d.B; w.P = P;
     const size_t sm = ((size_t)2 * d.Kst * 64 * WG_LD + (size_t)2 * 64 * WG_LD) * sizeof(__nv_bfloat16);
     CUDA_OK(cudaFuncSetAttribute(wgrad_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     wgrad_mma_kernel<<<d.sms, 256, sm, st>>>(w);
@@ -425,8 +458,8 @@ size_t cell_backward_tc(const gcrnn_cell* cell, const gcrnn_cell_params* p, cons
 
   CUDA_OK(cudaMemsetAsync(part, 0, part_bytes, st));
   if (d.tg) CUDA_OK(cudaMemsetAsync(dgt, 0, 2 * d.BT * sizeof(float), st));
-  prep_contract_weight(p->weight_B, WTb, d.F, d.Kst, 1, st);
-  cvt_bf16(h0, hb0, d.R * d.N, st);
+  prep_contract_weight(p->weight_B, WTb, d.F, d.Kst, 1, P, st);
+  cvt_bf16(h0, hb0, d.R, d.N, P, st);
 
   // ---- reverse-time sweep -------------------------------------------------------------------------------------------
   CUDA_OK(cudaMemsetAsync(red, 0, (size_t)d.R * 8 * sizeof(float), st));
@@ -434,7 +467,7 @@ size_t cell_backward_tc(const gcrnn_cell* cell, const gcrnn_cell_params* p, cons
   auto run_dpre = [&](long long t, const float* dhrec_in, __nv_bfloat16* v0_out) {
     DpreArgs da{};
     da.dH = dH + t * FN; da.dH_bstride = d.T * FN; da.Ht = H + t * FN; da.H_bstride = d.T * FN;
-    da.dhrec = dhrec_in; da.v0 = v0_out;
+    da.dhrec = dhrec_in; da.v0 = v0_out; da.P = P;
     da.gi = d.tg ? s.gt + t : nullptr; da.gf = d.tg ? s.gt + d.BT + t : nullptr; da.gate_stride = d.T;
     da.A = p->weight_A; da.bias = p->bias; da.Kin = d.Kin; da.G = d.G; da.F = d.F; da.N = d.N;
     da.x0 = X + t * GN; da.x0_bstride = d.T * GN; da.zx = s.zx + t * GN; da.zx_kstride = d.RX * d.N; da.zx_bstride = d.T * GN;
@@ -454,8 +487,8 @@ size_t cell_backward_tc(const gcrnn_cell* cell, const gcrnn_cell_params* p, cons
   for (long long t = d.T - 1; t >= 0; --t) {
     const float* hprev = t > 0 ? H + (t - 1) * FN : h0;
     const long long hstride = t > 0 ? d.T * FN : FN;
-    const __nv_bfloat16* hprev16 = t > 0 ? s.Hb + (size_t)(t - 1) * d.R * d.N : hb0;
-    chain(g, true, v0cur, vb, d.Kst, d.R, st);
+    const __nv_bfloat16* hprev16 = t > 0 ? s.Hb + (size_t)(t - 1) * d.R * d.LD : hb0;
+    chain(g, true, v0cur, vb, d.Kst, d.R, P, st);
     if (fused) {
       BwdFusedArgs fa{};
       fa.last = t == 0; fa.dh0 = dh0 ? dhrec : nullptr;
@@ -510,8 +543,8 @@ size_t cell_backward_tc(const gcrnn_cell* cell, const gcrnn_cell_params* p, cons
   // ---- time gates, batched over (b, t) -----------------------------------------------------------------------------------
   if (d.tg) {
     for (int gi = 0; gi < 2; ++gi) {
-      chain(g, false, hb0, vb, d.Kst, d.R, st);  // the v slabs are free here: they hold h0's forward chain for a moment
-      prep_contract_weight(p->t_weight_B[gi], Wb, d.F, d.Kst, 0, st);
+      chain(g, false, hb0, vb, d.Kst, d.R, P, st);  // the v slabs are free here: they hold h0's forward chain for a moment
+      prep_contract_weight(p->t_weight_B[gi], Wb, d.F, d.Kst, 0, P, st);
       ContractArgs cc = contract_base(d, hb0, vb);
       cc.out_f32 = c0; cc.out_bstride = FN; cc.bias = p->t_bias[gi]; cc.bias_scale = 2.f;
       launch_tap<TAP_PLAIN>(cc, Wb, d.sms, st);
@@ -528,11 +561,11 @@ size_t cell_backward_tc(const gcrnn_cell* cell, const gcrnn_cell_params* p, cons
         launched();
       }
       // h0 path of the sub-cell: v_k = dc0 (S^T)^k ; dB_g,k = v_k h0^T ; dh0 += sum_k B_g,k^T v_k
-      cvt_bf16(dc0, vb0, d.R * d.N, st);
-      chain(g, true, vb0, vb, d.Kst, d.R, st);
+      cvt_bf16(dc0, vb0, d.R, d.N, P, st);
+      chain(g, true, vb0, vb, d.Kst, d.R, P, st);
       if (gr->t_weight_B[gi]) { wgrad_v(vb0, h0, FN, hb0); wgrad_flush(gr->t_weight_B[gi]); }
       if (dh0) {
-        prep_contract_weight(p->t_weight_B[gi], Wb, d.F, d.Kst, 1, st);
+        prep_contract_weight(p->t_weight_B[gi], Wb, d.F, d.Kst, 1, P, st);
         ContractArgs cb = contract_base(d, vb0, vb);
         cb.out_f32 = dhrec; cb.out_bstride = FN; cb.hprev = h0; cb.hprev_bstride = FN; cb.accumulate = 1;
         launch_tap<TAP_BWD>(cb, Wb, d.sms, st);
@@ -543,24 +576,34 @@ size_t cell_backward_tc(const gcrnn_cell* cell, const gcrnn_cell_params* p, cons
   return a.off;
 }
 
+// bf16 copies of S and S^T, stacked planes [s_planes * N][N]: plane 0 = bf16(S / max|S|), plane 1 = bf16 of the residual.
+// An unweighted graph (cfg3: S = W / lambda_max with 0/1 W) is exact in plane 0 and keeps one plane; the split-bf16 path adds
+// the product with plane 1 for weighted graphs.
 void tc_prepare_graph(gcrnn_graph* g, const float* S) {
   const int N = g->N;
   GCRNN_CHECK(N % 128 == 0, "the tensor-core path needs N %% 128 == 0 (N=%d)", N);
-  std::vector<__nv_bfloat16> s((size_t)N * N), st((size_t)N * N);
+  const size_t NN = (size_t)N * N;
+  std::vector<__nv_bfloat16> s(2 * NN), st(2 * NN);
   float mx = 0.f;
-  for (size_t i = 0; i < (size_t)N * N; ++i) mx = std::max(mx, std::fabs(S[i]));
+  for (size_t i = 0; i < NN; ++i) mx = std::max(mx, std::fabs(S[i]));
   g->dense_scale = mx > 0.f ? mx : 1.f;
+  bool residual = false;
   for (int i = 0; i < N; ++i)
     for (int j = 0; j < N; ++j) {
-      __nv_bfloat16 v = __float2bfloat16(S[(size_t)i * N + j] / g->dense_scale);
-      s[(size_t)i * N + j] = v;
-      st[(size_t)j * N + i] = v;
+      const float x = S[(size_t)i * N + j] / g->dense_scale;
+      const __nv_bfloat16 hi = __float2bfloat16(x);
+      const __nv_bfloat16 lo = __float2bfloat16(x - __bfloat162float(hi));
+      residual = residual || __bfloat162float(lo) != 0.f;
+      s[(size_t)i * N + j] = hi; st[(size_t)j * N + i] = hi;
+      s[NN + (size_t)i * N + j] = lo; st[NN + (size_t)j * N + i] = lo;
     }
+  g->s_planes = residual ? 2 : 1;
+  const size_t bytes = (size_t)g->s_planes * NN * sizeof(__nv_bfloat16);
   for (int which = 0; which < 2; ++which) {
     __nv_bfloat16* d = nullptr;
-    CUDA_OK(cudaMalloc(&d, (size_t)N * N * sizeof(__nv_bfloat16)));
+    CUDA_OK(cudaMalloc(&d, bytes));
     g->owned.push_back(d);
-    CUDA_OK(cudaMemcpy(d, which ? st.data() : s.data(), (size_t)N * N * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(d, which ? st.data() : s.data(), bytes, cudaMemcpyHostToDevice));
     (which ? g->St_bf16 : g->S_bf16) = d;
   }
   g->Npad = N;
@@ -568,12 +611,14 @@ void tc_prepare_graph(gcrnn_graph* g, const float* S) {
 
 }  // namespace gcrnn
 
-extern "C" int gcrnn_debug_shift_gemm(const gcrnn_graph* g, int32_t backward, const void* A_bf16, int64_t M, void* out_bf16,
-                                      float* out_f32, void* stream) {
+extern "C" int gcrnn_debug_shift_gemm(const gcrnn_graph* g, int32_t backward, const void* A_bf16, int64_t M, int32_t planes_in,
+                                      void* out_bf16, int32_t planes_out, float* out_f32, void* stream) {
   try {
     if (!g || !A_bf16) throw gcrnn::Error(-2, "null argument");
-    CUDA_OK(cudaSetDevice(g->device));
-    gcrnn::tc::shift_gemm(g, backward != 0, (const __nv_bfloat16*)A_bf16, M, (__nv_bfloat16*)out_bf16, out_f32, (cudaStream_t)stream);
+    gcrnn::DeviceScope dev(g->device);
+    gcrnn::OptScope os(&g->opt);
+    gcrnn::tc::shift_gemm(g, backward != 0, (const __nv_bfloat16*)A_bf16, M, planes_in, (__nv_bfloat16*)out_bf16, planes_out, out_f32,
+                          (cudaStream_t)stream);
   } catch (const std::exception& e) {
     gcrnn::set_last_error("%s", e.what());
     return -1;

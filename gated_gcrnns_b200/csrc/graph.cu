@@ -82,7 +82,7 @@ static void build_attention_pattern(gcrnn_graph* g, const HostCsr& s) {
 
 gcrnn_graph* graph_from_host_csr(int N, int E, const std::vector<HostCsr>& ops, int device) {
   GCRNN_CHECK(N > 0 && E > 0, "bad graph size N=%d E=%d", N, E);
-  CUDA_OK(cudaSetDevice(device));
+  DeviceScope dev_scope(device);
   auto* g = new gcrnn_graph();
   g->N = N; g->E = E; g->device = device;
   try {
@@ -132,6 +132,7 @@ gcrnn_graph* graph_create_dense(int N, int E, const float* S, int keep_dense, in
   }
   gcrnn_graph* g = graph_from_host_csr(N, E, ops, device);
   if (keep_dense) {
+    DeviceScope dev_scope(device);
     try {
       GCRNN_CHECK(E == 1, "the tensor-core path needs E == 1 (got %d)", E);
       tc_prepare_graph(g, S);
@@ -146,7 +147,7 @@ gcrnn_graph* graph_create_dense(int N, int E, const float* S, int keep_dense, in
 
 void graph_destroy(gcrnn_graph* g) {
   if (!g) return;
-  cudaSetDevice(g->device);
+  DeviceScope dev_scope(g->device);
   for (void* p : g->owned) cudaFree(p);
   delete g;
 }

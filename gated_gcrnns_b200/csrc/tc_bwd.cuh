@@ -25,13 +25,19 @@ constexpr int BF_STAGES = 4;
 constexpr int BF_STAGE_BYTES = 32768;
 constexpr int BF_AUX = 2;
 constexpr int BF_AUX_BYTES = 16384 + 4096;
-constexpr int BF_W_BYTES = 6 * 8192;
 constexpr int BF_THREADS = 64 + 16 * 32;
 constexpr int BF_ZROWS = 16;                       // rows of a Zs tile: Kin*G taps, one constant row, zero padding
-constexpr int BF_SMEM = BF_STAGES * BF_STAGE_BYTES + BF_AUX * BF_AUX_BYTES + BF_W_BYTES + 256 + (64 * 8 + 64) * 4 + 8 * 8 + 1024;
+// dynamic shared memory: stage ring + aux ring + P weight planes of KB blocks + barriers / taps / bias / pointers
+inline int bf_smem_bytes(int P, int KB, int stages) {
+  return stages * BF_STAGE_BYTES + BF_AUX * BF_AUX_BYTES + P * KB * 8192 + 256 + (64 * 8 + 64) * 4 + 8 * 8 + 1024;
+}
 
 struct BwdFusedArgs {
-  int K, N, KB;                 // taps, nodes, 64-row weight blocks (2 * ceil(K/2))
+  int K, N, KB;                 // taps, nodes, 64-row weight blocks per plane (= K)
+  int P;                        // operand planes of the chain slabs, the weights and v0_out (1: bf16, 2: split hi + lo).
+                                // dh (MMA1) uses v0 W0 + v0 W1 + v1 W0; the weight-gradient products (MMA2 / MMA3) sum both
+                                // planes of v against plane 0 of h / Zs (their rounding noise averages over B*N summands)
+  int stages;                   // pair-stage ring depth (<= BF_STAGES)
   long long B, R;               // samples, rows per slab (B*64)
   int last;                     // t == 0: no earlier step; write dh0 instead
   float* dh0;                   // [B][64][N] (last only, may be null)
@@ -60,9 +66,9 @@ bwd_fused_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sV = smem;                                              // [BF_STAGES][2 halves][2 taps][64 rows][128 B]
-  uint8_t* sX = sV + BF_STAGES * BF_STAGE_BYTES;                   // [BF_AUX]{ h: [2 halves][64][128 B], Zs: [2 halves][16][128 B] }
-  uint8_t* sW = sX + BF_AUX * BF_AUX_BYTES;                        // [KB][64 rows g][128 B]
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sW + BF_W_BYTES);
+  uint8_t* sX = sV + a.stages * BF_STAGE_BYTES;                    // [BF_AUX]{ h: [2 halves][64][128 B], Zs: [2 halves][16][128 B] }
+  uint8_t* sW = sX + BF_AUX * BF_AUX_BYTES;                        // [P][KB][64 rows g][128 B]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sW + a.P * a.KB * 8192);
   uint64_t* empty_bar = full_bar + BF_STAGES;
   uint64_t* aux_full = empty_bar + BF_STAGES;
   uint64_t* aux_empty = aux_full + BF_AUX;
@@ -94,7 +100,7 @@ bwd_fused_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
   }
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
   // the unused second tap of an odd last pair is multiplied by zero weights: it must hold finite numbers
-  for (int i = threadIdx.x; i < BF_STAGES * BF_STAGE_BYTES / 16; i += BF_THREADS) reinterpret_cast<uint4*>(sV)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = threadIdx.x; i < a.stages * BF_STAGE_BYTES / 16; i += BF_THREADS) reinterpret_cast<uint4*>(sV)[i] = make_uint4(0, 0, 0, 0);
   if (!a.last) {
     for (int i = threadIdx.x; i < 64 * KG; i += BF_THREADS) sAw[i] = a.A[i];
     for (int kg = threadIdx.x; kg < KG; kg += BF_THREADS) {
@@ -113,8 +119,8 @@ bwd_fused_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0 && has_work) {
-      mbar_expect_tx(w_bar, (uint32_t)(a.KB * 8192));
-      for (int kb = 0; kb < a.KB; ++kb) tma_load_2d(sW + kb * 8192, &tmW, w_bar, kb * 64, 0);
+      mbar_expect_tx(w_bar, (uint32_t)(a.P * a.KB * 8192));
+      for (int kb = 0; kb < a.P * a.KB; ++kb) tma_load_2d(sW + kb * 8192, &tmW, w_bar, kb * 64, 0);   // plane q = blocks [q*KB, (q+1)*KB)
       int stage = 0; uint32_t phase = 0;
       int ax = 0; uint32_t aphase = 0;
       for (long long tile = tile_lo; tile < tile_hi; ++tile) {
@@ -128,7 +134,8 @@ bwd_fused_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
         tma_load_2d(xd + 16384, &tmZ, aux_full + ax, n0, (int)(a.zs_row0 + b * a.zs_rowb));
         tma_load_2d(xd + 16384 + 2048, &tmZ, aux_full + ax, n0 + 64, (int)(a.zs_row0 + b * a.zs_rowb));
         if (++ax == BF_AUX) { ax = 0; aphase ^= 1; }
-        for (int p = 0; p < NP; ++p) {
+        for (int pq = 0; pq < NP * a.P; ++pq) {                    // (tap pair p, signal plane q)
+          const int p = pq / a.P, q = pq % a.P;
           const int ntap = (2 * p + 1 < a.K) ? 2 : 1;
           mbar_wait(empty_bar + stage, phase ^ 1);
           uint8_t* dst = sV + stage * BF_STAGE_BYTES;
@@ -137,10 +144,10 @@ bwd_fused_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
             const int k = 2 * p + j;
             const CUtensorMap* tm = (k == 0) ? &tm0 : &tmc;
             const int row = (k == 0) ? (int)(b * 64) : (int)((long long)(k - 1) * a.R + b * 64);
-            tma_load_2d(dst + j * 8192, tm, full_bar + stage, n0, row);
-            tma_load_2d(dst + 16384 + j * 8192, tm, full_bar + stage, n0 + 64, row);
+            tma_load_2d(dst + j * 8192, tm, full_bar + stage, q * a.N + n0, row);
+            tma_load_2d(dst + 16384 + j * 8192, tm, full_bar + stage, q * a.N + n0 + 64, row);
           }
-          if (++stage == BF_STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == a.stages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -162,32 +169,36 @@ bwd_fused_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
         tc_fence_after();
         const uint32_t d1 = tmem_base + (uint32_t)(acc * 64);
         const uint32_t sh = smem_u32(sX + ax * BF_AUX_BYTES);
-        for (int p = 0; p < NP; ++p) {
+        for (int pq = 0; pq < NP * a.P; ++pq) {
+          const int p = pq / a.P, q = pq % a.P;
           const int ntap = (2 * p + 1 < a.K) ? 2 : 1;
           mbar_wait(full_bar + stage, phase);
           tc_fence_after();
           const uint32_t sv = smem_u32(sV + stage * BF_STAGE_BYTES);
-          // MMA1: contraction rows (tap, f) of this pair, 16 at a time
-          for (int ks = 0; ks < 4 * ntap; ++ks) {
-            const uint64_t adesc = make_mnmajor_sw128_desc(sv + ks * 2048, 16384);
-            const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(sW + (2 * p + (ks >> 2)) * 8192)) + (uint64_t)(2 * (ks & 3));
-            umma_f16(d1, adesc, bdesc, idesc1, (p | ks) != 0);
+          // MMA1: contraction rows (tap, f) of this pair, 16 at a time; signal plane q meets weight planes w with q + w < P
+          for (int w = 0; w + q < a.P; ++w) {
+            for (int ks = 0; ks < 4 * ntap; ++ks) {
+              const uint64_t adesc = make_mnmajor_sw128_desc(sv + ks * 2048, 16384);
+              const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(sW + (w * a.KB + 2 * p + (ks >> 2)) * 8192)) + (uint64_t)(2 * (ks & 3));
+              umma_f16(d1, adesc, bdesc, idesc1, (pq | w | ks) != 0);
+            }
           }
-          // MMA2 (+ MMA3 on pair 0): K = 128 nodes = 2 halves x 4 steps
+          // MMA2 (+ MMA3 on pair 0): K = 128 nodes = 2 halves x 4 steps; both signal planes accumulate into the same D
           const uint32_t d2 = tmem_base + TMEM_D2 + (uint32_t)(p * 64);
+          const bool fresh = first && q == 0;
 #pragma unroll
           for (int hs = 0; hs < 8; ++hs) {
             const int h = hs >> 2, ks = hs & 3;
             const uint64_t adesc = make_kmajor_sw128_desc(sv + h * 16384) + (uint64_t)(2 * ks);
             const uint64_t bdesc = make_kmajor_sw128_desc(sh + h * 8192) + (uint64_t)(2 * ks);
-            umma_f16(d2, adesc, bdesc, idesc2, !(first && hs == 0));
+            umma_f16(d2, adesc, bdesc, idesc2, !(fresh && hs == 0));
             if (p == 0) {
               const uint64_t zdesc = make_kmajor_sw128_desc(sh + 16384 + h * 2048) + (uint64_t)(2 * ks);
-              umma_f16(tmem_base + TMEM_D3, adesc, zdesc, idesc3, !(first && hs == 0));
+              umma_f16(tmem_base + TMEM_D3, adesc, zdesc, idesc3, !(fresh && hs == 0));
             }
           }
           umma_commit(empty_bar + stage);
-          if (++stage == BF_STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == a.stages) { stage = 0; phase ^= 1; }
         }
         first = false;
         umma_commit(tmem_full + acc);
@@ -244,13 +255,14 @@ bwd_fused_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
           if (lane == 0) atomicAdd(a.dgf + b * a.gate_stride, vgf > 1e-30f ? part / vgf : 0.f);
         }
       } else {
-        __nv_bfloat16* ob = a.v0_out + ((size_t)b * 64 + m0) * a.N + n;
+        const long long ldo = (long long)a.P * a.N;
+        __nv_bfloat16* ob = a.v0_out + ((size_t)b * 64 + m0) * ldo + n;
         const float* aw = sAw + m0 * KG;
         float sgi = 0.f, sgf = 0.f;
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const float dp = (dhn[i] + v[i]) * fmaf(-hp[i], hp[i], 1.f);
-          ob[(size_t)i * a.N] = __float2bfloat16(vgfn * dp);
+          store_planes(ob + (size_t)i * ldo, a.N, a.P, vgfn * dp);
           const float bb = sBias[m0 + i];
           float axb = bb;
 #pragma unroll

@@ -48,25 +48,34 @@ __device__ __forceinline__ float tanh_fast(float x) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));   // MUFU.TANH, |err| <= 2^-10.99: below the bf16 operand noise
   return y;
 }
-__global__ void cvt_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n4) {
+// in: fp32 [rows][N]  ->  out: bf16 [rows][P*N], plane 0 = bf16(x), plane 1 = bf16(x - plane 0)   (N4 = N / 4)
+__global__ void cvt_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n4, int N4, int P) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-    const float4 v = reinterpret_cast<const float4*>(in)[i];
-    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
-    uint2 u; u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
-    reinterpret_cast<uint2*>(out)[i] = u;
+    float4 v = reinterpret_cast<const float4*>(in)[i];
+    const long long row = i / N4, c = i % N4;
+    uint2* o = reinterpret_cast<uint2*>(out) + row * P * N4 + c;
+    uint2 u; u.x = pack_bf16x2(v.x, v.y); u.y = pack_bf16x2(v.z, v.w);
+    o[0] = u;
+    if (P > 1) {
+      bf16x2_residual(u.x, v.x, v.y); bf16x2_residual(u.y, v.z, v.w);
+      uint2 w; w.x = pack_bf16x2(v.x, v.y); w.y = pack_bf16x2(v.z, v.w);
+      o[N4] = w;
+    }
   }
 }
 
 // ---- weight preparation: W[f, k, g] fp32 -> bf16 [rows][ld] ------------------------------------------------------
 // mode 0: out[f][k*G + g] = W[f,k,g]          (forward contraction, rows = output features)
 // mode 1: out[g][k*F + f] = W[f,k,g]          (data-gradient contraction, rows = input features)
-__global__ void prep_weight_kernel(const float* __restrict__ W, __nv_bfloat16* __restrict__ out, int F, int K, int G, int ld, int mode) {
+// P planes per row at column offsets q * pstride (row length ld = P * pstride): plane 1 = bf16 residual of plane 0
+__global__ void prep_weight_kernel(const float* __restrict__ W, __nv_bfloat16* __restrict__ out, int F, int K, int G, int ld, int mode,
+                                   int P, int pstride) {
   const int total = F * K * G;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int g = i % G, k = (i / G) % K, f = i / (G * K);
     const float v = W[i];
-    if (mode == 0) out[(size_t)f * ld + k * G + g] = __float2bfloat16(v);
-    else out[(size_t)g * ld + k * F + f] = __float2bfloat16(v);
+    __nv_bfloat16* o = (mode == 0) ? out + (size_t)f * ld + k * G + g : out + (size_t)g * ld + k * F + f;
+    store_planes(o, pstride, P, v);
   }
 }
 
@@ -76,8 +85,9 @@ __global__ void prep_weight_kernel(const float* __restrict__ W, __nv_bfloat16* _
 
 struct ContractArgs {
   const __nv_bfloat16* W;    // [M][ldw] bf16, columns = slab-major
-  const __nv_bfloat16* slab[8];   // K slabs (taps), each [B][C][N] bf16
+  const __nv_bfloat16* slab[8];   // K slabs (taps), each [B][C][P*N] bf16
   int K, C, M, N, ldw;
+  int P;                          // operand planes per bf16 row (slabs, weights, bf16 outputs)
   long long B;
   // EPI_PLAIN: out_f32[b,m,n] = acc + bias_scale * bias[m]
   // EPI_FWD  : h = tanh(gi (a + bias) + gf (acc + bias)), a = sum_{k,g} A[m,k,g] zx_k[(b,t,g), n]
@@ -108,6 +118,7 @@ struct WgradArgs {
   const float* scale; long long scale_stride;   // per-sample scale (gf[b,t]) or null
   float* part;                                   // [grid][K][F][F] fp32, read-modify-write by its owner CTA
   int K, F, N; long long B;
+  int P;                                         // planes per row of the v slabs (row stride P*N); plane 0 is used
 };
 
 __global__ void __launch_bounds__(256, 1) wgrad_mma_kernel(const WgradArgs a) {
@@ -132,7 +143,7 @@ __global__ void __launch_bounds__(256, 1) wgrad_mma_kernel(const WgradArgs a) {
     for (int i = tid; i < a.K * 64 * 8; i += 256) {
       const int ch = i & 7, row = (i >> 3) & 63, k = i >> 9;
       if (row < a.F) {
-        const __nv_bfloat16* src = (k == 0 ? a.v0 : a.vc + (size_t)(k - 1) * a.B * a.F * a.N) + ((size_t)(b * a.F + row) * a.N + n0 + ch * 8);
+        const __nv_bfloat16* src = (k == 0 ? a.v0 : a.vc + (size_t)(k - 1) * a.B * a.F * a.P * a.N) + ((size_t)(b * a.F + row) * a.P * a.N + n0 + ch * 8);
         cp_async16(smem_u32(vd + ((size_t)k * 64 + row) * WG_LD + ch * 8), src);
       }
     }
@@ -229,7 +240,8 @@ struct DpreArgs {
   const float* dH; long long dH_bstride;        // dH[b, t]  : [F][N] at dH + b*bstride
   const float* Ht; long long H_bstride;         // h_t[b]
   const float* dhrec;                           // [B][F][N] or null (t = T-1)
-  __nv_bfloat16* v0;                            // out: bf16 (g_f * dpre) [B][F][N]: input of the adjoint chain (scaled)
+  __nv_bfloat16* v0;                            // out: bf16 (g_f * dpre) [B][F][P*N]: input of the adjoint chain (scaled)
+  int P;                                        // bf16 planes of v0
   const float* gi; const float* gf; long long gate_stride;
   const float* A; const float* bias; int Kin, G, F, N;
   const float* x0; long long x0_bstride; const float* zx; long long zx_kstride, zx_bstride;
@@ -255,7 +267,7 @@ __global__ void __launch_bounds__(256) dpre_kernel(const DpreArgs a) {
     const float4* pdH = reinterpret_cast<const float4*>(a.dH + b * a.dH_bstride + (size_t)f * a.N);
     const float4* pH = reinterpret_cast<const float4*>(a.Ht + b * a.H_bstride + (size_t)f * a.N);
     const float4* pR = a.dhrec ? reinterpret_cast<const float4*>(a.dhrec + ((size_t)b * a.F + f) * a.N) : nullptr;
-    uint2* pV = reinterpret_cast<uint2*>(a.v0 + ((size_t)b * a.F + f) * a.N);
+    uint2* pV = reinterpret_cast<uint2*>(a.v0 + ((size_t)b * a.F + f) * a.P * a.N);
     float sdp = 0.f, sa = 0.f;
     for (int kg0 = 0; kg0 < KG || kg0 == 0; kg0 += DP_KG) {
       float sz[DP_KG];
@@ -267,9 +279,14 @@ __global__ void __launch_bounds__(256) dpre_kernel(const DpreArgs a) {
         if (pR) { const float4 r = pR[i]; d.x += r.x; d.y += r.y; d.z += r.z; d.w += r.w; }
         d.x *= 1.f - hv.x * hv.x; d.y *= 1.f - hv.y * hv.y; d.z *= 1.f - hv.z * hv.z; d.w *= 1.f - hv.w * hv.w;
         if (kg0 == 0) {
-          __nv_bfloat162 p = __floats2bfloat162_rn(vgf * d.x, vgf * d.y), q = __floats2bfloat162_rn(vgf * d.z, vgf * d.w);
-          uint2 u; u.x = *reinterpret_cast<uint32_t*>(&p); u.y = *reinterpret_cast<uint32_t*>(&q);
+          float s0 = vgf * d.x, s1 = vgf * d.y, s2 = vgf * d.z, s3 = vgf * d.w;
+          uint2 u; u.x = pack_bf16x2(s0, s1); u.y = pack_bf16x2(s2, s3);
           pV[i] = u;
+          if (a.P > 1) {
+            bf16x2_residual(u.x, s0, s1); bf16x2_residual(u.y, s2, s3);
+            uint2 w; w.x = pack_bf16x2(s0, s1); w.y = pack_bf16x2(s2, s3);
+            pV[N4 + i] = w;
+          }
           sdp += (d.x + d.y) + (d.z + d.w);
         }
 #pragma unroll

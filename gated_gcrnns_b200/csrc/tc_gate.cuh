@@ -34,7 +34,9 @@ struct GateArgs {
   float* dA;                      // bwd: [F,Kin,G] +=
   int TC, nchunks, nbuf;          // time steps per item, items per (tile, sample), staging buffers
   int bchunk;                     // generic kernel: samples per CTA
+  int exact;                      // 1: tanh through ex2 + rcp (abs. error ~2e-7; split-bf16 mode), 0: tanh.approx (2^-11)
 };
+template <bool EX> __device__ __forceinline__ float gate_tanh(float x) { return EX ? tanh_acc(x) : tanh_fast(x); }
 
 inline size_t gate_smem_bytes(int TC, int KG, int F, int nbuf) {
   return ((size_t)nbuf * TC * KG * TG_NT + TG_NWMAX * (size_t)TC + 2 * (size_t)TC + 2 * (size_t)F * KG) * sizeof(float);
@@ -69,7 +71,7 @@ __device__ __forceinline__ void gate_stage(const GateArgs& a, const GateItem& it
 // FQ feature groups per CTA (64 * FQ threads, F / FQ features per thread).  FQ = 8 halves the per-thread tap registers so that
 // 16 warps are resident instead of 8: with 8 warps the kernel issues on only half of the cycles (profiles/r01_ncu_gate.raw.csv:
 // 2 warps per scheduler stalled on fixed-latency FMA -> MUFU dependencies).
-template <int KG, int FQ>
+template <int KG, int FQ, bool EX>
 __global__ void __launch_bounds__(64 * FQ, 1) time_gate_fwd_kernel(const GateArgs a) {
   constexpr int NTH = 64 * FQ, NW = NTH / 32, FMAXV = 64 / FQ;
   extern __shared__ __align__(16) float gsm[];
@@ -129,7 +131,7 @@ __global__ void __launch_bounds__(64 * FQ, 1) time_gate_fwd_kernel(const GateArg
                 float pre = c0v[i];
 #pragma unroll
                 for (int kg = 0; kg < KG; ++kg) pre = fmaf(ta[i][kg], z[kg], pre);
-                p = fmaf(wg[i], tanh_fast(pre), p);
+                p = fmaf(wg[i], gate_tanh<EX>(pre), p);
               }
             }
           }
@@ -154,7 +156,7 @@ __global__ void __launch_bounds__(64 * FQ, 1) time_gate_fwd_kernel(const GateArg
 
 // backward: given dl[b,t] = d loss / d logit:  dpu = dl Wg (1 - u^2);  dWg += dl u;  dc0[b,f,n] = sum_t dpu;
 // dA[f,kg] += sum_{b,t,n} dpu zx_kg.   u is recomputed (one MUFU) instead of being stored (8.6 GB per gate at cfg3).
-template <int KG, int FQ>
+template <int KG, int FQ, bool EX>
 __global__ void __launch_bounds__(64 * FQ, 1) time_gate_bwd_kernel(const GateArgs a) {
   constexpr int NTH = 64 * FQ, FMAXV = 64 / FQ;
   extern __shared__ __align__(16) float gsm[];
@@ -229,7 +231,7 @@ __global__ void __launch_bounds__(64 * FQ, 1) time_gate_bwd_kernel(const GateArg
             float pre = c0v[fb + i];
 #pragma unroll
             for (int kg = 0; kg < KG; ++kg) pre = fmaf(tb[i][kg], z[kg], pre);
-            const float u = tanh_fast(pre);
+            const float u = gate_tanh<EX>(pre);
             dw[i] = fmaf(dlv, u, dw[i]);
             const float dpu = (dlv * wg[fb + i]) * fmaf(-u, u, 1.f);
             dc[i] += dpu;
@@ -331,7 +333,7 @@ __global__ void __launch_bounds__(256) time_gate_generic_kernel(const GateArgs a
             const float* ap = As + (f0 + i) * KG;
 #pragma unroll 5
             for (int kg = 0; kg < KG; ++kg) pre = fmaf(ap[kg], zt[kg * TG_NT], pre);
-            part = fmaf(wg[i], tanh_fast(pre), part);
+            part = fmaf(wg[i], a.exact ? tanh_acc(pre) : tanh_fast(pre), part);
           }
         }
         part = warp_sum_f(part);
@@ -356,7 +358,7 @@ __global__ void __launch_bounds__(256) time_gate_generic_kernel(const GateArgs a
             float pre = c0v[i];
 #pragma unroll 5
             for (int kg = 0; kg < KG; ++kg) pre = fmaf(ap[kg], zt[kg * TG_NT], pre);
-            const float u = tanh_fast(pre);
+            const float u = a.exact ? tanh_acc(pre) : tanh_fast(pre);
             const float dlv = dls[t];
             dw = fmaf(dlv, u, dw);
             const float dpu = dlv * wg[i] * (1.f - u * u);

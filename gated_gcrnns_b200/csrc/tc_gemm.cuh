@@ -117,33 +117,70 @@ struct GemmSmem {
   static constexpr int TOTAL = TILE_BYTES + 256 + 1024;  // barriers + slack for the manual 1024 B alignment
 };
 
+// ---- split-bf16 operand planes ---------------------------------------------------------------------------------
+// A bf16 "slab" holds P planes per row: row r = [plane 0: N values | plane 1: N values | ...], plane 0 = bf16(x),
+// plane 1 = bf16(x - plane 0) (the rounding residual, exact in fp32), so plane 0 + plane 1 carries ~16 mantissa bits.
+// P = 1 is the plain bf16 path.  Products of split operands are K-concatenated MMAs into one fp32 accumulator:
+// x y ~= x0 y0 + x1 y0 + x0 y1 (the x1 y1 term is 2^-18 relative and dropped).
+constexpr int MAX_PLANES = 2;
+constexpr int MAX_SEGS = 3;
+struct ShiftSegs {
+  int n;                 // number of K-concatenated products (1..MAX_SEGS)
+  int a[MAX_SEGS];       // signal plane of product s (column offset a * N in the slab)
+  int b[MAX_SEGS];       // operator plane of product s (row offset b * N in the stacked operator)
+};
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&p);
+}
+// residuals of a packed pair: (a - bf16(a), b - bf16(b)), exact in fp32
+__device__ __forceinline__ void bf16x2_residual(uint32_t packed, float& a, float& b) {
+  a -= __uint_as_float(packed << 16);
+  b -= __uint_as_float(packed & 0xFFFF0000u);
+}
+
+// tanh(x) = 1 - 2 / (exp(2x) + 1): MUFU.EX2 + MUFU.RCP, absolute error ~2e-7 (saturates correctly at +-inf)
+__device__ __forceinline__ float tanh_acc(float x) {
+  float t, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(x * 2.885390081777927f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t + 1.f));
+  return fmaf(-2.f, r, 1.f);
+}
+// bf16 planes of x at dst[0], dst[plane_stride], ...: plane 0 = bf16(x), plane 1 = bf16(x - plane 0)
+__device__ __forceinline__ void store_planes(__nv_bfloat16* dst, long long plane_stride, int P, float x) {
+  const __nv_bfloat16 hi = __float2bfloat16(x);
+  dst[0] = hi;
+  if (P > 1) dst[plane_stride] = __float2bfloat16(x - __bfloat162float(hi));
+}
+
 // ---- epilogue functors: called once per (row, 32-column chunk) with the fp32 accumulators ------------------
 struct EpiStore {
-  __nv_bfloat16* out_bf16;   // [M, ld] or null
+  __nv_bfloat16* out_bf16;   // [M, planes * ld] or null
   float* out_f32;            // [M, ld] or null
   long long ld;
   float scale;               // the bf16 operator holds S / scale (exact for unweighted graphs); undone here in fp32
+  int planes;                // bf16 planes written per row (1 or 2)
   __device__ __forceinline__ void operator()(int row, int col0, float* v) const {
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] *= scale;
-    if (out_bf16) {
-      uint4* dst = reinterpret_cast<uint4*>(out_bf16 + (long long)row * ld + col0);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        __nv_bfloat162 a = __floats2bfloat162_rn(v[8 * i + 0], v[8 * i + 1]);
-        __nv_bfloat162 b = __floats2bfloat162_rn(v[8 * i + 2], v[8 * i + 3]);
-        __nv_bfloat162 c = __floats2bfloat162_rn(v[8 * i + 4], v[8 * i + 5]);
-        __nv_bfloat162 d = __floats2bfloat162_rn(v[8 * i + 6], v[8 * i + 7]);
-        uint4 u;
-        u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
-        u.z = *reinterpret_cast<uint32_t*>(&c); u.w = *reinterpret_cast<uint32_t*>(&d);
-        dst[i] = u;
-      }
-    }
     if (out_f32) {
       float4* dst = reinterpret_cast<float4*>(out_f32 + (long long)row * ld + col0);
 #pragma unroll
       for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    }
+    if (out_bf16) {
+      for (int q = 0; q < planes; ++q) {
+        uint4* dst = reinterpret_cast<uint4*>(out_bf16 + ((long long)row * planes + q) * ld + col0);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 u;
+          u.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]); u.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
+          u.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]); u.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+          dst[i] = u;
+          bf16x2_residual(u.x, v[8 * i + 0], v[8 * i + 1]); bf16x2_residual(u.y, v[8 * i + 2], v[8 * i + 3]);
+          bf16x2_residual(u.z, v[8 * i + 4], v[8 * i + 5]); bf16x2_residual(u.w, v[8 * i + 6], v[8 * i + 7]);
+        }
+      }
     }
   }
 };
@@ -264,15 +301,12 @@ template <int BN, class Epi>
 void launch_shift_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Epi& epi, int M, int N, int num_sms, cudaStream_t st) {
   using L = GemmSmem<BN>;
   auto kern = shift_gemm_kernel<BN, Epi>;
-  static bool configured = false;
-  if (!configured) {
-    CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-    configured = true;
-  }
+  static DeviceOnce configured;
+  if (configured.first()) CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
   const int tiles = ((M + BM - 1) / BM) * (N / BN);
   const int grid = tiles < num_sms ? tiles : num_sms;
   kern<<<grid, NUM_THREADS, L::TOTAL, st>>>(tmA, tmB, epi, M, N);
-  ++g_launches;
+  count_launch();
   CUDA_OK(cudaGetLastError());
 }
 

@@ -12,6 +12,10 @@
 // Structure per CTA (192 threads): warp 0 TMA producer, warp 1 MMA issuer (leader only) + TMEM allocator,
 // warps 2..5 epilogue (TMEM -> registers -> swizzled smem staging -> TMA bulk store); 6-stage smem ring (32 KB per
 // stage), 2 TMEM accumulator stages (512 columns).
+//
+// Split-bf16 operands (tc_gemm.cuh "planes"): the K loop runs over `segs.n` K-concatenated products
+// sum_s A[:, plane a_s] * Bop[plane b_s]^T into the SAME TMEM accumulator (signal hi/lo x operator hi/lo), and the
+// epilogue splits the fp32 accumulator into `out_planes` bf16 planes (hi, residual), one TMA store per plane.
 #pragma once
 #include "tc_gemm.cuh"
 
@@ -73,7 +77,7 @@ __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bu
 template <class Epi>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 shift_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                   const __grid_constant__ CUtensorMap tmC, Epi epi, int M, int N) {
+                   const __grid_constant__ CUtensorMap tmC, Epi epi, int M, int N, const ShiftSegs segs, int out_planes) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sOut = smem + G2_STAGES * G2_STAGE_BYTES;                 // [4 warps][2][32 rows][128 B] SW128
@@ -113,13 +117,16 @@ shift_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       for (int tile = pair; tile < num_tiles; tile += npairs) {
         const int m0 = (tile / tiles_n) * 256 + (int)rank * 128;
         const int n0 = (tile % tiles_n) * G2_BN + (int)rank * 128;
-        for (int kb = 0; kb < num_k; ++kb) {
-          mbar_wait(empty_bar + stage, phase ^ 1);
-          uint8_t* sa = smem + stage * G2_STAGE_BYTES;
-          if (rank == 0) mbar_expect_tx(full_bar + stage, 2 * G2_STAGE_BYTES);     // bytes of BOTH CTAs
-          tma_load_2d_pair(sa, &tmA, full_bar + stage, kb * BK, m0);
-          tma_load_2d_pair(sa + G2_HALF_BYTES, &tmB, full_bar + stage, kb * BK, n0);
-          if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
+        for (int sg = 0; sg < segs.n; ++sg) {
+          const int acol = segs.a[sg] * N, brow = segs.b[sg] * N + n0;
+          for (int kb = 0; kb < num_k; ++kb) {
+            mbar_wait(empty_bar + stage, phase ^ 1);
+            uint8_t* sa = smem + stage * G2_STAGE_BYTES;
+            if (rank == 0) mbar_expect_tx(full_bar + stage, 2 * G2_STAGE_BYTES);     // bytes of BOTH CTAs
+            tma_load_2d_pair(sa, &tmA, full_bar + stage, acol + kb * BK, m0);
+            tma_load_2d_pair(sa + G2_HALF_BYTES, &tmB, full_bar + stage, kb * BK, brow);
+            if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
+          }
         }
       }
     }
@@ -133,7 +140,8 @@ shift_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         mbar_wait(tmem_empty + acc, acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * G2_BN);
-        for (int kb = 0; kb < num_k; ++kb) {
+        const int total_k = segs.n * num_k;                 // K-concatenated products share the accumulator
+        for (int kb = 0; kb < total_k; ++kb) {
           mbar_wait(full_bar + stage, phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * G2_STAGE_BYTES);
@@ -173,27 +181,31 @@ shift_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             __syncwarp();
             if (lane == 0) mbar_arrive_leader(tmem_empty + acc);
           }
-          if (lane == 0) tma_store_wait_read<1>();     // the store that last used this staging buffer has read it
-          __syncwarp();
-          uint8_t* dst = stage_out + ob * 4096 + lane * 128;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            __nv_bfloat162 a = __floats2bfloat162_rn(v[8 * j + 0] * epi.scale, v[8 * j + 1] * epi.scale);
-            __nv_bfloat162 b = __floats2bfloat162_rn(v[8 * j + 2] * epi.scale, v[8 * j + 3] * epi.scale);
-            __nv_bfloat162 cc = __floats2bfloat162_rn(v[8 * j + 4] * epi.scale, v[8 * j + 5] * epi.scale);
-            __nv_bfloat162 d = __floats2bfloat162_rn(v[8 * j + 6] * epi.scale, v[8 * j + 7] * epi.scale);
-            uint4 u;
-            u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
-            u.z = *reinterpret_cast<uint32_t*>(&cc); u.w = *reinterpret_cast<uint32_t*>(&d);
-            *reinterpret_cast<uint4*>(dst + ((j ^ (lane & 7)) << 4)) = u;       // 128 B swizzle
+          for (int i = 0; i < 64; ++i) v[i] *= epi.scale;
+          for (int pl = 0; pl < out_planes; ++pl) {    // plane 0 = bf16(v), plane 1 = bf16(v - plane 0)
+            if (lane == 0) tma_store_wait_read<1>();   // the store that last used this staging buffer has read it
+            __syncwarp();
+            uint8_t* dst = stage_out + ob * 4096 + lane * 128;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              uint4 u;
+              u.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]); u.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+              u.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]); u.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+              *reinterpret_cast<uint4*>(dst + ((j ^ (lane & 7)) << 4)) = u;       // 128 B swizzle
+              if (pl + 1 < out_planes) {
+                bf16x2_residual(u.x, v[8 * j + 0], v[8 * j + 1]); bf16x2_residual(u.y, v[8 * j + 2], v[8 * j + 3]);
+                bf16x2_residual(u.z, v[8 * j + 4], v[8 * j + 5]); bf16x2_residual(u.w, v[8 * j + 6], v[8 * j + 7]);
+              }
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&tmC, stage_out + ob * 4096, pl * N + n0 + c * 64, m0 + q * 32);   // rows >= M are clipped by the TMA unit
+              tma_store_commit();
+            }
+            ob ^= 1;
           }
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) {
-            tma_store_2d(&tmC, stage_out + ob * 4096, n0 + c * 64, m0 + q * 32);   // rows >= M are clipped by the TMA unit
-            tma_store_commit();
-          }
-          ob ^= 1;
         }
       } else {
 #pragma unroll 1
@@ -218,18 +230,15 @@ shift_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 
 template <class Epi>
 void launch_shift_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const Epi& epi, int M, int N, int num_sms,
-                        cudaStream_t st) {
+                        const ShiftSegs& segs, int out_planes, cudaStream_t st) {
   auto kern = shift_gemm2_kernel<Epi>;
-  static bool configured = false;
-  if (!configured) {
-    CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM));
-    configured = true;
-  }
+  static DeviceOnce configured;
+  if (configured.first()) CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM));
   const int tiles = ((M + 255) / 256) * (N / G2_BN);
   int pairs = num_sms / 2;
   if (tiles < pairs) pairs = tiles;
-  kern<<<2 * pairs, NUM_THREADS, G2_SMEM, st>>>(tmA, tmB, tmC, epi, M, N);
-  ++g_launches;
+  kern<<<2 * pairs, NUM_THREADS, G2_SMEM, st>>>(tmA, tmB, tmC, epi, M, N, segs, out_planes);
+  count_launch();
   CUDA_OK(cudaGetLastError());
 }
 

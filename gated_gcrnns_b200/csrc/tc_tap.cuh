@@ -18,7 +18,7 @@ namespace gcrnn {
 namespace tc {
 
 constexpr int TAP_BM = 128;        // nodes per tile
-constexpr int TAP_STAGES = 8;      // ring of 64-row stages (16 KB each)
+constexpr int TAP_STAGES = 8;      // ring of 64-row stages (16 KB each); 6 with two operand planes (shared-memory budget)
 constexpr int TAP_STAGE_BYTES = 2 * 64 * 128;
 constexpr int TAP_MAX_KB = 6;      // K*C <= 384 contraction rows
 constexpr int TAP_THREADS = 64 + 16 * 32;   // TMA warp + MMA warp + 16 epilogue warps
@@ -27,6 +27,9 @@ enum { TAP_PLAIN = 0, TAP_FWD = 1, TAP_BWD = 2, TAP_BWDF = 3 };   // BWDF: BWD f
 
 struct TapArgs {
   int K, C, M, N, KB;              // slabs, channels per slab, output features, nodes, ceil(K*C/64)
+  int P;                           // operand planes (1: bf16, 2: split bf16 hi + lo) of slabs, weights and bf16 outputs
+  int stages;                      // stage ring depth (<= TAP_STAGES)
+  int exact;                       // 1: tanh through ex2 + rcp (abs. error ~2e-7) instead of tanh.approx (2^-11)
   long long B, R;                  // samples, rows per slab (B*C)
   // epilogue
   float* out_f32; long long out_bstride;
@@ -67,7 +70,6 @@ __device__ __forceinline__ float tap_tanh(float x) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   uint32_t* r = reinterpret_cast<uint32_t*>(v);
   asm volatile(
@@ -102,9 +104,9 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__
   extern __shared__ uint8_t smem_raw[];
   // 1024 B alignment by OFFSET (not by integer round-trip) so the compiler keeps the shared address space: LDS, not LD
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* sW = smem;                                              // [KB][64 rows][128 B]
-  uint8_t* sA = smem + TAP_MAX_KB * 8192;                          // [STAGES][2 halves][64 rows][128 B]
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sA + TAP_STAGES * TAP_STAGE_BYTES);
+  uint8_t* sW = smem;                                              // [P][KB][64 rows][128 B]
+  uint8_t* sA = smem + a.P * a.KB * 8192;                          // [stages][2 halves][64 rows][128 B]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sA + a.stages * TAP_STAGE_BYTES);
   uint64_t* empty_bar = full_bar + TAP_STAGES;
   uint64_t* tmem_full = empty_bar + TAP_STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -150,13 +152,14 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
-      mbar_expect_tx(w_bar, (uint32_t)(a.KB * a.M * 128));
-      for (int kb = 0; kb < a.KB; ++kb) tma_load_2d(sW + kb * 8192, &tmW, w_bar, kb * 64, 0);
+      mbar_expect_tx(w_bar, (uint32_t)(a.P * a.KB * a.M * 128));
+      for (int kb = 0; kb < a.P * a.KB; ++kb) tma_load_2d(sW + kb * 8192, &tmW, w_bar, kb * 64, 0);   // plane q = blocks [q*KB, (q+1)*KB)
       int stage = 0; uint32_t phase = 0;
       for (long long tile = tile_lo; tile < tile_hi; ++tile) {
         const long long b = tile / tiles_n;
         const int n0 = (int)(tile % tiles_n) * TAP_BM;
-        for (int s = 0; s < a.KB; ++s) {
+        for (int sq = 0; sq < a.KB * a.P; ++sq) {                  // (64-row block s, signal plane q)
+          const int s = sq / a.P, q = sq % a.P;
           const int rows = min(64, KK - 64 * s);
           mbar_wait(empty_bar + stage, phase ^ 1);
           uint8_t* dst = sA + stage * TAP_STAGE_BYTES;
@@ -165,10 +168,10 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__
             const int k = (64 * s + r0) / a.C;
             const CUtensorMap* tm = (k == 0) ? &tm0 : &tmc;
             const int row = (k == 0) ? (int)(b * a.C) : (int)((long long)(k - 1) * a.R + b * a.C);
-            tma_load_2d(dst + r0 * 128, tm, full_bar + stage, n0, row);
-            tma_load_2d(dst + 8192 + r0 * 128, tm, full_bar + stage, n0 + 64, row);
+            tma_load_2d(dst + r0 * 128, tm, full_bar + stage, q * a.N + n0, row);
+            tma_load_2d(dst + 8192 + r0 * 128, tm, full_bar + stage, q * a.N + n0 + 64, row);
           }
-          if (++stage == TAP_STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == a.stages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -184,19 +187,23 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__
         mbar_wait(tmem_empty + acc, acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * acc_stride);
-        for (int s = 0; s < a.KB; ++s) {
+        for (int sq = 0; sq < a.KB * a.P; ++sq) {
+          const int s = sq / a.P, q = sq % a.P;
           const int rows = min(64, KK - 64 * s);
           mbar_wait(full_bar + stage, phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(sA + stage * TAP_STAGE_BYTES);
-          const uint32_t sb = smem_u32(sW + s * 8192);
-          for (int j = 0; j < rows / 16; ++j) {
-            const uint64_t adesc = make_mnmajor_sw128_desc(sa + j * 2048, 8192);   // 16 K-rows = 2048 B
-            const uint64_t bdesc = make_kmajor_sw128_desc(sb) + (uint64_t)(2 * j); // 16 bf16 = 32 B along K
-            umma_f16(d_tmem, adesc, bdesc, idesc, (s | j) != 0);
+          // split operands: z W ~= z0 W0 + z0 W1 + z1 W0 (signal plane q meets weight planes w with q + w < P)
+          for (int w = 0; w + q < a.P; ++w) {
+            const uint32_t sb = smem_u32(sW + (w * a.KB + s) * 8192);
+            for (int j = 0; j < rows / 16; ++j) {
+              const uint64_t adesc = make_mnmajor_sw128_desc(sa + j * 2048, 8192);   // 16 K-rows = 2048 B
+              const uint64_t bdesc = make_kmajor_sw128_desc(sb) + (uint64_t)(2 * j); // 16 bf16 = 32 B along K
+              umma_f16(d_tmem, adesc, bdesc, idesc, (sq | w | j) != 0);
+            }
           }
           umma_commit(empty_bar + stage);
-          if (++stage == TAP_STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == a.stages) { stage = 0; phase ^= 1; }
         }
         umma_commit(tmem_full + acc);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -264,7 +271,8 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__
 #pragma unroll
           for (int i = 0; i < 16; ++i) of[(size_t)i * a.N] = v[i] + a.bias_scale * sBias[m0 + i];
         } else if (EPI == TAP_FWD) {
-          __nv_bfloat16* ob = a.out_bf16 + ((size_t)b * a.M + m0) * a.N + n;
+          const long long ldo = (long long)a.P * a.N;          // bf16 row = P planes of N
+          __nv_bfloat16* ob = a.out_bf16 + ((size_t)b * a.M + m0) * ldo + n;
           const float* aw = sAw + m0 * KG;
           const float gsum = vgi + vgf;
 #pragma unroll
@@ -273,13 +281,15 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__
 #pragma unroll
             for (int kg = 0; kg < KGM; ++kg) if (kg < KG) ax = fmaf(aw[i * KG + kg], z[kg], ax);
             // gi (ax + b) + gf (v + b)
-            const float h = tap_tanh(fmaf(vgi, ax, fmaf(vgf, v[i], gsum * sBias[m0 + i])));
+            const float pre = fmaf(vgi, ax, fmaf(vgf, v[i], gsum * sBias[m0 + i]));
+            const float h = a.exact ? tanh_acc(pre) : tap_tanh(pre);
             of[(size_t)i * a.N] = h;
-            ob[(size_t)i * a.N] = __float2bfloat16(h);
+            store_planes(ob + (size_t)i * ldo, a.N, a.P, h);
           }
         } else if (EPI == TAP_BWDF) {
           float part = 0.f;
-          __nv_bfloat16* ob = a.out_bf16 + ((size_t)b * a.M + m0) * a.N + n;
+          const long long ldo = (long long)a.P * a.N;
+          __nv_bfloat16* ob = a.out_bf16 + ((size_t)b * a.M + m0) * ldo + n;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {                 // 4 features x 8 kinds = 32 per-lane quantities per group
             float x[32];
@@ -288,7 +298,7 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__
               const int i = 4 * j + ii;
               part = fmaf(v[i], hp[i], part);
               const float dp = (dhn[i] + v[i]) * (1.f - hp[i] * hp[i]);
-              ob[(size_t)i * a.N] = __float2bfloat16(vgfn * dp);
+              store_planes(ob + (size_t)i * ldo, a.N, a.P, vgfn * dp);
               x[8 * ii] = dp;
 #pragma unroll
               for (int kg = 0; kg < 7; ++kg) x[8 * ii + 1 + kg] = (kg < KGM && kg < KG) ? dp * z[kg < KGM ? kg : 0] : 0.f;
@@ -389,6 +399,8 @@ __global__ void dpre_finish_kernel(float* __restrict__ red, const float* __restr
 constexpr int WT_STAGES = 4;
 struct WgradTcArgs {
   int K, N; long long B, R;
+  int P;                       // planes of the v slabs (both are summed); h contributes its plane 0 only: rounding noise of h
+                               // is independent across the B*N summands of a weight gradient and averages out
   float* part;                 // [grid][K][64][64]
 };
 __host__ __device__ constexpr int wt_stage_bytes(int K) { return (K + 1) * 8192; }
@@ -428,16 +440,18 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__
       for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const long long b = tile / tiles_n;
         const int n0 = (int)(tile % tiles_n) * 64;
-        mbar_wait(empty_bar + stage, phase ^ 1);
-        uint8_t* dst = smem + stage * stage_bytes;
-        mbar_expect_tx(full_bar + stage, (uint32_t)stage_bytes);
-        for (int k = 0; k < a.K; ++k) {
-          const CUtensorMap* tm = (k == 0) ? &tm0 : &tmc;
-          const int row = (k == 0) ? (int)(b * 64) : (int)((long long)(k - 1) * a.R + b * 64);
-          tma_load_2d(dst + k * 8192, tm, full_bar + stage, n0, row);
+        for (int q = 0; q < a.P; ++q) {
+          mbar_wait(empty_bar + stage, phase ^ 1);
+          uint8_t* dst = smem + stage * stage_bytes;
+          mbar_expect_tx(full_bar + stage, (uint32_t)stage_bytes);
+          for (int k = 0; k < a.K; ++k) {
+            const CUtensorMap* tm = (k == 0) ? &tm0 : &tmc;
+            const int row = (k == 0) ? (int)(b * 64) : (int)((long long)(k - 1) * a.R + b * 64);
+            tma_load_2d(dst + k * 8192, tm, full_bar + stage, q * a.N + n0, row);
+          }
+          tma_load_2d(dst + a.K * 8192, &tmH, full_bar + stage, n0, (int)(b * 64));
+          if (++stage == WT_STAGES) { stage = 0; phase ^= 1; }
         }
-        tma_load_2d(dst + a.K * 8192, &tmH, full_bar + stage, n0, (int)(b * 64));
-        if (++stage == WT_STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -446,19 +460,21 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__
       int stage = 0; uint32_t phase = 0;
       bool first = true;
       for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        mbar_wait(full_bar + stage, phase);
-        tc_fence_after();
-        const uint32_t sa = smem_u32(smem + stage * stage_bytes);
-        const uint64_t bdesc = make_kmajor_sw128_desc(sa + a.K * 8192);
-        for (int p = 0; p < NP; ++p) {
-          const uint64_t adesc = make_kmajor_sw128_desc(sa + p * 16384);
+        for (int q = 0; q < a.P; ++q) {
+          mbar_wait(full_bar + stage, phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * stage_bytes);
+          const uint64_t bdesc = make_kmajor_sw128_desc(sa + a.K * 8192);
+          for (int p = 0; p < NP; ++p) {
+            const uint64_t adesc = make_kmajor_sw128_desc(sa + p * 16384);
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            umma_f16(tmem_base + (uint32_t)(p * 64), adesc + (uint64_t)(2 * j), bdesc + (uint64_t)(2 * j), idesc, !(first && j == 0));
+            for (int j = 0; j < 4; ++j)
+              umma_f16(tmem_base + (uint32_t)(p * 64), adesc + (uint64_t)(2 * j), bdesc + (uint64_t)(2 * j), idesc, !(first && j == 0));
+          }
+          first = false;
+          umma_commit(empty_bar + stage);
+          if (++stage == WT_STAGES) { stage = 0; phase ^= 1; }
         }
-        first = false;
-        umma_commit(empty_bar + stage);
-        if (++stage == WT_STAGES) { stage = 0; phase ^= 1; }
       }
       umma_commit(done_bar);
     }
@@ -492,7 +508,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, tmem_cols); }
 }
 
-constexpr int TAP_SMEM = TAP_MAX_KB * 8192 + TAP_STAGES * TAP_STAGE_BYTES + 256 + (64 * 32 + 64) * 4 + 32 * 8 + 1024;
+// dynamic shared memory of tap_gemm_kernel: P weight planes of KB blocks + the stage ring + barriers / taps / bias / pointers
+inline int tap_smem_bytes(int P, int KB, int stages) {
+  return P * KB * 8192 + stages * TAP_STAGE_BYTES + 256 + (64 * 32 + 64) * 4 + 32 * 8 + 1024;
+}
 
 }  // namespace tc
 }  // namespace gcrnn

@@ -14,15 +14,21 @@ import torch
 from . import _lib
 from . import graph as _graph
 from . import dist as _dist
+from . import options as _options
 
-_precision = 'fp32'     # 'fp32' | 'bf16' | 'auto'
+_precision = 'fp32'     # 'fp32' | 'bf16x2' | 'bf16' | 'auto'
+PRECISIONS = ('fp32', 'bf16x2', 'bf16', 'auto')
 
 
 def set_precision(mode: str):
-    """'fp32': exact CUDA-core path everywhere.  'bf16': dense tcgen05 path for cells that support it.
-    'auto': bf16 tensor-core path for large dense graphs without spatial gating, fp32 otherwise."""
+    """'fp32'  : exact CUDA-core path everywhere (sparse shift).
+    'bf16x2': dense tcgen05 path with every operand split into bf16 hi + lo planes (16-bit mantissa, fp32 accumulate):
+              the tensor-core mode with a tight bound; raises for cells it does not support.
+    'bf16'  : dense tcgen05 path with plain bf16 operands (8-bit mantissa): fastest, short horizons / contractive
+              recurrences only; raises for cells it does not support.
+    'auto'  : 'bf16x2' for every cell whose shape the tensor-core kernels take, 'fp32' otherwise.  Never plain bf16."""
     global _precision
-    assert mode in ('fp32', 'bf16', 'auto')
+    assert mode in PRECISIONS
     _precision = mode
 
 
@@ -206,7 +212,17 @@ class CellHandle:
         self.handle = out.value
         self.slots = cell_param_slots(time_gating, spatial_gating, bias)
         self.F, self.G, self.N = F, G, g.N
+        self._opt_version = -1
         self._fin = weakref.finalize(self, _destroy_cell, self.handle)
+        self.sync_options()
+
+    def sync_options(self):
+        """Apply the host-side switch table (gated_gcrnns_b200.options) to this handle if it changed."""
+        v = _options.version()
+        if v != self._opt_version:
+            for name, value in _options.items():
+                self.set_option(name, value)
+            self._opt_version = v
 
     @property
     def ptr(self):
@@ -244,6 +260,7 @@ class _CellFn(torch.autograd.Function):
         H = torch.empty(B, T, cell.F, cell.N, dtype=torch.float32, device=dev)
         # execution-path selection (fp32 sparse precision): tell the library whether backward will want dX, let it choose,
         # and remember the choice so that backward runs on the path whose saved state this forward wrote
+        cell.sync_options()
         cell.set_option('path', -1)
         cell.set_option('need_dx', int(ctx.needs_input_grad[1]))
         sb, fb, _ = cell.workspace(B, T, False)
@@ -276,6 +293,7 @@ class _CellFn(torch.autograd.Function):
         pst = _fill_struct(cell.slots, p32)
         dX = torch.empty_like(X32) if need_x else None
         dh0 = torch.empty_like(h32) if need_h else None
+        cell.sync_options()
         cell.set_option('path', ctx.path)
         _, _, bb = cell.workspace(B, T, need_x or need_h)
         ws = _bytes(bb, dev)
@@ -283,7 +301,7 @@ class _CellFn(torch.autograd.Function):
                                                   _ptr(saved), saved.numel(), C.byref(gst), _ptr(dX), _ptr(dh0), _ptr(ws),
                                                   ws.numel(), B, T, _stream(dev)), 'cell_backward')
         cell.set_option('path', -1)
-        _dist.allreduce_bucket(bucket)
+        _dist.reduce_cell_bucket(bucket)          # only in dist.enable(reduce_in_backward=True) mode: cell parameters only, SUM
         grads = [v.reshape(s).to(d) for v, s, d in zip(views, pshapes, pds)]
         return (None, dX.to(xd) if need_x else None, dh0.to(hd) if need_h else None, *grads)
 

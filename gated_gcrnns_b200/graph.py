@@ -28,6 +28,10 @@ class Graph:
     def ptr(self):
         return C.c_void_p(self.handle)
 
+    def set_option(self, name: str, value: int):
+        """Tuning switch for calls made on the graph handle itself (the debug shift GEMM)."""
+        _lib.check(_lib.lib().gcrnn_graph_set_option(self.ptr, name.encode(), int(value)), 'graph_set_option')
+
     def info(self):
         n, e, nnz, na = C.c_int32(), C.c_int32(), C.c_int64(), C.c_int64()
         _lib.check(_lib.lib().gcrnn_graph_info(self.ptr, C.byref(n), C.byref(e), C.byref(nnz), C.byref(na)), 'graph_info')
@@ -108,8 +112,6 @@ def get(S: torch.Tensor, device, keep_dense=False) -> Graph:
     if hit is not None and hit[0]() is S:
         return hit[1]
     g = from_dense(S, device, keep_dense) if S.layout == torch.strided else from_sparse_tensor(S, device)
-    if len(_cache) > 64:
-        for k in [k for k, v in _cache.items() if v[0]() is None]:
-            del _cache[k]
-    _cache[key] = (weakref.ref(S), g)
+    # the entry (and with it the device copies of the operator) goes away as soon as the GSO tensor dies
+    _cache[key] = (weakref.ref(S, lambda _ref, key=key: _cache.pop(key, None)), g)
     return g

@@ -183,29 +183,57 @@ class GGCRNNCell(nn.Module):
                     setattr(self, f'{g}_attention', att)
 
     # -- the fused path ------------------------------------------------------------------------------------
-    def _precision_for(self, device):
+    def _tc_unsupported(self, split: bool, need_dx: bool):
+        """Why the dense tensor-core kernels cannot take this cell (None if they can).  Mirrors EVERY check of the
+        library's tensor-core path (csrc/gcrnn_tc.cu: tc_dims, launch_tap, cell_backward_tc) so that 'auto' never
+        picks a path that raises later."""
+        if self.S.layout != torch.strided:
+            return 'the GSO is sparse (dense [E,N,N] tensor needed)'
+        if self.E != 1:
+            return f'E={self.E} (E == 1 needed)'
+        if self.spatial_gating is not None:
+            return f'spatial_gating={self.spatial_gating!r} (time gating or none)'
+        if self.N % (256 if split else 128) != 0:
+            return f'N={self.N} (N % {256 if split else 128} == 0 needed)'
+        if self.F not in (16, 32, 64):
+            return f'F={self.F} (F in 16, 32, 64)'
+        if self.Kin * self.G > 32:
+            return f'Kin*G={self.Kin * self.G} (<= 32)'
+        if not 1 <= self.Kst <= 5 or self.Kst * self.F > 384:
+            return f'Kst={self.Kst} (<= 5)'
+        if need_dx:
+            return 'X requires grad (the tensor-core backward does not produce dX)'
+        return None
+
+    def _precision_for(self, device, need_dx=False):
         mode = Fn.get_precision()
-        dense_ok = (self.S.layout == torch.strided and self.E == 1 and self.spatial_gating is None
-                    and self.N % 128 == 0)
-        if mode == 'bf16':
-            if not dense_ok:
-                raise _lib.GcrnnError('bf16 tensor-core path needs a dense GSO with E=1, N % 128 == 0 and no spatial gating')
-            return _lib.PREC_BF16_TC
-        if mode == 'auto' and dense_ok and self.N >= 256:
-            return _lib.PREC_BF16_TC
+        if mode in ('bf16', 'bf16x2'):
+            why = self._tc_unsupported(mode == 'bf16x2', need_dx)
+            if why is not None:
+                raise _lib.GcrnnError(f"precision {mode!r}: the tensor-core path does not take this cell: {why}")
+            return _lib.PREC_BF16_TC if mode == 'bf16' else _lib.PREC_BF16X2_TC
+        if mode == 'auto' and self.N >= 256 and self._tc_unsupported(True, need_dx) is None:
+            return _lib.PREC_BF16X2_TC          # never plain bf16: 'auto' must not silently loosen the numerics
         return _lib.PREC_FP32
 
-    def _handle(self, device):
-        prec = self._precision_for(device)
+    def _handle(self, device, need_dx=False):
+        prec = self._precision_for(device, need_dx)
         key = (torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device(), prec)
         h = self._handles.get(key)
         if h is None:
-            g = _graph.get(self.S, device, keep_dense=(prec == _lib.PREC_BF16_TC))
+            g = _graph.get(self.S, device, keep_dense=(prec != _lib.PREC_FP32))
             sg = self.spatial_gating if self.spatial_gating in ('node', 'edge') else None
             h = Fn.CellHandle(g, self.G, self.F, self.Kin, self.Kst, self.E, self.time_gating == True, sg,  # noqa: E712
                               self.bias_flag, prec)
             self._handles[key] = h
         return h
+
+    # handles wrap raw C pointers owned by a finalizer: never copy or pickle them (copy.deepcopy(model) / torch.save(model)
+    # are how the reference snapshots its best model); they are rebuilt lazily on the next forward
+    def __getstate__(self):
+        st = self.__dict__.copy()
+        st['_handles'] = {}
+        return st
 
     def _used_parameters(self, slots):
         sd = dict(self.named_parameters())
@@ -224,7 +252,7 @@ class GGCRNNCell(nn.Module):
         assert h0.shape[1] == self.F and h0.shape[2] == self.N
         if h0.device != X.device:                      # train_rnn.py:256 builds h0 on the CPU
             h0 = h0.to(X.device)
-        cell = self._handle(X.device)
+        cell = self._handle(X.device, need_dx=bool(X.requires_grad and torch.is_grad_enabled()))
         return Fn.gated_gcrnn(cell, X, h0, self._used_parameters(cell.slots))
 
     def extra_repr(self):

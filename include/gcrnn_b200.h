@@ -31,14 +31,16 @@
 extern "C" {
 #endif
 
-#define GCRNN_ABI_VERSION 1
+#define GCRNN_ABI_VERSION 2
 
 typedef struct gcrnn_graph gcrnn_graph;   /* shift operator S (E edge features, N nodes) on one device */
 typedef struct gcrnn_cell  gcrnn_cell;    /* one GGCRNNCell configuration bound to a graph            */
 
 enum { GCRNN_SPATIAL_NONE = 0, GCRNN_SPATIAL_NODE = 1, GCRNN_SPATIAL_EDGE = 2 };
-enum { GCRNN_PREC_FP32 = 0,      /* CUDA-core fp32 everywhere, sparse (CSR) shift — exact path           */
-       GCRNN_PREC_BF16_TC = 1 }; /* dense shift on tcgen05 tensor cores, bf16 operands, fp32 accumulate   */
+enum { GCRNN_PREC_FP32 = 0,        /* CUDA-core fp32 everywhere, sparse (CSR) shift — exact path                                  */
+       GCRNN_PREC_BF16_TC = 1,     /* dense shift on tcgen05 tensor cores, bf16 operands (8-bit mantissa), fp32 accumulate         */
+       GCRNN_PREC_BF16X2_TC = 2 }; /* same kernels, every operand split into bf16 hi + lo planes (16-bit mantissa), products as    *
+                                    * K-concatenated MMAs x0 y0 + x1 y0 + x0 y1 into one fp32 accumulator; accurate tanh          */
 
 /* GGCRNNCell(G, F, Kin, Kst, sigma=tanh, time_gating, spatial_gating, E, bias)  graphML.py:2196 */
 typedef struct {
@@ -61,26 +63,34 @@ typedef struct {
   float *e_mixer[2], *e_weight[2];                  /* input_attention / forget_attention: [2F], [F,F]     */
 } gcrnn_cell_params;
 
+/* the library is built with -fvisibility=hidden: only the functions declared here are exported (no data symbols) */
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
 int         gcrnn_abi_version(void);
 const char* gcrnn_last_error(void);
 /* number of CUDA kernels this library has launched in this process (bench.py's `gpu_launches`) */
 uint64_t    gcrnn_debug_launch_count(void);
 /* the dominant kernel on its own (unit tests, roofline timing): out = A @ S (backward=0) or A @ S^T (backward=1),
- * A: device bf16 [M, N] row-major; out_bf16 / out_f32: device [M, N], either may be NULL.  Needs keep_dense. */
-int         gcrnn_debug_shift_gemm(const gcrnn_graph* g, int32_t backward, const void* A_bf16, int64_t M,
-                                   void* out_bf16, float* out_f32, void* stream);
+ * A: device bf16 [M, planes_in * N] row-major (plane q of row r at columns [q*N, (q+1)*N): plane 0 = bf16(x), plane 1 = bf16 of the
+ * rounding residual); out_bf16: device [M, planes_out * N], out_f32: device [M, N]; either may be NULL.  Needs keep_dense. */
+int         gcrnn_debug_shift_gemm(const gcrnn_graph* g, int32_t backward, const void* A_bf16, int64_t M, int32_t planes_in,
+                                   void* out_bf16, int32_t planes_out, float* out_f32, void* stream);
 
-/* tuning switches for tests and A/B measurements (process-wide): name = "gemm_pair" (1: CTA-pair cta_group::2 shift
- * GEMM when the shape allows, 0: single-CTA kernel), "bwd_fused" (fused reverse-time step kernel of the tensor-core path),
- * "sparse_fused" (fused F == 32 edge-gated kernels of the sparse fp32 path; 0 = the generic per-op kernels),
- * "graph_capture" (small fp32 cell calls are captured once per pointer set into a CUDA graph and replayed; 0 = direct launches),
- * "gate_fq8" (time-gate kernels with 8 feature groups per CTA: 0 off, 1 forward, 2 forward + backward), and for the fused
- * sparse kernels "sparse_v2" (bit mask of the stages that run their second-generation kernel: 1 shift, 2 gather-contract,
- * 4|8 aggregate + bwd_rows, 16 bwd_node, 32 dh; 0 = all first generation), "sparse_v2_tc" (tile contractions: 1 = 3xTF32
- * mma.sync, 0 = packed FFMA2), "sparse_v2_fuse_dpre", "sparse_v2_bps", "sparse_v2_rows_bps".  A backward always follows the
- * stage generations its forward used; every call invalidates captured CUDA graphs.
- * Returns the previous value, or -1 for an unknown name. */
-int         gcrnn_debug_set_option(const char* name, int32_t value);
+/* Tuning switches for tests and A/B measurements live on the HANDLE (the library keeps no process-wide mutable state):
+ * gcrnn_cell_set_option(cell, name, value) / gcrnn_graph_set_option(graph, name, value) with name =
+ *   "gemm_pair"     1: CTA-pair cta_group::2 shift GEMM when the shape allows, 0: single-CTA kernel  (cell and graph handles)
+ *   "bwd_fused"     fused reverse-time step kernel of the tensor-core path
+ *   "sparse_fused"  fused F == 32 edge-gated kernels of the sparse fp32 path; 0 = the generic per-op kernels
+ *   "graph_capture" small fp32 cell calls are captured once per pointer set into a CUDA graph and replayed; 0 = direct launches
+ *   "gate_fq8"      time-gate kernels with 8 feature groups per CTA: 0 off, 1 forward, 2 forward + backward
+ *   "sparse_v2"     bit mask of the fused sparse stages that run their second-generation kernel: 1 shift, 2 gather-contract,
+ *                   4|8 aggregate + bwd_rows, 16 bwd_node, 32 dh; 0 = all first generation
+ *   "sparse_v2_tc"  tile contractions: 1 = 3xTF32 mma.sync, 0 = packed FFMA2;  "sparse_v2_fuse_dpre", "sparse_v2_bps",
+ *                   "sparse_v2_rows_bps"
+ * A backward always follows the stage generations its forward used; every change invalidates the handle's captured CUDA graphs. */
+int         gcrnn_graph_set_option(gcrnn_graph* g, const char* name, int32_t value);
 
 /* ---- graph -------------------------------------------------------------------------------------- */
 /* E operators in CSR, HOST arrays: rowptr[e] has N+1 entries, entry (i, colidx[p]) = S_e[i, j] = vals[p].
@@ -122,7 +132,7 @@ int gcrnn_cell_destroy(gcrnn_cell* c);
  *   GENERIC  per-op kernels, any shape / gating mode, supports dX;
  *   NODE32   fused edge-gated kernels for F == 32, one warp per (sample, node) (csrc/sp32_kernels.cuh); a dX request makes
  *            backward run the generic sweep on the generic prefix of the saved state.
- * Options (per cell handle, used from one host thread at a time):
+ * Options (per cell handle, used from one host thread at a time; the tuning switches listed above are set the same way):
  *   "path"      (set)  -1 = automatic (default), otherwise force GCRNN_PATH_* — the autograd glue forces backward onto the path
  *                      its forward took;
  *   "need_dx"   (set)  hint for the next forward: backward will be asked for dX (reserved for paths that cannot serve it);
@@ -150,6 +160,10 @@ int gcrnn_comm_unique_id(void* id128 /* 128 bytes out */);
 int gcrnn_comm_create(gcrnn_comm** out, const void* id128, int32_t rank, int32_t world, int32_t device);
 int gcrnn_comm_destroy(gcrnn_comm* c);
 int gcrnn_allreduce_sum(gcrnn_comm* c, float* bucket, int64_t count, void* stream);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
 
 #ifdef __cplusplus
 }

@@ -25,7 +25,7 @@ def test_header_symbols_exported():
 
 def test_loads_and_reports_version():
     L = _lib.lib()
-    assert L.gcrnn_abi_version() == 1
+    assert L.gcrnn_abi_version() == 2
     assert isinstance(L.gcrnn_last_error(), bytes)
 
 
@@ -40,3 +40,30 @@ def test_workspace_query_is_pure_host_arithmetic():
     L = _lib.lib()
     rc = L.gcrnn_graph_info(None, None, None, None, None)
     assert rc != 0 and b'null graph' in L.gcrnn_last_error()
+
+
+def test_no_exported_mutable_globals():
+    """The library keeps no process-wide mutable state that a caller could reach: the dynamic symbol table holds functions
+    only (built with -fvisibility=hidden; tuning switches live on the handles, the launch counter is an internal atomic)."""
+    import subprocess
+    out = subprocess.run(['nm', '-D', '--defined-only', _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    data = [l for l in out.splitlines() if len(l.split()) >= 3 and l.split()[1] in 'BbDdGgSsCcVvRr']
+    assert not data, data
+    exported = sorted(l.split()[2] for l in out.splitlines() if len(l.split()) >= 3 and l.split()[1] == 'T')
+    assert exported == _declared(), set(exported) ^ set(_declared())
+
+
+def test_options_live_on_handles():
+    """Unknown option names are rejected by the handle entry points (NULL handle -> error code, not a crash)."""
+    L = _lib.lib()
+    assert L.gcrnn_cell_set_option(None, b'bwd_fused', 0) != 0
+    assert L.gcrnn_graph_set_option(None, b'gemm_pair', 0) != 0
+    assert not hasattr(L, 'gcrnn_debug_set_option')
+    import gated_gcrnns_b200 as gg
+    old = gg.options.set('bwd_fused', 0)
+    assert old == 1 and gg.options.get('bwd_fused') == 0
+    gg.options.reset()
+    assert gg.options.get('bwd_fused') == 1
+    import pytest
+    with pytest.raises(KeyError):
+        gg.options.set('no_such_switch', 1)

@@ -81,3 +81,71 @@ def test_two_rank_gradient_sum_equals_full_batch():
     for n, v in zip(names, parts):
         if g[n] is None:
             assert float(v.abs().max()) == 0.0
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# whole-model reduction: attach(model, 'mean') / allreduce_gradients reduce EVERY parameter once per backward
+# (the cell's own in-backward all-reduce covers the cell's parameters only)
+# ---------------------------------------------------------------------------------------------------------------
+def _model_and_data():
+    torch.manual_seed(1)
+    model = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 2))
+    unused = torch.nn.Linear(3, 3)                     # registered but never used in forward: its .grad stays None
+    model.add_module('never_used', unused)
+    X, Y = torch.randn(10, 6), torch.randn(10, 2)
+    return model, X, Y
+
+
+def _fwd(model, x):
+    return model[2](model[1](model[0](x)))
+
+
+def _attach_worker(rank, world, port, q, mode):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        model, X, Y = _model_and_data()
+        lo, hi = gdist.shard_range(X.shape[0], rank, world)       # 5 + 5
+        gdist.enable()
+        n0 = gdist.launches
+        if mode == 'attach':
+            att = gdist.attach(model, op='mean')
+            for _ in range(2):                                     # two steps: the hook re-arms after every backward
+                model.zero_grad()
+                torch.nn.functional.mse_loss(_fwd(model, X[lo:hi]), Y[lo:hi]).backward()
+            att.detach()
+            used = gdist.launches - n0
+        else:
+            model.zero_grad()
+            for a, b in ((lo, lo + 2), (lo + 2, hi)):              # gradient accumulation over two micro-batches
+                (torch.nn.functional.mse_loss(_fwd(model, X[a:b]), Y[a:b], reduction='sum') / (X.shape[0] * Y.shape[1])).backward()
+            gdist.allreduce_gradients(model.parameters(), op='sum')
+            used = gdist.launches - n0
+        gdist.disable()
+        if rank == 0:
+            q.put(([None if p.grad is None else p.grad.clone() for p in model.parameters()], used))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize('mode', ['attach', 'explicit'])
+def test_whole_model_gradients_match_single_process(mode):
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_attach_worker, args=(r, 2, port, q, mode)) for r in range(2)]
+    for pr in procs:
+        pr.start()
+    grads, used = q.get(timeout=240)
+    for pr in procs:
+        pr.join(timeout=60)
+        assert pr.exitcode == 0
+    model, X, Y = _model_and_data()
+    torch.nn.functional.mse_loss(_fwd(model, X), Y).backward()     # single process, whole batch, mean loss
+    assert used == (2 if mode == 'attach' else 1)                  # ONE collective per backward / per step
+    for g, p in zip(grads, model.parameters()):
+        if p.grad is None:
+            assert g is None                                       # never-used parameters keep None, as in the reference
+        else:
+            assert torch.allclose(g, p.grad, rtol=1e-5, atol=1e-7)

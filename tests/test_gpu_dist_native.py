@@ -1,7 +1,7 @@
 """GPU: the library's own NCCL transport (gcrnn_comm_* / gcrnn_allreduce_sum, resolved from the process's libnccl) on a
-single-rank communicator, and the in-backward gradient all-reduce of the cell (identity at world size 1, but it runs the
+single-rank communicator, and the opt-in in-backward gradient all-reduce of the cell (identity at world size 1, but it runs the
 whole path: unique id -> ncclCommInitRank -> ncclAllReduce on the backward stream).  The 2-rank arithmetic is covered on
-CPU by tests/test_dist_gloo.py and on 2-8 B200s by bench.py (profiles/r01_bench_n*_s*.json)."""
+CPU by tests/test_dist_gloo.py and on 2 GPUs by tests/test_gpu_dist2.py (skipped on a 1-GPU box); bench.py prints `grad_check`."""
 import os
 
 import pytest
@@ -22,7 +22,7 @@ def test_native_allreduce_single_rank_and_cell_hook():
     if created:
         dist.init_process_group('nccl', rank=0, world_size=1, device_id=torch.device(DEV))
     try:
-        gg.dist.enable(native=True, device=0)
+        gg.dist.enable(native=True, device=0, reduce_in_backward=True)
         b = torch.arange(1000, dtype=torch.float32, device=DEV)
         out = gg.dist.allreduce_bucket(b.clone())
         torch.cuda.synchronize()

@@ -181,16 +181,16 @@ def test_graph_replay_matches_direct_launches():
         torch.cuda.synchronize()
         return H.detach().clone(), cell.weight_B.grad.clone(), L.gcrnn_debug_launch_count() - l0
 
-    old = L.gcrnn_debug_set_option(b'graph_capture', 0)
+    old = gg.options.set('graph_capture', 0)
     try:
         Hd, gd, ld = run(X)
         Hd2, gd2, _ = run(2 * X)
     finally:
-        L.gcrnn_debug_set_option(b'graph_capture', old)
-    assert L.gcrnn_debug_set_option(b'graph_capture', 1) in (0, 1)
+        gg.options.set('graph_capture', old)
+    assert gg.options.set('graph_capture', 1) in (0, 1)
     outs = [run(X), run(2 * X), run(X), run(X)]
     assert all(o[2] == ld for o in outs), [o[2] for o in outs]
     assert torch.equal(outs[0][0], Hd) and torch.equal(outs[2][0], Hd) and torch.equal(outs[3][0], Hd)
     assert torch.equal(outs[1][0], Hd2)
     assert relerr(outs[3][1], gd) < 1e-6 and relerr(outs[1][1], gd2) < 1e-6      # float atomics: order may differ in the last bits
-    L.gcrnn_debug_set_option(b'graph_capture', old)
+    gg.options.set('graph_capture', old)

@@ -102,14 +102,14 @@ def test_fused_stage_generations_vs_oracle(mask):
     holds each stage's second-generation kernel ALONE (bits: 1 spmm, 2 filter, 4 + 8 aggregate and bwd_rows - they share the saved softmax statistics -, 16 bwd_node, 32 dh) and the
     all-first-generation path (0) to the same oracle bounds, on a graph whose N is not a multiple of the tile size."""
     L = _lib.lib()
-    old = L.gcrnn_debug_set_option(b'sparse_v2', mask)
+    old = gg.options.set('sparse_v2', mask)
     try:
         run_case(N=203, G_=2, Kin=3, Kst=3, T=4, B=3, bias=True, seed=21, expect_path=PATH_NODE32)
         if mask in (2, 16, 32):
             run_case(N=97, G_=1, Kin=2, Kst=4, T=3, B=2, bias=True, seed=22, expect_path=PATH_NODE32)
             run_case(N=131, G_=3, Kin=4, Kst=2, T=3, B=2, bias=False, seed=23, expect_path=PATH_NODE32)
     finally:
-        L.gcrnn_debug_set_option(b'sparse_v2', old)
+        gg.options.set('sparse_v2', old)
 
 
 @pytest.mark.parametrize('tc,bps', [(1, 1), (1, 2), (0, 1), (0, 2)])
@@ -118,15 +118,15 @@ def test_fused_tile_kernels_contraction_modes(tc, bps):
     fp32 FFMA2, at any number of resident blocks per SM (grid size / shared-memory carve-out): both hold the fp32 path's bounds
     (1e-5 on H, 1e-4 on gradients vs the fp64 oracle) for every supported tap count."""
     L = _lib.lib()
-    old_bps = L.gcrnn_debug_set_option(b'sparse_v2_bps', bps)
-    old_tc = L.gcrnn_debug_set_option(b'sparse_v2_tc', tc)
+    old_bps = gg.options.set('sparse_v2_bps', bps)
+    old_tc = gg.options.set('sparse_v2_tc', tc)
     try:
         run_case(N=300, G_=1, Kin=3, Kst=3, T=3, B=2, bias=True, seed=31, expect_path=PATH_NODE32)
         run_case(N=200, G_=2, Kin=2, Kst=4, T=2, B=2, bias=True, seed=32, expect_path=PATH_NODE32)
         run_case(N=170, G_=4, Kin=4, Kst=2, T=2, B=2, bias=True, seed=33, expect_path=PATH_NODE32)
     finally:
-        L.gcrnn_debug_set_option(b'sparse_v2_bps', old_bps)
-        L.gcrnn_debug_set_option(b'sparse_v2_tc', old_tc)
+        gg.options.set('sparse_v2_bps', old_bps)
+        gg.options.set('sparse_v2_tc', old_tc)
 
 
 def test_fused_dpre_epilogue_matches_separate_kernel():
@@ -134,11 +134,11 @@ def test_fused_dpre_epilogue_matches_separate_kernel():
     option off a separate dpre_k runs from a stored dh.  Same oracle bounds either way, and the two agree to rounding."""
     L = _lib.lib()
     _, H1, g1 = run_case(N=260, G_=1, Kin=3, Kst=3, T=6, B=3, bias=True, seed=41, expect_path=PATH_NODE32)
-    old = L.gcrnn_debug_set_option(b'sparse_v2_fuse_dpre', 0)
+    old = gg.options.set('sparse_v2_fuse_dpre', 0)
     try:
         _, H0, g0 = run_case(N=260, G_=1, Kin=3, Kst=3, T=6, B=3, bias=True, seed=41, expect_path=PATH_NODE32)
     finally:
-        L.gcrnn_debug_set_option(b'sparse_v2_fuse_dpre', old)
+        gg.options.set('sparse_v2_fuse_dpre', old)
     assert torch.equal(H0, H1)
     for k in g0:
         assert relerr(g1[k], g0[k]) < 1e-5, k
@@ -146,11 +146,11 @@ def test_fused_dpre_epilogue_matches_separate_kernel():
 
 def test_fused_matches_generic_kernels_and_falls_back_for_dX():
     L = _lib.lib()
-    old = L.gcrnn_debug_set_option(b'sparse_fused', 0)
+    old = gg.options.set('sparse_fused', 0)
     try:
         lg, Hg, gg_ = run_case(N=130, G_=1, Kin=3, Kst=3, T=4, B=2, bias=True, seed=5, expect_path=PATH_GENERIC)
     finally:
-        L.gcrnn_debug_set_option(b'sparse_fused', old)
+        gg.options.set('sparse_fused', old)
     lf, Hf, gf = run_case(N=130, G_=1, Kin=3, Kst=3, T=4, B=2, bias=True, seed=5)
     assert lf < lg
     assert relerr(Hf, Hg) < 2e-6

@@ -12,20 +12,30 @@ pytestmark = pytest.mark.gpu
 DEV = 'cuda:0'
 
 
-def _gemm(g, A_bf16, backward, want_f32=True, want_bf16=True):
-    M, N = A_bf16.shape
-    ob = torch.empty(M, N, dtype=torch.bfloat16, device=DEV) if want_bf16 else None
+def _gemm(g, A, backward, planes_in=1, planes_out=1, want_f32=True, want_bf16=True):
+    """A: bf16 [M, planes_in * N].  Returns (bf16 [M, planes_out * N], fp32 [M, N])."""
+    M, N = A.shape[0], A.shape[1] // planes_in
+    ob = torch.empty(M, planes_out * N, dtype=torch.bfloat16, device=DEV) if want_bf16 else None
     of = torch.empty(M, N, dtype=torch.float32, device=DEV) if want_f32 else None
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-    _lib.check(_lib.lib().gcrnn_debug_shift_gemm(g.ptr, int(backward), C.c_void_p(A_bf16.data_ptr()), M,
-                                                 C.c_void_p(ob.data_ptr() if ob is not None else 0),
+    _lib.check(_lib.lib().gcrnn_debug_shift_gemm(g.ptr, int(backward), C.c_void_p(A.data_ptr()), M, planes_in,
+                                                 C.c_void_p(ob.data_ptr() if ob is not None else 0), planes_out,
                                                  C.c_void_p(of.data_ptr() if of is not None else 0), st), 'debug_shift_gemm')
     torch.cuda.synchronize()
     return ob, of
 
 
 def _set_opt(name, value):
-    return _lib.lib().gcrnn_debug_set_option(name.encode(), int(value))
+    return gg.options.set(name, int(value))
+
+
+def _planes(x, P):
+    """fp32 [M, N] -> bf16 [M, P*N]: plane 0 = bf16(x), plane 1 = bf16(x - plane 0)."""
+    hi = x.to(torch.bfloat16)
+    if P == 1:
+        return hi.contiguous()
+    lo = (x - hi.float()).to(torch.bfloat16)
+    return torch.cat([hi, lo], dim=1).contiguous()
 
 
 @pytest.mark.parametrize('pair', [0, 1])
@@ -37,33 +47,60 @@ def test_shift_gemm_matches_torch(N, M, pair):
     torch.manual_seed(N + M)
     S = torch.randn(N, N) * (torch.rand(N, N) < 0.3) / 16
     g = ggraph.from_dense(S.reshape(1, N, N), DEV, keep_dense=True)
+    g.set_option('gemm_pair', pair)            # 1: CTA-pair (cta_group::2) kernel where the shape allows it
     mx = S.abs().max()
     S = (S / mx).to(torch.bfloat16).float() * mx
     A = torch.randn(M, N, device=DEV).to(torch.bfloat16)
-    old = _set_opt('gemm_pair', pair)          # 1: CTA-pair (cta_group::2) kernel where the shape allows it
-    try:
-        for backward in (False, True):
-            ob, of = _gemm(g, A, backward)
-            Sd = S.to(DEV)
-            ref = A.float() @ (Sd.t() if backward else Sd)
-            scale = ref.abs().max().item()
-            assert (of - ref).abs().max().item() / scale < 1e-5, (N, M, backward)
-            assert (ob.float() - ref).abs().max().item() / scale < 2 ** -8
-    finally:
-        _set_opt('gemm_pair', old)
+    for backward in (False, True):
+        ob, of = _gemm(g, A, backward)
+        Sd = S.to(DEV)
+        ref = A.float() @ (Sd.t() if backward else Sd)
+        scale = ref.abs().max().item()
+        assert (of - ref).abs().max().item() / scale < 1e-5, (N, M, backward)
+        assert (ob.float() - ref).abs().max().item() / scale < 2 ** -8
+
+
+@pytest.mark.parametrize('weighted', [False, True])
+@pytest.mark.parametrize('N,M', [(256, 64), (256, 300), (1024, 128 * 5 + 17), (512, 4096), (1024, 256 * 75 + 130)])
+def test_shift_gemm_split_planes(N, M, weighted):
+    """Split-bf16 operands: A = hi + lo planes, operator = hi (+ lo for a weighted graph) planes, products K-concatenated into
+    one fp32 accumulator.  The fp32 output must match an fp64 product of the fp32 signal with the fp32 operator to 2^-15 of
+    max|ref| (the dropped lo x lo term and the 16-bit split of each operand), the two output planes must reconstruct it to
+    2^-15 as well; with a single signal plane the same call reproduces the plain bf16 result."""
+    torch.manual_seed(N + M + int(weighted))
+    mask = (torch.rand(N, N) < 0.3).float()
+    S = (mask * torch.rand(N, N) if weighted else mask) / 40
+    g = ggraph.from_dense(S.reshape(1, N, N), DEV, keep_dense=True)
+    X = torch.randn(M, N, device=DEV)
+    A2 = _planes(X, 2)
+    Sd = S.to(DEV).double()
+    for backward in (False, True):
+        ref = X.double() @ (Sd.t() if backward else Sd)
+        scale = ref.abs().max().item()
+        ob, of = _gemm(g, A2, backward, 2, 2)
+        e_f32 = (of.double() - ref).abs().max().item() / scale
+        rec = ob[:, :N].double() + ob[:, N:].double()
+        e_rec = (rec - ref).abs().max().item() / scale
+        _log('split-gemm', dict(N=N, M=M, weighted=weighted, backward=backward), f'f32 {e_f32:.2e} planes {e_rec:.2e}')
+        assert e_f32 < 2 ** -15, (N, M, backward, e_f32)
+        assert e_rec < 2 ** -15, (N, M, backward, e_rec)
+        # bf16-only output (the TMA-store epilogue every GEMM of the recurrence uses) must agree with the fp32-output epilogue
+        ob2, _ = _gemm(g, A2, backward, 2, 2, want_f32=False)
+        assert torch.equal(ob2, ob)
 
 
 # ---------------------------------------------------------------------------------------------------------
-# the tensor-core cell path.  Stated bound for bf16 operands (8-bit mantissa) with fp32 accumulation, fp32
-# state and fp32 gates, max-norm error relative to max|ref|:
-#   one step (T = 1, "teacher forced")        : H <= 1e-2, parameter gradients <= 3e-2
-#   short horizons (T <= 6), reference init   : H <= 1e-1, parameter gradients <= 6e-2
-# With the reference initialisation the state map has gain > 1 (weight_B ~ U(+-1/sqrt(G*Kin)) over F inputs and an
-# eigenvalue-1 common mode of S), so any rounding difference is amplified step by step; see also the contractive
-# long-horizon test below.  The fp32 path's 1e-5 / 1e-4 bound does NOT apply here.
+# the tensor-core cell path.  Stated bounds, max-norm error relative to max|ref| (fp32 accumulation, fp32 state and gates):
+#   precision           operands                    one step (T = 1)          short horizons (T <= 6), reference init
+#   bf16   (PREC 1)     bf16, 8-bit mantissa        H 1e-2, grads 3e-2        H 1e-1, grads 6e-2
+#   bf16x2 (PREC 2)     bf16 hi + lo, 16 bits       H 1e-4, grads 2e-3        H 1e-3, grads 1e-2
+# With the reference initialisation the recurrence is CHAOTIC (state map gain > 1: weight_B ~ U(+-1/sqrt(G*Kin)) over F
+# inputs): any rounding difference, including fp32 vs fp64, grows by ~e^{0.2..0.35} per step (profiles/r02_numerics_emulation.txt).
+# Bounds are therefore stated per horizon; test_tc_cfg3_full_horizon_vs_oracle measures all three precisions against the fp64
+# oracle at cfg3's own T = 64 and holds bf16x2 to a multiple of the fp32 path's own drift.
 # ---------------------------------------------------------------------------------------------------------
-TC_TOL_H, TC_TOL_G = 1e-1, 6e-2
-TC_TOL_H1, TC_TOL_G1 = 1e-2, 3e-2
+TC_TOL = {'bf16': dict(H=1e-1, G=6e-2, H1=1e-2, G1=3e-2), 'bf16x2': dict(H=1e-3, G=1e-2, H1=1e-4, G1=2e-3)}
+TC_TOL_H, TC_TOL_G = TC_TOL['bf16']['H'], TC_TOL['bf16']['G']
 
 
 def _log(*a):
@@ -103,40 +140,46 @@ def _make_cell(S, G, F, K, tg, prec, seed=0):
     return cell.to(DEV)
 
 
+@pytest.mark.parametrize('prec', ['bf16', 'bf16x2'])
 @pytest.mark.parametrize('tg', [False, True])
-@pytest.mark.parametrize('N,F,K,T,B,G', [(256, 32, 3, 5, 8, 1), (128, 16, 4, 3, 5, 2), (512, 64, 5, 4, 6, 1),
-                                         (256, 32, 3, 1, 8, 1), (512, 64, 5, 1, 6, 1)])
-def test_tc_cell_matches_fp32_path(tg, N, F, K, T, B, G):
+@pytest.mark.parametrize('N,F,K,T,B,G', [(256, 32, 3, 5, 8, 1), (256, 16, 4, 3, 5, 2), (512, 64, 5, 4, 6, 1),
+                                         (256, 32, 3, 1, 8, 1), (512, 64, 5, 1, 6, 1), (128, 16, 4, 3, 5, 2)])
+def test_tc_cell_matches_fp32_path(prec, tg, N, F, K, T, B, G):
+    if prec == 'bf16x2' and N % 256:
+        pytest.skip('split-bf16 operands need N % 256 == 0')
     S = gg.graphs.dense_random(N, 0.3, seed=1)
     torch.manual_seed(3)
     X, h0, dH = torch.randn(B, T, G, N, device=DEV), 0.3 * torch.randn(B, F, N, device=DEV), torch.randn(B, T, F, N, device=DEV)
     out = {}
     try:
-        for prec in ('fp32', 'bf16'):
-            cell = _make_cell(S, G, F, K, tg, prec)
+        for pr in ('fp32', prec):
+            cell = _make_cell(S, G, F, K, tg, pr)
             hh = h0.clone().requires_grad_(True)
             H = cell(X, hh)
             (H * dH).sum().backward()
-            out[prec] = (H.detach(), {k: v.grad for k, v in cell.named_parameters()}, hh.grad)
+            out[pr] = (H.detach(), {k: v.grad for k, v in cell.named_parameters()}, hh.grad)
     finally:
         gg.set_precision('fp32')
     H32, g32, dh32 = out['fp32']
-    Hb, gb, dhb = out['bf16']
+    Hb, gb, dhb = out[prec]
     errs = {'H': _relerr(Hb, H32), 'dh0': _relerr(dhb, dh32)}
     errs.update(_grad_errs(gb, g32))
-    _log('tc-vs-fp32', dict(tg=tg, N=N, F=F, K=K, T=T, B=B, G=G), {k: f'{v:.2e}' for k, v in errs.items()})
-    tol_h, tol_g = (TC_TOL_H1, TC_TOL_G1) if T == 1 else (TC_TOL_H, TC_TOL_G)
+    _log(f'tc-vs-fp32 {prec}', dict(tg=tg, N=N, F=F, K=K, T=T, B=B, G=G), {k: f'{v:.2e}' for k, v in errs.items()})
+    tol = TC_TOL[prec]
+    tol_h, tol_g = (tol['H1'], tol['G1']) if T == 1 else (tol['H'], tol['G'])
     assert errs['H'] < tol_h, errs
     bad = {k: v for k, v in errs.items() if k != 'H' and v > tol_g}
     assert not bad, errs
 
 
+@pytest.mark.parametrize('prec', ['bf16', 'bf16x2'])
 @pytest.mark.parametrize('tg', [False, True])
 @pytest.mark.parametrize('N,K,T,B,G', [(512, 5, 4, 6, 1), (256, 4, 3, 5, 2), (1024, 2, 2, 3, 1)])
-def test_tc_fused_backward_step_matches_unfused(tg, N, K, T, B, G):
+def test_tc_fused_backward_step_matches_unfused(prec, tg, N, K, T, B, G):
     """F = 64: the fused reverse-time kernel (tensor-core weight/tap gradients, tc_bwd.cuh) against the separate
-    tap-contraction + wgrad kernels.  Both are bf16-operand paths with the same forward, so they agree much more tightly
-    than either does with fp32: 1e-2 of max|ref| on every gradient."""
+    tap-contraction + wgrad kernels.  Both run the same forward and the same operand precision, so they agree much more
+    tightly than either does with fp32: 1e-2 of max|ref| on every gradient (bf16), 2e-3 (bf16x2: the weight-gradient
+    products use plane 0 of h in the fused kernel and fp32 h in the unfused one)."""
     F = 64
     S = gg.graphs.dense_random(N, 0.3, seed=4)
     torch.manual_seed(6)
@@ -146,7 +189,7 @@ def test_tc_fused_backward_step_matches_unfused(tg, N, K, T, B, G):
     try:
         for fused in (0, 1):
             _set_opt('bwd_fused', fused)
-            cell = _make_cell(S, G, F, K, tg, 'bf16')
+            cell = _make_cell(S, G, F, K, tg, prec)
             hh = h0.clone().requires_grad_(True)
             H = cell(X, hh)
             (H * dH).sum().backward()
@@ -156,8 +199,81 @@ def test_tc_fused_backward_step_matches_unfused(tg, N, K, T, B, G):
         gg.set_precision('fp32')
     errs = {'dh0': _relerr(out[1][1], out[0][1])}
     errs.update(_grad_errs(out[1][0], out[0][0]))
-    _log('tc-fused-vs-unfused', dict(tg=tg, N=N, K=K, T=T, B=B, G=G), {k: f'{v:.2e}' for k, v in errs.items()})
-    assert all(v < 1e-2 for v in errs.values()), errs
+    _log(f'tc-fused-vs-unfused {prec}', dict(tg=tg, N=N, K=K, T=T, B=B, G=G), {k: f'{v:.2e}' for k, v in errs.items()})
+    assert all(v < (1e-2 if prec == 'bf16' else 2e-3) for v in errs.values()), errs
+
+
+def _weighted_dense(N, seed=0):
+    """cfg3-like graph with edge weights (Adj.p-like: the operator is NOT exactly representable in bf16)."""
+    S = gg.graphs.dense_random(N, 0.3, seed=seed)[0].double()
+    g = torch.Generator().manual_seed(seed + 5)
+    W = torch.rand(N, N, generator=g, dtype=torch.float64)
+    S = S * (W + W.t()) / 2
+    S = S / torch.linalg.eigvalsh(S).abs().max()
+    return S.float().reshape(1, N, N)
+
+
+@pytest.mark.parametrize('weighted', [False, True])
+@pytest.mark.parametrize('h0_scale', [0.0, 0.3])
+def test_tc_cfg3_full_horizon_vs_oracle(weighted, h0_scale):
+    """cfg3 at its OWN horizon against the fp64 oracle: N=1024, F=64, K=5, G=1, T=64, B=2, time-gated, reference init seed 0
+    (no weight scaling), h0 = 0 and h0 != 0, unweighted (cfg3) and weighted operator.  All three precisions run; the per-step
+    max-norm error curves go to gpurun_out/r02_horizon_<case>.json (committed under profiles/).
+
+    Under the reference init the recurrence is chaotic (see the header comment), so the fp32 exact path itself drifts from fp64;
+    it is the calibration.  Asserted:
+      fp32   : <= 1e-4 of max|H| over the first 16 steps (the stated 1e-5 bound holds at T <= 5, see test_gpu_parity.py);
+      bf16x2 : <= 2e-3 over the first 16 steps, and at every step t < 48 at most 100x the fp32 path's own error (floored at 1e-6);
+               parameter gradients of the T = 16 prefix problem <= 1e-2;
+      bf16   : <= 6e-2 over the first 4 steps only (it decorrelates from fp64 after ~20 steps: its curve is logged, and the
+               bench reports it as the fast mode for short horizons / contractive recurrences)."""
+    import json
+    import os
+    from oracle import gcrnn_oracle as orc
+    N, F, K, T, B = 1024, 64, 5, 64, 2
+    S = _weighted_dense(N) if weighted else gg.graphs.dense_random(N, 0.3, seed=0)
+    torch.manual_seed(0)
+    ref_cell = gg.GGCRNNCell(1, F, K, K, torch.tanh, True, None, 1, True)
+    ref_cell.addGSO(S)
+    p = {k: v.detach().double().cpu() for k, v in ref_cell.state_dict().items()}
+    torch.manual_seed(5)
+    X, h0, dH = torch.randn(B, T, 1, N), h0_scale * torch.randn(B, F, N), torch.randn(B, T, F, N)
+    T16 = 16
+    dH16 = dH.clone(); dH16[:, T16:] = 0          # gradients of the T = 16 prefix problem (same forward)
+    Href, gref = orc.cell_forward_backward(p, S.double(), X.double(), h0.double(), dH16.double(), True, None)
+    hmax = Href.abs().max().item()
+    curves, gerrs = {}, {}
+    try:
+        for prec in ('fp32', 'bf16x2', 'bf16'):
+            gg.set_precision(prec)
+            torch.manual_seed(0)
+            cell = gg.GGCRNNCell(1, F, K, K, torch.tanh, True, None, 1, True)
+            cell.addGSO(S)
+            cell = cell.to(DEV)
+            H = cell(X.to(DEV), h0.to(DEV))
+            (H * dH16.to(DEV)).sum().backward()
+            Hc = H.detach().double().cpu()
+            curves[prec] = [((Hc[:, t] - Href[:, t]).abs().max().item() / hmax) for t in range(T)]
+            gerrs[prec] = _grad_errs({k: v.grad for k, v in cell.named_parameters()}, {k: gref[k] for k, _ in cell.named_parameters()})
+    finally:
+        gg.set_precision('fp32')
+    case = f'{"weighted" if weighted else "cfg3"}_h0_{h0_scale}'
+    for prec in curves:
+        _log(f'horizon {case} {prec}: H err @t=0,3,7,15,31,47,63 ' + ' '.join(f'{curves[prec][t]:.1e}' for t in (0, 3, 7, 15, 31, 47, 63))
+             + f' | T=16 grads max {max(gerrs[prec].values()):.1e}')
+    if os.path.isdir('gpurun_out'):
+        with open(f'gpurun_out/r02_horizon_{case}.json', 'w') as f:
+            json.dump(dict(case=case, N=N, F=F, K=K, T=T, B=B, init='reference init, seed 0', reference='fp64 oracle (oracle/gcrnn_oracle.py)',
+                           metric='max_n |H[:, t] - H_ref[:, t]| / max|H_ref| per step t; grads: T=16 prefix problem, max-norm relative',
+                           curves=curves, grads_T16=gerrs), f, indent=1)
+    assert max(curves['fp32'][:16]) < 1e-4, curves['fp32'][:16]
+    assert max(curves['bf16x2'][:16]) < 2e-3, curves['bf16x2'][:16]
+    ratio = max(curves['bf16x2'][t] / max(curves['fp32'][t], 1e-6) for t in range(48))
+    _log(f'horizon {case}: max_t<48 bf16x2 / max(fp32, 1e-6) = {ratio:.1f}')
+    assert ratio < 100, ratio
+    assert max(gerrs['fp32'].values()) < 1e-3, gerrs['fp32']
+    assert max(gerrs['bf16x2'].values()) < 1e-2, gerrs['bf16x2']
+    assert max(curves['bf16'][:4]) < 6e-2, curves['bf16'][:4]
 
 
 def test_tc_cell_vs_fp64_oracle_reduced_cfg3():

@@ -20,7 +20,7 @@ Href, gref = orc.cell_forward_backward(p, [S.double().to_sparse_coo().coalesce()
 L = _lib.lib()
 res = {}
 for fused in (1, 0):
-    L.gcrnn_debug_set_option(b'sparse_fused', fused)
+    gg.options.set('sparse_fused', fused)
     cell = gg.GGCRNNCell(1, F_, K, K, torch.tanh, False, 'edge', 1, True)
     cell.addGSO(S); cell.load_state_dict(p); cell = cell.to(device=DEV, dtype=torch.float32)
     hg = h0.float().to(DEV).requires_grad_(True)
@@ -37,7 +37,7 @@ ref = gref['__h0']
 dd = (res[1][0].cpu().double() - ref).abs()
 idx = np.unravel_index(int(dd.argmax()), dd.shape)
 print('fused-vs-oracle worst at', idx, float(dd.max()), 'in-degree of that node', int(np.bincount(ci, minlength=N)[idx[2]]), 'count > 1e-4*max:', int((dd > 1e-4 * ref.abs().max()).sum()))
-L.gcrnn_debug_set_option(b'sparse_fused', 1)
+gg.options.set('sparse_fused', 1)
 for name, fused in (('fused', 1), ('generic', 0)):
     dd = (res[fused][0].cpu().double() - ref).abs()
     bad = (dd > 1e-4 * ref.abs().max()).nonzero()
