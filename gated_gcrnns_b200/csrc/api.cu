@@ -255,6 +255,7 @@ int gcrnn_cell_set_option(gcrnn_cell* c, const char* name, int32_t value) {
   GCRNN_CHECK(c && name, "null argument");
   const std::string n(name);
   if (n == "need_dx") c->need_dx = value != 0;
+  else if (n == "dh_last_only") c->dh_last_only = value != 0;
   else if (n == "path") { GCRNN_CHECK(value >= -1 && value <= GCRNN_PATH_NODE32, "bad path %d", value); c->forced_path = value; }
   else {
     int* f = option_field(c->opt, name);
@@ -268,6 +269,7 @@ int gcrnn_cell_get_option(const gcrnn_cell* c, const char* name, int32_t* value)
   GCRNN_CHECK(c && name && value, "null argument");
   const std::string n(name);
   if (n == "need_dx") *value = c->need_dx;
+  else if (n == "dh_last_only") *value = c->dh_last_only;
   else if (n == "path") *value = c->forced_path;
   else if (n == "last_path") *value = c->last_path;
   else {
@@ -327,7 +329,7 @@ int gcrnn_cell_backward(gcrnn_cell* c, const gcrnn_cell_params* p, const float* 
     key_params(key, n, grads);
     key.p[n++] = X; key.p[n++] = h0; key.p[n++] = H; key.p[n++] = dH; key.p[n++] = saved; key.p[n++] = dX; key.p[n++] = dh0; key.p[n++] = ws;
     key.p[n++] = (const void*)savedb; key.p[n++] = (const void*)wsb;
-    key.B = B; key.T = T; key.kind = 1; key.path = c->forced_path; key.need_dx = dX != nullptr; key.epoch = c->opt.epoch;
+    key.B = B; key.T = T; key.kind = 1; key.path = c->forced_path; key.need_dx = dX != nullptr; key.pad = c->dh_last_only; key.epoch = c->opt.epoch;
     run_graphed(c, key, (cudaStream_t)stream,
                 [&](cudaStream_t st) { cell_backward_f32(c, p, X, h0, H, dH, saved, savedb, grads, dX, dh0, ws, wsb, B, T, st); });
   } else cell_backward_f32(c, p, X, h0, H, dH, saved, savedb, grads, dX, dh0, ws, wsb, B, T, (cudaStream_t)stream);

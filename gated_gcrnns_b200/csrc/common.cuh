@@ -116,6 +116,7 @@ struct gcrnn_cell {
   const gcrnn_graph* g = nullptr;
   // execution-path selection of the fp32 sparse path (gcrnn_cell_set_option / gcrnn_cell_get_option)
   mutable int need_dx = 0;        // hint for the next forward: the caller will ask backward for dX
+  mutable int dh_last_only = 0;   // backward: `dH` is the gradient of the LAST state only, [B,F,N] (classification readout)
   mutable int forced_path = -1;   // -1: choose automatically; otherwise GCRNN_PATH_*
   mutable int last_path = 0;      // path taken by the last forward
   mutable int fwd_v2_mask = 63;   // fused sparse path: stage generations the last forward used (its backward follows them)
@@ -124,6 +125,15 @@ struct gcrnn_cell {
 };
 
 namespace gcrnn {
+
+// Gradient of the output at step t.  Dense dH[B,T,F,N]; or, with the cell option "dh_last_only", `dH` holds only the gradient of
+// H[:, T-1] as [B,F,N] and every earlier step reads ONE shared zero slab [F,N] with sample stride 0 (L2-resident: no HBM
+// traffic and no [B,T,F,N] gradient tensor at all).  Modules/architectures.py:1841-1850 uses only H.select(1, -1).
+struct DhView {
+  const float* dH; const float* zero; long long T, FN; bool last_only;
+  const float* ptr(long long t) const { return last_only ? (t == T - 1 ? dH : zero) : dH + t * FN; }
+  long long bstride(long long t) const { return last_only ? (t == T - 1 ? FN : 0) : T * FN; }
+};
 
 // Bump allocator over a caller-provided workspace.  With base == nullptr it only counts, which is how the
 // *_workspace_bytes entry points are implemented (same code path as the real run).

@@ -569,7 +569,7 @@ struct Bwd32Bufs { float *dya, *dyr, *pa, *pr, *dd, *wch, *dhrec, *acc; float2* 
 
 template <int KST>
 void e32_backward_steps(const Ctx& c, const CellDims& d, const gcrnn_cell_params* p, const Saved& s, const Saved32& x,
-                        const float* dH, const Bwd32Bufs& b) {
+                        const DhView& dv, const Bwd32Bufs& b) {
   const gcrnn_graph* g = c.g;
   const long long BN = d.B * d.N, BNF = d.B * d.NF;
   const Gather& fw = g->fwd[0];
@@ -597,7 +597,7 @@ void e32_backward_steps(const Ctx& c, const CellDims& d, const gcrnn_cell_params
     const float* wa = x.wu_a + t * BNF; const float* wr = x.wu_r + t * BNF;
     const float4* info = x.info + 2 * t * BN;
     if (!(fuse_dpre && t < d.T - 1)) {            // otherwise the dh kernel of step t+1 already left dya / dyr of this step
-      e32::dpre_k<<<g_dpre, 256, 0, c.st>>>(dH + t * d.NF, d.T * d.NF, t == d.T - 1 ? nullptr : b.dhrec, hn, x.masks + t * BN, b.dya, b.dyr,
+      e32::dpre_k<<<g_dpre, 256, 0, c.st>>>(dv.ptr(t), dv.bstride(t), t == d.T - 1 ? nullptr : b.dhrec, hn, x.masks + t * BN, b.dya, b.dyr,
                                             d.N, d.B);
       check_launch();
     }
@@ -628,7 +628,7 @@ void e32_backward_steps(const Ctx& c, const CellDims& d, const gcrnn_cell_params
     }
     if (v2(V2_DH))
       k_dh<<<g_dh2, 256, dh_smem, c.st>>>(gbw, wc, e32::Chain{}, 0, 1, p->weight_B, nullptr, nullptr, nullptr, b.dhrec, nullptr, d.N, d.B,
-                                          (fuse_dpre && t > 0) ? e32::DpreFuse{dH + (t - 1) * d.NF, d.T * d.NF, s.Hn + (t - 1) * BNF, x.masks + (t - 1) * BN, b.dya, b.dyr}
+                                          (fuse_dpre && t > 0) ? e32::DpreFuse{dv.ptr(t - 1), dv.bstride(t - 1), s.Hn + (t - 1) * BNF, x.masks + (t - 1) * BN, b.dya, b.dyr}
                                                                : e32::DpreFuse{});
     else
       e32::dh_k<KST><<<g_dh, 128, 0, c.st>>>(gbw, wc, p->weight_B, b.dhrec, d.N, BN);
@@ -648,12 +648,15 @@ size_t cell_backward_e32(const gcrnn_cell* cell, const gcrnn_cell_params* p, con
   b.dya = a.get<float>(d.B * d.NF); b.dyr = a.get<float>(d.B * d.NF); b.pa = a.get<float>(d.B * d.NF); b.pr = a.get<float>(d.B * d.NF);
   b.dd = a.get<float>(d.B * d.NF); b.wch = a.get<float>((size_t)(d.Kst - 2) * d.B * d.NF); b.dhrec = a.get<float>(d.B * d.NF);
   b.dr = a.get<float2>(d.B * d.N); b.acc = a.get<float>(e32::AccLayout::TOTAL);
+  float* zslab = cell->dh_last_only ? a.get<float>(d.NF) : nullptr;
   if (a.dry()) return a.off;
+  if (zslab) zero(c, zslab, d.NF * sizeof(float));
+  const DhView dv{dH, zslab, d.T, d.NF, cell->dh_last_only != 0};
   zero(c, b.acc, e32::AccLayout::TOTAL * sizeof(float));
   switch (d.Kst) {
-    case 2: e32_backward_steps<2>(c, d, p, s, x, dH, b); break;
-    case 3: e32_backward_steps<3>(c, d, p, s, x, dH, b); break;
-    default: e32_backward_steps<4>(c, d, p, s, x, dH, b); break;
+    case 2: e32_backward_steps<2>(c, d, p, s, x, dv, b); break;
+    case 3: e32_backward_steps<3>(c, d, p, s, x, dv, b); break;
+    default: e32_backward_steps<4>(c, d, p, s, x, dv, b); break;
   }
   e32::finalize_k<<<1, 1024, 0, st>>>(b.acc, p->weight_A, p->weight_B, p->bias, p->e_weight[0], p->e_weight[1], gr->weight_A,
                                       gr->weight_B, gr->bias, gr->e_mixer[0], gr->e_weight[0], gr->e_mixer[1], gr->e_weight[1],
@@ -791,7 +794,10 @@ size_t cell_backward_f32(const gcrnn_cell* cell, const gcrnn_cell_params* p, con
     ubuf = a.get<float>(d.TB * d.NF); c0 = a.get<float>(d.B * d.NF); dc0 = a.get<float>(d.B * d.NF);
     dzh0 = a.get<float>((size_t)SB * d.B * d.NF);
   }
+  float* zslab = cell->dh_last_only ? a.get<float>(d.NF) : nullptr;
   if (a.dry()) return a.off;
+  if (zslab) zero(c, zslab, d.NF * sizeof(float));
+  const DhView dv{dH, zslab, d.T, d.NF, cell->dh_last_only != 0};
 
   zero(c, dhn, d.B * d.NF * sizeof(float));
   if (d.tg) zero(c, dgt, 2 * d.TB * sizeof(float));
@@ -812,7 +818,7 @@ size_t cell_backward_f32(const gcrnn_cell* cell, const gcrnn_cell_params* p, con
       va = qa; vr = qr;
     }
     // dh_t = dH[:, t] (reference layout) + what flowed back from step t+1
-    transpose(c, dH + t * d.NF, dhn, dht, d.F, d.N, d.B, 1, d.T * d.NF, 0, d.NF, 0);
+    transpose(c, dv.ptr(t), dhn, dht, d.F, d.N, d.B, 1, dv.bstride(t), 0, d.NF, 0);
     {
       dim3 grid((d.N + 127) / 128, (unsigned)std::min<long long>(d.B, 32768));
       combine_bwd_k<<<grid, 128, 0, st>>>(dht, s.Hn + t * d.B * d.NF, va, vr,

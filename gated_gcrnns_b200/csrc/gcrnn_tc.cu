@@ -426,6 +426,7 @@ size_t cell_backward_tc(const gcrnn_cell* cell, const gcrnn_cell_params* p, cons
   const bool fused = opt().bwd_fused && d.F == 64 && d.Kin * d.G <= 8 && d.Kst <= 6 && d.N % 128 == 0 && bf_stages(P, d.Kst) >= 2;
   __nv_bfloat16* Zs = fused ? a.get<__nv_bfloat16>((size_t)d.BT * BF_ZROWS * d.N) : nullptr;
   float* partA = fused ? a.get<float>((size_t)max_sms * 64 * BF_ZROWS) : nullptr;
+  float* zslab = cell->dh_last_only ? a.get<float>((size_t)d.F * d.N) : nullptr;
   float *dgt = nullptr, *c0 = nullptr, *dc0 = nullptr, *dl = nullptr;
   __nv_bfloat16* Wb = nullptr;
   if (d.tg) {
@@ -439,6 +440,8 @@ size_t cell_backward_tc(const gcrnn_cell* cell, const gcrnn_cell_params* p, cons
   GCRNN_CHECK(d.sms <= max_sms, "unexpected SM count %d", d.sms);
   const long long FN = (long long)d.F * d.N, GN = (long long)d.G * d.N;
   const size_t part_bytes = (size_t)d.sms * d.Kst * d.F * d.F * sizeof(float);
+  if (zslab) CUDA_OK(cudaMemsetAsync(zslab, 0, (size_t)FN * sizeof(float), st));
+  const DhView dv{dH, zslab, d.T, FN, cell->dh_last_only != 0};
 
   // dB_k += sum_{b,n} V_k h^T with the (already g_f-scaled) adjoint chain in vb0/vb
   auto wgrad_v = [&](const __nv_bfloat16* v0p, const float* h32, long long hstride, const __nv_bfloat16* h16) {
@@ -466,7 +469,7 @@ size_t cell_backward_tc(const gcrnn_cell* cell, const gcrnn_cell_params* p, cons
   const bool can_fuse = d.Kin * d.G <= 7;
   auto run_dpre = [&](long long t, const float* dhrec_in, __nv_bfloat16* v0_out) {
     DpreArgs da{};
-    da.dH = dH + t * FN; da.dH_bstride = d.T * FN; da.Ht = H + t * FN; da.H_bstride = d.T * FN;
+    da.dH = dv.ptr(t); da.dH_bstride = dv.bstride(t); da.Ht = H + t * FN; da.H_bstride = d.T * FN;
     da.dhrec = dhrec_in; da.v0 = v0_out; da.P = P;
     da.gi = d.tg ? s.gt + t : nullptr; da.gf = d.tg ? s.gt + d.BT + t : nullptr; da.gate_stride = d.T;
     da.A = p->weight_A; da.bias = p->bias; da.Kin = d.Kin; da.G = d.G; da.F = d.F; da.N = d.N;
@@ -495,7 +498,7 @@ size_t cell_backward_tc(const gcrnn_cell* cell, const gcrnn_cell_params* p, cons
       fa.gf = d.tg ? s.gt + d.BT + t : nullptr; fa.gate_stride = d.T; fa.dgf = d.tg ? dgt + d.BT + t : nullptr;
       fa.hprev = hprev; fa.hprev_bstride = hstride;
       if (t > 0) {
-        fa.dHn = dH + (t - 1) * FN; fa.dHn_bstride = d.T * FN;
+        fa.dHn = dv.ptr(t - 1); fa.dHn_bstride = dv.bstride(t - 1);
         fa.gfn = d.tg ? s.gt + d.BT + (t - 1) : nullptr;
         fa.dgin = d.tg ? dgt + (t - 1) : nullptr; fa.dgfn = d.tg ? dgt + d.BT + (t - 1) : nullptr;
         fa.A = p->weight_A; fa.x0 = X + (t - 1) * GN; fa.zx = s.zx + (t - 1) * GN; fa.zx_kstride = d.RX * d.N; fa.z_bstride = d.T * GN;
@@ -514,7 +517,7 @@ size_t cell_backward_tc(const gcrnn_cell* cell, const gcrnn_cell_params* p, cons
     ca.scaled_chain = 1;                       // the chain input is g_f * dpre: acc = g_f q = dh_{t-1} directly
     if (t > 0 && can_fuse) {
       // fused: the epilogue forms step t-1's dpre, its bf16 chain input and the per-(b, f) sums it needs
-      ca.dHn = dH + (t - 1) * FN; ca.dHn_bstride = d.T * FN;
+      ca.dHn = dv.ptr(t - 1); ca.dHn_bstride = dv.bstride(t - 1);
       ca.gfn = d.tg ? s.gt + d.BT + (t - 1) : nullptr;
       ca.Kin = d.Kin; ca.G = d.G;
       ca.x0 = X + (t - 1) * GN; ca.x0_bstride = d.T * GN;

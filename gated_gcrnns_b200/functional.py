@@ -252,7 +252,7 @@ def _destroy_cell(h):
 
 class _CellFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, cell: CellHandle, X, h0, *params):
+    def forward(ctx, cell: CellHandle, last_only: bool, X, h0, *params):
         dev = X.device
         B, T = int(X.shape[0]), int(X.shape[1])
         X32, h32 = _f32(X, dev), _f32(h0, dev)
@@ -262,7 +262,7 @@ class _CellFn(torch.autograd.Function):
         # and remember the choice so that backward runs on the path whose saved state this forward wrote
         cell.sync_options()
         cell.set_option('path', -1)
-        cell.set_option('need_dx', int(ctx.needs_input_grad[1]))
+        cell.set_option('need_dx', int(ctx.needs_input_grad[2]))
         sb, fb, _ = cell.workspace(B, T, False)
         saved = _bytes(sb, dev)
         ws = _bytes(fb, dev)
@@ -270,9 +270,13 @@ class _CellFn(torch.autograd.Function):
         _lib.check(_lib.lib().gcrnn_cell_forward(cell.ptr, C.byref(st), _ptr(X32), _ptr(h32), _ptr(H), _ptr(saved),
                                                  saved.numel(), _ptr(ws), ws.numel(), B, T, _stream(dev)), 'cell_forward')
         ctx.cell = cell
+        ctx.last_only = bool(last_only)
         ctx.path = cell.get_option('last_path')
         ctx.types = (X.dtype, h0.dtype, [p.dtype for p in params], [p.shape for p in params])
         ctx.save_for_backward(X32, h32, H, saved, *p32)
+        if last_only:                  # only H[:, T-1] leaves; every state stays in `H` for the reverse sweep
+            out = H[:, T - 1]
+            return out.to(X.dtype) if X.dtype != torch.float32 else out.clone()
         return H.to(X.dtype) if X.dtype != torch.float32 else H
 
     @staticmethod
@@ -282,8 +286,8 @@ class _CellFn(torch.autograd.Function):
         dev = X32.device
         B, T = int(X32.shape[0]), int(X32.shape[1])
         xd, hd, pds, pshapes = ctx.types
-        need_x, need_h = ctx.needs_input_grad[1], ctx.needs_input_grad[2]
-        dH32 = _f32(dH, dev)
+        need_x, need_h = ctx.needs_input_grad[2], ctx.needs_input_grad[3]
+        dH32 = _f32(dH, dev)              # [B,T,F,N], or [B,F,N] in last-state-only mode
         # one flat fp32 bucket for every parameter gradient: the kernels accumulate straight into it and the
         # data-parallel all-reduce (if a process group is active) runs on it in one call
         sizes = [p.numel() for p in p32]
@@ -295,17 +299,22 @@ class _CellFn(torch.autograd.Function):
         dh0 = torch.empty_like(h32) if need_h else None
         cell.sync_options()
         cell.set_option('path', ctx.path)
+        cell.set_option('dh_last_only', int(ctx.last_only))
         _, _, bb = cell.workspace(B, T, need_x or need_h)
         ws = _bytes(bb, dev)
         _lib.check(_lib.lib().gcrnn_cell_backward(cell.ptr, C.byref(pst), _ptr(X32), _ptr(h32), _ptr(H), _ptr(dH32),
                                                   _ptr(saved), saved.numel(), C.byref(gst), _ptr(dX), _ptr(dh0), _ptr(ws),
                                                   ws.numel(), B, T, _stream(dev)), 'cell_backward')
         cell.set_option('path', -1)
+        cell.set_option('dh_last_only', 0)
         _dist.reduce_cell_bucket(bucket)          # only in dist.enable(reduce_in_backward=True) mode: cell parameters only, SUM
         grads = [v.reshape(s).to(d) for v, s, d in zip(views, pshapes, pds)]
-        return (None, dX.to(xd) if need_x else None, dh0.to(hd) if need_h else None, *grads)
+        return (None, None, dX.to(xd) if need_x else None, dh0.to(hd) if need_h else None, *grads)
 
 
-def gated_gcrnn(cell: CellHandle, X, h0, params: Sequence[torch.Tensor]):
-    """H = recurrence(X, h0) for the configuration in ``cell``; ``params`` ordered as ``cell.slots``."""
-    return _CellFn.apply(cell, X, h0, *params)
+def gated_gcrnn(cell: CellHandle, X, h0, params: Sequence[torch.Tensor], last_state_only: bool = False):
+    """H = recurrence(X, h0) for the configuration in ``cell``; ``params`` ordered as ``cell.slots``.
+
+    ``last_state_only=True`` returns H[:, T-1] ([B,F,N]) only: no [B,T,F,N] output or output-gradient tensor is handed to
+    autograd (the classification readout uses nothing else: Modules/architectures.py:1841-1850)."""
+    return _CellFn.apply(cell, bool(last_state_only), X, h0, *params)

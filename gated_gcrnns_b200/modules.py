@@ -144,6 +144,10 @@ class GGCRNNCell(nn.Module):
             self.register_parameter('bias', None)
         self.reset_parameters()
         self._handles = {}
+        # True: forward computes every state but exposes only the last one, as a stride-0 expansion [B,T,F,N] of H[:, T-1]
+        # (so `H.select(1, -1)` of the reference's classifier, architectures.py:1844, works unchanged); no [B,T,F,N] output or
+        # output-gradient tensor exists.  Set by install() on the classification architecture's cell, or by hand.
+        self.last_state_only = False
 
     def reset_parameters(self):
         stdv = 1. / math.sqrt(self.G * self.Kin)       # also for weight_B, as in the reference (graphML.py:2231)
@@ -253,6 +257,9 @@ class GGCRNNCell(nn.Module):
         if h0.device != X.device:                      # train_rnn.py:256 builds h0 on the CPU
             h0 = h0.to(X.device)
         cell = self._handle(X.device, need_dx=bool(X.requires_grad and torch.is_grad_enabled()))
+        if getattr(self, 'last_state_only', False):
+            hl = Fn.gated_gcrnn(cell, X, h0, self._used_parameters(cell.slots), last_state_only=True)
+            return hl.unsqueeze(1).expand(X.shape[0], X.shape[1], self.F, self.N)
         return Fn.gated_gcrnn(cell, X, h0, self._used_parameters(cell.slots))
 
     def extra_repr(self):

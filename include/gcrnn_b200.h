@@ -136,6 +136,9 @@ int gcrnn_cell_destroy(gcrnn_cell* c);
  *   "path"      (set)  -1 = automatic (default), otherwise force GCRNN_PATH_* — the autograd glue forces backward onto the path
  *                      its forward took;
  *   "need_dx"   (set)  hint for the next forward: backward will be asked for dX (reserved for paths that cannot serve it);
+ *   "dh_last_only" (set) 1: the next backward's `dH` is the gradient of the LAST state only, dH[:, T-1] as [B,F,N]; the gradient of
+ *                      every earlier output is zero and no [B,T,F,N] gradient tensor exists (classification readout,
+ *                      Modules/architectures.py:1841-1850 uses only H.select(1, -1));
  *   "last_path" (get)  path taken by the last forward on this handle. */
 enum { GCRNN_PATH_GENERIC = 0, GCRNN_PATH_NODE32 = 1 };
 int gcrnn_cell_set_option(gcrnn_cell* c, const char* name, int32_t value);
@@ -147,7 +150,7 @@ int gcrnn_cell_workspace_bytes(const gcrnn_cell* c, int64_t B, int64_t T, int32_
 int gcrnn_cell_forward(gcrnn_cell* c, const gcrnn_cell_params* p, const float* X, const float* h0,
                        float* H, void* saved, size_t saved_bytes,
                        void* workspace, size_t workspace_bytes, int64_t B, int64_t T, void* stream);
-/* grads: accumulated (+=).  dX / dh0 may be NULL.  Parameters the reference never uses
+/* dH: [B,T,F,N], or [B,F,N] with the cell option "dh_last_only".  grads: accumulated (+=).  dX / dh0 may be NULL.  Parameters the reference never uses
  * (GFL_out.*, MLP_out.*) do not appear here at all: their gradient stays None, as in the reference. */
 int gcrnn_cell_backward(gcrnn_cell* c, const gcrnn_cell_params* p, const float* X, const float* h0,
                         const float* H, const float* dH, const void* saved, size_t saved_bytes,

@@ -77,3 +77,151 @@ def test_reference_training_loop_runs_unchanged(tmp_path, spatial):
     np.testing.assert_allclose(our_losses, ref_losses, rtol=2e-4, atol=1e-6)
     for k in ref_sd:        # parameters after the SGD steps (and after MultipleModels re-loaded the 'Best' checkpoint)
         assert (our_sd[k] - ref_sd[k]).abs().max() <= 2e-4 * max(1.0, ref_sd[k].abs().max()), k
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# SURVEY 8f rank 1 + 2: readouts.  The reference architectures run UNCHANGED on our modules (after
+# install(gml, architectures)) and must reproduce the reference's own CPU run: outputs, every parameter gradient and a few
+# optimisation steps of the reference's training loops.
+# ---------------------------------------------------------------------------------------------------------------
+def _adj_p():
+    """The seismograph graph of epicenterEstimation.py (Adj.p / |lambda|max), from the committed golden fixture."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'cell_cfg2_node.npz'), allow_pickle=False)
+    return np.asarray(z['S'], dtype=np.float64).reshape(59, 59)
+
+
+def _fwd_bwd(net, x, h0, target, loss_fn):
+    net.zero_grad()
+    y = net(x, h0)
+    loss = loss_fn(y, target)
+    loss.backward()
+    return y.detach().double().cpu(), float(loss), {k: (None if p.grad is None else p.grad.detach().double().cpu()) for k, p in net.named_parameters()}
+
+
+def _compare(ref, ours, tol_y=1e-5, tol_g=2e-4):
+    (yr, lr, gr), (yo, lo, go) = ref, ours
+    assert yr.shape == yo.shape
+    assert (yr - yo).abs().max() <= tol_y * max(1.0, yr.abs().max())
+    assert abs(lr - lo) <= tol_y * max(1.0, abs(lr))
+    assert list(gr.keys()) == list(go.keys())
+    for k in gr:
+        if gr[k] is None:
+            assert go[k] is None, k
+            continue
+        assert (gr[k] - go[k]).abs().max() <= tol_g * max(gr[k].abs().max(), 1e-30), (k, float((gr[k] - go[k]).abs().max()), float(gr[k].abs().max()))
+
+
+@pytest.mark.parametrize('spatial', ['node', 'edge'])
+def test_classifier_last_state_only_matches_reference(spatial):
+    """GatedGCRNNforClassification on Adj.p (cfg2: N=59, F=20, K=4, T=20, 11 classes): install() switches its cell to
+    last-state-only mode (no [B,T,F,N] output / output-gradient tensor); logits, loss and all gradients equal the reference's."""
+    if not ref_shim.available():
+        pytest.skip('no copy of the reference tree on this box')
+    gml = ref_shim.load()
+    archs = ref_shim.load_architectures()
+    S = _adj_p()
+    N, F, K, T, B, C_ = 59, 20, 4, 20, 16, 11
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(B, T, 1, N, generator=g)
+    target = torch.randint(0, C_, (B,), generator=g)
+    ce = torch.nn.CrossEntropyLoss()
+
+    def build():
+        torch.manual_seed(0)
+        return archs.GatedGCRNNforClassification(1, F, K, K, torch.tanh, torch.nn.ReLU, [C_], S, True, time_gating=False,
+                                                 spatial_gating=spatial)
+    ref = _fwd_bwd(build(), x, torch.zeros(B, F, N), target, ce)
+    gg.install(gml, archs)
+    try:
+        net = build()
+        assert net.stateGCRNN.last_state_only
+        net.to(DEV)
+        H = net.stateGCRNN(x.to(DEV), torch.zeros(B, F, N, device=DEV))
+        assert H.shape == (B, T, F, N) and H.stride(1) == 0           # a stride-0 expansion of the last state: nothing materialised
+        ours = _fwd_bwd(net, x.to(DEV), torch.zeros(B, F, N), target.to(DEV), ce)
+        # the same model WITHOUT the last-state shortcut must agree too
+        net.stateGCRNN.last_state_only = False
+        full = _fwd_bwd(net, x.to(DEV), torch.zeros(B, F, N), target.to(DEV), ce)
+    finally:
+        gg.uninstall(gml, archs)
+    _compare(ref, ours)
+    _compare(ref, full)
+
+
+@pytest.mark.parametrize('mlp', ['multipMlp', 'oneMlp'])
+def test_regression_batched_node_readout_matches_reference(mlp):
+    """GatedGCRNNforRegression: the reference applies the per-node MLP in a Python loop over N (architectures.py:1613-1636);
+    readout.regression_forward is one batched contraction.  Reference on the CPU vs ours on the GPU."""
+    if not ref_shim.available():
+        pytest.skip('no copy of the reference tree on this box')
+    gml = ref_shim.load()
+    archs = ref_shim.load_architectures()
+    N, F, K, T, B = 20, 6, 3, 4, 5
+    S = gg.graphs.sbm(N, 4, 0.7, 0.2, seed=3)[0].numpy()
+    g = torch.Generator().manual_seed(4)
+    x, y = torch.randn(B, T, 1, N, generator=g), torch.randn(B, T, 1, N, generator=g)
+    l1 = torch.nn.L1Loss()
+
+    def build():
+        torch.manual_seed(0)
+        dims = [1] if mlp == 'multipMlp' else [N]
+        return archs.GatedGCRNNforRegression(1, F, K, K, torch.tanh, torch.tanh, dims, S, True, time_gating=True,
+                                             spatial_gating=None, mlpType=mlp)
+    ref = _fwd_bwd(build(), x, torch.zeros(B, F, N), y, l1)
+    gg.install(gml, archs)
+    try:
+        net = build()
+        net.to(DEV)
+        ours = _fwd_bwd(net, x.to(DEV), torch.zeros(B, F, N), y.to(DEV), l1)
+    finally:
+        gg.uninstall(gml, archs)
+    _compare(ref, ours)
+
+
+def test_gcrnn_gnn_and_selection_gnn_on_our_graph_filter():
+    """the GCRNN with a Selection-GNN readout (kStepPredGRNNs.py:308-335: `GCRNN_GNN`) and the stand-alone
+    SelectionGNN baseline (architectures.py:10-177) run on OUR GraphFilter after install(); outputs and gradients match the
+    reference's CPU run."""
+    if not ref_shim.available():
+        pytest.skip('no copy of the reference tree on this box')
+    gml = ref_shim.load()
+    archs = ref_shim.load_architectures()
+    N, F, K, T, B = 20, 6, 3, 4, 5
+    S = gg.graphs.sbm(N, 4, 0.7, 0.2, seed=3)[0].numpy()
+    g = torch.Generator().manual_seed(4)
+    x, y = torch.randn(B, T, 1, N, generator=g), torch.randn(B, T, 1, N, generator=g)
+    l1 = torch.nn.L1Loss()
+
+    def build_gcrnn_gnn():
+        torch.manual_seed(0)
+        # dimNodeSignals [F_h, 4, 1], taps [3, 3], no pooling (NoPool, all nodes kept), no final MLP
+        return archs.GatedGCRNNforRegression(1, F, K, K, torch.tanh, torch.nn.Tanh, [], S, True, time_gating=True, spatial_gating=None,
+                                             dimNodeSignals=[F, 4, 1], nFilterTaps=[3, 3], nSelectedNodes=[N, N],
+                                             poolingFunction=gml.NoPool, poolingSize=[1, 1])
+
+    def build_sel():
+        torch.manual_seed(0)
+        return archs.SelectionGNN([1, 5, 3], [3, 2], True, torch.nn.Tanh, [N, N], gml.NoPool, [1, 1], [2], S)
+
+    ref_a = _fwd_bwd(build_gcrnn_gnn(), x, torch.zeros(B, F, N), y, l1)
+    sel_ref = build_sel()
+    xs = torch.randn(7, 1, N, generator=g)
+    ys_ref = sel_ref(xs); ys_ref.square().sum().backward()
+    gref = {k: p.grad.double() for k, p in sel_ref.named_parameters()}
+    gg.install(gml, archs)
+    try:
+        net = build_gcrnn_gnn()
+        assert type(net.outputNN[0].GFL[0]).__module__.startswith('gated_gcrnns_b200')      # the readout filters are ours
+        net.to(DEV)
+        ours_a = _fwd_bwd(net, x.to(DEV), torch.zeros(B, F, N), y.to(DEV), l1)
+        sel = build_sel()
+        sel.to(DEV)
+        ys = sel(xs.to(DEV)); ys.square().sum().backward()
+        gour = {k: p.grad.double().cpu() for k, p in sel.named_parameters()}
+    finally:
+        gg.uninstall(gml, archs)
+    _compare(ref_a, ours_a)
+    assert (ys.detach().cpu() - ys_ref.detach()).abs().max() <= 1e-5 * max(1.0, ys_ref.abs().max())
+    for k in gref:
+        assert (gref[k] - gour[k]).abs().max() <= 2e-4 * gref[k].abs().max(), k
