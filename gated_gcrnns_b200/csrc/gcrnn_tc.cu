@@ -423,7 +423,8 @@ size_t cell_backward_tc(const gcrnn_cell* cell, const gcrnn_cell_params* p, cons
   __nv_bfloat16* hb0 = a.get<__nv_bfloat16>((size_t)d.R * d.LD);
   __nv_bfloat16* WTb = a.get<__nv_bfloat16>(wbuf);
   float* part = a.get<float>((size_t)max_sms * d.Kst * d.F * d.F);
-  const bool fused = opt().bwd_fused && d.F == 64 && d.Kin * d.G <= 8 && d.Kst <= 6 && d.N % 128 == 0 && bf_stages(P, d.Kst) >= 2;
+  const bool fused = opt().bwd_fused && d.F == 64 && d.Kin * d.G <= (P > 1 ? 7 : 8) && d.Kst <= 6 && d.N % 128 == 0 && bf_stages(P, d.Kst) >= 2;
+  const int zs_split = P > 1;       // Zs tiles carry hi rows 0..7 and residual rows 8..15
   __nv_bfloat16* Zs = fused ? a.get<__nv_bfloat16>((size_t)d.BT * BF_ZROWS * d.N) : nullptr;
   float* partA = fused ? a.get<float>((size_t)max_sms * 64 * BF_ZROWS) : nullptr;
   float* zslab = cell->dh_last_only ? a.get<float>((size_t)d.F * d.N) : nullptr;
@@ -484,7 +485,7 @@ size_t cell_backward_tc(const gcrnn_cell* cell, const gcrnn_cell_params* p, cons
   if (fused) {
     CUDA_OK(cudaMemsetAsync(partA, 0, (size_t)d.sms * 64 * BF_ZROWS * sizeof(float), st));
     zs_build_kernel<<<148 * 8, 256, 0, st>>>(X, s.zx, d.RX * d.N, d.G, d.Kin * d.G, d.tg ? s.gt : nullptr, d.tg ? s.gt + d.BT : nullptr,
-                                              Zs, d.BT, d.N);
+                                              Zs, d.BT, d.N, zs_split);
     launched();
   }
   for (long long t = d.T - 1; t >= 0; --t) {
@@ -539,7 +540,7 @@ size_t cell_backward_tc(const gcrnn_cell* cell, const gcrnn_cell_params* p, cons
   }
   wgrad_flush(gr->weight_B);
   if (fused) {
-    dax_reduce_kernel<<<(64 * BF_ZROWS + 255) / 256, 256, 0, st>>>(partA, gr->weight_A, gr->bias, d.sms, d.Kin * d.G);
+    dax_reduce_kernel<<<(64 * BF_ZROWS + 255) / 256, 256, 0, st>>>(partA, gr->weight_A, gr->bias, d.sms, d.Kin * d.G, zs_split);
     launched();
   }
 

@@ -323,15 +323,19 @@ bwd_fused_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
 
 // Zs[(b*T + t)*16 + j][n] (bf16): j < KG: (gi/gf)[b,t] * (x_t S^k)[b,g,n];  j == KG: (gi/gf)[b,t] + 1;  else 0.
 // With v_0 = bf16(gf dpre):  sum_n v_0 Zs_j = gi <dpre, z_j>  (-> dA)  and  (gi + gf) sum_n dpre  (-> dbias).
+// split == 1 (split-bf16 mode, KG <= 7): rows 8 + j hold the bf16 RESIDUAL of row j, so the tile carries both planes of Zs in
+// its 16 rows and MMA3 returns the hi and lo partial products in columns j and 8 + j (summed by dax_reduce_kernel).
 __global__ void zs_build_kernel(const float* __restrict__ X, const float* __restrict__ zx, long long zx_kstride, int G, int KG,
                                 const float* __restrict__ gi, const float* __restrict__ gf, __nv_bfloat16* __restrict__ Zs,
-                                long long BT, int N) {
+                                long long BT, int N, int split) {
   const int N8 = N / 8;
   const long long total = BT * BF_ZROWS * N8;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % N8);
-    const int j = (int)((i / N8) % BF_ZROWS);
+    const int jr = (int)((i / N8) % BF_ZROWS);
     const long long bt = i / ((long long)N8 * BF_ZROWS);
+    const bool lo = split && jr >= 8;
+    const int j = lo ? jr - 8 : jr;
     const float vgi = gi ? gi[bt] : 1.f, vgf = gf ? gf[bt] : 1.f;
     const float ratio = vgi / fmaxf(vgf, 1e-30f);
     float o[8];
@@ -348,22 +352,26 @@ __global__ void zs_build_kernel(const float* __restrict__ X, const float* __rest
       for (int e = 0; e < 8; ++e) o[e] = cst;
     }
     uint4 u;
-    __nv_bfloat162 q0 = __floats2bfloat162_rn(o[0], o[1]), q1 = __floats2bfloat162_rn(o[2], o[3]);
-    __nv_bfloat162 q2 = __floats2bfloat162_rn(o[4], o[5]), q3 = __floats2bfloat162_rn(o[6], o[7]);
-    u.x = *reinterpret_cast<uint32_t*>(&q0); u.y = *reinterpret_cast<uint32_t*>(&q1);
-    u.z = *reinterpret_cast<uint32_t*>(&q2); u.w = *reinterpret_cast<uint32_t*>(&q3);
+    u.x = pack_bf16x2(o[0], o[1]); u.y = pack_bf16x2(o[2], o[3]); u.z = pack_bf16x2(o[4], o[5]); u.w = pack_bf16x2(o[6], o[7]);
+    if (lo) {
+      bf16x2_residual(u.x, o[0], o[1]); bf16x2_residual(u.y, o[2], o[3]); bf16x2_residual(u.z, o[4], o[5]); bf16x2_residual(u.w, o[6], o[7]);
+      u.x = pack_bf16x2(o[0], o[1]); u.y = pack_bf16x2(o[2], o[3]); u.z = pack_bf16x2(o[4], o[5]); u.w = pack_bf16x2(o[6], o[7]);
+    }
     reinterpret_cast<uint4*>(Zs)[i] = u;
   }
 }
 
-// dA[f, kg] += sum_cta partA[cta][f][kg] (kg < KG);  dbias[f] += sum_cta partA[cta][f][KG]
-__global__ void dax_reduce_kernel(const float* __restrict__ partA, float* dA, float* dbias, int ncta, int KG) {
+// dA[f, kg] += sum_cta partA[cta][f][kg] (kg < KG);  dbias[f] += sum_cta partA[cta][f][KG]   (+ columns 8 + j when split)
+__global__ void dax_reduce_kernel(const float* __restrict__ partA, float* dA, float* dbias, int ncta, int KG, int split) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 64 * BF_ZROWS) return;
   const int f = i / BF_ZROWS, j = i % BF_ZROWS;
   if (j > KG) return;
   float s = 0.f;
-  for (int c = 0; c < ncta; ++c) s += partA[(size_t)c * 64 * BF_ZROWS + i];
+  for (int c = 0; c < ncta; ++c) {
+    s += partA[(size_t)c * 64 * BF_ZROWS + i];
+    if (split) s += partA[(size_t)c * 64 * BF_ZROWS + i + 8];
+  }
   if (j < KG) { if (dA) dA[(size_t)f * KG + j] += s; }
   else if (dbias) dbias[f] += s;
 }

@@ -88,7 +88,7 @@ def _adj_p():
     """The seismograph graph of epicenterEstimation.py (Adj.p / |lambda|max), from the committed golden fixture."""
     import os
     z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'cell_cfg2_node.npz'), allow_pickle=False)
-    return np.asarray(z['S'], dtype=np.float64).reshape(59, 59)
+    return np.asarray(z['S'], dtype=np.float32).reshape(59, 59)      # fp32: both sides run in the default dtype
 
 
 def _fwd_bwd(net, x, h0, target, loss_fn):
