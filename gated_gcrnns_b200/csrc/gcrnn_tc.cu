@@ -6,6 +6,7 @@
 #include "tc_tap.cuh"
 #include "tc_gate.cuh"
 #include "tc_bwd.cuh"
+#include "tc_hshift.cuh"
 #include <cstdlib>
 #include <cmath>
 #include <algorithm>
@@ -35,6 +36,20 @@ CUtensorMap make_tmap_bf16(const void* base, long long rows, long long cols, int
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   GCRNN_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) for [%lld x %lld] at %p", (int)r, rows, cols, base);
+  return tm;
+}
+
+// 2-D bf16 row-major [rows, cols] tensor, box = [box_rows, box_cols], NO swizzle (plain row-major shared-memory tile)
+CUtensorMap make_tmap_bf16_plain(const void* base, long long rows, long long cols, int box_cols, int box_rows) {
+  CUtensorMap tm;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = encode_fn()(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  GCRNN_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (plain) failed (%d) for [%lld x %lld] at %p", (int)r, rows, cols, base);
   return tm;
 }
 
@@ -260,6 +275,29 @@ static void launch_bwd_fused(const TcDims& d, BwdFusedArgs a, const __nv_bfloat1
   launched();
 }
 
+// one Horner stage (tc_hshift.cuh): out = Zin S + (I (x) W_k) hprev  [+ the state update when `fin` is set]
+static void launch_hshift(const gcrnn_graph* g, const TcDims& d, const __nv_bfloat16* Zin, const __nv_bfloat16* hprev, const __nv_bfloat16* Wk,
+                          __nv_bfloat16* out, const HShiftArgs* fin, cudaStream_t st) {
+  HShiftArgs a{};
+  if (fin) a = *fin;
+  a.M = (int)d.R; a.N = d.N; a.P = d.P; a.scale = g->dense_scale; a.final_stage = fin != nullptr; a.wcol = 0; a.wpstride = 64; a.exact = d.P > 1;
+  a.segs = ShiftSegs{};
+  for (int q = 0; q < d.P; ++q) { a.segs.a[a.segs.n] = q; a.segs.b[a.segs.n] = 0; ++a.segs.n; }
+  if (d.P > 1 && g->s_planes > 1) { a.segs.a[a.segs.n] = 0; a.segs.b[a.segs.n] = 1; ++a.segs.n; }
+  const CUtensorMap tmS = make_tmap_bf16(g->St_bf16, (long long)g->s_planes * d.N, d.N, 128);
+  const CUtensorMap tmZ = make_tmap_bf16(Zin, d.R, d.LD, 128);
+  const CUtensorMap tmH = make_tmap_bf16(hprev, d.R, d.LD, 64);
+  const CUtensorMap tmW = make_tmap_bf16(Wk, 64, (long long)d.P * 64, 32);
+  const CUtensorMap tmO = make_tmap_bf16_plain(out, d.R, d.LD, 128, 16);
+  static DeviceOnce once;
+  if (once.first()) CUDA_OK(cudaFuncSetAttribute(hshift_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HS_SMEM));
+  const int tiles = (int)((d.R + 255) / 256) * (d.N / 256);
+  int pairs = d.sms / 2;
+  if (tiles < pairs) pairs = tiles;
+  hshift_kernel<<<2 * pairs, HS_THREADS, HS_SMEM, st>>>(tmS, tmZ, tmH, tmW, tmO, a);
+  launched();
+}
+
 template <int KG, bool EX>
 static void gate_launch_kg_ex(bool bwd, const GateArgs& ga, int grid, size_t sm, cudaStream_t st) {
   if (!bwd) {
@@ -354,6 +392,11 @@ size_t cell_forward_tc(const gcrnn_cell* cell, const gcrnn_cell_params* p, const
   __nv_bfloat16* Wb = a.get<__nv_bfloat16>(weight_elems(d.F, d.Kst, P));
   float* c0 = d.tg ? a.get<float>((size_t)d.R * d.N) : nullptr;
   float* logit = d.tg ? a.get<float>(2 * d.BT) : nullptr;
+  // Horner-form forward (tc_hshift.cuh): the state filter's tap contraction rides in the shift GEMMs
+  const bool hfused = opt().fwd_fused && d.F == 64 && d.N % 256 == 0 && d.Kin * d.G <= 8 && d.Kst >= 2;
+  __nv_bfloat16* wping = hfused ? a.get<__nv_bfloat16>((size_t)d.R * d.LD) : nullptr;
+  __nv_bfloat16* wpong = hfused ? a.get<__nv_bfloat16>((size_t)d.R * d.LD) : nullptr;
+  __nv_bfloat16* Wtaps = hfused ? a.get<__nv_bfloat16>((size_t)d.Kst * 64 * P * 64) : nullptr;     // [K][64][P*64]
   if (a.dry()) return a.off;
   d.sms = num_sms(g->device);
   const long long FN = (long long)d.F * d.N, GN = (long long)d.G * d.N;
@@ -386,6 +429,33 @@ size_t cell_forward_tc(const gcrnn_cell* cell, const gcrnn_cell_params* p, const
     }
   }
   // ---- the recurrence -------------------------------------------------------------------------------------------
+  if (hfused) {
+    // Horner: w_{K-1} = B_{K-1} h ; w_k = B_k h + w_{k+1} S ; h_t = tanh(gi (A(S)x_t + b) + gf (w_0 + b)).
+    // Tap K-1 seeds the chain unscaled (tap kernel, MIX epilogue); taps 0..K-2 enter the shift GEMMs divided by the operator scale.
+    for (int k = 0; k < d.Kst; ++k) {
+      prep_tap_weight_kernel<<<(64 * 64 + 255) / 256, 256, 0, st>>>(p->weight_B, Wtaps + (size_t)k * 64 * P * 64, 64, d.Kst, k, P,
+                                                                    k == d.Kst - 1 ? 1.f : 1.f / g->dense_scale);
+      launched();
+    }
+    for (long long t = 0; t < d.T; ++t) {
+      const __nv_bfloat16* hprev = t == 0 ? hb0 : s.Hb + (size_t)(t - 1) * d.R * d.LD;
+      ContractArgs cm{};
+      cm.K = 1; cm.C = d.F; cm.M = d.F; cm.N = d.N; cm.B = d.B; cm.P = P; cm.slab[0] = hprev; cm.out_bf16 = wping;
+      launch_tap<TAP_MIX>(cm, Wtaps + (size_t)(d.Kst - 1) * 64 * P * 64, d.sms, st);
+      __nv_bfloat16* cur = wping; __nv_bfloat16* nxt = wpong;
+      for (int k = d.Kst - 2; k >= 1; --k) {
+        launch_hshift(g, d, cur, hprev, Wtaps + (size_t)k * 64 * P * 64, nxt, nullptr, st);
+        std::swap(cur, nxt);
+      }
+      HShiftArgs fa{};
+      fa.H = H + t * FN; fa.H_bstride = d.T * FN; fa.bias = p->bias;
+      fa.gi = d.tg ? s.gt + t : nullptr; fa.gf = d.tg ? s.gt + d.BT + t : nullptr; fa.gate_stride = d.T;
+      fa.A = p->weight_A; fa.KG = d.Kin * d.G; fa.G = d.G;
+      fa.x0 = X + t * GN; fa.zx = s.zx + t * GN; fa.zx_kstride = d.RX * d.N; fa.z_bstride = d.T * GN;
+      launch_hshift(g, d, cur, hprev, Wtaps, s.Hb + (size_t)t * d.R * d.LD, &fa, st);
+    }
+    return a.off;
+  }
   prep_contract_weight(p->weight_B, Wb, d.F, d.Kst, 0, P, st);
   for (long long t = 0; t < d.T; ++t) {
     const __nv_bfloat16* hprev = t == 0 ? hb0 : s.Hb + (size_t)(t - 1) * d.R * d.LD;

@@ -1,0 +1,281 @@
+// Horner-form forward step on tcgen05 (sm_100a, CTA pairs): the tap contraction of the state filter fused INTO the shift GEMMs.
+//
+// Reference: r = sum_k B_k (h S^k) + b  (Utils/graphML.py:117-139 inside GGCRNNCell.forward :2402-2423).  The feature mix B_k acts
+// on rows, the shift S on columns, so they commute and Horner's rule applies:
+//     w_{K-1} = B_{K-1} h ;   w_k = B_k h + w_{k+1} S   (k = K-2 .. 0) ;   r = w_0 + b.
+// One launch of this kernel is one Horner stage  OUT = Z S + (I_B (x) W) h  for all samples:
+//   * the accumulator is TRANSPOSED w.r.t. tc_gemm2.cuh: TMEM lane = NODE, TMEM column = signal row (b, f).  The main product
+//     D[n, (b,f)] = sum_m S^T[n, m] Z[(b,f), m] therefore has the operator tile as the MMA "A" operand (M = 256 nodes per CTA
+//     pair) and the signal tile as the "B" operand (N = 256 rows = 4 samples x 64 features), both plain K-major SW128 tiles;
+//   * the per-sample mix  D[n, (b, f)] += sum_f' h[b, f', n] W[f, f']  is then an M = 256, N = 64, K = 64 product per sample
+//     with the h tile as an MN-major A operand (node contiguous, exactly the operand form of tc_tap.cuh) and W K-major:
+//     no block-diagonal padding, +6 % tensor work per operand-plane term instead of a separate HBM-bound kernel that re-reads
+//     every chain slab;
+//   * split-bf16 operands (tc_gemm.cuh "planes"): main products K-concatenated over (signal plane, operator plane), mix products
+//     over (h plane q, weight plane w) with q + w < P; the operator is stored as S / scale, so the mix weights are W / scale
+//     and the epilogue multiplies the whole accumulator by scale;
+//   * epilogue (8 warps, thread <-> node): intermediate stages split the fp32 accumulator into bf16 planes, staged as
+//     [16 signal rows][128 nodes] tiles by the four node-quarter warps of a column group and written with TMA bulk stores; the
+//     LAST stage (k = 0) adds the input filter A(S)x_t, bias and time gates, applies tanh and writes H[b,t] (fp32) and the bf16
+//     planes of the new state — the state update of tc_tap.cuh's TAP_FWD epilogue.
+// Structure per CTA (320 threads): warp 0 TMA producer, warp 1 MMA issuer (leader CTA) + TMEM allocator, warps 2..9 epilogue;
+// 6-stage ring of 32 KB stages shared by main and mix loads, 2 TMEM accumulator stages (512 columns).
+#pragma once
+#include "tc_gemm2.cuh"
+#include "tc_tap.cuh"
+
+namespace gcrnn {
+namespace tc {
+
+constexpr int HS_THREADS = 64 + 8 * 32;
+constexpr int HS_STAGES = 6;
+constexpr int HS_OUT_BYTES = 2 * 2 * 4096;            // 2 column groups x 2 buffers x [16 rows][128 nodes] bf16
+constexpr int HS_W_BYTES = MAX_PLANES * 4096;         // this CTA's 32 weight rows x 64 columns per plane
+constexpr int HS_SMEM = HS_STAGES * G2_STAGE_BYTES + HS_OUT_BYTES + HS_W_BYTES + 256 + (64 * 8 + 64) * 4 + 8 * 8 + 1024;
+
+struct HShiftArgs {
+  int M, N;                       // signal rows (B * 64), nodes
+  ShiftSegs segs;                 // main products: a = signal plane, b = operator plane
+  int P;                          // planes of the signal in / out, of h and of the weights
+  float scale;                    // operator scale (the bf16 operator holds S / scale)
+  int final_stage;                // 0: write the planes of w_k; 1: state update (k = 0)
+  int wcol;                       // column of W_k's plane 0 in the prepared weight matrix (plane q at wcol + q * wpstride)
+  int wpstride;
+  int exact;
+  // final stage (time step t): operands of the TAP_FWD epilogue
+  float* H; long long H_bstride;                   // fp32 h_t[b] = H + b * H_bstride, [64][N]
+  const float* bias;
+  const float* gi; const float* gf; long long gate_stride;
+  const float* A; int KG, G;                       // input taps [64][KG]
+  const float* x0; const float* zx; long long zx_kstride, z_bstride;
+};
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(HS_THREADS, 1)
+hshift_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmH,
+              const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmO, const HShiftArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sOut = smem + HS_STAGES * G2_STAGE_BYTES;                 // [2 groups][2 buffers][16 rows][256 B]
+  uint8_t* sW = sOut + HS_OUT_BYTES;                                 // [P][32 rows][128 B] SW128
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sW + HS_W_BYTES);
+  uint64_t* empty_bar = full_bar + HS_STAGES;
+  uint64_t* tmem_full = empty_bar + HS_STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint64_t* w_bar = tmem_empty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
+  float* sAw = reinterpret_cast<float*>(tmem_slot + 4);              // [64][KG] input-filter taps (final stage)
+  float* sBias = sAw + 64 * 8;                                       // [64]
+  const float** sZb = reinterpret_cast<const float**>(sBias + 64);   // [8] base pointer of input row (k, g): X or zx slab
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int tiles_nodes = a.N / 256;
+  const int tiles_rows = (a.M + 255) / 256;
+  const int num_tiles = tiles_rows * tiles_nodes;
+  const int num_k = a.N / BK;
+  const int NS = 4;                                                  // samples (64-row blocks) per tile
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmS); tma_prefetch_desc(&tmZ); tma_prefetch_desc(&tmH); tma_prefetch_desc(&tmW); tma_prefetch_desc(&tmO);
+    for (int s = 0; s < HS_STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tmem_full + s, 1); mbar_init(tmem_empty + s, 16); }   // 8 epilogue warps x 2 CTAs
+    mbar_init(w_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc2(tmem_slot, 512);
+  if (a.final_stage) {
+    for (int i = threadIdx.x; i < 64 * a.KG; i += HS_THREADS) sAw[i] = a.A[i];
+    for (int kg = threadIdx.x; kg < a.KG; kg += HS_THREADS) {
+      const int k = kg / a.G, g = kg % a.G;
+      sZb[kg] = (k == 0 ? a.x0 : a.zx + (size_t)(k - 1) * a.zx_kstride) + (size_t)g * a.N;
+    }
+    for (int i = threadIdx.x; i < 64; i += HS_THREADS) sBias[i] = a.bias ? a.bias[i] : 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                 // both CTAs' barriers are initialised before any remote arrive / TMA signal
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs): own 128 nodes of the operator, own half of the signal rows, own nodes of h =====
+    if (lane == 0) {
+      if (rank == 0) mbar_expect_tx(w_bar, (uint32_t)(2 * a.P * 4096));          // weight rows of BOTH CTAs
+      for (int q = 0; q < a.P; ++q) tma_load_2d_pair(sW + q * 4096, &tmW, w_bar, a.wcol + q * a.wpstride, (int)rank * 32);
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += npairs) {
+        const int r0 = (tile / tiles_nodes) * 256;                               // first signal row of the tile
+        const int n0 = (tile % tiles_nodes) * 256 + (int)rank * 128;             // this CTA's first node
+        for (int sg = 0; sg < a.segs.n; ++sg) {
+          const int zcol = a.segs.a[sg] * a.N, srow = a.segs.b[sg] * a.N + n0;
+          for (int kb = 0; kb < num_k; ++kb) {
+            mbar_wait(empty_bar + stage, phase ^ 1);
+            uint8_t* sa = smem + stage * G2_STAGE_BYTES;
+            if (rank == 0) mbar_expect_tx(full_bar + stage, 2 * G2_STAGE_BYTES);
+            tma_load_2d_pair(sa, &tmS, full_bar + stage, kb * BK, srow);
+            tma_load_2d_pair(sa + G2_HALF_BYTES, &tmZ, full_bar + stage, zcol + kb * BK, r0 + (int)rank * 128);
+            if (++stage == HS_STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+        for (int s = 0; s < NS; ++s) {                                           // h tiles of the tile's four samples
+          for (int q = 0; q < a.P; ++q) {
+            mbar_wait(empty_bar + stage, phase ^ 1);
+            uint8_t* sa = smem + stage * G2_STAGE_BYTES;
+            if (rank == 0) mbar_expect_tx(full_bar + stage, 2 * G2_HALF_BYTES);
+            tma_load_2d_pair(sa, &tmH, full_bar + stage, q * a.N + n0, r0 + 64 * s);            // rows >= M: zero filled
+            tma_load_2d_pair(sa + 8192, &tmH, full_bar + stage, q * a.N + n0 + 64, r0 + 64 * s);
+            if (++stage == HS_STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: one thread of the leader CTA drives both tensor cores =====
+    if (rank == 0 && lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(256, 256);
+      constexpr uint32_t idesc_mix = make_idesc_bf16_amn(256, 64);
+      mbar_wait(w_bar, 0);
+      tc_fence_after();
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += npairs) {
+        mbar_wait(tmem_empty + acc, acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256);
+        const int total_k = a.segs.n * num_k;
+        for (int kb = 0; kb < total_k; ++kb) {
+          mbar_wait(full_bar + stage, phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * G2_STAGE_BYTES);
+          const uint64_t adesc = make_kmajor_sw128_desc(sa);
+          const uint64_t bdesc = make_kmajor_sw128_desc(sa + G2_HALF_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k)
+            umma_f16_pair(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+          umma_commit_pair(empty_bar + stage);
+          if (++stage == HS_STAGES) { stage = 0; phase ^= 1; }
+        }
+        for (int s = 0; s < NS; ++s) {
+          for (int q = 0; q < a.P; ++q) {
+            mbar_wait(full_bar + stage, phase);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + stage * G2_STAGE_BYTES);
+            for (int w = 0; w + q < a.P; ++w) {
+              const uint64_t bdesc0 = make_kmajor_sw128_desc(smem_u32(sW + w * 4096));
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {                                      // 64 contraction rows f' in steps of 16
+                const uint64_t adesc = make_mnmajor_sw128_desc(sa + j * 2048, 8192);
+                umma_f16_pair(d_tmem + (uint32_t)(64 * s), adesc, bdesc0 + (uint64_t)(2 * j), idesc_mix, 1u);
+              }
+            }
+            umma_commit_pair(empty_bar + stage);
+            if (++stage == HS_STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+        umma_commit_pair(tmem_full + acc);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===== epilogue warps 2..9: node quarter q = warp % 4 (TMEM lanes), column group g = (warp - 2) / 4 (128 columns) =====
+    const int q = warp & 3;
+    const int g = (warp - 2) >> 2;
+    const int gt = threadIdx.x - 64 - g * 128;                     // 0..127 within the column group
+    const bool elected = (q == ((2 + 4 * g) & 3)) && lane == 0;     // first warp of the group
+    uint8_t* gout = sOut + g * 8192;
+    int ob = 0;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = pair; tile < num_tiles; tile += npairs) {
+      const int r0 = (tile / tiles_nodes) * 256;
+      const int n0 = (tile % tiles_nodes) * 256 + (int)rank * 128;
+      const int nl = q * 32 + lane;                                 // node within this CTA's 128
+      const int n = n0 + nl;
+      mbar_wait(tmem_full + acc, acc_phase);
+      tc_fence_after();
+      const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256 + g * 128);
+      float z[8];
+      float vgi = 1.f, vgf = 1.f;
+#pragma unroll 1
+      for (int c = 0; c < 8; ++c) {                                 // 16 accumulator columns = 16 signal rows (one sample, 16 features)
+        const int row0 = r0 + g * 128 + c * 16;                     // first signal row (b * 64 + f) of the chunk
+        const long long b = row0 >> 6;
+        const int f0 = row0 & 63;
+        const bool live = row0 < a.M;
+        if (a.final_stage && (c & 3) == 0 && live) {                // new sample: gates and the node's input-filter rows
+          if (a.gi) vgi = __ldg(a.gi + b * a.gate_stride);
+          if (a.gf) vgf = __ldg(a.gf + b * a.gate_stride);
+          const size_t zo = (size_t)b * a.z_bstride + n;
+#pragma unroll
+          for (int kg = 0; kg < 8; ++kg) z[kg] = kg < a.KG ? __ldg(sZb[kg] + zo) : 0.f;
+        }
+        float v[16];
+        tmem_ld16(t0 + (uint32_t)(c * 16), v);
+        if (c == 7) {                                               // accumulator fully read: hand the TMEM stage back early
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_leader(tmem_empty + acc);
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] *= a.scale;
+        if (a.final_stage) {
+          const float gsum = vgi + vgf;
+          float* of = a.H + b * a.H_bstride + (size_t)f0 * a.N + n;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float* aw = sAw + (f0 + i) * a.KG;
+            float ax = 0.f;
+#pragma unroll
+            for (int kg = 0; kg < 8; ++kg) if (kg < a.KG) ax = fmaf(aw[kg], z[kg], ax);
+            const float pre = fmaf(vgi, ax, fmaf(vgf, v[i], gsum * sBias[f0 + i]));       // gi (ax + b) + gf (r + b)
+            const float h = a.exact ? tanh_acc(pre) : tap_tanh(pre);
+            if (live) of[(size_t)i * a.N] = h;
+            v[i] = h;
+          }
+        }
+        for (int pl = 0; pl < a.P; ++pl) {                          // plane 0 = bf16(v), plane 1 = bf16(v - plane 0)
+          if (elected) tma_store_wait_read<1>();                    // the store that last used this staging buffer has read it
+          named_bar_sync(1 + g, 128);
+          __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(gout + ob * 4096) + nl;      // [16 rows][128 nodes]
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const __nv_bfloat16 hi = __float2bfloat16(v[i]);
+            dst[i * 128] = hi;
+            if (pl + 1 < a.P) v[i] -= __bfloat162float(hi);
+          }
+          fence_proxy_async();
+          named_bar_sync(3 + g, 128);
+          if (elected) {
+            tma_store_2d(&tmO, gout + ob * 4096, pl * a.N + n0, row0);                       // rows >= M are clipped by the TMA unit
+            tma_store_commit();
+          }
+          ob ^= 1;
+        }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (elected) tma_store_wait_all();
+    (void)gt;
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                 // the peer may still be reading this CTA's shared memory / signalling its barriers
+  if (warp == 1) { tc_fence_after(); tmem_dealloc2(tmem_base, 512); }
+}
+
+// W[f, k, g] fp32 (the reference's weight_B[f, 0, k, g]) -> bf16 planes of ONE tap divided by `scale`:
+// out[f][q * 64 + g], row length P * 64
+__global__ void prep_tap_weight_kernel(const float* __restrict__ W, __nv_bfloat16* __restrict__ out, int F, int K, int k, int P, float inv_scale) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= F * F) return;
+  const int g = i % F, f = i / F;
+  store_planes(out + (size_t)f * P * F + g, F, P, W[((size_t)f * K + k) * F + g] * inv_scale);
+}
+
+}  // namespace tc
+}  // namespace gcrnn

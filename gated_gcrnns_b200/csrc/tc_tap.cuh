@@ -23,7 +23,8 @@ constexpr int TAP_STAGE_BYTES = 2 * 64 * 128;
 constexpr int TAP_MAX_KB = 6;      // K*C <= 384 contraction rows
 constexpr int TAP_THREADS = 64 + 16 * 32;   // TMA warp + MMA warp + 16 epilogue warps
 
-enum { TAP_PLAIN = 0, TAP_FWD = 1, TAP_BWD = 2, TAP_BWDF = 3 };   // BWDF: BWD fused with the next step's dpre
+enum { TAP_PLAIN = 0, TAP_FWD = 1, TAP_BWD = 2, TAP_BWDF = 3, TAP_MIX = 4 };   // BWDF: BWD fused with the next step's dpre;
+                                                                             // MIX: bf16 planes of the plain product (Horner seed w_{K-1} = B_{K-1} h)
 
 struct TapArgs {
   int K, C, M, N, KB;              // slabs, channels per slab, output features, nodes, ceil(K*C/64)
@@ -270,6 +271,11 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__
         if (EPI == TAP_PLAIN) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) of[(size_t)i * a.N] = v[i] + a.bias_scale * sBias[m0 + i];
+        } else if (EPI == TAP_MIX) {
+          const long long ldo = (long long)a.P * a.N;
+          __nv_bfloat16* ob = a.out_bf16 + ((size_t)b * a.M + m0) * ldo + n;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) store_planes(ob + (size_t)i * ldo, a.N, a.P, v[i]);
         } else if (EPI == TAP_FWD) {
           const long long ldo = (long long)a.P * a.N;          // bf16 row = P planes of N
           __nv_bfloat16* ob = a.out_bf16 + ((size_t)b * a.M + m0) * ldo + n;

@@ -205,6 +205,40 @@ def test_tc_fused_backward_step_matches_unfused(prec, tg, N, K, T, B, G):
     assert all(v < (1e-2 if prec == 'bf16' else 2e-3) for v in errs.values()), errs
 
 
+@pytest.mark.parametrize('prec', ['bf16', 'bf16x2'])
+@pytest.mark.parametrize('tg', [False, True])
+@pytest.mark.parametrize('N,K,T,B,G,weighted', [(512, 5, 4, 6, 1, False), (256, 4, 3, 5, 2, False), (1024, 2, 2, 3, 1, False),
+                                               (256, 3, 3, 9, 1, True), (1024, 5, 3, 4, 1, True)])
+def test_tc_horner_forward_matches_unfused(prec, tg, N, K, T, B, G, weighted):
+    """F = 64: the Horner-form forward (tap contraction inside the shift GEMMs, tc_hshift.cuh) against the chain + tap-kernel
+    forward, same operand precision.  The two round different intermediates (w_k = B_k h + w_{k+1} S vs z_k = z_{k-1} S), so they
+    agree to the mode's own rounding level: 3e-2 of max|ref| (bf16), 3e-4 (bf16x2) on H and on every gradient except the
+    state-tap weight gradient (plane-0 products, see TC_TOL).  B not a multiple of 4 exercises the clipped last row tile."""
+    F = 64
+    S = _weighted_dense(N, seed=3) if weighted else gg.graphs.dense_random(N, 0.3, seed=4)
+    torch.manual_seed(6)
+    X, h0, dH = torch.randn(B, T, G, N, device=DEV), 0.3 * torch.randn(B, F, N, device=DEV), torch.randn(B, T, F, N, device=DEV)
+    out = {}
+    old = _set_opt('fwd_fused', 1)
+    try:
+        for fused in (0, 1):
+            _set_opt('fwd_fused', fused)
+            cell = _make_cell(S, G, F, K, tg, prec)
+            hh = h0.clone().requires_grad_(True)
+            H = cell(X, hh)
+            (H * dH).sum().backward()
+            out[fused] = (H.detach(), {k: v.grad for k, v in cell.named_parameters()}, hh.grad)
+    finally:
+        _set_opt('fwd_fused', old)
+        gg.set_precision('fp32')
+    errs = {'H': _relerr(out[1][0], out[0][0]), 'dh0': _relerr(out[1][2], out[0][2])}
+    errs.update(_grad_errs(out[1][1], out[0][1]))
+    _log(f'tc-horner-vs-chain {prec}', dict(tg=tg, N=N, K=K, T=T, B=B, G=G, weighted=weighted), {k: f'{v:.2e}' for k, v in errs.items()})
+    tol = 3e-2 if prec == 'bf16' else 3e-4
+    assert errs['H'] < tol, errs
+    assert all(v < (tol if 'weight_B' not in k else max(tol, 5e-3)) for k, v in errs.items()), errs
+
+
 def _weighted_dense(N, seed=0):
     """cfg3-like graph with edge weights (Adj.p-like: the operator is NOT exactly representable in bf16)."""
     S = gg.graphs.dense_random(N, 0.3, seed=seed)[0].double()
