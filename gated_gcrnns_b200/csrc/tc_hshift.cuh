@@ -14,10 +14,12 @@
 //   * split-bf16 operands (tc_gemm.cuh "planes"): main products K-concatenated over (signal plane, operator plane), mix products
 //     over (h plane q, weight plane w) with q + w < P; the operator is stored as S / scale, so the mix weights are W / scale
 //     and the epilogue multiplies the whole accumulator by scale;
-//   * epilogue (8 warps, thread <-> node): intermediate stages split the fp32 accumulator into bf16 planes, staged as
-//     [16 signal rows][128 nodes] tiles by the four node-quarter warps of a column group and written with TMA bulk stores; the
-//     LAST stage (k = 0) adds the input filter A(S)x_t, bias and time gates, applies tanh and writes H[b,t] (fp32) and the bf16
-//     planes of the new state — the state update of tc_tap.cuh's TAP_FWD epilogue.
+//   * epilogue (8 warps, thread <-> node): intermediate stages split the fp32 accumulator into bf16 planes and store them
+//     directly — for one signal row a warp writes 32 consecutive nodes = 64 contiguous bytes (two full sectors; a first version
+//     staged [16 rows][128 nodes] tiles for TMA bulk stores and was bound by the store's read-completion latency with two
+//     buffers per column group: 548 us vs 333 us for the plain GEMM); the LAST stage (k = 0) adds the input filter A(S)x_t,
+//     bias and time gates, applies tanh and writes H[b,t] (fp32) and the bf16 planes of the new state — the state update of
+//     tc_tap.cuh's TAP_FWD epilogue.
 // Structure per CTA (320 threads): warp 0 TMA producer, warp 1 MMA issuer (leader CTA) + TMEM allocator, warps 2..9 epilogue;
 // 6-stage ring of 32 KB stages shared by main and mix loads, 2 TMEM accumulator stages (512 columns).
 #pragma once
@@ -29,9 +31,8 @@ namespace tc {
 
 constexpr int HS_THREADS = 64 + 8 * 32;
 constexpr int HS_STAGES = 6;
-constexpr int HS_OUT_BYTES = 2 * 2 * 4096;            // 2 column groups x 2 buffers x [16 rows][128 nodes] bf16
 constexpr int HS_W_BYTES = MAX_PLANES * 4096;         // this CTA's 32 weight rows x 64 columns per plane
-constexpr int HS_SMEM = HS_STAGES * G2_STAGE_BYTES + HS_OUT_BYTES + HS_W_BYTES + 256 + (64 * 8 + 64) * 4 + 8 * 8 + 1024;
+constexpr int HS_SMEM = HS_STAGES * G2_STAGE_BYTES + HS_W_BYTES + 256 + (64 * 8 + 64) * 4 + 8 * 8 + 1024;
 
 struct HShiftArgs {
   int M, N;                       // signal rows (B * 64), nodes
@@ -42,6 +43,7 @@ struct HShiftArgs {
   int wcol;                       // column of W_k's plane 0 in the prepared weight matrix (plane q at wcol + q * wpstride)
   int wpstride;
   int exact;
+  __nv_bfloat16* out;             // [M][P * N] bf16 planes of the stage's result
   // final stage (time step t): operands of the TAP_FWD epilogue
   float* H; long long H_bstride;                   // fp32 h_t[b] = H + b * H_bstride, [64][N]
   const float* bias;
@@ -50,17 +52,12 @@ struct HShiftArgs {
   const float* x0; const float* zx; long long zx_kstride, z_bstride;
 };
 
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(HS_THREADS, 1)
 hshift_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmH,
-              const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmO, const HShiftArgs a) {
+              const __grid_constant__ CUtensorMap tmW, const HShiftArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* sOut = smem + HS_STAGES * G2_STAGE_BYTES;                 // [2 groups][2 buffers][16 rows][256 B]
-  uint8_t* sW = sOut + HS_OUT_BYTES;                                 // [P][32 rows][128 B] SW128
+  uint8_t* sW = smem + HS_STAGES * G2_STAGE_BYTES;                   // [P][32 rows][128 B] SW128
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(sW + HS_W_BYTES);
   uint64_t* empty_bar = full_bar + HS_STAGES;
   uint64_t* tmem_full = empty_bar + HS_STAGES;
@@ -82,7 +79,7 @@ hshift_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
   const int NS = 4;                                                  // samples (64-row blocks) per tile
 
   if (threadIdx.x == 0) {
-    tma_prefetch_desc(&tmS); tma_prefetch_desc(&tmZ); tma_prefetch_desc(&tmH); tma_prefetch_desc(&tmW); tma_prefetch_desc(&tmO);
+    tma_prefetch_desc(&tmS); tma_prefetch_desc(&tmZ); tma_prefetch_desc(&tmH); tma_prefetch_desc(&tmW);
     for (int s = 0; s < HS_STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(tmem_full + s, 1); mbar_init(tmem_empty + s, 16); }   // 8 epilogue warps x 2 CTAs
     mbar_init(w_bar, 1);
@@ -186,16 +183,11 @@ hshift_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
     // ===== epilogue warps 2..9: node quarter q = warp % 4 (TMEM lanes), column group g = (warp - 2) / 4 (128 columns) =====
     const int q = warp & 3;
     const int g = (warp - 2) >> 2;
-    const int gt = threadIdx.x - 64 - g * 128;                     // 0..127 within the column group
-    const bool elected = (q == ((2 + 4 * g) & 3)) && lane == 0;     // first warp of the group
-    uint8_t* gout = sOut + g * 8192;
-    int ob = 0;
+    const long long LD = (long long)a.P * a.N;
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = pair; tile < num_tiles; tile += npairs) {
       const int r0 = (tile / tiles_nodes) * 256;
-      const int n0 = (tile % tiles_nodes) * 256 + (int)rank * 128;
-      const int nl = q * 32 + lane;                                 // node within this CTA's 128
-      const int n = n0 + nl;
+      const int n = (tile % tiles_nodes) * 256 + (int)rank * 128 + q * 32 + lane;      // this thread's node
       mbar_wait(tmem_full + acc, acc_phase);
       tc_fence_after();
       const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256 + g * 128);
@@ -221,6 +213,7 @@ hshift_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
           __syncwarp();
           if (lane == 0) mbar_arrive_leader(tmem_empty + acc);
         }
+        if (!live) continue;                                        // rows beyond M (clipped last row tile)
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] *= a.scale;
         if (a.final_stage) {
@@ -234,33 +227,16 @@ hshift_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
             for (int kg = 0; kg < 8; ++kg) if (kg < a.KG) ax = fmaf(aw[kg], z[kg], ax);
             const float pre = fmaf(vgi, ax, fmaf(vgf, v[i], gsum * sBias[f0 + i]));       // gi (ax + b) + gf (r + b)
             const float h = a.exact ? tanh_acc(pre) : tap_tanh(pre);
-            if (live) of[(size_t)i * a.N] = h;
+            of[(size_t)i * a.N] = h;
             v[i] = h;
           }
         }
-        for (int pl = 0; pl < a.P; ++pl) {                          // plane 0 = bf16(v), plane 1 = bf16(v - plane 0)
-          if (elected) tma_store_wait_read<1>();                    // the store that last used this staging buffer has read it
-          named_bar_sync(1 + g, 128);
-          __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(gout + ob * 4096) + nl;      // [16 rows][128 nodes]
+        __nv_bfloat16* ob = a.out + (size_t)row0 * LD + n;          // a warp writes 32 consecutive nodes of one signal row: 64 B
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const __nv_bfloat16 hi = __float2bfloat16(v[i]);
-            dst[i * 128] = hi;
-            if (pl + 1 < a.P) v[i] -= __bfloat162float(hi);
-          }
-          fence_proxy_async();
-          named_bar_sync(3 + g, 128);
-          if (elected) {
-            tma_store_2d(&tmO, gout + ob * 4096, pl * a.N + n0, row0);                       // rows >= M are clipped by the TMA unit
-            tma_store_commit();
-          }
-          ob ^= 1;
-        }
+        for (int i = 0; i < 16; ++i) store_planes(ob + (size_t)i * LD, a.N, a.P, v[i]);
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-    if (elected) tma_store_wait_all();
-    (void)gt;
   }
   tc_fence_before();
   __syncthreads();
