@@ -14,14 +14,16 @@
 //   * split-bf16 operands (tc_gemm.cuh "planes"): main products K-concatenated over (signal plane, operator plane), mix products
 //     over (h plane q, weight plane w) with q + w < P; the operator is stored as S / scale, so the mix weights are W / scale
 //     and the epilogue multiplies the whole accumulator by scale;
-//   * epilogue (8 warps, thread <-> node): intermediate stages split the fp32 accumulator into bf16 planes and store them
-//     directly — for one signal row a warp writes 32 consecutive nodes = 64 contiguous bytes (two full sectors; a first version
-//     staged [16 rows][128 nodes] tiles for TMA bulk stores and was bound by the store's read-completion latency with two
-//     buffers per column group: 548 us vs 333 us for the plain GEMM); the LAST stage (k = 0) adds the input filter A(S)x_t,
-//     bias and time gates, applies tanh and writes H[b,t] (fp32) and the bf16 planes of the new state — the state update of
-//     tc_tap.cuh's TAP_FWD epilogue.
+//   * epilogue (8 warps, thread <-> node): the fp32 accumulator is split into bf16 planes, staged as [16 signal rows][128 nodes]
+//     tiles by the four node-quarter warps of a column group and written with TMA bulk stores, FOUR staging buffers per group
+//     (32 KB per CTA in flight: a bulk store takes ~1.45 us to release its buffer, and the tile's 128 KB per plane must leave
+//     within the tile's MMA time; two buffers per group gave 321 us per launch, direct 64-byte STG.U16 stores 282 us — both
+//     epilogue-bound — against 166 us for the plain GEMM); the LAST stage (k = 0) adds the input filter A(S)x_t, bias and time
+//     gates, applies tanh and writes H[b,t] (fp32, coalesced 128-byte rows) and the bf16 planes of the new state — the state
+//     update of tc_tap.cuh's TAP_FWD epilogue.
 // Structure per CTA (320 threads): warp 0 TMA producer, warp 1 MMA issuer (leader CTA) + TMEM allocator, warps 2..9 epilogue;
-// 6-stage ring of 32 KB stages shared by main and mix loads, 2 TMEM accumulator stages (512 columns).
+// 6-stage ring of 32 KB stages shared by main and mix loads (a mix stage carries one h tile and this CTA's rows of W_k), 2 TMEM
+// accumulator stages (512 columns).  Shared memory is used to the last KB: the dynamic segment must start 1024-byte aligned.
 #pragma once
 #include "tc_gemm2.cuh"
 #include "tc_tap.cuh"
@@ -31,8 +33,9 @@ namespace tc {
 
 constexpr int HS_THREADS = 64 + 8 * 32;
 constexpr int HS_STAGES = 6;
-constexpr int HS_W_BYTES = MAX_PLANES * 4096;         // this CTA's 32 weight rows x 64 columns per plane
-constexpr int HS_SMEM = HS_STAGES * G2_STAGE_BYTES + HS_W_BYTES + 256 + (64 * 8 + 64) * 4 + 8 * 8 + 1024;
+constexpr int HS_OUT_BUFS = 4;                        // staging buffers per column group
+constexpr int HS_OUT_BYTES = 2 * HS_OUT_BUFS * 4096;  // 2 column groups x 4 buffers x [16 rows][128 nodes] bf16
+constexpr int HS_SMEM = HS_STAGES * G2_STAGE_BYTES + HS_OUT_BYTES + 192 + (64 * 8 + 64) * 4 + 8 * 8;
 
 struct HShiftArgs {
   int M, N;                       // signal rows (B * 64), nodes
@@ -57,18 +60,22 @@ __device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* tm, int c0
   asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(tm), "r"(c0), "r"(c1) : "memory");
 }
 
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(HS_THREADS, 1)
 hshift_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmH,
-              const __grid_constant__ CUtensorMap tmW, const HShiftArgs a) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* sW = smem + HS_STAGES * G2_STAGE_BYTES;                   // [P][32 rows][128 B] SW128
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sW + HS_W_BYTES);
+              const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmO, const HShiftArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem_raw) & 1023u) != 0) __trap();                   // SW128 tiles need 1024-byte alignment; there is no slack to fix it up
+  uint8_t* sOut = smem + HS_STAGES * G2_STAGE_BYTES;                 // [2 groups][4 buffers][16 rows][256 B]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sOut + HS_OUT_BYTES);
   uint64_t* empty_bar = full_bar + HS_STAGES;
   uint64_t* tmem_full = empty_bar + HS_STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint64_t* w_bar = tmem_empty + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   float* sAw = reinterpret_cast<float*>(tmem_slot + 4);              // [64][KG] input-filter taps (final stage)
   float* sBias = sAw + 64 * 8;                                       // [64]
   const float** sZb = reinterpret_cast<const float**>(sBias + 64);   // [8] base pointer of input row (k, g): X or zx slab
@@ -84,10 +91,9 @@ hshift_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
   const int NS = 4;                                                  // samples (64-row blocks) per tile
 
   if (threadIdx.x == 0) {
-    tma_prefetch_desc(&tmS); tma_prefetch_desc(&tmZ); tma_prefetch_desc(&tmH); tma_prefetch_desc(&tmW);
+    tma_prefetch_desc(&tmS); tma_prefetch_desc(&tmZ); tma_prefetch_desc(&tmH); tma_prefetch_desc(&tmW); tma_prefetch_desc(&tmO);
     for (int s = 0; s < HS_STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(tmem_full + s, 1); mbar_init(tmem_empty + s, 16); }   // 8 epilogue warps x 2 CTAs
-    mbar_init(w_bar, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc2(tmem_slot, 512);
@@ -108,8 +114,6 @@ hshift_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
   if (warp == 0) {
     // ===== TMA producer (both CTAs): own 128 nodes of the operator, own half of the signal rows, own nodes of h =====
     if (lane == 0) {
-      if (rank == 0) mbar_expect_tx(w_bar, (uint32_t)(2 * a.P * 4096));          // weight rows of BOTH CTAs
-      for (int q = 0; q < a.P; ++q) tma_load_2d_pair(sW + q * 4096, &tmW, w_bar, a.wcol + q * a.wpstride, (int)rank * 32);
       int stage = 0; uint32_t phase = 0;
       for (int tile = pair; tile < num_tiles; tile += npairs) {
         const int r0 = (tile / tiles_nodes) * 256;                               // first signal row of the tile
@@ -133,13 +137,15 @@ hshift_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
             if (++stage == HS_STAGES) { stage = 0; phase ^= 1; }
           }
         }
-        for (int s = 0; s < NS; ++s) {                                           // h tiles of the tile's four samples
+        for (int s = 0; s < NS; ++s) {                        // h tiles of the tile's four samples
           for (int q = 0; q < a.P; ++q) {
             mbar_wait(empty_bar + stage, phase ^ 1);
             uint8_t* sa = smem + stage * G2_STAGE_BYTES;
-            if (rank == 0) mbar_expect_tx(full_bar + stage, 2 * G2_HALF_BYTES);
+            if (rank == 0) mbar_expect_tx(full_bar + stage, 2 * (G2_HALF_BYTES + a.P * 4096));
             tma_load_2d_pair(sa, &tmH, full_bar + stage, q * a.N + n0, r0 + 64 * s);            // rows >= M: zero filled
             tma_load_2d_pair(sa + 8192, &tmH, full_bar + stage, q * a.N + n0 + 64, r0 + 64 * s);
+            for (int w = 0; w < a.P; ++w)                                        // this CTA's 32 rows of W_k, every plane (L2 hits)
+              tma_load_2d_pair(sa + G2_HALF_BYTES + w * 4096, &tmW, full_bar + stage, a.wcol + w * a.wpstride, (int)rank * 32);
             if (++stage == HS_STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -150,8 +156,6 @@ hshift_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
     if (rank == 0 && lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(256, 256);
       constexpr uint32_t idesc_mix = make_idesc_bf16_amn(256, 64);
-      mbar_wait(w_bar, 0);
-      tc_fence_after();
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int tile = pair; tile < num_tiles; tile += npairs) {
@@ -177,7 +181,7 @@ hshift_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
             tc_fence_after();
             const uint32_t sa = smem_u32(smem + stage * G2_STAGE_BYTES);
             for (int w = 0; w + q < a.P; ++w) {
-              const uint64_t bdesc0 = make_kmajor_sw128_desc(smem_u32(sW + w * 4096));
+              const uint64_t bdesc0 = make_kmajor_sw128_desc(sa + G2_HALF_BYTES + w * 4096);
 #pragma unroll
               for (int j = 0; j < 4; ++j) {                                      // 64 contraction rows f' in steps of 16
                 const uint64_t adesc = make_mnmajor_sw128_desc(sa + j * 2048, 8192);
@@ -196,11 +200,15 @@ hshift_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
     // ===== epilogue warps 2..9: node quarter q = warp % 4 (TMEM lanes), column group g = (warp - 2) / 4 (128 columns) =====
     const int q = warp & 3;
     const int g = (warp - 2) >> 2;
-    const long long LD = (long long)a.P * a.N;
+    const bool elected = q == 2 && lane == 0;                       // first warp of each group (warps 2 and 6)
+    uint8_t* gout = sOut + g * (HS_OUT_BUFS * 4096);
+    const int nl = q * 32 + lane;                                   // node within this CTA's 128
+    int ob = 0;
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = pair; tile < num_tiles; tile += npairs) {
       const int r0 = (tile / tiles_nodes) * 256;
-      const int n = (tile % tiles_nodes) * 256 + (int)rank * 128 + q * 32 + lane;      // this thread's node
+      const int n0 = (tile % tiles_nodes) * 256 + (int)rank * 128;
+      const int n = n0 + nl;                                        // this thread's node
       mbar_wait(tmem_full + acc, acc_phase);
       tc_fence_after();
       const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256 + g * 128);
@@ -226,7 +234,6 @@ hshift_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
           __syncwarp();
           if (lane == 0) mbar_arrive_leader(tmem_empty + acc);
         }
-        if (!live) continue;                                        // rows beyond M (clipped last row tile)
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] *= a.scale;
         if (a.final_stage) {
@@ -240,16 +247,32 @@ hshift_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
             for (int kg = 0; kg < 8; ++kg) if (kg < a.KG) ax = fmaf(aw[kg], z[kg], ax);
             const float pre = fmaf(vgi, ax, fmaf(vgf, v[i], gsum * sBias[f0 + i]));       // gi (ax + b) + gf (r + b)
             const float h = a.exact ? tanh_acc(pre) : tap_tanh(pre);
-            of[(size_t)i * a.N] = h;
+            if (live) of[(size_t)i * a.N] = h;
             v[i] = h;
           }
         }
-        __nv_bfloat16* ob = a.out + (size_t)row0 * LD + n;          // a warp writes 32 consecutive nodes of one signal row: 64 B
+        for (int pl = 0; pl < a.P; ++pl) {                          // plane 0 = bf16(v), plane 1 = bf16(v - plane 0)
+          if (elected) tma_store_wait_read<HS_OUT_BUFS - 1>();      // the store that last used this staging buffer has read it
+          named_bar_sync(1 + g, 128);
+          __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(gout + ob * 4096) + nl;      // [16 rows][128 nodes]
 #pragma unroll
-        for (int i = 0; i < 16; ++i) store_planes(ob + (size_t)i * LD, a.N, a.P, v[i]);
+          for (int i = 0; i < 16; ++i) {
+            const __nv_bfloat16 hi = __float2bfloat16(v[i]);
+            dst[i * 128] = hi;
+            if (pl + 1 < a.P) v[i] -= __bfloat162float(hi);
+          }
+          fence_proxy_async();
+          named_bar_sync(3 + g, 128);
+          if (elected) {
+            tma_store_2d(&tmO, gout + ob * 4096, pl * a.N + n0, row0);                       // rows >= M are clipped by the TMA unit
+            tma_store_commit();
+          }
+          if (++ob == HS_OUT_BUFS) ob = 0;
+        }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (elected) tma_store_wait_all();
   }
   tc_fence_before();
   __syncthreads();
