@@ -289,13 +289,12 @@ static void launch_hshift(const gcrnn_graph* g, const TcDims& d, const __nv_bflo
   const CUtensorMap tmH = make_tmap_bf16(hprev, d.R, d.LD, 64);
   const CUtensorMap tmW = make_tmap_bf16(Wk, 64, (long long)d.P * 64, 32);
   a.out = out;
-  const CUtensorMap tmO = make_tmap_bf16_plain(out, d.R, d.LD, 128, 16);
   static DeviceOnce once;
   if (once.first()) CUDA_OK(cudaFuncSetAttribute(hshift_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HS_SMEM));
   const int tiles = (int)((d.R + 255) / 256) * (d.N / 256);
   int pairs = d.sms / 2;
   if (tiles < pairs) pairs = tiles;
-  hshift_kernel<<<2 * pairs, HS_THREADS, HS_SMEM, st>>>(tmS, tmZ, tmH, tmW, tmO, a);
+  hshift_kernel<<<2 * pairs, HS_THREADS, HS_SMEM, st>>>(tmS, tmZ, tmH, tmW, a);
   launched();
 }
 

@@ -14,16 +14,18 @@
 //   * split-bf16 operands (tc_gemm.cuh "planes"): main products K-concatenated over (signal plane, operator plane), mix products
 //     over (h plane q, weight plane w) with q + w < P; the operator is stored as S / scale, so the mix weights are W / scale
 //     and the epilogue multiplies the whole accumulator by scale;
-//   * epilogue (8 warps, thread <-> node): the fp32 accumulator is split into bf16 planes, staged as [16 signal rows][128 nodes]
-//     tiles by the four node-quarter warps of a column group and written with TMA bulk stores, FOUR staging buffers per group
-//     (32 KB per CTA in flight: a bulk store takes ~1.45 us to release its buffer, and the tile's 128 KB per plane must leave
-//     within the tile's MMA time; two buffers per group gave 321 us per launch, direct 64-byte STG.U16 stores 282 us — both
-//     epilogue-bound — against 166 us for the plain GEMM); the LAST stage (k = 0) adds the input filter A(S)x_t, bias and time
-//     gates, applies tanh and writes H[b,t] (fp32, coalesced 128-byte rows) and the bf16 planes of the new state — the state
-//     update of tc_tap.cuh's TAP_FWD epilogue.
+//   * epilogue (8 warps, thread <-> node).  A thread owns ONE node and 16 signal rows per chunk, but memory is node-contiguous:
+//     storing element by element (16-bit stores, to global or to a staging tile for TMA) costs one LSU instruction per
+//     element-row and made the kernel epilogue-bound (282 .. 327 us per launch against 166 us for the plain GEMM, whatever the
+//     number of staging buffers).  Instead each warp transposes its [32 nodes][16 rows] bf16 block through a 1 KB shared-memory
+//     buffer: two 16-byte stores per thread (node-major, nodes placed in a permuted slot order), then two ldmatrix.x4.trans, after
+//     which a thread holds EIGHT consecutive nodes of one signal row in four registers -> one 16-byte global store (8 rows x 64 B
+//     per warp instruction): 6 LSU instructions per chunk and plane instead of 16, no cross-warp synchronisation.
+//     The LAST stage (k = 0) adds the input filter A(S)x_t, bias and time gates, applies tanh and writes H[b,t] (fp32, one
+//     128-byte row segment per warp store) and the bf16 planes of the new state — the state update of tc_tap.cuh's TAP_FWD.
 // Structure per CTA (320 threads): warp 0 TMA producer, warp 1 MMA issuer (leader CTA) + TMEM allocator, warps 2..9 epilogue;
 // 6-stage ring of 32 KB stages shared by main and mix loads (a mix stage carries one h tile and this CTA's rows of W_k), 2 TMEM
-// accumulator stages (512 columns).  Shared memory is used to the last KB: the dynamic segment must start 1024-byte aligned.
+// accumulator stages (512 columns).
 #pragma once
 #include "tc_gemm2.cuh"
 #include "tc_tap.cuh"
@@ -33,9 +35,8 @@ namespace tc {
 
 constexpr int HS_THREADS = 64 + 8 * 32;
 constexpr int HS_STAGES = 6;
-constexpr int HS_OUT_BUFS = 4;                        // staging buffers per column group
-constexpr int HS_OUT_BYTES = 2 * HS_OUT_BUFS * 4096;  // 2 column groups x 4 buffers x [16 rows][128 nodes] bf16
-constexpr int HS_SMEM = HS_STAGES * G2_STAGE_BYTES + HS_OUT_BYTES + 192 + (64 * 8 + 64) * 4 + 8 * 8;
+constexpr int HS_OUT_BYTES = 8 * 1024;                // per epilogue warp: [32 node slots][16 rows] bf16 transpose buffer
+constexpr int HS_SMEM = HS_STAGES * G2_STAGE_BYTES + HS_OUT_BYTES + 192 + (64 * 8 + 64) * 4 + 8 * 8 + 1024;
 
 struct HShiftArgs {
   int M, N;                       // signal rows (B * 64), nodes
@@ -60,17 +61,17 @@ __device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* tm, int c0
   asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(tm), "r"(c0), "r"(c1) : "memory");
 }
 
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t* r, uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr) : "memory");
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(HS_THREADS, 1)
 hshift_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmH,
-              const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmO, const HShiftArgs a) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = smem_raw;
-  if ((smem_u32(smem_raw) & 1023u) != 0) __trap();                   // SW128 tiles need 1024-byte alignment; there is no slack to fix it up
-  uint8_t* sOut = smem + HS_STAGES * G2_STAGE_BYTES;                 // [2 groups][4 buffers][16 rows][256 B]
+              const __grid_constant__ CUtensorMap tmW, const HShiftArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sOut = smem + HS_STAGES * G2_STAGE_BYTES;                 // [8 epilogue warps][32 node slots][16 rows] bf16
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(sOut + HS_OUT_BYTES);
   uint64_t* empty_bar = full_bar + HS_STAGES;
   uint64_t* tmem_full = empty_bar + HS_STAGES;
@@ -91,7 +92,7 @@ hshift_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
   const int NS = 4;                                                  // samples (64-row blocks) per tile
 
   if (threadIdx.x == 0) {
-    tma_prefetch_desc(&tmS); tma_prefetch_desc(&tmZ); tma_prefetch_desc(&tmH); tma_prefetch_desc(&tmW); tma_prefetch_desc(&tmO);
+    tma_prefetch_desc(&tmS); tma_prefetch_desc(&tmZ); tma_prefetch_desc(&tmH); tma_prefetch_desc(&tmW);
     for (int s = 0; s < HS_STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(tmem_full + s, 1); mbar_init(tmem_empty + s, 16); }   // 8 epilogue warps x 2 CTAs
     fence_barrier_init();
@@ -200,15 +201,18 @@ hshift_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
     // ===== epilogue warps 2..9: node quarter q = warp % 4 (TMEM lanes), column group g = (warp - 2) / 4 (128 columns) =====
     const int q = warp & 3;
     const int g = (warp - 2) >> 2;
-    const bool elected = q == 2 && lane == 0;                       // first warp of each group (warps 2 and 6)
-    uint8_t* gout = sOut + g * (HS_OUT_BUFS * 4096);
-    const int nl = q * 32 + lane;                                   // node within this CTA's 128
-    int ob = 0;
+    const long long LD = (long long)a.P * a.N;
+    // transpose buffer: lane l (node l of the warp's 32) owns slot 8j + 2c + e with l = 8c + 2j + e, so that after
+    // ldmatrix.x4.trans thread t holds nodes 8 (t % 4) .. + 7 of signal row (t / 4) in its four registers
+    const uint32_t tb = smem_u32(sOut + (warp - 2) * 1024);
+    const uint32_t my_slot = (uint32_t)(8 * ((lane & 7) >> 1) + 2 * (lane >> 3) + (lane & 1));
+    const uint32_t st_addr = tb + my_slot * 32;
+    const uint32_t ld_addr = tb + (uint32_t)lane * 32;             // thread 8 i + m supplies row m (= slot 8 i + m) of matrix i
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = pair; tile < num_tiles; tile += npairs) {
       const int r0 = (tile / tiles_nodes) * 256;
-      const int n0 = (tile % tiles_nodes) * 256 + (int)rank * 128;
-      const int n = n0 + nl;                                        // this thread's node
+      const int nw0 = (tile % tiles_nodes) * 256 + (int)rank * 128 + q * 32;     // first node of this warp
+      const int n = nw0 + lane;                                     // this thread's node (TMEM lane)
       mbar_wait(tmem_full + acc, acc_phase);
       tc_fence_after();
       const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256 + g * 128);
@@ -234,6 +238,7 @@ hshift_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
           __syncwarp();
           if (lane == 0) mbar_arrive_leader(tmem_empty + acc);
         }
+        if (!live) continue;                                        // rows beyond M (clipped last row tile); warp-uniform
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] *= a.scale;
         if (a.final_stage) {
@@ -247,32 +252,32 @@ hshift_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
             for (int kg = 0; kg < 8; ++kg) if (kg < a.KG) ax = fmaf(aw[kg], z[kg], ax);
             const float pre = fmaf(vgi, ax, fmaf(vgf, v[i], gsum * sBias[f0 + i]));       // gi (ax + b) + gf (r + b)
             const float h = a.exact ? tanh_acc(pre) : tap_tanh(pre);
-            if (live) of[(size_t)i * a.N] = h;
+            of[(size_t)i * a.N] = h;
             v[i] = h;
           }
         }
         for (int pl = 0; pl < a.P; ++pl) {                          // plane 0 = bf16(v), plane 1 = bf16(v - plane 0)
-          if (elected) tma_store_wait_read<HS_OUT_BUFS - 1>();      // the store that last used this staging buffer has read it
-          named_bar_sync(1 + g, 128);
-          __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(gout + ob * 4096) + nl;      // [16 rows][128 nodes]
+          uint32_t pk[8];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const __nv_bfloat16 hi = __float2bfloat16(v[i]);
-            dst[i * 128] = hi;
-            if (pl + 1 < a.P) v[i] -= __bfloat162float(hi);
+          for (int k = 0; k < 8; ++k) {
+            pk[k] = pack_bf16x2(v[2 * k], v[2 * k + 1]);
+            if (pl + 1 < a.P) bf16x2_residual(pk[k], v[2 * k], v[2 * k + 1]);
           }
-          fence_proxy_async();
-          named_bar_sync(3 + g, 128);
-          if (elected) {
-            tma_store_2d(&tmO, gout + ob * 4096, pl * a.N + n0, row0);                       // rows >= M are clipped by the TMA unit
-            tma_store_commit();
+          __syncwarp();                                             // the previous ldmatrix reads of this buffer are done
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(st_addr), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(st_addr + 16), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]) : "memory");
+          __syncwarp();
+          __nv_bfloat16* ob = a.out + (size_t)(row0 + (lane >> 2)) * LD + (size_t)pl * a.N + nw0 + 8 * (lane & 3);
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {                          // signal rows row0 + 8 hh + lane / 4
+            uint32_t r[4];
+            ldsm_x4_trans(r, ld_addr + hh * 16);
+            *reinterpret_cast<uint4*>(ob + (size_t)(8 * hh) * LD) = make_uint4(r[0], r[1], r[2], r[3]);
           }
-          if (++ob == HS_OUT_BUFS) ob = 0;
         }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-    if (elected) tma_store_wait_all();
   }
   tc_fence_before();
   __syncthreads();
