@@ -47,6 +47,7 @@ struct HShiftArgs {
   int wcol;                       // column of W_k's plane 0 in the prepared weight matrix (plane q at wcol + q * wpstride)
   int wpstride;
   int exact;
+  int epi_warps;                  // 4 or 8 epilogue warps take part (see the scheduling note in the kernel)
   __nv_bfloat16* out;             // [M][P * N] bf16 planes of the stage's result
   // final stage (time step t): operands of the TAP_FWD epilogue
   float* H; long long H_bstride;                   // fp32 h_t[b] = H + b * H_bstride, [64][N]
@@ -94,7 +95,7 @@ hshift_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmS); tma_prefetch_desc(&tmZ); tma_prefetch_desc(&tmH); tma_prefetch_desc(&tmW);
     for (int s = 0; s < HS_STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tmem_full + s, 1); mbar_init(tmem_empty + s, 16); }   // 8 epilogue warps x 2 CTAs
+    for (int s = 0; s < 2; ++s) { mbar_init(tmem_full + s, 1); mbar_init(tmem_empty + s, 2 * a.epi_warps); }   // epilogue warps x 2 CTAs
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc2(tmem_slot, 512);
@@ -197,10 +198,16 @@ hshift_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
-  } else {
-    // ===== epilogue warps 2..9: node quarter q = warp % 4 (TMEM lanes), column group g = (warp - 2) / 4 (128 columns) =====
+  } else if (warp - 2 < a.epi_warps) {
+    // ===== epilogue warps: node quarter q = warp % 4 (TMEM lanes); with 8 warps, column group g = (warp - 2) / 4 takes 128 of the
+    // 256 columns.  Scheduling note: the single MMA-issuing thread (warp 1) shares its SM sub-partition with every epilogue warp
+    // of quarter 1, and its ~100-instruction dependent loop per k-block only keeps the tensor pipe fed while it gets most issue
+    // slots: with two busy epilogue warps next to it the pipe ran 65 % active (ncu) whatever the store mechanism, with one
+    // (4 epilogue warps, as in tc_gemm2.cuh) it is fed.  Intermediate stages therefore use 4 warps; the final stage's heavier
+    // epilogue (tanh, fp32 H) may use 8.
     const int q = warp & 3;
     const int g = (warp - 2) >> 2;
+    const int cols_per_warp = a.epi_warps == 8 ? 128 : 256;
     const long long LD = (long long)a.P * a.N;
     // transpose buffer: lane l (node l of the warp's 32) owns slot 8j + 2c + e with l = 8c + 2j + e, so that after
     // ldmatrix.x4.trans thread t holds nodes 8 (t % 4) .. + 7 of signal row (t / 4) in its four registers
@@ -215,12 +222,13 @@ hshift_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
       const int n = nw0 + lane;                                     // this thread's node (TMEM lane)
       mbar_wait(tmem_full + acc, acc_phase);
       tc_fence_after();
-      const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256 + g * 128);
+      const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256 + g * cols_per_warp);
+      const int nchunk = cols_per_warp / 16;
       float z[8];
       float vgi = 1.f, vgf = 1.f;
 #pragma unroll 1
-      for (int c = 0; c < 8; ++c) {                                 // 16 accumulator columns = 16 signal rows (one sample, 16 features)
-        const int row0 = r0 + g * 128 + c * 16;                     // first signal row (b * 64 + f) of the chunk
+      for (int c = 0; c < nchunk; ++c) {                            // 16 accumulator columns = 16 signal rows (one sample, 16 features)
+        const int row0 = r0 + g * cols_per_warp + c * 16;           // first signal row (b * 64 + f) of the chunk
         const long long b = row0 >> 6;
         const int f0 = row0 & 63;
         const bool live = row0 < a.M;
@@ -233,7 +241,7 @@ hshift_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
         }
         float v[16];
         tmem_ld16(t0 + (uint32_t)(c * 16), v);
-        if (c == 7) {                                               // accumulator fully read: hand the TMEM stage back early
+        if (c == nchunk - 1) {                                      // accumulator fully read: hand the TMEM stage back early
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_leader(tmem_empty + acc);
