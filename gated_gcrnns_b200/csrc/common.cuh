@@ -27,7 +27,8 @@ struct Options {
   int graph_capture = 1;        // replay small fp32 cell calls as CUDA graphs keyed by their pointer set (api.cu)
   int gate_fq8 = 2;             // time-gate kernels with 8 feature groups (512 threads): 1 = forward, 2 = forward + backward
   int gemm_pair = 1;            // CTA-pair (cta_group::2) shift GEMM when the shape allows
-  int fwd_fused = 1;            // forward tap contraction fused into the shift GEMMs (Horner form) when the shape allows
+  int fwd_fused = 0;            // 1: forward tap contraction fused into the shift GEMMs (Horner form, tc_hshift.cuh); measured
+                                // slower than chain + tap kernel in bf16 and 2 % faster in bf16x2, hence off by default
   long long epoch = 0;          // bumped by every option change on the handle: captured CUDA graphs are keyed by it
 };
 const Options& opt();

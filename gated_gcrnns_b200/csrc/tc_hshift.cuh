@@ -23,7 +23,17 @@
 //     per warp instruction): 6 LSU instructions per chunk and plane instead of 16, no cross-warp synchronisation.
 //     The LAST stage (k = 0) adds the input filter A(S)x_t, bias and time gates, applies tanh and writes H[b,t] (fp32, one
 //     128-byte row segment per warp store) and the bf16 planes of the new state — the state update of tc_tap.cuh's TAP_FWD.
-// Structure per CTA (320 threads): warp 0 TMA producer, warp 1 MMA issuer (leader CTA) + TMEM allocator, warps 2..9 epilogue;
+//
+// MEASURED OUTCOME (B200, N = 1024, 131072 signal rows per launch; profiles/r02_horner_notes.txt): an intermediate stage takes
+// 224 us (bf16) / 461 us (bf16x2) against 166 / 332 us for the plain pair GEMM, i.e. +35 % / +39 %, although the mix adds only
+// +6 % / +9 % flops: an M = 256, N = 64 tcgen05.mma occupies the tensor pipe about as long as an N = 256 one (~130-190 cycles per
+// instruction whether its A operand is MN- or K-major, dependent or interleaved accumulators), so the cost is the instruction
+// COUNT: 16 (48) mix instructions next to 64 (128) main ones.  With the seed kernel (109 / 213 us) and the final stage's heavier
+// epilogue (363 / 575 us with 16 epilogue warps) a forward step costs 1144 / 2171 us against 1016 / 2215 us for chain + tap
+// kernel: no gain in bf16, 2 % in bf16x2.  The path is therefore OFF by default (option "fwd_fused" = 1 enables it); it is kept
+// because it is correct (tests/test_gpu_tc.py::test_tc_horner_forward_matches_unfused) and documents what the hardware does.
+//
+// Structure per CTA (576 threads): warp 0 TMA producer, warp 1 MMA issuer (leader CTA) + TMEM allocator, up to 16 epilogue warps;
 // 6-stage ring of 32 KB stages shared by main and mix loads (a mix stage carries one h tile and this CTA's rows of W_k), 2 TMEM
 // accumulator stages (512 columns).
 #pragma once
