@@ -43,9 +43,9 @@
 namespace gcrnn {
 namespace tc {
 
-constexpr int HS_THREADS = 64 + 8 * 32;
+constexpr int HS_THREADS = 64 + 16 * 32;      // TMA warp + MMA warp + up to 16 epilogue warps
 constexpr int HS_STAGES = 6;
-constexpr int HS_OUT_BYTES = 8 * 1024;                // per epilogue warp: [32 node slots][16 rows] bf16 transpose buffer
+constexpr int HS_OUT_BYTES = 16 * 1024;               // per epilogue warp: [32 node slots][16 rows] bf16 transpose buffer
 constexpr int HS_SMEM = HS_STAGES * G2_STAGE_BYTES + HS_OUT_BYTES + 192 + (64 * 8 + 64) * 4 + 8 * 8 + 1024;
 
 struct HShiftArgs {
@@ -57,7 +57,7 @@ struct HShiftArgs {
   int wcol;                       // column of W_k's plane 0 in the prepared weight matrix (plane q at wcol + q * wpstride)
   int wpstride;
   int exact;
-  int epi_warps;                  // 4 or 8 epilogue warps take part (see the scheduling note in the kernel)
+  int epi_warps;                  // 4, 8 or 16 epilogue warps take part (the others idle)
   __nv_bfloat16* out;             // [M][P * N] bf16 planes of the stage's result
   // final stage (time step t): operands of the TAP_FWD epilogue
   float* H; long long H_bstride;                   // fp32 h_t[b] = H + b * H_bstride, [64][N]
@@ -209,15 +209,12 @@ hshift_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
       }
     }
   } else if (warp - 2 < a.epi_warps) {
-    // ===== epilogue warps: node quarter q = warp % 4 (TMEM lanes); with 8 warps, column group g = (warp - 2) / 4 takes 128 of the
-    // 256 columns.  Scheduling note: the single MMA-issuing thread (warp 1) shares its SM sub-partition with every epilogue warp
-    // of quarter 1, and its ~100-instruction dependent loop per k-block only keeps the tensor pipe fed while it gets most issue
-    // slots: with two busy epilogue warps next to it the pipe ran 65 % active (ncu) whatever the store mechanism, with one
-    // (4 epilogue warps, as in tc_gemm2.cuh) it is fed.  Intermediate stages therefore use 4 warps; the final stage's heavier
-    // epilogue (tanh, fp32 H) may use 8.
+    // ===== epilogue warps: node quarter q = warp % 4 (TMEM lanes); column group g = (warp - 2) / 4 takes 1024 / epi_warps of the
+    // 256 columns.  Intermediate stages run at the same speed with 4 or 8 warps; the final stage's epilogue (input filter, gates,
+    // tanh, fp32 H, planes) is the heavy one: 720 us per launch with 4 warps, ~460 with 8, 363 with 16 (bf16).
     const int q = warp & 3;
     const int g = (warp - 2) >> 2;
-    const int cols_per_warp = a.epi_warps == 8 ? 128 : 256;
+    const int cols_per_warp = 1024 / a.epi_warps;                   // 256, 128 or 64 accumulator columns per warp
     const long long LD = (long long)a.P * a.N;
     // transpose buffer: lane l (node l of the warp's 32) owns slot 8j + 2c + e with l = 8c + 2j + e, so that after
     // ldmatrix.x4.trans thread t holds nodes 8 (t % 4) .. + 7 of signal row (t / 4) in its four registers
