@@ -281,7 +281,7 @@ static void launch_hshift(const gcrnn_graph* g, const TcDims& d, const __nv_bflo
   HShiftArgs a{};
   if (fin) a = *fin;
   a.M = (int)d.R; a.N = d.N; a.P = d.P; a.scale = g->dense_scale; a.final_stage = fin != nullptr; a.wcol = 0; a.wpstride = 64; a.exact = d.P > 1;
-  a.epi_warps = fin ? (opt().fwd_fused >= 2 ? 4 : 8) : (opt().fwd_fused >= 3 ? 8 : 4);      // fwd_fused 2 / 3: A/B of the epilogue warp count
+  a.epi_warps = fin ? 16 : 4;
   a.segs = ShiftSegs{};
   for (int q = 0; q < d.P; ++q) { a.segs.a[a.segs.n] = q; a.segs.b[a.segs.n] = 0; ++a.segs.n; }
   if (d.P > 1 && g->s_planes > 1) { a.segs.a[a.segs.n] = 0; a.segs.b[a.segs.n] = 1; ++a.segs.n; }
