@@ -14,7 +14,13 @@
 // the end (no atomics), reduced once per backward pass by wgrad_reduce_kernel / dax_reduce_kernel.
 //
 // Shared memory: ring of 4 "pair stages" (two taps x 128 nodes, 32 KB: [node half][tap][64 rows][128 B], SW128),
-// ring of 2 aux stages (h_{t-1} bf16 tile 16 KB + Zs tile 4 KB), resident weights 48 KB.
+// ring of 2 aux stages ([node half]{h_{t-1} bf16 64 rows, Zs 16 rows}: 20 KB), resident weights.
+//
+// Instruction count matters here: an M = 128 tcgen05.mma with N = 16 or 64 occupies the tensor pipe about as long as one with
+// N = 128 (profiles/r02_horner_notes.txt), and with separate instructions per operand plane and per product this kernel was
+// bound by them, not by HBM (split-bf16: 124 per tile, 1059 us per launch for 4.8 GB).  Hence (i) MMA3 rides in MMA2: the B
+// operand is the stacked [h; Zs] tile (N = 80), columns 64..79 of the first pair's accumulator are dAx; (ii) with split operands
+// MMA1 multiplies signal plane 0 by the stacked weight planes [W0; W1] (N = 128) and the epilogue sums the two column halves.
 #pragma once
 #include "tc_tap.cuh"
 
@@ -66,8 +72,8 @@ bwd_fused_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sV = smem;                                              // [BF_STAGES][2 halves][2 taps][64 rows][128 B]
-  uint8_t* sX = sV + a.stages * BF_STAGE_BYTES;                    // [BF_AUX]{ h: [2 halves][64][128 B], Zs: [2 halves][16][128 B] }
-  uint8_t* sW = sX + BF_AUX * BF_AUX_BYTES;                        // [P][KB][64 rows g][128 B]
+  uint8_t* sX = sV + a.stages * BF_STAGE_BYTES;                    // [BF_AUX][2 halves]{ h: [64][128 B], Zs: [16][128 B] }
+  uint8_t* sW = sX + BF_AUX * BF_AUX_BYTES;                        // [KB][P][64 rows g][128 B]: the planes of a tap are stacked
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(sW + a.P * a.KB * 8192);
   uint64_t* empty_bar = full_bar + BF_STAGES;
   uint64_t* aux_full = empty_bar + BF_STAGES;
@@ -88,7 +94,7 @@ bwd_fused_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
   const long long tile_lo = blockIdx.x * per_cta;
   const long long tile_hi = tile_lo + per_cta < num_tiles ? tile_lo + per_cta : num_tiles;
   const int NP = (a.K + 1) / 2;
-  constexpr uint32_t TMEM_D2 = 128, TMEM_D3 = 320, TMEM_COLS = 512;
+  constexpr uint32_t TMEM_D2 = 256, D2_STRIDE = 80, TMEM_COLS = 512;    // D1: 2 stages x 128 columns; D2: up to 3 pairs x 80
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tm0); tma_prefetch_desc(&tmc); tma_prefetch_desc(&tmH); tma_prefetch_desc(&tmZ); tma_prefetch_desc(&tmW);
@@ -120,7 +126,9 @@ bwd_fused_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
     // ===== TMA producer =====
     if (lane == 0 && has_work) {
       mbar_expect_tx(w_bar, (uint32_t)(a.P * a.KB * 8192));
-      for (int kb = 0; kb < a.P * a.KB; ++kb) tma_load_2d(sW + kb * 8192, &tmW, w_bar, kb * 64, 0);   // plane q = blocks [q*KB, (q+1)*KB)
+      for (int kb = 0; kb < a.KB; ++kb)
+        for (int w = 0; w < a.P; ++w)                            // global: plane w = column blocks [w*KB, (w+1)*KB)
+          tma_load_2d(sW + (kb * a.P + w) * 8192, &tmW, w_bar, (w * a.KB + kb) * 64, 0);
       int stage = 0; uint32_t phase = 0;
       int ax = 0; uint32_t aphase = 0;
       for (long long tile = tile_lo; tile < tile_hi; ++tile) {
@@ -129,10 +137,10 @@ bwd_fused_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
         mbar_wait(aux_empty + ax, aphase ^ 1);
         uint8_t* xd = sX + ax * BF_AUX_BYTES;
         mbar_expect_tx(aux_full + ax, BF_AUX_BYTES);
-        tma_load_2d(xd, &tmH, aux_full + ax, n0, (int)(b * 64));
-        tma_load_2d(xd + 8192, &tmH, aux_full + ax, n0 + 64, (int)(b * 64));
-        tma_load_2d(xd + 16384, &tmZ, aux_full + ax, n0, (int)(a.zs_row0 + b * a.zs_rowb));
-        tma_load_2d(xd + 16384 + 2048, &tmZ, aux_full + ax, n0 + 64, (int)(a.zs_row0 + b * a.zs_rowb));
+        tma_load_2d(xd, &tmH, aux_full + ax, n0, (int)(b * 64));                                     // half 0: h rows 0..63
+        tma_load_2d(xd + 8192, &tmZ, aux_full + ax, n0, (int)(a.zs_row0 + b * a.zs_rowb));          //         Zs rows 64..79
+        tma_load_2d(xd + 10240, &tmH, aux_full + ax, n0 + 64, (int)(b * 64));                        // half 1
+        tma_load_2d(xd + 10240 + 8192, &tmZ, aux_full + ax, n0 + 64, (int)(a.zs_row0 + b * a.zs_rowb));
         if (++ax == BF_AUX) { ax = 0; aphase ^= 1; }
         for (int pq = 0; pq < NP * a.P; ++pq) {                    // (tap pair p, signal plane q)
           const int p = pq / a.P, q = pq % a.P;
@@ -154,9 +162,9 @@ bwd_fused_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0 && has_work) {
-      constexpr uint32_t idesc1 = make_idesc_bf16_amn(128, 64);   // dh:  A MN-major (nodes), B K-major (weights)
-      constexpr uint32_t idesc2 = make_idesc_bf16(128, 64);       // dB:  both K-major (K = nodes)
-      constexpr uint32_t idesc3 = make_idesc_bf16(128, BF_ZROWS); // dAx
+      constexpr uint32_t idesc1 = make_idesc_bf16_amn(128, 64);   // dh:  A MN-major (nodes), B K-major (weights), one plane
+      constexpr uint32_t idesc1p = make_idesc_bf16_amn(128, 128); //      signal plane 0 against the stacked weight planes
+      constexpr uint32_t idesc2 = make_idesc_bf16(128, 64 + BF_ZROWS);   // dB | dAx: both K-major (K = nodes), B = [h; Zs]
       mbar_wait(w_bar, 0);
       tc_fence_after();
       int stage = 0; uint32_t phase = 0;
@@ -167,7 +175,7 @@ bwd_fused_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
         mbar_wait(tmem_empty + acc, acc_phase ^ 1);
         mbar_wait(aux_full + ax, aphase);
         tc_fence_after();
-        const uint32_t d1 = tmem_base + (uint32_t)(acc * 64);
+        const uint32_t d1 = tmem_base + (uint32_t)(acc * 128);
         const uint32_t sh = smem_u32(sX + ax * BF_AUX_BYTES);
         for (int pq = 0; pq < NP * a.P; ++pq) {
           const int p = pq / a.P, q = pq % a.P;
@@ -175,27 +183,23 @@ bwd_fused_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
           mbar_wait(full_bar + stage, phase);
           tc_fence_after();
           const uint32_t sv = smem_u32(sV + stage * BF_STAGE_BYTES);
-          // MMA1: contraction rows (tap, f) of this pair, 16 at a time; signal plane q meets weight planes w with q + w < P
-          for (int w = 0; w + q < a.P; ++w) {
-            for (int ks = 0; ks < 4 * ntap; ++ks) {
-              const uint64_t adesc = make_mnmajor_sw128_desc(sv + ks * 2048, 16384);
-              const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(sW + (w * a.KB + 2 * p + (ks >> 2)) * 8192)) + (uint64_t)(2 * (ks & 3));
-              umma_f16(d1, adesc, bdesc, idesc1, (pq | w | ks) != 0);
-            }
+          // MMA1: contraction rows (tap, f) of this pair, 16 at a time.  Split operands: plane 0 against the stacked [W0; W1]
+          // (two column halves of D1, summed by the epilogue), plane 1 against W0 (first half)
+          for (int ks = 0; ks < 4 * ntap; ++ks) {
+            const uint64_t adesc = make_mnmajor_sw128_desc(sv + ks * 2048, 16384);
+            const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(sW + (2 * p + (ks >> 2)) * a.P * 8192)) + (uint64_t)(2 * (ks & 3));
+            umma_f16(d1, adesc, bdesc, (a.P > 1 && q == 0) ? idesc1p : idesc1, (pq | ks) != 0);
           }
-          // MMA2 (+ MMA3 on pair 0): K = 128 nodes = 2 halves x 4 steps; both signal planes accumulate into the same D
-          const uint32_t d2 = tmem_base + TMEM_D2 + (uint32_t)(p * 64);
+          // MMA2 + MMA3: K = 128 nodes = 2 halves x 4 steps, B = [h; Zs] (80 rows); both signal planes accumulate into the same D.
+          // Columns 64..79 are the input-tap / bias gradients for pair 0 (rows of tap 0) and unused for the other pairs.
+          const uint32_t d2 = tmem_base + TMEM_D2 + (uint32_t)(p * D2_STRIDE);
           const bool fresh = first && q == 0;
 #pragma unroll
           for (int hs = 0; hs < 8; ++hs) {
             const int h = hs >> 2, ks = hs & 3;
             const uint64_t adesc = make_kmajor_sw128_desc(sv + h * 16384) + (uint64_t)(2 * ks);
-            const uint64_t bdesc = make_kmajor_sw128_desc(sh + h * 8192) + (uint64_t)(2 * ks);
+            const uint64_t bdesc = make_kmajor_sw128_desc(sh + h * 10240) + (uint64_t)(2 * ks);
             umma_f16(d2, adesc, bdesc, idesc2, !(fresh && hs == 0));
-            if (p == 0) {
-              const uint64_t zdesc = make_kmajor_sw128_desc(sh + 16384 + h * 2048) + (uint64_t)(2 * ks);
-              umma_f16(tmem_base + TMEM_D3, adesc, zdesc, idesc3, !(fresh && hs == 0));
-            }
           }
           umma_commit(empty_bar + stage);
           if (++stage == a.stages) { stage = 0; phase ^= 1; }
@@ -237,7 +241,13 @@ bwd_fused_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
       mbar_wait(tmem_full + acc, acc_phase);
       tc_fence_after();
       float v[16];
-      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 64 + m0), v);
+      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 128 + m0), v);
+      if (a.P > 1) {                                     // second column half: signal plane 0 x weight plane 1
+        float v2[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 128 + 64 + m0), v2);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] += v2[i];
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tmem_empty + acc);      // accumulator is in registers: release the TMEM stage
@@ -292,7 +302,7 @@ bwd_fused_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
 #pragma unroll 1
         for (int c = 0; c < 64; c += 32) {
           float w[32];
-          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + TMEM_D2 + (uint32_t)(cg * 64 + c), w);
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + TMEM_D2 + (uint32_t)(cg * D2_STRIDE + c), w);
           if (k < a.K) {
             float4* o = reinterpret_cast<float4*>(mine + ((size_t)k * 64 + f) * 64 + c);
 #pragma unroll
@@ -305,7 +315,7 @@ bwd_fused_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
         }
       } else if (cg == 3 && row < 64) {
         float w[16];
-        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + TMEM_D3, w);
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + TMEM_D2 + 64, w);        // pair 0, rows of tap 0, columns 64..79
         float4* o = reinterpret_cast<float4*>(a.partA + ((size_t)blockIdx.x * 64 + row) * BF_ZROWS);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {

@@ -105,7 +105,7 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__
   extern __shared__ uint8_t smem_raw[];
   // 1024 B alignment by OFFSET (not by integer round-trip) so the compiler keeps the shared address space: LDS, not LD
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* sW = smem;                                              // [P][KB][64 rows][128 B]
+  uint8_t* sW = smem;                                              // [KB][P][M rows][128 B]: the planes of a block are STACKED
   uint8_t* sA = smem + a.P * a.KB * 8192;                          // [stages][2 halves][64 rows][128 B]
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(sA + a.stages * TAP_STAGE_BYTES);
   uint64_t* empty_bar = full_bar + TAP_STAGES;
@@ -126,8 +126,14 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__
   const long long tile_lo = blockIdx.x * per_cta;
   const long long tile_hi = tile_lo + per_cta < num_tiles ? tile_lo + per_cta : num_tiles;
   const int KK = a.K * a.C;
-  const int acc_stride = a.M < 32 ? 32 : a.M;                      // TMEM columns per accumulator stage
-  const uint32_t tmem_cols = (2 * acc_stride <= 32) ? 32 : (2 * acc_stride <= 64) ? 64 : 128;
+  // Split operands: signal plane 0 meets BOTH weight planes in ONE instruction whose B operand is the stacked [W0; W1] block
+  // (N = 2 M): its two column halves are summed by the epilogue.  An M = 128 tcgen05.mma with N = 64 occupies the tensor pipe
+  // about as long as one with N = 128 (profiles/r02_horner_notes.txt), and with 3 separate plane products per k-step the
+  // kernel was bound by the instruction count (60 per tile), not by HBM: 895 us per launch for 3.8 GB at cfg3.
+  const int NW = a.P * a.M;                                        // accumulator columns written by a plane-0 instruction
+  const int acc_stride = NW < 32 ? 32 : NW;                        // TMEM columns per accumulator stage
+  const uint32_t tmem_cols = (2 * acc_stride <= 32) ? 32 : (2 * acc_stride <= 64) ? 64 : (2 * acc_stride <= 128) ? 128 : 256;
+  const int wblk = a.M * 128;                                      // bytes of one plane of one 64-column weight block
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tm0); tma_prefetch_desc(&tmc); tma_prefetch_desc(&tmW);
@@ -154,7 +160,9 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__
     // ===== TMA producer =====
     if (lane == 0) {
       mbar_expect_tx(w_bar, (uint32_t)(a.P * a.KB * a.M * 128));
-      for (int kb = 0; kb < a.P * a.KB; ++kb) tma_load_2d(sW + kb * 8192, &tmW, w_bar, kb * 64, 0);   // plane q = blocks [q*KB, (q+1)*KB)
+      for (int kb = 0; kb < a.KB; ++kb)
+        for (int w = 0; w < a.P; ++w)                              // global: plane w = column blocks [w*KB, (w+1)*KB)
+          tma_load_2d(sW + (kb * a.P + w) * wblk, &tmW, w_bar, (w * a.KB + kb) * 64, 0);
       int stage = 0; uint32_t phase = 0;
       for (long long tile = tile_lo; tile < tile_hi; ++tile) {
         const long long b = tile / tiles_n;
@@ -179,7 +187,8 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16_amn(TAP_BM, a.M);
+      const uint32_t idesc1 = make_idesc_bf16_amn(TAP_BM, a.M);    // one weight plane
+      const uint32_t idescP = make_idesc_bf16_amn(TAP_BM, NW);     // signal plane 0 against the stacked weight planes
       mbar_wait(w_bar, 0);
       tc_fence_after();
       int stage = 0; uint32_t phase = 0;
@@ -194,14 +203,13 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__
           mbar_wait(full_bar + stage, phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(sA + stage * TAP_STAGE_BYTES);
-          // split operands: z W ~= z0 W0 + z0 W1 + z1 W0 (signal plane q meets weight planes w with q + w < P)
-          for (int w = 0; w + q < a.P; ++w) {
-            const uint32_t sb = smem_u32(sW + (w * a.KB + s) * 8192);
-            for (int j = 0; j < rows / 16; ++j) {
-              const uint64_t adesc = make_mnmajor_sw128_desc(sa + j * 2048, 8192);   // 16 K-rows = 2048 B
-              const uint64_t bdesc = make_kmajor_sw128_desc(sb) + (uint64_t)(2 * j); // 16 bf16 = 32 B along K
-              umma_f16(d_tmem, adesc, bdesc, idesc, (sq | w | j) != 0);
-            }
+          // split operands: z W ~= z0 [W0; W1] (two column halves, summed in the epilogue) + z1 W0
+          const uint32_t sb = smem_u32(sW + s * a.P * wblk);
+          for (int j = 0; j < rows / 16; ++j) {
+            const uint64_t adesc = make_mnmajor_sw128_desc(sa + j * 2048, 8192);   // 16 K-rows = 2048 B
+            const uint64_t bdesc = make_kmajor_sw128_desc(sb) + (uint64_t)(2 * j); // 16 bf16 = 32 B along K
+            // the very first instruction of a tile (plane 0) overwrites all NW columns
+            umma_f16(d_tmem, adesc, bdesc, q == 0 ? idescP : idesc1, (sq | j) != 0);
           }
           umma_commit(empty_bar + stage);
           if (++stage == a.stages) { stage = 0; phase ^= 1; }
@@ -265,6 +273,12 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__
         tc_fence_after();
         float v[16];
         tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * acc_stride + m0), v);
+        if (a.P > 1) {                                  // second column half: signal plane 0 x weight plane 1
+          float v2[16];
+          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * acc_stride + a.M + m0), v2);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] += v2[i];
+        }
         tc_fence_before();
         mbar_arrive(tmem_empty + acc);                  // accumulator values are in registers: release the TMEM stage early
         float* of = a.out_f32 + b * a.out_bstride + (size_t)m0 * a.N + n;
