@@ -8,11 +8,11 @@ See DESIGN.md / INTEGRATION.md.  The C ABI is include/gcrnn_b200.h.
 """
 from .functional import LSIGF, graph_attention_relu, gated_gcrnn, set_precision, get_precision, cell_param_slots
 from .modules import GraphFilter, GraphAttentional, GGCRNNCell
-from . import dist, graph, graphs, options, readout
+from . import dist, graph, graphs, options, readout, train
 from ._lib import GcrnnError, LIB_PATH
 
 __all__ = ['LSIGF', 'GraphFilter', 'GraphAttentional', 'GGCRNNCell', 'install', 'uninstall', 'set_precision',
-           'get_precision', 'dist', 'graph', 'graphs', 'options', 'GcrnnError']
+           'get_precision', 'dist', 'graph', 'graphs', 'options', 'readout', 'train', 'GcrnnError']
 
 _PATCHED = ('LSIGF', 'GraphFilter', 'GraphAttentional', 'GGCRNNCell')
 _originals = {}

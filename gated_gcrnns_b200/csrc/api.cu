@@ -80,7 +80,11 @@ void key_params(GraphKey& k, int& n, const gcrnn_cell_params* p) {
   const void* const* q = reinterpret_cast<const void* const*>(p);
   for (size_t i = 0; i < sizeof(gcrnn_cell_params) / sizeof(void*); ++i) { GCRNN_CHECK(n < GK_PTRS, "graph key overflow"); k.p[n++] = q[i]; }
 }
-bool graph_eligible(const gcrnn_cell* c, int64_t B, int64_t T) {
+bool graph_eligible(const gcrnn_cell* c, int64_t B, int64_t T, cudaStream_t user) {
+  // a caller that is itself capturing (whole-step CUDA graph: gated_gcrnns_b200/train.py) gets plain launches on its stream
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(user, &cs) != cudaSuccess) { cudaGetLastError(); return false; }
+  if (cs != cudaStreamCaptureStatusNone) return false;
   return c->opt.graph_capture && c->d.precision == GCRNN_PREC_FP32 &&
          (long long)B * T * c->g->N * c->d.F <= (1ll << 22);
 }
@@ -304,7 +308,7 @@ int gcrnn_cell_forward(gcrnn_cell* c, const gcrnn_cell_params* p, const float* X
   GCRNN_CHECK(c && p && X && h0 && H && ws && saved, "null argument");
   DeviceScope dev_scope(c->g->device); OptScope opt_scope(&c->opt);
   if (c->d.precision != GCRNN_PREC_FP32) cell_forward_tc(c, p, X, h0, H, saved, savedb, nullptr, ws, wsb, B, T, (cudaStream_t)stream);
-  else if (graph_eligible(c, B, T)) {
+  else if (graph_eligible(c, B, T, (cudaStream_t)stream)) {
     GraphKey key; memset(&key, 0, sizeof key);
     int n = 0;
     key_params(key, n, p);
@@ -322,7 +326,7 @@ int gcrnn_cell_backward(gcrnn_cell* c, const gcrnn_cell_params* p, const float* 
   GCRNN_CHECK(c && p && X && h0 && H && dH && saved && grads && ws, "null argument");
   DeviceScope dev_scope(c->g->device); OptScope opt_scope(&c->opt);
   if (c->d.precision != GCRNN_PREC_FP32) cell_backward_tc(c, p, X, h0, H, dH, saved, savedb, grads, dX, dh0, ws, wsb, B, T, (cudaStream_t)stream);
-  else if (graph_eligible(c, B, T)) {
+  else if (graph_eligible(c, B, T, (cudaStream_t)stream)) {
     GraphKey key; memset(&key, 0, sizeof key);
     int n = 0;
     key_params(key, n, p);
