@@ -390,18 +390,21 @@ def run_ours(args):
         hc = torch.zeros(Bc, F, N, device=dev)
         dc = torch.ones(Bc, T, F, N, device=dev)
         clo, chi = gg.dist.shard_range(Bc, rank, world)
-        for p in used:
-            p.grad = None
-        torch.autograd.backward(cell(Xc[clo:chi], hc[clo:chi]), dc[clo:chi])
-        red = gg.dist.allreduce_gradients(used, op='sum').clone()
-        if rank == 0:
+        grad_check = dict(B=Bc, what='gradient bucket of 64 sequences sharded over the ranks and summed by gated_gcrnns_b200.dist.'
+                                     'allreduce_gradients vs the same 64 sequences on rank 0 alone (max-norm relative), at T = 8 and at the '
+                                     'full T = 64 (where float-atomic summation order is amplified by the chaotic recurrence: two single-GPU '
+                                     'runs differ by the same amount)')
+        for Tc in (8, T):
             for p in used:
                 p.grad = None
-            torch.autograd.backward(cell(Xc, hc), dc)
-            full = torch.cat([p.grad.reshape(-1) for p in used])
-            grad_check = dict(B=Bc, rel_err=((red - full).abs().max() / full.abs().max()).item(),
-                              what='gradient bucket of 64 sequences sharded over the ranks and summed by gated_gcrnns_b200.dist.'
-                                   'allreduce_gradients vs the same 64 sequences on rank 0 alone (max-norm relative)')
+            torch.autograd.backward(cell(Xc[clo:chi, :Tc], hc[clo:chi]), dc[clo:chi, :Tc])
+            red = gg.dist.allreduce_gradients(used, op='sum').clone()
+            if rank == 0:
+                for p in used:
+                    p.grad = None
+                torch.autograd.backward(cell(Xc[:, :Tc], hc), dc[:, :Tc])
+                full = torch.cat([p.grad.reshape(-1) for p in used])
+                grad_check[f'rel_err_T{Tc}'] = ((red - full).abs().max() / full.abs().max()).item()
 
     # ---- roofline of the dominant kernel (tcgen05 shift GEMM), timed live with CUDA events on its stream -------------
     pk = peaks()
@@ -703,6 +706,51 @@ def run_small(args):
     steps = max(args.steps, 20)
     ms, launches, clocks = timed(False, steps, max(args.warmup, 5))
     ms_e, _, _ = timed(True, steps, 3)
+
+    # whole TRAINING step (reordering gather + recurrence + per-node readout + L1 loss + backward + Adam) as ONE CUDA graph
+    # (gated_gcrnns_b200.train.GraphedStep) next to the same step launched eagerly
+    whole = None
+    if not args.no_whole_step:
+        class Net(torch.nn.Module):
+            def __init__(self):
+                super().__init__()
+                self.cell = gg.GGCRNNCell(G, F, K, K, torch.tanh, tg, sg, 1, True)
+                self.cell.addGSO(S)
+                self.readout = torch.nn.Linear(F, 1)
+
+            def forward(self, x, h):
+                return self.readout(self.cell(x, h).transpose(2, 3)).squeeze(-1).unsqueeze(2)
+        torch.manual_seed(0)
+        net = Net().to(dev)
+        opt = torch.optim.Adam(net.parameters(), lr=1e-3, capturable=True)
+        Y = torch.randn(B, T, 1, N, device=dev)
+        order = list(np.random.RandomState(0).permutation(N))
+        oidx = torch.as_tensor(order, device=dev)
+        l1 = torch.nn.L1Loss()
+
+        def eager_step():
+            opt.zero_grad(set_to_none=True)
+            loss = l1(net(X_dev.index_select(-1, oidx), h0_dev), Y)
+            loss.backward()
+            opt.step()
+            return loss
+
+        def time_fn(fn, n):
+            for _ in range(5):
+                fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(n):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / n
+        ms_eager = time_fn(eager_step, steps)
+        gstep = gg.train.GraphedStep(net, l1, opt, X_dev, h0_dev, target=Y, order=order)
+        ms_graph = time_fn(lambda: gstep(X_dev, h0_dev, target=Y), steps)
+        whole = dict(what='one training step: node-reordering gather + GGCRNNCell + per-node Linear(F,1) readout + L1 loss + backward + Adam',
+                     eager_seq_per_s=B / (ms_eager * 1e-3), graphed_seq_per_s=B / (ms_graph * 1e-3), ms_eager=ms_eager, ms_graphed=ms_graph)
     cb = None
     if not args.no_cpu_baseline:
         cfg = dict(N=N, F=F, G=G, K=K, T=T, density=None)
@@ -714,7 +762,7 @@ def run_small(args):
                data='synthetic',
                config=dict(workload=f'{args.workload}: N={N} F={F} G={G} K={K} T={T} B={B} time_gating={tg} spatial_gating={sg}, fp32 sparse exact path',
                            l2='working set fits L2 (launch/latency-bound case; no roofline claim, SURVEY.md 8d)'),
-               roofline=None, cpu_baseline=cb, clocks=clocks,
+               roofline=None, cpu_baseline=cb, clocks=clocks, whole_step=whole,
                e2e=dict(value=B * steps / (ms_e * 1e-3), unit='sequences/s', h2d_bytes_per_step=int(X_host.numel() * 4 + h0_host.numel() * 4),
                         d2h_bytes_per_step=int(cell.weight_B.numel() * 4), ms_per_step=ms_e / steps),
                gpu_launches=int(launches))
@@ -738,6 +786,7 @@ def main():
     ap.add_argument('--also', default='bf16', type=lambda v: [m for m in v.split(',') if m],
                     help='other precisions of the same workload to time briefly for the `modes` object (comma separated; "" = none)')
     ap.add_argument('--no-parity', action='store_true', help='skip the in-run parity measurement')
+    ap.add_argument('--no-whole-step', action='store_true', help='small workloads: skip the whole-training-step CUDA-graph leg')
     ap.add_argument('--native-allreduce', type=int, default=0, help='N > 1: 1 = the library\'s own NCCL transport (gcrnn_allreduce_sum)')
     ap.add_argument('--cpu-batch', type=int, default=16)
     ap.add_argument('--cpu-T', type=int, default=8)

@@ -10,7 +10,7 @@ if attached, optimiser — into one graph and replays it with new data copied in
     for x, y in batches:
         loss = step(x, h0, y)          # one cudaGraphLaunch; `loss` is a device scalar (no host sync)
 
-Everything inside the step must be capturable: device-resident inputs (the reference loop creates ``h0`` on the CPU every
+Everything inside the step must be capturable: an optimiser built with ``capturable=True`` (torch.optim.Adam / AdamW / SGD), device-resident inputs (the reference loop creates ``h0`` on the CPU every
 step — pass a device tensor here), no ``.item()`` / host reads, shapes fixed.  The library's own kernels are launched on the
 capturing stream (its internal per-call graph cache steps aside while a capture is in progress).
 """
