@@ -32,6 +32,7 @@ int* option_field(Options& o, const char* name) {
   if (n == "gate_fq8") return &o.gate_fq8;
   if (n == "gemm_pair") return &o.gemm_pair;
   if (n == "fwd_fused") return &o.fwd_fused;
+  if (n == "persist") return &o.persist;
   return nullptr;
 }
 void set_last_error(const char* fmt, ...) {
@@ -260,7 +261,7 @@ int gcrnn_cell_set_option(gcrnn_cell* c, const char* name, int32_t value) {
   const std::string n(name);
   if (n == "need_dx") c->need_dx = value != 0;
   else if (n == "dh_last_only") c->dh_last_only = value != 0;
-  else if (n == "path") { GCRNN_CHECK(value >= -1 && value <= GCRNN_PATH_NODE32, "bad path %d", value); c->forced_path = value; }
+  else if (n == "path") { GCRNN_CHECK(value >= -1 && value <= GCRNN_PATH_PERSIST, "bad path %d", value); c->forced_path = value; }
   else {
     int* f = option_field(c->opt, name);
     GCRNN_CHECK(f != nullptr, "unknown cell option '%s'", name);

@@ -29,6 +29,7 @@ struct Options {
   int gemm_pair = 1;            // CTA-pair (cta_group::2) shift GEMM when the shape allows
   int fwd_fused = 0;            // 1: forward tap contraction fused into the shift GEMMs (Horner form, tc_hshift.cuh); measured
                                 // slower than chain + tap kernel in bf16 and 2 % faster in bf16x2, hence off by default
+  int persist = 1;              // persistent fused recurrence (persist_f32.cuh) for small ungated / time-gated fp32 cells
   long long epoch = 0;          // bumped by every option change on the handle: captured CUDA graphs are keyed by it
 };
 const Options& opt();

@@ -5,6 +5,7 @@
 #include "kernels_f32.cuh"
 #include "sp32_kernels.cuh"
 #include "sp32_tile.cuh"
+#include "persist_f32.cuh"
 #include <climits>
 
 namespace gcrnn {
@@ -668,13 +669,83 @@ size_t cell_backward_e32(const gcrnn_cell* cell, const gcrnn_cell_params* p, con
 
 }  // namespace
 
+// ===================================================================================================
+// persistent fused recurrence for small graphs (persist_f32.cuh): one launch forward, one launch backward
+// ===================================================================================================
 namespace {
-// which path a forward takes (GCRNN_PATH_*): the fused per-node kernels when the shape allows, else the generic kernels
+constexpr long long PERSIST_SMEM_MAX = 220 * 1024;
+bool persist_ok(const gcrnn_cell* cell) {
+  const gcrnn_cell_desc& d = cell->d;
+  const gcrnn_graph* g = cell->g;
+  if (!opt().persist || d.E != 1 || g->E != 1 || d.spatial_gating != GCRNN_SPATIAL_NONE || cell->need_dx) return false;
+  const long long fl = persist::bwd_floats(d.F, d.G, d.Kin, d.Kst, g->N, d.time_gating != 0);
+  return fl * 4 <= PERSIST_SMEM_MAX;
+}
+persist::Args persist_args(const gcrnn_cell* cell, const gcrnn_cell_params* p, int64_t B, int64_t T) {
+  const gcrnn_graph* g = cell->g;
+  persist::Args a{};
+  a.N = g->N; a.F = cell->d.F; a.G = cell->d.G; a.Kin = cell->d.Kin; a.Kst = cell->d.Kst;
+  a.tg = cell->d.time_gating != 0; a.has_bias = cell->d.bias != 0; a.B = B; a.T = T;
+  a.cptr = g->fwd[0].ptr; a.cidx = g->fwd[0].idx; a.cval = g->fwd[0].val;
+  a.rptr = g->bwd[0].ptr; a.ridx = g->bwd[0].idx; a.rval = g->bwd[0].val;
+  if (p) {
+    a.A = p->weight_A; a.Bw = p->weight_B; a.bias = p->bias;
+    for (int i = 0; i < 2; ++i) { a.tA[i] = p->t_weight_A[i]; a.tB[i] = p->t_weight_B[i]; a.tb[i] = p->t_bias[i]; a.tW[i] = p->t_mlp_w[i]; a.tc[i] = p->t_mlp_b[i]; }
+  }
+  return a;
+}
+size_t cell_forward_persist(const gcrnn_cell* cell, const gcrnn_cell_params* p, const float* X, const float* h0, float* H,
+                            void* saved, size_t savedb, size_t* saved_used, void* ws, int64_t B, int64_t T, cudaStream_t st) {
+  Arena sa(saved, savedb);
+  float* gt = sa.get<float>(2 * B * T);
+  if (saved_used) *saved_used = sa.off;
+  if (ws == nullptr) return 256;
+  GCRNN_CHECK(saved != nullptr, "forward needs the `saved` buffer");
+  persist::Args a = persist_args(cell, p, B, T);
+  a.X = X; a.h0 = h0; a.H = H; a.gt = gt;
+  const size_t smem = (size_t)persist::fwd_floats(a.F, a.G, a.Kin, a.Kst, a.N, a.tg) * sizeof(float);
+  static DeviceOnce once;
+  if (once.first()) CUDA_OK(cudaFuncSetAttribute(persist::persist_fwd_k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  persist::persist_fwd_k<<<(unsigned)B, persist::PT, smem, st>>>(a);
+  check_launch();
+  return 256;
+}
+size_t cell_backward_persist(const gcrnn_cell* cell, const gcrnn_cell_params* p, const float* X, const float* h0, const float* H,
+                             const float* dH, const void* saved, size_t savedb, const gcrnn_cell_params* gr, float* dh0, void* ws,
+                             int64_t B, int64_t T, cudaStream_t st) {
+  Arena sa(const_cast<void*>(saved), savedb);
+  float* gt = sa.get<float>(2 * B * T);
+  if (ws == nullptr) return 256;
+  persist::Args a = persist_args(cell, p, B, T);
+  const long long FN = (long long)a.F * a.N;
+  a.X = X; a.h0 = h0; a.H = const_cast<float*>(H); a.gt = gt;
+  a.dH = dH; a.dh_last_only = cell->dh_last_only;
+  a.dH_bstride = cell->dh_last_only ? FN : T * FN; a.dH_tstride = FN;
+  a.dA = gr->weight_A; a.dBw = gr->weight_B; a.dbias = gr->bias;
+  for (int i = 0; i < 2; ++i) { a.dtA[i] = gr->t_weight_A[i]; a.dtB[i] = gr->t_weight_B[i]; a.dtb[i] = gr->t_bias[i]; a.dtW[i] = gr->t_mlp_w[i]; a.dtc[i] = gr->t_mlp_b[i]; }
+  a.dh0 = dh0;
+  const size_t smem = (size_t)persist::bwd_floats(a.F, a.G, a.Kin, a.Kst, a.N, a.tg) * sizeof(float);
+  static DeviceOnce once;
+  if (once.first()) CUDA_OK(cudaFuncSetAttribute(persist::persist_bwd_k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  persist::persist_bwd_k<<<(unsigned)B, persist::PT, smem, st>>>(a);
+  check_launch();
+  return 256;
+}
+
+// which path a forward takes (GCRNN_PATH_*): the persistent kernel for small ungated / time-gated cells, the fused per-node
+// kernels for F == 32 edge gating when the shape allows, else the generic kernels
 int pick_path(const gcrnn_cell* cell) {
   if (cell->forced_path >= 0) {
     if (cell->forced_path == GCRNN_PATH_NODE32) GCRNN_CHECK(edge32_ok(cell), "path NODE32 does not support this cell");
+    if (cell->forced_path == GCRNN_PATH_PERSIST) {
+      const gcrnn_cell_desc& d = cell->d;
+      GCRNN_CHECK(d.E == 1 && d.spatial_gating == GCRNN_SPATIAL_NONE &&
+                  persist::bwd_floats(d.F, d.G, d.Kin, d.Kst, cell->g->N, d.time_gating != 0) * 4 <= PERSIST_SMEM_MAX,
+                  "path PERSIST does not support this cell");
+    }
     return cell->forced_path;
   }
+  if (persist_ok(cell)) return GCRNN_PATH_PERSIST;
   return edge32_ok(cell) ? GCRNN_PATH_NODE32 : GCRNN_PATH_GENERIC;
 }
 }  // namespace
@@ -686,6 +757,7 @@ size_t cell_forward_f32(const gcrnn_cell* cell, const gcrnn_cell_params* p, cons
     const int path = pick_path(cell);
     if (ws != nullptr) cell->last_path = path;
     if (path == GCRNN_PATH_NODE32) return cell_forward_e32(cell, p, X, h0, H, saved, savedb, saved_used, ws, wsb, B, T, st);
+    if (path == GCRNN_PATH_PERSIST) return cell_forward_persist(cell, p, X, h0, H, saved, savedb, saved_used, ws, B, T, st);
   }
   const CellDims d = dims_of(cell, B, T);
   Arena a(ws, wsb);
@@ -761,6 +833,10 @@ size_t cell_backward_f32(const gcrnn_cell* cell, const gcrnn_cell_params* p, con
     // generic sweep then runs on the generic prefix of what NODE32's forward saved.
     const int path = pick_path(cell);
     if (path == GCRNN_PATH_NODE32 && !dX) return cell_backward_e32(cell, p, dH, saved, savedb, gr, dh0, ws, wsb, B, T, st);
+    if (path == GCRNN_PATH_PERSIST) {
+      GCRNN_CHECK(dX == nullptr, "the persistent small-graph path does not produce dX");
+      return cell_backward_persist(cell, p, X, h0, H, dH, saved, savedb, gr, dh0, ws, B, T, st);
+    }
   }
   Arena a(ws, wsb);
   Ctx c{cell->g, st, a.dry()};

@@ -9,7 +9,7 @@ from __future__ import annotations
 
 DEFAULTS = {
     'bwd_fused': 1, 'sparse_fused': 1, 'sparse_v2': 63, 'sparse_v2_rows_bps': 2, 'sparse_v2_fuse_dpre': 1,
-    'sparse_v2_tc': 1, 'sparse_v2_bps': 2, 'graph_capture': 1, 'gate_fq8': 2, 'gemm_pair': 1, 'fwd_fused': 0,
+    'sparse_v2_tc': 1, 'sparse_v2_bps': 2, 'graph_capture': 1, 'gate_fq8': 2, 'gemm_pair': 1, 'fwd_fused': 0, 'persist': 1,
 }
 _values = dict(DEFAULTS)
 _version = 0

@@ -87,6 +87,8 @@ int         gcrnn_debug_shift_gemm(const gcrnn_graph* g, int32_t backward, const
  *   "gate_fq8"      time-gate kernels with 8 feature groups per CTA: 0 off, 1 forward, 2 forward + backward
  *   "sparse_v2"     bit mask of the fused sparse stages that run their second-generation kernel: 1 shift, 2 gather-contract,
  *                   4|8 aggregate + bwd_rows, 16 bwd_node, 32 dh; 0 = all first generation
+ *   "persist"       persistent small-graph kernels (GCRNN_PATH_PERSIST) when the cell allows; 0 = per-op kernels
+ *   "fwd_fused"     1 = Horner-form forward of the tensor-core path (csrc/tc_hshift.cuh; off by default, see its header)
  *   "sparse_v2_tc"  tile contractions: 1 = 3xTF32 mma.sync, 0 = packed FFMA2;  "sparse_v2_fuse_dpre", "sparse_v2_bps",
  *                   "sparse_v2_rows_bps"
  * A backward always follows the stage generations its forward used; every change invalidates the handle's captured CUDA graphs. */
@@ -130,6 +132,9 @@ int gcrnn_cell_create(gcrnn_cell** out, const gcrnn_cell_desc* desc, const gcrnn
 int gcrnn_cell_destroy(gcrnn_cell* c);
 /* Execution paths of the fp32 sparse precision (same results within the stated fp32 tolerance):
  *   GENERIC  per-op kernels, any shape / gating mode, supports dX;
+ *   PERSIST  persistent fused recurrence for small graphs (csrc/persist_f32.cuh): ONE launch runs the whole sequence of every sample
+ *            with the shift operator, the taps, the time-gate weights and h_t on chip across all T steps, ONE launch the reverse
+ *            sweep; E == 1, no spatial gating, no dX, sizes that fit one SM's shared memory (the reference's own N = 80 config);
  *   NODE32   fused edge-gated kernels for F == 32, one warp per (sample, node) (csrc/sp32_kernels.cuh); a dX request makes
  *            backward run the generic sweep on the generic prefix of the saved state.
  * Options (per cell handle, used from one host thread at a time; the tuning switches listed above are set the same way):
@@ -140,7 +145,7 @@ int gcrnn_cell_destroy(gcrnn_cell* c);
  *                      every earlier output is zero and no [B,T,F,N] gradient tensor exists (classification readout,
  *                      Modules/architectures.py:1841-1850 uses only H.select(1, -1));
  *   "last_path" (get)  path taken by the last forward on this handle. */
-enum { GCRNN_PATH_GENERIC = 0, GCRNN_PATH_NODE32 = 1 };
+enum { GCRNN_PATH_GENERIC = 0, GCRNN_PATH_NODE32 = 1, GCRNN_PATH_PERSIST = 2 };
 int gcrnn_cell_set_option(gcrnn_cell* c, const char* name, int32_t value);
 int gcrnn_cell_get_option(const gcrnn_cell* c, const char* name, int32_t* value);
 /* saved_bytes: buffer written by forward and read by backward; fwd/bwd_bytes: scratch. */

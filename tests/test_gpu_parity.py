@@ -194,3 +194,78 @@ def test_graph_replay_matches_direct_launches():
     assert torch.equal(outs[1][0], Hd2)
     assert relerr(outs[3][1], gd) < 1e-6 and relerr(outs[1][1], gd2) < 1e-6      # float atomics: order may differ in the last bits
     gg.options.set('graph_capture', old)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# persistent fused recurrence for small graphs (csrc/persist_f32.cuh, GCRNN_PATH_PERSIST): one launch per direction
+# ---------------------------------------------------------------------------------------------------------------
+PATH_PERSIST = 2
+
+
+def _last_path(cell):
+    h = next(iter(cell._handles.values()))
+    return h.get_option('last_path')
+
+
+@pytest.mark.parametrize('name', [n for n in G.names('cell_') if n.endswith('_time') or n.endswith('_none')])
+def test_persistent_path_golden(name):
+    """The reference's own outputs and gradients (fixtures generated from the unmodified reference) on the persistent path:
+    X does not require grad here (as in the reference's training loops), so the library picks it for ungated / time-gated cells."""
+    c = G.load(name)
+    m = G.cell_meta(c)
+    cell = build_cell(m, torch.tensor(c['S']), c['param'])
+    X, h0 = f32(c['X']), f32(c['h0']).requires_grad_(True)
+    l0 = _lib.lib().gcrnn_debug_launch_count()
+    H = cell(X, h0)
+    assert _last_path(cell) == PATH_PERSIST, 'expected the persistent small-graph path'
+    (H * f32(c['dH'])).sum().backward()
+    torch.cuda.synchronize()
+    assert _lib.lib().gcrnn_debug_launch_count() - l0 == 2          # ONE launch forward, ONE launch backward
+    errs = {'H': relerr(H, c['H']), 'dh0': relerr(h0.grad, c['dh0'])}
+    named = dict(cell.named_parameters())
+    for k, ref in c['grad'].items():
+        if ref.size == 0:
+            assert named[k].grad is None, f'{k}: the reference leaves this gradient None'
+        else:
+            errs[k] = relerr(named[k].grad, ref)
+    bad = {k: v for k, v in errs.items() if v > (TOL_OUT if k == 'H' else TOL_GRAD)}
+    assert not bad, f'{name}: {bad}'
+
+
+@pytest.mark.parametrize('tg', [False, True])
+@pytest.mark.parametrize('N,G_,F_,Kin,Kst,T,B,bias', [(37, 3, 6, 4, 3, 6, 5, True), (80, 1, 20, 5, 5, 5, 7, True), (59, 2, 8, 1, 4, 3, 4, False),
+                                                     (16, 1, 4, 2, 1, 2, 3, True)])
+def test_persistent_path_matches_per_op_kernels(tg, N, G_, F_, Kin, Kst, T, B, bias):
+    """Same cell, same inputs: persistent kernels vs the generic per-op kernels (option persist = 0), including a non-symmetric
+    operator, G > 1, Kin != Kst, K = 1, no bias, h0 != 0, and the last-state-only gradient."""
+    torch.manual_seed(N + T)
+    S = torch.rand(1, N, N) * (torch.rand(1, N, N) < 0.2)
+    S = S / torch.linalg.eigvals(S[0]).abs().max()
+    X, h0 = torch.randn(B, T, G_, N, device=DEV), 0.3 * torch.randn(B, F_, N, device=DEV)
+    dH, dHl = torch.randn(B, T, F_, N, device=DEV), torch.randn(B, F_, N, device=DEV)
+    out = {}
+    old = gg.options.set('persist', 1)
+    try:
+        for persist in (0, 1):
+            gg.options.set('persist', persist)
+            torch.manual_seed(1)
+            cell = gg.GGCRNNCell(G_, F_, Kin, Kst, torch.tanh, tg, None, 1, bias)
+            cell.addGSO(S)
+            cell = cell.to(DEV)
+            hh = h0.clone().requires_grad_(True)
+            H = cell(X, hh)
+            assert (_last_path(cell) == PATH_PERSIST) == bool(persist)
+            (H * dH).sum().backward()
+            res = [H.detach(), hh.grad.clone()] + [p.grad.clone() for p in cell.parameters() if p.grad is not None]
+            cell.zero_grad()
+            cell.last_state_only = True
+            hh2 = h0.clone().requires_grad_(True)
+            Hl = cell(X, hh2)
+            (Hl.select(1, -1) * dHl).sum().backward()
+            res += [hh2.grad.clone()] + [p.grad.clone() for p in cell.parameters() if p.grad is not None]
+            out[persist] = res
+    finally:
+        gg.options.set('persist', old)
+    assert len(out[0]) == len(out[1])
+    for i, (a, b) in enumerate(zip(out[1], out[0])):
+        assert relerr(a, b) < (TOL_OUT if i == 0 else TOL_GRAD), (i, relerr(a, b))
