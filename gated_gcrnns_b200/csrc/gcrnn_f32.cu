@@ -679,7 +679,14 @@ bool persist_ok(const gcrnn_cell* cell) {
   const gcrnn_graph* g = cell->g;
   if (!opt().persist || d.E != 1 || g->E != 1 || d.spatial_gating != GCRNN_SPATIAL_NONE || cell->need_dx) return false;
   const long long fl = persist::bwd_floats(d.F, d.G, d.Kin, d.Kst, g->N, d.time_gating != 0);
-  return fl * 4 <= PERSIST_SMEM_MAX;
+  return fl * 4 <= PERSIST_SMEM_MAX && g->N < 65536;
+}
+// stage the gather lists in shared memory when both fit next to the rest
+bool persist_lists_fit(const gcrnn_cell* cell) {
+  const gcrnn_cell_desc& d = cell->d;
+  const gcrnn_graph* g = cell->g;
+  const long long fl = persist::bwd_floats(d.F, d.G, d.Kin, d.Kst, g->N, d.time_gating != 0);
+  return fl * 4 + 2 * persist::list_bytes(g->N, (int)g->fwd[0].nnz) <= 226 * 1024;
 }
 persist::Args persist_args(const gcrnn_cell* cell, const gcrnn_cell_params* p, int64_t B, int64_t T) {
   const gcrnn_graph* g = cell->g;
@@ -688,6 +695,7 @@ persist::Args persist_args(const gcrnn_cell* cell, const gcrnn_cell_params* p, i
   a.tg = cell->d.time_gating != 0; a.has_bias = cell->d.bias != 0; a.B = B; a.T = T;
   a.cptr = g->fwd[0].ptr; a.cidx = g->fwd[0].idx; a.cval = g->fwd[0].val;
   a.rptr = g->bwd[0].ptr; a.ridx = g->bwd[0].idx; a.rval = g->bwd[0].val;
+  a.nnz = (int)g->fwd[0].nnz; a.lists_smem = persist_lists_fit(cell);
   if (p) {
     a.A = p->weight_A; a.Bw = p->weight_B; a.bias = p->bias;
     for (int i = 0; i < 2; ++i) { a.tA[i] = p->t_weight_A[i]; a.tB[i] = p->t_weight_B[i]; a.tb[i] = p->t_bias[i]; a.tW[i] = p->t_mlp_w[i]; a.tc[i] = p->t_mlp_b[i]; }
@@ -703,7 +711,7 @@ size_t cell_forward_persist(const gcrnn_cell* cell, const gcrnn_cell_params* p, 
   GCRNN_CHECK(saved != nullptr, "forward needs the `saved` buffer");
   persist::Args a = persist_args(cell, p, B, T);
   a.X = X; a.h0 = h0; a.H = H; a.gt = gt;
-  const size_t smem = (size_t)persist::fwd_floats(a.F, a.G, a.Kin, a.Kst, a.N, a.tg) * sizeof(float);
+  const size_t smem = (size_t)persist::fwd_floats(a.F, a.G, a.Kin, a.Kst, a.N, a.tg) * sizeof(float) + (a.lists_smem ? persist::list_bytes(a.N, a.nnz) : 0);
   static DeviceOnce once;
   if (once.first()) CUDA_OK(cudaFuncSetAttribute(persist::persist_fwd_k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   persist::persist_fwd_k<<<(unsigned)B, persist::PT, smem, st>>>(a);
@@ -724,7 +732,7 @@ size_t cell_backward_persist(const gcrnn_cell* cell, const gcrnn_cell_params* p,
   a.dA = gr->weight_A; a.dBw = gr->weight_B; a.dbias = gr->bias;
   for (int i = 0; i < 2; ++i) { a.dtA[i] = gr->t_weight_A[i]; a.dtB[i] = gr->t_weight_B[i]; a.dtb[i] = gr->t_bias[i]; a.dtW[i] = gr->t_mlp_w[i]; a.dtc[i] = gr->t_mlp_b[i]; }
   a.dh0 = dh0;
-  const size_t smem = (size_t)persist::bwd_floats(a.F, a.G, a.Kin, a.Kst, a.N, a.tg) * sizeof(float);
+  const size_t smem = (size_t)persist::bwd_floats(a.F, a.G, a.Kin, a.Kst, a.N, a.tg) * sizeof(float) + (a.lists_smem ? 2 * persist::list_bytes(a.N, a.nnz) : 0);
   static DeviceOnce once;
   if (once.first()) CUDA_OK(cudaFuncSetAttribute(persist::persist_bwd_k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   persist::persist_bwd_k<<<(unsigned)B, persist::PT, smem, st>>>(a);

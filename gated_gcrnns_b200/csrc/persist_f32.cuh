@@ -22,13 +22,15 @@
 namespace gcrnn {
 namespace persist {
 
-constexpr int PT = 256;       // threads per CTA
+constexpr int PT = 512;       // threads per CTA
 
 struct Args {
   int N, F, G, Kin, Kst, tg, has_bias;
   long long B, T;
   const int *cptr, *cidx; const float* cval;     // gather form of z @ S   (CSC of S):  out[n] = sum_p cval[p] in[cidx[p]]
   const int *rptr, *ridx; const float* rval;     // gather form of g @ S^T (CSR of S)
+  int nnz;                                       // entries of S
+  int lists_smem;                                // 1: both gather lists are staged in shared memory (16-bit indices)
   const float *A, *Bw, *bias;                    // [F,Kin,G] [F,Kst,F] [F]
   const float *tA[2], *tB[2], *tb[2], *tW[2], *tc[2];
   const float *X, *h0;                           // [B,T,G,N] [B,F,N]
@@ -56,6 +58,26 @@ __host__ __device__ inline long long bwd_floats(int F, int G, int Kin, int Kst, 
          (tg ? 2 * FN : 0) + 64;
 }
 
+// shared-memory bytes of ONE staged gather list: ptr[N+1] (int), val[nnz] (float), idx[nnz] (u16), 16-byte aligned pieces
+__host__ __device__ inline long long list_bytes(int N, int nnz) {
+  return (((long long)(N + 1) * 4 + 15) & ~15LL) + (((long long)nnz * 4 + 15) & ~15LL) + (((long long)nnz * 2 + 15) & ~15LL);
+}
+struct List {                                    // a gather list, in shared memory (idx16) or global memory (idx32)
+  const int* ptr; const float* val; const unsigned short* idx16; const int* idx32;
+  __device__ __forceinline__ int idx(int p) const { return idx16 ? (int)idx16[p] : __ldg(idx32 + p); }
+};
+__device__ __forceinline__ List stage_list(unsigned char*& sp, const int* gptr, const int* gidx, const float* gval, int N, int nnz, bool to_smem) {
+  List l;
+  if (!to_smem) { l.ptr = gptr; l.val = gval; l.idx16 = nullptr; l.idx32 = gidx; return l; }
+  int* sptr = reinterpret_cast<int*>(sp); sp += ((N + 1) * 4 + 15) & ~15;
+  float* sval = reinterpret_cast<float*>(sp); sp += (nnz * 4 + 15) & ~15;
+  unsigned short* sidx = reinterpret_cast<unsigned short*>(sp); sp += (nnz * 2 + 15) & ~15;
+  for (int i = threadIdx.x; i <= N; i += PT) sptr[i] = gptr[i];
+  for (int i = threadIdx.x; i < nnz; i += PT) { sval[i] = gval[i]; sidx[i] = (unsigned short)gidx[i]; }
+  l.ptr = sptr; l.val = sval; l.idx16 = sidx; l.idx32 = nullptr;
+  return l;
+}
+
 __device__ __forceinline__ float block_sum(float v, float* red) {      // red: >= 33 floats; result broadcast to all threads
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -74,20 +96,20 @@ __device__ __forceinline__ float block_sum(float v, float* red) {      // red: >
 }
 
 // out[r][n] = sum_p val[p] in[r][idx[p]], p in [ptr[n], ptr[n+1])   (rows r < R; in / out in shared memory, [R][N])
-__device__ __forceinline__ void shift(const int* __restrict__ ptr, const int* __restrict__ idx, const float* __restrict__ val,
-                                      const float* in, float* out, int R, int N) {
+__device__ __forceinline__ void shift(const List& l, const float* in, float* out, int R, int N) {
   for (int e = threadIdx.x; e < R * N; e += PT) {
     const int r = e / N, n = e - r * N;
     const float* row = in + r * N;
     float s = 0.f;
-    for (int p = __ldg(ptr + n); p < __ldg(ptr + n + 1); ++p) s = fmaf(__ldg(val + p), row[__ldg(idx + p)], s);
+    const int p1 = l.ptr[n + 1];
+    for (int p = l.ptr[n]; p < p1; ++p) s = fmaf(l.val[p], row[l.idx(p)], s);
     out[e] = s;
   }
 }
 // z[k] = z[k-1] S for k = 1..K-1, z: [K][R][N]
-__device__ __forceinline__ void chain(const Args& a, float* z, int K, int R) {
+__device__ __forceinline__ void chain(const List& fw, float* z, int K, int R, int N) {
   for (int k = 1; k < K; ++k) {
-    shift(a.cptr, a.cidx, a.cval, z + (size_t)(k - 1) * R * a.N, z + (size_t)k * R * a.N, R, a.N);
+    shift(fw, z + (size_t)(k - 1) * R * N, z + (size_t)k * R * N, R, N);
     __syncthreads();
   }
 }
@@ -134,12 +156,14 @@ __global__ void __launch_bounds__(PT, 1) persist_fwd_k(const Args a) {
   float* zh = p; p += (size_t)a.Kst * FN;
   float* hn = p; p += FN;
   float* c0 = p; p += a.tg ? 2 * FN : 0;
-  float* red = p;
+  float* red = p; p += 64;
+  unsigned char* sp = reinterpret_cast<unsigned char*>(p);
+  const List fw = stage_list(sp, a.cptr, a.cidx, a.cval, N, a.nnz, a.lists_smem != 0);
   load_weights(w, a);
   for (int e = threadIdx.x; e < FN; e += PT) zh[e] = a.h0[b * FN + e];
   __syncthreads();
   if (a.tg) {                                                     // T-invariant gate term: B_g(S) h0 + 2 b_g   (graphML.py:2362, :2417-2423)
-    chain(a, zh, a.Kst, F);
+    chain(fw, zh, a.Kst, F, N);
     for (int g = 0; g < 2; ++g)
       for (int e = threadIdx.x; e < FN; e += PT) {
         const int f = e / N, n = e - f * N;
@@ -151,7 +175,7 @@ __global__ void __launch_bounds__(PT, 1) persist_fwd_k(const Args a) {
     const float* xt = a.X + (b * a.T + t) * GN;
     for (int e = threadIdx.x; e < GN; e += PT) zx[e] = xt[e];
     __syncthreads();
-    chain(a, zx, a.Kin, a.G);
+    chain(fw, zx, a.Kin, a.G, N);
     float gi = 1.f, gf = 1.f;
     if (a.tg) {
       for (int g = 0; g < 2; ++g) {
@@ -167,7 +191,7 @@ __global__ void __launch_bounds__(PT, 1) persist_fwd_k(const Args a) {
         if (threadIdx.x == 0) a.gt[((long long)g * a.B + b) * a.T + t] = gv;
       }
     }
-    if (!(a.tg && t == 0)) chain(a, zh, a.Kst, F);                // at t = 0 with gating the h0 chain is already there
+    if (!(a.tg && t == 0)) chain(fw, zh, a.Kst, F, N);                // at t = 0 with gating the h0 chain is already there
     float* Ht = a.H + (b * a.T + t) * FN;
     for (int e = threadIdx.x; e < FN; e += PT) {
       const int f = e / N, n = e - f * N;
@@ -190,13 +214,14 @@ __device__ __forceinline__ void wgrad_acc(float* acc, const float* d, const floa
     const float* dr = d + (size_t)f * N;
     const float* zr = z + (size_t)kc * N;
     float s = 0.f;
-    for (int n = 0; n < N; ++n) s = fmaf(dr[n], zr[n], s);
+    int nn = threadIdx.x % N;                                      // skewed start: the lanes of a warp read different banks
+    for (int n = 0; n < N; ++n) { s = fmaf(dr[nn], zr[nn], s); if (++nn == N) nn = 0; }
     acc[o] += s;
   }
 }
 // dh[g][n] (+)= Horner over k of ( sum_f W[f][k][g] d[f][n] ) with S^T:  out = u_0 + (u_1 + (... u_{K-1} S^T ...) S^T) S^T
 // b1 / b2: [C][N] scratch; result ADDED to `out` if accumulate else written
-__device__ __forceinline__ void adjoint_chain(const Args& a, const float* W, const float* d, float* b1, float* b2, float* out,
+__device__ __forceinline__ void adjoint_chain(const Args& a, const List& bw, const float* W, const float* d, float* b1, float* b2, float* out,
                                               int K, int C, bool accumulate) {
   const int N = a.N, F = a.F;
   float* cur = b1; float* nxt = b2;
@@ -207,7 +232,8 @@ __device__ __forceinline__ void adjoint_chain(const Args& a, const float* W, con
       float s = 0.f;
       if (k < K - 1) {
         const float* row = cur + (size_t)g * N;
-        for (int p = __ldg(a.rptr + n); p < __ldg(a.rptr + n + 1); ++p) s = fmaf(__ldg(a.rval + p), row[__ldg(a.ridx + p)], s);
+        const int p1 = bw.ptr[n + 1];
+        for (int p = bw.ptr[n]; p < p1; ++p) s = fmaf(bw.val[p], row[bw.idx(p)], s);
       }
       for (int f = 0; f < F; ++f) s = fmaf(W[((size_t)f * K + k) * C + g], d[(size_t)f * N + n], s);
       if (k == 0) { if (accumulate) out[e] += s; else out[e] = s; }
@@ -236,7 +262,10 @@ __global__ void __launch_bounds__(PT, 1) persist_bwd_k(const Args a) {
   float* c0 = p; p += a.tg ? 2 * FN : 0;
   float* dc0 = p; p += a.tg ? 2 * FN : 0;
   float* dpu = p; p += a.tg ? FN : 0;
-  float* red = p;
+  float* red = p; p += 64;
+  unsigned char* sp = reinterpret_cast<unsigned char*>(p);
+  const List fw = stage_list(sp, a.cptr, a.cidx, a.cval, N, a.nnz, a.lists_smem != 0);
+  const List bw = stage_list(sp, a.rptr, a.ridx, a.rval, N, a.nnz, a.lists_smem != 0);
   load_weights(w, a);
   for (float* q = gacc.A; q < zx; q += PT) { if (q + threadIdx.x < zx) q[threadIdx.x] = 0.f; }      // zero every accumulator
   for (int e = threadIdx.x; e < FN; e += PT) { dh[e] = 0.f; if (a.tg) { dc0[e] = 0.f; dc0[FN + e] = 0.f; } }
@@ -245,7 +274,7 @@ __global__ void __launch_bounds__(PT, 1) persist_bwd_k(const Args a) {
   if (a.tg) {                                                     // c0 of both gates (needed to recompute u at every step)
     for (int e = threadIdx.x; e < FN; e += PT) zh[e] = a.h0[b * FN + e];
     __syncthreads();
-    chain(a, zh, a.Kst, F);
+    chain(fw, zh, a.Kst, F, N);
     for (int g = 0; g < 2; ++g)
       for (int e = threadIdx.x; e < FN; e += PT) {
         const int f = e / N, n = e - f * N;
@@ -259,8 +288,8 @@ __global__ void __launch_bounds__(PT, 1) persist_bwd_k(const Args a) {
     for (int e = threadIdx.x; e < FN; e += PT) zh[e] = hprev[e];
     for (int e = threadIdx.x; e < GN; e += PT) zx[e] = xt[e];
     __syncthreads();
-    chain(a, zh, a.Kst, F);
-    chain(a, zx, a.Kin, a.G);
+    chain(fw, zh, a.Kst, F, N);
+    chain(fw, zx, a.Kin, a.G, N);
     float gi = 1.f, gf = 1.f;
     if (a.tg) { gi = a.gt[((long long)0 * a.B + b) * a.T + t]; gf = a.gt[((long long)1 * a.B + b) * a.T + t]; }
     const float* Ht = a.H + (b * a.T + t) * FN;
@@ -286,7 +315,7 @@ __global__ void __launch_bounds__(PT, 1) persist_bwd_k(const Args a) {
       for (int n = 0; n < N; ++n) s += da[(size_t)f * N + n] + dr[(size_t)f * N + n];
       gacc.bias[f] += s;
     }
-    adjoint_chain(a, w.Bw, dr, b1, b2, dh, a.Kst, F, false);      // dh_{t-1} (recurrent part)
+    adjoint_chain(a, bw, w.Bw, dr, b1, b2, dh, a.Kst, F, false);      // dh_{t-1} (recurrent part)
     if (a.tg) {
       for (int g = 0; g < 2; ++g) {
         const float gv = g == 0 ? gi : gf;
@@ -316,7 +345,7 @@ __global__ void __launch_bounds__(PT, 1) persist_bwd_k(const Args a) {
         for (int n = 0; n < N; ++n) s += v[(size_t)f * N + n];
         gacc.tb[g][f] += 2.f * s;                                  // the sub-cell adds its bias twice (:2421-2422)
       }
-      if (a.dh0) adjoint_chain(a, w.tB[g], v, b1, b2, dh, a.Kst, F, true);
+      if (a.dh0) adjoint_chain(a, bw, w.tB[g], v, b1, b2, dh, a.Kst, F, true);
       __syncthreads();
     }
   }

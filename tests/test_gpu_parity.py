@@ -10,6 +10,7 @@ import torch
 import gated_gcrnns_b200 as gg
 from oracle import gcrnn_oracle as orc
 from tests import _golden as G
+from gated_gcrnns_b200 import _lib
 
 pytestmark = pytest.mark.gpu
 TOL_OUT, TOL_GRAD = 1e-5, 1e-4
