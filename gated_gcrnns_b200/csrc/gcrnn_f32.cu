@@ -842,7 +842,7 @@ size_t cell_backward_f32(const gcrnn_cell* cell, const gcrnn_cell_params* p, con
     const int path = pick_path(cell);
     if (path == GCRNN_PATH_NODE32 && !dX) return cell_backward_e32(cell, p, dH, saved, savedb, gr, dh0, ws, wsb, B, T, st);
     if (path == GCRNN_PATH_PERSIST) {
-      GCRNN_CHECK(dX == nullptr, "the persistent small-graph path does not produce dX");
+      GCRNN_CHECK(ws == nullptr || dX == nullptr, "the persistent small-graph path does not produce dX");
       return cell_backward_persist(cell, p, X, h0, H, dH, saved, savedb, gr, dh0, ws, B, T, st);
     }
   }

@@ -100,10 +100,12 @@ __device__ __forceinline__ void shift(const List& l, const float* in, float* out
   for (int e = threadIdx.x; e < R * N; e += PT) {
     const int r = e / N, n = e - r * N;
     const float* row = in + r * N;
-    float s = 0.f;
+    float s0 = 0.f, s1 = 0.f;                                     // two chains: the loop is latency-bound on the dependent FMA
     const int p1 = l.ptr[n + 1];
-    for (int p = l.ptr[n]; p < p1; ++p) s = fmaf(l.val[p], row[l.idx(p)], s);
-    out[e] = s;
+    int p = l.ptr[n];
+    for (; p + 1 < p1; p += 2) { s0 = fmaf(l.val[p], row[l.idx(p)], s0); s1 = fmaf(l.val[p + 1], row[l.idx(p + 1)], s1); }
+    if (p < p1) s0 = fmaf(l.val[p], row[l.idx(p)], s0);
+    out[e] = s0 + s1;
   }
 }
 // z[k] = z[k-1] S for k = 1..K-1, z: [K][R][N]
@@ -115,11 +117,19 @@ __device__ __forceinline__ void chain(const List& fw, float* z, int K, int R, in
 }
 // y[f][n] = sum_{k,g} W[f][k][g] z[k][g][n]   for one (f, n)
 __device__ __forceinline__ float contract(const float* W, const float* z, int f, int n, int K, int C, int N) {
-  float s = 0.f;
   const float* w = W + (size_t)f * K * C;
-  for (int k = 0; k < K; ++k)
-    for (int g = 0; g < C; ++g) s = fmaf(w[k * C + g], z[((size_t)k * C + g) * N + n], s);
-  return s;
+  const float* zc = z + n;
+  const int KC = K * C;                                           // rows (k, g) of z are contiguous: z[(k*C + g)*N + n]
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;                   // four independent chains
+  int i = 0;
+  for (; i + 3 < KC; i += 4) {
+    s0 = fmaf(w[i], zc[(size_t)i * N], s0);
+    s1 = fmaf(w[i + 1], zc[(size_t)(i + 1) * N], s1);
+    s2 = fmaf(w[i + 2], zc[(size_t)(i + 2) * N], s2);
+    s3 = fmaf(w[i + 3], zc[(size_t)(i + 3) * N], s3);
+  }
+  for (; i < KC; ++i) s0 = fmaf(w[i], zc[(size_t)i * N], s0);
+  return (s0 + s1) + (s2 + s3);
 }
 
 struct Weights { float *A, *Bw, *bias, *tA[2], *tB[2], *tb[2], *tW[2]; };
@@ -213,10 +223,15 @@ __device__ __forceinline__ void wgrad_acc(float* acc, const float* d, const floa
     const int f = o / (K * C), kc = o - f * (K * C);
     const float* dr = d + (size_t)f * N;
     const float* zr = z + (size_t)kc * N;
-    float s = 0.f;
+    float s0 = 0.f, s1 = 0.f;
     int nn = threadIdx.x % N;                                      // skewed start: the lanes of a warp read different banks
-    for (int n = 0; n < N; ++n) { s = fmaf(dr[nn], zr[nn], s); if (++nn == N) nn = 0; }
-    acc[o] += s;
+    int n = 0;
+    for (; n + 1 < N; n += 2) {
+      s0 = fmaf(dr[nn], zr[nn], s0); if (++nn == N) nn = 0;
+      s1 = fmaf(dr[nn], zr[nn], s1); if (++nn == N) nn = 0;
+    }
+    if (n < N) s0 = fmaf(dr[nn], zr[nn], s0);
+    acc[o] += s0 + s1;
   }
 }
 // dh[g][n] (+)= Horner over k of ( sum_f W[f][k][g] d[f][n] ) with S^T:  out = u_0 + (u_1 + (... u_{K-1} S^T ...) S^T) S^T
@@ -235,7 +250,14 @@ __device__ __forceinline__ void adjoint_chain(const Args& a, const List& bw, con
         const int p1 = bw.ptr[n + 1];
         for (int p = bw.ptr[n]; p < p1; ++p) s = fmaf(bw.val[p], row[bw.idx(p)], s);
       }
-      for (int f = 0; f < F; ++f) s = fmaf(W[((size_t)f * K + k) * C + g], d[(size_t)f * N + n], s);
+      float t0 = 0.f, t1 = 0.f;
+      int f = 0;
+      for (; f + 1 < F; f += 2) {
+        t0 = fmaf(W[((size_t)f * K + k) * C + g], d[(size_t)f * N + n], t0);
+        t1 = fmaf(W[((size_t)(f + 1) * K + k) * C + g], d[(size_t)(f + 1) * N + n], t1);
+      }
+      if (f < F) t0 = fmaf(W[((size_t)f * K + k) * C + g], d[(size_t)f * N + n], t0);
+      s += t0 + t1;
       if (k == 0) { if (accumulate) out[e] += s; else out[e] = s; }
       else nxt[e] = s;
     }
