@@ -458,6 +458,33 @@ def run_ours(args):
         times, cores, kind = cpu_sample(dict(CFG3), args.cpu_batch, args.cpu_T, 2)
         cb = cpu_baseline_dict(dict(CFG3), times, cores, args.cpu_batch, args.cpu_T, kind)
 
+    # ---- secondary workloads in the SAME line (N = 1 only): cfg5 (sparse kNN graph, HBM roofline) and cfg1 (the reference's own
+    # CPU-runnable configuration), each measured by the code path `--workload cfg5 / cfg1` runs, with fewer steps ------------------
+    secondary = None
+    if rank == 0 and world == 1 and not args.no_secondary:
+        import copy
+        peak_gb = round(torch.cuda.max_memory_allocated() / 1e9, 1)
+        del X_dev, dH, xbuf, hbuf, h0_dev
+        cell.zero_grad(set_to_none=True)
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+        secondary = {}
+        for wl, st_, wu_ in (('cfg5', 10, 2), ('cfg1', 20, 5)):
+            a2 = copy.copy(args)
+            a2.workload, a2.steps, a2.warmup, a2.no_cpu_baseline, a2.batch = wl, st_, wu_, True, CFG3['B']
+            try:
+                o = run_cfg5(a2, emit_line=False) if wl == 'cfg5' else run_small(a2, emit_line=False)
+                secondary[wl] = {k: o[k] for k in ('value', 'unit', 'steps', 'warmup', 'ms_per_step', 'dtype', 'config', 'roofline', 'e2e', 'gpu_launches',
+                                                   'whole_step') if k in o}
+            except Exception as e:                      # a secondary leg must never take the headline line down
+                secondary[wl] = dict(error=f'{type(e).__name__}: {e}')
+            gc.collect()
+            torch.cuda.empty_cache()
+        gg.set_precision(args.precision)
+    else:
+        peak_gb = round(torch.cuda.max_memory_allocated() / 1e9, 1)
+
     if rank == 0:
         out = dict(metric='GCRNN sequences/sec fwd+bwd', value=seqs, unit='sequences/s', n_gpus=world, steps=args.steps,
                    warmup=args.warmup, ms_per_step=ms_dev / args.steps, higher_is_better=True, scaling='strong',
@@ -470,8 +497,8 @@ def run_ours(args):
                    roofline=roof, cpu_baseline=cb, clocks=clocks,
                    e2e=dict(value=seqs_e2e, unit='sequences/s', h2d_bytes_per_step=int(X_host.numel() * 4 + (Bl // mb) * h0_host.numel() * 4),
                             d2h_bytes_per_step=int(sum(p.numel() for p in used) * 4), ms_per_step=ms_e2e / args.steps),
-                   modes=modes, parity=parity, grad_check=grad_check,
-                   gpu_launches=int(launches), peak_hbm_gb=round(torch.cuda.max_memory_allocated() / 1e9, 1))
+                   modes=modes, parity=parity, grad_check=grad_check, secondary=secondary,
+                   gpu_launches=int(launches), peak_hbm_gb=peak_gb)
         emit(out)
     if world > 1:
         gg.dist.disable()
@@ -543,7 +570,7 @@ def cfg5_dram_bytes_per_sequence(cfg):
     return tot * cfg['T'] / 32
 
 
-def run_cfg5(args):
+def run_cfg5(args, emit_line=True):
     import torch
     import torch.distributed as dist
     import gated_gcrnns_b200 as gg
@@ -645,9 +672,11 @@ def run_cfg5(args):
                    e2e=dict(value=seqs_e2e, unit='sequences/s', h2d_bytes_per_step=int(X_host.numel() * 4),
                             d2h_bytes_per_step=int(sum(p.numel() for p in used) * 4), ms_per_step=ms_e2e / args.steps),
                    gpu_launches=int(launches))
-        emit(out)
+        if emit_line:
+            emit(out)
     if world > 1:
         dist.destroy_process_group()
+    return out if rank == 0 else None
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -660,7 +689,7 @@ SMALL = {'cfg1': ('cell_cfg1_time', True, None, 5, 5), 'cfg2-node': ('cell_cfg2_
          'cfg2-edge': ('cell_cfg2_edge', False, 'edge', 4, 20)}
 
 
-def run_small(args):
+def run_small(args, emit_line=True):
     import numpy as np
     import torch
     import gated_gcrnns_b200 as gg
@@ -766,7 +795,9 @@ def run_small(args):
                e2e=dict(value=B * steps / (ms_e * 1e-3), unit='sequences/s', h2d_bytes_per_step=int(X_host.numel() * 4 + h0_host.numel() * 4),
                         d2h_bytes_per_step=int(cell.weight_B.numel() * 4), ms_per_step=ms_e / steps),
                gpu_launches=int(launches))
-    emit(out)
+    if emit_line:
+        emit(out)
+    return out
 
 
 def main():
@@ -786,6 +817,7 @@ def main():
     ap.add_argument('--also', default='bf16', type=lambda v: [m for m in v.split(',') if m],
                     help='other precisions of the same workload to time briefly for the `modes` object (comma separated; "" = none)')
     ap.add_argument('--no-parity', action='store_true', help='skip the in-run parity measurement')
+    ap.add_argument('--no-secondary', action='store_true', help='N = 1: skip the cfg5 / cfg1 secondary measurements in the same line')
     ap.add_argument('--no-whole-step', action='store_true', help='small workloads: skip the whole-training-step CUDA-graph leg')
     ap.add_argument('--native-allreduce', type=int, default=0, help='N > 1: 1 = the library\'s own NCCL transport (gcrnn_allreduce_sum)')
     ap.add_argument('--cpu-batch', type=int, default=16)
