@@ -25,6 +25,7 @@ SYMBOLS = [
     'gcrnn_cell_create', 'gcrnn_cell_destroy', 'gcrnn_cell_set_option', 'gcrnn_cell_get_option', 'gcrnn_cell_workspace_bytes',
     'gcrnn_cell_forward', 'gcrnn_cell_backward',
     'gcrnn_comm_unique_id', 'gcrnn_comm_create', 'gcrnn_comm_destroy', 'gcrnn_allreduce_sum',
+    'gcrnn_build_knn_csr', 'gcrnn_data_diffusion',
 ]
 
 
@@ -100,6 +101,9 @@ def lib():
     L.gcrnn_comm_create.argtypes = [C.POINTER(_P), _P, C.c_int32, C.c_int32, C.c_int32]
     L.gcrnn_comm_destroy.argtypes = [_P]
     L.gcrnn_allreduce_sum.argtypes = [_P, _P, C.c_int64, _P]
+    L.gcrnn_build_knn_csr.argtypes = [C.c_int32, C.c_int32, _P, C.c_float, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P,
+                                      C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    L.gcrnn_data_diffusion.argtypes = [_P, _P, _P, _P, C.c_int64, C.c_int32, _P]
     if L.gcrnn_abi_version() != 2:
         raise GcrnnError('libgcrnn_b200.so ABI version mismatch')
     _lib = L

@@ -4,7 +4,7 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SRC = ['api.cu', 'graph.cu', 'gcrnn_f32.cu', 'gcrnn_tc.cu']
+SRC = ['api.cu', 'graph.cu', 'gcrnn_f32.cu', 'gcrnn_tc.cu', 'builders.cu']
 OUT = os.path.join(HERE, 'libgcrnn_b200.so')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17', '--use_fast_math=false',
          '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=hidden', '-shared']

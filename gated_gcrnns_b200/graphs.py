@@ -80,3 +80,43 @@ def knn_csr(N=100_000, k=16, seed=0, sigma2=None, power_iters=50):
 def csr_to_torch_sparse(rowptr, colidx, vals, N) -> torch.Tensor:
     return torch.sparse_csr_tensor(torch.as_tensor(rowptr), torch.as_tensor(colidx).to(torch.int64), torch.as_tensor(vals),
                                    size=(N, N))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# on-GPU builders: the same two inputs built by the CUDA library (csrc/builders.cu)
+# ---------------------------------------------------------------------------------------------------------------------
+def knn_csr_gpu(N=100_000, k=16, seed=0, sigma2=None, power_iters=50, device='cuda:0', reorder=True, points=None):
+    """cfg5's graph built on the GPU: uniform-grid kNN search, weights exp(-d^2/sigma^2), normalisation by the spectral norm from
+    `power_iters` power iterations, nodes renumbered along a Hilbert curve of the grid cells when ``reorder`` (the locality the
+    gather kernels live on is then supplied by the library, not by the caller).  Same points as ``knn_csr`` for the same seed.
+    Returns (rowptr int64, colidx int32, vals float32, info) with info = dict(perm (new -> old), sigma2, lam)."""
+    import ctypes as C
+    from . import _lib
+    if points is None:
+        points = np.random.RandomState(seed).rand(N, 2)
+    dev = torch.device(device)
+    xy = torch.as_tensor(np.ascontiguousarray(points, dtype=np.float32)).to(dev)
+    rowptr = np.empty(N + 1, dtype=np.int64); colidx = np.empty(N * k, dtype=np.int32); vals = np.empty(N * k, dtype=np.float32)
+    perm = np.empty(N, dtype=np.int32)
+    s2, lam = C.c_float(), C.c_float()
+    di = dev.index if dev.index is not None else torch.cuda.current_device()
+    _lib.check(_lib.lib().gcrnn_build_knn_csr(N, k, C.c_void_p(xy.data_ptr()), float(sigma2) if sigma2 else 0.0, int(power_iters), int(bool(reorder)),
+                                              di, rowptr.ctypes.data_as(C.c_void_p), colidx.ctypes.data_as(C.c_void_p),
+                                              vals.ctypes.data_as(C.c_void_p), perm.ctypes.data_as(C.c_void_p), C.byref(s2), C.byref(lam)),
+               'build_knn_csr')
+    return rowptr, colidx, vals, dict(perm=perm, sigma2=s2.value, lam=lam.value)
+
+
+def diffusion_signals(graph_handle, x0: torch.Tensor, T: int, noise: torch.Tensor = None) -> torch.Tensor:
+    """x_{t+1} = x_t S + w_t on the GPU (Utils/dataTools.py:1290-1297).  x0: [R,N] CUDA fp32, noise: [T,R,N] or None -> [T+1,R,N]."""
+    import ctypes as C
+    from . import _lib
+    assert x0.is_cuda and x0.dtype == torch.float32 and x0.dim() == 2
+    R, N = x0.shape
+    out = torch.empty(T + 1, R, N, dtype=torch.float32, device=x0.device)
+    x0c = x0.contiguous()
+    nz = noise.contiguous() if noise is not None else None
+    st = C.c_void_p(torch.cuda.current_stream(x0.device).cuda_stream)
+    _lib.check(_lib.lib().gcrnn_data_diffusion(graph_handle.ptr, C.c_void_p(x0c.data_ptr()), C.c_void_p(nz.data_ptr() if nz is not None else 0),
+                                               C.c_void_p(out.data_ptr()), R, T, st), 'data_diffusion')
+    return out

@@ -169,6 +169,20 @@ int gcrnn_comm_create(gcrnn_comm** out, const void* id128, int32_t rank, int32_t
 int gcrnn_comm_destroy(gcrnn_comm* c);
 int gcrnn_allreduce_sum(gcrnn_comm* c, float* bucket, int64_t count, void* stream);
 
+/* ---- on-device builders of the synthetic benchmark inputs ------------------------------------------
+ * Directed kNN graph of N points of the unit square (xy_dev: DEVICE fp32 [N][2]): row i holds its k nearest neighbours (i itself
+ * excluded, ties broken by index) with weights exp(-d^2 / sigma2) (sigma2 <= 0: the mean squared distance to the k-th neighbour),
+ * divided by the spectral-norm estimate of `power_iters` power iterations on A^T A (0: no normalisation) — what the reference does
+ * with dense matrices and numpy eig (Utils/graphTools.py:516-634, kStepPredGRNNs.py:768) and gated_gcrnns_b200/graphs.py did with
+ * scipy on the host.  Uniform-grid search and power iteration run on the GPU; the CSR (N*k entries, ascending columns per row)
+ * is returned in HOST arrays rowptr[N+1], colidx[N*k], vals[N*k].  reorder != 0 renumbers the nodes along a Hilbert curve of the
+ * grid cells (neighbour rows then share cache lines in the gather kernels); perm[new] = old (may be NULL). */
+int gcrnn_build_knn_csr(int32_t N, int32_t k, const float* xy_dev, float sigma2, int32_t power_iters, int32_t reorder, int32_t device,
+                        int64_t* rowptr, int32_t* colidx, float* vals, int32_t* perm, float* sigma2_out, float* lambda_out);
+/* Diffusion-process signals of the k-step prediction task (Utils/dataTools.py:1290-1297): out[0] = x0, out[t+1] = out[t] S + noise[t].
+ * x0: device [R,N]; noise: device [T,R,N] or NULL; out: device [T+1,R,N]. */
+int gcrnn_data_diffusion(const gcrnn_graph* g, const float* x0, const float* noise, float* out, int64_t R, int32_t T, void* stream);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif
