@@ -590,7 +590,15 @@ def run_cfg5(args, emit_line=True):
     mb = min(cfg['mb'], Bl)
     assert Bl % mb == 0
     gg.set_precision('fp32')
-    rp, ci, va = gg.graphs.knn_csr(N, cfg['knn'], seed=0)
+    # the graph is built by the library's on-device builder (csrc/builders.cu): 'hilbert' = the library renumbers the nodes along a
+    # Hilbert curve (locality owned by the library), 'random' = the generator's random node order is kept, 'host' = round 1's scipy path
+    order = getattr(args, 'cfg5_order', 'hilbert')
+    t_build = time.perf_counter()
+    if order == 'host':
+        rp, ci, va = gg.graphs.knn_csr(N, cfg['knn'], seed=0)
+    else:
+        rp, ci, va, _ = gg.graphs.knn_csr_gpu(N, cfg['knn'], seed=0, device=dev, reorder=(order == 'hilbert'))
+    t_build = time.perf_counter() - t_build
     S = gg.graphs.csr_to_torch_sparse(rp, ci, va, N)
     torch.manual_seed(0)
     cell = gg.GGCRNNCell(G, F, K, K, torch.tanh, False, 'edge', 1, True)
@@ -659,6 +667,7 @@ def run_cfg5(args, emit_line=True):
         out = dict(metric='GCRNN sequences/sec fwd+bwd', value=seqs, unit='sequences/s', n_gpus=world, steps=args.steps, warmup=args.warmup,
                    ms_per_step=ms_dev / args.steps, higher_is_better=True, scaling='strong', vs_baseline=None, dtype='f32', data='synthetic',
                    config=dict(workload='cfg5: sparse directed 16-NN graph N=100000 (CSR SpMM path), F=32 G=1 K=3 T=32 edge-gated GGCRNNCell fwd+bwd',
+                               node_order=order, graph_build_s=round(t_build, 2),
                                global_batch=cfg['B'], per_gpu_batch=Bl, microbatch=mb, precision='fp32',
                                parallelism=f'dp{world} (batch sharded, one gradient all-reduce per step)',
                                l2='per-micro-batch working set (H 13 GB) larger than L2; no explicit flush'),
@@ -817,6 +826,8 @@ def main():
     ap.add_argument('--also', default='bf16', type=lambda v: [m for m in v.split(',') if m],
                     help='other precisions of the same workload to time briefly for the `modes` object (comma separated; "" = none)')
     ap.add_argument('--no-parity', action='store_true', help='skip the in-run parity measurement')
+    ap.add_argument('--cfg5-order', default='hilbert', choices=['hilbert', 'random', 'host'],
+                    help='cfg5 graph: built on the GPU with library-owned Hilbert renumbering (default), on the GPU in the random input order, or by the host generator')
     ap.add_argument('--no-secondary', action='store_true', help='N = 1: skip the cfg5 / cfg1 secondary measurements in the same line')
     ap.add_argument('--no-whole-step', action='store_true', help='small workloads: skip the whole-training-step CUDA-graph leg')
     ap.add_argument('--native-allreduce', type=int, default=0, help='N > 1: 1 = the library\'s own NCCL transport (gcrnn_allreduce_sum)')
