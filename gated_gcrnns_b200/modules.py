@@ -104,16 +104,32 @@ class GraphAttentional(nn.Module):
         self.N = N
         self.S = S
 
+    def _preactivation(self, x, k):
+        """Attention output of head k BEFORE the nonlinearity.  The CUDA kernel fuses the ReLU the cell uses (graphML.py:2327);
+        negating both the mixer and the weight leaves every attention coefficient unchanged and flips the sign of the output,
+        so  y = relu(GAT(x; a, W)) - relu(GAT(x; -a, -W))  recovers it from two calls of the same kernel."""
+        a, w = self.mixer[k, 0], self.weight[k, 0]
+        return Fn.graph_attention_relu(x, a, w, self.S) - Fn.graph_attention_relu(x, -a, -w, self.S)
+
     def forward(self, x):
         _cuda_only(x, 'GraphAttentional')
-        if self.E != 1 or not self.concatenate or self.nonlinearity not in (nn.functional.relu, torch.relu):
-            raise NotImplementedError('the CUDA attention kernel implements what GGCRNNCell uses: E=1, ReLU, '
-                                      'concatenated heads (graphML.py:2327); there is no fallback path')
+        if self.E != 1:
+            raise NotImplementedError('the CUDA attention kernel implements one edge feature (E = 1), which is all GGCRNNCell uses '
+                                      '(graphML.py:2327); there is no fallback path')
         B, _, Nin = x.shape
         if Nin < self.N:
             x = torch.cat((x, x.new_zeros(B, x.shape[1], self.N - Nin)), dim=2)
-        heads = [Fn.graph_attention_relu(x, self.mixer[k, 0], self.weight[k, 0], self.S) for k in range(self.K)]
-        y = heads[0] if self.K == 1 else torch.cat(heads, dim=1)     # (k, f) order, graphML.py:2105-2107
+        relu = self.nonlinearity in (nn.functional.relu, torch.relu)
+        if self.concatenate:
+            # nonlinearity per head, then heads stacked (k, f)-major (graphML.py:2099-2107)
+            heads = [Fn.graph_attention_relu(x, self.mixer[k, 0], self.weight[k, 0], self.S) if relu
+                     else self.nonlinearity(self._preactivation(x, k)) for k in range(self.K)]
+            y = heads[0] if self.K == 1 else torch.cat(heads, dim=1)
+        elif self.K == 1 and relu:
+            y = Fn.graph_attention_relu(x, self.mixer[0, 0], self.weight[0, 0], self.S)
+        else:
+            # average over the heads first, then the nonlinearity (graphML.py:2108-2112)
+            y = self.nonlinearity(torch.stack([self._preactivation(x, k) for k in range(self.K)], dim=0).mean(dim=0))
         if Nin < self.N:
             y = y[:, :, :Nin]
         return y

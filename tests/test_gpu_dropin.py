@@ -225,3 +225,36 @@ def test_gcrnn_gnn_and_selection_gnn_on_our_graph_filter():
     assert (ys.detach().cpu() - ys_ref.detach()).abs().max() <= 1e-5 * max(1.0, ys_ref.abs().max())
     for k in gref:
         assert (gref[k] - gour[k]).abs().max() <= 2e-4 * gref[k].abs().max(), k
+
+
+@pytest.mark.parametrize('K,concat,nl', [(3, True, 'tanh'), (3, False, 'relu'), (2, False, 'sigmoid'), (1, True, 'relu')])
+def test_graph_attentional_general_heads_and_nonlinearity(K, concat, nl):
+    """GraphAttentional beyond what the cell uses (graphML.py:1999-2128): several heads, averaging instead of concatenation, any
+    nonlinearity — against the reference module on the CPU."""
+    if not ref_shim.available():
+        pytest.skip('no copy of the reference tree on this box')
+    gml = ref_shim.load()
+    fn = {'tanh': torch.tanh, 'relu': torch.nn.functional.relu, 'sigmoid': torch.sigmoid}[nl]
+    N, G_, F_, B = 30, 4, 5, 6
+    S = torch.rand(1, N, N) * (torch.rand(1, N, N) < 0.2)
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(B, G_, N, generator=g)
+    dy = torch.randn(B, K * F_ if concat else F_, N, generator=g)
+    torch.manual_seed(0)
+    ref = gml.GraphAttentional(G_, F_, K, 1, fn, concat)
+    ref.addGSO(S)
+    xr = x.clone().requires_grad_(True)
+    yr = ref(xr)
+    (yr * dy).sum().backward()
+    torch.manual_seed(0)
+    ours = gg.GraphAttentional(G_, F_, K, 1, fn, concat)
+    ours.addGSO(S)
+    ours = ours.to(DEV)
+    xo = x.clone().to(DEV).requires_grad_(True)
+    yo = ours(xo)
+    (yo * dy.to(DEV)).sum().backward()
+    assert yo.shape == yr.shape
+    assert (yo.detach().cpu() - yr.detach()).abs().max() <= 2e-5 * max(1.0, yr.abs().max())
+    assert (xo.grad.cpu() - xr.grad).abs().max() <= 2e-4 * max(xr.grad.abs().max(), 1e-30)
+    for (k, pr), (_, po) in zip(ref.named_parameters(), ours.named_parameters()):
+        assert (po.grad.cpu() - pr.grad).abs().max() <= 2e-4 * max(pr.grad.abs().max(), 1e-30), k
