@@ -120,3 +120,24 @@ def diffusion_signals(graph_handle, x0: torch.Tensor, T: int, noise: torch.Tenso
     _lib.check(_lib.lib().gcrnn_data_diffusion(graph_handle.ptr, C.c_void_p(x0c.data_ptr()), C.c_void_p(nz.data_ptr() if nz is not None else 0),
                                                C.c_void_p(out.data_ptr()), R, T, st), 'data_diffusion')
     return out
+
+
+def rcm_order(rowptr, colidx, N):
+    """Reverse Cuthill-McKee permutation (new -> old) of a user's CSR graph and the renumbered CSR: the sparse gather kernels
+    read neighbour rows through L1, so a bandwidth-reducing node order roughly doubles their throughput on graphs given in a
+    random order (cfg5: 66 -> 130 seq/s).  Apply the permutation to the node axis of X / h0 and invert it on H."""
+    import scipy.sparse as sp
+    from scipy.sparse.csgraph import reverse_cuthill_mckee
+    A = sp.csr_matrix((np.ones(len(colidx), dtype=np.float32), np.asarray(colidx), np.asarray(rowptr)), shape=(N, N))
+    perm = reverse_cuthill_mckee((A + A.T).tocsr(), symmetric_mode=True).astype(np.int64)
+    return perm
+
+
+def permute_csr(rowptr, colidx, vals, perm):
+    """CSR of P S P^T for perm (new -> old)."""
+    import scipy.sparse as sp
+    N = len(perm)
+    A = sp.csr_matrix((np.asarray(vals), np.asarray(colidx), np.asarray(rowptr)), shape=(N, N))
+    B = A[perm][:, perm].tocsr()
+    B.sort_indices()
+    return B.indptr.astype(np.int64), B.indices.astype(np.int32), B.data.astype(np.float32)

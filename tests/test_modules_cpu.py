@@ -85,3 +85,23 @@ def test_install_rebinds_only_hot_path_names():
     assert fake.GGCRNNCell is gg.GGCRNNCell and fake.LSIGF is gg.LSIGF and fake.NoPool is keep
     gg.uninstall(fake)
     assert fake.GGCRNNCell is not gg.GGCRNNCell
+
+
+def test_rcm_order_is_a_bandwidth_reducing_relabelling():
+    """Host helper for user graphs given in a random node order (the library renumbers only the graphs it builds itself)."""
+    import numpy as np
+    import scipy.sparse as sp
+    from gated_gcrnns_b200 import graphs
+    rng = np.random.RandomState(0)
+    N = 400
+    pts = rng.rand(N, 2)
+    d = ((pts[:, None, :] - pts[None, :, :]) ** 2).sum(-1)
+    A = sp.csr_matrix((d < 0.01) & (d > 0)).astype(np.float32)
+    rp, ci, va = A.indptr.astype(np.int64), A.indices.astype(np.int32), A.data
+    perm = graphs.rcm_order(rp, ci, N)
+    assert sorted(perm.tolist()) == list(range(N))
+    rp2, ci2, va2 = graphs.permute_csr(rp, ci, va, perm)
+    bw = lambda r, c: np.abs(c - np.repeat(np.arange(N), np.diff(r))).mean()
+    assert bw(rp2, ci2) < 0.5 * bw(rp, ci)
+    B = sp.csr_matrix((va2, ci2, rp2), shape=(N, N))
+    assert abs(B.sum() - A.sum()) < 1e-3 and B.nnz == A.nnz
