@@ -713,8 +713,12 @@ size_t cell_forward_persist(const gcrnn_cell* cell, const gcrnn_cell_params* p, 
   a.X = X; a.h0 = h0; a.H = H; a.gt = gt;
   const size_t smem = (size_t)persist::fwd_floats(a.F, a.G, a.Kin, a.Kst, a.N, a.tg) * sizeof(float) + (a.lists_smem ? persist::list_bytes(a.N, a.nnz) : 0);
   static DeviceOnce once;
-  if (once.first()) CUDA_OK(cudaFuncSetAttribute(persist::persist_fwd_k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  persist::persist_fwd_k<<<(unsigned)B, persist::PT, smem, st>>>(a);
+  if (once.first()) {
+    CUDA_OK(cudaFuncSetAttribute(persist::persist_fwd_k<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_OK(cudaFuncSetAttribute(persist::persist_fwd_k<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  }
+  if (a.N % 4 == 0 && a.F % 4 == 0) persist::persist_fwd_k<4><<<(unsigned)B, persist::PT, smem, st>>>(a);      // blocked loops, 16-byte loads
+  else persist::persist_fwd_k<1><<<(unsigned)B, persist::PT, smem, st>>>(a);
   check_launch();
   return 256;
 }
@@ -734,8 +738,12 @@ size_t cell_backward_persist(const gcrnn_cell* cell, const gcrnn_cell_params* p,
   a.dh0 = dh0;
   const size_t smem = (size_t)persist::bwd_floats(a.F, a.G, a.Kin, a.Kst, a.N, a.tg) * sizeof(float) + (a.lists_smem ? 2 * persist::list_bytes(a.N, a.nnz) : 0);
   static DeviceOnce once;
-  if (once.first()) CUDA_OK(cudaFuncSetAttribute(persist::persist_bwd_k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  persist::persist_bwd_k<<<(unsigned)B, persist::PT, smem, st>>>(a);
+  if (once.first()) {
+    CUDA_OK(cudaFuncSetAttribute(persist::persist_bwd_k<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_OK(cudaFuncSetAttribute(persist::persist_bwd_k<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  }
+  if (a.N % 4 == 0 && a.F % 4 == 0) persist::persist_bwd_k<4><<<(unsigned)B, persist::PT, smem, st>>>(a);
+  else persist::persist_bwd_k<1><<<(unsigned)B, persist::PT, smem, st>>>(a);
   check_launch();
   return 256;
 }

@@ -95,50 +95,87 @@ __device__ __forceinline__ float block_sum(float v, float* red) {      // red: >
   return red[32];
 }
 
+// ---- blocked inner loops ------------------------------------------------------------------------------------------------
+// Every loop below is register-blocked so that one shared-memory load feeds several FMAs (the first version issued two loads
+// per FMA and ran at 40 % issue utilisation with 16 warps: profiles/r02_ncu_persist_*): NB = 4 consecutive nodes per thread with
+// 16-byte loads where the contraction runs over rows (needs N % 4 == 0), RB = 4 rows per thread where a gather list is shared.
+
 // out[r][n] = sum_p val[p] in[r][idx[p]], p in [ptr[n], ptr[n+1])   (rows r < R; in / out in shared memory, [R][N])
+template <int RB>
 __device__ __forceinline__ void shift(const List& l, const float* in, float* out, int R, int N) {
-  for (int e = threadIdx.x; e < R * N; e += PT) {
-    const int r = e / N, n = e - r * N;
-    const float* row = in + r * N;
-    float s0 = 0.f, s1 = 0.f;                                     // two chains: the loop is latency-bound on the dependent FMA
+  const int RG = R / RB;
+  for (int e = threadIdx.x; e < RG * N; e += PT) {
+    const int rg = e / N, n = e - rg * N;
+    const float* row = in + (size_t)rg * RB * N;
+    float s[RB];
+#pragma unroll
+    for (int j = 0; j < RB; ++j) s[j] = 0.f;
     const int p1 = l.ptr[n + 1];
-    int p = l.ptr[n];
-    for (; p + 1 < p1; p += 2) { s0 = fmaf(l.val[p], row[l.idx(p)], s0); s1 = fmaf(l.val[p + 1], row[l.idx(p + 1)], s1); }
-    if (p < p1) s0 = fmaf(l.val[p], row[l.idx(p)], s0);
-    out[e] = s0 + s1;
+    for (int p = l.ptr[n]; p < p1; ++p) {
+      const float v = l.val[p];
+      const int i = l.idx(p);
+#pragma unroll
+      for (int j = 0; j < RB; ++j) s[j] = fmaf(v, row[(size_t)j * N + i], s[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < RB; ++j) out[((size_t)rg * RB + j) * N + n] = s[j];
   }
 }
 // z[k] = z[k-1] S for k = 1..K-1, z: [K][R][N]
 __device__ __forceinline__ void chain(const List& fw, float* z, int K, int R, int N) {
   for (int k = 1; k < K; ++k) {
-    shift(fw, z + (size_t)(k - 1) * R * N, z + (size_t)k * R * N, R, N);
+    if (R % 4 == 0) shift<4>(fw, z + (size_t)(k - 1) * R * N, z + (size_t)k * R * N, R, N);
+    else shift<1>(fw, z + (size_t)(k - 1) * R * N, z + (size_t)k * R * N, R, N);
     __syncthreads();
   }
 }
-// y[f][n] = sum_{k,g} W[f][k][g] z[k][g][n]   for one (f, n)
-__device__ __forceinline__ float contract(const float* W, const float* z, int f, int n, int K, int C, int N) {
-  const float* w = W + (size_t)f * K * C;
-  const float* zc = z + n;
-  const int KC = K * C;                                           // rows (k, g) of z are contiguous: z[(k*C + g)*N + n]
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;                   // four independent chains
-  int i = 0;
-  for (; i + 3 < KC; i += 4) {
-    s0 = fmaf(w[i], zc[(size_t)i * N], s0);
-    s1 = fmaf(w[i + 1], zc[(size_t)(i + 1) * N], s1);
-    s2 = fmaf(w[i + 2], zc[(size_t)(i + 2) * N], s2);
-    s3 = fmaf(w[i + 3], zc[(size_t)(i + 3) * N], s3);
+// y[j] = sum_i W[f][i] z[i][n0 + j], j < NB   (i over the KC = K * C rows of z)
+template <int NB>
+__device__ __forceinline__ void contract(const float* W, const float* z, int f, int n0, int KC, int N, float* y) {
+  const float* w = W + (size_t)f * KC;
+  const float* zc = z + n0;
+#pragma unroll
+  for (int j = 0; j < NB; ++j) y[j] = 0.f;
+  if (NB == 4) {
+    float y2[4] = {0.f, 0.f, 0.f, 0.f};                           // second set of chains for the odd rows
+    int i = 0;
+    for (; i + 1 < KC; i += 2) {
+      const float4 a = *reinterpret_cast<const float4*>(zc + (size_t)i * N);
+      const float4 c = *reinterpret_cast<const float4*>(zc + (size_t)(i + 1) * N);
+      const float w0 = w[i], w1 = w[i + 1];
+      y[0] = fmaf(w0, a.x, y[0]); y[1] = fmaf(w0, a.y, y[1]); y[2] = fmaf(w0, a.z, y[2]); y[3] = fmaf(w0, a.w, y[3]);
+      y2[0] = fmaf(w1, c.x, y2[0]); y2[1] = fmaf(w1, c.y, y2[1]); y2[2] = fmaf(w1, c.z, y2[2]); y2[3] = fmaf(w1, c.w, y2[3]);
+    }
+    if (i < KC) {
+      const float4 a = *reinterpret_cast<const float4*>(zc + (size_t)i * N);
+      const float w0 = w[i];
+      y[0] = fmaf(w0, a.x, y[0]); y[1] = fmaf(w0, a.y, y[1]); y[2] = fmaf(w0, a.z, y[2]); y[3] = fmaf(w0, a.w, y[3]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) y[j] += y2[j];
+  } else {
+    float s0 = 0.f, s1 = 0.f;
+    int i = 0;
+    for (; i + 1 < KC; i += 2) { s0 = fmaf(w[i], zc[(size_t)i * N], s0); s1 = fmaf(w[i + 1], zc[(size_t)(i + 1) * N], s1); }
+    if (i < KC) s0 = fmaf(w[i], zc[(size_t)i * N], s0);
+    y[0] = s0 + s1;
   }
-  for (; i < KC; ++i) s0 = fmaf(w[i], zc[(size_t)i * N], s0);
-  return (s0 + s1) + (s2 + s3);
 }
 
-struct Weights { float *A, *Bw, *bias, *tA[2], *tB[2], *tb[2], *tW[2]; };
+struct Weights {
+  float *A, *Bw, *bias, *tA0, *tB0, *tb0, *tW0, *tA1, *tB1, *tb1, *tW1;
+  __device__ __forceinline__ float* tA(int g) const { return g ? tA1 : tA0; }
+  __device__ __forceinline__ float* tB(int g) const { return g ? tB1 : tB0; }
+  __device__ __forceinline__ float* tb(int g) const { return g ? tb1 : tb0; }
+  __device__ __forceinline__ float* tW(int g) const { return g ? tW1 : tW0; }
+};
 __device__ __forceinline__ float* carve(Weights& w, float* p, const Args& a) {
   const int nA = a.F * a.Kin * a.G, nB = a.F * a.Kst * a.F;
   w.A = p; p += nA; w.Bw = p; p += nB; w.bias = p; p += a.F;
-  for (int g = 0; g < 2; ++g) {
-    if (a.tg) { w.tA[g] = p; p += nA; w.tB[g] = p; p += nB; w.tb[g] = p; p += a.F; w.tW[g] = p; p += a.F * a.N; }
-    else { w.tA[g] = w.tB[g] = w.tb[g] = w.tW[g] = nullptr; }
+  w.tA0 = w.tB0 = w.tb0 = w.tW0 = w.tA1 = w.tB1 = w.tb1 = w.tW1 = p;
+  if (a.tg) {
+    w.tA0 = p; p += nA; w.tB0 = p; p += nB; w.tb0 = p; p += a.F; w.tW0 = p; p += a.F * a.N;
+    w.tA1 = p; p += nA; w.tB1 = p; p += nB; w.tb1 = p; p += a.F; w.tW1 = p; p += a.F * a.N;
   }
   return p;
 }
@@ -149,16 +186,18 @@ __device__ __forceinline__ void load_weights(const Weights& w, const Args& a) {
   for (int i = threadIdx.x; i < a.F; i += PT) w.bias[i] = a.has_bias ? a.bias[i] : 0.f;
   if (a.tg)
     for (int g = 0; g < 2; ++g) {
-      for (int i = threadIdx.x; i < nA; i += PT) w.tA[g][i] = a.tA[g][i];
-      for (int i = threadIdx.x; i < nB; i += PT) w.tB[g][i] = a.tB[g][i];
-      for (int i = threadIdx.x; i < a.F; i += PT) w.tb[g][i] = a.has_bias ? a.tb[g][i] : 0.f;
-      for (int i = threadIdx.x; i < FN; i += PT) w.tW[g][i] = a.tW[g][i];
+      for (int i = threadIdx.x; i < nA; i += PT) w.tA(g)[i] = a.tA[g][i];
+      for (int i = threadIdx.x; i < nB; i += PT) w.tB(g)[i] = a.tB[g][i];
+      for (int i = threadIdx.x; i < a.F; i += PT) w.tb(g)[i] = a.has_bias ? a.tb[g][i] : 0.f;
+      for (int i = threadIdx.x; i < FN; i += PT) w.tW(g)[i] = a.tW[g][i];
     }
 }
 
+template <int NB>
 __global__ void __launch_bounds__(PT, 1) persist_fwd_k(const Args a) {
   extern __shared__ __align__(16) float psm[];
-  const int N = a.N, F = a.F, FN = F * N, GN = a.G * N;
+  const int N = a.N, F = a.F, FN = F * N, GN = a.G * N, NQ = N / NB;
+  const int KCa = a.Kin * a.G, KCb = a.Kst * F;
   const long long b = blockIdx.x;
   Weights w;
   float* p = carve(w, psm, a);
@@ -174,10 +213,14 @@ __global__ void __launch_bounds__(PT, 1) persist_fwd_k(const Args a) {
   __syncthreads();
   if (a.tg) {                                                     // T-invariant gate term: B_g(S) h0 + 2 b_g   (graphML.py:2362, :2417-2423)
     chain(fw, zh, a.Kst, F, N);
+#pragma unroll
     for (int g = 0; g < 2; ++g)
-      for (int e = threadIdx.x; e < FN; e += PT) {
-        const int f = e / N, n = e - f * N;
-        c0[g * FN + e] = contract(w.tB[g], zh, f, n, a.Kst, F, N) + 2.f * w.tb[g][f];
+      for (int e = threadIdx.x; e < F * NQ; e += PT) {
+        const int f = e / NQ, n0 = (e - f * NQ) * NB;
+        float y[NB];
+        contract<NB>(w.tB(g), zh, f, n0, KCb, N, y);
+#pragma unroll
+        for (int j = 0; j < NB; ++j) c0[g * FN + f * N + n0 + j] = y[j] + 2.f * w.tb(g)[f];
       }
     __syncthreads();
   }
@@ -188,12 +231,15 @@ __global__ void __launch_bounds__(PT, 1) persist_fwd_k(const Args a) {
     chain(fw, zx, a.Kin, a.G, N);
     float gi = 1.f, gf = 1.f;
     if (a.tg) {
+#pragma unroll
       for (int g = 0; g < 2; ++g) {
         float part = 0.f;
-        for (int e = threadIdx.x; e < FN; e += PT) {
-          const int f = e / N, n = e - f * N;
-          const float u = tanhf(contract(w.tA[g], zx, f, n, a.Kin, a.G, N) + c0[g * FN + e]);
-          part = fmaf(w.tW[g][e], u, part);
+        for (int e = threadIdx.x; e < F * NQ; e += PT) {
+          const int f = e / NQ, n0 = (e - f * NQ) * NB;
+          float y[NB];
+          contract<NB>(w.tA(g), zx, f, n0, KCa, N, y);
+#pragma unroll
+          for (int j = 0; j < NB; ++j) part = fmaf(w.tW(g)[f * N + n0 + j], tanhf(y[j] + c0[g * FN + f * N + n0 + j]), part);
         }
         const float logit = block_sum(part, red) + (a.has_bias ? __ldg(a.tc[g]) : 0.f);
         const float gv = 1.f / (1.f + expf(-logit));
@@ -201,15 +247,20 @@ __global__ void __launch_bounds__(PT, 1) persist_fwd_k(const Args a) {
         if (threadIdx.x == 0) a.gt[((long long)g * a.B + b) * a.T + t] = gv;
       }
     }
-    if (!(a.tg && t == 0)) chain(fw, zh, a.Kst, F, N);                // at t = 0 with gating the h0 chain is already there
+    if (!(a.tg && t == 0)) chain(fw, zh, a.Kst, F, N);            // at t = 0 with gating the h0 chain is already there
     float* Ht = a.H + (b * a.T + t) * FN;
-    for (int e = threadIdx.x; e < FN; e += PT) {
-      const int f = e / N, n = e - f * N;
-      const float av = contract(w.A, zx, f, n, a.Kin, a.G, N) + w.bias[f];
-      const float rv = contract(w.Bw, zh, f, n, a.Kst, F, N) + w.bias[f];           // the same bias in both filters (:2405-2407)
-      const float h = tanhf(fmaf(gi, av, gf * rv));
-      Ht[e] = h;
-      hn[e] = h;
+    for (int e = threadIdx.x; e < F * NQ; e += PT) {
+      const int f = e / NQ, n0 = (e - f * NQ) * NB;
+      float av[NB], rv[NB];
+      contract<NB>(w.A, zx, f, n0, KCa, N, av);
+      contract<NB>(w.Bw, zh, f, n0, KCb, N, rv);
+      const float bb = w.bias[f];                                  // the same bias in both filters (:2405-2407)
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        const float h = tanhf(fmaf(gi, av[j] + bb, gf * (rv[j] + bb)));
+        Ht[f * N + n0 + j] = h;
+        hn[f * N + n0 + j] = h;
+      }
     }
     __syncthreads();
     for (int e = threadIdx.x; e < FN; e += PT) zh[e] = hn[e];
@@ -217,59 +268,82 @@ __global__ void __launch_bounds__(PT, 1) persist_fwd_k(const Args a) {
   }
 }
 
-// acc[f,k,g] += sum_n d[f][n] z[k][g][n]   (every output owned by one thread; acc in shared memory)
-__device__ __forceinline__ void wgrad_acc(float* acc, const float* d, const float* z, int F, int K, int C, int N) {
-  for (int o = threadIdx.x; o < F * K * C; o += PT) {
-    const int f = o / (K * C), kc = o - f * (K * C);
+// acc[f][kc] += sum_n d[f][n] z[kc][n]   (every output owned by one thread; acc in shared memory)
+template <int NB>
+__device__ __forceinline__ void wgrad_acc(float* acc, const float* d, const float* z, int F, int KC, int N) {
+  for (int o = threadIdx.x; o < F * KC; o += PT) {
+    const int f = o / KC, kc = o - f * KC;
     const float* dr = d + (size_t)f * N;
     const float* zr = z + (size_t)kc * N;
     float s0 = 0.f, s1 = 0.f;
-    int nn = threadIdx.x % N;                                      // skewed start: the lanes of a warp read different banks
-    int n = 0;
-    for (; n + 1 < N; n += 2) {
-      s0 = fmaf(dr[nn], zr[nn], s0); if (++nn == N) nn = 0;
-      s1 = fmaf(dr[nn], zr[nn], s1); if (++nn == N) nn = 0;
+    if (NB == 4) {
+      const int NQ = N / 4;
+      int q = threadIdx.x % NQ;                                    // skewed start: the lanes of a warp read different banks
+      for (int i = 0; i < NQ; ++i) {
+        const float4 a = *reinterpret_cast<const float4*>(dr + 4 * q);
+        const float4 c = *reinterpret_cast<const float4*>(zr + 4 * q);
+        s0 = fmaf(a.x, c.x, s0); s1 = fmaf(a.y, c.y, s1); s0 = fmaf(a.z, c.z, s0); s1 = fmaf(a.w, c.w, s1);
+        if (++q == NQ) q = 0;
+      }
+    } else {
+      int nn = threadIdx.x % N;
+      for (int n = 0; n < N; ++n) { if (n & 1) s1 = fmaf(dr[nn], zr[nn], s1); else s0 = fmaf(dr[nn], zr[nn], s0); if (++nn == N) nn = 0; }
     }
-    if (n < N) s0 = fmaf(dr[nn], zr[nn], s0);
     acc[o] += s0 + s1;
   }
 }
-// dh[g][n] (+)= Horner over k of ( sum_f W[f][k][g] d[f][n] ) with S^T:  out = u_0 + (u_1 + (... u_{K-1} S^T ...) S^T) S^T
-// b1 / b2: [C][N] scratch; result ADDED to `out` if accumulate else written
+// out[g][n] (+)= Horner over k of ( sum_f W[f][k][g] d[f][n] ) with S^T:  out = u_0 + (u_1 + (... u_{K-1} S^T ...) S^T) S^T
+// b1 / b2: [C][N] scratch.  GB features g per thread share the S^T gather list of node n and the loads of d[f][n].
+template <int GB>
 __device__ __forceinline__ void adjoint_chain(const Args& a, const List& bw, const float* W, const float* d, float* b1, float* b2, float* out,
                                               int K, int C, bool accumulate) {
-  const int N = a.N, F = a.F;
+  const int N = a.N, F = a.F, CG = C / GB;
   float* cur = b1; float* nxt = b2;
   for (int k = K - 1; k >= 0; --k) {
-    // nxt[g][n] = (cur S^T)[g][n] (if k < K-1) + sum_f W[f][k][g] d[f][n]
-    for (int e = threadIdx.x; e < C * N; e += PT) {
-      const int g = e / N, n = e - g * N;
-      float s = 0.f;
+    for (int e = threadIdx.x; e < CG * N; e += PT) {
+      const int cg = e / N, n = e - cg * N, g0 = cg * GB;
+      float s[GB];
+#pragma unroll
+      for (int j = 0; j < GB; ++j) s[j] = 0.f;
       if (k < K - 1) {
-        const float* row = cur + (size_t)g * N;
+        const float* row = cur + (size_t)g0 * N;
         const int p1 = bw.ptr[n + 1];
-        for (int p = bw.ptr[n]; p < p1; ++p) s = fmaf(bw.val[p], row[bw.idx(p)], s);
+        for (int p = bw.ptr[n]; p < p1; ++p) {
+          const float v = bw.val[p];
+          const int i = bw.idx(p);
+#pragma unroll
+          for (int j = 0; j < GB; ++j) s[j] = fmaf(v, row[(size_t)j * N + i], s[j]);
+        }
       }
-      float t0 = 0.f, t1 = 0.f;
-      int f = 0;
-      for (; f + 1 < F; f += 2) {
-        t0 = fmaf(W[((size_t)f * K + k) * C + g], d[(size_t)f * N + n], t0);
-        t1 = fmaf(W[((size_t)(f + 1) * K + k) * C + g], d[(size_t)(f + 1) * N + n], t1);
+      for (int f = 0; f < F; ++f) {
+        const float dv = d[(size_t)f * N + n];
+        const float* wp = W + ((size_t)f * K + k) * C + g0;
+        if (GB == 4) {
+          const float4 wv = *reinterpret_cast<const float4*>(wp);
+          s[0] = fmaf(wv.x, dv, s[0]); s[1 % GB] = fmaf(wv.y, dv, s[1 % GB]); s[2 % GB] = fmaf(wv.z, dv, s[2 % GB]); s[3 % GB] = fmaf(wv.w, dv, s[3 % GB]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < GB; ++j) s[j] = fmaf(wp[j], dv, s[j]);
+        }
       }
-      if (f < F) t0 = fmaf(W[((size_t)f * K + k) * C + g], d[(size_t)f * N + n], t0);
-      s += t0 + t1;
-      if (k == 0) { if (accumulate) out[e] += s; else out[e] = s; }
-      else nxt[e] = s;
+#pragma unroll
+      for (int j = 0; j < GB; ++j) {
+        const size_t o = (size_t)(g0 + j) * N + n;
+        if (k == 0) { if (accumulate) out[o] += s[j]; else out[o] = s[j]; }
+        else nxt[o] = s[j];
+      }
     }
     __syncthreads();
     float* t = cur; cur = nxt; nxt = t;
   }
 }
 
+template <int NB>
 __global__ void __launch_bounds__(PT, 1) persist_bwd_k(const Args a) {
   extern __shared__ __align__(16) float psm[];
-  const int N = a.N, F = a.F, FN = F * N, GN = a.G * N;
+  const int N = a.N, F = a.F, FN = F * N, GN = a.G * N, NQ = N / NB;
   const int nA = F * a.Kin * a.G, nB = F * a.Kst * F;
+  const int KCa = a.Kin * a.G, KCb = a.Kst * F;
   const long long b = blockIdx.x;
   Weights w, gacc;
   float* p = carve(w, psm, a);
@@ -297,13 +371,18 @@ __global__ void __launch_bounds__(PT, 1) persist_bwd_k(const Args a) {
     for (int e = threadIdx.x; e < FN; e += PT) zh[e] = a.h0[b * FN + e];
     __syncthreads();
     chain(fw, zh, a.Kst, F, N);
+#pragma unroll
     for (int g = 0; g < 2; ++g)
-      for (int e = threadIdx.x; e < FN; e += PT) {
-        const int f = e / N, n = e - f * N;
-        c0[g * FN + e] = contract(w.tB[g], zh, f, n, a.Kst, F, N) + 2.f * w.tb[g][f];
+      for (int e = threadIdx.x; e < F * NQ; e += PT) {
+        const int f = e / NQ, n0 = (e - f * NQ) * NB;
+        float y[NB];
+        contract<NB>(w.tB(g), zh, f, n0, KCb, N, y);
+#pragma unroll
+        for (int j = 0; j < NB; ++j) c0[g * FN + f * N + n0 + j] = y[j] + 2.f * w.tb(g)[f];
       }
     __syncthreads();
   }
+  constexpr int GB = NB;                                          // F % 4 == 0 is part of the NB = 4 eligibility
   for (long long t = a.T - 1; t >= 0; --t) {
     const float* hprev = t > 0 ? a.H + (b * a.T + t - 1) * FN : a.h0 + b * FN;
     const float* xt = a.X + (b * a.T + t) * GN;
@@ -318,56 +397,70 @@ __global__ void __launch_bounds__(PT, 1) persist_bwd_k(const Args a) {
     const bool has_dH = !(a.dh_last_only && t < a.T - 1);
     const float* dHt = a.dH + b * a.dH_bstride + (a.dh_last_only ? 0 : t * a.dH_tstride);
     float sgi = 0.f, sgf = 0.f;
-    for (int e = threadIdx.x; e < FN; e += PT) {
-      const int f = e / N, n = e - f * N;
-      const float av = contract(w.A, zx, f, n, a.Kin, a.G, N) + w.bias[f];
-      const float rv = contract(w.Bw, zh, f, n, a.Kst, F, N) + w.bias[f];
-      const float h = Ht[e];
-      const float dp = ((has_dH ? dHt[e] : 0.f) + dh[e]) * (1.f - h * h);
-      sgi = fmaf(dp, av, sgi); sgf = fmaf(dp, rv, sgf);
-      da[e] = gi * dp; dr[e] = gf * dp;
+    for (int e = threadIdx.x; e < F * NQ; e += PT) {
+      const int f = e / NQ, n0 = (e - f * NQ) * NB;
+      float av[NB], rv[NB];
+      contract<NB>(w.A, zx, f, n0, KCa, N, av);
+      contract<NB>(w.Bw, zh, f, n0, KCb, N, rv);
+      const float bb = w.bias[f];
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        const int o = f * N + n0 + j;
+        const float h = Ht[o];
+        const float dp = ((has_dH ? dHt[o] : 0.f) + dh[o]) * (1.f - h * h);
+        sgi = fmaf(dp, av[j] + bb, sgi); sgf = fmaf(dp, rv[j] + bb, sgf);
+        da[o] = gi * dp; dr[o] = gf * dp;
+      }
     }
     float dgi = 0.f, dgf = 0.f;
     if (a.tg) { dgi = block_sum(sgi, red); dgf = block_sum(sgf, red); }
     __syncthreads();
-    wgrad_acc(gacc.A, da, zx, F, a.Kin, a.G, N);
-    wgrad_acc(gacc.Bw, dr, zh, F, a.Kst, F, N);
+    wgrad_acc<NB>(gacc.A, da, zx, F, KCa, N);
+    wgrad_acc<NB>(gacc.Bw, dr, zh, F, KCb, N);
     for (int f = threadIdx.x; f < F; f += PT) {
       float s = 0.f;
       for (int n = 0; n < N; ++n) s += da[(size_t)f * N + n] + dr[(size_t)f * N + n];
       gacc.bias[f] += s;
     }
-    adjoint_chain(a, bw, w.Bw, dr, b1, b2, dh, a.Kst, F, false);      // dh_{t-1} (recurrent part)
+    adjoint_chain<GB>(a, bw, w.Bw, dr, b1, b2, dh, a.Kst, F, false);      // dh_{t-1} (recurrent part)
     if (a.tg) {
+#pragma unroll
       for (int g = 0; g < 2; ++g) {
         const float gv = g == 0 ? gi : gf;
         const float dl = (g == 0 ? dgi : dgf) * gv * (1.f - gv);
         dtc[g] += dl;
-        for (int e = threadIdx.x; e < FN; e += PT) {
-          const int f = e / N, n = e - f * N;
-          const float u = tanhf(contract(w.tA[g], zx, f, n, a.Kin, a.G, N) + c0[g * FN + e]);
-          gacc.tW[g][e] += dl * u;
-          const float d = dl * w.tW[g][e] * (1.f - u * u);
-          dc0[g * FN + e] += d;
-          dpu[e] = d;
+        for (int e = threadIdx.x; e < F * NQ; e += PT) {
+          const int f = e / NQ, n0 = (e - f * NQ) * NB;
+          float y[NB];
+          contract<NB>(w.tA(g), zx, f, n0, KCa, N, y);
+#pragma unroll
+          for (int j = 0; j < NB; ++j) {
+            const int o = f * N + n0 + j;
+            const float u = tanhf(y[j] + c0[g * FN + o]);
+            gacc.tW(g)[o] += dl * u;
+            const float dd = dl * w.tW(g)[o] * (1.f - u * u);
+            dc0[g * FN + o] += dd;
+            dpu[o] = dd;
+          }
         }
         __syncthreads();
-        wgrad_acc(gacc.tA[g], dpu, zx, F, a.Kin, a.G, N);
+        wgrad_acc<NB>(gacc.tA(g), dpu, zx, F, KCa, N);
         __syncthreads();
       }
     }
   }
   // ---- T-invariant gate term: after t = 0 the zh buffers hold h0's chain ------------------------------------------------------
   if (a.tg) {
+#pragma unroll
     for (int g = 0; g < 2; ++g) {
       const float* v = dc0 + (size_t)g * FN;
-      wgrad_acc(gacc.tB[g], v, zh, F, a.Kst, F, N);
+      wgrad_acc<NB>(gacc.tB(g), v, zh, F, KCb, N);
       for (int f = threadIdx.x; f < F; f += PT) {
         float s = 0.f;
         for (int n = 0; n < N; ++n) s += v[(size_t)f * N + n];
-        gacc.tb[g][f] += 2.f * s;                                  // the sub-cell adds its bias twice (:2421-2422)
+        gacc.tb(g)[f] += 2.f * s;                                  // the sub-cell adds its bias twice (:2421-2422)
       }
-      if (a.dh0) adjoint_chain(a, bw, w.tB[g], v, b1, b2, dh, a.Kst, F, true);
+      if (a.dh0) adjoint_chain<GB>(a, bw, w.tB(g), v, b1, b2, dh, a.Kst, F, true);
       __syncthreads();
     }
   }
@@ -378,10 +471,10 @@ __global__ void __launch_bounds__(PT, 1) persist_bwd_k(const Args a) {
   for (int i = threadIdx.x; i < F; i += PT) if (a.dbias) atomicAdd(a.dbias + i, gacc.bias[i]);
   if (a.tg)
     for (int g = 0; g < 2; ++g) {
-      for (int i = threadIdx.x; i < nA; i += PT) if (a.dtA[g]) atomicAdd(a.dtA[g] + i, gacc.tA[g][i]);
-      for (int i = threadIdx.x; i < nB; i += PT) if (a.dtB[g]) atomicAdd(a.dtB[g] + i, gacc.tB[g][i]);
-      for (int i = threadIdx.x; i < F; i += PT) if (a.dtb[g]) atomicAdd(a.dtb[g] + i, gacc.tb[g][i]);
-      for (int i = threadIdx.x; i < FN; i += PT) if (a.dtW[g]) atomicAdd(a.dtW[g] + i, gacc.tW[g][i]);
+      for (int i = threadIdx.x; i < nA; i += PT) if (a.dtA[g]) atomicAdd(a.dtA[g] + i, gacc.tA(g)[i]);
+      for (int i = threadIdx.x; i < nB; i += PT) if (a.dtB[g]) atomicAdd(a.dtB[g] + i, gacc.tB(g)[i]);
+      for (int i = threadIdx.x; i < F; i += PT) if (a.dtb[g]) atomicAdd(a.dtb[g] + i, gacc.tb(g)[i]);
+      for (int i = threadIdx.x; i < FN; i += PT) if (a.dtW[g]) atomicAdd(a.dtW[g] + i, gacc.tW(g)[i]);
       if (threadIdx.x == 0 && a.dtc[g]) atomicAdd(a.dtc[g], dtc[g]);
     }
 }
