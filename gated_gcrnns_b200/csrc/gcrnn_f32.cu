@@ -677,28 +677,31 @@ constexpr long long PERSIST_SMEM_MAX = 220 * 1024;
 bool persist_ok(const gcrnn_cell* cell) {
   const gcrnn_cell_desc& d = cell->d;
   const gcrnn_graph* g = cell->g;
-  if (!opt().persist || d.E != 1 || g->E != 1 || d.spatial_gating != GCRNN_SPATIAL_NONE || cell->need_dx) return false;
-  const long long fl = persist::bwd_floats(d.F, d.G, d.Kin, d.Kst, g->N, d.time_gating != 0);
+  if (!opt().persist || d.E != 1 || g->E != 1 || d.spatial_gating == GCRNN_SPATIAL_EDGE || cell->need_dx) return false;
+  const long long fl = persist::bwd_floats(d.F, d.G, d.Kin, d.Kst, g->N, d.time_gating != 0, d.spatial_gating == GCRNN_SPATIAL_NODE);
   return fl * 4 <= PERSIST_SMEM_MAX && g->N < 65536;
 }
 // stage the gather lists in shared memory when both fit next to the rest
 bool persist_lists_fit(const gcrnn_cell* cell) {
   const gcrnn_cell_desc& d = cell->d;
   const gcrnn_graph* g = cell->g;
-  const long long fl = persist::bwd_floats(d.F, d.G, d.Kin, d.Kst, g->N, d.time_gating != 0);
+  const long long fl = persist::bwd_floats(d.F, d.G, d.Kin, d.Kst, g->N, d.time_gating != 0, d.spatial_gating == GCRNN_SPATIAL_NODE);
   return fl * 4 + 2 * persist::list_bytes(g->N, (int)g->fwd[0].nnz) <= 226 * 1024;
 }
 persist::Args persist_args(const gcrnn_cell* cell, const gcrnn_cell_params* p, int64_t B, int64_t T) {
   const gcrnn_graph* g = cell->g;
   persist::Args a{};
   a.N = g->N; a.F = cell->d.F; a.G = cell->d.G; a.Kin = cell->d.Kin; a.Kst = cell->d.Kst;
-  a.tg = cell->d.time_gating != 0; a.has_bias = cell->d.bias != 0; a.B = B; a.T = T;
+  a.tg = cell->d.time_gating != 0; a.node = cell->d.spatial_gating == GCRNN_SPATIAL_NODE; a.has_bias = cell->d.bias != 0; a.B = B; a.T = T;
   a.cptr = g->fwd[0].ptr; a.cidx = g->fwd[0].idx; a.cval = g->fwd[0].val;
   a.rptr = g->bwd[0].ptr; a.ridx = g->bwd[0].idx; a.rval = g->bwd[0].val;
   a.nnz = (int)g->fwd[0].nnz; a.lists_smem = persist_lists_fit(cell);
   if (p) {
     a.A = p->weight_A; a.Bw = p->weight_B; a.bias = p->bias;
-    for (int i = 0; i < 2; ++i) { a.tA[i] = p->t_weight_A[i]; a.tB[i] = p->t_weight_B[i]; a.tb[i] = p->t_bias[i]; a.tW[i] = p->t_mlp_w[i]; a.tc[i] = p->t_mlp_b[i]; }
+    for (int i = 0; i < 2; ++i) {
+      a.tA[i] = p->t_weight_A[i]; a.tB[i] = p->t_weight_B[i]; a.tb[i] = p->t_bias[i]; a.tW[i] = p->t_mlp_w[i]; a.tc[i] = p->t_mlp_b[i];
+      a.nA[i] = p->n_weight_A[i]; a.nB[i] = p->n_weight_B[i]; a.nb[i] = p->n_bias[i]; a.nhw[i] = p->n_head_w[i]; a.nhb[i] = p->n_head_b[i];
+    }
   }
   return a;
 }
@@ -706,12 +709,13 @@ size_t cell_forward_persist(const gcrnn_cell* cell, const gcrnn_cell_params* p, 
                             void* saved, size_t savedb, size_t* saved_used, void* ws, int64_t B, int64_t T, cudaStream_t st) {
   Arena sa(saved, savedb);
   float* gt = sa.get<float>(2 * B * T);
+  float* qn = sa.get<float>(cell->d.spatial_gating == GCRNN_SPATIAL_NODE ? (size_t)2 * B * T * cell->g->N : 0);
   if (saved_used) *saved_used = sa.off;
   if (ws == nullptr) return 256;
   GCRNN_CHECK(saved != nullptr, "forward needs the `saved` buffer");
   persist::Args a = persist_args(cell, p, B, T);
-  a.X = X; a.h0 = h0; a.H = H; a.gt = gt;
-  const size_t smem = (size_t)persist::fwd_floats(a.F, a.G, a.Kin, a.Kst, a.N, a.tg) * sizeof(float) + (a.lists_smem ? persist::list_bytes(a.N, a.nnz) : 0);
+  a.X = X; a.h0 = h0; a.H = H; a.gt = gt; a.qn = qn;
+  const size_t smem = (size_t)persist::fwd_floats(a.F, a.G, a.Kin, a.Kst, a.N, a.tg, a.node) * sizeof(float) + (a.lists_smem ? persist::list_bytes(a.N, a.nnz) : 0);
   static DeviceOnce once;
   if (once.first()) {
     CUDA_OK(cudaFuncSetAttribute(persist::persist_fwd_k<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -727,16 +731,20 @@ size_t cell_backward_persist(const gcrnn_cell* cell, const gcrnn_cell_params* p,
                              int64_t B, int64_t T, cudaStream_t st) {
   Arena sa(const_cast<void*>(saved), savedb);
   float* gt = sa.get<float>(2 * B * T);
+  float* qn = sa.get<float>(cell->d.spatial_gating == GCRNN_SPATIAL_NODE ? (size_t)2 * B * T * cell->g->N : 0);
   if (ws == nullptr) return 256;
   persist::Args a = persist_args(cell, p, B, T);
   const long long FN = (long long)a.F * a.N;
-  a.X = X; a.h0 = h0; a.H = const_cast<float*>(H); a.gt = gt;
+  a.X = X; a.h0 = h0; a.H = const_cast<float*>(H); a.gt = gt; a.qn = qn;
   a.dH = dH; a.dh_last_only = cell->dh_last_only;
   a.dH_bstride = cell->dh_last_only ? FN : T * FN; a.dH_tstride = FN;
   a.dA = gr->weight_A; a.dBw = gr->weight_B; a.dbias = gr->bias;
-  for (int i = 0; i < 2; ++i) { a.dtA[i] = gr->t_weight_A[i]; a.dtB[i] = gr->t_weight_B[i]; a.dtb[i] = gr->t_bias[i]; a.dtW[i] = gr->t_mlp_w[i]; a.dtc[i] = gr->t_mlp_b[i]; }
+  for (int i = 0; i < 2; ++i) {
+    a.dtA[i] = gr->t_weight_A[i]; a.dtB[i] = gr->t_weight_B[i]; a.dtb[i] = gr->t_bias[i]; a.dtW[i] = gr->t_mlp_w[i]; a.dtc[i] = gr->t_mlp_b[i];
+    a.dnA[i] = gr->n_weight_A[i]; a.dnB[i] = gr->n_weight_B[i]; a.dnb[i] = gr->n_bias[i]; a.dnhw[i] = gr->n_head_w[i]; a.dnhb[i] = gr->n_head_b[i];
+  }
   a.dh0 = dh0;
-  const size_t smem = (size_t)persist::bwd_floats(a.F, a.G, a.Kin, a.Kst, a.N, a.tg) * sizeof(float) + (a.lists_smem ? 2 * persist::list_bytes(a.N, a.nnz) : 0);
+  const size_t smem = (size_t)persist::bwd_floats(a.F, a.G, a.Kin, a.Kst, a.N, a.tg, a.node) * sizeof(float) + (a.lists_smem ? 2 * persist::list_bytes(a.N, a.nnz) : 0);
   static DeviceOnce once;
   if (once.first()) {
     CUDA_OK(cudaFuncSetAttribute(persist::persist_bwd_k<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -755,8 +763,8 @@ int pick_path(const gcrnn_cell* cell) {
     if (cell->forced_path == GCRNN_PATH_NODE32) GCRNN_CHECK(edge32_ok(cell), "path NODE32 does not support this cell");
     if (cell->forced_path == GCRNN_PATH_PERSIST) {
       const gcrnn_cell_desc& d = cell->d;
-      GCRNN_CHECK(d.E == 1 && d.spatial_gating == GCRNN_SPATIAL_NONE &&
-                  persist::bwd_floats(d.F, d.G, d.Kin, d.Kst, cell->g->N, d.time_gating != 0) * 4 <= PERSIST_SMEM_MAX,
+      GCRNN_CHECK(d.E == 1 && d.spatial_gating != GCRNN_SPATIAL_EDGE &&
+                  persist::bwd_floats(d.F, d.G, d.Kin, d.Kst, cell->g->N, d.time_gating != 0, d.spatial_gating == GCRNN_SPATIAL_NODE) * 4 <= PERSIST_SMEM_MAX,
                   "path PERSIST does not support this cell");
     }
     return cell->forced_path;

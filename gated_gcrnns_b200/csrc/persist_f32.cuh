@@ -14,8 +14,11 @@
 //            across all steps (one atomicAdd per parameter and CTA at the end); dh_{t-1} by Horner's rule with S^T;
 //            gate path: d logit -> dW_g, dc_g, dA_g, and the T-invariant term dc0 -> dB_g, db_g, dh0 once per sequence.
 //
-// Supported: E = 1, no spatial gating, time gating on or off, no dX (the reference never asks for it: train_rnn.py:256);
-// sizes such that everything fits the 227 KB of one SM (persist_smem_floats).  Everything else takes the per-op kernels.
+//            node gates (graphML.py:2379-2407): q = sigmoid(GraphFilter_{F->1}(tanh(A_n(S)x_t + B_n(S)h0 + 2 b_n))) per node, the
+//            F -> 1 head contracted first and shifted as a scalar signal (Horner), applied as g_i q_i[n] a + g_f q_f[n] r.
+//
+// Supported: E = 1, time gating on or off, node gating on or off (not edge gating), no dX (the reference never asks for it:
+// train_rnn.py:256); sizes such that everything fits the 227 KB of one SM.  Everything else takes the per-op kernels.
 #pragma once
 #include "common.cuh"
 
@@ -25,37 +28,41 @@ namespace persist {
 constexpr int PT = 512;       // threads per CTA
 
 struct Args {
-  int N, F, G, Kin, Kst, tg, has_bias;
+  int N, F, G, Kin, Kst, tg, node, has_bias;
   long long B, T;
   const int *cptr, *cidx; const float* cval;     // gather form of z @ S   (CSC of S):  out[n] = sum_p cval[p] in[cidx[p]]
   const int *rptr, *ridx; const float* rval;     // gather form of g @ S^T (CSR of S)
   int nnz;                                       // entries of S
   int lists_smem;                                // 1: both gather lists are staged in shared memory (16-bit indices)
   const float *A, *Bw, *bias;                    // [F,Kin,G] [F,Kst,F] [F]
-  const float *tA[2], *tB[2], *tb[2], *tW[2], *tc[2];
+  const float *tA[2], *tB[2], *tb[2], *tW[2], *tc[2];          // time-gate sub-cells + MLP
+  const float *nA[2], *nB[2], *nb[2], *nhw[2], *nhb[2];         // node-gate sub-cells + F -> 1 head [Kst][F], [1]
   const float *X, *h0;                           // [B,T,G,N] [B,F,N]
   float* H;                                      // [B,T,F,N]  (forward: out; backward: in)
   float* gt;                                     // [2][B][T] time-gate values (forward: out; backward: in)
+  float* qn;                                     // [2][B][T][N] node-gate values (forward: out; backward: in)
   // backward
   const float* dH; long long dH_bstride, dH_tstride; int dh_last_only;   // dH[b,t] = dH + b*bstride + t*tstride ([F][N]); last_only: zero for t < T-1
   float *dA, *dBw, *dbias, *dtA[2], *dtB[2], *dtb[2], *dtW[2], *dtc[2];
+  float *dnA[2], *dnB[2], *dnb[2], *dnhw[2], *dnhb[2];
   float* dh0;                                    // [B,F,N] or null
 };
 
 // shared-memory floats of the two kernels (same formula on host and device)
-__host__ __device__ inline long long weights_floats(int F, int G, int Kin, int Kst, int N, int tg) {
+__host__ __device__ inline long long weights_floats(int F, int G, int Kin, int Kst, int N, int tg, int node) {
   const long long cell = (long long)F * Kin * G + (long long)F * Kst * F + F;
-  return cell + (tg ? 2 * cell + 2LL * F * N : 0);
+  return cell + (tg ? 2 * cell + 2LL * F * N : 0) + (node ? 2 * cell + 2LL * Kst * F : 0);
 }
-__host__ __device__ inline long long fwd_floats(int F, int G, int Kin, int Kst, int N, int tg) {
-  return weights_floats(F, G, Kin, Kst, N, tg) + (long long)Kin * G * N + (long long)Kst * F * N + (long long)F * N /*hn*/ +
-         (tg ? 2LL * F * N : 0) /*c0*/ + 64;
-}
-__host__ __device__ inline long long bwd_floats(int F, int G, int Kin, int Kst, int N, int tg) {
+__host__ __device__ inline long long fwd_floats(int F, int G, int Kin, int Kst, int N, int tg, int node) {
   const long long FN = (long long)F * N;
-  return weights_floats(F, G, Kin, Kst, N, tg) /*weights*/ + weights_floats(F, G, Kin, Kst, N, tg) /*gradient accumulators*/ +
-         (long long)Kin * G * N + (long long)Kst * F * N + 5 * FN /*da dr dh b1 b2*/ + (tg ? 3 * FN : 0) /*c0 x2... see kernel*/ +
-         (tg ? 2 * FN : 0) + 64;
+  return weights_floats(F, G, Kin, Kst, N, tg, node) + (long long)Kin * G * N + (long long)Kst * FN + FN /*hn*/ +
+         (tg ? 2 * FN : 0) /*c0*/ + (node ? 3 * FN + (long long)Kst * N + 2LL * N : 0) /*c0n, s, pk, q*/ + 64;
+}
+__host__ __device__ inline long long bwd_floats(int F, int G, int Kin, int Kst, int N, int tg, int node) {
+  const long long FN = (long long)F * N;
+  return 2 * weights_floats(F, G, Kin, Kst, N, tg, node) /*weights + gradient accumulators*/ +
+         (long long)Kin * G * N + (long long)Kst * FN + 5 * FN /*da dr dh b1 b2*/ + (tg ? 4 * FN : 0) /*c0, dc0*/ +
+         ((tg || node) ? FN : 0) /*dpu*/ + (node ? 5 * FN + (long long)Kst * N + 4LL * N : 0) /*c0n, dc0n, s, vch, q, dq*/ + 64;
 }
 
 // shared-memory bytes of ONE staged gather list: ptr[N+1] (int), val[nnz] (float), idx[nnz] (u16), 16-byte aligned pieces
@@ -162,35 +169,97 @@ __device__ __forceinline__ void contract(const float* W, const float* z, int f, 
   }
 }
 
+struct Sub { float *A, *B, *b; };                 // an ungated sub-cell: input taps, state taps, bias
 struct Weights {
-  float *A, *Bw, *bias, *tA0, *tB0, *tb0, *tW0, *tA1, *tB1, *tb1, *tW1;
-  __device__ __forceinline__ float* tA(int g) const { return g ? tA1 : tA0; }
-  __device__ __forceinline__ float* tB(int g) const { return g ? tB1 : tB0; }
-  __device__ __forceinline__ float* tb(int g) const { return g ? tb1 : tb0; }
-  __device__ __forceinline__ float* tW(int g) const { return g ? tW1 : tW0; }
+  float *A, *Bw, *bias;
+  Sub ts[2]; float* tW[2];                       // time gates: sub-cell + MLP weights [F*N]
+  Sub ns[2]; float* nh[2];                       // node gates: sub-cell + head taps [Kst][F]
 };
 __device__ __forceinline__ float* carve(Weights& w, float* p, const Args& a) {
   const int nA = a.F * a.Kin * a.G, nB = a.F * a.Kst * a.F;
   w.A = p; p += nA; w.Bw = p; p += nB; w.bias = p; p += a.F;
-  w.tA0 = w.tB0 = w.tb0 = w.tW0 = w.tA1 = w.tB1 = w.tb1 = w.tW1 = p;
-  if (a.tg) {
-    w.tA0 = p; p += nA; w.tB0 = p; p += nB; w.tb0 = p; p += a.F; w.tW0 = p; p += a.F * a.N;
-    w.tA1 = p; p += nA; w.tB1 = p; p += nB; w.tb1 = p; p += a.F; w.tW1 = p; p += a.F * a.N;
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    w.ts[g].A = w.ts[g].B = w.ts[g].b = w.tW[g] = p;
+    if (a.tg) { w.ts[g].A = p; p += nA; w.ts[g].B = p; p += nB; w.ts[g].b = p; p += a.F; w.tW[g] = p; p += a.F * a.N; }
+  }
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    w.ns[g].A = w.ns[g].B = w.ns[g].b = w.nh[g] = p;
+    if (a.node) { w.ns[g].A = p; p += nA; w.ns[g].B = p; p += nB; w.ns[g].b = p; p += a.F; w.nh[g] = p; p += a.Kst * a.F; }
   }
   return p;
+}
+__device__ __forceinline__ void load_sub(const Sub& s, const float* A, const float* B, const float* b, const Args& a) {
+  const int nA = a.F * a.Kin * a.G, nB = a.F * a.Kst * a.F;
+  for (int i = threadIdx.x; i < nA; i += PT) s.A[i] = A[i];
+  for (int i = threadIdx.x; i < nB; i += PT) s.B[i] = B[i];
+  for (int i = threadIdx.x; i < a.F; i += PT) s.b[i] = a.has_bias ? b[i] : 0.f;
 }
 __device__ __forceinline__ void load_weights(const Weights& w, const Args& a) {
   const int nA = a.F * a.Kin * a.G, nB = a.F * a.Kst * a.F, FN = a.F * a.N;
   for (int i = threadIdx.x; i < nA; i += PT) w.A[i] = a.A[i];
   for (int i = threadIdx.x; i < nB; i += PT) w.Bw[i] = a.Bw[i];
   for (int i = threadIdx.x; i < a.F; i += PT) w.bias[i] = a.has_bias ? a.bias[i] : 0.f;
-  if (a.tg)
-    for (int g = 0; g < 2; ++g) {
-      for (int i = threadIdx.x; i < nA; i += PT) w.tA(g)[i] = a.tA[g][i];
-      for (int i = threadIdx.x; i < nB; i += PT) w.tB(g)[i] = a.tB[g][i];
-      for (int i = threadIdx.x; i < a.F; i += PT) w.tb(g)[i] = a.has_bias ? a.tb[g][i] : 0.f;
-      for (int i = threadIdx.x; i < FN; i += PT) w.tW(g)[i] = a.tW[g][i];
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    if (a.tg) {
+      load_sub(w.ts[g], a.tA[g], a.tB[g], a.tb[g], a);
+      for (int i = threadIdx.x; i < FN; i += PT) w.tW[g][i] = a.tW[g][i];
     }
+    if (a.node) {
+      load_sub(w.ns[g], a.nA[g], a.nB[g], a.nb[g], a);
+      for (int i = threadIdx.x; i < a.Kst * a.F; i += PT) w.nh[g][i] = a.nhw[g][i];
+    }
+  }
+}
+// c0[f][n] = sum_{k,g} B_s[f][k][g] zh[k][g][n] + 2 b_s[f]: the T-invariant term of a sub-cell run from the initial state
+template <int NB>
+__device__ __forceinline__ void subcell_c0(const Sub& sc, const float* zh, float* c0, int F, int KCb, int N) {
+  const int NQ = N / NB;
+  for (int e = threadIdx.x; e < F * NQ; e += PT) {
+    const int f = e / NQ, n0 = (e - f * NQ) * NB;
+    float y[NB];
+    contract<NB>(sc.B, zh, f, n0, KCb, N, y);
+#pragma unroll
+    for (int j = 0; j < NB; ++j) c0[f * N + n0 + j] = y[j] + 2.f * sc.b[f];
+  }
+}
+// node-gate head, forward: s = tanh(A_n(S)x_t + c0n) (kept in `sbuf`), p_k[n] = sum_f wh[k][f] s[f][n], Horner with S:
+// lin = p_0 + (p_1 + (... p_{K-1} S ...) S) S, q = sigmoid(lin + c)   -> qs[n]
+template <int NB>
+__device__ __forceinline__ void node_gate_fwd(const Args& a, const List& fw, const Sub& sc, const float* wh, float hb, const float* zx,
+                                              const float* c0n, float* sbuf, float* pk, float* qs) {
+  const int N = a.N, F = a.F, NQ = N / NB, KCa = a.Kin * a.G;
+  for (int e = threadIdx.x; e < F * NQ; e += PT) {
+    const int f = e / NQ, n0 = (e - f * NQ) * NB;
+    float y[NB];
+    contract<NB>(sc.A, zx, f, n0, KCa, N, y);
+#pragma unroll
+    for (int j = 0; j < NB; ++j) sbuf[f * N + n0 + j] = tanhf(y[j] + c0n[f * N + n0 + j]);
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < a.Kst * N; e += PT) {
+    const int k = e / N, n = e - k * N;
+    float s0 = 0.f, s1 = 0.f;
+    int f = 0;
+    for (; f + 1 < F; f += 2) { s0 = fmaf(wh[k * F + f], sbuf[f * N + n], s0); s1 = fmaf(wh[k * F + f + 1], sbuf[(f + 1) * N + n], s1); }
+    if (f < F) s0 = fmaf(wh[k * F + f], sbuf[f * N + n], s0);
+    pk[e] = s0 + s1;
+  }
+  __syncthreads();
+  for (int k = a.Kst - 2; k >= 0; --k) {                            // pk[k] += pk[k+1] S
+    const float* cur = pk + (size_t)(k + 1) * N;
+    for (int n = threadIdx.x; n < N; n += PT) {
+      float s = 0.f;
+      const int p1 = fw.ptr[n + 1];
+      for (int p = fw.ptr[n]; p < p1; ++p) s = fmaf(fw.val[p], cur[fw.idx(p)], s);
+      pk[(size_t)k * N + n] += s;
+    }
+    __syncthreads();
+  }
+  for (int n = threadIdx.x; n < N; n += PT) qs[n] = 1.f / (1.f + expf(-(pk[n] + hb)));
+  __syncthreads();
 }
 
 template <int NB>
@@ -205,23 +274,24 @@ __global__ void __launch_bounds__(PT, 1) persist_fwd_k(const Args a) {
   float* zh = p; p += (size_t)a.Kst * FN;
   float* hn = p; p += FN;
   float* c0 = p; p += a.tg ? 2 * FN : 0;
+  float* c0n = p; p += a.node ? 2 * FN : 0;
+  float* sbuf = p; p += a.node ? FN : 0;
+  float* pk = p; p += a.node ? a.Kst * N : 0;
+  float* qs = p; p += a.node ? 2 * N : 0;
   float* red = p; p += 64;
   unsigned char* sp = reinterpret_cast<unsigned char*>(p);
   const List fw = stage_list(sp, a.cptr, a.cidx, a.cval, N, a.nnz, a.lists_smem != 0);
   load_weights(w, a);
   for (int e = threadIdx.x; e < FN; e += PT) zh[e] = a.h0[b * FN + e];
   __syncthreads();
-  if (a.tg) {                                                     // T-invariant gate term: B_g(S) h0 + 2 b_g   (graphML.py:2362, :2417-2423)
+  const bool gated = a.tg || a.node;
+  if (gated) {                                                    // T-invariant gate terms: B_s(S) h0 + 2 b_s   (graphML.py:2362, :2383, :2417-2423)
     chain(fw, zh, a.Kst, F, N);
 #pragma unroll
-    for (int g = 0; g < 2; ++g)
-      for (int e = threadIdx.x; e < F * NQ; e += PT) {
-        const int f = e / NQ, n0 = (e - f * NQ) * NB;
-        float y[NB];
-        contract<NB>(w.tB(g), zh, f, n0, KCb, N, y);
-#pragma unroll
-        for (int j = 0; j < NB; ++j) c0[g * FN + f * N + n0 + j] = y[j] + 2.f * w.tb(g)[f];
-      }
+    for (int g = 0; g < 2; ++g) {
+      if (a.tg) subcell_c0<NB>(w.ts[g], zh, c0 + g * FN, F, KCb, N);
+      if (a.node) subcell_c0<NB>(w.ns[g], zh, c0n + g * FN, F, KCb, N);
+    }
     __syncthreads();
   }
   for (long long t = 0; t < a.T; ++t) {
@@ -237,9 +307,9 @@ __global__ void __launch_bounds__(PT, 1) persist_fwd_k(const Args a) {
         for (int e = threadIdx.x; e < F * NQ; e += PT) {
           const int f = e / NQ, n0 = (e - f * NQ) * NB;
           float y[NB];
-          contract<NB>(w.tA(g), zx, f, n0, KCa, N, y);
+          contract<NB>(w.ts[g].A, zx, f, n0, KCa, N, y);
 #pragma unroll
-          for (int j = 0; j < NB; ++j) part = fmaf(w.tW(g)[f * N + n0 + j], tanhf(y[j] + c0[g * FN + f * N + n0 + j]), part);
+          for (int j = 0; j < NB; ++j) part = fmaf(w.tW[g][f * N + n0 + j], tanhf(y[j] + c0[g * FN + f * N + n0 + j]), part);
         }
         const float logit = block_sum(part, red) + (a.has_bias ? __ldg(a.tc[g]) : 0.f);
         const float gv = 1.f / (1.f + expf(-logit));
@@ -247,7 +317,15 @@ __global__ void __launch_bounds__(PT, 1) persist_fwd_k(const Args a) {
         if (threadIdx.x == 0) a.gt[((long long)g * a.B + b) * a.T + t] = gv;
       }
     }
-    if (!(a.tg && t == 0)) chain(fw, zh, a.Kst, F, N);            // at t = 0 with gating the h0 chain is already there
+    if (a.node) {
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        node_gate_fwd<NB>(a, fw, w.ns[g], w.nh[g], a.has_bias ? __ldg(a.nhb[g]) : 0.f, zx, c0n + g * FN, sbuf, pk, qs + g * N);
+        float* qo = a.qn + (((long long)g * a.B + b) * a.T + t) * N;
+        for (int n = threadIdx.x; n < N; n += PT) qo[n] = qs[g * N + n];
+      }
+    }
+    if (!(gated && t == 0)) chain(fw, zh, a.Kst, F, N);           // at t = 0 with gating the h0 chain is already there
     float* Ht = a.H + (b * a.T + t) * FN;
     for (int e = threadIdx.x; e < F * NQ; e += PT) {
       const int f = e / NQ, n0 = (e - f * NQ) * NB;
@@ -257,7 +335,8 @@ __global__ void __launch_bounds__(PT, 1) persist_fwd_k(const Args a) {
       const float bb = w.bias[f];                                  // the same bias in both filters (:2405-2407)
 #pragma unroll
       for (int j = 0; j < NB; ++j) {
-        const float h = tanhf(fmaf(gi, av[j] + bb, gf * (rv[j] + bb)));
+        const float wi = a.node ? gi * qs[n0 + j] : gi, wf = a.node ? gf * qs[N + n0 + j] : gf;
+        const float h = tanhf(fmaf(wi, av[j] + bb, wf * (rv[j] + bb)));
         Ht[f * N + n0 + j] = h;
         hn[f * N + n0 + j] = h;
       }
@@ -338,6 +417,26 @@ __device__ __forceinline__ void adjoint_chain(const Args& a, const List& bw, con
   }
 }
 
+// T-invariant term of a sub-cell, backward: v = sum_t d pre_s.  dB_s += v zh0^T, db_s += 2 sum_n v, dh0 += adjoint chain
+template <int NB>
+__device__ __forceinline__ void subcell_c0_bwd(const Args& a, const List& bw, const Sub& sc, const Sub& gsc, const float* v, const float* zh,
+                                               float* b1, float* b2, float* dh) {
+  const int N = a.N, F = a.F;
+  wgrad_acc<NB>(gsc.B, v, zh, F, a.Kst * F, N);
+  for (int f = threadIdx.x; f < F; f += PT) {
+    float s = 0.f;
+    for (int n = 0; n < N; ++n) s += v[(size_t)f * N + n];
+    gsc.b[f] += 2.f * s;                                           // the sub-cell adds its bias twice (:2421-2422)
+  }
+  if (a.dh0) adjoint_chain<NB>(a, bw, sc.B, v, b1, b2, dh, a.Kst, F, true);
+  __syncthreads();
+}
+__device__ __forceinline__ void flush_sub(const Sub& g, float* dA, float* dB, float* db, int nA, int nB, int F) {
+  for (int i = threadIdx.x; i < nA; i += PT) if (dA) atomicAdd(dA + i, g.A[i]);
+  for (int i = threadIdx.x; i < nB; i += PT) if (dB) atomicAdd(dB + i, g.B[i]);
+  for (int i = threadIdx.x; i < F; i += PT) if (db) atomicAdd(db + i, g.b[i]);
+}
+
 template <int NB>
 __global__ void __launch_bounds__(PT, 1) persist_bwd_k(const Args a) {
   extern __shared__ __align__(16) float psm[];
@@ -357,37 +456,49 @@ __global__ void __launch_bounds__(PT, 1) persist_bwd_k(const Args a) {
   float* b2 = p; p += FN;
   float* c0 = p; p += a.tg ? 2 * FN : 0;
   float* dc0 = p; p += a.tg ? 2 * FN : 0;
-  float* dpu = p; p += a.tg ? FN : 0;
+  float* dpu = p; p += (a.tg || a.node) ? FN : 0;
+  float* c0n = p; p += a.node ? 2 * FN : 0;
+  float* dc0n = p; p += a.node ? 2 * FN : 0;
+  float* sbuf = p; p += a.node ? FN : 0;
+  float* vch = p; p += a.node ? a.Kst * N : 0;
+  float* qs = p; p += a.node ? 2 * N : 0;
+  float* dq = p; p += a.node ? 2 * N : 0;
   float* red = p; p += 64;
   unsigned char* sp = reinterpret_cast<unsigned char*>(p);
   const List fw = stage_list(sp, a.cptr, a.cidx, a.cval, N, a.nnz, a.lists_smem != 0);
   const List bw = stage_list(sp, a.rptr, a.ridx, a.rval, N, a.nnz, a.lists_smem != 0);
   load_weights(w, a);
   for (float* q = gacc.A; q < zx; q += PT) { if (q + threadIdx.x < zx) q[threadIdx.x] = 0.f; }      // zero every accumulator
-  for (int e = threadIdx.x; e < FN; e += PT) { dh[e] = 0.f; if (a.tg) { dc0[e] = 0.f; dc0[FN + e] = 0.f; } }
-  float dtc[2] = {0.f, 0.f};
+  for (int e = threadIdx.x; e < FN; e += PT) {
+    dh[e] = 0.f;
+    if (a.tg) { dc0[e] = 0.f; dc0[FN + e] = 0.f; }
+    if (a.node) { dc0n[e] = 0.f; dc0n[FN + e] = 0.f; }
+  }
+  float dtc[2] = {0.f, 0.f}, dnc[2] = {0.f, 0.f};
   __syncthreads();
-  if (a.tg) {                                                     // c0 of both gates (needed to recompute u at every step)
+  const bool gated = a.tg || a.node;
+  if (gated) {                                                    // c0 of every gate sub-cell (needed to recompute their states)
     for (int e = threadIdx.x; e < FN; e += PT) zh[e] = a.h0[b * FN + e];
     __syncthreads();
     chain(fw, zh, a.Kst, F, N);
 #pragma unroll
-    for (int g = 0; g < 2; ++g)
-      for (int e = threadIdx.x; e < F * NQ; e += PT) {
-        const int f = e / NQ, n0 = (e - f * NQ) * NB;
-        float y[NB];
-        contract<NB>(w.tB(g), zh, f, n0, KCb, N, y);
-#pragma unroll
-        for (int j = 0; j < NB; ++j) c0[g * FN + f * N + n0 + j] = y[j] + 2.f * w.tb(g)[f];
-      }
+    for (int g = 0; g < 2; ++g) {
+      if (a.tg) subcell_c0<NB>(w.ts[g], zh, c0 + g * FN, F, KCb, N);
+      if (a.node) subcell_c0<NB>(w.ns[g], zh, c0n + g * FN, F, KCb, N);
+    }
     __syncthreads();
   }
-  constexpr int GB = NB;                                          // F % 4 == 0 is part of the NB = 4 eligibility
   for (long long t = a.T - 1; t >= 0; --t) {
     const float* hprev = t > 0 ? a.H + (b * a.T + t - 1) * FN : a.h0 + b * FN;
     const float* xt = a.X + (b * a.T + t) * GN;
     for (int e = threadIdx.x; e < FN; e += PT) zh[e] = hprev[e];
     for (int e = threadIdx.x; e < GN; e += PT) zx[e] = xt[e];
+    if (a.node)
+      for (int e = threadIdx.x; e < 2 * N; e += PT) {
+        const int g = e / N, n = e - g * N;
+        qs[e] = a.qn[(((long long)g * a.B + b) * a.T + t) * N + n];
+        dq[e] = 0.f;
+      }
     __syncthreads();
     chain(fw, zh, a.Kst, F, N);
     chain(fw, zx, a.Kin, a.G, N);
@@ -405,11 +516,14 @@ __global__ void __launch_bounds__(PT, 1) persist_bwd_k(const Args a) {
       const float bb = w.bias[f];
 #pragma unroll
       for (int j = 0; j < NB; ++j) {
-        const int o = f * N + n0 + j;
+        const int n = n0 + j, o = f * N + n;
         const float h = Ht[o];
         const float dp = ((has_dH ? dHt[o] : 0.f) + dh[o]) * (1.f - h * h);
-        sgi = fmaf(dp, av[j] + bb, sgi); sgf = fmaf(dp, rv[j] + bb, sgf);
-        da[o] = gi * dp; dr[o] = gf * dp;
+        const float qi = a.node ? qs[n] : 1.f, qf = a.node ? qs[N + n] : 1.f;
+        const float ta = dp * (av[j] + bb), tr = dp * (rv[j] + bb);      // d pre / d (g_i q_i), d pre / d (g_f q_f)
+        sgi = fmaf(ta, qi, sgi); sgf = fmaf(tr, qf, sgf);
+        if (a.node) { atomicAdd(dq + n, gi * ta); atomicAdd(dq + N + n, gf * tr); }
+        da[o] = gi * qi * dp; dr[o] = gf * qf * dp;
       }
     }
     float dgi = 0.f, dgf = 0.f;
@@ -422,7 +536,7 @@ __global__ void __launch_bounds__(PT, 1) persist_bwd_k(const Args a) {
       for (int n = 0; n < N; ++n) s += da[(size_t)f * N + n] + dr[(size_t)f * N + n];
       gacc.bias[f] += s;
     }
-    adjoint_chain<GB>(a, bw, w.Bw, dr, b1, b2, dh, a.Kst, F, false);      // dh_{t-1} (recurrent part)
+    adjoint_chain<NB>(a, bw, w.Bw, dr, b1, b2, dh, a.Kst, F, false);      // dh_{t-1} (recurrent part)
     if (a.tg) {
 #pragma unroll
       for (int g = 0; g < 2; ++g) {
@@ -432,51 +546,93 @@ __global__ void __launch_bounds__(PT, 1) persist_bwd_k(const Args a) {
         for (int e = threadIdx.x; e < F * NQ; e += PT) {
           const int f = e / NQ, n0 = (e - f * NQ) * NB;
           float y[NB];
-          contract<NB>(w.tA(g), zx, f, n0, KCa, N, y);
+          contract<NB>(w.ts[g].A, zx, f, n0, KCa, N, y);
 #pragma unroll
           for (int j = 0; j < NB; ++j) {
             const int o = f * N + n0 + j;
             const float u = tanhf(y[j] + c0[g * FN + o]);
-            gacc.tW(g)[o] += dl * u;
-            const float dd = dl * w.tW(g)[o] * (1.f - u * u);
+            gacc.tW[g][o] += dl * u;
+            const float dd = dl * w.tW[g][o] * (1.f - u * u);
             dc0[g * FN + o] += dd;
             dpu[o] = dd;
           }
         }
         __syncthreads();
-        wgrad_acc<NB>(gacc.tA(g), dpu, zx, F, KCa, N);
+        wgrad_acc<NB>(gacc.ts[g].A, dpu, zx, F, KCa, N);
+        __syncthreads();
+      }
+    }
+    if (a.node) {
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        // d lin = dq q (1 - q);  v_k = v_{k-1} S^T (k < Kst) are the gradients of the head's tap outputs p_k
+        float part = 0.f;
+        for (int n = threadIdx.x; n < N; n += PT) {
+          const float q = qs[g * N + n];
+          const float dl = dq[g * N + n] * q * (1.f - q);
+          vch[n] = dl;
+          part += dl;
+        }
+        dnc[g] += block_sum(part, red);
+        for (int k = 1; k < a.Kst; ++k) {
+          const float* cur = vch + (size_t)(k - 1) * N;
+          for (int n = threadIdx.x; n < N; n += PT) {
+            float s = 0.f;
+            const int p1 = bw.ptr[n + 1];
+            for (int pp = bw.ptr[n]; pp < p1; ++pp) s = fmaf(bw.val[pp], cur[bw.idx(pp)], s);
+            vch[(size_t)k * N + n] = s;
+          }
+          __syncthreads();
+        }
+        // recompute the sub-cell state s, then d wh[k][f] += sum_n v_k[n] s[f][n],  d pre_s = (sum_k wh[k][f] v_k[n]) (1 - s^2)
+        for (int e = threadIdx.x; e < F * NQ; e += PT) {
+          const int f = e / NQ, n0 = (e - f * NQ) * NB;
+          float y[NB];
+          contract<NB>(w.ns[g].A, zx, f, n0, KCa, N, y);
+#pragma unroll
+          for (int j = 0; j < NB; ++j) sbuf[f * N + n0 + j] = tanhf(y[j] + c0n[g * FN + f * N + n0 + j]);
+        }
+        __syncthreads();
+        wgrad_acc<NB>(gacc.nh[g], vch, sbuf, a.Kst, F, N);
+        for (int o = threadIdx.x; o < FN; o += PT) {
+          const int f = o / N, n = o - f * N;
+          float ds = 0.f;
+          for (int k = 0; k < a.Kst; ++k) ds = fmaf(w.nh[g][k * F + f], vch[(size_t)k * N + n], ds);
+          const float sv = sbuf[o];
+          const float dd = ds * (1.f - sv * sv);
+          dc0n[g * FN + o] += dd;
+          dpu[o] = dd;
+        }
+        __syncthreads();
+        wgrad_acc<NB>(gacc.ns[g].A, dpu, zx, F, KCa, N);
         __syncthreads();
       }
     }
   }
-  // ---- T-invariant gate term: after t = 0 the zh buffers hold h0's chain ------------------------------------------------------
-  if (a.tg) {
+  // ---- T-invariant gate terms: after t = 0 the zh buffers hold h0's chain ---------------------------------------------------
 #pragma unroll
-    for (int g = 0; g < 2; ++g) {
-      const float* v = dc0 + (size_t)g * FN;
-      wgrad_acc<NB>(gacc.tB(g), v, zh, F, KCb, N);
-      for (int f = threadIdx.x; f < F; f += PT) {
-        float s = 0.f;
-        for (int n = 0; n < N; ++n) s += v[(size_t)f * N + n];
-        gacc.tb(g)[f] += 2.f * s;                                  // the sub-cell adds its bias twice (:2421-2422)
-      }
-      if (a.dh0) adjoint_chain<GB>(a, bw, w.tB(g), v, b1, b2, dh, a.Kst, F, true);
-      __syncthreads();
-    }
+  for (int g = 0; g < 2; ++g) {
+    if (a.tg) subcell_c0_bwd<NB>(a, bw, w.ts[g], gacc.ts[g], dc0 + (size_t)g * FN, zh, b1, b2, dh);
+    if (a.node) subcell_c0_bwd<NB>(a, bw, w.ns[g], gacc.ns[g], dc0n + (size_t)g * FN, zh, b1, b2, dh);
   }
   if (a.dh0) for (int e = threadIdx.x; e < FN; e += PT) a.dh0[b * FN + e] = dh[e];
   // ---- one atomicAdd per parameter and CTA ---------------------------------------------------------------------------------
   for (int i = threadIdx.x; i < nA; i += PT) if (a.dA) atomicAdd(a.dA + i, gacc.A[i]);
   for (int i = threadIdx.x; i < nB; i += PT) if (a.dBw) atomicAdd(a.dBw + i, gacc.Bw[i]);
   for (int i = threadIdx.x; i < F; i += PT) if (a.dbias) atomicAdd(a.dbias + i, gacc.bias[i]);
-  if (a.tg)
-    for (int g = 0; g < 2; ++g) {
-      for (int i = threadIdx.x; i < nA; i += PT) if (a.dtA[g]) atomicAdd(a.dtA[g] + i, gacc.tA(g)[i]);
-      for (int i = threadIdx.x; i < nB; i += PT) if (a.dtB[g]) atomicAdd(a.dtB[g] + i, gacc.tB(g)[i]);
-      for (int i = threadIdx.x; i < F; i += PT) if (a.dtb[g]) atomicAdd(a.dtb[g] + i, gacc.tb(g)[i]);
-      for (int i = threadIdx.x; i < FN; i += PT) if (a.dtW[g]) atomicAdd(a.dtW[g] + i, gacc.tW(g)[i]);
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    if (a.tg) {
+      flush_sub(gacc.ts[g], a.dtA[g], a.dtB[g], a.dtb[g], nA, nB, F);
+      for (int i = threadIdx.x; i < FN; i += PT) if (a.dtW[g]) atomicAdd(a.dtW[g] + i, gacc.tW[g][i]);
       if (threadIdx.x == 0 && a.dtc[g]) atomicAdd(a.dtc[g], dtc[g]);
     }
+    if (a.node) {
+      flush_sub(gacc.ns[g], a.dnA[g], a.dnB[g], a.dnb[g], nA, nB, F);
+      for (int i = threadIdx.x; i < a.Kst * F; i += PT) if (a.dnhw[g]) atomicAdd(a.dnhw[g] + i, gacc.nh[g][i]);
+      if (threadIdx.x == 0 && a.dnhb[g]) atomicAdd(a.dnhb[g], dnc[g]);
+    }
+  }
 }
 
 }  // namespace persist
