@@ -604,6 +604,13 @@ def run_cfg5(args, emit_line=True):
     cell = gg.GGCRNNCell(G, F, K, K, torch.tanh, False, 'edge', 1, True)
     cell.addGSO(S)
     cell = cell.to(dev)
+    # node renumbering owned by the library (graph option 'reorder', include/gcrnn_b200.h): the same cached handle the cell uses
+    gh = gg.graph.get(cell.S, dev, keep_dense=False)
+    gh.set_option('reorder', {'off': 0, 'auto': 1, 'force': 2}[args.cfg5_reorder])
+    reorder = dict(mode=args.cfg5_reorder, reordered=bool(gh.get_option('reordered')),
+                   tile_rows_before=gh.get_option('tile_rows_before_x100') / 100, tile_rows_after=gh.get_option('tile_rows_after_x100') / 100,
+                   note='distinct neighbour rows per 128-node tile / 128 in the caller\'s node order and in the library\'s; the library '
+                        'renumbers (breadth-first balls of 128 nodes) when that lowers it by >= 1.5x')
     used = [dict(cell.named_parameters())[n] for _, _, n in gg.cell_param_slots(False, 'edge', True)]
     gen = torch.Generator(device='cpu').manual_seed(1234 + rank)
     X_host = torch.randn(Bl, T, G, N, generator=gen).pin_memory()
@@ -667,7 +674,7 @@ def run_cfg5(args, emit_line=True):
         out = dict(metric='GCRNN sequences/sec fwd+bwd', value=seqs, unit='sequences/s', n_gpus=world, steps=args.steps, warmup=args.warmup,
                    ms_per_step=ms_dev / args.steps, higher_is_better=True, scaling='strong', vs_baseline=None, dtype='f32', data='synthetic',
                    config=dict(workload='cfg5: sparse directed 16-NN graph N=100000 (CSR SpMM path), F=32 G=1 K=3 T=32 edge-gated GGCRNNCell fwd+bwd',
-                               node_order=order, graph_build_s=round(t_build, 2),
+                               node_order=order, library_reorder=reorder, graph_build_s=round(t_build, 2),
                                global_batch=cfg['B'], per_gpu_batch=Bl, microbatch=mb, precision='fp32',
                                parallelism=f'dp{world} (batch sharded, one gradient all-reduce per step)',
                                l2='per-micro-batch working set (H 13 GB) larger than L2; no explicit flush'),
@@ -826,6 +833,8 @@ def main():
     ap.add_argument('--also', default='bf16,fp32', type=lambda v: [m for m in v.split(',') if m],
                     help='other precisions of the same workload to time briefly for the `modes` object (comma separated; "" = none)')
     ap.add_argument('--no-parity', action='store_true', help='skip the in-run parity measurement')
+    ap.add_argument('--cfg5-reorder', default='auto', choices=['auto', 'off', 'force'],
+                    help='library-owned node renumbering of the fused sparse path (graph option "reorder")')
     ap.add_argument('--cfg5-order', default='hilbert', choices=['hilbert', 'random', 'host'],
                     help='cfg5 graph: built on the GPU with library-owned Hilbert renumbering (default), on the GPU in the random input order, or by the host generator')
     ap.add_argument('--no-secondary', action='store_true', help='N = 1: skip the cfg5 / cfg1 secondary measurements in the same line')

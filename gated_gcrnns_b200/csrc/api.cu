@@ -147,9 +147,29 @@ uint64_t gcrnn_debug_launch_count(void) { return launch_count(); }
 int gcrnn_graph_set_option(gcrnn_graph* g, const char* name, int32_t value) {
   API_BEGIN
   GCRNN_CHECK(g && name, "null argument");
+  if (std::strcmp(name, "reorder") == 0) {          // node renumbering for the fused sparse path (graph.cu: locality_view)
+    GCRNN_CHECK(value >= 0 && value <= 2, "reorder: 0 never, 1 when it pays, 2 always");
+    g->reorder_mode = value;
+    if (g->reorder_state == 2) g->reorder_state = 0;
+    return 0;
+  }
   int* f = option_field(g->opt, name);
   GCRNN_CHECK(f != nullptr, "unknown option '%s'", name);
   *f = value; ++g->opt.epoch;
+  API_END
+}
+int gcrnn_graph_get_option(const gcrnn_graph* g, const char* name, int32_t* value) {
+  API_BEGIN
+  GCRNN_CHECK(g && name && value, "null argument");
+  if (std::strcmp(name, "reorder") == 0) *value = g->reorder_mode;
+  else if (std::strcmp(name, "reordered") == 0) *value = locality_view(g) != g;      // evaluates the ordering if not done yet
+  else if (std::strcmp(name, "tile_rows_before_x100") == 0) { locality_view(g); *value = (int32_t)std::lround(100.f * g->tile_rows[0]); }
+  else if (std::strcmp(name, "tile_rows_after_x100") == 0) { locality_view(g); *value = (int32_t)std::lround(100.f * g->tile_rows[1]); }
+  else {
+    const int* f = option_field(const_cast<gcrnn::Options&>(g->opt), name);
+    GCRNN_CHECK(f != nullptr, "unknown option '%s'", name);
+    *value = *f;
+  }
   API_END
 }
 

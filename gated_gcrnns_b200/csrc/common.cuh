@@ -111,6 +111,15 @@ struct gcrnn_graph {
   int s_planes = 1;                   // operator planes kept, stacked [s_planes * N][N]: 2 when S / dense_scale is not exact in bf16
   std::vector<void*> owned;           // every device allocation, for destroy
   gcrnn::Options opt;                 // tuning switches used by calls made on the graph handle itself (gcrnn_graph_set_option)
+  // Library-owned node reordering for the fused sparse path (graph.cu: locality_view).  The host CSR of a one-operator graph is
+  // kept so that the renumbered copy can be built on first use; `perm` maps new -> old node index (device).
+  std::vector<int> h_ptr, h_idx; std::vector<float> h_val;
+  int reorder_mode = 1;               // graph option "reorder": 0 never, 1 when it pays (default), 2 always
+  mutable int reorder_state = 0;      // 0 not evaluated yet, 1 renumbered copy in use, 2 evaluated and rejected
+  mutable gcrnn_graph* reordered = nullptr;
+  mutable int* perm = nullptr;        // new -> old
+  mutable int* iperm = nullptr;       // old -> new
+  mutable float tile_rows[2] = {0.f, 0.f};   // distinct neighbour rows per 128-node tile / 128, before and after
 };
 
 struct gcrnn_cell {
@@ -181,5 +190,8 @@ size_t cell_backward_tc(const gcrnn_cell* c, const gcrnn_cell_params* p, const f
                         const gcrnn_cell_params* gr, float* dX, float* dh0, void* ws, size_t wsb, int64_t B,
                         int64_t T, cudaStream_t st);
 void tc_prepare_graph(gcrnn_graph* g, const float* S_host);
+
+// graph.cu: the graph whose node numbering the fused sparse kernels should run on (g itself, or its renumbered copy)
+const gcrnn_graph* locality_view(const gcrnn_graph* g);
 
 }  // namespace gcrnn

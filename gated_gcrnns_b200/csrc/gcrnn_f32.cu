@@ -31,6 +31,24 @@ void copy(const Ctx& c, void* dst, const void* src, size_t bytes) {
 }
 void check_launch() { count_launch(); CUDA_OK(cudaGetLastError()); }
 
+// reference layout [.., C, N] -> node-major [.., N, C] (in_dir) or back, through the graph's node renumbering (graph.cu).
+// C == 32: rows are full 128-byte lines, gathered (out) or scattered (in) whole; the reference-layout side stays coalesced.
+struct NodeMap { const int* perm; const int* iperm; explicit operator bool() const { return perm != nullptr; } };
+NodeMap node_map(const gcrnn_graph* g, const gcrnn_graph* view) { return view != g ? NodeMap{g->perm, g->iperm} : NodeMap{nullptr, nullptr}; }
+void permute_nodes(const Ctx& c, bool in_dir, const float* in, float* out, NodeMap m, int C, int N, long long R1, long long R2,
+                   long long is1, long long is2, long long os1, long long os2) {
+  if (c.dry) return;
+  const bool c32 = C == 32 && N >= 1024 && ((uintptr_t)in % 16 == 0) && ((uintptr_t)out % 16 == 0) && is1 % 4 == 0 && is2 % 4 == 0 &&
+                   os1 % 4 == 0 && os2 % 4 == 0;
+  const long long work = R1 * R2 * ((N + 127) / 128);
+  const unsigned grid = (unsigned)std::min<long long>(work, 148LL * 64);
+  if (c32 && in_dir) scatter_rows_c32_k<<<grid, 256, 0, c.st>>>(in, out, N, R1, R2, is1, is2, os1, os2, m.iperm);
+  else if (c32) transpose_c32_k<<<grid, 256, 0, c.st>>>(in, out, N, R1, R2, is1, is2, os1, os2, m.iperm);
+  else if (in_dir) permute_nodes_k<true><<<grid1d(R1 * R2 * N * C, TPB), TPB, 0, c.st>>>(in, out, m.perm, C, N, R1, R2, is1, is2, os1, os2);
+  else permute_nodes_k<false><<<grid1d(R1 * R2 * N * C, TPB), TPB, 0, c.st>>>(in, out, m.perm, C, N, R1, R2, is1, is2, os1, os2);
+  check_launch();
+}
+
 void transpose(const Ctx& c, const float* in, const float* add, float* out, int A, int Bd, long long R1, long long R2,
                long long is1, long long is2, long long os1, long long os2) {
   if (c.dry) return;
@@ -43,7 +61,7 @@ void transpose(const Ctx& c, const float* in, const float* add, float* out, int 
   }
   if (Bd == 32 && A >= 1024 && add == nullptr && ((uintptr_t)in % 16 == 0) && is1 % 4 == 0 && is2 % 4 == 0) {
     const long long work = R1 * R2 * ((A + 127) / 128);
-    transpose_c32_k<<<(unsigned)std::min<long long>(work, 148LL * 64), 256, 0, c.st>>>(in, out, A, R1, R2, is1, is2, os1, os2);
+    transpose_c32_k<<<(unsigned)std::min<long long>(work, 148LL * 64), 256, 0, c.st>>>(in, out, A, R1, R2, is1, is2, os1, os2, nullptr);
     check_launch();
     return;
   }
@@ -525,7 +543,9 @@ size_t cell_forward_e32(const gcrnn_cell* cell, const gcrnn_cell_params* p, cons
                         cudaStream_t st) {
   const CellDims d = dims_of(cell, B, T);
   Arena a(ws, wsb);
-  Ctx c{cell->g, st, a.dry()};
+  const gcrnn_graph* view = locality_view(cell->g);              // the graph itself, or its renumbered copy (graph.cu)
+  const NodeMap perm = node_map(cell->g, view);
+  Ctx c{view, st, a.dry()};
   t_v2_mask = normalise_v2(opt().sparse_v2);
   if (ws != nullptr) cell->fwd_v2_mask = t_v2_mask;
   Saved s; Saved32 x;
@@ -543,12 +563,17 @@ size_t cell_forward_e32(const gcrnn_cell* cell, const gcrnn_cell_params* p, cons
   float* xa = detour ? a.get<float>(d.TB * d.NG) : nullptr;
   float* xb = detour ? a.get<float>(d.TB * d.NG) : nullptr;
   if (a.dry()) return a.off;
-  transpose(c, X, nullptr, s.Xn, d.G, d.N, d.B, d.T, d.T * d.NG, d.NG, d.NG, d.B * d.NG);          // [B,T,G,N] -> [T,B,N,G]
-  transpose(c, h0, nullptr, s.h0n, d.F, d.N, d.B, 1, d.NF, 0, d.NF, 0);                            // [B,F,N]  -> [B,N,F]
+  if (perm) {
+    permute_nodes(c, true, X, s.Xn, perm, d.G, d.N, d.B, d.T, d.T * d.NG, d.NG, d.NG, d.B * d.NG);
+    permute_nodes(c, true, h0, s.h0n, perm, d.F, d.N, d.B, 1, d.NF, 0, d.NF, 0);
+  } else {
+    transpose(c, X, nullptr, s.Xn, d.G, d.N, d.B, d.T, d.T * d.NG, d.NG, d.NG, d.B * d.NG);        // [B,T,G,N] -> [T,B,N,G]
+    transpose(c, h0, nullptr, s.h0n, d.F, d.N, d.B, 1, d.NF, 0, d.NF, 0);                          // [B,F,N]  -> [B,N,F]
+  }
   if (detour) {
     transpose(c, s.Xn, nullptr, xa, (int)d.TB, (int)d.NG, 1, 1, 0, 0, 0, 0);                       // [TB][N*G] -> [N*G][TB]
     for (int k = 1; k < d.Kin; ++k) {
-      spmm(c, cell->g->fwd[0], xa, nullptr, xb, (int)(d.G * d.TB), 1);
+      spmm(c, view->fwd[0], xa, nullptr, xb, (int)(d.G * d.TB), 1);
       transpose(c, xb, nullptr, s.zx + (long long)(k - 1) * d.TB * d.NG, (int)d.NG, (int)d.TB, 1, 1, 0, 0, 0, 0);
       std::swap(xa, xb);
     }
@@ -562,15 +587,16 @@ size_t cell_forward_e32(const gcrnn_cell* cell, const gcrnn_cell_params* p, cons
     case 3: e32_forward_steps<3>(c, d, p, s, x, prep, rc); break;
     default: e32_forward_steps<4>(c, d, p, s, x, prep, rc); break;
   }
-  transpose(c, s.Hn, nullptr, H, d.N, d.F, d.T, d.B, d.B * d.NF, d.NF, d.NF, d.T * d.NF);           // [T,B,N,F] -> [B,T,F,N]
+  if (perm) permute_nodes(c, false, s.Hn, H, perm, d.F, d.N, d.T, d.B, d.B * d.NF, d.NF, d.NF, d.T * d.NF);
+  else transpose(c, s.Hn, nullptr, H, d.N, d.F, d.T, d.B, d.B * d.NF, d.NF, d.NF, d.T * d.NF);      // [T,B,N,F] -> [B,T,F,N]
   return a.off;
 }
 
-struct Bwd32Bufs { float *dya, *dyr, *pa, *pr, *dd, *wch, *dhrec, *acc; float2* dr; };
+struct Bwd32Bufs { float *dya, *dyr, *pa, *pr, *dd, *wch, *dhrec, *acc, *dhn; float2* dr; };
 
 template <int KST>
 void e32_backward_steps(const Ctx& c, const CellDims& d, const gcrnn_cell_params* p, const Saved& s, const Saved32& x,
-                        const DhView& dv, const Bwd32Bufs& b) {
+                        const DhView& dv, const Bwd32Bufs& b, NodeMap perm) {
   const gcrnn_graph* g = c.g;
   const long long BN = d.B * d.N, BNF = d.B * d.NF;
   const Gather& fw = g->fwd[0];
@@ -593,13 +619,21 @@ void e32_backward_steps(const Ctx& c, const CellDims& d, const gcrnn_cell_params
   const int g_node2 = v2(V2_NODE) ? tile_grid(k_node, 256, node_smem, tile_bps(), tiles) : 0;
   auto k_rows = opt().sparse_v2_rows_bps == 3 ? e32::bwd_rows_v2_k<3> : e32::bwd_rows_v2_k<2>;     // 3: more warps, some spills
   const int g_rows2 = v2(V2_ROWS) ? tile_grid(k_rows, 256, 0, opt().sparse_v2_rows_bps == 3 ? 3 : 2, groups) : 0;
+  // dH of step t as the dpre code reads it: the caller's reference layout, or (renumbered graph) converted into b.dhn first
+  struct DhStep { const float* p; long long bs; int node_major; };
+  auto dh_step = [&](long long t) {
+    if (!perm || (dv.last_only && t < d.T - 1)) return DhStep{dv.ptr(t), dv.bstride(t), 0};      // the zero slab needs no renumbering
+    permute_nodes(c, true, dv.ptr(t), b.dhn, perm, d.F, d.N, d.B, 1, dv.bstride(t), 0, d.NF, 0);
+    return DhStep{b.dhn, d.NF, 1};
+  };
   for (long long t = d.T - 1; t >= 0; --t) {
     const float* hn = s.Hn + t * BNF;
     const float* wa = x.wu_a + t * BNF; const float* wr = x.wu_r + t * BNF;
     const float4* info = x.info + 2 * t * BN;
     if (!(fuse_dpre && t < d.T - 1)) {            // otherwise the dh kernel of step t+1 already left dya / dyr of this step
-      e32::dpre_k<<<g_dpre, 256, 0, c.st>>>(dv.ptr(t), dv.bstride(t), t == d.T - 1 ? nullptr : b.dhrec, hn, x.masks + t * BN, b.dya, b.dyr,
-                                            d.N, d.B);
+      const DhStep g = dh_step(t);
+      e32::dpre_k<<<g_dpre, 256, 0, c.st>>>(g.p, g.bs, t == d.T - 1 ? nullptr : b.dhrec, hn, x.masks + t * BN, b.dya, b.dyr,
+                                            d.N, d.B, g.node_major);
       check_launch();
     }
     zero(c, b.dr, BN * sizeof(float2));
@@ -627,10 +661,14 @@ void e32_backward_steps(const Ctx& c, const CellDims& d, const gcrnn_cell_params
       spmm32(c, bw, wc.p[k - 1], out, d.B);
       wc.p[k] = out;
     }
-    if (v2(V2_DH))
-      k_dh<<<g_dh2, 256, dh_smem, c.st>>>(gbw, wc, e32::Chain{}, 0, 1, p->weight_B, nullptr, nullptr, nullptr, b.dhrec, nullptr, d.N, d.B,
-                                          (fuse_dpre && t > 0) ? e32::DpreFuse{dv.ptr(t - 1), dv.bstride(t - 1), s.Hn + (t - 1) * BNF, x.masks + (t - 1) * BN, b.dya, b.dyr}
-                                                               : e32::DpreFuse{});
+    if (v2(V2_DH)) {
+      e32::DpreFuse fz{};
+      if (fuse_dpre && t > 0) {
+        const DhStep g = dh_step(t - 1);
+        fz = e32::DpreFuse{g.p, g.bs, s.Hn + (t - 1) * BNF, x.masks + (t - 1) * BN, b.dya, b.dyr, g.node_major};
+      }
+      k_dh<<<g_dh2, 256, dh_smem, c.st>>>(gbw, wc, e32::Chain{}, 0, 1, p->weight_B, nullptr, nullptr, nullptr, b.dhrec, nullptr, d.N, d.B, fz);
+    }
     else
       e32::dh_k<KST><<<g_dh, 128, 0, c.st>>>(gbw, wc, p->weight_B, b.dhrec, d.N, BN);
     check_launch();
@@ -641,7 +679,9 @@ size_t cell_backward_e32(const gcrnn_cell* cell, const gcrnn_cell_params* p, con
                          const gcrnn_cell_params* gr, float* dh0, void* ws, size_t wsb, int64_t B, int64_t T, cudaStream_t st) {
   const CellDims d = dims_of(cell, B, T);
   Arena a(ws, wsb);
-  Ctx c{cell->g, st, a.dry()};
+  const gcrnn_graph* view = locality_view(cell->g);
+  const NodeMap perm = node_map(cell->g, view);
+  Ctx c{view, st, a.dry()};
   t_v2_mask = (normalise_v2(opt().sparse_v2) & ~(V2_AGG | V2_ROWS)) | (cell->fwd_v2_mask & (V2_AGG | V2_ROWS));
   Saved s; Saved32 x;
   { Arena sa(const_cast<void*>(saved), savedb); s.layout(sa, d); x.layout(sa, d); }
@@ -650,20 +690,22 @@ size_t cell_backward_e32(const gcrnn_cell* cell, const gcrnn_cell_params* p, con
   b.dd = a.get<float>(d.B * d.NF); b.wch = a.get<float>((size_t)(d.Kst - 2) * d.B * d.NF); b.dhrec = a.get<float>(d.B * d.NF);
   b.dr = a.get<float2>(d.B * d.N); b.acc = a.get<float>(e32::AccLayout::TOTAL);
   float* zslab = cell->dh_last_only ? a.get<float>(d.NF) : nullptr;
+  b.dhn = perm ? a.get<float>(d.B * d.NF) : nullptr;      // one step's dH converted to the renumbered node-major layout
   if (a.dry()) return a.off;
   if (zslab) zero(c, zslab, d.NF * sizeof(float));
   const DhView dv{dH, zslab, d.T, d.NF, cell->dh_last_only != 0};
   zero(c, b.acc, e32::AccLayout::TOTAL * sizeof(float));
   switch (d.Kst) {
-    case 2: e32_backward_steps<2>(c, d, p, s, x, dv, b); break;
-    case 3: e32_backward_steps<3>(c, d, p, s, x, dv, b); break;
-    default: e32_backward_steps<4>(c, d, p, s, x, dv, b); break;
+    case 2: e32_backward_steps<2>(c, d, p, s, x, dv, b, perm); break;
+    case 3: e32_backward_steps<3>(c, d, p, s, x, dv, b, perm); break;
+    default: e32_backward_steps<4>(c, d, p, s, x, dv, b, perm); break;
   }
   e32::finalize_k<<<1, 1024, 0, st>>>(b.acc, p->weight_A, p->weight_B, p->bias, p->e_weight[0], p->e_weight[1], gr->weight_A,
                                       gr->weight_B, gr->bias, gr->e_mixer[0], gr->e_weight[0], gr->e_mixer[1], gr->e_weight[1],
                                       d.Kin * d.G, d.Kst);
   check_launch();
-  if (dh0) transpose(c, b.dhrec, nullptr, dh0, d.N, d.F, d.B, 1, d.NF, 0, d.NF, 0);
+  if (dh0 && perm) permute_nodes(c, false, b.dhrec, dh0, perm, d.F, d.N, d.B, 1, d.NF, 0, d.NF, 0);
+  else if (dh0) transpose(c, b.dhrec, nullptr, dh0, d.N, d.F, d.B, 1, d.NF, 0, d.NF, 0);
   return a.off;
 }
 

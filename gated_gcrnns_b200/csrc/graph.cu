@@ -20,6 +20,7 @@ static T* upload(gcrnn_graph* g, const std::vector<T>& v) {
 }
 
 struct HostCsr { std::vector<int> ptr, idx; std::vector<float> val; };
+constexpr int REORDER_MIN_N = 4096;     // below this the whole signal sits in L1 / shared memory anyway
 
 static HostCsr transpose_csr(int N, const HostCsr& a) {
   HostCsr t;
@@ -80,12 +81,13 @@ static void build_attention_pattern(gcrnn_graph* g, const HostCsr& s) {
   g->att_cval = upload(g, cval);
 }
 
-gcrnn_graph* graph_from_host_csr(int N, int E, const std::vector<HostCsr>& ops, int device) {
+gcrnn_graph* graph_from_host_csr(int N, int E, const std::vector<HostCsr>& ops, int device, bool keep_host = true) {
   GCRNN_CHECK(N > 0 && E > 0, "bad graph size N=%d E=%d", N, E);
   DeviceScope dev_scope(device);
   auto* g = new gcrnn_graph();
   g->N = N; g->E = E; g->device = device;
   try {
+    if (E == 1 && keep_host) { g->h_ptr = ops[0].ptr; g->h_idx = ops[0].idx; g->h_val = ops[0].val; }
     for (int e = 0; e < E; ++e) {
       GCRNN_CHECK(ops[e].idx.size() < (size_t)INT32_MAX, "nnz too large");
       g->bwd.push_back(to_device(g, ops[e]));                    // CSR: rows i gather over j
@@ -148,8 +150,101 @@ gcrnn_graph* graph_create_dense(int N, int E, const float* S, int keep_dense, in
 void graph_destroy(gcrnn_graph* g) {
   if (!g) return;
   DeviceScope dev_scope(g->device);
+  if (g->reordered) graph_destroy(g->reordered);
   for (void* p : g->owned) cudaFree(p);
   delete g;
+}
+
+// ---- library-owned node reordering -------------------------------------------------------------------------------------------
+// The fused sparse kernels process tiles of 128 consecutive nodes and live on L1 hits of the gathered neighbour rows
+// (DESIGN.md 4a): what matters is how many DISTINCT neighbour rows a tile touches.  The reference fixes no node order
+// (Utils/graphTools.py builds S in whatever order the data came), so for a graph whose numbering has no locality the library
+// renumbers the nodes itself: tiles are grown as breadth-first balls of 128 nodes (seeded in the order a Cuthill-McKee sweep
+// discovers them), which makes every tile a compact patch of the graph.  X / h0 / dH are gathered and H / dh0 scattered through
+// `perm` at the boundary kernels that convert layouts anyway, so callers never see the internal numbering.
+namespace {
+
+// distinct neighbour rows per tile of `tile` consecutive rows, relative to the tile size (1 = perfect reuse)
+float tile_rows_metric(int N, const std::vector<int>& ptr, const std::vector<int>& idx, int tile) {
+  std::vector<int> stamp(N, -1);
+  long long distinct = 0;
+  for (int i = 0; i < N; ++i) {
+    const int tl = i / tile;
+    for (int p = ptr[i]; p < ptr[i + 1]; ++p) if (stamp[idx[p]] != tl) { stamp[idx[p]] = tl; ++distinct; }
+  }
+  return (float)distinct / (float)N;
+}
+
+// new -> old order: breadth-first balls of `tile` nodes over the symmetrised pattern
+std::vector<int> ball_order(int N, const HostCsr& a, const HostCsr& at, int tile) {
+  std::vector<int> order; order.reserve(N);
+  std::vector<char> taken(N, 0);
+  std::vector<int> seeds; seeds.reserve(N);      // FIFO of nodes seen next to a finished ball (may contain taken nodes)
+  size_t seed_head = 0;
+  int scan = 0, fill = 0;
+  std::vector<int> q; q.reserve(tile); size_t qh = 0;
+  auto visit = [&](int u, auto&& on_neighbour) {
+    for (int p = a.ptr[u]; p < a.ptr[u + 1]; ++p) on_neighbour(a.idx[p]);
+    for (int p = at.ptr[u]; p < at.ptr[u + 1]; ++p) on_neighbour(at.idx[p]);
+  };
+  while ((int)order.size() < N) {
+    int seed = -1;
+    while (seed_head < seeds.size()) { const int c = seeds[seed_head++]; if (!taken[c]) { seed = c; break; } }
+    if (seed < 0) { while (taken[scan]) ++scan; seed = scan; }
+    taken[seed] = 1; q.clear(); qh = 0; q.push_back(seed); ++fill;
+    while (qh < q.size()) {
+      const int u = q[qh++];
+      order.push_back(u);
+      visit(u, [&](int v) {
+        if (taken[v]) return;
+        if (fill < tile) { taken[v] = 1; q.push_back(v); ++fill; } else seeds.push_back(v);
+      });
+    }
+    if (fill >= tile) fill = 0;                    // ball complete; otherwise the pocket was smaller: next seed continues this tile
+  }
+  return order;
+}
+
+}  // namespace
+
+const gcrnn_graph* locality_view(const gcrnn_graph* g) {
+  if (g->reorder_mode == 0 || g->E != 1 || g->h_ptr.empty() || (g->reorder_mode == 1 && g->N < REORDER_MIN_N)) return g;
+  if (g->reorder_state == 0) {
+    const int N = g->N, TILE = 128;
+    HostCsr a{g->h_ptr, g->h_idx, g->h_val};
+    const HostCsr at = transpose_csr(N, a);
+    const std::vector<int> order = ball_order(N, a, at, TILE);
+    std::vector<int> inv(N);
+    for (int i = 0; i < N; ++i) inv[order[i]] = i;
+    HostCsr b; b.ptr.assign(N + 1, 0); b.idx.reserve(a.idx.size()); b.val.reserve(a.idx.size());
+    std::vector<std::pair<int, float>> row;
+    for (int i = 0; i < N; ++i) {
+      const int o = order[i];
+      row.clear();
+      for (int p = a.ptr[o]; p < a.ptr[o + 1]; ++p) row.emplace_back(inv[a.idx[p]], a.val[p]);
+      std::sort(row.begin(), row.end());
+      for (auto& e : row) { b.idx.push_back(e.first); b.val.push_back(e.second); }
+      b.ptr[i + 1] = (int)b.idx.size();
+    }
+    g->tile_rows[0] = tile_rows_metric(N, a.ptr, a.idx, TILE);
+    g->tile_rows[1] = tile_rows_metric(N, b.ptr, b.idx, TILE);
+    const bool pays = g->tile_rows[0] > 1.5f * g->tile_rows[1];
+    if (g->reorder_mode == 2 || pays) {
+      DeviceScope dev_scope(g->device);
+      g->reordered = graph_from_host_csr(N, 1, std::vector<HostCsr>{b}, g->device, false);
+      int* d = nullptr;
+      CUDA_OK(cudaMalloc(&d, (size_t)2 * N * sizeof(int)));
+      const_cast<gcrnn_graph*>(g)->owned.push_back(d);
+      CUDA_OK(cudaMemcpy(d, order.data(), (size_t)N * sizeof(int), cudaMemcpyHostToDevice));
+      CUDA_OK(cudaMemcpy(d + N, inv.data(), (size_t)N * sizeof(int), cudaMemcpyHostToDevice));
+      g->perm = d; g->iperm = d + N;
+      g->reordered->opt = g->opt;
+      g->reorder_state = 1;
+    } else {
+      g->reorder_state = 2;
+    }
+  }
+  return g->reorder_state == 1 ? g->reordered : g;
 }
 
 }  // namespace gcrnn

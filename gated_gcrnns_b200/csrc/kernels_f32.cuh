@@ -58,8 +58,11 @@ __global__ void transpose_k(const float* __restrict__ in, const float* add, floa
 
 // node-major -> feature-major with 32 channels: in[r][a][32] -> out[r][32][a].  A block moves a 128 x 32 tile with 16 KB of
 // float4 loads in flight (the generic 32 x 32 tiles leave HBM latency-bound at ~3 TB/s); same (r1, r2) stride interface.
+// rowmap != nullptr: output column a comes from input row rowmap[a] (library-owned node renumbering, graph.cu: rowmap = old -> new);
+// a row is one full 128-byte line, so the renumbering costs gathered lines on the read side and nothing on the write side.
 __global__ void __launch_bounds__(256) transpose_c32_k(const float* __restrict__ in, float* __restrict__ out, int A,
-                                                       long long R1, long long R2, long long is1, long long is2, long long os1, long long os2) {
+                                                       long long R1, long long R2, long long is1, long long is2, long long os1, long long os2,
+                                                       const int* __restrict__ rowmap) {
   __shared__ float tile[128][33];
   const long long R = R1 * R2;
   const int tiles_a = (A + 127) / 128;
@@ -67,13 +70,18 @@ __global__ void __launch_bounds__(256) transpose_c32_k(const float* __restrict__
   for (long long w = blockIdx.x; w < R * tiles_a; w += gridDim.x) {
     const long long r = w / tiles_a; const int a0 = (int)(w - r * tiles_a) * 128;
     const long long r1 = r / R2, r2 = r % R2;
-    const float4* ip = reinterpret_cast<const float4*>(in + r1 * is1 + r2 * is2 + (long long)a0 * 32);
+    const float* ib = in + r1 * is1 + r2 * is2;
     float* op = out + r1 * os1 + r2 * os2 + a0;
     float4 v[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const int idx = threadIdx.x + 256 * q;
-      v[q] = (a0 + (idx >> 3) < A) ? __ldg(ip + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const int idx = threadIdx.x + 256 * q, a = a0 + (idx >> 3);
+      if (a < A) {
+        const long long row = rowmap ? __ldg(rowmap + a) : a;
+        v[q] = __ldg(reinterpret_cast<const float4*>(ib + row * 32) + (idx & 7));
+      } else {
+        v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     }
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -91,6 +99,59 @@ __global__ void __launch_bounds__(256) transpose_c32_k(const float* __restrict__
       }
     }
     __syncthreads();
+  }
+}
+
+// feature-major -> node-major with 32 channels through a row map: in[r][32][a] -> out[r][rowmap[a]][32] (coalesced reads along a,
+// one full 128-byte line written per node)
+__global__ void __launch_bounds__(256) scatter_rows_c32_k(const float* __restrict__ in, float* __restrict__ out, int A,
+                                                          long long R1, long long R2, long long is1, long long is2, long long os1, long long os2,
+                                                          const int* __restrict__ rowmap) {
+  __shared__ float tile[128][33];
+  const long long R = R1 * R2;
+  const int tiles_a = (A + 127) / 128;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (long long w = blockIdx.x; w < R * tiles_a; w += gridDim.x) {
+    const long long r = w / tiles_a; const int a0 = (int)(w - r * tiles_a) * 128;
+    const long long r1 = r / R2, r2 = r % R2;
+    const float* ip = in + r1 * is1 + r2 * is2 + a0;
+    float* ob = out + r1 * os1 + r2 * os2;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int f = warp + 8 * j;
+#pragma unroll
+      for (int pass = 0; pass < 4; ++pass) {
+        const int node = pass * 32 + lane;
+        tile[node][f] = (a0 + node < A) ? __ldg(ip + (long long)f * A + node) : 0.f;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int idx = threadIdx.x + 256 * q, node = idx >> 3, c = (idx & 7) * 4, a = a0 + node;
+      if (a < A) {
+        const long long row = __ldg(rowmap + a);
+        *(reinterpret_cast<float4*>(ob + row * 32) + (idx & 7)) = make_float4(tile[node][c], tile[node][c + 1], tile[node][c + 2], tile[node][c + 3]);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// reference layout <-> node-major through a node renumbering (perm: new -> old), same (r1, r2) stride interface:
+//   IN : out[r][n][c] = in[r][c][perm[n]]        OUT: out[r][c][perm[n]] = in[r][n][c]
+template <bool IN>
+__global__ void permute_nodes_k(const float* __restrict__ in, float* __restrict__ out, const int* __restrict__ perm, int C, int N,
+                                long long R1, long long R2, long long is1, long long is2, long long os1, long long os2) {
+  const long long total = R1 * R2 * N * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const long long rn = i / C;
+    const int n = (int)(rn % N);
+    const long long r = rn / N, r1 = r / R2, r2 = r % R2;
+    const long long ref = (long long)c * N + __ldg(perm + n), nm = (long long)n * C + c;
+    if (IN) out[r1 * os1 + r2 * os2 + nm] = in[r1 * is1 + r2 * is2 + ref];
+    else    out[r1 * os1 + r2 * os2 + ref] = in[r1 * is1 + r2 * is2 + nm];
   }
 }
 

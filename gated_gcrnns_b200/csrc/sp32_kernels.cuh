@@ -493,7 +493,7 @@ __global__ void __launch_bounds__(128) aggregate_k(const int* __restrict__ cptr,
 __global__ void __launch_bounds__(256) dpre_k(const float* __restrict__ dHt /* dH + t*F*N */, long long sample_stride,
                                               const float* __restrict__ dhrec, const float* __restrict__ hn,
                                               const uint2* __restrict__ masks, float* __restrict__ dya, float* __restrict__ dyr,
-                                              int N, long long R) {
+                                              int N, long long R, int node_major /* 1: dHt is already [R][N][32] */) {
   __shared__ float tile[32][33];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int bit = lane_of_feat(lane);
@@ -502,14 +502,15 @@ __global__ void __launch_bounds__(256) dpre_k(const float* __restrict__ dHt /* d
   for (long long tl = blockIdx.x; tl < tiles; tl += gridDim.x) {
     const long long r = tl / tiles_n; const int n0 = (int)(tl - r * tiles_n) * 32;
     const float* src = dHt + r * sample_stride;
-    for (int f = warp; f < 32; f += 8) tile[f][lane] = (n0 + lane < N) ? src[(size_t)f * N + n0 + lane] : 0.f;
+    if (!node_major)
+      for (int f = warp; f < 32; f += 8) tile[f][lane] = (n0 + lane < N) ? src[(size_t)f * N + n0 + lane] : 0.f;
     __syncthreads();
     for (int nn = warp; nn < 32; nn += 8)
       if (n0 + nn < N) {
         const long long task = r * N + n0 + nn;
         const long long o = task * 32 + lane;
         const float h = hn[o];
-        float gq = tile[lane][nn];
+        float gq = node_major ? src[(size_t)(n0 + nn) * 32 + lane] : tile[lane][nn];
         if (dhrec) gq += dhrec[o];
         gq *= 1.f - h * h;
         const uint2 mk = masks[task];

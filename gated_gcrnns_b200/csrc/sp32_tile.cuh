@@ -308,6 +308,7 @@ struct DpreFuse {
   const float* dHt; long long sample_stride;      // dH + (t-1) F N in the reference layout [B,T,F,N]
   const float* hn; const uint2* masks;            // h_{t-1} [B,N,32] and its relu masks
   float* dya; float* dyr;
+  int node_major;                                 // 1: dHt is node-major [B,N,32] (the renumbered path converts it first), 0: reference layout
 };
 template <int KST, int NT>
 __host__ __device__ constexpr int gc_smem_floats(int mode) {
@@ -397,14 +398,15 @@ __global__ void __launch_bounds__(NT, 512 / NT) gather_contract_k(Gather3 gop, C
         } else if (n < N) {
           if (fz.dHt != nullptr) {                  // fused dpre of the next reverse step
             const uint2 mk = fz.masks[rb + n];
-            const float* dHp = fz.dHt + w.r * fz.sample_stride + n;
+            const float* dHp = fz.dHt + w.r * fz.sample_stride + (fz.node_major ? (size_t)n * 32 : (size_t)n);
+            const size_t fs = fz.node_major ? 1 : (size_t)N;      // stride between features
 #pragma unroll
             for (int nt = 0; nt < 4; ++nt) {
               const int f = 8 * nt + 2 * t;          // features f, f + 1: mask bits 8 (f & 3) + (f >> 2)
               const size_t o = (rb + n) * 32 + f;
               const float2 hv = *reinterpret_cast<const float2*>(fz.hn + o);
-              const float g0 = (__ldg(dHp + (size_t)f * N) + dd[nt][2 * h]) * (1.f - hv.x * hv.x);
-              const float g1 = (__ldg(dHp + (size_t)(f + 1) * N) + dd[nt][2 * h + 1]) * (1.f - hv.y * hv.y);
+              const float g0 = (__ldg(dHp + (size_t)f * fs) + dd[nt][2 * h]) * (1.f - hv.x * hv.x);
+              const float g1 = (__ldg(dHp + (size_t)(f + 1) * fs) + dd[nt][2 * h + 1]) * (1.f - hv.y * hv.y);
               const int b0 = 8 * (f & 3) + (f >> 2), b1 = 8 * ((f + 1) & 3) + ((f + 1) >> 2);
               *reinterpret_cast<float2*>(fz.dya + o) = make_float2(((mk.x >> b0) & 1u) ? g0 : 0.f, ((mk.x >> b1) & 1u) ? g1 : 0.f);
               *reinterpret_cast<float2*>(fz.dyr + o) = make_float2(((mk.y >> b0) & 1u) ? g0 : 0.f, ((mk.y >> b1) & 1u) ? g1 : 0.f);

@@ -29,8 +29,15 @@ class Graph:
         return C.c_void_p(self.handle)
 
     def set_option(self, name: str, value: int):
-        """Tuning switch for calls made on the graph handle itself (the debug shift GEMM)."""
+        """Tuning switch for calls made on the graph handle itself (the debug shift GEMM), and ``'reorder'`` (0 never, 1 when it
+        pays, 2 always): the library-owned node renumbering of the fused sparse path (include/gcrnn_b200.h)."""
         _lib.check(_lib.lib().gcrnn_graph_set_option(self.ptr, name.encode(), int(value)), 'graph_set_option')
+
+    def get_option(self, name: str) -> int:
+        """Also reads ``'reordered'`` and ``'tile_rows_before_x100'`` / ``'tile_rows_after_x100'`` (locality diagnostics)."""
+        v = C.c_int32()
+        _lib.check(_lib.lib().gcrnn_graph_get_option(self.ptr, name.encode(), C.byref(v)), 'graph_get_option')
+        return v.value
 
     def info(self):
         n, e, nnz, na = C.c_int32(), C.c_int32(), C.c_int64(), C.c_int64()

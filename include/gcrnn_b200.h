@@ -91,8 +91,17 @@ int         gcrnn_debug_shift_gemm(const gcrnn_graph* g, int32_t backward, const
  *   "fwd_fused"     1 = Horner-form forward of the tensor-core path (csrc/tc_hshift.cuh; off by default, see its header)
  *   "sparse_v2_tc"  tile contractions: 1 = 3xTF32 mma.sync, 0 = packed FFMA2;  "sparse_v2_fuse_dpre", "sparse_v2_bps",
  *                   "sparse_v2_rows_bps"
- * A backward always follows the stage generations its forward used; every change invalidates the handle's captured CUDA graphs. */
+ * A backward always follows the stage generations its forward used; every change invalidates the handle's captured CUDA graphs.
+ *
+ * Graph handles only: "reorder" = 0 never, 1 when it pays (default), 2 always.  The reference fixes no node order
+ * (Utils/graphTools.py builds S in whatever order the data came in); the fused sparse kernels live on L1 reuse of neighbour rows
+ * inside tiles of 128 consecutive nodes.  On first use of a one-operator CSR graph with N >= 4096 the library builds a renumbered
+ * copy (breadth-first balls of 128 nodes) and keeps it when it lowers the distinct neighbour rows per tile by >= 1.5x; X / h0 / dH
+ * are gathered and H / dh0 scattered through the permutation inside the layout-conversion kernels, so callers never see the
+ * internal numbering.  Set it before the first forward on the graph.  gcrnn_graph_get_option also reads "reordered" (0 / 1),
+ * "tile_rows_before_x100" and "tile_rows_after_x100" (distinct neighbour rows per 128-node tile / 128, x 100). */
 int         gcrnn_graph_set_option(gcrnn_graph* g, const char* name, int32_t value);
+int         gcrnn_graph_get_option(const gcrnn_graph* g, const char* name, int32_t* value);
 
 /* ---- graph -------------------------------------------------------------------------------------- */
 /* E operators in CSR, HOST arrays: rowptr[e] has N+1 entries, entry (i, colidx[p]) = S_e[i, j] = vals[p].

@@ -49,7 +49,7 @@ def ragged_graph(N, seed, max_out=31, hub=True):
 PATH_GENERIC, PATH_NODE32 = 0, 1
 
 
-def run_case(N, G_, Kin, Kst, T, B, bias, seed, need_x=False, expect_path=None):
+def run_case(N, G_, Kin, Kst, T, B, bias, seed, need_x=False, expect_path=None, reorder=None):
     torch.manual_seed(seed)
     F_ = 32
     S = ragged_graph(N, seed)
@@ -64,6 +64,8 @@ def run_case(N, G_, Kin, Kst, T, B, bias, seed, need_x=False, expect_path=None):
     cell.addGSO(S)
     cell.load_state_dict({k: v for k, v in p.items()})
     cell = cell.to(device=DEV, dtype=torch.float32)
+    if reorder is not None:
+        gg.graph.get(cell.S, DEV, keep_dense=False).set_option('reorder', reorder)
     Xg = X.float().to(DEV).requires_grad_(need_x)
     hg = h0.float().to(DEV).requires_grad_(True)
     L = _lib.lib()
@@ -72,6 +74,8 @@ def run_case(N, G_, Kin, Kst, T, B, bias, seed, need_x=False, expect_path=None):
     (H * dH.float().to(DEV)).sum().backward()
     torch.cuda.synchronize()
     launches = L.gcrnn_debug_launch_count() - l0
+    if reorder is not None:
+        assert gg.graph.get(cell.S, DEV, keep_dense=False).get_option('reordered') == int(reorder == 2)
     if expect_path is not None:
         took = cell._handle(torch.device(DEV)).get_option('last_path')
         assert took == expect_path, f'forward took path {took}, expected {expect_path}'
@@ -158,6 +162,52 @@ def test_fused_matches_generic_kernels_and_falls_back_for_dX():
         assert relerr(gf[k], gg_[k]) < 2e-5, k
     # dX requested: fused forward, generic reverse sweep on the prefix of the saved state
     run_case(N=130, G_=2, Kin=3, Kst=3, T=4, B=2, bias=True, seed=6, need_x=True)
+
+
+@pytest.mark.parametrize('G_,Kin,Kst,bias', [(1, 3, 3, True), (2, 4, 2, True), (1, 2, 4, False)])
+def test_library_reorder_vs_oracle(G_, Kin, Kst, bias):
+    """The library-owned node renumbering (graph option 'reorder' = 2: forced, the graph is far below the automatic threshold):
+    X / h0 / dH gathered, H / dh0 scattered through the permutation; outputs and every gradient against the fp64 oracle in the
+    CALLER's node order, on a non-symmetric ragged graph (hub column, isolated node, explicit diagonal)."""
+    run_case(N=200, G_=G_, Kin=Kin, Kst=Kst, T=4, B=3, bias=bias, seed=11, expect_path=PATH_NODE32, reorder=2)
+
+
+def test_library_reorder_decision_and_equivalence():
+    """N = 8192 16-NN graph: in the generator's random node order the library renumbers on its own ('reorder' = 1, the default)
+    and the results equal those of the un-renumbered run ('reorder' = 0), also for the last-state-only gradient; the same graph
+    numbered along a Hilbert curve is left alone."""
+    N, F_, K, T, B = 8192, 32, 3, 3, 2
+    res = {}
+    for mode in (0, 1):
+        rp, ci, va, _ = gg.graphs.knn_csr_gpu(N, 16, seed=3, device=DEV, reorder=False)
+        S = gg.graphs.csr_to_torch_sparse(rp, ci, va, N)
+        torch.manual_seed(0)
+        cell = gg.GGCRNNCell(1, F_, K, K, torch.tanh, False, 'edge', 1, True)
+        cell.addGSO(S)
+        cell = cell.to(DEV)
+        gh = gg.graph.get(cell.S, DEV, keep_dense=False)
+        gh.set_option('reorder', mode)
+        assert gh.get_option('reordered') == mode
+        if mode:
+            assert gh.get_option('tile_rows_before_x100') > 1.5 * gh.get_option('tile_rows_after_x100')
+        torch.manual_seed(1)
+        X = torch.randn(B, T, 1, N, device=DEV)
+        h0 = (0.1 * torch.randn(B, F_, N, device=DEV)).requires_grad_(True)
+        dH = torch.randn(B, T, F_, N, device=DEV)
+        H = cell(X, h0)
+        (H * dH).sum().backward()
+        out = [H.detach(), h0.grad.clone()] + [p.grad.clone() for p in cell.parameters() if p.grad is not None]
+        cell.zero_grad(); cell.last_state_only = True
+        h1 = h0.detach().clone().requires_grad_(True)
+        Hl = cell(X, h1)
+        (Hl.select(1, -1) * dH[:, -1]).sum().backward()
+        out += [h1.grad.clone()] + [p.grad.clone() for p in cell.parameters() if p.grad is not None]
+        res[mode] = out
+    for i, (a, b) in enumerate(zip(res[1], res[0])):
+        assert relerr(a, b) < (5e-6 if i == 0 else TOL_GRAD), (i, relerr(a, b))
+    rp, ci, va, _ = gg.graphs.knn_csr_gpu(N, 16, seed=3, device=DEV, reorder=True)
+    S = gg.graphs.csr_to_torch_sparse(rp, ci, va, N)
+    assert gg.graph.get(S, DEV, keep_dense=False).get_option('reordered') == 0, 'a Hilbert-numbered graph needs no renumbering'
 
 
 def test_fused_large_knn_properties():
