@@ -716,25 +716,34 @@ size_t cell_backward_e32(const gcrnn_cell* cell, const gcrnn_cell_params* p, con
 // ===================================================================================================
 namespace {
 constexpr long long PERSIST_SMEM_MAX = 220 * 1024;
+persist::Shape persist_shape(const gcrnn_cell* cell) {
+  const gcrnn_cell_desc& d = cell->d;
+  return persist::Shape{d.F, d.G, d.Kin, d.Kst, cell->g->N, d.time_gating != 0, d.spatial_gating == GCRNN_SPATIAL_NODE,
+                        d.spatial_gating == GCRNN_SPATIAL_EDGE, (int)cell->g->nnz_att};
+}
+// bytes that must sit in shared memory besides the float buffers: the attention pattern of an edge-gated cell
+long long persist_fixed_bytes(const gcrnn_cell* cell) {
+  return cell->d.spatial_gating == GCRNN_SPATIAL_EDGE ? persist::att_bytes(cell->g->N, (int)cell->g->nnz_att) : 0;
+}
 bool persist_ok(const gcrnn_cell* cell) {
   const gcrnn_cell_desc& d = cell->d;
   const gcrnn_graph* g = cell->g;
-  if (!opt().persist || d.E != 1 || g->E != 1 || d.spatial_gating == GCRNN_SPATIAL_EDGE || cell->need_dx) return false;
-  const long long fl = persist::bwd_floats(d.F, d.G, d.Kin, d.Kst, g->N, d.time_gating != 0, d.spatial_gating == GCRNN_SPATIAL_NODE);
-  return fl * 4 <= PERSIST_SMEM_MAX && g->N < 65536;
+  if (!opt().persist || d.E != 1 || g->E != 1 || cell->need_dx || g->N >= 65536 || g->nnz_att >= 65536) return false;
+  return persist::bwd_floats(persist_shape(cell)) * 4 + persist_fixed_bytes(cell) <= PERSIST_SMEM_MAX;
 }
 // stage the gather lists in shared memory when both fit next to the rest
 bool persist_lists_fit(const gcrnn_cell* cell) {
-  const gcrnn_cell_desc& d = cell->d;
   const gcrnn_graph* g = cell->g;
-  const long long fl = persist::bwd_floats(d.F, d.G, d.Kin, d.Kst, g->N, d.time_gating != 0, d.spatial_gating == GCRNN_SPATIAL_NODE);
-  return fl * 4 + 2 * persist::list_bytes(g->N, (int)g->fwd[0].nnz) <= 226 * 1024;
+  return persist::bwd_floats(persist_shape(cell)) * 4 + persist_fixed_bytes(cell) + 2 * persist::list_bytes(g->N, (int)g->fwd[0].nnz) <= 226 * 1024;
 }
 persist::Args persist_args(const gcrnn_cell* cell, const gcrnn_cell_params* p, int64_t B, int64_t T) {
   const gcrnn_graph* g = cell->g;
   persist::Args a{};
   a.N = g->N; a.F = cell->d.F; a.G = cell->d.G; a.Kin = cell->d.Kin; a.Kst = cell->d.Kst;
-  a.tg = cell->d.time_gating != 0; a.node = cell->d.spatial_gating == GCRNN_SPATIAL_NODE; a.has_bias = cell->d.bias != 0; a.B = B; a.T = T;
+  a.tg = cell->d.time_gating != 0; a.node = cell->d.spatial_gating == GCRNN_SPATIAL_NODE; a.edge = cell->d.spatial_gating == GCRNN_SPATIAL_EDGE;
+  a.has_bias = cell->d.bias != 0; a.B = B; a.T = T;
+  a.arptr = g->att_rptr; a.acol = g->att_col; a.aval = g->att_val; a.acptr = g->att_cptr; a.acrow = g->att_crow; a.aceid = g->att_ceid;
+  a.annz = (int)g->nnz_att;
   a.cptr = g->fwd[0].ptr; a.cidx = g->fwd[0].idx; a.cval = g->fwd[0].val;
   a.rptr = g->bwd[0].ptr; a.ridx = g->bwd[0].idx; a.rval = g->bwd[0].val;
   a.nnz = (int)g->fwd[0].nnz; a.lists_smem = persist_lists_fit(cell);
@@ -743,6 +752,7 @@ persist::Args persist_args(const gcrnn_cell* cell, const gcrnn_cell_params* p, i
     for (int i = 0; i < 2; ++i) {
       a.tA[i] = p->t_weight_A[i]; a.tB[i] = p->t_weight_B[i]; a.tb[i] = p->t_bias[i]; a.tW[i] = p->t_mlp_w[i]; a.tc[i] = p->t_mlp_b[i];
       a.nA[i] = p->n_weight_A[i]; a.nB[i] = p->n_weight_B[i]; a.nb[i] = p->n_bias[i]; a.nhw[i] = p->n_head_w[i]; a.nhb[i] = p->n_head_b[i];
+      a.eW[i] = p->e_weight[i]; a.em[i] = p->e_mixer[i];
     }
   }
   return a;
@@ -757,7 +767,7 @@ size_t cell_forward_persist(const gcrnn_cell* cell, const gcrnn_cell_params* p, 
   GCRNN_CHECK(saved != nullptr, "forward needs the `saved` buffer");
   persist::Args a = persist_args(cell, p, B, T);
   a.X = X; a.h0 = h0; a.H = H; a.gt = gt; a.qn = qn;
-  const size_t smem = (size_t)persist::fwd_floats(a.F, a.G, a.Kin, a.Kst, a.N, a.tg, a.node) * sizeof(float) + (a.lists_smem ? persist::list_bytes(a.N, a.nnz) : 0);
+  const size_t smem = (size_t)persist::fwd_floats(persist_shape(cell)) * sizeof(float) + persist_fixed_bytes(cell) + (a.lists_smem ? persist::list_bytes(a.N, a.nnz) : 0);
   static DeviceOnce once;
   if (once.first()) {
     CUDA_OK(cudaFuncSetAttribute(persist::persist_fwd_k<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -784,9 +794,10 @@ size_t cell_backward_persist(const gcrnn_cell* cell, const gcrnn_cell_params* p,
   for (int i = 0; i < 2; ++i) {
     a.dtA[i] = gr->t_weight_A[i]; a.dtB[i] = gr->t_weight_B[i]; a.dtb[i] = gr->t_bias[i]; a.dtW[i] = gr->t_mlp_w[i]; a.dtc[i] = gr->t_mlp_b[i];
     a.dnA[i] = gr->n_weight_A[i]; a.dnB[i] = gr->n_weight_B[i]; a.dnb[i] = gr->n_bias[i]; a.dnhw[i] = gr->n_head_w[i]; a.dnhb[i] = gr->n_head_b[i];
+    a.deW[i] = gr->e_weight[i]; a.dem[i] = gr->e_mixer[i];
   }
   a.dh0 = dh0;
-  const size_t smem = (size_t)persist::bwd_floats(a.F, a.G, a.Kin, a.Kst, a.N, a.tg, a.node) * sizeof(float) + (a.lists_smem ? 2 * persist::list_bytes(a.N, a.nnz) : 0);
+  const size_t smem = (size_t)persist::bwd_floats(persist_shape(cell)) * sizeof(float) + persist_fixed_bytes(cell) + (a.lists_smem ? 2 * persist::list_bytes(a.N, a.nnz) : 0);
   static DeviceOnce once;
   if (once.first()) {
     CUDA_OK(cudaFuncSetAttribute(persist::persist_bwd_k<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -798,15 +809,14 @@ size_t cell_backward_persist(const gcrnn_cell* cell, const gcrnn_cell_params* p,
   return 256;
 }
 
-// which path a forward takes (GCRNN_PATH_*): the persistent kernel for small ungated / time-gated cells, the fused per-node
+// which path a forward takes (GCRNN_PATH_*): the persistent kernel for small graphs (any gating, one edge feature), the fused per-node
 // kernels for F == 32 edge gating when the shape allows, else the generic kernels
 int pick_path(const gcrnn_cell* cell) {
   if (cell->forced_path >= 0) {
     if (cell->forced_path == GCRNN_PATH_NODE32) GCRNN_CHECK(edge32_ok(cell), "path NODE32 does not support this cell");
     if (cell->forced_path == GCRNN_PATH_PERSIST) {
-      const gcrnn_cell_desc& d = cell->d;
-      GCRNN_CHECK(d.E == 1 && d.spatial_gating != GCRNN_SPATIAL_EDGE &&
-                  persist::bwd_floats(d.F, d.G, d.Kin, d.Kst, cell->g->N, d.time_gating != 0, d.spatial_gating == GCRNN_SPATIAL_NODE) * 4 <= PERSIST_SMEM_MAX,
+      GCRNN_CHECK(cell->d.E == 1 && cell->g->nnz_att < 65536 &&
+                  persist::bwd_floats(persist_shape(cell)) * 4 + persist_fixed_bytes(cell) <= PERSIST_SMEM_MAX,
                   "path PERSIST does not support this cell");
     }
     return cell->forced_path;

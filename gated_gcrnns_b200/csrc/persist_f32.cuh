@@ -17,7 +17,12 @@
 //            node gates (graphML.py:2379-2407): q = sigmoid(GraphFilter_{F->1}(tanh(A_n(S)x_t + B_n(S)h0 + 2 b_n))) per node, the
 //            F -> 1 head contracted first and shifted as a scalar signal (Horner), applied as g_i q_i[n] a + g_f q_f[n] r.
 //
-// Supported: E = 1, time gating on or off, node gating on or off (not edge gating), no dX (the reference never asks for it:
+//            edge gates (graphML.py:2409-2416, 521-627): both filter outputs pass through a one-head graph attention layer over
+//            the pattern of S + I (scores leaky_relu(a2.Wy_i + a1.Wy_j), row softmax, S'-weighted aggregation, ReLU); the pattern
+//            (row view + column view with edge ids) sits in shared memory next to the gather lists, attention weights are
+//            recomputed in the reverse sweep.
+//
+// Supported: E = 1, time gating on or off, node OR edge gating or neither, no dX (the reference never asks for it:
 // train_rnn.py:256); sizes such that everything fits the 227 KB of one SM.  Everything else takes the per-op kernels.
 #pragma once
 #include "common.cuh"
@@ -28,7 +33,7 @@ namespace persist {
 constexpr int PT = 512;       // threads per CTA
 
 struct Args {
-  int N, F, G, Kin, Kst, tg, node, has_bias;
+  int N, F, G, Kin, Kst, tg, node, edge, has_bias;
   long long B, T;
   const int *cptr, *cidx; const float* cval;     // gather form of z @ S   (CSC of S):  out[n] = sum_p cval[p] in[cidx[p]]
   const int *rptr, *ridx; const float* rval;     // gather form of g @ S^T (CSR of S)
@@ -37,6 +42,9 @@ struct Args {
   const float *A, *Bw, *bias;                    // [F,Kin,G] [F,Kst,F] [F]
   const float *tA[2], *tB[2], *tb[2], *tW[2], *tc[2];          // time-gate sub-cells + MLP
   const float *nA[2], *nB[2], *nb[2], *nhw[2], *nhb[2];         // node-gate sub-cells + F -> 1 head [Kst][F], [1]
+  // edge gates: attention pattern of S + I (row view; column view carrying row and edge id), weight [F][F], mixer [2F] per gate
+  const int *arptr, *acol; const float* aval; const int *acptr, *acrow, *aceid; int annz;
+  const float *eW[2], *em[2];
   const float *X, *h0;                           // [B,T,G,N] [B,F,N]
   float* H;                                      // [B,T,F,N]  (forward: out; backward: in)
   float* gt;                                     // [2][B][T] time-gate values (forward: out; backward: in)
@@ -45,24 +53,34 @@ struct Args {
   const float* dH; long long dH_bstride, dH_tstride; int dh_last_only;   // dH[b,t] = dH + b*bstride + t*tstride ([F][N]); last_only: zero for t < T-1
   float *dA, *dBw, *dbias, *dtA[2], *dtB[2], *dtb[2], *dtW[2], *dtc[2];
   float *dnA[2], *dnB[2], *dnb[2], *dnhw[2], *dnhb[2];
+  float *deW[2], *dem[2];
   float* dh0;                                    // [B,F,N] or null
 };
 
 // shared-memory floats of the two kernels (same formula on host and device)
-__host__ __device__ inline long long weights_floats(int F, int G, int Kin, int Kst, int N, int tg, int node) {
-  const long long cell = (long long)F * Kin * G + (long long)F * Kst * F + F;
-  return cell + (tg ? 2 * cell + 2LL * F * N : 0) + (node ? 2 * cell + 2LL * Kst * F : 0);
+struct Shape { int F, G, Kin, Kst, N, tg, node, edge, annz; };
+__host__ __device__ inline long long weights_floats(const Shape& s) {
+  const long long cell = (long long)s.F * s.Kin * s.G + (long long)s.F * s.Kst * s.F + s.F;
+  return cell + (s.tg ? 2 * cell + 2LL * s.F * s.N : 0) + (s.node ? 2 * cell + 2LL * s.Kst * s.F : 0) + (s.edge ? 2LL * (s.F * s.F + 2 * s.F) : 0);
 }
-__host__ __device__ inline long long fwd_floats(int F, int G, int Kin, int Kst, int N, int tg, int node) {
-  const long long FN = (long long)F * N;
-  return weights_floats(F, G, Kin, Kst, N, tg, node) + (long long)Kin * G * N + (long long)Kst * FN + FN /*hn*/ +
-         (tg ? 2 * FN : 0) /*c0*/ + (node ? 3 * FN + (long long)Kst * N + 2LL * N : 0) /*c0n, s, pk, q*/ + 64;
+__host__ __device__ inline long long annz4(const Shape& s) { return (s.annz + 3) & ~3; }
+__host__ __device__ inline long long fwd_floats(const Shape& s) {
+  const long long FN = (long long)s.F * s.N;
+  return weights_floats(s) + (long long)s.Kin * s.G * s.N + (long long)s.Kst * FN + FN /*hn*/ +
+         (s.tg ? 2 * FN : 0) /*c0*/ + (s.node ? 3 * FN + (long long)s.Kst * s.N + 2LL * s.N : 0) /*c0n, s, pk, q*/ +
+         (s.edge ? 5 * FN + 2LL * s.N + annz4(s) : 0) /*ya, yr, Wx, out_a, out_r, rr, cc, al*/ + 64;
 }
-__host__ __device__ inline long long bwd_floats(int F, int G, int Kin, int Kst, int N, int tg, int node) {
-  const long long FN = (long long)F * N;
-  return 2 * weights_floats(F, G, Kin, Kst, N, tg, node) /*weights + gradient accumulators*/ +
-         (long long)Kin * G * N + (long long)Kst * FN + 5 * FN /*da dr dh b1 b2*/ + (tg ? 4 * FN : 0) /*c0, dc0*/ +
-         ((tg || node) ? FN : 0) /*dpu*/ + (node ? 5 * FN + (long long)Kst * N + 4LL * N : 0) /*c0n, dc0n, s, vch, q, dq*/ + 64;
+__host__ __device__ inline long long bwd_floats(const Shape& s) {
+  const long long FN = (long long)s.F * s.N;
+  return 2 * weights_floats(s) /*weights + gradient accumulators*/ +
+         (long long)s.Kin * s.G * s.N + (long long)s.Kst * FN + 5 * FN /*da dr dh b1 b2*/ + (s.tg ? 4 * FN : 0) /*c0, dc0*/ +
+         ((s.tg || s.node) ? FN : 0) /*dpu*/ + (s.node ? 5 * FN + (long long)s.Kst * s.N + 4LL * s.N : 0) /*c0n, dc0n, s, vch, q, dq*/ +
+         (s.edge ? 6 * FN + 4LL * s.N + 2 * annz4(s) : 0) /*ya, yr, dp, Wx, out/dy, dWx, rr, cc, drr, dcc, al, tmp*/ + 64;
+}
+// shared-memory bytes of the staged attention pattern: rptr, cptr (int), val (float), col, crow, ceid, erow (u16)
+__host__ __device__ inline long long att_bytes(int N, int annz) {
+  const long long p = ((long long)(N + 1) * 4 + 15) & ~15LL, v = ((long long)annz * 4 + 15) & ~15LL, h = ((long long)annz * 2 + 15) & ~15LL;
+  return 2 * p + v + 4 * h;
 }
 
 // shared-memory bytes of ONE staged gather list: ptr[N+1] (int), val[nnz] (float), idx[nnz] (u16), 16-byte aligned pieces
@@ -174,6 +192,7 @@ struct Weights {
   float *A, *Bw, *bias;
   Sub ts[2]; float* tW[2];                       // time gates: sub-cell + MLP weights [F*N]
   Sub ns[2]; float* nh[2];                       // node gates: sub-cell + head taps [Kst][F]
+  float* eW[2]; float* em[2];                    // edge gates: attention weight [F][F], mixer [2F]
 };
 __device__ __forceinline__ float* carve(Weights& w, float* p, const Args& a) {
   const int nA = a.F * a.Kin * a.G, nB = a.F * a.Kst * a.F;
@@ -187,6 +206,11 @@ __device__ __forceinline__ float* carve(Weights& w, float* p, const Args& a) {
   for (int g = 0; g < 2; ++g) {
     w.ns[g].A = w.ns[g].B = w.ns[g].b = w.nh[g] = p;
     if (a.node) { w.ns[g].A = p; p += nA; w.ns[g].B = p; p += nB; w.ns[g].b = p; p += a.F; w.nh[g] = p; p += a.Kst * a.F; }
+  }
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    w.eW[g] = w.em[g] = p;
+    if (a.edge) { w.eW[g] = p; p += a.F * a.F; w.em[g] = p; p += 2 * a.F; }
   }
   return p;
 }
@@ -210,6 +234,10 @@ __device__ __forceinline__ void load_weights(const Weights& w, const Args& a) {
     if (a.node) {
       load_sub(w.ns[g], a.nA[g], a.nB[g], a.nb[g], a);
       for (int i = threadIdx.x; i < a.Kst * a.F; i += PT) w.nh[g][i] = a.nhw[g][i];
+    }
+    if (a.edge) {
+      for (int i = threadIdx.x; i < a.F * a.F; i += PT) w.eW[g][i] = a.eW[g][i];
+      for (int i = threadIdx.x; i < 2 * a.F; i += PT) w.em[g][i] = a.em[g][i];
     }
   }
 }
@@ -262,6 +290,69 @@ __device__ __forceinline__ void node_gate_fwd(const Args& a, const List& fw, con
   __syncthreads();
 }
 
+// ---- edge gates: one-head graph attention over the pattern of S' = S + I, all in shared memory -------------------------------
+struct Att {                                     // row i: edges p in [rptr[i], rptr[i+1]) -> column col[p], value val[p];
+  const int* rptr; const int* cptr;              // column j: entries q in [cptr[j], cptr[j+1]) -> row crow[q], edge id ceid[q]
+  const float* val; const unsigned short *col, *crow, *ceid, *erow;
+  int nnz;
+};
+__device__ __forceinline__ Att stage_att(unsigned char*& sp, const Args& a) {
+  Att t; t.nnz = a.annz;
+  const int N = a.N, nnz = a.annz;
+  int* rp = reinterpret_cast<int*>(sp); sp += ((N + 1) * 4 + 15) & ~15;
+  int* cp = reinterpret_cast<int*>(sp); sp += ((N + 1) * 4 + 15) & ~15;
+  float* v = reinterpret_cast<float*>(sp); sp += (nnz * 4 + 15) & ~15;
+  unsigned short* h[4];
+  for (int i = 0; i < 4; ++i) { h[i] = reinterpret_cast<unsigned short*>(sp); sp += (nnz * 2 + 15) & ~15; }
+  for (int i = threadIdx.x; i <= N; i += PT) { rp[i] = a.arptr[i]; cp[i] = a.acptr[i]; }
+  for (int i = threadIdx.x; i < nnz; i += PT) {
+    v[i] = a.aval[i]; h[0][i] = (unsigned short)a.acol[i]; h[1][i] = (unsigned short)a.acrow[i]; h[2][i] = (unsigned short)a.aceid[i];
+  }
+  for (int i = threadIdx.x; i < N; i += PT)
+    for (int p = a.arptr[i]; p < a.arptr[i + 1]; ++p) h[3][p] = (unsigned short)i;
+  t.rptr = rp; t.cptr = cp; t.val = v; t.col = h[0]; t.crow = h[1]; t.ceid = h[2]; t.erow = h[3];
+  return t;
+}
+__device__ __forceinline__ float leaky02(float x) { return x > 0.f ? x : 0.2f * x; }     // graphML.py:521 negative_slope
+// out[f][j] = sum_i Wy[f][i] S'_ij al_ij,  Wy = W y,  al = row softmax of leaky(a2.Wy_i + a1.Wy_j)   (graphML.py:586-625; no ReLU here)
+template <int NB>
+__device__ __forceinline__ void gat_fwd(int N, int F, const Att& t, const float* W, const float* mix, const float* y,
+                                        float* Wy, float* rr, float* cc, float* al, float* out) {
+  const int NQ = N / NB;
+  for (int e = threadIdx.x; e < F * NQ; e += PT) {
+    const int f = e / NQ, n0 = (e - f * NQ) * NB;
+    float v[NB];
+    contract<NB>(W, y, f, n0, F, N, v);
+#pragma unroll
+    for (int j = 0; j < NB; ++j) Wy[f * N + n0 + j] = v[j];
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < 2 * N; e += PT) {
+    const int h = e / N, n = e - h * N;
+    float s0 = 0.f;
+    for (int f = 0; f < F; ++f) s0 = fmaf(mix[h * F + f], Wy[f * N + n], s0);
+    (h ? cc : rr)[n] = s0;                                         // mixer[:F] pairs with the column node j, mixer[F:] with the row node i
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < N; i += PT) {
+    const int p0 = t.rptr[i], p1 = t.rptr[i + 1];
+    float m = -INFINITY;
+    for (int p = p0; p < p1; ++p) m = fmaxf(m, leaky02(cc[i] + rr[t.col[p]]));
+    float den = 0.f;
+    for (int p = p0; p < p1; ++p) { const float e = expf(leaky02(cc[i] + rr[t.col[p]]) - m); al[p] = e; den += e; }
+    const float inv = 1.f / den;
+    for (int p = p0; p < p1; ++p) al[p] *= inv;
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < F * N; o += PT) {
+    const int f = o / N, j = o - f * N;
+    float s0 = 0.f;
+    for (int q = t.cptr[j]; q < t.cptr[j + 1]; ++q) { const int e = t.ceid[q]; s0 = fmaf(Wy[f * N + t.crow[q]], t.val[e] * al[e], s0); }
+    out[o] = s0;
+  }
+  __syncthreads();
+}
+
 template <int NB>
 __global__ void __launch_bounds__(PT, 1) persist_fwd_k(const Args a) {
   extern __shared__ __align__(16) float psm[];
@@ -278,9 +369,19 @@ __global__ void __launch_bounds__(PT, 1) persist_fwd_k(const Args a) {
   float* sbuf = p; p += a.node ? FN : 0;
   float* pk = p; p += a.node ? a.Kst * N : 0;
   float* qs = p; p += a.node ? 2 * N : 0;
+  float* ya = p; p += a.edge ? FN : 0;
+  float* yr = p; p += a.edge ? FN : 0;
+  float* Wy = p; p += a.edge ? FN : 0;
+  float* oa = p; p += a.edge ? FN : 0;
+  float* orr = p; p += a.edge ? FN : 0;
+  float* rr = p; p += a.edge ? N : 0;
+  float* cc = p; p += a.edge ? N : 0;
+  float* al = p; p += a.edge ? ((a.annz + 3) & ~3) : 0;
   float* red = p; p += 64;
   unsigned char* sp = reinterpret_cast<unsigned char*>(p);
   const List fw = stage_list(sp, a.cptr, a.cidx, a.cval, N, a.nnz, a.lists_smem != 0);
+  Att att{};
+  if (a.edge) att = stage_att(sp, a);
   load_weights(w, a);
   for (int e = threadIdx.x; e < FN; e += PT) zh[e] = a.h0[b * FN + e];
   __syncthreads();
@@ -333,6 +434,11 @@ __global__ void __launch_bounds__(PT, 1) persist_fwd_k(const Args a) {
       contract<NB>(w.A, zx, f, n0, KCa, N, av);
       contract<NB>(w.Bw, zh, f, n0, KCb, N, rv);
       const float bb = w.bias[f];                                  // the same bias in both filters (:2405-2407)
+      if (a.edge) {
+#pragma unroll
+        for (int j = 0; j < NB; ++j) { ya[f * N + n0 + j] = av[j] + bb; yr[f * N + n0 + j] = rv[j] + bb; }
+        continue;
+      }
 #pragma unroll
       for (int j = 0; j < NB; ++j) {
         const float wi = a.node ? gi * qs[n0 + j] : gi, wf = a.node ? gf * qs[N + n0 + j] : gf;
@@ -342,6 +448,16 @@ __global__ void __launch_bounds__(PT, 1) persist_fwd_k(const Args a) {
       }
     }
     __syncthreads();
+    if (a.edge) {                                                  // :2409-2416: both filter outputs through their attention layer
+      gat_fwd<NB>(N, F, att, w.eW[0], w.em[0], ya, Wy, rr, cc, al, oa);
+      gat_fwd<NB>(N, F, att, w.eW[1], w.em[1], yr, Wy, rr, cc, al, orr);
+      for (int o = threadIdx.x; o < FN; o += PT) {
+        const float h = tanhf(fmaf(gi, fmaxf(oa[o], 0.f), gf * fmaxf(orr[o], 0.f)));
+        Ht[o] = h;
+        hn[o] = h;
+      }
+      __syncthreads();
+    }
     for (int e = threadIdx.x; e < FN; e += PT) zh[e] = hn[e];
     __syncthreads();
   }
@@ -437,6 +553,64 @@ __device__ __forceinline__ void flush_sub(const Sub& g, float* dA, float* dB, fl
   for (int i = threadIdx.x; i < F; i += PT) if (db) atomicAdd(db + i, g.b[i]);
 }
 
+// reverse of gat_fwd for one gate.  In: y (the filter output), Wy / rr / cc / al as gat_fwd left them, dy = d loss / d out (ReLU mask
+// and gate scalar applied).  Out: dyin = d loss / d y; gW [F][F] and gmix [2F] accumulate.  tmp: [nnz], drr / dcc: [N], dWy: [F][N].
+template <int NB>
+__device__ __forceinline__ void gat_bwd(int N, int F, const Att& t, const float* W, const float* mix, float* gW, float* gmix,
+                                        const float* y, const float* Wy, const float* dy, float* dWy, const float* rr, const float* cc,
+                                        float* drr, float* dcc, const float* al, float* tmp, float* dyin) {
+  for (int e = threadIdx.x; e < t.nnz; e += PT) {                  // d al_ij = S'_ij <Wy_i, dy_j>
+    const int i = t.erow[e], j = t.col[e];
+    float s0 = 0.f;
+    for (int f = 0; f < F; ++f) s0 = fmaf(Wy[f * N + i], dy[f * N + j], s0);
+    tmp[e] = t.val[e] * s0;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < N; i += PT) {                      // softmax and leaky_relu backward, row sums
+    const int p0 = t.rptr[i], p1 = t.rptr[i + 1];
+    float sd = 0.f;
+    for (int p = p0; p < p1; ++p) sd = fmaf(al[p], tmp[p], sd);
+    float acc = 0.f;
+    for (int p = p0; p < p1; ++p) {
+      float ds = al[p] * (tmp[p] - sd);
+      ds *= (cc[i] + rr[t.col[p]] > 0.f) ? 1.f : 0.2f;
+      tmp[p] = ds; acc += ds;
+    }
+    dcc[i] = acc;
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < N; j += PT) {                      // column sums
+    float acc = 0.f;
+    for (int q = t.cptr[j]; q < t.cptr[j + 1]; ++q) acc += tmp[t.ceid[q]];
+    drr[j] = acc;
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < F * N; o += PT) {                  // d Wy
+    const int f = o / N, i = o - f * N;
+    float s0 = fmaf(mix[f], drr[i], mix[F + f] * dcc[i]);
+    for (int p = t.rptr[i]; p < t.rptr[i + 1]; ++p) s0 = fmaf(t.val[p] * al[p], dy[f * N + t.col[p]], s0);
+    dWy[o] = s0;
+  }
+  for (int h = threadIdx.x; h < 2 * F; h += PT) {                  // d mixer
+    const float* dv = h < F ? drr : dcc;
+    const int f = h < F ? h : h - F;
+    float s0 = 0.f;
+    for (int n = 0; n < N; ++n) s0 = fmaf(dv[n], Wy[f * N + n], s0);
+    gmix[h] += s0;
+  }
+  __syncthreads();
+  wgrad_acc<NB>(gW, dWy, y, F, F, N);                              // d W[f][g] += sum_n dWy[f][n] y[g][n]
+  for (int o = threadIdx.x; o < F * N; o += PT) {                  // d y[g][n] = sum_f W[f][g] dWy[f][n]
+    const int g = o / N, n = o - g * N;
+    float s0 = 0.f, s1 = 0.f;
+    int f = 0;
+    for (; f + 1 < F; f += 2) { s0 = fmaf(W[f * F + g], dWy[f * N + n], s0); s1 = fmaf(W[(f + 1) * F + g], dWy[(f + 1) * N + n], s1); }
+    if (f < F) s0 = fmaf(W[f * F + g], dWy[f * N + n], s0);
+    dyin[o] = s0 + s1;
+  }
+  __syncthreads();
+}
+
 template <int NB>
 __global__ void __launch_bounds__(PT, 1) persist_bwd_k(const Args a) {
   extern __shared__ __align__(16) float psm[];
@@ -463,10 +637,24 @@ __global__ void __launch_bounds__(PT, 1) persist_bwd_k(const Args a) {
   float* vch = p; p += a.node ? a.Kst * N : 0;
   float* qs = p; p += a.node ? 2 * N : 0;
   float* dq = p; p += a.node ? 2 * N : 0;
+  float* ya = p; p += a.edge ? FN : 0;
+  float* yr = p; p += a.edge ? FN : 0;
+  float* dpb = p; p += a.edge ? FN : 0;
+  float* Wy = p; p += a.edge ? FN : 0;
+  float* og = p; p += a.edge ? FN : 0;                             // a gate's attention output, then its gradient dy in place
+  float* dWy = p; p += a.edge ? FN : 0;
+  float* rr = p; p += a.edge ? N : 0;
+  float* cc = p; p += a.edge ? N : 0;
+  float* drr = p; p += a.edge ? N : 0;
+  float* dcc = p; p += a.edge ? N : 0;
+  float* al = p; p += a.edge ? ((a.annz + 3) & ~3) : 0;
+  float* etmp = p; p += a.edge ? ((a.annz + 3) & ~3) : 0;
   float* red = p; p += 64;
   unsigned char* sp = reinterpret_cast<unsigned char*>(p);
   const List fw = stage_list(sp, a.cptr, a.cidx, a.cval, N, a.nnz, a.lists_smem != 0);
   const List bw = stage_list(sp, a.rptr, a.ridx, a.rval, N, a.nnz, a.lists_smem != 0);
+  Att att{};
+  if (a.edge) att = stage_att(sp, a);
   load_weights(w, a);
   for (float* q = gacc.A; q < zx; q += PT) { if (q + threadIdx.x < zx) q[threadIdx.x] = 0.f; }      // zero every accumulator
   for (int e = threadIdx.x; e < FN; e += PT) {
@@ -519,11 +707,30 @@ __global__ void __launch_bounds__(PT, 1) persist_bwd_k(const Args a) {
         const int n = n0 + j, o = f * N + n;
         const float h = Ht[o];
         const float dp = ((has_dH ? dHt[o] : 0.f) + dh[o]) * (1.f - h * h);
+        if (a.edge) { ya[o] = av[j] + bb; yr[o] = rv[j] + bb; dpb[o] = dp; continue; }
         const float qi = a.node ? qs[n] : 1.f, qf = a.node ? qs[N + n] : 1.f;
         const float ta = dp * (av[j] + bb), tr = dp * (rv[j] + bb);      // d pre / d (g_i q_i), d pre / d (g_f q_f)
         sgi = fmaf(ta, qi, sgi); sgf = fmaf(tr, qf, sgf);
         if (a.node) { atomicAdd(dq + n, gi * ta); atomicAdd(dq + N + n, gf * tr); }
         da[o] = gi * qi * dp; dr[o] = gf * qf * dp;
+      }
+    }
+    if (a.edge) {                                                  // recompute each attention layer, then its reverse
+      __syncthreads();
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        const float* y = g == 0 ? ya : yr;
+        gat_fwd<NB>(N, F, att, w.eW[g], w.em[g], y, Wy, rr, cc, al, og);
+        const float gs = g == 0 ? gi : gf;
+        float sg = 0.f;
+        for (int o = threadIdx.x; o < FN; o += PT) {
+          const float ov = og[o], dp = dpb[o];
+          sg = fmaf(dp, fmaxf(ov, 0.f), sg);                       // d pre / d (time gate scalar)
+          og[o] = ov > 0.f ? gs * dp : 0.f;
+        }
+        if (g == 0) sgi = sg; else sgf = sg;
+        __syncthreads();
+        gat_bwd<NB>(N, F, att, w.eW[g], w.em[g], gacc.eW[g], gacc.em[g], y, Wy, og, dWy, rr, cc, drr, dcc, al, etmp, g == 0 ? da : dr);
       }
     }
     float dgi = 0.f, dgf = 0.f;
@@ -626,6 +833,10 @@ __global__ void __launch_bounds__(PT, 1) persist_bwd_k(const Args a) {
       flush_sub(gacc.ts[g], a.dtA[g], a.dtB[g], a.dtb[g], nA, nB, F);
       for (int i = threadIdx.x; i < FN; i += PT) if (a.dtW[g]) atomicAdd(a.dtW[g] + i, gacc.tW[g][i]);
       if (threadIdx.x == 0 && a.dtc[g]) atomicAdd(a.dtc[g], dtc[g]);
+    }
+    if (a.edge) {
+      for (int i = threadIdx.x; i < F * F; i += PT) if (a.deW[g]) atomicAdd(a.deW[g] + i, gacc.eW[g][i]);
+      for (int i = threadIdx.x; i < 2 * F; i += PT) if (a.dem[g]) atomicAdd(a.dem[g] + i, gacc.em[g][i]);
     }
     if (a.node) {
       flush_sub(gacc.ns[g], a.dnA[g], a.dnB[g], a.dnb[g], nA, nB, F);

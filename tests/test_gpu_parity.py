@@ -208,11 +208,11 @@ def _last_path(cell):
     return h.get_option('last_path')
 
 
-@pytest.mark.parametrize('name', [n for n in G.names('cell_') if not n.endswith('_edge')])
+@pytest.mark.parametrize('name', G.names('cell_'))
 def test_persistent_path_golden(name):
     """The reference's own outputs and gradients (fixtures generated from the unmodified reference) on the persistent path:
-    X does not require grad here (as in the reference's training loops), so the library picks it for ungated, time-gated and
-    node-gated cells with one edge feature."""
+    X does not require grad here (as in the reference's training loops), so the library picks it for every gating mode (none,
+    time, node, edge, time + node / edge) with one edge feature."""
     c = G.load(name)
     m = G.cell_meta(c)
     if m['E'] != 1:
@@ -236,7 +236,7 @@ def test_persistent_path_golden(name):
     assert not bad, f'{name}: {bad}'
 
 
-@pytest.mark.parametrize('tg,sg', [(False, None), (True, None), (False, 'node'), (True, 'node')])
+@pytest.mark.parametrize('tg,sg', [(False, None), (True, None), (False, 'node'), (True, 'node'), (False, 'edge'), (True, 'edge')])
 @pytest.mark.parametrize('N,G_,F_,Kin,Kst,T,B,bias', [(37, 3, 6, 4, 3, 6, 5, True), (80, 1, 20, 5, 5, 5, 7, True), (59, 2, 8, 1, 4, 3, 4, False),
                                                      (16, 1, 4, 2, 1, 2, 3, True)])
 def test_persistent_path_matches_per_op_kernels(tg, sg, N, G_, F_, Kin, Kst, T, B, bias):
