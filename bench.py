@@ -470,7 +470,7 @@ def run_ours(args):
         gc.collect()
         torch.cuda.empty_cache()
         secondary = {}
-        for wl, st_, wu_ in (('cfg5', 10, 2), ('cfg1', 20, 5)):
+        for wl, st_, wu_ in (('cfg5', 10, 2), ('cfg1', 20, 5), ('cfg2-node', 20, 5), ('cfg2-edge', 20, 5)):
             a2 = copy.copy(args)
             a2.workload, a2.steps, a2.warmup, a2.no_cpu_baseline, a2.batch = wl, st_, wu_, True, CFG3['B']
             try:
@@ -837,7 +837,7 @@ def main():
                     help='library-owned node renumbering of the fused sparse path (graph option "reorder")')
     ap.add_argument('--cfg5-order', default='hilbert', choices=['hilbert', 'random', 'host'],
                     help='cfg5 graph: built on the GPU with library-owned Hilbert renumbering (default), on the GPU in the random input order, or by the host generator')
-    ap.add_argument('--no-secondary', action='store_true', help='N = 1: skip the cfg5 / cfg1 secondary measurements in the same line')
+    ap.add_argument('--no-secondary', action='store_true', help='N = 1: skip the cfg5 / cfg1 / cfg2 secondary measurements in the same line')
     ap.add_argument('--no-whole-step', action='store_true', help='small workloads: skip the whole-training-step CUDA-graph leg')
     ap.add_argument('--native-allreduce', type=int, default=0, help='N > 1: 1 = the library\'s own NCCL transport (gcrnn_allreduce_sum)')
     ap.add_argument('--cpu-batch', type=int, default=16)

@@ -17,7 +17,7 @@ PREC_FP32, PREC_BF16_TC, PREC_BF16X2_TC = 0, 1, 2
 
 # every symbol include/gcrnn_b200.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
-    'gcrnn_abi_version', 'gcrnn_last_error', 'gcrnn_debug_launch_count', 'gcrnn_debug_shift_gemm',
+    'gcrnn_abi_version', 'gcrnn_last_error', 'gcrnn_debug_launch_count', 'gcrnn_debug_shift_gemm', 'gcrnn_debug_edge_relu_masks',
     'gcrnn_graph_set_option', 'gcrnn_graph_get_option',
     'gcrnn_graph_create_csr', 'gcrnn_graph_create_dense', 'gcrnn_graph_destroy', 'gcrnn_graph_info',
     'gcrnn_lsigf_workspace_bytes', 'gcrnn_lsigf_forward', 'gcrnn_lsigf_backward',
@@ -68,6 +68,7 @@ def lib():
     L.gcrnn_abi_version.restype = C.c_int
     L.gcrnn_last_error.restype = C.c_char_p
     L.gcrnn_debug_launch_count.restype = C.c_uint64
+    L.gcrnn_debug_edge_relu_masks.argtypes = [_P, _P, C.c_size_t, C.c_int64, C.c_int64, _P, _P]
     L.gcrnn_debug_shift_gemm.argtypes = [_P, C.c_int32, _P, C.c_int64, C.c_int32, _P, C.c_int32, _P, _P]
     L.gcrnn_graph_set_option.argtypes = [_P, C.c_char_p, C.c_int32]
     L.gcrnn_graph_get_option.argtypes = [_P, C.c_char_p, C.POINTER(C.c_int32)]

@@ -158,6 +158,13 @@ int gcrnn_graph_set_option(gcrnn_graph* g, const char* name, int32_t value) {
   *f = value; ++g->opt.epoch;
   API_END
 }
+int gcrnn_debug_edge_relu_masks(const gcrnn_cell* cell, const void* saved, size_t saved_bytes, int64_t B, int64_t T, uint8_t* out, void* stream) {
+  API_BEGIN
+  GCRNN_CHECK(cell && saved && out, "null argument");
+  DeviceScope dev(cell->g->device);
+  debug_edge_relu_masks(cell, saved, saved_bytes, B, T, out, (cudaStream_t)stream);
+  API_END
+}
 int gcrnn_graph_get_option(const gcrnn_graph* g, const char* name, int32_t* value) {
   API_BEGIN
   GCRNN_CHECK(g && name && value, "null argument");

@@ -181,6 +181,9 @@ size_t cell_backward_f32(const gcrnn_cell* c, const gcrnn_cell_params* p, const 
                          const gcrnn_cell_params* gr, float* dX, float* dh0, void* ws, size_t wsb, int64_t B,
                          int64_t T, cudaStream_t st);
 
+// test aid (gcrnn_debug_edge_relu_masks)
+void debug_edge_relu_masks(const gcrnn_cell* cell, const void* saved, size_t savedb, int64_t B, int64_t T, unsigned char* out, cudaStream_t st);
+
 // tensor-core path (gcrnn_tc.cu)
 size_t cell_forward_tc(const gcrnn_cell* c, const gcrnn_cell_params* p, const float* X, const float* h0, float* H,
                        void* saved, size_t savedb, size_t* saved_used, void* ws, size_t wsb, int64_t B, int64_t T,

@@ -709,12 +709,38 @@ size_t cell_backward_e32(const gcrnn_cell* cell, const gcrnn_cell_params* p, con
   return a.off;
 }
 
+// test aid: the ReLU decisions the fused forward saved, in the caller's layout and node order, out[gate][b][t][f][n] (1 = passed)
+__global__ void e32_decode_masks_k(const uint2* __restrict__ masks, const int* __restrict__ perm, unsigned char* __restrict__ out,
+                                   int N, long long B, long long T) {
+  const long long total = T * B * N;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(i % N);
+    const long long tb = i / N, b = tb % B, t = tb / B;
+    const uint2 mk = masks[i];
+    const int no = perm ? perm[n] : n;
+    for (int f = 0; f < 32; ++f) {
+      const int bit = e32::lane_of_feat(f);
+      out[(((0 * B + b) * T + t) * 32 + f) * N + no] = (mk.x >> bit) & 1u;
+      out[(((1 * B + b) * T + t) * 32 + f) * N + no] = (mk.y >> bit) & 1u;
+    }
+  }
+}
 }  // namespace
 
+void debug_edge_relu_masks(const gcrnn_cell* cell, const void* saved, size_t savedb, int64_t B, int64_t T, unsigned char* out, cudaStream_t st) {
+  GCRNN_CHECK(cell->last_path == GCRNN_PATH_NODE32, "the last forward of this cell did not take the fused edge-gated path");
+  const CellDims d = dims_of(cell, B, T);
+  Saved s; Saved32 x;
+  { Arena sa(const_cast<void*>(saved), savedb); s.layout(sa, d); x.layout(sa, d); }
+  const gcrnn_graph* view = locality_view(cell->g);
+  e32_decode_masks_k<<<grid1d(d.TB * d.N, 256), 256, 0, st>>>(x.masks, view != cell->g ? cell->g->perm : nullptr, out, d.N, B, T);
+  check_launch();
+}
+
+namespace {
 // ===================================================================================================
 // persistent fused recurrence for small graphs (persist_f32.cuh): one launch forward, one launch backward
 // ===================================================================================================
-namespace {
 constexpr long long PERSIST_SMEM_MAX = 220 * 1024;
 persist::Shape persist_shape(const gcrnn_cell* cell) {
   const gcrnn_cell_desc& d = cell->d;
@@ -757,6 +783,30 @@ persist::Args persist_args(const gcrnn_cell* cell, const gcrnn_cell_params* p, i
   }
   return a;
 }
+// kernel variants: NB = 4 (blocked loops with 16-byte loads, needs N % 4 == 0 and F % 4 == 0) or 1; spatial gating none / node / edge
+template <int NB, int SG>
+void persist_launch_v(bool bwd, const persist::Args& a, unsigned B, size_t smem, cudaStream_t st) {
+  static DeviceOnce once;
+  if (once.first()) {
+    CUDA_OK(cudaFuncSetAttribute(persist::persist_fwd_k<NB, SG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_OK(cudaFuncSetAttribute(persist::persist_bwd_k<NB, SG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  }
+  if (bwd) persist::persist_bwd_k<NB, SG><<<B, persist::PT, smem, st>>>(a);
+  else persist::persist_fwd_k<NB, SG><<<B, persist::PT, smem, st>>>(a);
+  check_launch();
+}
+void persist_launch(bool bwd, const persist::Args& a, unsigned B, size_t smem, cudaStream_t st) {
+  const bool nb4 = a.N % 4 == 0 && a.F % 4 == 0;
+  const int sg = a.node ? 1 : a.edge ? 2 : 0;
+  switch (sg * 2 + (nb4 ? 1 : 0)) {
+    case 0: persist_launch_v<1, 0>(bwd, a, B, smem, st); break;
+    case 1: persist_launch_v<4, 0>(bwd, a, B, smem, st); break;
+    case 2: persist_launch_v<1, 1>(bwd, a, B, smem, st); break;
+    case 3: persist_launch_v<4, 1>(bwd, a, B, smem, st); break;
+    case 4: persist_launch_v<1, 2>(bwd, a, B, smem, st); break;
+    default: persist_launch_v<4, 2>(bwd, a, B, smem, st); break;
+  }
+}
 size_t cell_forward_persist(const gcrnn_cell* cell, const gcrnn_cell_params* p, const float* X, const float* h0, float* H,
                             void* saved, size_t savedb, size_t* saved_used, void* ws, int64_t B, int64_t T, cudaStream_t st) {
   Arena sa(saved, savedb);
@@ -768,14 +818,7 @@ size_t cell_forward_persist(const gcrnn_cell* cell, const gcrnn_cell_params* p, 
   persist::Args a = persist_args(cell, p, B, T);
   a.X = X; a.h0 = h0; a.H = H; a.gt = gt; a.qn = qn;
   const size_t smem = (size_t)persist::fwd_floats(persist_shape(cell)) * sizeof(float) + persist_fixed_bytes(cell) + (a.lists_smem ? persist::list_bytes(a.N, a.nnz) : 0);
-  static DeviceOnce once;
-  if (once.first()) {
-    CUDA_OK(cudaFuncSetAttribute(persist::persist_fwd_k<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CUDA_OK(cudaFuncSetAttribute(persist::persist_fwd_k<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  }
-  if (a.N % 4 == 0 && a.F % 4 == 0) persist::persist_fwd_k<4><<<(unsigned)B, persist::PT, smem, st>>>(a);      // blocked loops, 16-byte loads
-  else persist::persist_fwd_k<1><<<(unsigned)B, persist::PT, smem, st>>>(a);
-  check_launch();
+  persist_launch(false, a, (unsigned)B, smem, st);
   return 256;
 }
 size_t cell_backward_persist(const gcrnn_cell* cell, const gcrnn_cell_params* p, const float* X, const float* h0, const float* H,
@@ -798,14 +841,7 @@ size_t cell_backward_persist(const gcrnn_cell* cell, const gcrnn_cell_params* p,
   }
   a.dh0 = dh0;
   const size_t smem = (size_t)persist::bwd_floats(persist_shape(cell)) * sizeof(float) + persist_fixed_bytes(cell) + (a.lists_smem ? 2 * persist::list_bytes(a.N, a.nnz) : 0);
-  static DeviceOnce once;
-  if (once.first()) {
-    CUDA_OK(cudaFuncSetAttribute(persist::persist_bwd_k<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CUDA_OK(cudaFuncSetAttribute(persist::persist_bwd_k<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  }
-  if (a.N % 4 == 0 && a.F % 4 == 0) persist::persist_bwd_k<4><<<(unsigned)B, persist::PT, smem, st>>>(a);
-  else persist::persist_bwd_k<1><<<(unsigned)B, persist::PT, smem, st>>>(a);
-  check_launch();
+  persist_launch(true, a, (unsigned)B, smem, st);
   return 256;
 }
 

@@ -353,8 +353,9 @@ __device__ __forceinline__ void gat_fwd(int N, int F, const Att& t, const float*
   __syncthreads();
 }
 
-template <int NB>
+template <int NB, int SG>      // SG: spatial gating 0 none, 1 node, 2 edge (compile-time so that the other modes cost nothing)
 __global__ void __launch_bounds__(PT, 1) persist_fwd_k(const Args a) {
+  constexpr bool NODE = SG == 1, EDGE = SG == 2;
   extern __shared__ __align__(16) float psm[];
   const int N = a.N, F = a.F, FN = F * N, GN = a.G * N, NQ = N / NB;
   const int KCa = a.Kin * a.G, KCb = a.Kst * F;
@@ -365,33 +366,33 @@ __global__ void __launch_bounds__(PT, 1) persist_fwd_k(const Args a) {
   float* zh = p; p += (size_t)a.Kst * FN;
   float* hn = p; p += FN;
   float* c0 = p; p += a.tg ? 2 * FN : 0;
-  float* c0n = p; p += a.node ? 2 * FN : 0;
-  float* sbuf = p; p += a.node ? FN : 0;
-  float* pk = p; p += a.node ? a.Kst * N : 0;
-  float* qs = p; p += a.node ? 2 * N : 0;
-  float* ya = p; p += a.edge ? FN : 0;
-  float* yr = p; p += a.edge ? FN : 0;
-  float* Wy = p; p += a.edge ? FN : 0;
-  float* oa = p; p += a.edge ? FN : 0;
-  float* orr = p; p += a.edge ? FN : 0;
-  float* rr = p; p += a.edge ? N : 0;
-  float* cc = p; p += a.edge ? N : 0;
-  float* al = p; p += a.edge ? ((a.annz + 3) & ~3) : 0;
+  float* c0n = p; p += NODE ? 2 * FN : 0;
+  float* sbuf = p; p += NODE ? FN : 0;
+  float* pk = p; p += NODE ? a.Kst * N : 0;
+  float* qs = p; p += NODE ? 2 * N : 0;
+  float* ya = p; p += EDGE ? FN : 0;
+  float* yr = p; p += EDGE ? FN : 0;
+  float* Wy = p; p += EDGE ? FN : 0;
+  float* oa = p; p += EDGE ? FN : 0;
+  float* orr = p; p += EDGE ? FN : 0;
+  float* rr = p; p += EDGE ? N : 0;
+  float* cc = p; p += EDGE ? N : 0;
+  float* al = p; p += EDGE ? ((a.annz + 3) & ~3) : 0;
   float* red = p; p += 64;
   unsigned char* sp = reinterpret_cast<unsigned char*>(p);
   const List fw = stage_list(sp, a.cptr, a.cidx, a.cval, N, a.nnz, a.lists_smem != 0);
   Att att{};
-  if (a.edge) att = stage_att(sp, a);
+  if (EDGE) att = stage_att(sp, a);
   load_weights(w, a);
   for (int e = threadIdx.x; e < FN; e += PT) zh[e] = a.h0[b * FN + e];
   __syncthreads();
-  const bool gated = a.tg || a.node;
+  const bool gated = a.tg || NODE;
   if (gated) {                                                    // T-invariant gate terms: B_s(S) h0 + 2 b_s   (graphML.py:2362, :2383, :2417-2423)
     chain(fw, zh, a.Kst, F, N);
 #pragma unroll
     for (int g = 0; g < 2; ++g) {
       if (a.tg) subcell_c0<NB>(w.ts[g], zh, c0 + g * FN, F, KCb, N);
-      if (a.node) subcell_c0<NB>(w.ns[g], zh, c0n + g * FN, F, KCb, N);
+      if (NODE) subcell_c0<NB>(w.ns[g], zh, c0n + g * FN, F, KCb, N);
     }
     __syncthreads();
   }
@@ -418,7 +419,7 @@ __global__ void __launch_bounds__(PT, 1) persist_fwd_k(const Args a) {
         if (threadIdx.x == 0) a.gt[((long long)g * a.B + b) * a.T + t] = gv;
       }
     }
-    if (a.node) {
+    if (NODE) {
 #pragma unroll
       for (int g = 0; g < 2; ++g) {
         node_gate_fwd<NB>(a, fw, w.ns[g], w.nh[g], a.has_bias ? __ldg(a.nhb[g]) : 0.f, zx, c0n + g * FN, sbuf, pk, qs + g * N);
@@ -434,21 +435,21 @@ __global__ void __launch_bounds__(PT, 1) persist_fwd_k(const Args a) {
       contract<NB>(w.A, zx, f, n0, KCa, N, av);
       contract<NB>(w.Bw, zh, f, n0, KCb, N, rv);
       const float bb = w.bias[f];                                  // the same bias in both filters (:2405-2407)
-      if (a.edge) {
+      if constexpr (EDGE) {
 #pragma unroll
         for (int j = 0; j < NB; ++j) { ya[f * N + n0 + j] = av[j] + bb; yr[f * N + n0 + j] = rv[j] + bb; }
-        continue;
-      }
+      } else {
 #pragma unroll
-      for (int j = 0; j < NB; ++j) {
-        const float wi = a.node ? gi * qs[n0 + j] : gi, wf = a.node ? gf * qs[N + n0 + j] : gf;
-        const float h = tanhf(fmaf(wi, av[j] + bb, wf * (rv[j] + bb)));
-        Ht[f * N + n0 + j] = h;
-        hn[f * N + n0 + j] = h;
+        for (int j = 0; j < NB; ++j) {
+          const float wi = NODE ? gi * qs[n0 + j] : gi, wf = NODE ? gf * qs[N + n0 + j] : gf;
+          const float h = tanhf(fmaf(wi, av[j] + bb, wf * (rv[j] + bb)));
+          Ht[f * N + n0 + j] = h;
+          hn[f * N + n0 + j] = h;
+        }
       }
     }
     __syncthreads();
-    if (a.edge) {                                                  // :2409-2416: both filter outputs through their attention layer
+    if (EDGE) {                                                  // :2409-2416: both filter outputs through their attention layer
       gat_fwd<NB>(N, F, att, w.eW[0], w.em[0], ya, Wy, rr, cc, al, oa);
       gat_fwd<NB>(N, F, att, w.eW[1], w.em[1], yr, Wy, rr, cc, al, orr);
       for (int o = threadIdx.x; o < FN; o += PT) {
@@ -611,8 +612,9 @@ __device__ __forceinline__ void gat_bwd(int N, int F, const Att& t, const float*
   __syncthreads();
 }
 
-template <int NB>
+template <int NB, int SG>      // SG: spatial gating 0 none, 1 node, 2 edge (compile-time so that the other modes cost nothing)
 __global__ void __launch_bounds__(PT, 1) persist_bwd_k(const Args a) {
+  constexpr bool NODE = SG == 1, EDGE = SG == 2;
   extern __shared__ __align__(16) float psm[];
   const int N = a.N, F = a.F, FN = F * N, GN = a.G * N, NQ = N / NB;
   const int nA = F * a.Kin * a.G, nB = F * a.Kst * F;
@@ -630,41 +632,41 @@ __global__ void __launch_bounds__(PT, 1) persist_bwd_k(const Args a) {
   float* b2 = p; p += FN;
   float* c0 = p; p += a.tg ? 2 * FN : 0;
   float* dc0 = p; p += a.tg ? 2 * FN : 0;
-  float* dpu = p; p += (a.tg || a.node) ? FN : 0;
-  float* c0n = p; p += a.node ? 2 * FN : 0;
-  float* dc0n = p; p += a.node ? 2 * FN : 0;
-  float* sbuf = p; p += a.node ? FN : 0;
-  float* vch = p; p += a.node ? a.Kst * N : 0;
-  float* qs = p; p += a.node ? 2 * N : 0;
-  float* dq = p; p += a.node ? 2 * N : 0;
-  float* ya = p; p += a.edge ? FN : 0;
-  float* yr = p; p += a.edge ? FN : 0;
-  float* dpb = p; p += a.edge ? FN : 0;
-  float* Wy = p; p += a.edge ? FN : 0;
-  float* og = p; p += a.edge ? FN : 0;                             // a gate's attention output, then its gradient dy in place
-  float* dWy = p; p += a.edge ? FN : 0;
-  float* rr = p; p += a.edge ? N : 0;
-  float* cc = p; p += a.edge ? N : 0;
-  float* drr = p; p += a.edge ? N : 0;
-  float* dcc = p; p += a.edge ? N : 0;
-  float* al = p; p += a.edge ? ((a.annz + 3) & ~3) : 0;
-  float* etmp = p; p += a.edge ? ((a.annz + 3) & ~3) : 0;
+  float* dpu = p; p += (a.tg || NODE) ? FN : 0;
+  float* c0n = p; p += NODE ? 2 * FN : 0;
+  float* dc0n = p; p += NODE ? 2 * FN : 0;
+  float* sbuf = p; p += NODE ? FN : 0;
+  float* vch = p; p += NODE ? a.Kst * N : 0;
+  float* qs = p; p += NODE ? 2 * N : 0;
+  float* dq = p; p += NODE ? 2 * N : 0;
+  float* ya = p; p += EDGE ? FN : 0;
+  float* yr = p; p += EDGE ? FN : 0;
+  float* dpb = p; p += EDGE ? FN : 0;
+  float* Wy = p; p += EDGE ? FN : 0;
+  float* og = p; p += EDGE ? FN : 0;                             // a gate's attention output, then its gradient dy in place
+  float* dWy = p; p += EDGE ? FN : 0;
+  float* rr = p; p += EDGE ? N : 0;
+  float* cc = p; p += EDGE ? N : 0;
+  float* drr = p; p += EDGE ? N : 0;
+  float* dcc = p; p += EDGE ? N : 0;
+  float* al = p; p += EDGE ? ((a.annz + 3) & ~3) : 0;
+  float* etmp = p; p += EDGE ? ((a.annz + 3) & ~3) : 0;
   float* red = p; p += 64;
   unsigned char* sp = reinterpret_cast<unsigned char*>(p);
   const List fw = stage_list(sp, a.cptr, a.cidx, a.cval, N, a.nnz, a.lists_smem != 0);
   const List bw = stage_list(sp, a.rptr, a.ridx, a.rval, N, a.nnz, a.lists_smem != 0);
   Att att{};
-  if (a.edge) att = stage_att(sp, a);
+  if (EDGE) att = stage_att(sp, a);
   load_weights(w, a);
   for (float* q = gacc.A; q < zx; q += PT) { if (q + threadIdx.x < zx) q[threadIdx.x] = 0.f; }      // zero every accumulator
   for (int e = threadIdx.x; e < FN; e += PT) {
     dh[e] = 0.f;
     if (a.tg) { dc0[e] = 0.f; dc0[FN + e] = 0.f; }
-    if (a.node) { dc0n[e] = 0.f; dc0n[FN + e] = 0.f; }
+    if (NODE) { dc0n[e] = 0.f; dc0n[FN + e] = 0.f; }
   }
   float dtc[2] = {0.f, 0.f}, dnc[2] = {0.f, 0.f};
   __syncthreads();
-  const bool gated = a.tg || a.node;
+  const bool gated = a.tg || NODE;
   if (gated) {                                                    // c0 of every gate sub-cell (needed to recompute their states)
     for (int e = threadIdx.x; e < FN; e += PT) zh[e] = a.h0[b * FN + e];
     __syncthreads();
@@ -672,7 +674,7 @@ __global__ void __launch_bounds__(PT, 1) persist_bwd_k(const Args a) {
 #pragma unroll
     for (int g = 0; g < 2; ++g) {
       if (a.tg) subcell_c0<NB>(w.ts[g], zh, c0 + g * FN, F, KCb, N);
-      if (a.node) subcell_c0<NB>(w.ns[g], zh, c0n + g * FN, F, KCb, N);
+      if (NODE) subcell_c0<NB>(w.ns[g], zh, c0n + g * FN, F, KCb, N);
     }
     __syncthreads();
   }
@@ -681,7 +683,7 @@ __global__ void __launch_bounds__(PT, 1) persist_bwd_k(const Args a) {
     const float* xt = a.X + (b * a.T + t) * GN;
     for (int e = threadIdx.x; e < FN; e += PT) zh[e] = hprev[e];
     for (int e = threadIdx.x; e < GN; e += PT) zx[e] = xt[e];
-    if (a.node)
+    if (NODE)
       for (int e = threadIdx.x; e < 2 * N; e += PT) {
         const int g = e / N, n = e - g * N;
         qs[e] = a.qn[(((long long)g * a.B + b) * a.T + t) * N + n];
@@ -707,15 +709,15 @@ __global__ void __launch_bounds__(PT, 1) persist_bwd_k(const Args a) {
         const int n = n0 + j, o = f * N + n;
         const float h = Ht[o];
         const float dp = ((has_dH ? dHt[o] : 0.f) + dh[o]) * (1.f - h * h);
-        if (a.edge) { ya[o] = av[j] + bb; yr[o] = rv[j] + bb; dpb[o] = dp; continue; }
-        const float qi = a.node ? qs[n] : 1.f, qf = a.node ? qs[N + n] : 1.f;
+        if (EDGE) { ya[o] = av[j] + bb; yr[o] = rv[j] + bb; dpb[o] = dp; continue; }
+        const float qi = NODE ? qs[n] : 1.f, qf = NODE ? qs[N + n] : 1.f;
         const float ta = dp * (av[j] + bb), tr = dp * (rv[j] + bb);      // d pre / d (g_i q_i), d pre / d (g_f q_f)
         sgi = fmaf(ta, qi, sgi); sgf = fmaf(tr, qf, sgf);
-        if (a.node) { atomicAdd(dq + n, gi * ta); atomicAdd(dq + N + n, gf * tr); }
+        if (NODE) { atomicAdd(dq + n, gi * ta); atomicAdd(dq + N + n, gf * tr); }
         da[o] = gi * qi * dp; dr[o] = gf * qf * dp;
       }
     }
-    if (a.edge) {                                                  // recompute each attention layer, then its reverse
+    if (EDGE) {                                                  // recompute each attention layer, then its reverse
       __syncthreads();
 #pragma unroll
       for (int g = 0; g < 2; ++g) {
@@ -769,7 +771,7 @@ __global__ void __launch_bounds__(PT, 1) persist_bwd_k(const Args a) {
         __syncthreads();
       }
     }
-    if (a.node) {
+    if (NODE) {
 #pragma unroll
       for (int g = 0; g < 2; ++g) {
         // d lin = dq q (1 - q);  v_k = v_{k-1} S^T (k < Kst) are the gradients of the head's tap outputs p_k
@@ -820,7 +822,7 @@ __global__ void __launch_bounds__(PT, 1) persist_bwd_k(const Args a) {
 #pragma unroll
   for (int g = 0; g < 2; ++g) {
     if (a.tg) subcell_c0_bwd<NB>(a, bw, w.ts[g], gacc.ts[g], dc0 + (size_t)g * FN, zh, b1, b2, dh);
-    if (a.node) subcell_c0_bwd<NB>(a, bw, w.ns[g], gacc.ns[g], dc0n + (size_t)g * FN, zh, b1, b2, dh);
+    if (NODE) subcell_c0_bwd<NB>(a, bw, w.ns[g], gacc.ns[g], dc0n + (size_t)g * FN, zh, b1, b2, dh);
   }
   if (a.dh0) for (int e = threadIdx.x; e < FN; e += PT) a.dh0[b * FN + e] = dh[e];
   // ---- one atomicAdd per parameter and CTA ---------------------------------------------------------------------------------
@@ -834,11 +836,11 @@ __global__ void __launch_bounds__(PT, 1) persist_bwd_k(const Args a) {
       for (int i = threadIdx.x; i < FN; i += PT) if (a.dtW[g]) atomicAdd(a.dtW[g] + i, gacc.tW[g][i]);
       if (threadIdx.x == 0 && a.dtc[g]) atomicAdd(a.dtc[g], dtc[g]);
     }
-    if (a.edge) {
+    if (EDGE) {
       for (int i = threadIdx.x; i < F * F; i += PT) if (a.deW[g]) atomicAdd(a.deW[g] + i, gacc.eW[g][i]);
       for (int i = threadIdx.x; i < 2 * F; i += PT) if (a.dem[g]) atomicAdd(a.dem[g] + i, gacc.em[g][i]);
     }
-    if (a.node) {
+    if (NODE) {
       flush_sub(gacc.ns[g], a.dnA[g], a.dnB[g], a.dnb[g], nA, nB, F);
       for (int i = threadIdx.x; i < a.Kst * F; i += PT) if (a.dnhw[g]) atomicAdd(a.dnhw[g] + i, gacc.nh[g][i]);
       if (threadIdx.x == 0 && a.dnhb[g]) atomicAdd(a.dnhb[g], dnc[g]);

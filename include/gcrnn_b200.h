@@ -78,6 +78,12 @@ uint64_t    gcrnn_debug_launch_count(void);
 int         gcrnn_debug_shift_gemm(const gcrnn_graph* g, int32_t backward, const void* A_bf16, int64_t M, int32_t planes_in,
                                    void* out_bf16, int32_t planes_out, float* out_f32, void* stream);
 
+/* Test aid: the ReLU decisions (1 = passed) of the two attention layers that the last fused edge-gated forward (GCRNN_PATH_NODE32)
+ * left in `saved`, decoded into the caller's layout and node order: out = device uint8 [2 gates][B][T][32][N].  Lets a test evaluate
+ * the fp64 oracle with exactly the one-sided derivatives the GPU picked at the kinks (tests/test_gpu_sparse_fused.py). */
+int         gcrnn_debug_edge_relu_masks(const gcrnn_cell* cell, const void* saved, size_t saved_bytes, int64_t B, int64_t T,
+                                        uint8_t* out, void* stream);
+
 /* Tuning switches for tests and A/B measurements live on the HANDLE (the library keeps no process-wide mutable state):
  * gcrnn_cell_set_option(cell, name, value) / gcrnn_graph_set_option(graph, name, value) with name =
  *   "gemm_pair"     1: CTA-pair cta_group::2 shift GEMM when the shape allows, 0: single-CTA kernel  (cell and graph handles)

@@ -42,6 +42,8 @@ import torch
 
 ZERO_TOL = 1e-9          # graphML.py:42  zeroTolerance
 NEG_SLOPE = 0.2          # graphML.py:521 negative_slope default
+RELU = torch.relu        # the attention layer's nonlinearity (:2101).  A test may swap it for a relu with GIVEN one-sided
+                         # derivatives to show that a deviation comes from the kink and nothing else; never changed otherwise.
 
 GSO = Union[torch.Tensor, Sequence[torch.Tensor]]
 
@@ -154,7 +156,7 @@ def graph_attention(x, mixer, weight, S: GSO):
             al = p / den[:, ei]
             contrib = Wx[:, :, ei] * (ev * al).unsqueeze(1)            # [B,F,nnz]
             yk = yk + torch.zeros(B, Fo, N, dtype=x.dtype).index_add(2, ej, contrib)
-        heads.append(torch.relu(yk))                                   # :2101
+        heads.append(RELU(yk))                                         # :2101
     return torch.cat(heads, 1)                                         # (k, f) order :2105-2107
 
 

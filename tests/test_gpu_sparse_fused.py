@@ -258,6 +258,7 @@ def test_cfg5_generator_vs_sparse_fp64_oracle(N, B, T):
     cell = cell.to(device=DEV, dtype=torch.float32)
     hg = h0.float().to(DEV).requires_grad_(True)
     H = cell(X.float().to(DEV), hg)
+    saved = H.grad_fn.saved_tensors[3]              # the forward's saved state (read before backward frees it)
     (H * dH.float().to(DEV)).sum().backward()
     assert cell._handle(torch.device(DEV)).get_option('last_path') == PATH_NODE32
     errs = {'H': relerr(H, Href)}
@@ -278,3 +279,34 @@ def test_cfg5_generator_vs_sparse_fp64_oracle(N, B, T):
     assert frac_bad < (1e-9 if N <= 2000 else 1e-3), errs
     bad = {k: v for k, v in errs.items() if k not in ('H', 'dh0_frac_above_tol') and v > tol_g}
     assert not bad, errs
+    if N > 2000:
+        # Proof that the loosened bounds are the kinks and nothing else: the fp64 oracle evaluated with EXACTLY the one-sided ReLU
+        # derivatives the GPU picked (gcrnn_debug_edge_relu_masks decodes them from the forward's saved state).  The forward value
+        # changes only where |y| is at rounding level; every gradient must then meet the un-loosened bounds.
+        masks = torch.empty(2, B, T, F_, N, dtype=torch.uint8, device=DEV)
+        _lib.check(_lib.lib().gcrnn_debug_edge_relu_masks(cell._handle(torch.device(DEV)).ptr, C.c_void_p(saved.data_ptr()), saved.numel(),
+                                                          B, T, C.c_void_p(masks.data_ptr()), None), 'debug_edge_relu_masks')
+        mk = masks.cpu().double()
+        calls = []
+
+        def relu_with_gpu_decisions(y):                 # the oracle evaluates input gate then forget gate, step after step
+            c = len(calls); calls.append(c)
+            m = mk[c % 2, :, c // 2]
+            flips = int(((y.detach() > 0).double() != m).sum())
+            calls[-1] = flips
+            return y * m
+        orc.RELU = relu_with_gpu_decisions
+        try:
+            _, gk = orc.cell_forward_backward(p, [S.double().to_sparse_coo().coalesce()], X, h0, dH, False, 'edge', input_grads=True)
+        finally:
+            orc.RELU = torch.relu
+        assert len(calls) == 2 * T
+        tight = {k: relerr(v.grad, gk[k]) for k, v in cell.named_parameters() if gk[k] is not None}
+        dk = (hg.grad.detach().cpu().double() - gk['__h0']).abs() / gk['__h0'].abs().max()
+        tight['dh0_max'] = float(dk.max())
+        tight['relu_decisions_that_differ_from_fp64'] = int(sum(calls))
+        import json, os
+        os.makedirs('gpurun_out', exist_ok=True)
+        with open('gpurun_out/cfg5_kink_proof.json', 'w') as f:
+            json.dump(dict(N=N, B=B, T=T, gpu_vs_fp64_oracle=errs, gpu_vs_fp64_oracle_with_gpu_relu_decisions=tight), f, indent=1)
+        assert all(v < TOL_GRAD for k, v in tight.items() if k != 'relu_decisions_that_differ_from_fp64'), tight
