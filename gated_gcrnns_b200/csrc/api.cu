@@ -267,7 +267,7 @@ int gcrnn_cell_create(gcrnn_cell** out, const gcrnn_cell_desc* d, const gcrnn_gr
   GCRNN_CHECK(d->spatial_gating >= 0 && d->spatial_gating <= 2, "bad spatial_gating %d", d->spatial_gating);
   if (d->precision == GCRNN_PREC_BF16_TC || d->precision == GCRNN_PREC_BF16X2_TC) {
     GCRNN_CHECK(g->S_bf16 != nullptr, "tensor-core precision needs a graph created with keep_dense != 0");
-    GCRNN_CHECK(d->spatial_gating == GCRNN_SPATIAL_NONE, "tensor-core path supports time gating only; use fp32 for node/edge gating");
+    GCRNN_CHECK(d->spatial_gating != GCRNN_SPATIAL_EDGE, "tensor-core path: time and node gating only; use fp32 for edge gating");
   } else {
     GCRNN_CHECK(d->precision == GCRNN_PREC_FP32, "unknown precision %d", d->precision);
   }

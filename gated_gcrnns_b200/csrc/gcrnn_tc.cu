@@ -5,6 +5,7 @@
 #include "tc_cell.cuh"
 #include "tc_tap.cuh"
 #include "tc_gate.cuh"
+#include "tc_node.cuh"
 #include "tc_bwd.cuh"
 #include "tc_hshift.cuh"
 #include <cstdlib>
@@ -108,15 +109,18 @@ struct TcDims {
   long long LD;          // bf16 row length P * N
   long long B, T, R, RX, BT;
   bool tg, bias;
+  bool node;             // node gates (tc_node.cuh)
 };
 static TcDims tc_dims(const gcrnn_cell* c, int64_t B, int64_t T) {
   TcDims d;
   d.N = c->g->N; d.F = c->d.F; d.G = c->d.G; d.Kin = c->d.Kin; d.Kst = c->d.Kst;
   d.B = B; d.T = T; d.R = B * d.F; d.RX = B * T * d.G; d.BT = B * T;
-  d.tg = c->d.time_gating != 0; d.bias = c->d.bias != 0;
+  d.tg = c->d.time_gating != 0; d.bias = c->d.bias != 0; d.node = c->d.spatial_gating == GCRNN_SPATIAL_NODE;
   d.P = c->d.precision == GCRNN_PREC_BF16X2_TC ? 2 : 1; d.LD = (long long)d.P * d.N;
   GCRNN_CHECK(d.P == 1 || d.N % 256 == 0, "split-bf16 tensor-core path: N %% 256 == 0 (N=%d)", d.N);
-  GCRNN_CHECK(c->d.E == 1 && c->d.spatial_gating == GCRNN_SPATIAL_NONE, "tensor-core path: E == 1, no spatial gating");
+  GCRNN_CHECK(c->d.E == 1 && c->d.spatial_gating != GCRNN_SPATIAL_EDGE, "tensor-core path: E == 1, no edge gating");
+  GCRNN_CHECK(!d.node || (d.Kin * d.G <= NG_KG && d.Kst <= NG_KMAX && d.F % NG_FC == 0 && d.N % 128 == 0),
+              "tensor-core node gates: Kin*G <= %d, Kst <= %d", NG_KG, NG_KMAX);
   GCRNN_CHECK(d.F % 16 == 0 && d.F <= 64, "tensor-core path: F must be a multiple of 16 and <= 64 (F=%d)", d.F);
   GCRNN_CHECK(d.N % 128 == 0, "tensor-core path: N %% 128 == 0 (N=%d)", d.N);
   GCRNN_CHECK(d.Kin * d.G <= 32, "tensor-core path: Kin*G <= 32 (got %d); use the fp32 path", d.Kin * d.G);
@@ -130,10 +134,12 @@ struct TcSaved {
   float* zx;            // [Kin-1][RX][N]   x_t S^k, k >= 1
   float* gt;            // [2][B][T]        time-gate values
   __nv_bfloat16* Hb;    // [T][R][P*N]      bf16 planes of every state (GEMM / wgrad operand)
+  float* qn;            // [2][B][T][N]     node-gate values
   void layout(Arena& a, const TcDims& d) {
     zx = a.get<float>((size_t)(d.Kin - 1) * d.RX * d.N);
     gt = d.tg ? a.get<float>(2 * d.BT) : nullptr;
     Hb = a.get<__nv_bfloat16>((size_t)d.T * d.R * d.LD);
+    qn = d.node ? a.get<float>((size_t)2 * d.BT * d.N) : nullptr;
   }
 };
 
@@ -170,6 +176,7 @@ static void launch_tap(const ContractArgs& ca, const __nv_bfloat16* Wp, int sms,
   t.x0 = ca.x0; t.x0_bstride = ca.x0_bstride; t.zx = ca.zx; t.zx_kstride = ca.zx_kstride; t.zx_bstride = ca.zx_bstride;
   t.hprev = ca.hprev; t.hprev_bstride = ca.hprev_bstride; t.dgf = ca.dgf; t.accumulate = ca.accumulate; t.scaled_chain = ca.scaled_chain;
   t.dHn = ca.dHn; t.dHn_bstride = ca.dHn_bstride; t.gfn = ca.gfn; t.red = ca.red;
+  t.qi = ca.qi; t.qf = ca.qf; t.q_bstride = ca.q_bstride;
   for (int k = 2; k < ca.K; ++k)
     GCRNN_CHECK(ca.slab[k] == ca.slab[1] + (size_t)(k - 1) * t.R * ca.P * ca.N, "tap_gemm: slabs 1..K-1 must be contiguous");
   const long long LD = (long long)ca.P * ca.N;
@@ -391,10 +398,15 @@ size_t cell_forward_tc(const gcrnn_cell* cell, const gcrnn_cell_params* p, const
   __nv_bfloat16* hb0 = a.get<__nv_bfloat16>((size_t)d.R * d.LD);
   __nv_bfloat16* zb = a.get<__nv_bfloat16>((size_t)(d.Kst - 1) * d.R * d.LD);
   __nv_bfloat16* Wb = a.get<__nv_bfloat16>(weight_elems(d.F, d.Kst, P));
-  float* c0 = d.tg ? a.get<float>((size_t)d.R * d.N) : nullptr;
+  float* c0 = (d.tg || d.node) ? a.get<float>((size_t)d.R * d.N) : nullptr;
   float* logit = d.tg ? a.get<float>(2 * d.BT) : nullptr;
+  // node gates: head signals p_k [Kst][B*T][N], Horner accumulator, shift output, bf16 planes of the shift input
+  float* pbuf = d.node ? a.get<float>((size_t)d.Kst * d.BT * d.N) : nullptr;
+  float* rcur = d.node ? a.get<float>((size_t)d.BT * d.N) : nullptr;
+  float* rtmp = d.node ? a.get<float>((size_t)d.BT * d.N) : nullptr;
+  __nv_bfloat16* rb = d.node ? a.get<__nv_bfloat16>((size_t)d.BT * d.LD) : nullptr;
   // Horner-form forward (tc_hshift.cuh): the state filter's tap contraction rides in the shift GEMMs
-  const bool hfused = opt().fwd_fused && d.F == 64 && d.N % 256 == 0 && d.Kin * d.G <= 8 && d.Kst >= 2;
+  const bool hfused = opt().fwd_fused && d.F == 64 && d.N % 256 == 0 && d.Kin * d.G <= 8 && d.Kst >= 2 && !d.node;
   __nv_bfloat16* wping = hfused ? a.get<__nv_bfloat16>((size_t)d.R * d.LD) : nullptr;
   __nv_bfloat16* wpong = hfused ? a.get<__nv_bfloat16>((size_t)d.R * d.LD) : nullptr;
   __nv_bfloat16* Wtaps = hfused ? a.get<__nv_bfloat16>((size_t)d.Kst * 64 * P * 64) : nullptr;     // [K][64][P*64]
@@ -413,8 +425,8 @@ size_t cell_forward_tc(const gcrnn_cell* cell, const gcrnn_cell_params* p, const
   }
   cvt_bf16(h0, hb0, d.R, d.N, P, st);
   // ---- time gates (graphML.py:2357-2374): depend on (x_t, h0) only -> all (b, t) at once ---------------------------
+  if (d.tg || d.node) chain(g, false, hb0, zb, d.Kst, d.R, P, st);      // h0 S^k: the T-invariant term of every gate sub-cell
   if (d.tg) {
-    chain(g, false, hb0, zb, d.Kst, d.R, P, st);
     CUDA_OK(cudaMemsetAsync(logit, 0, 2 * d.BT * sizeof(float), st));
     for (int gi = 0; gi < 2; ++gi) {
       prep_contract_weight(p->t_weight_B[gi], Wb, d.F, d.Kst, 0, P, st);
@@ -427,6 +439,36 @@ size_t cell_forward_tc(const gcrnn_cell* cell, const gcrnn_cell_params* p, const
       gate_launch(false, ga, d, st);
       gate_sigmoid_kernel<<<(unsigned)((d.BT + 255) / 256), 256, 0, st>>>(logit + gi * d.BT, p->t_mlp_b[gi], s.gt + gi * d.BT, d.BT);
       launched();
+    }
+  }
+  // ---- node gates (graphML.py:2379-2407): also functions of (x_t, h0) only -> all (b, t) at once (tc_node.cuh) -------------
+  if (d.node) {
+    const long long n4 = d.BT * (d.N / 4);
+    const unsigned eg = (unsigned)std::min<long long>((n4 + 255) / 256, 148 * 16);
+    for (int gi = 0; gi < 2; ++gi) {
+      prep_contract_weight(p->n_weight_B[gi], Wb, d.F, d.Kst, 0, P, st);
+      ContractArgs ca = contract_base(d, hb0, zb);
+      ca.out_f32 = c0; ca.out_bstride = FN; ca.bias = p->n_bias[gi]; ca.bias_scale = 2.f;
+      launch_tap<TAP_PLAIN>(ca, Wb, d.sms, st);
+      NodeGateArgs na{};
+      na.A = p->n_weight_A[gi]; na.wh = p->n_head_w[gi]; na.X = X; na.zx = s.zx; na.zx_kstride = d.RX * d.N; na.c0 = c0;
+      na.Kin = d.Kin; na.G = d.G; na.F = d.F; na.N = d.N; na.Kst = d.Kst; na.exact = P > 1; na.B = d.B; na.T = d.T; na.p = pbuf;
+      node_gate_fwd_kernel<64><<<(unsigned)std::min<long long>(d.B * (d.N / 128), 148 * 16), 128, node_gate_smem_bytes(d.F, d.Kst, false), st>>>(na);
+      launched();
+      float* q = s.qn + (size_t)gi * d.BT * d.N;
+      const float* r = pbuf + (size_t)(d.Kst - 1) * d.BT * d.N;            // Horner: r = p_{K-1}; r = r S + p_k
+      for (int k = d.Kst - 2; k >= 0; --k) {
+        cvt_bf16(r, rb, d.BT, d.N, P, st);
+        shift_gemm(g, false, rb, d.BT, P, nullptr, P, rtmp, st);
+        node_head_add_kernel<<<eg, 256, 0, st>>>(reinterpret_cast<const float4*>(rtmp), reinterpret_cast<const float4*>(pbuf + (size_t)k * d.BT * d.N),
+                                                reinterpret_cast<float4*>(k == 0 ? q : rcur), n4, p->n_head_b[gi], k == 0);
+        launched();
+        r = rcur;
+      }
+      if (d.Kst == 1) {
+        node_head_add_kernel<<<eg, 256, 0, st>>>(nullptr, reinterpret_cast<const float4*>(pbuf), reinterpret_cast<float4*>(q), n4, p->n_head_b[gi], 1);
+        launched();
+      }
     }
   }
   // ---- the recurrence -------------------------------------------------------------------------------------------
@@ -460,7 +502,7 @@ size_t cell_forward_tc(const gcrnn_cell* cell, const gcrnn_cell_params* p, const
   prep_contract_weight(p->weight_B, Wb, d.F, d.Kst, 0, P, st);
   for (long long t = 0; t < d.T; ++t) {
     const __nv_bfloat16* hprev = t == 0 ? hb0 : s.Hb + (size_t)(t - 1) * d.R * d.LD;
-    if (!(t == 0 && d.tg)) chain(g, false, hprev, zb, d.Kst, d.R, P, st);      // at t = 0 the gates' h0 chain is still in zb
+    if (!(t == 0 && (d.tg || d.node))) chain(g, false, hprev, zb, d.Kst, d.R, P, st);      // at t = 0 the gates' h0 chain is still in zb
     ContractArgs ca = contract_base(d, hprev, zb);
     ca.out_f32 = H + t * FN; ca.out_bstride = d.T * FN; ca.out_bf16 = s.Hb + (size_t)t * d.R * d.LD;
     ca.bias = p->bias;
@@ -468,6 +510,7 @@ size_t cell_forward_tc(const gcrnn_cell* cell, const gcrnn_cell_params* p, const
     ca.A = p->weight_A; ca.Kin = d.Kin; ca.G = d.G;
     ca.x0 = X + t * GN; ca.x0_bstride = d.T * GN;
     ca.zx = s.zx + t * GN; ca.zx_kstride = d.RX * d.N; ca.zx_bstride = d.T * GN;
+    if (d.node) { ca.qi = s.qn + t * d.N; ca.qf = s.qn + (size_t)d.BT * d.N + t * d.N; ca.q_bstride = d.T * d.N; }
     launch_tap<TAP_FWD>(ca, Wb, d.sms, st);
   }
   return a.off;
@@ -494,17 +537,19 @@ size_t cell_backward_tc(const gcrnn_cell* cell, const gcrnn_cell_params* p, cons
   __nv_bfloat16* hb0 = a.get<__nv_bfloat16>((size_t)d.R * d.LD);
   __nv_bfloat16* WTb = a.get<__nv_bfloat16>(wbuf);
   float* part = a.get<float>((size_t)max_sms * d.Kst * d.F * d.F);
-  const bool fused = opt().bwd_fused && d.F == 64 && d.Kin * d.G <= (P > 1 ? 7 : 8) && d.Kst <= 6 && d.N % 128 == 0 && bf_stages(P, d.Kst) >= 2;
+  const bool fused = opt().bwd_fused && d.F == 64 && d.Kin * d.G <= (P > 1 ? 7 : 8) && d.Kst <= 6 && d.N % 128 == 0 && bf_stages(P, d.Kst) >= 2 && !d.node;
   const int zs_split = P > 1;       // Zs tiles carry hi rows 0..7 and residual rows 8..15
   __nv_bfloat16* Zs = fused ? a.get<__nv_bfloat16>((size_t)d.BT * BF_ZROWS * d.N) : nullptr;
   float* partA = fused ? a.get<float>((size_t)max_sms * 64 * BF_ZROWS) : nullptr;
   float* zslab = cell->dh_last_only ? a.get<float>((size_t)d.F * d.N) : nullptr;
   float *dgt = nullptr, *c0 = nullptr, *dc0 = nullptr, *dl = nullptr;
   __nv_bfloat16* Wb = nullptr;
-  if (d.tg) {
-    dgt = a.get<float>(2 * d.BT); c0 = a.get<float>((size_t)d.R * d.N); dc0 = a.get<float>((size_t)d.R * d.N);
-    dl = a.get<float>(d.BT); Wb = a.get<__nv_bfloat16>(wbuf);
-  }
+  if (d.tg || d.node) { c0 = a.get<float>((size_t)d.R * d.N); dc0 = a.get<float>((size_t)d.R * d.N); Wb = a.get<__nv_bfloat16>(wbuf); }
+  if (d.tg) { dgt = a.get<float>(2 * d.BT); dl = a.get<float>(d.BT); }
+  // node gates: d lin [2][B*T][N] (accumulated by dpre_kernel), adjoint head signals v_k [Kst][B*T][N], bf16 planes of a shift input
+  float* dlin = d.node ? a.get<float>((size_t)2 * d.BT * d.N) : nullptr;
+  float* vhead = d.node ? a.get<float>((size_t)d.Kst * d.BT * d.N) : nullptr;
+  __nv_bfloat16* rb = d.node ? a.get<__nv_bfloat16>((size_t)d.BT * d.LD) : nullptr;
   if (a.dry()) return a.off;
   GCRNN_CHECK(dX == nullptr, "the tensor-core path does not produce dX (the reference never asks for it: train_rnn.py:256); "
                              "use precision fp32 for input gradients");
@@ -533,12 +578,13 @@ size_t cell_backward_tc(const gcrnn_cell* cell, const gcrnn_cell_params* p, cons
 
   CUDA_OK(cudaMemsetAsync(part, 0, part_bytes, st));
   if (d.tg) CUDA_OK(cudaMemsetAsync(dgt, 0, 2 * d.BT * sizeof(float), st));
+  if (d.node) CUDA_OK(cudaMemsetAsync(dlin, 0, (size_t)2 * d.BT * d.N * sizeof(float), st));
   prep_contract_weight(p->weight_B, WTb, d.F, d.Kst, 1, P, st);
   cvt_bf16(h0, hb0, d.R, d.N, P, st);
 
   // ---- reverse-time sweep -------------------------------------------------------------------------------------------
   CUDA_OK(cudaMemsetAsync(red, 0, (size_t)d.R * 8 * sizeof(float), st));
-  const bool can_fuse = d.Kin * d.G <= 7;
+  const bool can_fuse = d.Kin * d.G <= 7 && !d.node;
   auto run_dpre = [&](long long t, const float* dhrec_in, __nv_bfloat16* v0_out) {
     DpreArgs da{};
     da.dH = dv.ptr(t); da.dH_bstride = dv.bstride(t); da.Ht = H + t * FN; da.H_bstride = d.T * FN;
@@ -548,7 +594,11 @@ size_t cell_backward_tc(const gcrnn_cell* cell, const gcrnn_cell_params* p, cons
     da.x0 = X + t * GN; da.x0_bstride = d.T * GN; da.zx = s.zx + t * GN; da.zx_kstride = d.RX * d.N; da.zx_bstride = d.T * GN;
     da.dgi = d.tg ? dgt + t : nullptr; da.dgf = d.tg ? dgt + d.BT + t : nullptr;
     da.dA = fused ? nullptr : gr->weight_A; da.dbias = fused ? nullptr : gr->bias; da.B = d.B;   // fused: MMA3 covers every step
-    dpre_kernel<<<(unsigned)std::min<long long>(d.B * (d.F / DP_FC), 148 * 32), 256, 0, st>>>(da);
+    if (d.node) {
+      da.qi = s.qn + t * d.N; da.qf = s.qn + (size_t)d.BT * d.N + t * d.N; da.q_bstride = d.T * d.N;
+      da.dlin_i = dlin + t * d.N; da.dlin_f = dlin + (size_t)d.BT * d.N + t * d.N;
+    }
+    dpre_kernel<<<(unsigned)std::min<long long>(d.B * (d.F / DP_FC), 148 * 32), 256, d.node ? 2 * d.N * sizeof(float) : 0, st>>>(da);
     launched();
   };
   __nv_bfloat16* v0cur = vb0; __nv_bfloat16* v0nxt = vb0b;
@@ -615,14 +665,34 @@ size_t cell_backward_tc(const gcrnn_cell* cell, const gcrnn_cell_params* p, cons
     launched();
   }
 
+  // T-invariant term of a gate sub-cell, forward again: c0 = B_s(S) h0 + 2 b_s   (the v slabs are free here: they hold h0's chain for a moment)
+  auto subcell_c0 = [&](const float* wB, const float* bias) {
+    chain(g, false, hb0, vb, d.Kst, d.R, P, st);
+    prep_contract_weight(wB, Wb, d.F, d.Kst, 0, P, st);
+    ContractArgs cc = contract_base(d, hb0, vb);
+    cc.out_f32 = c0; cc.out_bstride = FN; cc.bias = bias; cc.bias_scale = 2.f;
+    launch_tap<TAP_PLAIN>(cc, Wb, d.sms, st);
+  };
+  // ... and its adjoint from dc0 = sum_t d pre_s: db_s += 2 sum_n dc0; v_k = dc0 (S^T)^k; dB_s,k = v_k h0^T; dh0 += sum_k B_s,k^T v_k
+  auto subcell_h0_path = [&](const float* wB, float* gwB, float* gbias) {
+    if (gbias) {
+      rowsum_bfn_kernel<<<(unsigned)std::min<long long>(d.R, 148 * 8), 256, 0, st>>>(dc0, gbias, d.B, d.F, d.N, 2.f);
+      launched();
+    }
+    cvt_bf16(dc0, vb0, d.R, d.N, P, st);
+    chain(g, true, vb0, vb, d.Kst, d.R, P, st);
+    if (gwB) { wgrad_v(vb0, h0, FN, hb0); wgrad_flush(gwB); }
+    if (dh0) {
+      prep_contract_weight(wB, Wb, d.F, d.Kst, 1, P, st);
+      ContractArgs cb = contract_base(d, vb0, vb);
+      cb.out_f32 = dhrec; cb.out_bstride = FN; cb.hprev = h0; cb.hprev_bstride = FN; cb.accumulate = 1;
+      launch_tap<TAP_BWD>(cb, Wb, d.sms, st);
+    }
+  };
   // ---- time gates, batched over (b, t) -----------------------------------------------------------------------------------
   if (d.tg) {
     for (int gi = 0; gi < 2; ++gi) {
-      chain(g, false, hb0, vb, d.Kst, d.R, P, st);  // the v slabs are free here: they hold h0's forward chain for a moment
-      prep_contract_weight(p->t_weight_B[gi], Wb, d.F, d.Kst, 0, P, st);
-      ContractArgs cc = contract_base(d, hb0, vb);
-      cc.out_f32 = c0; cc.out_bstride = FN; cc.bias = p->t_bias[gi]; cc.bias_scale = 2.f;
-      launch_tap<TAP_PLAIN>(cc, Wb, d.sms, st);
+      subcell_c0(p->t_weight_B[gi], p->t_bias[gi]);
       gate_dlogit_kernel<<<1, 1024, 0, st>>>(dgt + gi * d.BT, s.gt + gi * d.BT, dl, gr->t_mlp_b[gi], d.BT);
       launched();
       GateArgs ga{};
@@ -631,20 +701,30 @@ size_t cell_backward_tc(const gcrnn_cell* cell, const gcrnn_cell_params* p, cons
       ga.dWg = gr->t_mlp_w[gi]; ga.dc0 = dc0; ga.dA = gr->t_weight_A[gi];
       GCRNN_CHECK(ga.dWg && ga.dA, "time-gate gradient buffers missing");
       gate_launch(true, ga, d, st);
-      if (gr->t_bias[gi]) {
-        rowsum_bfn_kernel<<<(unsigned)std::min<long long>(d.R, 148 * 8), 256, 0, st>>>(dc0, gr->t_bias[gi], d.B, d.F, d.N, 2.f);
-        launched();
+      subcell_h0_path(p->t_weight_B[gi], gr->t_weight_B[gi], gr->t_bias[gi]);
+    }
+  }
+  // ---- node gates, batched over (b, t): adjoint head chain on scalar node signals, then the sub-cell (tc_node.cuh) -----------
+  if (d.node) {
+    const long long nelem = d.BT * d.N;
+    for (int gi = 0; gi < 2; ++gi) {
+      subcell_c0(p->n_weight_B[gi], p->n_bias[gi]);
+      const float* dl_g = dlin + (size_t)gi * nelem;
+      if (gr->n_head_b[gi]) { sum_all_kernel<<<148 * 4, 256, 0, st>>>(dl_g, gr->n_head_b[gi], nelem); launched(); }
+      CUDA_OK(cudaMemcpyAsync(vhead, dl_g, (size_t)nelem * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      for (int k = 1; k < d.Kst; ++k) {                                       // v_k = v_{k-1} S^T
+        cvt_bf16(vhead + (size_t)(k - 1) * nelem, rb, d.BT, d.N, P, st);
+        shift_gemm(g, true, rb, d.BT, P, nullptr, P, vhead + (size_t)k * nelem, st);
       }
-      // h0 path of the sub-cell: v_k = dc0 (S^T)^k ; dB_g,k = v_k h0^T ; dh0 += sum_k B_g,k^T v_k
-      cvt_bf16(dc0, vb0, d.R, d.N, P, st);
-      chain(g, true, vb0, vb, d.Kst, d.R, P, st);
-      if (gr->t_weight_B[gi]) { wgrad_v(vb0, h0, FN, hb0); wgrad_flush(gr->t_weight_B[gi]); }
-      if (dh0) {
-        prep_contract_weight(p->t_weight_B[gi], Wb, d.F, d.Kst, 1, P, st);
-        ContractArgs cb = contract_base(d, vb0, vb);
-        cb.out_f32 = dhrec; cb.out_bstride = FN; cb.hprev = h0; cb.hprev_bstride = FN; cb.accumulate = 1;
-        launch_tap<TAP_BWD>(cb, Wb, d.sms, st);
-      }
+      NodeGateArgs na{};
+      na.A = p->n_weight_A[gi]; na.wh = p->n_head_w[gi]; na.X = X; na.zx = s.zx; na.zx_kstride = d.RX * d.N; na.c0 = c0;
+      na.Kin = d.Kin; na.G = d.G; na.F = d.F; na.N = d.N; na.Kst = d.Kst; na.exact = P > 1; na.B = d.B; na.T = d.T;
+      na.v = vhead; na.dA = gr->n_weight_A[gi]; na.dwh = gr->n_head_w[gi]; na.dc0 = dc0;
+      GCRNN_CHECK(na.dA && na.dwh, "node-gate gradient buffers missing");
+      node_gate_bwd_kernel<<<(unsigned)std::min<long long>(d.B * (d.N / 128) * (d.F / NG_FC), 148 * 16), 128,
+                             node_gate_smem_bytes(d.F, d.Kst, true), st>>>(na);
+      launched();
+      subcell_h0_path(p->n_weight_B[gi], gr->n_weight_B[gi], gr->n_bias[gi]);
     }
   }
   if (dh0) CUDA_OK(cudaMemcpyAsync(dh0, dhrec, (size_t)d.R * d.N * sizeof(float), cudaMemcpyDeviceToDevice, st));

@@ -102,6 +102,7 @@ struct ContractArgs {
   const float* hprev; long long hprev_bstride;                  // EPI_BWD: fp32 h_{t-1}[b] = hprev + b*bstride
   float* dgf; int accumulate; int scaled_chain;
   const float* dHn; long long dHn_bstride; const float* gfn; float* red;   // fused backward epilogue (tc_tap.cuh TAP_BWDF)
+  const float* qi; const float* qf; long long q_bstride;                   // EPI_FWD: node gates of this step (null: 1), tc_node.cuh
 };
 
 // =====================================================================================================
@@ -249,37 +250,54 @@ struct DpreArgs {
   float* dA;                                    // [F][Kin][G]  += gi * sum_n dpre zx_k
   float* dbias;                                 // [F]          += (gi + gf) * sum_n dpre
   long long B;
+  // node gates (tc_node.cuh): q_i, q_f of this step at q + b * q_bstride + n; the update is tanh(gi q_i (a + b) + gf q_f (r + b)).
+  // Out: d lin_i[b][n] += (1 - q_i) gi q_i sum_f dpre (a + b),  d lin_f[b][n] += (1 - q_f) sum_f dpre (atanh(h) - gi q_i (a + b))
+  // (gf q_f (r + b) recovered from the state itself: no recomputation of the state filter).  Needs Kin*G <= DP_KG and 2N floats
+  // of dynamic shared memory.
+  const float* qi; const float* qf; long long q_bstride;
+  float* dlin_i; float* dlin_f;
 };
 constexpr int DP_FC = 8;      // features (warps) per CTA
 constexpr int DP_KG = 8;      // (k, g) pairs handled per pass
 
 __global__ void __launch_bounds__(256) dpre_kernel(const DpreArgs a) {
   __shared__ float s_gi[DP_FC];
+  extern __shared__ float s_dl[];               // node gates: [2][N] per-node sums over the CTA's DP_FC features
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int KG = a.Kin * a.G;
   const int fgroups = a.F / DP_FC;
   const int N4 = a.N / 4;
+  const bool node = a.qi != nullptr;
+  if (node) {
+    for (int i = threadIdx.x; i < 2 * a.N; i += blockDim.x) s_dl[i] = 0.f;
+    __syncthreads();
+  }
   for (long long item = blockIdx.x; item < a.B * fgroups; item += gridDim.x) {
     const long long b = item / fgroups;
     const int f = (int)(item % fgroups) * DP_FC + warp;
     const float vgi = a.gi ? a.gi[b * a.gate_stride] : 1.f;
     const float vgf = a.gf ? a.gf[b * a.gate_stride] : 1.f;
+    const float bb = a.bias ? a.bias[f] : 0.f;
     const float4* pdH = reinterpret_cast<const float4*>(a.dH + b * a.dH_bstride + (size_t)f * a.N);
     const float4* pH = reinterpret_cast<const float4*>(a.Ht + b * a.H_bstride + (size_t)f * a.N);
     const float4* pR = a.dhrec ? reinterpret_cast<const float4*>(a.dhrec + ((size_t)b * a.F + f) * a.N) : nullptr;
+    const float4* pQi = node ? reinterpret_cast<const float4*>(a.qi + b * a.q_bstride) : nullptr;
+    const float4* pQf = node ? reinterpret_cast<const float4*>(a.qf + b * a.q_bstride) : nullptr;
     uint2* pV = reinterpret_cast<uint2*>(a.v0 + ((size_t)b * a.F + f) * a.P * a.N);
-    float sdp = 0.f, sa = 0.f;
+    float sdi = 0.f, sdf = 0.f, sa = 0.f;       // sum_n dpre q_i, sum_n dpre q_f, <dpre q_i, A(S)x>
     for (int kg0 = 0; kg0 < KG || kg0 == 0; kg0 += DP_KG) {
-      float sz[DP_KG];
+      float sz[DP_KG], Af[DP_KG];
 #pragma unroll
-      for (int j = 0; j < DP_KG; ++j) sz[j] = 0.f;
+      for (int j = 0; j < DP_KG; ++j) { sz[j] = 0.f; Af[j] = (kg0 + j < KG) ? a.A[(size_t)f * KG + kg0 + j] : 0.f; }
       for (int i = lane; i < N4; i += 32) {
         const float4 hv = pH[i];
         float4 d = pdH[i];
         if (pR) { const float4 r = pR[i]; d.x += r.x; d.y += r.y; d.z += r.z; d.w += r.w; }
         d.x *= 1.f - hv.x * hv.x; d.y *= 1.f - hv.y * hv.y; d.z *= 1.f - hv.z * hv.z; d.w *= 1.f - hv.w * hv.w;
+        float4 qi4 = make_float4(1.f, 1.f, 1.f, 1.f), qf4 = qi4;
+        if (node) { qi4 = pQi[i]; qf4 = pQf[i]; }
         if (kg0 == 0) {
-          float s0 = vgf * d.x, s1 = vgf * d.y, s2 = vgf * d.z, s3 = vgf * d.w;
+          float s0 = vgf * qf4.x * d.x, s1 = vgf * qf4.y * d.y, s2 = vgf * qf4.z * d.z, s3 = vgf * qf4.w * d.w;
           uint2 u; u.x = pack_bf16x2(s0, s1); u.y = pack_bf16x2(s2, s3);
           pV[i] = u;
           if (a.P > 1) {
@@ -287,8 +305,11 @@ __global__ void __launch_bounds__(256) dpre_kernel(const DpreArgs a) {
             uint2 w; w.x = pack_bf16x2(s0, s1); w.y = pack_bf16x2(s2, s3);
             pV[N4 + i] = w;
           }
-          sdp += (d.x + d.y) + (d.z + d.w);
+          sdi += fmaf(d.x, qi4.x, d.y * qi4.y) + fmaf(d.z, qi4.z, d.w * qi4.w);
+          sdf += fmaf(d.x, qf4.x, d.y * qf4.y) + fmaf(d.z, qf4.z, d.w * qf4.w);
         }
+        const float4 dq = make_float4(d.x * qi4.x, d.y * qi4.y, d.z * qi4.z, d.w * qi4.w);
+        float4 ax = make_float4(bb, bb, bb, bb);                        // A(S)x + b of this feature (node gates only)
 #pragma unroll
         for (int j = 0; j < DP_KG; ++j) {
           const int kg = kg0 + j;
@@ -297,7 +318,19 @@ __global__ void __launch_bounds__(256) dpre_kernel(const DpreArgs a) {
             const float* zp = (k == 0) ? a.x0 + b * a.x0_bstride + (size_t)g * a.N
                                        : a.zx + (size_t)(k - 1) * a.zx_kstride + b * a.zx_bstride + (size_t)g * a.N;
             const float4 z = reinterpret_cast<const float4*>(zp)[i];
-            sz[j] = fmaf(d.x, z.x, fmaf(d.y, z.y, fmaf(d.z, z.z, fmaf(d.w, z.w, sz[j]))));
+            sz[j] = fmaf(dq.x, z.x, fmaf(dq.y, z.y, fmaf(dq.z, z.z, fmaf(dq.w, z.w, sz[j]))));
+            ax.x = fmaf(Af[j], z.x, ax.x); ax.y = fmaf(Af[j], z.y, ax.y); ax.z = fmaf(Af[j], z.z, ax.z); ax.w = fmaf(Af[j], z.w, ax.w);
+          }
+        }
+        if (node) {
+          const float hx[4] = {hv.x, hv.y, hv.z, hv.w}, dx[4] = {d.x, d.y, d.z, d.w}, axx[4] = {ax.x, ax.y, ax.z, ax.w};
+          const float qix[4] = {qi4.x, qi4.y, qi4.z, qi4.w}, qfx[4] = {qf4.x, qf4.y, qf4.z, qf4.w};
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const float wi = vgi * qix[c] * axx[c];                     // gi q_i (a + b)
+            const float pre = atanhf(fminf(fmaxf(hx[c], -0.99999994f), 0.99999994f));
+            atomicAdd(s_dl + 4 * i + c, (1.f - qix[c]) * dx[c] * wi);
+            atomicAdd(s_dl + a.N + 4 * i + c, (1.f - qfx[c]) * dx[c] * (pre - wi));
           }
         }
       }
@@ -306,17 +339,16 @@ __global__ void __launch_bounds__(256) dpre_kernel(const DpreArgs a) {
         const int kg = kg0 + j;
         if (kg < KG) {
           const float v = warp_sum_f(sz[j]);
-          sa = fmaf(a.A[(size_t)f * KG + kg], v, sa);                  // <dpre, A(S)x> = sum_kg A[f,kg] <dpre, zx_kg>
+          sa = fmaf(Af[j], v, sa);                                     // <dpre q_i, A(S)x> = sum_kg A[f,kg] <dpre q_i, zx_kg>
           if (lane == 0 && a.dA) atomicAdd(a.dA + (size_t)f * KG + kg, vgi * v);
         }
       }
     }
-    sdp = warp_sum_f(sdp);
-    const float bb = a.bias ? a.bias[f] : 0.f;
+    sdi = warp_sum_f(sdi); sdf = warp_sum_f(sdf);
     if (lane == 0) {
-      if (a.dbias) atomicAdd(a.dbias + f, (vgi + vgf) * sdp);
-      s_gi[warp] = sa + bb * sdp;
-      if (a.dgf) atomicAdd(a.dgf + b * a.gate_stride, bb * sdp);
+      if (a.dbias) atomicAdd(a.dbias + f, vgi * sdi + vgf * sdf);
+      s_gi[warp] = sa + bb * sdi;
+      if (a.dgf) atomicAdd(a.dgf + b * a.gate_stride, bb * sdf);
     }
     __syncthreads();
     if (threadIdx.x == 0 && a.dgi) {
@@ -324,6 +356,13 @@ __global__ void __launch_bounds__(256) dpre_kernel(const DpreArgs a) {
 #pragma unroll
       for (int w = 0; w < DP_FC; ++w) t += s_gi[w];
       atomicAdd(a.dgi + b * a.gate_stride, t);
+    }
+    if (node) {
+      for (int i = threadIdx.x; i < a.N; i += blockDim.x) {
+        atomicAdd(a.dlin_i + b * a.q_bstride + i, s_dl[i]);
+        atomicAdd(a.dlin_f + b * a.q_bstride + i, s_dl[a.N + i]);
+        s_dl[i] = 0.f; s_dl[a.N + i] = 0.f;
+      }
     }
     __syncthreads();
   }

@@ -49,6 +49,8 @@ struct TapArgs {
   const float* dHn; long long dHn_bstride;
   const float* gfn;              // gf[b, t-1] at gfn[b * gate_stride] (null: 1)
   float* red;                    // [B][M][8]
+  // TAP_FWD with node gates (tc_node.cuh): h = tanh(gi q_i[n] (ax + b) + gf q_f[n] (v + b)), q at q + b * q_bstride + n
+  const float* qi; const float* qf; long long q_bstride;
 };
 
 // sum over the 32 lanes of 32 per-lane quantities with 31 shuffles: afterwards lane l holds the total of x[l] in x[0]
@@ -294,6 +296,7 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__
           const long long ldo = (long long)a.P * a.N;          // bf16 row = P planes of N
           __nv_bfloat16* ob = a.out_bf16 + ((size_t)b * a.M + m0) * ldo + n;
           const float* aw = sAw + m0 * KG;
+          if (a.qi) { vgi *= __ldg(a.qi + b * a.q_bstride + n); vgf *= __ldg(a.qf + b * a.q_bstride + n); }      // per-node gates
           const float gsum = vgi + vgf;
 #pragma unroll
           for (int i = 0; i < 16; ++i) {

@@ -211,8 +211,10 @@ class GGCRNNCell(nn.Module):
             return 'the GSO is sparse (dense [E,N,N] tensor needed)'
         if self.E != 1:
             return f'E={self.E} (E == 1 needed)'
-        if self.spatial_gating is not None:
-            return f'spatial_gating={self.spatial_gating!r} (time gating or none)'
+        if self.spatial_gating == 'edge':
+            return "spatial_gating='edge' (time and node gating only)"
+        if self.spatial_gating == 'node' and self.Kin * self.G > 8:
+            return f'node gating with Kin*G={self.Kin * self.G} (<= 8)'
         if self.N % (256 if split else 128) != 0:
             return f'N={self.N} (N % {256 if split else 128} == 0 needed)'
         if self.F not in (16, 32, 64):

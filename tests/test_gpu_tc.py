@@ -134,9 +134,9 @@ def _grad_errs(got, ref):
     return errs
 
 
-def _make_cell(S, G, F, K, tg, prec, seed=0):
+def _make_cell(S, G, F, K, tg, prec, seed=0, sg=None, bias=True):
     torch.manual_seed(seed)
-    cell = gg.GGCRNNCell(G, F, K, K, torch.tanh, tg, None, 1, True)
+    cell = gg.GGCRNNCell(G, F, K, K, torch.tanh, tg, sg, 1, bias)
     cell.addGSO(S)
     gg.set_precision(prec)
     return cell.to(DEV)
@@ -172,6 +172,56 @@ def test_tc_cell_matches_fp32_path(prec, tg, N, F, K, T, B, G):
     assert errs['H'] < tol_h, errs
     bad = {k: v for k, v in errs.items() if k != 'H' and v > tol_g}
     assert not bad, errs
+
+
+@pytest.mark.parametrize('prec', ['bf16', 'bf16x2'])
+@pytest.mark.parametrize('tg', [False, True])
+@pytest.mark.parametrize('N,F,K,T,B,G,bias', [(256, 32, 3, 5, 8, 1, True), (512, 64, 5, 4, 6, 1, True), (256, 16, 4, 3, 5, 2, False),
+                                              (256, 32, 3, 1, 8, 1, True), (256, 64, 1, 3, 4, 1, True)])
+def test_tc_node_gated_cell_matches_fp32_path(prec, tg, N, F, K, T, B, G, bias):
+    """Node gates on the tensor-core path (csrc/tc_node.cuh; graphML.py:2379-2407): outputs and EVERY gradient (main cell, the
+    node-gate sub-cells, their F -> 1 heads, time gates when present, dh0) against the exact fp32 path on the same weights and
+    inputs, with the bounds of the ungated / time-gated tensor-core cell."""
+    S = gg.graphs.dense_random(N, 0.3, seed=1)
+    torch.manual_seed(3)
+    X, h0, dH = torch.randn(B, T, G, N, device=DEV), 0.3 * torch.randn(B, F, N, device=DEV), torch.randn(B, T, F, N, device=DEV)
+    out = {}
+    try:
+        for pr in ('fp32', prec):
+            cell = _make_cell(S, G, F, K, tg, pr, sg='node', bias=bias)
+            hh = h0.clone().requires_grad_(True)
+            H = cell(X, hh)
+            (H * dH).sum().backward()
+            out[pr] = (H.detach(), {k: v.grad for k, v in cell.named_parameters()}, hh.grad)
+    finally:
+        gg.set_precision('fp32')
+    H32, g32, dh32 = out['fp32']
+    Hb, gb, dhb = out[prec]
+    errs = {'H': _relerr(Hb, H32), 'dh0': _relerr(dhb, dh32)}
+    errs.update(_grad_errs(gb, g32))
+    _log(f'tc-node-vs-fp32 {prec}', dict(tg=tg, N=N, F=F, K=K, T=T, B=B, G=G), {k: f'{v:.2e}' for k, v in errs.items()})
+    tol = TC_TOL[prec]
+    tol_h, tol_g = (tol['H1'], tol['G1']) if T == 1 else (tol['H'], tol['G'])
+    assert errs['H'] < tol_h, errs
+    bad = {k: v for k, v in errs.items() if k != 'H' and v > tol_g}
+    assert not bad, errs
+
+
+def test_tc_auto_precision_takes_node_gated_dense_cells():
+    """precision 'auto' picks the split-bf16 tensor-core path for a cfg3-shaped node-gated cell and keeps fp32 for an edge-gated one."""
+    S = gg.graphs.dense_random(256, 0.3, seed=1)
+    try:
+        gg.set_precision('auto')
+        for sg, want in (('node', _lib.PREC_BF16X2_TC), ('edge', _lib.PREC_FP32), (None, _lib.PREC_BF16X2_TC)):
+            torch.manual_seed(0)
+            cell = gg.GGCRNNCell(1, 32, 3, 3, torch.tanh, True, sg, 1, True)
+            cell.addGSO(S)
+            cell = cell.to(DEV)
+            assert cell._precision_for(torch.device(DEV), False) == want, sg
+            H = cell(torch.randn(2, 2, 1, 256, device=DEV), torch.zeros(2, 32, 256, device=DEV))
+            assert torch.isfinite(H).all()
+    finally:
+        gg.set_precision('fp32')
 
 
 @pytest.mark.parametrize('prec', ['bf16', 'bf16x2'])
