@@ -227,10 +227,11 @@ def run_ours(args):
     gg.set_precision(args.precision)
     S = gg.graphs.dense_random(N, cfg['density'], seed=0)
     torch.manual_seed(0)
-    cell = gg.GGCRNNCell(G, F, K, K, torch.tanh, True, None, 1, True)
+    sg = 'node' if getattr(args, 'cfg3_spatial', 'none') == 'node' else None      # extra: the same dense config with node gates on top
+    cell = gg.GGCRNNCell(G, F, K, K, torch.tanh, True, sg, 1, True)
     cell.addGSO(S)
     cell = cell.to(dev)
-    used = [dict(cell.named_parameters())[n] for _, _, n in gg.cell_param_slots(True, None, True)]
+    used = [dict(cell.named_parameters())[n] for _, _, n in gg.cell_param_slots(True, sg, True)]
     gen = torch.Generator(device='cpu').manual_seed(1234 + rank)
     X_host = torch.randn(Bl, T, G, N, generator=gen).pin_memory()
     h0_host = torch.zeros(mb, F, N).pin_memory()
@@ -489,7 +490,8 @@ def run_ours(args):
         out = dict(metric='GCRNN sequences/sec fwd+bwd', value=seqs, unit='sequences/s', n_gpus=world, steps=args.steps,
                    warmup=args.warmup, ms_per_step=ms_dev / args.steps, higher_is_better=True, scaling='strong',
                    vs_baseline=None, dtype=PREC_DTYPE[args.precision], data='synthetic',
-                   config=dict(workload='cfg3: dense N=1024 F=64 G=1 K=5 T=64 time-gated GGCRNNCell fwd+bwd',
+                   config=dict(workload='cfg3: dense N=1024 F=64 G=1 K=5 T=64 time-gated GGCRNNCell fwd+bwd'
+                                        + (' + NODE gates (extra; step_frac still counts the time-gated cell\'s 82.82 GFLOP/sequence)' if sg else ''),
                                global_batch=cfg['B'], per_gpu_batch=Bl, microbatch=mb, precision=args.precision,
                                parallelism=f'dp{world} (batch sharded, one gradient all-reduce per step'
                                            + (f' through gated_gcrnns_b200.dist.allreduce_gradients, transport {"gcrnn_allreduce_sum (C ABI)" if args.native_allreduce else "torch.distributed nccl"})' if world > 1 else ')'),
@@ -833,6 +835,8 @@ def main():
     ap.add_argument('--also', default='bf16,fp32', type=lambda v: [m for m in v.split(',') if m],
                     help='other precisions of the same workload to time briefly for the `modes` object (comma separated; "" = none)')
     ap.add_argument('--no-parity', action='store_true', help='skip the in-run parity measurement')
+    ap.add_argument('--cfg3-spatial', default='none', choices=['none', 'node'],
+                    help='cfg3 extra: add node gates to the time-gated dense cell (tensor-core path, csrc/tc_node.cuh)')
     ap.add_argument('--cfg5-reorder', default='auto', choices=['auto', 'off', 'force'],
                     help='library-owned node renumbering of the fused sparse path (graph option "reorder")')
     ap.add_argument('--cfg5-order', default='hilbert', choices=['hilbert', 'random', 'host'],

@@ -364,26 +364,27 @@ def test_tc_cfg3_full_horizon_vs_oracle(weighted, h0_scale):
     assert max(curves['bf16'][:4]) < 6e-2, curves['bf16'][:4]
 
 
-def test_tc_cell_vs_fp64_oracle_reduced_cfg3():
-    """cfg3's shapes with a small batch: N=1024, F=64, K=5, G=1, time-gated, against the fp64 oracle."""
+@pytest.mark.parametrize('sg,prec', [(None, 'bf16'), ('node', 'bf16'), ('node', 'bf16x2')])
+def test_tc_cell_vs_fp64_oracle_reduced_cfg3(sg, prec):
+    """cfg3's shapes with a small batch: N=1024, F=64, K=5, G=1, time-gated (and time + node gated), against the fp64 oracle."""
     from oracle import gcrnn_oracle as orc
     N, F, K, T, B = 1024, 64, 5, 6, 2
     S = gg.graphs.dense_random(N, 0.3, seed=0)
     try:
-        cell = _make_cell(S, 1, F, K, True, 'bf16')
+        cell = _make_cell(S, 1, F, K, True, prec, sg=sg)
         torch.manual_seed(5)
         X, h0, dH = torch.randn(B, T, 1, N), torch.zeros(B, F, N), torch.randn(B, T, F, N)
         p = {k: v.detach().double().cpu() for k, v in cell.state_dict().items()}
-        Href, gref = orc.cell_forward_backward(p, S.double(), X.double(), h0.double(), dH.double(), True, None)
+        Href, gref = orc.cell_forward_backward(p, S.double(), X.double(), h0.double(), dH.double(), True, sg)
         H = cell(X.to(DEV), h0.to(DEV))
         (H * dH.to(DEV)).sum().backward()
     finally:
         gg.set_precision('fp32')
     errs = {'H': _relerr(H, Href)}
     errs.update(_grad_errs({k: v.grad for k, v in cell.named_parameters()}, {k: gref[k] for k, _ in cell.named_parameters()}))
-    _log('tc-vs-fp64', {k: f'{v:.2e}' for k, v in errs.items()})
-    assert errs['H'] < TC_TOL_H, errs
-    assert all(v < TC_TOL_G for k, v in errs.items() if k != 'H'), errs
+    _log(f'tc-vs-fp64 {prec} sg={sg}', {k: f'{v:.2e}' for k, v in errs.items()})
+    assert errs['H'] < TC_TOL[prec]['H'], errs
+    assert all(v < TC_TOL[prec]['G'] for k, v in errs.items() if k != 'H'), errs
 
 
 def test_tc_cell_long_horizon_contractive():
