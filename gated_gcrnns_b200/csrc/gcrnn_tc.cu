@@ -453,7 +453,7 @@ size_t cell_forward_tc(const gcrnn_cell* cell, const gcrnn_cell_params* p, const
       NodeGateArgs na{};
       na.A = p->n_weight_A[gi]; na.wh = p->n_head_w[gi]; na.X = X; na.zx = s.zx; na.zx_kstride = d.RX * d.N; na.c0 = c0;
       na.Kin = d.Kin; na.G = d.G; na.F = d.F; na.N = d.N; na.Kst = d.Kst; na.exact = P > 1; na.B = d.B; na.T = d.T; na.p = pbuf;
-      node_gate_fwd_kernel<64><<<(unsigned)std::min<long long>(d.B * (d.N / 128), 148 * 16), 128, node_gate_smem_bytes(d.F, d.Kst, false), st>>>(na);
+      node_gate_fwd_kernel<64><<<(unsigned)std::min<long long>(d.B * (d.N / 128), 148 * 16), 128, node_gate_smem_bytes(d.F), st>>>(na);
       launched();
       float* q = s.qn + (size_t)gi * d.BT * d.N;
       const float* r = pbuf + (size_t)(d.Kst - 1) * d.BT * d.N;            // Horner: r = p_{K-1}; r = r S + p_k
@@ -721,8 +721,8 @@ size_t cell_backward_tc(const gcrnn_cell* cell, const gcrnn_cell_params* p, cons
       na.Kin = d.Kin; na.G = d.G; na.F = d.F; na.N = d.N; na.Kst = d.Kst; na.exact = P > 1; na.B = d.B; na.T = d.T;
       na.v = vhead; na.dA = gr->n_weight_A[gi]; na.dwh = gr->n_head_w[gi]; na.dc0 = dc0;
       GCRNN_CHECK(na.dA && na.dwh, "node-gate gradient buffers missing");
-      node_gate_bwd_kernel<<<(unsigned)std::min<long long>(d.B * (d.N / 128) * (d.F / NG_FC), 148 * 16), 128,
-                             node_gate_smem_bytes(d.F, d.Kst, true), st>>>(na);
+      node_gate_bwd_kernel<<<(unsigned)std::min<long long>(d.B * (d.N / 32), d.sms * (d.F >= 64 ? 1 : 2)), 32 * (d.F / NG_FC),
+                             node_gate_smem_bytes(d.F), st>>>(na);
       launched();
       subcell_h0_path(p->n_weight_B[gi], gr->n_weight_B[gi], gr->n_bias[gi]);
     }

@@ -15,7 +15,7 @@ namespace tc {
 
 constexpr int NG_KG = 8;        // Kin * G taps kept in registers
 constexpr int NG_KMAX = 6;      // head taps
-constexpr int NG_FC = 8;        // features per thread in the backward kernel
+constexpr int NG_FC = 4;        // features per warp in the backward kernel
 
 struct NodeGateArgs {
   const float* A;               // sub-cell input taps [F][KG]
@@ -49,15 +49,28 @@ __device__ __forceinline__ void ng_load_taps(const NodeGateArgs& a, long long b,
   }
 }
 
+// shared-memory weight tables, 8 floats per feature each so that one feature costs two 16-byte broadcast loads per table
+// (scalar loads made these kernels shared-memory-issue-bound: 13 LDS per feature against ~20 arithmetic instructions)
+__device__ __forceinline__ void ng_stage_weights(const NodeGateArgs& a, float* sA, float* sW) {
+  const int KG = a.Kin * a.G;
+  for (int i = threadIdx.x; i < a.F * 8; i += blockDim.x) {
+    const int f = i >> 3, j = i & 7;
+    sA[i] = j < KG ? a.A[f * KG + j] : 0.f;
+    sW[i] = j < a.Kst ? a.wh[j * a.F + f] : 0.f;                     // transposed: [f][k]
+  }
+}
+__device__ __forceinline__ void ng_row8(const float* tab, int f, float* w) {
+  const float4 lo = *reinterpret_cast<const float4*>(tab + f * 8), hi = *reinterpret_cast<const float4*>(tab + f * 8 + 4);
+  w[0] = lo.x; w[1] = lo.y; w[2] = lo.z; w[3] = lo.w; w[4] = hi.x; w[5] = hi.y; w[6] = hi.z; w[7] = hi.w;
+}
+
 // thread <-> (b, n): c0[b][:][n] in registers, loop over t.  Block = 128 nodes of one sample.
 template <int FMAX>
 __global__ void __launch_bounds__(128) node_gate_fwd_kernel(const NodeGateArgs a) {
-  extern __shared__ float ng_sm[];
-  const int KG = a.Kin * a.G;
-  float* sA = ng_sm;                         // [F][NG_KG]
-  float* sW = sA + a.F * NG_KG;              // [Kst][F]
-  for (int i = threadIdx.x; i < a.F * NG_KG; i += blockDim.x) { const int f = i / NG_KG, kg = i - f * NG_KG; sA[i] = kg < KG ? a.A[f * KG + kg] : 0.f; }
-  for (int i = threadIdx.x; i < a.Kst * a.F; i += blockDim.x) sW[i] = a.wh[i];
+  extern __shared__ __align__(16) float ng_sm[];
+  float* sA = ng_sm;                         // [F][8]
+  float* sW = sA + a.F * 8;                  // [F][8]
+  ng_stage_weights(a, sA, sW);
   __syncthreads();
   const int tiles_n = a.N / 128;
   const long long BT = a.B * a.T;
@@ -70,18 +83,20 @@ __global__ void __launch_bounds__(128) node_gate_fwd_kernel(const NodeGateArgs a
     for (long long t = 0; t < a.T; ++t) {
       float z[NG_KG];
       ng_load_taps(a, b, t, n, z);
-      float pk[NG_KMAX];
+      float pk[8];
 #pragma unroll
-      for (int k = 0; k < NG_KMAX; ++k) pk[k] = 0.f;
+      for (int k = 0; k < 8; ++k) pk[k] = 0.f;
 #pragma unroll
       for (int f = 0; f < FMAX; ++f) {
         if (f < a.F) {
+          float wa[8], ww[8];
+          ng_row8(sA, f, wa); ng_row8(sW, f, ww);
           float y = c0[f];
 #pragma unroll
-          for (int kg = 0; kg < NG_KG; ++kg) y = fmaf(sA[f * NG_KG + kg], z[kg], y);
+          for (int kg = 0; kg < NG_KG; ++kg) y = fmaf(wa[kg], z[kg], y);
           const float s = ng_tanh(y, a.exact);
 #pragma unroll
-          for (int k = 0; k < NG_KMAX; ++k) if (k < a.Kst) pk[k] = fmaf(sW[k * a.F + f], s, pk[k]);
+          for (int k = 0; k < NG_KMAX; ++k) pk[k] = fmaf(ww[k], s, pk[k]);
         }
       }
 #pragma unroll
@@ -90,34 +105,34 @@ __global__ void __launch_bounds__(128) node_gate_fwd_kernel(const NodeGateArgs a
   }
 }
 
-// thread <-> (b, n, chunk of NG_FC features): loop over t with the chunk's gradient accumulators in registers; one block reduction and
-// one atomicAdd per parameter and block at the end.  Block = 128 nodes of one (sample, feature chunk).
-__global__ void __launch_bounds__(128) node_gate_bwd_kernel(const NodeGateArgs a) {
-  extern __shared__ float ng_sm[];
+// warp <-> chunk of NG_FC features, lane <-> node: a block of F / NG_FC warps covers every feature of 32 nodes of one sample, so the
+// taps and head signals of a node are read from HBM once (the other warps hit L1).  Loop over t with the chunk's gradient
+// accumulators in registers; they persist over all tiles of the block: one warp reduction and one atomicAdd per parameter at the end.
+__global__ void __launch_bounds__(512, 1) node_gate_bwd_kernel(const NodeGateArgs a) {
+  extern __shared__ __align__(16) float ng_sm[];
   const int KG = a.Kin * a.G;
-  float* sA = ng_sm;                         // [F][NG_KG]
-  float* sW = sA + a.F * NG_KG;              // [Kst][F]
-  float* sR = sW + a.Kst * a.F;              // reduction scratch [4 warps][NG_FC * (NG_KG + NG_KMAX)]
-  for (int i = threadIdx.x; i < a.F * NG_KG; i += blockDim.x) { const int f = i / NG_KG, kg = i - f * NG_KG; sA[i] = kg < KG ? a.A[f * KG + kg] : 0.f; }
-  for (int i = threadIdx.x; i < a.Kst * a.F; i += blockDim.x) sW[i] = a.wh[i];
+  float* sA = ng_sm;                         // [F][8]
+  float* sW = sA + a.F * 8;                  // [F][8]
+  ng_stage_weights(a, sA, sW);
   __syncthreads();
-  const int tiles_n = a.N / 128, chunks = a.F / NG_FC;
+  const int tiles_n = a.N / 32;
   const long long BT = a.B * a.T;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (long long item = blockIdx.x; item < a.B * tiles_n * chunks; item += gridDim.x) {
-    const int fc = (int)(item % chunks);
-    const long long bn = item / chunks, b = bn / tiles_n;
-    const int n = (int)(bn - b * tiles_n) * 128 + threadIdx.x;
-    const int f0 = fc * NG_FC;
-    float c0[NG_FC], dc0[NG_FC], dA[NG_FC][NG_KG], dW[NG_KMAX][NG_FC];
+  const int f0 = warp * NG_FC;
+  float dA[NG_FC][NG_KG], dW[NG_KMAX][NG_FC];
 #pragma unroll
-    for (int j = 0; j < NG_FC; ++j) {
-      c0[j] = __ldg(a.c0 + ((size_t)b * a.F + f0 + j) * a.N + n); dc0[j] = 0.f;
+  for (int j = 0; j < NG_FC; ++j) {
 #pragma unroll
-      for (int kg = 0; kg < NG_KG; ++kg) dA[j][kg] = 0.f;
+    for (int kg = 0; kg < NG_KG; ++kg) dA[j][kg] = 0.f;
 #pragma unroll
-      for (int k = 0; k < NG_KMAX; ++k) dW[k][j] = 0.f;
-    }
+    for (int k = 0; k < NG_KMAX; ++k) dW[k][j] = 0.f;
+  }
+  for (long long item = blockIdx.x; item < a.B * tiles_n; item += gridDim.x) {
+    const long long b = item / tiles_n;
+    const int n = (int)(item - b * tiles_n) * 32 + lane;
+    float c0[NG_FC], dc0[NG_FC];
+#pragma unroll
+    for (int j = 0; j < NG_FC; ++j) { c0[j] = __ldg(a.c0 + ((size_t)b * a.F + f0 + j) * a.N + n); dc0[j] = 0.f; }
     for (long long t = 0; t < a.T; ++t) {
       float z[NG_KG], vk[NG_KMAX];
       ng_load_taps(a, b, t, n, z);
@@ -125,13 +140,15 @@ __global__ void __launch_bounds__(128) node_gate_bwd_kernel(const NodeGateArgs a
       for (int k = 0; k < NG_KMAX; ++k) vk[k] = k < a.Kst ? __ldg(a.v + ((size_t)k * BT + b * a.T + t) * a.N + n) : 0.f;
 #pragma unroll
       for (int j = 0; j < NG_FC; ++j) {
+        float wa[8], ww[8];
+        ng_row8(sA, f0 + j, wa); ng_row8(sW, f0 + j, ww);
         float y = c0[j];
 #pragma unroll
-        for (int kg = 0; kg < NG_KG; ++kg) y = fmaf(sA[(f0 + j) * NG_KG + kg], z[kg], y);
+        for (int kg = 0; kg < NG_KG; ++kg) y = fmaf(wa[kg], z[kg], y);
         const float s = ng_tanh(y, a.exact);
         float ds = 0.f;
 #pragma unroll
-        for (int k = 0; k < NG_KMAX; ++k) if (k < a.Kst) { ds = fmaf(sW[k * a.F + f0 + j], vk[k], ds); dW[k][j] = fmaf(vk[k], s, dW[k][j]); }
+        for (int k = 0; k < NG_KMAX; ++k) { ds = fmaf(ww[k], vk[k], ds); dW[k][j] = fmaf(vk[k], s, dW[k][j]); }
         const float dps = ds * (1.f - s * s);
         dc0[j] += dps;
 #pragma unroll
@@ -140,42 +157,26 @@ __global__ void __launch_bounds__(128) node_gate_bwd_kernel(const NodeGateArgs a
     }
 #pragma unroll
     for (int j = 0; j < NG_FC; ++j) a.dc0[((size_t)b * a.F + f0 + j) * a.N + n] = dc0[j];
-    // block reduction of the parameter gradients
-    constexpr int PER = NG_FC * (NG_KG + NG_KMAX);
+  }
 #pragma unroll
-    for (int j = 0; j < NG_FC; ++j) {
+  for (int j = 0; j < NG_FC; ++j) {
 #pragma unroll
-      for (int kg = 0; kg < NG_KG; ++kg) {
-        float v = dA[j][kg];
+    for (int kg = 0; kg < NG_KG; ++kg) {
+      float v = dA[j][kg];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) sR[warp * PER + j * NG_KG + kg] = v;
-      }
-#pragma unroll
-      for (int k = 0; k < NG_KMAX; ++k) {
-        float v = dW[k][j];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) sR[warp * PER + NG_FC * NG_KG + k * NG_FC + j] = v;
-      }
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0 && kg < KG) atomicAdd(a.dA + (size_t)(f0 + j) * KG + kg, v);
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < PER; i += blockDim.x) {
-      const float v = sR[i] + sR[PER + i] + sR[2 * PER + i] + sR[3 * PER + i];
-      if (i < NG_FC * NG_KG) {
-        const int j = i / NG_KG, kg = i - j * NG_KG;
-        if (kg < KG) atomicAdd(a.dA + (size_t)(f0 + j) * KG + kg, v);
-      } else {
-        const int r = i - NG_FC * NG_KG, k = r / NG_FC, j = r - k * NG_FC;
-        if (k < a.Kst) atomicAdd(a.dwh + (size_t)k * a.F + f0 + j, v);
-      }
+#pragma unroll
+    for (int k = 0; k < NG_KMAX; ++k) {
+      float v = dW[k][j];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0 && k < a.Kst) atomicAdd(a.dwh + (size_t)k * a.F + f0 + j, v);
     }
-    __syncthreads();
   }
 }
-inline size_t node_gate_smem_bytes(int F, int Kst, bool bwd) {
-  return ((size_t)F * NG_KG + (size_t)Kst * F + (bwd ? 4 * NG_FC * (NG_KG + NG_KMAX) : 0)) * sizeof(float);
-}
+inline size_t node_gate_smem_bytes(int F) { return (size_t)F * 16 * sizeof(float); }
 
 // Horner step on scalar node signals: out = shifted + p  (fp32, n4 float4s), or the last one: q = sigmoid(shifted + p + c)
 __global__ void node_head_add_kernel(const float4* __restrict__ shifted, const float4* __restrict__ p, float4* __restrict__ out, long long n4,
