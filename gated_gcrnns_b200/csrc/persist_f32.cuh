@@ -122,7 +122,7 @@ __device__ __forceinline__ float block_sum(float v, float* red) {      // red: >
 
 // ---- blocked inner loops ------------------------------------------------------------------------------------------------
 // Every loop below is register-blocked so that one shared-memory load feeds several FMAs (the first version issued two loads
-// per FMA and ran at 40 % issue utilisation with 16 warps: profiles/r02_ncu_persist_*): NB = 4 consecutive nodes per thread with
+// per FMA and ran at 40 % issue utilisation with 16 warps: profiles/r02_ncu_persist_*.raw.csv): NB = 4 consecutive nodes per thread with
 // 16-byte loads where the contraction runs over rows (needs N % 4 == 0), RB = 4 rows per thread where a gather list is shared.
 
 // out[r][n] = sum_p val[p] in[r][idx[p]], p in [ptr[n], ptr[n+1])   (rows r < R; in / out in shared memory, [R][N])
