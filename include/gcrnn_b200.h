@@ -148,8 +148,9 @@ int gcrnn_cell_destroy(gcrnn_cell* c);
 /* Execution paths of the fp32 sparse precision (same results within the stated fp32 tolerance):
  *   GENERIC  per-op kernels, any shape / gating mode, supports dX;
  *   PERSIST  persistent fused recurrence for small graphs (csrc/persist_f32.cuh): ONE launch runs the whole sequence of every sample
- *            with the shift operator, the taps, the time-gate weights and h_t on chip across all T steps, ONE launch the reverse
- *            sweep; E == 1, no spatial gating, no dX, sizes that fit one SM's shared memory (the reference's own N = 80 config);
+ *            with the shift operator, the taps, every gate's weights (time, node or edge gates; for edge gates also the attention
+ *            pattern of S + I) and h_t on chip across all T steps, ONE launch the reverse sweep; E == 1, no dX, sizes that fit one
+ *            SM's shared memory (the reference's own N = 80 and N = 59 configurations);
  *   NODE32   fused edge-gated kernels for F == 32, one warp per (sample, node) (csrc/sp32_kernels.cuh); a dX request makes
  *            backward run the generic sweep on the generic prefix of the saved state.
  * Options (per cell handle, used from one host thread at a time; the tuning switches listed above are set the same way):
