@@ -131,6 +131,7 @@ struct gcrnn_cell {
   mutable int forced_path = -1;   // -1: choose automatically; otherwise GCRNN_PATH_*
   mutable int last_path = 0;      // path taken by the last forward
   mutable int fwd_v2_mask = 63;   // fused sparse path: stage generations the last forward used (its backward follows them)
+  mutable int fwd_reordered = 0;  // fused sparse path: the last forward ran on the graph's renumbered copy (its saved state is in that order)
   gcrnn::Options opt;             // tuning switches of this handle (gcrnn_cell_set_option)
   mutable void* graph_cache = nullptr;   // api.cu: CUDA graphs of small (launch-bound) fp32 forward / backward calls
 };

@@ -543,11 +543,13 @@ size_t cell_forward_e32(const gcrnn_cell* cell, const gcrnn_cell_params* p, cons
                         cudaStream_t st) {
   const CellDims d = dims_of(cell, B, T);
   Arena a(ws, wsb);
-  const gcrnn_graph* view = locality_view(cell->g);              // the graph itself, or its renumbered copy (graph.cu)
+  // the graph itself, or its renumbered copy (graph.cu).  A caller that will ask for dX gets the plain order: dX comes from the
+  // generic reverse sweep, which reads this forward's saved state in the caller's numbering
+  const gcrnn_graph* view = cell->need_dx ? cell->g : locality_view(cell->g);
   const NodeMap perm = node_map(cell->g, view);
   Ctx c{view, st, a.dry()};
   t_v2_mask = normalise_v2(opt().sparse_v2);
-  if (ws != nullptr) cell->fwd_v2_mask = t_v2_mask;
+  if (ws != nullptr) { cell->fwd_v2_mask = t_v2_mask; cell->fwd_reordered = view != cell->g; }
   Saved s; Saved32 x;
   {
     Arena sa(saved, savedb);
@@ -679,7 +681,7 @@ size_t cell_backward_e32(const gcrnn_cell* cell, const gcrnn_cell_params* p, con
                          const gcrnn_cell_params* gr, float* dh0, void* ws, size_t wsb, int64_t B, int64_t T, cudaStream_t st) {
   const CellDims d = dims_of(cell, B, T);
   Arena a(ws, wsb);
-  const gcrnn_graph* view = locality_view(cell->g);
+  const gcrnn_graph* view = cell->fwd_reordered ? locality_view(cell->g) : cell->g;      // the numbering the forward's saved state is in
   const NodeMap perm = node_map(cell->g, view);
   Ctx c{view, st, a.dry()};
   t_v2_mask = (normalise_v2(opt().sparse_v2) & ~(V2_AGG | V2_ROWS)) | (cell->fwd_v2_mask & (V2_AGG | V2_ROWS));
@@ -732,7 +734,7 @@ void debug_edge_relu_masks(const gcrnn_cell* cell, const void* saved, size_t sav
   const CellDims d = dims_of(cell, B, T);
   Saved s; Saved32 x;
   { Arena sa(const_cast<void*>(saved), savedb); s.layout(sa, d); x.layout(sa, d); }
-  const gcrnn_graph* view = locality_view(cell->g);
+  const gcrnn_graph* view = cell->fwd_reordered ? locality_view(cell->g) : cell->g;
   e32_decode_masks_k<<<grid1d(d.TB * d.N, 256), 256, 0, st>>>(x.masks, view != cell->g ? cell->g->perm : nullptr, out, d.N, B, T);
   check_launch();
 }
@@ -945,6 +947,8 @@ size_t cell_backward_f32(const gcrnn_cell* cell, const gcrnn_cell_params* p, con
     // generic sweep then runs on the generic prefix of what NODE32's forward saved.
     const int path = pick_path(cell);
     if (path == GCRNN_PATH_NODE32 && !dX) return cell_backward_e32(cell, p, dH, saved, savedb, gr, dh0, ws, wsb, B, T, st);
+    GCRNN_CHECK(!(path == GCRNN_PATH_NODE32 && ws != nullptr && cell->fwd_reordered),
+                "dX requested from a forward that ran on the renumbered graph: set the cell option \"need_dx\" before the forward");
     if (path == GCRNN_PATH_PERSIST) {
       GCRNN_CHECK(ws == nullptr || dX == nullptr, "the persistent small-graph path does not produce dX");
       return cell_backward_persist(cell, p, X, h0, H, dH, saved, savedb, gr, dh0, ws, B, T, st);

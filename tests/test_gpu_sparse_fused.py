@@ -210,6 +210,29 @@ def test_library_reorder_decision_and_equivalence():
     assert gg.graph.get(S, DEV, keep_dense=False).get_option('reordered') == 0, 'a Hilbert-numbered graph needs no renumbering'
 
 
+def test_library_reorder_with_input_gradients():
+    """A caller that wants dX: the forward then stays in the caller's numbering (dX comes from the generic reverse sweep, which reads
+    the forward's saved state), so the results must equal those of a graph whose renumbering is switched off."""
+    N, F_, K, T, B = 8192, 32, 3, 2, 2
+    res = {}
+    for mode in (0, 1):
+        rp, ci, va, _ = gg.graphs.knn_csr_gpu(N, 16, seed=5, device=DEV, reorder=False)
+        S = gg.graphs.csr_to_torch_sparse(rp, ci, va, N)
+        torch.manual_seed(0)
+        cell = gg.GGCRNNCell(1, F_, K, K, torch.tanh, False, 'edge', 1, True)
+        cell.addGSO(S)
+        cell = cell.to(DEV)
+        gg.graph.get(cell.S, DEV, keep_dense=False).set_option('reorder', mode)
+        torch.manual_seed(1)
+        X = torch.randn(B, T, 1, N, device=DEV, requires_grad=True)
+        h0 = (0.1 * torch.randn(B, F_, N, device=DEV)).requires_grad_(True)
+        H = cell(X, h0)
+        (H * torch.randn(B, T, F_, N, device=DEV, generator=torch.Generator(device=DEV).manual_seed(2))).sum().backward()
+        res[mode] = [H.detach(), X.grad.clone(), h0.grad.clone()] + [p.grad.clone() for p in cell.parameters() if p.grad is not None]
+    for i, (a, b) in enumerate(zip(res[1], res[0])):
+        assert relerr(a, b) < (5e-6 if i == 0 else TOL_GRAD), (i, relerr(a, b))
+
+
 def test_fused_large_knn_properties():
     """cfg5-like sizes (N = 20000 here): finite outputs, |h| <= 1, and batch-sample independence (sample b of a
     batch equals the same sample run alone), which a mis-indexed gather or a cross-sample race would break."""
