@@ -537,7 +537,8 @@ size_t cell_backward_tc(const gcrnn_cell* cell, const gcrnn_cell_params* p, cons
   __nv_bfloat16* hb0 = a.get<__nv_bfloat16>((size_t)d.R * d.LD);
   __nv_bfloat16* WTb = a.get<__nv_bfloat16>(wbuf);
   float* part = a.get<float>((size_t)max_sms * d.Kst * d.F * d.F);
-  const bool fused = opt().bwd_fused && d.F == 64 && d.Kin * d.G <= (P > 1 ? 7 : 8) && d.Kst <= 6 && d.N % 128 == 0 && bf_stages(P, d.Kst) >= 2 && !d.node;
+  // node gates and input gradients take the unfused reverse step (tap TAP_BWD + dpre_kernel + weight-gradient kernel)
+  const bool fused = opt().bwd_fused && d.F == 64 && d.Kin * d.G <= (P > 1 ? 7 : 8) && d.Kst <= 6 && d.N % 128 == 0 && bf_stages(P, d.Kst) >= 2 && !d.node && !dX;
   const int zs_split = P > 1;       // Zs tiles carry hi rows 0..7 and residual rows 8..15
   __nv_bfloat16* Zs = fused ? a.get<__nv_bfloat16>((size_t)d.BT * BF_ZROWS * d.N) : nullptr;
   float* partA = fused ? a.get<float>((size_t)max_sms * 64 * BF_ZROWS) : nullptr;
@@ -550,9 +551,15 @@ size_t cell_backward_tc(const gcrnn_cell* cell, const gcrnn_cell_params* p, cons
   float* dlin = d.node ? a.get<float>((size_t)2 * d.BT * d.N) : nullptr;
   float* vhead = d.node ? a.get<float>((size_t)d.Kst * d.BT * d.N) : nullptr;
   __nv_bfloat16* rb = d.node ? a.get<__nv_bfloat16>((size_t)d.BT * d.LD) : nullptr;
+  // input gradient (dX != null; workspace sized for it whenever the query says so): per-tap contributions dxk [Kin][RX][N], then
+  // dX = dxk_0 + (dxk_1 + (... dxk_{K-1} S^T ...) S^T) S^T by Horner with shift GEMMs on the RX = B*T*G rows
+  const bool want_dx = dX != nullptr || (a.dry() && cell->need_dx);
+  float* dxk = want_dx ? a.get<float>((size_t)d.Kin * d.RX * d.N) : nullptr;
+  float* dxtmp = want_dx && d.Kin > 1 ? a.get<float>((size_t)d.RX * d.N) : nullptr;
+  __nv_bfloat16* dxb = want_dx && d.Kin > 1 ? a.get<__nv_bfloat16>((size_t)d.RX * d.LD) : nullptr;
   if (a.dry()) return a.off;
-  GCRNN_CHECK(dX == nullptr, "the tensor-core path does not produce dX (the reference never asks for it: train_rnn.py:256); "
-                             "use precision fp32 for input gradients");
+  GCRNN_CHECK(dX == nullptr || (dxk != nullptr && d.Kin * d.G <= DP_KG), "tensor-core input gradients need Kin*G <= %d", DP_KG);
+  if (dX) CUDA_OK(cudaMemsetAsync(dxk, 0, (size_t)d.Kin * d.RX * d.N * sizeof(float), st));
   d.sms = num_sms(g->device);
   GCRNN_CHECK(d.sms <= max_sms, "unexpected SM count %d", d.sms);
   const long long FN = (long long)d.F * d.N, GN = (long long)d.G * d.N;
@@ -584,7 +591,7 @@ size_t cell_backward_tc(const gcrnn_cell* cell, const gcrnn_cell_params* p, cons
 
   // ---- reverse-time sweep -------------------------------------------------------------------------------------------
   CUDA_OK(cudaMemsetAsync(red, 0, (size_t)d.R * 8 * sizeof(float), st));
-  const bool can_fuse = d.Kin * d.G <= 7 && !d.node;
+  const bool can_fuse = d.Kin * d.G <= 7 && !d.node && !dX;
   auto run_dpre = [&](long long t, const float* dhrec_in, __nv_bfloat16* v0_out) {
     DpreArgs da{};
     da.dH = dv.ptr(t); da.dH_bstride = dv.bstride(t); da.Ht = H + t * FN; da.H_bstride = d.T * FN;
@@ -598,7 +605,14 @@ size_t cell_backward_tc(const gcrnn_cell* cell, const gcrnn_cell_params* p, cons
       da.qi = s.qn + t * d.N; da.qf = s.qn + (size_t)d.BT * d.N + t * d.N; da.q_bstride = d.T * d.N;
       da.dlin_i = dlin + t * d.N; da.dlin_f = dlin + (size_t)d.BT * d.N + t * d.N;
     }
-    dpre_kernel<<<(unsigned)std::min<long long>(d.B * (d.F / DP_FC), 148 * 32), 256, d.node ? 2 * d.N * sizeof(float) : 0, st>>>(da);
+    if (dX) { da.dxk = dxk + t * GN; da.dxk_kstride = d.RX * d.N; da.dxk_bstride = d.T * GN; }
+    const size_t dsm = ((d.node ? 2 * d.N : 0) + (dX ? (size_t)d.Kin * d.G * d.N : 0)) * sizeof(float);
+    if (dsm > 48 * 1024) {
+      static DeviceOnce once;
+      if (once.first()) CUDA_OK(cudaFuncSetAttribute(dpre_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      GCRNN_CHECK(dsm <= 100 * 1024, "dpre kernel: Kin*G*N too large for shared memory staging (%zu B)", dsm);
+    }
+    dpre_kernel<<<(unsigned)std::min<long long>(d.B * (d.F / DP_FC), 148 * 32), 256, dsm, st>>>(da);
     launched();
   };
   __nv_bfloat16* v0cur = vb0; __nv_bfloat16* v0nxt = vb0b;
@@ -701,6 +715,14 @@ size_t cell_backward_tc(const gcrnn_cell* cell, const gcrnn_cell_params* p, cons
       ga.dWg = gr->t_mlp_w[gi]; ga.dc0 = dc0; ga.dA = gr->t_weight_A[gi];
       GCRNN_CHECK(ga.dWg && ga.dA, "time-gate gradient buffers missing");
       gate_launch(true, ga, d, st);
+      if (dX) {                                                              // the gate sub-cell's own input-filter path into dX
+        GateDxArgs gx{};
+        gx.g.A = p->t_weight_A[gi]; gx.g.X = X; gx.g.zx = s.zx; gx.g.zx_kstride = d.RX * d.N; gx.g.c0 = c0;
+        gx.g.Kin = d.Kin; gx.g.G = d.G; gx.g.F = d.F; gx.g.N = d.N; gx.g.Kst = d.Kst; gx.g.exact = P > 1; gx.g.B = d.B; gx.g.T = d.T;
+        gx.Wg = p->t_mlp_w[gi]; gx.dl = dl; gx.dxk = dxk; gx.dxk_kstride = d.RX * d.N;
+        gate_dx_kernel<0><<<(unsigned)std::min<long long>(d.B * (d.N / 128), 148 * 16), 128, node_gate_smem_bytes(d.F), st>>>(gx);
+        launched();
+      }
       subcell_h0_path(p->t_weight_B[gi], gr->t_weight_B[gi], gr->t_bias[gi]);
     }
   }
@@ -724,10 +746,31 @@ size_t cell_backward_tc(const gcrnn_cell* cell, const gcrnn_cell_params* p, cons
       node_gate_bwd_kernel<<<(unsigned)std::min<long long>(d.B * (d.N / 32), d.sms * (d.F >= 64 ? 1 : 2)), 32 * (d.F / NG_FC),
                              node_gate_smem_bytes(d.F), st>>>(na);
       launched();
+      if (dX) {
+        GateDxArgs gx{};
+        gx.g = na; gx.dxk = dxk; gx.dxk_kstride = d.RX * d.N;
+        gate_dx_kernel<1><<<(unsigned)std::min<long long>(d.B * (d.N / 128), 148 * 16), 128, node_gate_smem_bytes(d.F), st>>>(gx);
+        launched();
+      }
       subcell_h0_path(p->n_weight_B[gi], gr->n_weight_B[gi], gr->n_bias[gi]);
     }
   }
   if (dh0) CUDA_OK(cudaMemcpyAsync(dh0, dhrec, (size_t)d.R * d.N * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (dX) {                                                           // Horner over the input taps with S^T
+    const long long n4 = d.RX * (d.N / 4);
+    const unsigned eg = (unsigned)std::min<long long>((n4 + 255) / 256, 148 * 16);
+    const float* r = dxk + (size_t)(d.Kin - 1) * d.RX * d.N;
+    for (int k = d.Kin - 2; k >= 0; --k) {
+      cvt_bf16(r, dxb, d.RX, d.N, P, st);
+      shift_gemm(g, true, dxb, d.RX, P, nullptr, P, dxtmp, st);
+      float* out = k == 0 ? dX : dxk + (size_t)(d.Kin - 1) * d.RX * d.N;           // the last tap's slab doubles as the accumulator
+      node_head_add_kernel<<<eg, 256, 0, st>>>(reinterpret_cast<const float4*>(dxtmp), reinterpret_cast<const float4*>(dxk + (size_t)k * d.RX * d.N),
+                                              reinterpret_cast<float4*>(out), n4, nullptr, 0);
+      launched();
+      r = out;
+    }
+    if (d.Kin == 1) CUDA_OK(cudaMemcpyAsync(dX, dxk, (size_t)d.RX * d.N * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  }
   return a.off;
 }
 

@@ -256,6 +256,10 @@ struct DpreArgs {
   // of dynamic shared memory.
   const float* qi; const float* qf; long long q_bstride;
   float* dlin_i; float* dlin_f;
+  // input gradient: dxk[kg][b][n] += sum_f A[f][kg] gi q_i dpre[f][n] at dxk + kg * dxk_kstride + b * dxk_bstride + g_row * N + n
+  // (the rows of one [B,T,G,N] layout, like zx); the caller shifts tap k by (S^T)^k afterwards.  Needs Kin*G <= DP_KG and
+  // Kin*G*N more floats of dynamic shared memory (after the node gates' 2N, when present).
+  float* dxk; long long dxk_kstride, dxk_bstride;
 };
 constexpr int DP_FC = 8;      // features (warps) per CTA
 constexpr int DP_KG = 8;      // (k, g) pairs handled per pass
@@ -268,8 +272,10 @@ __global__ void __launch_bounds__(256) dpre_kernel(const DpreArgs a) {
   const int fgroups = a.F / DP_FC;
   const int N4 = a.N / 4;
   const bool node = a.qi != nullptr;
-  if (node) {
-    for (int i = threadIdx.x; i < 2 * a.N; i += blockDim.x) s_dl[i] = 0.f;
+  const bool wantdx = a.dxk != nullptr;
+  float* s_dx = s_dl + (node ? 2 * a.N : 0);      // [KG][N]
+  if (node || wantdx) {
+    for (int i = threadIdx.x; i < (node ? 2 * a.N : 0) + (wantdx ? KG * a.N : 0); i += blockDim.x) s_dl[i] = 0.f;
     __syncthreads();
   }
   for (long long item = blockIdx.x; item < a.B * fgroups; item += gridDim.x) {
@@ -322,6 +328,15 @@ __global__ void __launch_bounds__(256) dpre_kernel(const DpreArgs a) {
             ax.x = fmaf(Af[j], z.x, ax.x); ax.y = fmaf(Af[j], z.y, ax.y); ax.z = fmaf(Af[j], z.z, ax.z); ax.w = fmaf(Af[j], z.w, ax.w);
           }
         }
+        if (wantdx) {
+#pragma unroll
+          for (int j = 0; j < DP_KG; ++j)
+            if (kg0 + j < KG) {
+              float* sx = s_dx + (size_t)(kg0 + j) * a.N + 4 * i;
+              const float w = vgi * Af[j];
+              atomicAdd(sx, w * dq.x); atomicAdd(sx + 1, w * dq.y); atomicAdd(sx + 2, w * dq.z); atomicAdd(sx + 3, w * dq.w);
+            }
+        }
         if (node) {
           const float hx[4] = {hv.x, hv.y, hv.z, hv.w}, dx[4] = {d.x, d.y, d.z, d.w}, axx[4] = {ax.x, ax.y, ax.z, ax.w};
           const float qix[4] = {qi4.x, qi4.y, qi4.z, qi4.w}, qfx[4] = {qf4.x, qf4.y, qf4.z, qf4.w};
@@ -362,6 +377,13 @@ __global__ void __launch_bounds__(256) dpre_kernel(const DpreArgs a) {
         atomicAdd(a.dlin_i + b * a.q_bstride + i, s_dl[i]);
         atomicAdd(a.dlin_f + b * a.q_bstride + i, s_dl[a.N + i]);
         s_dl[i] = 0.f; s_dl[a.N + i] = 0.f;
+      }
+    }
+    if (wantdx) {
+      for (int i = threadIdx.x; i < KG * a.N; i += blockDim.x) {
+        const int kg = i / a.N, n = i - kg * a.N, k = kg / a.G, g = kg - k * a.G;
+        atomicAdd(a.dxk + (size_t)k * a.dxk_kstride + b * a.dxk_bstride + (size_t)g * a.N + n, s_dx[i]);
+        s_dx[i] = 0.f;
       }
     }
     __syncthreads();

@@ -178,6 +178,89 @@ __global__ void __launch_bounds__(512, 1) node_gate_bwd_kernel(const NodeGateArg
 }
 inline size_t node_gate_smem_bytes(int F) { return (size_t)F * 16 * sizeof(float); }
 
+// Input gradient through a gate sub-cell (only when the caller asks for dX): dxk[k][(b,t,g)][n] += sum_f A_s[f][k,g] d pre_s[f][n] with
+//   time gate: d pre_s = dl[b,t] Wg[f][n] (1 - u^2)            node gate: d pre_s = (sum_k wh[k][f] v_k[n]) (1 - u^2)
+// u recomputed once more (this path is rare: a cell that is not the first layer).  thread <-> (b, n), features in halves of 32 so that
+// c0 / Wg stay in registers; a thread owns its (b, t, n) entries of dxk: plain read-modify-write, no atomics.
+struct GateDxArgs {
+  NodeGateArgs g;               // A, X, zx, c0, sizes; node mode: wh, v
+  const float* Wg;              // time mode: [F][N]
+  const float* dl;              // time mode: [B][T]
+  float* dxk; long long dxk_kstride;     // [Kin][RX][N]
+};
+template <int MODE>             // 0: time gate, 1: node gate
+__global__ void __launch_bounds__(128) gate_dx_kernel(const GateDxArgs q) {
+  const NodeGateArgs& a = q.g;
+  extern __shared__ __align__(16) float ng_sm[];
+  float* sA = ng_sm;
+  float* sW = sA + a.F * 8;
+  if (MODE == 1) ng_stage_weights(a, sA, sW);
+  else {
+    const int KG = a.Kin * a.G;
+    for (int i = threadIdx.x; i < a.F * 8; i += blockDim.x) { const int f = i >> 3, j = i & 7; sA[i] = j < KG ? a.A[f * KG + j] : 0.f; }
+  }
+  __syncthreads();
+  constexpr int FH = 32;
+  const int tiles_n = a.N / 128, KG = a.Kin * a.G;
+  const long long BT = a.B * a.T;
+  for (long long item = blockIdx.x; item < a.B * tiles_n; item += gridDim.x) {
+    const long long b = item / tiles_n;
+    const int n = (int)(item - b * tiles_n) * 128 + threadIdx.x;
+    for (int fh = 0; fh < a.F; fh += FH) {
+      float c0[FH], wg[FH];
+#pragma unroll
+      for (int j = 0; j < FH; ++j) {
+        const bool ok = fh + j < a.F;
+        c0[j] = ok ? __ldg(a.c0 + ((size_t)b * a.F + fh + j) * a.N + n) : 0.f;
+        wg[j] = (MODE == 0 && ok) ? __ldg(q.Wg + (size_t)(fh + j) * a.N + n) : 0.f;
+      }
+      for (long long t = 0; t < a.T; ++t) {
+        float z[NG_KG], vk[NG_KMAX], acc[NG_KG];
+        ng_load_taps(a, b, t, n, z);
+#pragma unroll
+        for (int kg = 0; kg < NG_KG; ++kg) acc[kg] = 0.f;
+        float dlv = 0.f;
+        if (MODE == 0) dlv = __ldg(q.dl + b * a.T + t);
+        else {
+#pragma unroll
+          for (int k = 0; k < NG_KMAX; ++k) vk[k] = k < a.Kst ? __ldg(a.v + ((size_t)k * BT + b * a.T + t) * a.N + n) : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < FH; ++j) {
+          if (fh + j < a.F) {
+            float wa[8];
+            ng_row8(sA, fh + j, wa);
+            float y = c0[j];
+#pragma unroll
+            for (int kg = 0; kg < NG_KG; ++kg) y = fmaf(wa[kg], z[kg], y);
+            const float u = ng_tanh(y, a.exact);
+            float ds;
+            if (MODE == 0) ds = dlv * wg[j];
+            else {
+              float ww[8];
+              ng_row8(sW, fh + j, ww);
+              ds = 0.f;
+#pragma unroll
+              for (int k = 0; k < NG_KMAX; ++k) ds = fmaf(ww[k], vk[k], ds);
+            }
+            const float dps = ds * (1.f - u * u);
+#pragma unroll
+            for (int kg = 0; kg < NG_KG; ++kg) acc[kg] = fmaf(wa[kg], dps, acc[kg]);
+          }
+        }
+#pragma unroll
+        for (int kg = 0; kg < NG_KG; ++kg) {
+          if (kg < KG) {
+            const int k = kg / a.G, g = kg - k * a.G;
+            float* o = q.dxk + (size_t)k * q.dxk_kstride + ((size_t)(b * a.T + t) * a.G + g) * a.N + n;
+            *o += acc[kg];
+          }
+        }
+      }
+    }
+  }
+}
+
 // Horner step on scalar node signals: out = shifted + p  (fp32, n4 float4s), or the last one: q = sigmoid(shifted + p + c)
 __global__ void node_head_add_kernel(const float4* __restrict__ shifted, const float4* __restrict__ p, float4* __restrict__ out, long long n4,
                                      const float* __restrict__ c, int sigmoid) {

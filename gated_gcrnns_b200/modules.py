@@ -223,8 +223,8 @@ class GGCRNNCell(nn.Module):
             return f'Kin*G={self.Kin * self.G} (<= 32)'
         if not 1 <= self.Kst <= 5 or self.Kst * self.F > 384:
             return f'Kst={self.Kst} (<= 5)'
-        if need_dx:
-            return 'X requires grad (the tensor-core backward does not produce dX)'
+        if need_dx and self.Kin * self.G > 8:
+            return f'X requires grad with Kin*G={self.Kin * self.G} (input gradients on the tensor-core path need <= 8)'
         return None
 
     def _precision_for(self, device, need_dx=False):

@@ -207,6 +207,37 @@ def test_tc_node_gated_cell_matches_fp32_path(prec, tg, N, F, K, T, B, G, bias):
     assert not bad, errs
 
 
+@pytest.mark.parametrize('prec', ['bf16', 'bf16x2'])
+@pytest.mark.parametrize('tg,sg', [(False, None), (True, None), (True, 'node')])
+@pytest.mark.parametrize('N,F,K,T,B,G', [(256, 32, 3, 4, 6, 1), (512, 64, 5, 3, 4, 1), (256, 16, 4, 3, 5, 2), (256, 32, 1, 2, 4, 1)])
+def test_tc_input_gradients_match_fp32_path(prec, tg, sg, N, F, K, T, B, G):
+    """dX on the tensor-core path (a cell that is not the first layer): per-tap contributions from the reverse sweep, then Horner with
+    S^T as shift GEMMs on the B*T*G rows.  Against the exact fp32 path, together with every other gradient."""
+    S = gg.graphs.dense_random(N, 0.3, seed=1)
+    torch.manual_seed(3)
+    X0, h0, dH = torch.randn(B, T, G, N, device=DEV), 0.3 * torch.randn(B, F, N, device=DEV), torch.randn(B, T, F, N, device=DEV)
+    out = {}
+    try:
+        for pr in ('fp32', prec):
+            cell = _make_cell(S, G, F, K, tg, pr, sg=sg)
+            X = X0.clone().requires_grad_(True)
+            hh = h0.clone().requires_grad_(True)
+            H = cell(X, hh)
+            (H * dH).sum().backward()
+            out[pr] = (H.detach(), {k: v.grad for k, v in cell.named_parameters()}, hh.grad, X.grad)
+    finally:
+        gg.set_precision('fp32')
+    H32, g32, dh32, dx32 = out['fp32']
+    Hb, gb, dhb, dxb = out[prec]
+    errs = {'H': _relerr(Hb, H32), 'dh0': _relerr(dhb, dh32), 'dX': _relerr(dxb, dx32)}
+    errs.update(_grad_errs(gb, g32))
+    _log(f'tc-dX-vs-fp32 {prec}', dict(tg=tg, sg=sg, N=N, F=F, K=K, T=T, B=B, G=G), {k: f'{v:.2e}' for k, v in errs.items()})
+    tol = TC_TOL[prec]
+    assert errs['H'] < tol['H'], errs
+    bad = {k: v for k, v in errs.items() if k != 'H' and v > tol['G']}
+    assert not bad, errs
+
+
 def test_tc_auto_precision_takes_node_gated_dense_cells():
     """precision 'auto' picks the split-bf16 tensor-core path for a cfg3-shaped node-gated cell and keeps fp32 for an edge-gated one."""
     S = gg.graphs.dense_random(256, 0.3, seed=1)
