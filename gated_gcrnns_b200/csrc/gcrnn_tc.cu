@@ -248,10 +248,14 @@ template <int KG>
 static void bwd_fused_launch_kg(const CUtensorMap& tm0, const CUtensorMap& tmc, const CUtensorMap& tmH, const CUtensorMap& tmZ,
                                 const CUtensorMap& tmW, const BwdFusedArgs& a, int grid, cudaStream_t st) {
   static DeviceOnce once;
-  if (once.first()) CUDA_OK(cudaFuncSetAttribute(bwd_fused_kernel<KG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  if (once.first()) {
+    CUDA_OK(cudaFuncSetAttribute(bwd_fused_kernel<KG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_OK(cudaFuncSetAttribute(bwd_fused_kernel<KG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  }
   const int smem = bf_smem_bytes(a.P, a.KB, a.stages);
   GCRNN_CHECK(smem <= 227 * 1024, "fused backward step: shared memory budget exceeded (%d B)", smem);
-  bwd_fused_kernel<KG><<<grid, BF_THREADS, smem, st>>>(tm0, tmc, tmH, tmZ, tmW, a);
+  if (a.qin || (a.last && a.dlin_i)) bwd_fused_kernel<KG, true><<<grid, BF_THREADS, smem, st>>>(tm0, tmc, tmH, tmZ, tmW, a);
+  else bwd_fused_kernel<KG, false><<<grid, BF_THREADS, smem, st>>>(tm0, tmc, tmH, tmZ, tmW, a);
 }
 // pair-stage ring depth that fits 227 KB next to P weight planes of K blocks
 static int bf_stages(int P, int K) {
@@ -537,11 +541,13 @@ size_t cell_backward_tc(const gcrnn_cell* cell, const gcrnn_cell_params* p, cons
   __nv_bfloat16* hb0 = a.get<__nv_bfloat16>((size_t)d.R * d.LD);
   __nv_bfloat16* WTb = a.get<__nv_bfloat16>(wbuf);
   float* part = a.get<float>((size_t)max_sms * d.Kst * d.F * d.F);
-  // node gates and input gradients take the unfused reverse step (tap TAP_BWD + dpre_kernel + weight-gradient kernel)
-  const bool fused = opt().bwd_fused && d.F == 64 && d.Kin * d.G <= (P > 1 ? 7 : 8) && d.Kst <= 6 && d.N % 128 == 0 && bf_stages(P, d.Kst) >= 2 && !d.node && !dX;
+  // input gradients take the unfused reverse step (tap TAP_BWD + dpre_kernel + weight-gradient kernel)
+  // (the workspace query passes a dX flag whenever ANY input gradient is wanted: buffers are sized for both variants)
+  const bool fusable = opt().bwd_fused && d.F == 64 && d.Kin * d.G <= (P > 1 ? 7 : 8) && d.Kst <= 6 && d.N % 128 == 0 && bf_stages(P, d.Kst) >= 2;
+  const bool fused = fusable && !dX;
   const int zs_split = P > 1;       // Zs tiles carry hi rows 0..7 and residual rows 8..15
-  __nv_bfloat16* Zs = fused ? a.get<__nv_bfloat16>((size_t)d.BT * BF_ZROWS * d.N) : nullptr;
-  float* partA = fused ? a.get<float>((size_t)max_sms * 64 * BF_ZROWS) : nullptr;
+  __nv_bfloat16* Zs = fusable ? a.get<__nv_bfloat16>((size_t)d.BT * BF_ZROWS * d.N) : nullptr;
+  float* partA = fusable ? a.get<float>((size_t)max_sms * 64 * BF_ZROWS) : nullptr;
   float* zslab = cell->dh_last_only ? a.get<float>((size_t)d.F * d.N) : nullptr;
   float *dgt = nullptr, *c0 = nullptr, *dc0 = nullptr, *dl = nullptr;
   __nv_bfloat16* Wb = nullptr;
@@ -620,7 +626,7 @@ size_t cell_backward_tc(const gcrnn_cell* cell, const gcrnn_cell_params* p, cons
   if (fused) {
     CUDA_OK(cudaMemsetAsync(partA, 0, (size_t)d.sms * 64 * BF_ZROWS * sizeof(float), st));
     zs_build_kernel<<<148 * 8, 256, 0, st>>>(X, s.zx, d.RX * d.N, d.G, d.Kin * d.G, d.tg ? s.gt : nullptr, d.tg ? s.gt + d.BT : nullptr,
-                                              Zs, d.BT, d.N, zs_split);
+                                              Zs, d.BT, d.N, zs_split, d.node ? s.qn : nullptr, d.node ? s.qn + (size_t)d.BT * d.N : nullptr);
     launched();
   }
   for (long long t = d.T - 1; t >= 0; --t) {
@@ -639,6 +645,11 @@ size_t cell_backward_tc(const gcrnn_cell* cell, const gcrnn_cell_params* p, cons
         fa.dgin = d.tg ? dgt + (t - 1) : nullptr; fa.dgfn = d.tg ? dgt + d.BT + (t - 1) : nullptr;
         fa.A = p->weight_A; fa.x0 = X + (t - 1) * GN; fa.zx = s.zx + (t - 1) * GN; fa.zx_kstride = d.RX * d.N; fa.z_bstride = d.T * GN;
         fa.v0_out = v0nxt;
+        if (d.node) {
+          fa.qin = s.qn + (t - 1) * d.N; fa.qfn = s.qn + (size_t)d.BT * d.N + (t - 1) * d.N; fa.q_bstride = d.T * d.N;
+          fa.gin = d.tg ? s.gt + (t - 1) : nullptr;
+          fa.dlin_i = dlin + (t - 1) * d.N; fa.dlin_f = dlin + (size_t)d.BT * d.N + (t - 1) * d.N;
+        }
       }
       fa.bias = p->bias;
       fa.zs_row0 = t * BF_ZROWS; fa.zs_rowb = d.T * BF_ZROWS;

@@ -59,12 +59,17 @@ struct BwdFusedArgs {
   const float* x0; const float* zx; long long zx_kstride, z_bstride; int G;   // rows x_{t-1} S^k (fp32)
   __nv_bfloat16* v0_out;                           // [B][64][N] next chain input
   long long zs_row0, zs_rowb;                      // Zs tile of (b, t) starts at row zs_row0 + b * zs_rowb
+  // node gates (tc_node.cuh), step t-1: q_i / q_f at q + b * q_bstride + n, gi[b, t-1] at gin[b * gate_stride] (null: 1).
+  // v0' = bf16(gf q_f dpre); the per-node head gradients d lin_i / d lin_f (see dpre_kernel) are accumulated with one atomicAdd per
+  // 16-feature group and node.  Zs then carries the per-node ratio (gi q_i) / (gf q_f) (zs_build_kernel).
+  const float* qin; const float* qfn; long long q_bstride; const float* gin;
+  float* dlin_i; float* dlin_f;
   // accumulators
   float* part;                  // [grid][K][64][64]
   float* partA;                 // [grid][64][16]
 };
 
-template <int KG>
+template <int KG, bool NODE>     // NODE: per-node gates (compile-time so that the ungated / time-gated kernel is untouched)
 __global__ void __launch_bounds__(BF_THREADS, 1)
 bwd_fused_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tmc,
                  const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmZ,
@@ -223,7 +228,7 @@ bwd_fused_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
       const int n = (int)(tile % tiles_n) * 128 + q * 32 + lane;
       float hp[16], dhn[16], z[KG];
       const float vgf = a.gf ? __ldg(a.gf + b * a.gate_stride) : 1.f;
-      float vgfn = 1.f;
+      float vgfn = 1.f, vgin = 1.f, qi = 1.f, qf = 1.f;
       {
         const float* hb = a.hprev + b * a.hprev_bstride + (size_t)m0 * a.N + n;
 #pragma unroll
@@ -234,6 +239,10 @@ bwd_fused_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
 #pragma unroll
         for (int i = 0; i < 16; ++i) dhn[i] = __ldg(db + (size_t)i * a.N);
         if (a.gfn) vgfn = __ldg(a.gfn + b * a.gate_stride);
+        if (NODE) {
+          qi = __ldg(a.qin + b * a.q_bstride + n); qf = __ldg(a.qfn + b * a.q_bstride + n);
+          if (a.gin) vgin = __ldg(a.gin + b * a.gate_stride);
+        }
         const size_t zo = (size_t)b * a.z_bstride + n;
 #pragma unroll
         for (int kg = 0; kg < KG; ++kg) z[kg] = __ldg(sZb[kg] + zo);
@@ -268,17 +277,27 @@ bwd_fused_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
         const long long ldo = (long long)a.P * a.N;
         __nv_bfloat16* ob = a.v0_out + ((size_t)b * 64 + m0) * ldo + n;
         const float* aw = sAw + m0 * KG;
-        float sgi = 0.f, sgf = 0.f;
+        float sgi = 0.f, sgf = 0.f, li = 0.f, lf = 0.f;
+        const float wfn = vgfn * qf, win = vgin * qi;
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const float dp = (dhn[i] + v[i]) * fmaf(-hp[i], hp[i], 1.f);
-          store_planes(ob + (size_t)i * ldo, a.N, a.P, vgfn * dp);
+          store_planes(ob + (size_t)i * ldo, a.N, a.P, wfn * dp);
           const float bb = sBias[m0 + i];
           float axb = bb;
 #pragma unroll
           for (int kg = 0; kg < KG; ++kg) axb = fmaf(aw[i * KG + kg], z[kg], axb);
           sgi = fmaf(dp, axb, sgi);
           sgf = fmaf(dp, bb, sgf);
+          if (NODE) {                                    // gf q_f (r + b) = atanh(h) - gi q_i (a + b): no state filter recomputation
+            lf = fmaf(dp, atanhf(fminf(fmaxf(hp[i], -0.99999994f), 0.99999994f)) - win * axb, lf);
+          }
+        }
+        if (NODE) {
+          li = win * sgi;                                // sum_f dpre gi q_i (a + b) over this thread's 16 features
+          atomicAdd(a.dlin_i + b * a.q_bstride + n, (1.f - qi) * li);
+          atomicAdd(a.dlin_f + b * a.q_bstride + n, (1.f - qf) * lf);
+          sgi *= qi; sgf *= qf;                          // the time gates see q_i (a + b) and q_f b
         }
         if (a.dgf) {                                     // time gating on: three per-sample scalars
           part = warp_sum_f(part); sgi = warp_sum_f(sgi); sgf = warp_sum_f(sgf);
@@ -335,9 +354,10 @@ bwd_fused_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
 // With v_0 = bf16(gf dpre):  sum_n v_0 Zs_j = gi <dpre, z_j>  (-> dA)  and  (gi + gf) sum_n dpre  (-> dbias).
 // split == 1 (split-bf16 mode, KG <= 7): rows 8 + j hold the bf16 RESIDUAL of row j, so the tile carries both planes of Zs in
 // its 16 rows and MMA3 returns the hi and lo partial products in columns j and 8 + j (summed by dax_reduce_kernel).
+// Node gates (qi / qf != null, [BT][N]): the ratio is per node, (gi q_i[n]) / (gf q_f[n]).
 __global__ void zs_build_kernel(const float* __restrict__ X, const float* __restrict__ zx, long long zx_kstride, int G, int KG,
                                 const float* __restrict__ gi, const float* __restrict__ gf, __nv_bfloat16* __restrict__ Zs,
-                                long long BT, int N, int split) {
+                                long long BT, int N, int split, const float* __restrict__ qi, const float* __restrict__ qf) {
   const int N8 = N / 8;
   const long long total = BT * BF_ZROWS * N8;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -347,7 +367,13 @@ __global__ void zs_build_kernel(const float* __restrict__ X, const float* __rest
     const bool lo = split && jr >= 8;
     const int j = lo ? jr - 8 : jr;
     const float vgi = gi ? gi[bt] : 1.f, vgf = gf ? gf[bt] : 1.f;
-    const float ratio = vgi / fmaxf(vgf, 1e-30f);
+    float ratio[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float num = vgi, den = vgf;
+      if (qi) { const size_t qo = (size_t)bt * N + c * 8 + e; num *= __ldg(qi + qo); den *= __ldg(qf + qo); }
+      ratio[e] = num / fmaxf(den, 1e-30f);
+    }
     float o[8];
     if (j < KG) {
       const int k = j / G, g = j % G;
@@ -355,11 +381,10 @@ __global__ void zs_build_kernel(const float* __restrict__ X, const float* __rest
       const float4 p0 = reinterpret_cast<const float4*>(src)[0], p1 = reinterpret_cast<const float4*>(src)[1];
       o[0] = p0.x; o[1] = p0.y; o[2] = p0.z; o[3] = p0.w; o[4] = p1.x; o[5] = p1.y; o[6] = p1.z; o[7] = p1.w;
 #pragma unroll
-      for (int e = 0; e < 8; ++e) o[e] *= ratio;
+      for (int e = 0; e < 8; ++e) o[e] *= ratio[e];
     } else {
-      const float cst = (j == KG) ? ratio + 1.f : 0.f;
 #pragma unroll
-      for (int e = 0; e < 8; ++e) o[e] = cst;
+      for (int e = 0; e < 8; ++e) o[e] = (j == KG) ? ratio[e] + 1.f : 0.f;
     }
     uint4 u;
     u.x = pack_bf16x2(o[0], o[1]); u.y = pack_bf16x2(o[2], o[3]); u.z = pack_bf16x2(o[4], o[5]); u.w = pack_bf16x2(o[6], o[7]);

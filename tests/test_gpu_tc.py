@@ -256,9 +256,9 @@ def test_tc_auto_precision_takes_node_gated_dense_cells():
 
 
 @pytest.mark.parametrize('prec', ['bf16', 'bf16x2'])
-@pytest.mark.parametrize('tg', [False, True])
+@pytest.mark.parametrize('tg,sg', [(False, None), (True, None), (False, 'node'), (True, 'node')])
 @pytest.mark.parametrize('N,K,T,B,G', [(512, 5, 4, 6, 1), (256, 4, 3, 5, 2), (1024, 2, 2, 3, 1)])
-def test_tc_fused_backward_step_matches_unfused(prec, tg, N, K, T, B, G):
+def test_tc_fused_backward_step_matches_unfused(prec, tg, sg, N, K, T, B, G):
     """F = 64: the fused reverse-time kernel (tensor-core weight/tap gradients, tc_bwd.cuh) against the separate
     tap-contraction + wgrad kernels.  Both run the same forward and the same operand precision, so they agree much more
     tightly than either does with fp32: 1e-2 of max|ref| on every gradient (bf16), 2e-3 (bf16x2: the weight-gradient
@@ -272,7 +272,7 @@ def test_tc_fused_backward_step_matches_unfused(prec, tg, N, K, T, B, G):
     try:
         for fused in (0, 1):
             _set_opt('bwd_fused', fused)
-            cell = _make_cell(S, G, F, K, tg, prec)
+            cell = _make_cell(S, G, F, K, tg, prec, sg=sg)
             hh = h0.clone().requires_grad_(True)
             H = cell(X, hh)
             (H * dH).sum().backward()
@@ -282,7 +282,7 @@ def test_tc_fused_backward_step_matches_unfused(prec, tg, N, K, T, B, G):
         gg.set_precision('fp32')
     errs = {'dh0': _relerr(out[1][1], out[0][1])}
     errs.update(_grad_errs(out[1][0], out[0][0]))
-    _log(f'tc-fused-vs-unfused {prec}', dict(tg=tg, N=N, K=K, T=T, B=B, G=G), {k: f'{v:.2e}' for k, v in errs.items()})
+    _log(f'tc-fused-vs-unfused {prec}', dict(tg=tg, sg=sg, N=N, K=K, T=T, B=B, G=G), {k: f'{v:.2e}' for k, v in errs.items()})
     assert all(v < (1e-2 if prec == 'bf16' else 2e-3) for v in errs.values()), errs
 
 
