@@ -64,7 +64,9 @@ __device__ __forceinline__ void ng_row8(const float* tab, int f, float* w) {
   w[0] = lo.x; w[1] = lo.y; w[2] = lo.z; w[3] = lo.w; w[4] = hi.x; w[5] = hi.y; w[6] = hi.z; w[7] = hi.w;
 }
 
-// thread <-> (b, n): c0[b][:][n] in registers, loop over t.  Block = 128 nodes of one sample.
+// thread <-> (b, n), loop over t and all features.  c0[b][f][n] is re-read per step (64 coalesced loads that stay in L1: 32 KB per
+// block) instead of living in 64 registers: the register version ran 12 warps per SM and issued on 42 % of the cycles
+// (profiles/r02_ncu_node_gate_fwd.raw.csv); the next step's taps are prefetched while this step computes.
 template <int FMAX>
 __global__ void __launch_bounds__(128) node_gate_fwd_kernel(const NodeGateArgs a) {
   extern __shared__ __align__(16) float ng_sm[];
@@ -77,30 +79,29 @@ __global__ void __launch_bounds__(128) node_gate_fwd_kernel(const NodeGateArgs a
   for (long long item = blockIdx.x; item < a.B * tiles_n; item += gridDim.x) {
     const long long b = item / tiles_n;
     const int n = (int)(item - b * tiles_n) * 128 + threadIdx.x;
-    float c0[FMAX];
-#pragma unroll
-    for (int f = 0; f < FMAX; ++f) c0[f] = f < a.F ? __ldg(a.c0 + ((size_t)b * a.F + f) * a.N + n) : 0.f;
+    const float* c0p = a.c0 + (size_t)b * a.F * a.N + n;
+    float z[NG_KG], zn[NG_KG];
+    ng_load_taps(a, b, 0, n, z);
     for (long long t = 0; t < a.T; ++t) {
-      float z[NG_KG];
-      ng_load_taps(a, b, t, n, z);
+      if (t + 1 < a.T) ng_load_taps(a, b, t + 1, n, zn);
       float pk[8];
 #pragma unroll
       for (int k = 0; k < 8; ++k) pk[k] = 0.f;
+#pragma unroll 8
+      for (int f = 0; f < a.F; ++f) {
+        float wa[8], ww[8];
+        ng_row8(sA, f, wa); ng_row8(sW, f, ww);
+        float y = __ldg(c0p + (size_t)f * a.N);
 #pragma unroll
-      for (int f = 0; f < FMAX; ++f) {
-        if (f < a.F) {
-          float wa[8], ww[8];
-          ng_row8(sA, f, wa); ng_row8(sW, f, ww);
-          float y = c0[f];
+        for (int kg = 0; kg < NG_KG; ++kg) y = fmaf(wa[kg], z[kg], y);
+        const float s = ng_tanh(y, a.exact);
 #pragma unroll
-          for (int kg = 0; kg < NG_KG; ++kg) y = fmaf(wa[kg], z[kg], y);
-          const float s = ng_tanh(y, a.exact);
-#pragma unroll
-          for (int k = 0; k < NG_KMAX; ++k) pk[k] = fmaf(ww[k], s, pk[k]);
-        }
+        for (int k = 0; k < NG_KMAX; ++k) pk[k] = fmaf(ww[k], s, pk[k]);
       }
 #pragma unroll
       for (int k = 0; k < NG_KMAX; ++k) if (k < a.Kst) a.p[((size_t)k * BT + b * a.T + t) * a.N + n] = pk[k];
+#pragma unroll
+      for (int kg = 0; kg < NG_KG; ++kg) z[kg] = zn[kg];
     }
   }
 }
@@ -133,11 +134,16 @@ __global__ void __launch_bounds__(512, 1) node_gate_bwd_kernel(const NodeGateArg
     float c0[NG_FC], dc0[NG_FC];
 #pragma unroll
     for (int j = 0; j < NG_FC; ++j) { c0[j] = __ldg(a.c0 + ((size_t)b * a.F + f0 + j) * a.N + n); dc0[j] = 0.f; }
-    for (long long t = 0; t < a.T; ++t) {
-      float z[NG_KG], vk[NG_KMAX];
-      ng_load_taps(a, b, t, n, z);
+    float z[NG_KG], vk[NG_KMAX], zn[NG_KG], vn[NG_KMAX];
+    ng_load_taps(a, b, 0, n, z);
 #pragma unroll
-      for (int k = 0; k < NG_KMAX; ++k) vk[k] = k < a.Kst ? __ldg(a.v + ((size_t)k * BT + b * a.T + t) * a.N + n) : 0.f;
+    for (int k = 0; k < NG_KMAX; ++k) vk[k] = k < a.Kst ? __ldg(a.v + ((size_t)k * BT + b * a.T) * a.N + n) : 0.f;
+    for (long long t = 0; t < a.T; ++t) {
+      if (t + 1 < a.T) {                      // the next step's operands travel while this step computes
+        ng_load_taps(a, b, t + 1, n, zn);
+#pragma unroll
+        for (int k = 0; k < NG_KMAX; ++k) vn[k] = k < a.Kst ? __ldg(a.v + ((size_t)k * BT + b * a.T + t + 1) * a.N + n) : 0.f;
+      }
 #pragma unroll
       for (int j = 0; j < NG_FC; ++j) {
         float wa[8], ww[8];
@@ -154,6 +160,10 @@ __global__ void __launch_bounds__(512, 1) node_gate_bwd_kernel(const NodeGateArg
 #pragma unroll
         for (int kg = 0; kg < NG_KG; ++kg) dA[j][kg] = fmaf(dps, z[kg], dA[j][kg]);
       }
+#pragma unroll
+      for (int kg = 0; kg < NG_KG; ++kg) z[kg] = zn[kg];
+#pragma unroll
+      for (int k = 0; k < NG_KMAX; ++k) vk[k] = vn[k];
     }
 #pragma unroll
     for (int j = 0; j < NG_FC; ++j) a.dc0[((size_t)b * a.F + f0 + j) * a.N + n] = dc0[j];
