@@ -754,8 +754,14 @@ size_t cell_backward_tc(const gcrnn_cell* cell, const gcrnn_cell_params* p, cons
       na.Kin = d.Kin; na.G = d.G; na.F = d.F; na.N = d.N; na.Kst = d.Kst; na.exact = P > 1; na.B = d.B; na.T = d.T;
       na.v = vhead; na.dA = gr->n_weight_A[gi]; na.dwh = gr->n_head_w[gi]; na.dc0 = dc0;
       GCRNN_CHECK(na.dA && na.dwh, "node-gate gradient buffers missing");
-      node_gate_bwd_kernel<<<(unsigned)std::min<long long>(d.B * (d.N / 32), d.sms * (d.F >= 64 ? 1 : 2)), 32 * (d.F / NG_FC),
-                             node_gate_smem_bytes(d.F), st>>>(na);
+      {
+        const unsigned ng = (unsigned)std::min<long long>(d.B * (d.N / 32), d.sms * (d.F >= 64 ? 1 : 2)), nt = 32 * (d.F / NG_FC);
+        const size_t nsm = node_gate_smem_bytes(d.F);
+        const int kgx = d.Kin * d.G;
+        if (kgx == 5 && d.Kst == 5) node_gate_bwd_kernel<5, 5><<<ng, nt, nsm, st>>>(na);
+        else if (kgx <= 4 && d.Kst <= 4) node_gate_bwd_kernel<4, 4><<<ng, nt, nsm, st>>>(na);
+        else node_gate_bwd_kernel<NG_KG, NG_KMAX><<<ng, nt, nsm, st>>>(na);
+      }
       launched();
       if (dX) {
         GateDxArgs gx{};

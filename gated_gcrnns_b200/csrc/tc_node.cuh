@@ -49,6 +49,25 @@ __device__ __forceinline__ void ng_load_taps(const NodeGateArgs& a, long long b,
   }
 }
 
+// per-(sample, node) base pointers of the taps at t = 0; step t is `tstride` floats further (address arithmetic out of the t loop:
+// with it inside, index math was more than a third of the instructions of these kernels)
+template <int KGT>
+__device__ __forceinline__ void ng_tap_ptrs(const NodeGateArgs& a, long long b, int n, const float** zp) {
+  const int KG = a.Kin * a.G;
+#pragma unroll
+  for (int kg = 0; kg < KGT; ++kg) {
+    const int kq = kg < KG ? kg : 0;
+    const int k = kq / a.G, g = kq - k * a.G;
+    const size_t row = ((size_t)(b * a.T) * a.G + g) * a.N + n;
+    zp[kg] = k == 0 ? a.X + row : a.zx + (size_t)(k - 1) * a.zx_kstride + row;
+  }
+}
+template <int KGT>
+__device__ __forceinline__ void ng_taps_at(const float* const* zp, size_t off, int KG, float* z) {
+#pragma unroll
+  for (int kg = 0; kg < KGT; ++kg) z[kg] = kg < KG ? __ldg(zp[kg] + off) : 0.f;
+}
+
 // shared-memory weight tables, 8 floats per feature each so that one feature costs two 16-byte broadcast loads per table
 // (scalar loads made these kernels shared-memory-issue-bound: 13 LDS per feature against ~20 arithmetic instructions)
 __device__ __forceinline__ void ng_stage_weights(const NodeGateArgs& a, float* sA, float* sW) {
@@ -80,10 +99,15 @@ __global__ void __launch_bounds__(128) node_gate_fwd_kernel(const NodeGateArgs a
     const long long b = item / tiles_n;
     const int n = (int)(item - b * tiles_n) * 128 + threadIdx.x;
     const float* c0p = a.c0 + (size_t)b * a.F * a.N + n;
+    const float* zp[NG_KG];
+    ng_tap_ptrs<NG_KG>(a, b, n, zp);
+    const size_t tstride = (size_t)a.G * a.N;
+    const int KG = a.Kin * a.G;
     float z[NG_KG], zn[NG_KG];
-    ng_load_taps(a, b, 0, n, z);
+    ng_taps_at<NG_KG>(zp, 0, KG, z);
+    float* pout = a.p + ((size_t)b * a.T) * a.N + n;
     for (long long t = 0; t < a.T; ++t) {
-      if (t + 1 < a.T) ng_load_taps(a, b, t + 1, n, zn);
+      if (t + 1 < a.T) ng_taps_at<NG_KG>(zp, (size_t)(t + 1) * tstride, KG, zn);
       float pk[8];
 #pragma unroll
       for (int k = 0; k < 8; ++k) pk[k] = 0.f;
@@ -99,7 +123,7 @@ __global__ void __launch_bounds__(128) node_gate_fwd_kernel(const NodeGateArgs a
         for (int k = 0; k < NG_KMAX; ++k) pk[k] = fmaf(ww[k], s, pk[k]);
       }
 #pragma unroll
-      for (int k = 0; k < NG_KMAX; ++k) if (k < a.Kst) a.p[((size_t)k * BT + b * a.T + t) * a.N + n] = pk[k];
+      for (int k = 0; k < NG_KMAX; ++k) if (k < a.Kst) pout[((size_t)k * BT + t) * a.N] = pk[k];
 #pragma unroll
       for (int kg = 0; kg < NG_KG; ++kg) z[kg] = zn[kg];
     }
@@ -109,6 +133,9 @@ __global__ void __launch_bounds__(128) node_gate_fwd_kernel(const NodeGateArgs a
 // warp <-> chunk of NG_FC features, lane <-> node: a block of F / NG_FC warps covers every feature of 32 nodes of one sample, so the
 // taps and head signals of a node are read from HBM once (the other warps hit L1).  Loop over t with the chunk's gradient
 // accumulators in registers; they persist over all tiles of the block: one warp reduction and one atomicAdd per parameter at the end.
+// KGT / KST: compile-time tap counts (exact for the common shapes, NG_KG / NG_KMAX padded otherwise: 37 vs 29 FMA-pipe
+// instructions per (feature, step) at cfg3's Kin = Kst = 5).
+template <int KGT, int KST>
 __global__ void __launch_bounds__(512, 1) node_gate_bwd_kernel(const NodeGateArgs a) {
   extern __shared__ __align__(16) float ng_sm[];
   const int KG = a.Kin * a.G;
@@ -120,50 +147,57 @@ __global__ void __launch_bounds__(512, 1) node_gate_bwd_kernel(const NodeGateArg
   const long long BT = a.B * a.T;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int f0 = warp * NG_FC;
-  float dA[NG_FC][NG_KG], dW[NG_KMAX][NG_FC];
+  float dA[NG_FC][KGT], dW[KST][NG_FC];
 #pragma unroll
   for (int j = 0; j < NG_FC; ++j) {
 #pragma unroll
-    for (int kg = 0; kg < NG_KG; ++kg) dA[j][kg] = 0.f;
+    for (int kg = 0; kg < KGT; ++kg) dA[j][kg] = 0.f;
 #pragma unroll
-    for (int k = 0; k < NG_KMAX; ++k) dW[k][j] = 0.f;
+    for (int k = 0; k < KST; ++k) dW[k][j] = 0.f;
   }
+  const size_t tstride = (size_t)a.G * a.N, kvs = (size_t)BT * a.N;
   for (long long item = blockIdx.x; item < a.B * tiles_n; item += gridDim.x) {
     const long long b = item / tiles_n;
     const int n = (int)(item - b * tiles_n) * 32 + lane;
     float c0[NG_FC], dc0[NG_FC];
 #pragma unroll
     for (int j = 0; j < NG_FC; ++j) { c0[j] = __ldg(a.c0 + ((size_t)b * a.F + f0 + j) * a.N + n); dc0[j] = 0.f; }
-    float z[NG_KG], vk[NG_KMAX], zn[NG_KG], vn[NG_KMAX];
-    ng_load_taps(a, b, 0, n, z);
+    const float* zp[KGT];
+    ng_tap_ptrs<KGT>(a, b, n, zp);
+    const float* vp = a.v + ((size_t)b * a.T) * a.N + n;
+    float z[KGT], vk[KST], zn[KGT], vn[KST];
+    ng_taps_at<KGT>(zp, 0, KG, z);
 #pragma unroll
-    for (int k = 0; k < NG_KMAX; ++k) vk[k] = k < a.Kst ? __ldg(a.v + ((size_t)k * BT + b * a.T) * a.N + n) : 0.f;
+    for (int k = 0; k < KST; ++k) vk[k] = k < a.Kst ? __ldg(vp + k * kvs) : 0.f;
     for (long long t = 0; t < a.T; ++t) {
-      if (t + 1 < a.T) {                      // the next step's operands travel while this step computes
-        ng_load_taps(a, b, t + 1, n, zn);
+      if (t + 1 < a.T) {                               // the next step's operands travel while this step computes
+        ng_taps_at<KGT>(zp, (size_t)(t + 1) * tstride, KG, zn);
 #pragma unroll
-        for (int k = 0; k < NG_KMAX; ++k) vn[k] = k < a.Kst ? __ldg(a.v + ((size_t)k * BT + b * a.T + t + 1) * a.N + n) : 0.f;
+        for (int k = 0; k < KST; ++k) vn[k] = k < a.Kst ? __ldg(vp + k * kvs + (size_t)(t + 1) * a.N) : 0.f;
       }
 #pragma unroll
       for (int j = 0; j < NG_FC; ++j) {
         float wa[8], ww[8];
         ng_row8(sA, f0 + j, wa); ng_row8(sW, f0 + j, ww);
-        float y = c0[j];
+        float y0 = c0[j], y1 = 0.f;                      // two chains: the dependent FMA latency is what this kernel waits on
 #pragma unroll
-        for (int kg = 0; kg < NG_KG; ++kg) y = fmaf(wa[kg], z[kg], y);
-        const float s = ng_tanh(y, a.exact);
-        float ds = 0.f;
+        for (int kg = 0; kg < KGT; ++kg) { if (kg & 1) y1 = fmaf(wa[kg], z[kg], y1); else y0 = fmaf(wa[kg], z[kg], y0); }
+        const float s = ng_tanh(y0 + y1, a.exact);
+        float d0 = 0.f, d1 = 0.f;
 #pragma unroll
-        for (int k = 0; k < NG_KMAX; ++k) { ds = fmaf(ww[k], vk[k], ds); dW[k][j] = fmaf(vk[k], s, dW[k][j]); }
-        const float dps = ds * (1.f - s * s);
+        for (int k = 0; k < KST; ++k) {
+          if (k & 1) d1 = fmaf(ww[k], vk[k], d1); else d0 = fmaf(ww[k], vk[k], d0);
+          dW[k][j] = fmaf(vk[k], s, dW[k][j]);
+        }
+        const float dps = (d0 + d1) * (1.f - s * s);
         dc0[j] += dps;
 #pragma unroll
-        for (int kg = 0; kg < NG_KG; ++kg) dA[j][kg] = fmaf(dps, z[kg], dA[j][kg]);
+        for (int kg = 0; kg < KGT; ++kg) dA[j][kg] = fmaf(dps, z[kg], dA[j][kg]);
       }
 #pragma unroll
-      for (int kg = 0; kg < NG_KG; ++kg) z[kg] = zn[kg];
+      for (int kg = 0; kg < KGT; ++kg) z[kg] = zn[kg];
 #pragma unroll
-      for (int k = 0; k < NG_KMAX; ++k) vk[k] = vn[k];
+      for (int k = 0; k < KST; ++k) vk[k] = vn[k];
     }
 #pragma unroll
     for (int j = 0; j < NG_FC; ++j) a.dc0[((size_t)b * a.F + f0 + j) * a.N + n] = dc0[j];
@@ -171,14 +205,14 @@ __global__ void __launch_bounds__(512, 1) node_gate_bwd_kernel(const NodeGateArg
 #pragma unroll
   for (int j = 0; j < NG_FC; ++j) {
 #pragma unroll
-    for (int kg = 0; kg < NG_KG; ++kg) {
+    for (int kg = 0; kg < KGT; ++kg) {
       float v = dA[j][kg];
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
       if (lane == 0 && kg < KG) atomicAdd(a.dA + (size_t)(f0 + j) * KG + kg, v);
     }
 #pragma unroll
-    for (int k = 0; k < NG_KMAX; ++k) {
+    for (int k = 0; k < KST; ++k) {
       float v = dW[k][j];
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -34,7 +34,7 @@ class _Data:
         return torch.mean((yHat - y) ** 2)
 
 
-def _run(device, patched, tmp, spatial):
+def _run(device, patched, tmp, spatial, N=20, F=6, dense=False):
     gml = ref_shim.load()
     archs = ref_shim.load_architectures()
     import Modules.model as model
@@ -42,8 +42,8 @@ def _run(device, patched, tmp, spatial):
     if patched:
         gg.install(gml)
     try:
-        N, T, F, K = 20, 4, 6, 3
-        S = gg.graphs.sbm(N, 4, 0.7, 0.2, seed=3)[0].numpy()
+        T, K = 4, 3
+        S = (gg.graphs.dense_random(N, 0.3, seed=3) if dense else gg.graphs.sbm(N, 4, 0.7, 0.2, seed=3))[0].numpy()
         torch.manual_seed(0)
         np.random.seed(0)
         net = archs.GatedGCRNNforRegression(1, F, K, K, torch.tanh, torch.tanh, [N], S, True, time_gating=True,
@@ -60,6 +60,7 @@ def _run(device, patched, tmp, spatial):
         m = model.Model(net, loss, opt, 'GCRNNdropin', str(tmp), list(range(N)))
         data = _Data(N, T, 12, 4, device)
         train.MultipleModels({'GCRNNdropin': m}, data, 2, 4, T, F, F, validationInterval=100)
+        _run.precisions = sorted({k[1] for mod in net.modules() if hasattr(mod, '_handles') for k in mod._handles})
         return losses, {k: v.detach().cpu().double() for k, v in net.state_dict().items()}
     finally:
         if patched:
@@ -77,6 +78,28 @@ def test_reference_training_loop_runs_unchanged(tmp_path, spatial):
     np.testing.assert_allclose(our_losses, ref_losses, rtol=2e-4, atol=1e-6)
     for k in ref_sd:        # parameters after the SGD steps (and after MultipleModels re-loaded the 'Best' checkpoint)
         assert (our_sd[k] - ref_sd[k]).abs().max() <= 2e-4 * max(1.0, ref_sd[k].abs().max()), k
+
+
+@pytest.mark.parametrize('spatial', [None, 'node'])
+def test_reference_training_loop_on_the_tensor_core_path(tmp_path, spatial):
+    """The same unchanged reference loop on a DENSE N = 256 graph with precision 'auto': the cell (time gates, and time + node gates)
+    then runs on the split-bf16 tcgen05 path.  Losses of the first optimisation steps against the reference's own fp32 CPU run, at
+    the tensor-core mode's bound instead of the fp32 one."""
+    if not ref_shim.available():
+        pytest.skip('no copy of the reference tree on this box')
+    ref_losses, ref_sd = _run('cpu', False, tmp_path / 'ref', spatial, N=256, F=16, dense=True)
+    l0 = gg._lib.lib().gcrnn_debug_launch_count()
+    try:
+        gg.set_precision('auto')
+        our_losses, our_sd = _run(DEV, True, tmp_path / 'ours', spatial, N=256, F=16, dense=True)
+    finally:
+        gg.set_precision('fp32')
+    assert gg._lib.lib().gcrnn_debug_launch_count() > l0
+    assert _run.precisions == [gg._lib.PREC_BF16X2_TC], f'the cell did not take the split-bf16 tensor-core path: {_run.precisions}'
+    assert len(ref_losses) == len(our_losses) and len(ref_losses) >= 6
+    np.testing.assert_allclose(our_losses, ref_losses, rtol=2e-3, atol=1e-5)
+    for k in ref_sd:
+        assert (our_sd[k] - ref_sd[k]).abs().max() <= 5e-3 * max(1.0, ref_sd[k].abs().max()), k
 
 
 # ---------------------------------------------------------------------------------------------------------------
