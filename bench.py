@@ -482,6 +482,12 @@ def run_ours(args):
                 secondary[wl] = dict(error=f'{type(e).__name__}: {e}')
             gc.collect()
             torch.cuda.empty_cache()
+        try:
+            secondary['cfg3-node'] = cfg3_node_extra(dev, cfg, mb)
+        except Exception as e:
+            secondary['cfg3-node'] = dict(error=f'{type(e).__name__}: {e}')
+        gc.collect()
+        torch.cuda.empty_cache()
         gg.set_precision(args.precision)
     else:
         peak_gb = round(torch.cuda.max_memory_allocated() / 1e9, 1)
@@ -505,6 +511,48 @@ def run_ours(args):
     if world > 1:
         gg.dist.disable()
         dist.destroy_process_group()
+
+
+def cfg3_node_extra(dev, cfg, mb, precisions=('bf16x2', 'bf16')):
+    """cfg3 with NODE gates on top of the time gates (SURVEY.md 8d extra): device-resident forward + backward of one micro-batch on the
+    tensor-core path (csrc/tc_node.cuh), per operand mode; 1 warm-up + 2 timed micro-batches."""
+    import torch
+    import gated_gcrnns_b200 as gg
+    N, F, G, K, T = cfg['N'], cfg['F'], cfg['G'], cfg['K'], cfg['T']
+    S = gg.graphs.dense_random(N, cfg['density'], seed=0)
+    out = {}
+    X = torch.randn(mb, T, G, N, device=dev)
+    h0 = torch.zeros(mb, F, N, device=dev)
+    dH = torch.ones(mb, T, F, N, device=dev)
+    try:
+        for prec in precisions:
+            gg.set_precision(prec)
+            torch.manual_seed(0)
+            cell = gg.GGCRNNCell(G, F, K, K, torch.tanh, True, 'node', 1, True)
+            cell.addGSO(S)
+            cell = cell.to(dev)
+
+            def once():
+                cell.zero_grad(set_to_none=True)
+                H = cell(X, h0)
+                torch.autograd.backward(H, dH)
+                del H
+            once()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(2):
+                once()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 2
+            out[prec] = dict(value=mb / (ms * 1e-3), unit='sequences/s', ms_per_microbatch=ms)
+            del cell
+    finally:
+        del X, h0, dH
+    out['config'] = dict(workload=f'cfg3 + node gates: dense N={N} F={F} G={G} K={K} T={T}, time + node gated GGCRNNCell fwd+bwd, micro-batch {mb}, '
+                                  'inputs resident in HBM, tensor-core path')
+    return out
 
 
 def ncu_traffic_for_shape(R, N, P, pair):

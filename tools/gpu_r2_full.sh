@@ -13,5 +13,5 @@ print('value', d['value'], 'e2e', d['e2e']['value'], 'modes', {k: round(v['value
 print('roofline', {k: d['roofline'][k] for k in ('frac','tensor_pipe_frac','step_frac','step_frac_of_mode_equivalent_peak')})
 print('parity', {k: d['parity'][k] for k in ('max_rel_H_first16','max_rel_H','max_rel_grad_T16')})
 print('cpu', d['cpu_baseline'] and d['cpu_baseline']['value'], 'clocks', d['clocks'])
-for k,v in (d.get('secondary') or {}).items(): print('secondary', k, {kk: (vv if not isinstance(vv, dict) else '...') for kk,vv in v.items() if kk in ('value','ms_per_step','error','steps')}, v.get('roofline') and v['roofline'].get('frac'), v.get('whole_step') and v['whole_step'].get('graphed_seq_per_s'))
+for k,v in (d.get('secondary') or {}).items(): print('secondary', k, {kk: (vv if not isinstance(vv, dict) else {a: round(b) if isinstance(b, float) else b for a, b in vv.items() if a != 'workload'}) for kk,vv in v.items() if kk in ('value','ms_per_step','error','steps','bf16x2','bf16')}, v.get('roofline') and v['roofline'].get('frac'), v.get('whole_step') and v['whole_step'].get('graphed_seq_per_s'))
 PY
