@@ -404,7 +404,7 @@ def test_tc_cell_vs_fp64_oracle_reduced_cfg3(sg, prec):
     try:
         cell = _make_cell(S, 1, F, K, True, prec, sg=sg)
         torch.manual_seed(5)
-        X, h0, dH = torch.randn(B, T, 1, N), torch.zeros(B, F, N), torch.randn(B, T, F, N)
+        X, h0, dH = torch.randn(B, T, 1, N), 0.2 * torch.randn(B, F, N), torch.randn(B, T, F, N)      # h0 != 0: the sub-cells' state taps get gradients
         p = {k: v.detach().double().cpu() for k, v in cell.state_dict().items()}
         Href, gref = orc.cell_forward_backward(p, S.double(), X.double(), h0.double(), dH.double(), True, sg)
         H = cell(X.to(DEV), h0.to(DEV))
