@@ -785,29 +785,32 @@ persist::Args persist_args(const gcrnn_cell* cell, const gcrnn_cell_params* p, i
   }
   return a;
 }
-// kernel variants: NB = 4 (blocked loops with 16-byte loads, needs N % 4 == 0 and F % 4 == 0) or 1; spatial gating none / node / edge
-template <int NB, int SG>
+// kernel variants: NB = 4 / 1, spatial gating none / node / edge, quad layout on / off
+template <int NB, int SG, bool QZ>
 void persist_launch_v(bool bwd, const persist::Args& a, unsigned B, size_t smem, cudaStream_t st) {
   static DeviceOnce once;
   if (once.first()) {
-    CUDA_OK(cudaFuncSetAttribute(persist::persist_fwd_k<NB, SG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CUDA_OK(cudaFuncSetAttribute(persist::persist_bwd_k<NB, SG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_OK(cudaFuncSetAttribute(persist::persist_fwd_k<NB, SG, QZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_OK(cudaFuncSetAttribute(persist::persist_bwd_k<NB, SG, QZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   }
-  if (bwd) persist::persist_bwd_k<NB, SG><<<B, persist::PT, smem, st>>>(a);
-  else persist::persist_fwd_k<NB, SG><<<B, persist::PT, smem, st>>>(a);
+  if (bwd) persist::persist_bwd_k<NB, SG, QZ><<<B, persist::PT, smem, st>>>(a);
+  else persist::persist_fwd_k<NB, SG, QZ><<<B, persist::PT, smem, st>>>(a);
   check_launch();
 }
+template <int SG>
+void persist_launch_sg(bool bwd, const persist::Args& a, unsigned B, size_t smem, cudaStream_t st) {
+  // NB = 4: blocked loops over 4 consecutive nodes with 16-byte loads along the nodes (N % 4 == 0 and F % 4 == 0: cfg1).  Otherwise, with
+  // F % 4 == 0 (cfg2: N = 59), the state-side slabs take the quad layout (QZ): +21 % / +12 % at cfg2-node / cfg2-edge.  The two do not
+  // combine as written: four consecutive nodes of a quad-layout slab are 64 bytes apart per thread (4-way bank conflicts, cfg1 205k ->
+  // 182k), and NB = 1 with the quad layout measures the same as NB = 4 without it at cfg1 (200k vs 205k).
+  if (a.N % 4 == 0 && a.F % 4 == 0) persist_launch_v<4, SG, false>(bwd, a, B, smem, st);
+  else if (a.F % 4 == 0) persist_launch_v<1, SG, true>(bwd, a, B, smem, st);
+  else persist_launch_v<1, SG, false>(bwd, a, B, smem, st);
+}
 void persist_launch(bool bwd, const persist::Args& a, unsigned B, size_t smem, cudaStream_t st) {
-  const bool nb4 = a.N % 4 == 0 && a.F % 4 == 0;
-  const int sg = a.node ? 1 : a.edge ? 2 : 0;
-  switch (sg * 2 + (nb4 ? 1 : 0)) {
-    case 0: persist_launch_v<1, 0>(bwd, a, B, smem, st); break;
-    case 1: persist_launch_v<4, 0>(bwd, a, B, smem, st); break;
-    case 2: persist_launch_v<1, 1>(bwd, a, B, smem, st); break;
-    case 3: persist_launch_v<4, 1>(bwd, a, B, smem, st); break;
-    case 4: persist_launch_v<1, 2>(bwd, a, B, smem, st); break;
-    default: persist_launch_v<4, 2>(bwd, a, B, smem, st); break;
-  }
+  if (a.node) persist_launch_sg<1>(bwd, a, B, smem, st);
+  else if (a.edge) persist_launch_sg<2>(bwd, a, B, smem, st);
+  else persist_launch_sg<0>(bwd, a, B, smem, st);
 }
 size_t cell_forward_persist(const gcrnn_cell* cell, const gcrnn_cell_params* p, const float* X, const float* h0, float* H,
                             void* saved, size_t savedb, size_t* saved_used, void* ws, int64_t B, int64_t T, cudaStream_t st) {

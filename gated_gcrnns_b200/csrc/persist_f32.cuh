@@ -64,16 +64,17 @@ __host__ __device__ inline long long weights_floats(const Shape& s) {
   return cell + (s.tg ? 2 * cell + 2LL * s.F * s.N : 0) + (s.node ? 2 * cell + 2LL * s.Kst * s.F : 0) + (s.edge ? 2LL * (s.F * s.F + 2 * s.F) : 0);
 }
 __host__ __device__ inline long long annz4(const Shape& s) { return (s.annz + 3) & ~3; }
+__host__ __device__ inline long long zx_floats(int Kin, int G, int N) { return ((long long)Kin * G * N + 3) & ~3LL; }
 __host__ __device__ inline long long fwd_floats(const Shape& s) {
   const long long FN = (long long)s.F * s.N;
-  return weights_floats(s) + (long long)s.Kin * s.G * s.N + (long long)s.Kst * FN + FN /*hn*/ +
+  return weights_floats(s) + zx_floats(s.Kin, s.G, s.N) + (long long)s.Kst * FN + FN /*hn*/ +
          (s.tg ? 2 * FN : 0) /*c0*/ + (s.node ? 3 * FN + (long long)s.Kst * s.N + 2LL * s.N : 0) /*c0n, s, pk, q*/ +
          (s.edge ? 5 * FN + 2LL * s.N + annz4(s) : 0) /*ya, yr, Wx, out_a, out_r, rr, cc, al*/ + 64;
 }
 __host__ __device__ inline long long bwd_floats(const Shape& s) {
   const long long FN = (long long)s.F * s.N;
   return 2 * weights_floats(s) /*weights + gradient accumulators*/ +
-         (long long)s.Kin * s.G * s.N + (long long)s.Kst * FN + 5 * FN /*da dr dh b1 b2*/ + (s.tg ? 4 * FN : 0) /*c0, dc0*/ +
+         zx_floats(s.Kin, s.G, s.N) + (long long)s.Kst * FN + 5 * FN /*da dr dh b1 b2*/ + (s.tg ? 4 * FN : 0) /*c0, dc0*/ +
          ((s.tg || s.node) ? FN : 0) /*dpu*/ + (s.node ? 5 * FN + (long long)s.Kst * s.N + 4LL * s.N : 0) /*c0n, dc0n, s, vch, q, dq*/ +
          (s.edge ? 6 * FN + 4LL * s.N + 2 * annz4(s) : 0) /*ya, yr, dp, Wx, out/dy, dWx, rr, cc, drr, dcc, al, tmp*/ + 64;
 }
@@ -187,6 +188,96 @@ __device__ __forceinline__ void contract(const float* W, const float* z, int f, 
   }
 }
 
+// ---- "quad" layout of the state-side slabs (QZ, needs F % 4 == 0) ---------------------------------------------------------------
+// The shift of a 4-row group gathers in[r..r+3][idx] per edge: four scalar loads at stride N plus their address arithmetic were the
+// hot spot of these kernels (profiles/r02_ncu_persist_*.source_top.txt).  With the four rows of a group interleaved per node,
+//   element (c, n) of a slab at  ((c / 4) * N + n) * 4 + c % 4,
+// an edge costs ONE 16-byte load, and the contractions read a weight quad and a signal quad per four FMAs.  Slabs k = 0..K-1 are
+// contiguous, so row i = k*C + c of the stacked signal lives in quad i / 4.
+__device__ __forceinline__ int quad_index(int c, int n, int N) { return (((c >> 2) * N + n) << 2) + (c & 3); }
+template <bool QZ>
+__device__ __forceinline__ void put_state(float* z0, const float* src, int F, int N) {      // slab 0 <- src [F][N] (global or shared)
+  for (int e = threadIdx.x; e < F * N; e += PT) {
+    if (QZ) { const int c = e / N, n = e - c * N; z0[quad_index(c, n, N)] = src[e]; }
+    else z0[e] = src[e];
+  }
+}
+__device__ __forceinline__ void shift_quad(const List& l, const float* in, float* out, int R, int N) {
+  const float4* in4 = reinterpret_cast<const float4*>(in);
+  float4* out4 = reinterpret_cast<float4*>(out);
+  for (int e = threadIdx.x; e < (R >> 2) * N; e += PT) {
+    const int rg = e / N, n = e - rg * N;
+    const float4* row = in4 + (size_t)rg * N;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int p1 = l.ptr[n + 1];
+    for (int p = l.ptr[n]; p < p1; ++p) {
+      const float v = l.val[p];
+      const float4 x = row[l.idx(p)];
+      s.x = fmaf(v, x.x, s.x); s.y = fmaf(v, x.y, s.y); s.z = fmaf(v, x.z, s.z); s.w = fmaf(v, x.w, s.w);
+    }
+    out4[e] = s;
+  }
+}
+template <bool QZ>
+__device__ __forceinline__ void chain_z(const List& fw, float* z, int K, int R, int N) {
+  if constexpr (!QZ) {
+    chain(fw, z, K, R, N);
+  } else {
+    for (int k = 1; k < K; ++k) {
+      shift_quad(fw, z + (size_t)(k - 1) * R * N, z + (size_t)k * R * N, R, N);
+      __syncthreads();
+    }
+  }
+}
+// y[j] = sum_i W[f][i] z[i][n0 + j], j < NB, z in quad layout (KC % 4 == 0)
+template <int NB>
+__device__ __forceinline__ void contract_quad(const float* W, const float* z, int f, int n0, int KC, int N, float* y) {
+  const float4* w4 = reinterpret_cast<const float4*>(W + (size_t)f * KC);
+  const float4* z4 = reinterpret_cast<const float4*>(z) + n0;
+  float acc[NB][2];
+#pragma unroll
+  for (int j = 0; j < NB; ++j) { acc[j][0] = 0.f; acc[j][1] = 0.f; }
+  const int Q = KC >> 2;
+  for (int q = 0; q < Q; ++q) {
+    const float4 w = w4[q];
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      const float4 x = z4[(size_t)q * N + j];
+      acc[j][0] = fmaf(w.x, x.x, fmaf(w.y, x.y, acc[j][0]));
+      acc[j][1] = fmaf(w.z, x.z, fmaf(w.w, x.w, acc[j][1]));
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < NB; ++j) y[j] = acc[j][0] + acc[j][1];
+}
+template <int NB, bool QZ>
+__device__ __forceinline__ void contract_z(const float* W, const float* z, int f, int n0, int KC, int N, float* y) {
+  if (QZ) contract_quad<NB>(W, z, f, n0, KC, N, y); else contract<NB>(W, z, f, n0, KC, N, y);
+}
+// acc[f][4q..4q+3] += sum_n d[f][n] z4[q][n]: a thread owns one feature and one quad of stacked rows; the lanes of a warp walk the
+// nodes from different starting points so that their 16-byte loads fall into different banks
+__device__ __forceinline__ void wgrad_quad(float* acc, const float* d, const float* z, int F, int KC, int N) {
+  const int Q = KC >> 2;
+  const float4* z4 = reinterpret_cast<const float4*>(z);
+  for (int o = threadIdx.x; o < F * Q; o += PT) {
+    const int f = o / Q, q = o - f * Q;
+    const float* dr = d + (size_t)f * N;
+    const float4* zr = z4 + (size_t)q * N;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    int n = threadIdx.x % N;
+    for (int i = 0; i < N; ++i) {
+      const float dv = dr[n];
+      const float4 x = zr[n];
+      s.x = fmaf(dv, x.x, s.x); s.y = fmaf(dv, x.y, s.y); s.z = fmaf(dv, x.z, s.z); s.w = fmaf(dv, x.w, s.w);
+      if (++n == N) n = 0;
+    }
+    float4* ap = reinterpret_cast<float4*>(acc + (size_t)f * KC) + q;
+    float4 t = *ap;
+    t.x += s.x; t.y += s.y; t.z += s.z; t.w += s.w;
+    *ap = t;
+  }
+}
+
 struct Sub { float *A, *B, *b; };                 // an ungated sub-cell: input taps, state taps, bias
 struct Weights {
   float *A, *Bw, *bias;
@@ -242,13 +333,13 @@ __device__ __forceinline__ void load_weights(const Weights& w, const Args& a) {
   }
 }
 // c0[f][n] = sum_{k,g} B_s[f][k][g] zh[k][g][n] + 2 b_s[f]: the T-invariant term of a sub-cell run from the initial state
-template <int NB>
+template <int NB, bool QZ>
 __device__ __forceinline__ void subcell_c0(const Sub& sc, const float* zh, float* c0, int F, int KCb, int N) {
   const int NQ = N / NB;
   for (int e = threadIdx.x; e < F * NQ; e += PT) {
     const int f = e / NQ, n0 = (e - f * NQ) * NB;
     float y[NB];
-    contract<NB>(sc.B, zh, f, n0, KCb, N, y);
+    contract_z<NB, QZ>(sc.B, zh, f, n0, KCb, N, y);
 #pragma unroll
     for (int j = 0; j < NB; ++j) c0[f * N + n0 + j] = y[j] + 2.f * sc.b[f];
   }
@@ -353,7 +444,7 @@ __device__ __forceinline__ void gat_fwd(int N, int F, const Att& t, const float*
   __syncthreads();
 }
 
-template <int NB, int SG>      // SG: spatial gating 0 none, 1 node, 2 edge (compile-time so that the other modes cost nothing)
+template <int NB, int SG, bool QZ>      // SG: spatial gating 0 none, 1 node, 2 edge; QZ: quad layout of the state-side slabs (F % 4 == 0)
 __global__ void __launch_bounds__(PT, 1) persist_fwd_k(const Args a) {
   constexpr bool NODE = SG == 1, EDGE = SG == 2;
   extern __shared__ __align__(16) float psm[];
@@ -362,7 +453,7 @@ __global__ void __launch_bounds__(PT, 1) persist_fwd_k(const Args a) {
   const long long b = blockIdx.x;
   Weights w;
   float* p = carve(w, psm, a);
-  float* zx = p; p += (size_t)a.Kin * GN;
+  float* zx = p; p += zx_floats(a.Kin, a.G, N);
   float* zh = p; p += (size_t)a.Kst * FN;
   float* hn = p; p += FN;
   float* c0 = p; p += a.tg ? 2 * FN : 0;
@@ -384,15 +475,15 @@ __global__ void __launch_bounds__(PT, 1) persist_fwd_k(const Args a) {
   Att att{};
   if (EDGE) att = stage_att(sp, a);
   load_weights(w, a);
-  for (int e = threadIdx.x; e < FN; e += PT) zh[e] = a.h0[b * FN + e];
+  put_state<QZ>(zh, a.h0 + b * FN, F, N);
   __syncthreads();
   const bool gated = a.tg || NODE;
   if (gated) {                                                    // T-invariant gate terms: B_s(S) h0 + 2 b_s   (graphML.py:2362, :2383, :2417-2423)
-    chain(fw, zh, a.Kst, F, N);
+    chain_z<QZ>(fw, zh, a.Kst, F, N);
 #pragma unroll
     for (int g = 0; g < 2; ++g) {
-      if (a.tg) subcell_c0<NB>(w.ts[g], zh, c0 + g * FN, F, KCb, N);
-      if (NODE) subcell_c0<NB>(w.ns[g], zh, c0n + g * FN, F, KCb, N);
+      if (a.tg) subcell_c0<NB, QZ>(w.ts[g], zh, c0 + g * FN, F, KCb, N);
+      if (NODE) subcell_c0<NB, QZ>(w.ns[g], zh, c0n + g * FN, F, KCb, N);
     }
     __syncthreads();
   }
@@ -427,13 +518,13 @@ __global__ void __launch_bounds__(PT, 1) persist_fwd_k(const Args a) {
         for (int n = threadIdx.x; n < N; n += PT) qo[n] = qs[g * N + n];
       }
     }
-    if (!(gated && t == 0)) chain(fw, zh, a.Kst, F, N);           // at t = 0 with gating the h0 chain is already there
+    if (!(gated && t == 0)) chain_z<QZ>(fw, zh, a.Kst, F, N);           // at t = 0 with gating the h0 chain is already there
     float* Ht = a.H + (b * a.T + t) * FN;
     for (int e = threadIdx.x; e < F * NQ; e += PT) {
       const int f = e / NQ, n0 = (e - f * NQ) * NB;
       float av[NB], rv[NB];
       contract<NB>(w.A, zx, f, n0, KCa, N, av);
-      contract<NB>(w.Bw, zh, f, n0, KCb, N, rv);
+      contract_z<NB, QZ>(w.Bw, zh, f, n0, KCb, N, rv);
       const float bb = w.bias[f];                                  // the same bias in both filters (:2405-2407)
       if constexpr (EDGE) {
 #pragma unroll
@@ -459,7 +550,7 @@ __global__ void __launch_bounds__(PT, 1) persist_fwd_k(const Args a) {
       }
       __syncthreads();
     }
-    for (int e = threadIdx.x; e < FN; e += PT) zh[e] = hn[e];
+    put_state<QZ>(zh, hn, F, N);
     __syncthreads();
   }
 }
@@ -534,18 +625,64 @@ __device__ __forceinline__ void adjoint_chain(const Args& a, const List& bw, con
   }
 }
 
+// same with the scratch signals in quad layout (C % 4 == 0): the S^T gather of four features is one 16-byte load per edge
+__device__ __forceinline__ void adjoint_chain_quad(const Args& a, const List& bw, const float* W, const float* d, float* b1, float* b2, float* out,
+                                                   int K, int C, bool accumulate) {
+  const int N = a.N, F = a.F, CG = C >> 2;
+  float4* cur = reinterpret_cast<float4*>(b1); float4* nxt = reinterpret_cast<float4*>(b2);
+  for (int k = K - 1; k >= 0; --k) {
+    for (int e = threadIdx.x; e < CG * N; e += PT) {
+      const int cg = e / N, n = e - cg * N, g0 = cg << 2;
+      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k < K - 1) {
+        const float4* row = cur + (size_t)cg * N;
+        const int p1 = bw.ptr[n + 1];
+        for (int p = bw.ptr[n]; p < p1; ++p) {
+          const float v = bw.val[p];
+          const float4 x = row[bw.idx(p)];
+          s.x = fmaf(v, x.x, s.x); s.y = fmaf(v, x.y, s.y); s.z = fmaf(v, x.z, s.z); s.w = fmaf(v, x.w, s.w);
+        }
+      }
+      for (int f = 0; f < F; ++f) {
+        const float dv = d[(size_t)f * N + n];
+        const float4 wv = *reinterpret_cast<const float4*>(W + ((size_t)f * K + k) * C + g0);
+        s.x = fmaf(wv.x, dv, s.x); s.y = fmaf(wv.y, dv, s.y); s.z = fmaf(wv.z, dv, s.z); s.w = fmaf(wv.w, dv, s.w);
+      }
+      if (k == 0) {
+        float* o = out + (size_t)g0 * N + n;
+        if (accumulate) { o[0] += s.x; o[N] += s.y; o[2 * N] += s.z; o[3 * N] += s.w; }
+        else { o[0] = s.x; o[N] = s.y; o[2 * N] = s.z; o[3 * N] = s.w; }
+      } else {
+        nxt[e] = s;
+      }
+    }
+    __syncthreads();
+    float4* t = cur; cur = nxt; nxt = t;
+  }
+}
+template <int NB, bool QZ>
+__device__ __forceinline__ void adjoint_z(const Args& a, const List& bw, const float* W, const float* d, float* b1, float* b2, float* out,
+                                          int K, int C, bool accumulate) {
+  if (QZ) adjoint_chain_quad(a, bw, W, d, b1, b2, out, K, C, accumulate);
+  else adjoint_chain<NB>(a, bw, W, d, b1, b2, out, K, C, accumulate);
+}
+template <int NB, bool QZ>
+__device__ __forceinline__ void wgrad_z(float* acc, const float* d, const float* z, int F, int KC, int N) {
+  if (QZ) wgrad_quad(acc, d, z, F, KC, N); else wgrad_acc<NB>(acc, d, z, F, KC, N);
+}
+
 // T-invariant term of a sub-cell, backward: v = sum_t d pre_s.  dB_s += v zh0^T, db_s += 2 sum_n v, dh0 += adjoint chain
-template <int NB>
+template <int NB, bool QZ>
 __device__ __forceinline__ void subcell_c0_bwd(const Args& a, const List& bw, const Sub& sc, const Sub& gsc, const float* v, const float* zh,
                                                float* b1, float* b2, float* dh) {
   const int N = a.N, F = a.F;
-  wgrad_acc<NB>(gsc.B, v, zh, F, a.Kst * F, N);
+  wgrad_z<NB, QZ>(gsc.B, v, zh, F, a.Kst * F, N);
   for (int f = threadIdx.x; f < F; f += PT) {
     float s = 0.f;
     for (int n = 0; n < N; ++n) s += v[(size_t)f * N + n];
     gsc.b[f] += 2.f * s;                                           // the sub-cell adds its bias twice (:2421-2422)
   }
-  if (a.dh0) adjoint_chain<NB>(a, bw, sc.B, v, b1, b2, dh, a.Kst, F, true);
+  if (a.dh0) adjoint_z<NB, QZ>(a, bw, sc.B, v, b1, b2, dh, a.Kst, F, true);
   __syncthreads();
 }
 __device__ __forceinline__ void flush_sub(const Sub& g, float* dA, float* dB, float* db, int nA, int nB, int F) {
@@ -612,7 +749,7 @@ __device__ __forceinline__ void gat_bwd(int N, int F, const Att& t, const float*
   __syncthreads();
 }
 
-template <int NB, int SG>      // SG: spatial gating 0 none, 1 node, 2 edge (compile-time so that the other modes cost nothing)
+template <int NB, int SG, bool QZ>
 __global__ void __launch_bounds__(PT, 1) persist_bwd_k(const Args a) {
   constexpr bool NODE = SG == 1, EDGE = SG == 2;
   extern __shared__ __align__(16) float psm[];
@@ -623,7 +760,7 @@ __global__ void __launch_bounds__(PT, 1) persist_bwd_k(const Args a) {
   Weights w, gacc;
   float* p = carve(w, psm, a);
   p = carve(gacc, p, a);                                          // gradient accumulators, same layout as the weights
-  float* zx = p; p += (size_t)a.Kin * GN;
+  float* zx = p; p += zx_floats(a.Kin, a.G, N);
   float* zh = p; p += (size_t)a.Kst * FN;
   float* da = p; p += FN;
   float* dr = p; p += FN;
@@ -668,20 +805,20 @@ __global__ void __launch_bounds__(PT, 1) persist_bwd_k(const Args a) {
   __syncthreads();
   const bool gated = a.tg || NODE;
   if (gated) {                                                    // c0 of every gate sub-cell (needed to recompute their states)
-    for (int e = threadIdx.x; e < FN; e += PT) zh[e] = a.h0[b * FN + e];
+    put_state<QZ>(zh, a.h0 + b * FN, F, N);
     __syncthreads();
-    chain(fw, zh, a.Kst, F, N);
+    chain_z<QZ>(fw, zh, a.Kst, F, N);
 #pragma unroll
     for (int g = 0; g < 2; ++g) {
-      if (a.tg) subcell_c0<NB>(w.ts[g], zh, c0 + g * FN, F, KCb, N);
-      if (NODE) subcell_c0<NB>(w.ns[g], zh, c0n + g * FN, F, KCb, N);
+      if (a.tg) subcell_c0<NB, QZ>(w.ts[g], zh, c0 + g * FN, F, KCb, N);
+      if (NODE) subcell_c0<NB, QZ>(w.ns[g], zh, c0n + g * FN, F, KCb, N);
     }
     __syncthreads();
   }
   for (long long t = a.T - 1; t >= 0; --t) {
     const float* hprev = t > 0 ? a.H + (b * a.T + t - 1) * FN : a.h0 + b * FN;
     const float* xt = a.X + (b * a.T + t) * GN;
-    for (int e = threadIdx.x; e < FN; e += PT) zh[e] = hprev[e];
+    put_state<QZ>(zh, hprev, F, N);
     for (int e = threadIdx.x; e < GN; e += PT) zx[e] = xt[e];
     if (NODE)
       for (int e = threadIdx.x; e < 2 * N; e += PT) {
@@ -690,7 +827,7 @@ __global__ void __launch_bounds__(PT, 1) persist_bwd_k(const Args a) {
         dq[e] = 0.f;
       }
     __syncthreads();
-    chain(fw, zh, a.Kst, F, N);
+    chain_z<QZ>(fw, zh, a.Kst, F, N);
     chain(fw, zx, a.Kin, a.G, N);
     float gi = 1.f, gf = 1.f;
     if (a.tg) { gi = a.gt[((long long)0 * a.B + b) * a.T + t]; gf = a.gt[((long long)1 * a.B + b) * a.T + t]; }
@@ -702,7 +839,7 @@ __global__ void __launch_bounds__(PT, 1) persist_bwd_k(const Args a) {
       const int f = e / NQ, n0 = (e - f * NQ) * NB;
       float av[NB], rv[NB];
       contract<NB>(w.A, zx, f, n0, KCa, N, av);
-      contract<NB>(w.Bw, zh, f, n0, KCb, N, rv);
+      contract_z<NB, QZ>(w.Bw, zh, f, n0, KCb, N, rv);
       const float bb = w.bias[f];
 #pragma unroll
       for (int j = 0; j < NB; ++j) {
@@ -739,13 +876,13 @@ __global__ void __launch_bounds__(PT, 1) persist_bwd_k(const Args a) {
     if (a.tg) { dgi = block_sum(sgi, red); dgf = block_sum(sgf, red); }
     __syncthreads();
     wgrad_acc<NB>(gacc.A, da, zx, F, KCa, N);
-    wgrad_acc<NB>(gacc.Bw, dr, zh, F, KCb, N);
+    wgrad_z<NB, QZ>(gacc.Bw, dr, zh, F, KCb, N);
     for (int f = threadIdx.x; f < F; f += PT) {
       float s = 0.f;
       for (int n = 0; n < N; ++n) s += da[(size_t)f * N + n] + dr[(size_t)f * N + n];
       gacc.bias[f] += s;
     }
-    adjoint_chain<NB>(a, bw, w.Bw, dr, b1, b2, dh, a.Kst, F, false);      // dh_{t-1} (recurrent part)
+    adjoint_z<NB, QZ>(a, bw, w.Bw, dr, b1, b2, dh, a.Kst, F, false);      // dh_{t-1} (recurrent part)
     if (a.tg) {
 #pragma unroll
       for (int g = 0; g < 2; ++g) {
@@ -821,8 +958,8 @@ __global__ void __launch_bounds__(PT, 1) persist_bwd_k(const Args a) {
   // ---- T-invariant gate terms: after t = 0 the zh buffers hold h0's chain ---------------------------------------------------
 #pragma unroll
   for (int g = 0; g < 2; ++g) {
-    if (a.tg) subcell_c0_bwd<NB>(a, bw, w.ts[g], gacc.ts[g], dc0 + (size_t)g * FN, zh, b1, b2, dh);
-    if (NODE) subcell_c0_bwd<NB>(a, bw, w.ns[g], gacc.ns[g], dc0n + (size_t)g * FN, zh, b1, b2, dh);
+    if (a.tg) subcell_c0_bwd<NB, QZ>(a, bw, w.ts[g], gacc.ts[g], dc0 + (size_t)g * FN, zh, b1, b2, dh);
+    if (NODE) subcell_c0_bwd<NB, QZ>(a, bw, w.ns[g], gacc.ns[g], dc0n + (size_t)g * FN, zh, b1, b2, dh);
   }
   if (a.dh0) for (int e = threadIdx.x; e < FN; e += PT) a.dh0[b * FN + e] = dh[e];
   // ---- one atomicAdd per parameter and CTA ---------------------------------------------------------------------------------
