@@ -368,11 +368,17 @@ __global__ void zs_build_kernel(const float* __restrict__ X, const float* __rest
     const int j = lo ? jr - 8 : jr;
     const float vgi = gi ? gi[bt] : 1.f, vgf = gf ? gf[bt] : 1.f;
     float ratio[8];
+    if (qi) {
+      const float4* a4 = reinterpret_cast<const float4*>(qi + (size_t)bt * N + c * 8);
+      const float4* b4 = reinterpret_cast<const float4*>(qf + (size_t)bt * N + c * 8);
+      const float4 a0 = __ldg(a4), a1 = __ldg(a4 + 1), b0 = __ldg(b4), b1 = __ldg(b4 + 1);
+      const float qa[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w}, qb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      float num = vgi, den = vgf;
-      if (qi) { const size_t qo = (size_t)bt * N + c * 8 + e; num *= __ldg(qi + qo); den *= __ldg(qf + qo); }
-      ratio[e] = num / fmaxf(den, 1e-30f);
+      for (int e = 0; e < 8; ++e) ratio[e] = (vgi * qa[e]) / fmaxf(vgf * qb[e], 1e-30f);
+    } else {
+      const float r = vgi / fmaxf(vgf, 1e-30f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) ratio[e] = r;
     }
     float o[8];
     if (j < KG) {
